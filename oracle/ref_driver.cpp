@@ -1,0 +1,534 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Drives the UNMODIFIED reference implementation (lizabelos/libCML,
+// src/cml/optimization/dso/DSOBundleAdjustment.cpp, compiled in place from /root/reference by
+// oracle/Makefile) on a synthetic window read from a CMLW file, and dumps golden vectors.
+// Nothing here is linked into, imported by, or executed from the product (libcml_b200/, include/);
+// only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs run it.
+//
+//   cmlba_ref --window in.cmlw --mode stages|run|bench --out out.cmlw [--repeat K]
+//
+// mode stages : replays DSOBundleAdjustment::run (BA:744-910) call by call through the class's own
+//               (protected) methods and dumps every intermediate quantity SURVEY.md section 8(d) lists.
+// mode run    : calls the public run() only and dumps the final state (checks that "stages" == run()).
+// mode bench  : times linearizeAll / addToHessianTop+stitchDoubleTop / addToHessianSC+stitchDoubleSC
+//               and whole run() with std::chrono, prints one JSON line (single thread = reference behaviour).
+#include <cml/config.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <unistd.h>
+#include <sstream>
+#include <iostream>
+#include <fstream>
+#include <map>
+#include <set>
+#include <list>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <atomic>
+#include <functional>
+#include <algorithm>
+#include <random>
+#include <optional>
+#include <variant>
+#include <any>
+#include <queue>
+#include <deque>
+#include <condition_variable>
+#include <future>
+#include <regex>
+#include <iomanip>
+#include <Eigen/Dense>
+#include <sophus/se3.hpp>
+
+#define private public
+#define protected public
+#include <cml/base/AbstractFunction.h>
+#include <cml/map/Map.h>
+#include <cml/capture/CaptureImage.h>
+#include <cml/optimization/dso/DSOBundleAdjustment.h>
+#undef private
+#undef protected
+
+#include "cmlw_io.h"
+
+// ---- the two link stubs named in SURVEY.md section 8(c) step 3 -------------------------------
+namespace CML {
+Atomic<size_t> __array2DCounter = 0;
+namespace Evaluation {
+double align(const List<Camera> &, const List<Optional<Camera>> &, List<Camera> &) { return 0; }
+}  // namespace Evaluation
+}  // namespace CML
+
+using namespace CML;
+using namespace CML::Optimization;
+
+struct Root : public AbstractFunction {
+    Root() : AbstractFunction(nullptr) {}
+    Map map;
+    Map &getMap() override { return map; }
+    std::string getName() override { return "root"; }
+};
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct RefWindow {
+    int W, H, N, P;
+    Root *root;
+    InternalCalibration *calib;
+    CaptureImageGenerator *gen;
+    DSOBundleAdjustment *ba;
+    std::vector<PFrame> frames;
+    std::vector<PPoint> points;
+    std::unordered_map<MapPoint *, int> pointIndex;
+    std::unordered_map<Frame *, int> frameIndex;
+    int iterations;
+    bool updatePointsOnly;
+};
+
+static Camera cameraFromRt(const double *p) {
+    Matrix33 R;
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R(r, c) = p[r * 3 + c];
+    Vector3 t(p[9], p[10], p[11]);
+    return Camera(t, R);
+}
+
+static RefWindow *buildWindow(const cmlw::File &in) {
+    RefWindow *w = new RefWindow;
+    const int32_t *size = in.get("size").as<int32_t>();
+    w->W = size[0]; w->H = size[1];
+    const double *K = in.get("calib").as<double>();
+    w->N = (int) in.get("frame_evalpt").dims[0];
+    w->P = (int) in.get("pt_host").dims[0];
+    w->iterations = in.has("iterations") ? in.get("iterations").as<int32_t>()[0] : 4;
+    w->updatePointsOnly = in.has("update_points_only") ? in.get("update_points_only").as<int32_t>()[0] != 0 : false;
+
+    w->root = new Root;
+    w->calib = new InternalCalibration(PinholeUndistorter(Vector2(K[0], K[1]), Vector2(K[2], K[3])), Vector2(w->W, w->H));
+    w->gen = new CaptureImageGenerator(w->W, w->H, w->N + 2, w->N + 2);
+    w->ba = new DSOBundleAdjustment(w->root);
+    w->ba->setNumFrames(w->N + 2);
+    w->ba->setNumIterations(w->iterations);
+    if (in.has("optimize_a")) w->ba->mOptimizeA.set(in.get("optimize_a").as<int32_t>()[0] != 0);
+    if (in.has("optimize_b")) w->ba->mOptimizeB.set(in.get("optimize_b").as<int32_t>()[0] != 0);
+    if (in.has("force_accept")) w->ba->mForceAccept.set(in.get("force_accept").as<int32_t>()[0] != 0);
+    if (in.has("fixed_lambda")) w->ba->mFixedLambda.set((float) in.get("fixed_lambda").as<double>()[0]);
+
+    Map &map = w->root->getMap();
+    int immature = map.createMapPointGroup("immature");
+
+    const double *evalpt = in.get("frame_evalpt").as<double>();
+    const double *cam = in.get("frame_cam").as<double>();
+    const double *aff = in.get("frame_affine").as<double>();
+    const double *expo = in.get("frame_exposure").as<double>();
+    const float *gray = in.get("gray").as<float>();
+    const uint8_t *isInit = in.has("frame_init") ? in.get("frame_init").as<uint8_t>() : nullptr;
+
+    for (int i = 0; i < w->N; i++) {
+        FloatImage img(w->W, w->H);
+        memcpy(img.data(), gray + (size_t) i * w->W * w->H, sizeof(float) * w->W * w->H);
+        auto cap = w->gen->create().setImage(img).setTime(i).setCalibration(w->calib).setExposure(expo[i]).generate();
+        PFrame f = map.createFrame(cap);
+        f->setCamera(cameraFromRt(evalpt + 12 * i));
+        f->setExposureParameters(Exposure(expo[i], aff[2 * i], aff[2 * i + 1]));
+        if (isInit && isInit[i]) f->setGroup(map.INITFRAME, true);
+        map.addFrame(f);
+        w->frames.push_back(f);
+        w->frameIndex[f.p()] = i;
+    }
+    for (int i = 0; i < w->N; i++) w->ba->addNewFrame(w->frames[i], immature);
+    // the "current estimate" at run() time (run() starts with updateCamera -> setStateFromCamera, BA:753-755)
+    for (int i = 0; i < w->N; i++) w->frames[i]->setCamera(cameraFromRt(cam + 12 * i));
+
+    const int32_t *host = in.get("pt_host").as<int32_t>();
+    const float *xy = in.get("pt_xy").as<float>();
+    const double *idepth = in.get("pt_idepth").as<double>();
+    std::vector<std::vector<int>> perHost(w->N);
+    for (int p = 0; p < w->P; p++) perHost[host[p]].push_back(p);
+    w->points.resize(w->P, PPoint());
+    PointSet set;
+    for (int h = 0; h < w->N; h++) {
+        if (perHost[h].empty()) continue;
+        List<Corner> corners;
+        for (int p : perHost[h]) corners.emplace_back(Corner(DistortedVector2d(xy[2 * p], xy[2 * p + 1])));
+        int gid = w->frames[h]->addFeaturePoints(corners);
+        for (size_t k = 0; k < perHost[h].size(); k++) {
+            int p = perHost[h][k];
+            PPoint mp = map.createMapPoint(w->frames[h], FeatureIndex(gid, (short) k), DIRECTTYPE);
+            mp->setReferenceInverseDepth(idepth[p]);
+            w->points[p] = mp;
+            w->pointIndex[mp.p()] = p;
+            set.insert(mp);
+        }
+    }
+    w->ba->addPoints(set);
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename M> static void putMat(cmlw::File &out, const std::string &name, const M &m) {
+    std::vector<double> v((size_t) m.rows() * m.cols());
+    for (int r = 0; r < m.rows(); r++) for (int c = 0; c < m.cols(); c++) v[(size_t) r * m.cols() + c] = (double) m(r, c);
+    out.put<double>(name, v, {(uint64_t) m.rows(), (uint64_t) m.cols()});
+}
+
+static void dumpFrames(RefWindow *w, cmlw::File &out, const std::string &pre) {
+    int N = w->N;
+    std::vector<double> state(N * 10), zero(N * 10), scaled(N * 10), evalpt(N * 12), pre_w2c(N * 12), prior(N * 8), delta(N * 8), dprior(N * 8), th(N), step(N * 10);
+    std::vector<double> nsp(N * 36), nss(N * 6), nsa(N * 8), camRt(N * 12), aff(N * 2);
+    for (int i = 0; i < N; i++) {
+        auto d = w->ba->get(w->frames[i]);
+        for (int k = 0; k < 10; k++) { state[i * 10 + k] = d->state[k]; zero[i * 10 + k] = d->state_zero[k]; scaled[i * 10 + k] = d->state_scaled[k]; step[i * 10 + k] = d->step[k]; }
+        Matrix33 R0 = d->worldToCam_evalPT.rotationMatrix(); Vector3 t0 = d->worldToCam_evalPT.translation();
+        Matrix33 R1 = d->PRE_worldToCam.rotationMatrix(); Vector3 t1 = d->PRE_worldToCam.translation();
+        Matrix33 Rc = w->frames[i]->getCamera().getRotationMatrix(); Vector3 tc = w->frames[i]->getCamera().getTranslation();
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { evalpt[i * 12 + r * 3 + c] = R0(r, c); pre_w2c[i * 12 + r * 3 + c] = R1(r, c); camRt[i * 12 + r * 3 + c] = Rc(r, c); }
+        for (int r = 0; r < 3; r++) { evalpt[i * 12 + 9 + r] = t0[r]; pre_w2c[i * 12 + 9 + r] = t1[r]; camRt[i * 12 + 9 + r] = tc[r]; }
+        for (int k = 0; k < 8; k++) { prior[i * 8 + k] = d->prior[k]; delta[i * 8 + k] = d->delta[k]; dprior[i * 8 + k] = d->delta_prior[k]; }
+        th[i] = d->frameEnergyTH;
+        for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) nsp[i * 36 + r * 6 + c] = d->nullspaces_pose(r, c);
+        for (int r = 0; r < 6; r++) nss[i * 6 + r] = d->nullspaces_scale[r];
+        for (int r = 0; r < 4; r++) for (int c = 0; c < 2; c++) nsa[i * 8 + r * 2 + c] = d->nullspaces_affine(r, c);
+        aff[i * 2 + 0] = w->frames[i]->getExposure().getParameters()(0);
+        aff[i * 2 + 1] = w->frames[i]->getExposure().getParameters()(1);
+    }
+    out.put<double>(pre + "frame_state", state, {(uint64_t) N, 10});
+    out.put<double>(pre + "frame_state_zero", zero, {(uint64_t) N, 10});
+    out.put<double>(pre + "frame_state_scaled", scaled, {(uint64_t) N, 10});
+    out.put<double>(pre + "frame_step", step, {(uint64_t) N, 10});
+    out.put<double>(pre + "frame_evalpt", evalpt, {(uint64_t) N, 12});
+    out.put<double>(pre + "frame_pre_w2c", pre_w2c, {(uint64_t) N, 12});
+    out.put<double>(pre + "frame_cam", camRt, {(uint64_t) N, 12});
+    out.put<double>(pre + "frame_affine", aff, {(uint64_t) N, 2});
+    out.put<double>(pre + "frame_prior", prior, {(uint64_t) N, 8});
+    out.put<double>(pre + "frame_delta", delta, {(uint64_t) N, 8});
+    out.put<double>(pre + "frame_delta_prior", dprior, {(uint64_t) N, 8});
+    out.put<double>(pre + "frame_energy_th", th, {(uint64_t) N});
+    out.put<double>(pre + "frame_ns_pose", nsp, {(uint64_t) N, 6, 6});
+    out.put<double>(pre + "frame_ns_scale", nss, {(uint64_t) N, 6});
+    out.put<double>(pre + "frame_ns_affine", nsa, {(uint64_t) N, 4, 2});
+}
+
+static void dumpAdjoints(RefWindow *w, cmlw::File &out, const std::string &pre) {
+    int N = w->N;
+    std::vector<double> ah(N * N * 64), at(N * N * 64), dd(N * N * 8);
+    for (int i = 0; i < N * N; i++) {
+        for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) { ah[i * 64 + r * 8 + c] = w->ba->mAdHost[i](r, c); at[i * 64 + r * 8 + c] = w->ba->mAdTarget[i](r, c); }
+        for (int c = 0; c < 8; c++) dd[i * 8 + c] = w->ba->mAdHTdeltaF[i](0, c);
+    }
+    out.put<double>(pre + "ad_host", ah, {(uint64_t) N * N, 8, 8});
+    out.put<double>(pre + "ad_target", at, {(uint64_t) N * N, 8, 8});
+    out.put<double>(pre + "ad_ht_delta", dd, {(uint64_t) N * N, 8});
+}
+
+// per-residual dump in mActiveResiduals order; `full` adds the raw Jacobian rJ (what linearize just wrote)
+static void dumpResiduals(RefWindow *w, cmlw::File &out, const std::string &pre, bool full, bool useEfs) {
+    auto &res = w->ba->mActiveResiduals;
+    size_t R = res.size();
+    std::vector<int32_t> pt(R), tgt(R), host(R), state(R), nstate(R), good(R), lin(R);
+    std::vector<double> e(R), ne(R), neo(R), cpt(R * 3);
+    std::vector<float> jpjd(R * 8), resF, Jpdxi, Jpdc, Jpdd, JIdx, JabF, JIdx2, JabJIdx, Jab2;
+    if (full) { resF.resize(R * 8); Jpdxi.resize(R * 12); Jpdc.resize(R * 8); Jpdd.resize(R * 2); JIdx.resize(R * 16); JabF.resize(R * 16); JIdx2.resize(R * 4); JabJIdx.resize(R * 4); Jab2.resize(R * 4); }
+    for (size_t i = 0; i < R; i++) {
+        DSOResidual *r = res[i];
+        pt[i] = w->pointIndex.at(r->elements.mapPoint.p());
+        tgt[i] = w->frameIndex.at(r->elements.frame.p());
+        host[i] = w->frameIndex.at(r->elements.mapPoint->getReferenceFrame().p());
+        state[i] = (int) r->getState(); nstate[i] = (int) r->getNewState();
+        good[i] = r->isActiveAndIsGoodNEW; lin[i] = r->isLinearized;
+        e[i] = r->state_energy; ne[i] = r->state_NewEnergy; neo[i] = r->state_NewEnergyWithOutlier;
+        for (int k = 0; k < 3; k++) cpt[i * 3 + k] = r->getCenterProjectedTo()[k];
+        for (int k = 0; k < 8; k++) jpjd[i * 8 + k] = r->JpJdF[k];
+        if (full) {
+            const DSORawResidualJacobian &J = useEfs ? r->efsJ : r->rJ;
+            for (int k = 0; k < 8; k++) resF[i * 8 + k] = J.resF[k];
+            for (int a = 0; a < 2; a++) {
+                for (int k = 0; k < 6; k++) Jpdxi[i * 12 + a * 6 + k] = J.Jpdxi[a][k];
+                for (int k = 0; k < 4; k++) Jpdc[i * 8 + a * 4 + k] = J.Jpdc[a][k];
+                Jpdd[i * 2 + a] = J.Jpdd[a];
+                for (int k = 0; k < 8; k++) { JIdx[i * 16 + a * 8 + k] = J.JIdx[a][k]; JabF[i * 16 + a * 8 + k] = J.JabF[a][k]; }
+                for (int b = 0; b < 2; b++) { JIdx2[i * 4 + a * 2 + b] = J.JIdx2(a, b); JabJIdx[i * 4 + a * 2 + b] = J.JabJIdx(a, b); Jab2[i * 4 + a * 2 + b] = J.Jab2(a, b); }
+            }
+        }
+    }
+    out.put1<int32_t>(pre + "res_point", pt); out.put1<int32_t>(pre + "res_target", tgt); out.put1<int32_t>(pre + "res_host", host);
+    out.put1<int32_t>(pre + "res_state", state); out.put1<int32_t>(pre + "res_new_state", nstate);
+    out.put1<int32_t>(pre + "res_good", good); out.put1<int32_t>(pre + "res_linearized", lin);
+    out.put1<double>(pre + "res_energy", e); out.put1<double>(pre + "res_new_energy", ne); out.put1<double>(pre + "res_new_energy_wo", neo);
+    out.put<double>(pre + "res_center", cpt, {(uint64_t) R, 3});
+    out.put<float>(pre + "res_JpJdF", jpjd, {(uint64_t) R, 8});
+    if (full) {
+        out.put<float>(pre + "rJ_resF", resF, {(uint64_t) R, 8});
+        out.put<float>(pre + "rJ_Jpdxi", Jpdxi, {(uint64_t) R, 2, 6});
+        out.put<float>(pre + "rJ_Jpdc", Jpdc, {(uint64_t) R, 2, 4});
+        out.put<float>(pre + "rJ_Jpdd", Jpdd, {(uint64_t) R, 2});
+        out.put<float>(pre + "rJ_JIdx", JIdx, {(uint64_t) R, 2, 8});
+        out.put<float>(pre + "rJ_JabF", JabF, {(uint64_t) R, 2, 8});
+        out.put<float>(pre + "rJ_JIdx2", JIdx2, {(uint64_t) R, 2, 2});
+        out.put<float>(pre + "rJ_JabJIdx", JabJIdx, {(uint64_t) R, 2, 2});
+        out.put<float>(pre + "rJ_Jab2", Jab2, {(uint64_t) R, 2, 2});
+    }
+}
+
+static void dumpPoints(RefWindow *w, cmlw::File &out, const std::string &pre) {
+    int P = w->P;
+    std::vector<double> idepth(P), step(P), unc(P), colors(P * 8), weights(P * 8);
+    std::vector<float> hdd(P), bd(P), hcd(P * 4), hdi(P), bdsum(P), deltaF(P), priorF(P), idz(P), idh(P), mrb(P);
+    std::vector<int32_t> alive(P), ngood(P), nres(P), last0(P), last1(P), outlier(P);
+    for (int p = 0; p < P; p++) {
+        PPoint mp = w->points[p];
+        alive[p] = w->ba->have(mp) && w->ba->getPoints().count(mp) > 0;
+        idepth[p] = mp->getReferenceInverseDepth();
+        unc[p] = mp->getUncertainty();
+        outlier[p] = w->ba->mOutliers.count(mp) > 0;
+        if (!w->ba->have(mp)) continue;
+        auto d = w->ba->get(mp);
+        step[p] = d->step;
+        hdd[p] = d->Hdd_accAF; bd[p] = d->bd_accAF; for (int k = 0; k < 4; k++) hcd[p * 4 + k] = d->Hcd_accAF[k];
+        hdi[p] = d->HdiF; bdsum[p] = d->bdSumF; deltaF[p] = d->deltaF; priorF[p] = d->priorF; idz[p] = d->idepth_zero;
+        idh[p] = d->getInverseDepthHessian(); mrb[p] = d->getMaxRelBaseline();
+        ngood[p] = d->numGoodResiduals; nres[p] = (int) d->getResiduals().size();
+        last0[p] = d->getLastResidual(0).first ? (int) d->getLastResidual(0).second : -1;
+        last1[p] = d->getLastResidual(1).first ? (int) d->getLastResidual(1).second : -1;
+        for (int k = 0; k < 8; k++) { colors[p * 8 + k] = d->colors[k]; weights[p * 8 + k] = d->weights.size() == 8 ? d->weights[k] : 0; }
+    }
+    out.put1<double>(pre + "pt_idepth", idepth); out.put1<double>(pre + "pt_step", step); out.put1<double>(pre + "pt_uncertainty", unc);
+    out.put1<float>(pre + "pt_Hdd", hdd); out.put1<float>(pre + "pt_bd", bd); out.put<float>(pre + "pt_Hcd", hcd, {(uint64_t) P, 4});
+    out.put1<float>(pre + "pt_HdiF", hdi); out.put1<float>(pre + "pt_bdSumF", bdsum); out.put1<float>(pre + "pt_deltaF", deltaF);
+    out.put1<float>(pre + "pt_priorF", priorF); out.put1<float>(pre + "pt_idepth_zero", idz); out.put1<float>(pre + "pt_idepth_hessian", idh);
+    out.put1<float>(pre + "pt_max_rel_baseline", mrb);
+    out.put1<int32_t>(pre + "pt_alive", alive); out.put1<int32_t>(pre + "pt_num_good", ngood); out.put1<int32_t>(pre + "pt_num_res", nres);
+    out.put1<int32_t>(pre + "pt_last0", last0); out.put1<int32_t>(pre + "pt_last1", last1); out.put1<int32_t>(pre + "pt_outlier", outlier);
+    out.put<double>(pre + "pt_colors", colors, {(uint64_t) P, 8}); out.put<double>(pre + "pt_weights", weights, {(uint64_t) P, 8});
+}
+
+static void dumpSystem(RefWindow *w, cmlw::File &out, const std::string &pre) {
+    int N = w->N;
+    auto *ba = w->ba;
+    std::vector<float> acc((size_t) N * N * 169); std::vector<int32_t> accNum(N * N);
+    for (int i = 0; i < N * N; i++) {
+        accNum[i] = (int) ba->mAccumulatorActive[i].num;
+        for (int r = 0; r < 13; r++) for (int c = 0; c < 13; c++) acc[(size_t) i * 169 + r * 13 + c] = ba->mAccumulatorActive[i].H(r, c);
+    }
+    out.put<float>(pre + "acc_active", acc, {(uint64_t) N * N, 13, 13});
+    out.put1<int32_t>(pre + "acc_active_num", accNum);
+    std::vector<float> accE((size_t) N * N * 32), accEB((size_t) N * N * 8), accD((size_t) N * N * N * 64);
+    for (int i = 0; i < N * N; i++) {
+        for (int r = 0; r < 8; r++) { for (int c = 0; c < 4; c++) accE[(size_t) i * 32 + r * 4 + c] = ba->mAccE[i].A1m(r, c); accEB[(size_t) i * 8 + r] = ba->mAccEB[i].A1m[r]; }
+    }
+    for (int i = 0; i < N * N * N; i++) for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) accD[(size_t) i * 64 + r * 8 + c] = ba->mAccD[i].A1m(r, c);
+    out.put<float>(pre + "acc_E", accE, {(uint64_t) N * N, 8, 4});
+    out.put<float>(pre + "acc_EB", accEB, {(uint64_t) N * N, 8});
+    out.put<float>(pre + "acc_D", accD, {(uint64_t) N * N * N, 8, 8});
+    putMat(out, pre + "HA_top", ba->HA_top); putMat(out, pre + "HL_top", ba->HL_top); putMat(out, pre + "H_sc", ba->H_sc);
+    putMat(out, pre + "bA_top", ba->bA_top); putMat(out, pre + "bL_top", ba->bL_top); putMat(out, pre + "b_sc", ba->b_sc); putMat(out, pre + "bM_top", ba->bM_top);
+    // x = -(step) for every frame (BA:1439); calibration step is identically 0 when !optimizeCalibration
+    std::vector<double> x(8 * N + 4, 0.0);
+    for (int k = 0; k < 4; k++) x[k] = -ba->mCalibStep[k];
+    for (int i = 0; i < N; i++) { auto d = ba->get(w->frames[i]); for (int k = 0; k < 8; k++) x[4 + 8 * i + k] = -d->step[k]; }
+    out.put1<double>(pre + "x", x);
+}
+
+// rebuild mActiveResiduals exactly as run() does (BA:764-779)
+static void collectActive(RefWindow *w) {
+    auto *ba = w->ba;
+    ba->mActiveResiduals.clear();
+    for (auto r : ba->getResiduals()) {
+        if (!r->isLinearized) { ba->mActiveResiduals.push_back(r); r->resetOOB(); }
+        else if (ba->mAddLinearizedPoints.b()) { ba->mActiveResiduals.push_back(r); r->resetOOB(); r->isLinearized = false; }
+    }
+}
+
+static void dumpFinal(RefWindow *w, cmlw::File &out, const std::string &pre, bool ok) {
+    out.scalar<int32_t>(pre + "ok", ok ? 1 : 0);
+    dumpFrames(w, out, pre);
+    dumpPoints(w, out, pre);
+    // surviving residuals (point,target) with their committed state
+    std::vector<int32_t> pt, tgt, state;
+    std::vector<double> e;
+    for (auto r : w->ba->getResiduals()) {
+        pt.push_back(w->pointIndex.at(r->elements.mapPoint.p())); tgt.push_back(w->frameIndex.at(r->elements.frame.p()));
+        state.push_back((int) r->getState()); e.push_back(r->state_energy);
+    }
+    out.put1<int32_t>(pre + "alive_res_point", pt); out.put1<int32_t>(pre + "alive_res_target", tgt);
+    out.put1<int32_t>(pre + "alive_res_state", state); out.put1<double>(pre + "alive_res_energy", e);
+    std::vector<int32_t> goodTrack;
+    for (auto p : w->ba->getGoodPointsForTracking()) goodTrack.push_back(w->pointIndex.at(p.p()));
+    std::sort(goodTrack.begin(), goodTrack.end());
+    out.put1<int32_t>(pre + "good_points_for_tracking", goodTrack);
+}
+
+static int runStages(RefWindow *w, cmlw::File &out) {
+    auto *ba = w->ba;
+    // level-0 derivative image and gray of frame 0 as the reference built them (capture/CaptureImage.cpp:209-262)
+    {
+        std::vector<float> g((size_t) w->N * w->W * w->H * 3);
+        for (int i = 0; i < w->N; i++) {
+            const GradientImage &im = w->frames[i]->getCaptureFrame().getDerivativeImage(0);
+            for (int y = 0; y < w->H; y++) for (int x = 0; x < w->W; x++) {
+                Vector3f v = im.get(x, y);
+                size_t o = (((size_t) i * w->H + y) * w->W + x) * 3;
+                g[o] = v[0]; g[o + 1] = v[1]; g[o + 2] = v[2];
+            }
+        }
+        out.put<float>("grad_images", g, {(uint64_t) w->N, (uint64_t) w->H, (uint64_t) w->W, 3});
+    }
+    // --- run() prologue (BA:753-790)
+    for (auto f : ba->getFrames()) ba->updateCamera(f);
+    ba->mOutliers = PointSet();
+    collectActive(w);
+    ba->computeAdjoints();
+    ba->computeDelta();
+    dumpFrames(w, out, "pre_");
+    dumpAdjoints(w, out, "pre_");
+    dumpPoints(w, out, "pre_");
+
+    Vector3 lastEnergy = ba->linearizeAll(false);
+    double lastEnergyL = ba->calcLEnergy(), lastEnergyM = ba->calcMEnergy();
+    out.scalar<double>("lin0_energy", lastEnergy[0]);
+    dumpResiduals(w, out, "lin0_", true, false);
+    { std::vector<double> th(w->N); for (int i = 0; i < w->N; i++) th[i] = ba->get(w->frames[i])->frameEnergyTH; out.put1<double>("lin0_frame_energy_th", th); }
+    ba->applyActiveRes(true);
+    dumpResiduals(w, out, "app0_", false, false);
+
+    int numIterations = ba->mNumIterations.i();
+    double lambda = ba->mFixedLambda.f();
+    int itDone = 0;
+    std::vector<int32_t> accepted;
+    for (int it = 0; it < numIterations; it++) {
+        std::string s = std::to_string(it);
+        ba->backupState();
+        if (!ba->solveSystem(it, lambda)) { out.scalar<int32_t>("failed_at", it); return 1; }
+        dumpSystem(w, out, "sol" + s + "_");
+        dumpPoints(w, out, "sol" + s + "_");
+        { // nullspace matrix as orthogonalize() would stack it (BA:1204-1220), for K3 parity
+            int n = 8 * w->N + 4; std::vector<double> ns((size_t) 7 * n);
+            for (int k = 0; k < 6; k++) for (int r = 0; r < n; r++) ns[(size_t) k * n + r] = ba->mLastNullspaces_pose[k][r];
+            for (int r = 0; r < n; r++) ns[(size_t) 6 * n + r] = ba->mLastNullspaces_scale[0][r];
+            out.put<double>("sol" + s + "_nullspaces", ns, {7, (uint64_t) n});
+        }
+        bool canbreak = ba->doStepFromBackup(w->updatePointsOnly);
+        out.scalar<int32_t>("step" + s + "_canbreak", canbreak ? 1 : 0);
+        dumpFrames(w, out, "step" + s + "_");
+        { std::vector<double> id(w->P); for (int p = 0; p < w->P; p++) id[p] = w->points[p]->getReferenceInverseDepth(); out.put1<double>("step" + s + "_pt_idepth", id); }
+
+        Vector3 newEnergy = ba->linearizeAll(false);
+        double newEnergyL = ba->calcLEnergy(), newEnergyM = ba->calcMEnergy();
+        out.scalar<double>("lin" + std::to_string(it + 1) + "_energy", newEnergy[0]);
+        dumpResiduals(w, out, "lin" + std::to_string(it + 1) + "_", it + 1 == numIterations || it == 0, false);
+        { std::vector<double> th(w->N); for (int i = 0; i < w->N; i++) th[i] = ba->get(w->frames[i])->frameEnergyTH; out.put1<double>("lin" + std::to_string(it + 1) + "_frame_energy_th", th); }
+        double newTotal = newEnergy[0] + newEnergy[1] + newEnergyL + newEnergyM;
+        double lastTotal = lastEnergy[0] + lastEnergy[1] + lastEnergyL + lastEnergyM;
+        if (!std::isfinite(newTotal)) { out.scalar<int32_t>("failed_at", it); return 1; }
+        if (newTotal < lastTotal || ba->mForceAccept.b()) {
+            ba->applyActiveRes(true);
+            lastEnergy = newEnergy; lastEnergyL = newEnergyL; lastEnergyM = newEnergyM;
+            lambda *= 0.25; accepted.push_back(1);
+        } else {
+            ba->loadSateBackup();
+            lastEnergy = ba->linearizeAll(false); lastEnergyL = ba->calcLEnergy(); lastEnergyM = ba->calcMEnergy();
+            lambda *= 1e2; accepted.push_back(0);
+        }
+        itDone = it + 1;
+        if (canbreak && it >= 1) break;
+    }
+    out.scalar<int32_t>("iterations_done", itDone);
+    out.put1<int32_t>("accepted", accepted);
+    // --- run() epilogue (BA:885-896)
+    auto back = ba->get(ba->getFrames().back());
+    Vector<10> nz = Vector<10>::Zero();
+    nz.segment<2>(6) = back->get_state().segment<2>(6);
+    back->setEvalPT(back->PRE_worldToCam, nz, ba->mScaleTranslation.f(), ba->mScaleRotation.f(), ba->mScaleLightA.f(), ba->mScaleLightB.f());
+    ba->mDeltaValid = false; ba->mAdjointsValid = false;
+    ba->computeAdjoints(); ba->computeDelta();
+    // per-residual view of the final linearization BEFORE residuals get deleted inside linearizeAll(true):
+    // not reachable from outside, so keep (point,target) of the active list and report survivors afterwards.
+    std::vector<int32_t> apt, atg;
+    for (auto r : ba->mActiveResiduals) { apt.push_back(w->pointIndex.at(r->elements.mapPoint.p())); atg.push_back(w->frameIndex.at(r->elements.frame.p())); }
+    out.put1<int32_t>("fin_active_point", apt); out.put1<int32_t>("fin_active_target", atg);
+    lastEnergy = ba->linearizeAll(true);
+    ba->mActiveResiduals.clear();  // dangling after linearizeAll(true) (SURVEY 8c gotcha)
+    out.scalar<double>("fin_energy", lastEnergy[0]);
+    bool ok = std::isfinite((double) lastEnergy[0]);
+    dumpFinal(w, out, "fin_", ok);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    std::string window, mode = "stages", outPath;
+    int repeat = 3;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "--window" && i + 1 < argc) window = argv[++i];
+        else if (a == "--mode" && i + 1 < argc) mode = argv[++i];
+        else if (a == "--out" && i + 1 < argc) outPath = argv[++i];
+        else if (a == "--repeat" && i + 1 < argc) repeat = atoi(argv[++i]);
+    }
+    if (window.empty()) { fprintf(stderr, "usage: cmlba_ref --window in.cmlw --mode stages|run|bench [--out out.cmlw] [--repeat K]\n"); return 2; }
+    initCML();
+    cmlw::File in;
+    if (!in.load(window)) { fprintf(stderr, "cannot read %s\n", window.c_str()); return 2; }
+
+    int rc = 0;
+    if (mode == "stages") {
+        RefWindow *w = buildWindow(in);
+        cmlw::File out;
+        rc = runStages(w, out);
+        if (!outPath.empty()) out.save(outPath);
+    } else if (mode == "run") {
+        RefWindow *w = buildWindow(in);
+        cmlw::File out;
+        double t0 = now_s();
+        bool ok = w->ba->run(w->updatePointsOnly);
+        double t1 = now_s();
+        w->ba->mActiveResiduals.clear();
+        out.scalar<double>("run_seconds", t1 - t0);
+        dumpFinal(w, out, "fin_", ok);
+        if (!outPath.empty()) out.save(outPath);
+    } else if (mode == "bench") {
+        // min over `repeat` freshly built windows, 1 thread (the reference BA is single-threaded)
+        double tLin = 1e30, tTop = 1e30, tSC = 1e30, tRun = 1e30; size_t R = 0; int itDone = 0;
+        for (int rep = 0; rep < repeat; rep++) {
+            RefWindow *w = buildWindow(in);
+            auto *ba = w->ba;
+            for (auto f : ba->getFrames()) ba->updateCamera(f);
+            collectActive(w);
+            R = ba->mActiveResiduals.size();
+            ba->computeAdjoints(); ba->computeDelta();
+            double a = now_s(); ba->linearizeAll(false); double b = now_s();
+            tLin = std::min(tLin, b - a);
+            ba->applyActiveRes(true);
+            ba->setZero(); ba->computeNullspaces();
+            auto pts = ba->getPointsAsList();
+            a = now_s();
+            for (size_t i = 0; i < pts.size(); i++) ba->addToHessianTop(pts[i].first, pts[i].second, DSORES_ACTIVE);
+            ba->stitchDoubleTop(ba->mAccumulatorActive, ba->HA_top, ba->bA_top, false);
+            b = now_s(); tTop = std::min(tTop, b - a);
+            a = now_s();
+            for (size_t i = 0; i < pts.size(); i++) ba->addToHessianSC(pts[i].first, pts[i].second, true);
+            ba->stitchDoubleSC(ba->H_sc, ba->b_sc);
+            b = now_s(); tSC = std::min(tSC, b - a);
+            // whole run() on a second fresh window
+            RefWindow *w2 = buildWindow(in);
+            a = now_s(); w2->ba->run(w2->updatePointsOnly); b = now_s();
+            tRun = std::min(tRun, b - a);
+            itDone = w2->iterations;
+        }
+        printf("{\"residuals\": %zu, \"t_linearize\": %.6f, \"t_top\": %.6f, \"t_sc\": %.6f, \"t_run\": %.6f, \"iterations\": %d, \"threads\": 1, \"repeat\": %d}\n",
+               R, tLin, tTop, tSC, tRun, itDone, repeat);
+    } else {
+        fprintf(stderr, "unknown mode %s\n", mode.c_str());
+        rc = 2;
+    }
+    fflush(stdout);
+    _exit(rc);  // destructor order trips ~PrivateData's abort
+}
