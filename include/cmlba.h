@@ -1,0 +1,165 @@
+/* cmlba.h -- C ABI of libcmlba.so: B200-native photometric bundle adjustment (DSO-style sliding window).
+ *
+ * Drop-in boundary for ONE path of lizabelos/libCML: CML::Optimization::DSOBundleAdjustment
+ * (reference: src/cml/optimization/dso/DSOBundleAdjustment.{h,cpp}, "BA.h"/"BA" below).  The reference
+ * exposes a C++ class, not a C ABI; every entry point below cites the class
+ * member it replaces.  A handle mirrors one DSOBundleAdjustment instance: it owns the window
+ * bookkeeping (frames, points, residuals, FEJ evaluation points, energy thresholds) on the host and all
+ * device memory on one GPU.  The caller (CML's Frame/MapPoint graph via the adapter shown in
+ * INTEGRATION.md) stays authoritative: it pushes cameras in at run() and reads poses / affine /
+ * inverse depths / outliers back out.
+ *
+ * Conventions: poses are world->camera, R row-major 3x3 + t (double[12] = R(9) | t(3)), as
+ * CML::Camera (map/Camera.h:289-315).  All pointers are HOST pointers valid for the duration of the
+ * call only.  Every function returns 0 on success or a negative cmlba_status; cmlba_last_error()
+ * gives the message.  Nothing aborts.  A handle is single-threaded (BA is not re-entrant: SURVEY 8b).
+ * There is NO CPU fallback: without a CUDA device cmlba_create fails with CMLBA_ERR_CUDA.
+ */
+#ifndef CMLBA_H
+#define CMLBA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMLBA_MAX_FRAMES 16 /* window size limit (reference default maxFrames = 6, BA.h:271) */
+#define CMLBA_PATTERN 8     /* PredefinedPattern::star8, types.h:1395-1407 */
+
+typedef struct cmlba_handle cmlba_handle;
+
+typedef enum cmlba_status {
+    CMLBA_OK = 0,
+    CMLBA_ERR_ARG = -1,      /* bad argument (null pointer, unknown id, window too large ...) */
+    CMLBA_ERR_CUDA = -2,     /* CUDA runtime error / no device */
+    CMLBA_ERR_STATE = -3,    /* call order violated (e.g. run() before set_calib) */
+    CMLBA_ERR_NUMERIC = -4,  /* non-finite energy or step: the reference's run() returns false (BA:836-841, 898-905, 1489-1492) */
+    CMLBA_ERR_UNSUPPORTED = -5
+} cmlba_status;
+
+/* residual states, DSOResidual.h:14-16 */
+enum { CMLBA_RES_IN = 0, CMLBA_RES_OOB = 1, CMLBA_RES_OUTLIER = 2 };
+
+/* BA parameters (BA.h:235-288, same meaning and defaults; YAML key dsoBa.<name>) */
+typedef struct cmlba_config {
+    int iterations;             /* "iterations" 4 */
+    float huber_threshold;      /* "Huber threshold" 9 */
+    float outlier_th_sum;       /* "outlierTHSumComponent" 2500 */
+    float th_opt_iterations;    /* "ThOptIterations" 1.2 */
+    float scale_rotation;       /* "Rotation scale" 1 */
+    float scale_translation;    /* "translationScale" 0.5 */
+    float scale_light_a;        /* "Light A scale" 10 */
+    float scale_light_b;        /* "Light B scale" 1000 */
+    float scale_f;              /* "Scale F" 50 */
+    float scale_c;              /* "Scale C" 50 */
+    int force_accept;           /* "forceAccept" true */
+    int fix_lambda;             /* "fixLambda" true */
+    float fixed_lambda;         /* "fixedLambda" 1e-5 */
+    int idepth_fix_prior;       /* "iDepth Fix Prior" 2500 */
+    float solver_mode_delta;    /* "Solver mode delta" 1e-5 */
+    int optimize_light_a;       /* "optimizeLightA" true */
+    int optimize_light_b;       /* "optimizeLightB" true */
+    int disable_marginalization;/* "disableMarginalization" true */
+    int max_frames;             /* "maxFrames" 6 (only bounds checking here) */
+} cmlba_config;
+
+/* Fills *cfg with the reference defaults. */
+int cmlba_default_config(cmlba_config *cfg);
+
+/* new DSOBundleAdjustment(parent) (BA:322-334).  device = CUDA ordinal. */
+int cmlba_create(const cmlba_config *cfg, int device, cmlba_handle **out);
+int cmlba_destroy(cmlba_handle *h);
+const char *cmlba_last_error(const cmlba_handle *h);
+
+/* The level-0 pinhole + size cached by addNewFrame (BA:419-425: mPinhole, mWidth, mHeight). */
+int cmlba_set_calib(cmlba_handle *h, double fx, double fy, double cx, double cy, int width, int height);
+
+/* addNewFrame(PFrame, immatureGroup) (BA:417-462): appends a keyframe to the window.
+ *   frame_id      caller's id (Frame::getId()); must be larger than every id already in the window
+ *   world_to_cam  Frame::getCamera() at insertion -> becomes the FEJ evaluation point (DSOFrame::setEvalPT_scaled)
+ *   aff_a,aff_b   Frame::getExposure().getParameters();  exposure_time = CaptureImage::getExposureTime()
+ *   grad_aos      getCaptureFrame().getDerivativeImage(0): width*height texels of (I, dI/dx, dI/dy) fp32, row-major
+ *   is_init_frame Frame::isGroup(Map::INITFRAME) (-> hasDepthPrior of its points, BA:396)
+ * Creates residuals from every point already in the window to this frame (BA:455-460). */
+int cmlba_add_frame(cmlba_handle *h, int64_t frame_id, const double world_to_cam[12], double aff_a, double aff_b,
+                    double exposure_time, const float *grad_aos, int is_init_frame);
+
+/* addPoints(const PointSet&) (BA:382-415).  n points; host_frame_id[i] = getReferenceFrame()->getId(),
+ * xy = getReferenceCorner() (float x,y), idepth = getReferenceInverseDepth().  Reference colours
+ * (integer-pixel gray, MapObject.h:398-399) and gradient weights (BA:405-411) are computed on the
+ * device from the host frame's image.  One residual per (point, other frame) is created (BA:398-400). */
+int cmlba_add_points(cmlba_handle *h, int n, const int64_t *point_id, const int64_t *host_frame_id, const float *xy,
+                     const double *idepth);
+
+/* DSOContext::removePoint / frame removal without marginalisation prior (DSOContext.h:94-110, 152-172). */
+int cmlba_remove_point(cmlba_handle *h, int64_t point_id);
+int cmlba_remove_frame(cmlba_handle *h, int64_t frame_id);
+
+/* bool run(bool updatePointsOnly) (BA:744-910).  cams = the graph's current Frame::getCamera() for every
+ * window frame in window order (what updateCamera() reads, BA.h:54-60); NULL = keep current states.
+ * iterations <= 0 uses cfg.iterations.  Returns CMLBA_ERR_NUMERIC where the reference returns false. */
+typedef struct cmlba_run_result {
+    int iterations_done;
+    int num_residuals;          /* active residuals linearised per pass */
+    int num_dropped;            /* residuals deleted by the final linearizeAll(true) (BA:1623-1640) */
+    int num_outliers;           /* points left without residual -> getOutliers() */
+    double energy_first;        /* lastEnergy[0] before iteration 0 */
+    double energy_last;         /* energy of the final linearizeAll(true) */
+    double gpu_ms;              /* device time of the whole run (CUDA events) */
+    int kernel_launches;        /* kernels launched by this run */
+} cmlba_run_result;
+int cmlba_run(cmlba_handle *h, const double *cams /* [n_frames][12] or NULL */, int iterations, int update_points_only,
+              cmlba_run_result *result);
+
+/* ---- write-back side of the boundary (what run() stores into the graph, BA:934-940, 966-982) ---- */
+int cmlba_num_frames(const cmlba_handle *h);
+int cmlba_num_points(const cmlba_handle *h);
+int cmlba_num_residuals(const cmlba_handle *h);
+/* per frame, window order: Frame::setCamera(PRE_worldToCam), setExposureParameters(aff_g2l), + BA-internal state */
+int cmlba_get_frames(const cmlba_handle *h, int64_t *frame_id, double *world_to_cam /*[n][12]*/, double *aff_ab /*[n][2]*/,
+                     double *state /*[n][10]*/, double *evalpt /*[n][12]*/, double *energy_th /*[n]*/);
+/* per point, insertion order (dropped points removed): setReferenceInverseDepth, setUncertainty (DSOPoint.h:107-118) */
+int cmlba_get_points(const cmlba_handle *h, int64_t *point_id, double *idepth, double *uncertainty, float *idepth_hessian,
+                     float *max_rel_baseline, int32_t *num_good_residuals, int32_t *good_for_tracking);
+/* getOutliers() (BA.h:50): ids of points that lost all residuals in the last run(); returns count via *n (capacity in) */
+int cmlba_get_outliers(const cmlba_handle *h, int64_t *point_id, int *n);
+/* surviving residuals: (point_id, target frame_id, state, energy) */
+int cmlba_get_residuals(const cmlba_handle *h, int64_t *point_id, int64_t *target_frame_id, int32_t *state, double *energy);
+
+/* ---- stage entry points (protected members of the class; used by parity tests and profiling) ----
+ * cmlba_prepare      run() prologue BA:753-782: updateCamera, collect active residuals, computeAdjoints, computeDelta
+ * cmlba_linearize    linearizeAll(fixLinearization) BA:1497-1646 (+ setNewFrameEnergyTH); *energy = returned [0]
+ * cmlba_apply        applyActiveRes(true) BA:2045-2049
+ * cmlba_solve        backupState + solveSystem(iteration, lambda) BA:912-926, 1339-1495 (accumulate, Schur, stitch, LM solve, back-substitute)
+ * cmlba_step         doStepFromBackup(updatePointsOnly) BA:948-1028; *can_break = returned bool
+ */
+int cmlba_prepare(cmlba_handle *h, const double *cams);
+int cmlba_linearize(cmlba_handle *h, int fix_linearization, double *energy);
+int cmlba_apply(cmlba_handle *h);
+int cmlba_solve(cmlba_handle *h, int iteration);
+int cmlba_step(cmlba_handle *h, int update_points_only, int *can_break);
+
+/* Named read-back of internal buffers for parity tests (device -> host copy, residual arrays in the
+ * order of cmlba_read("res_point")/("res_target")).  Returns the number of BYTES the buffer holds in
+ * *bytes; copies min(capacity, bytes) into dst (dst may be NULL to query the size).  Names are listed in
+ * DESIGN.md ("debug buffers"). */
+int cmlba_read(cmlba_handle *h, const char *name, void *dst, size_t capacity, size_t *bytes);
+
+/* ---- multi-GPU (points sharded, images/frames replicated) ----
+ * Every rank holds the same frames and its own shard of the points.  The reduced system
+ * [H_A | b_A | H_sc | b_sc | energies | quantile histogram] is summed across ranks once per GN
+ * iteration with ncclAllReduce (libnccl is dlopen'ed on first use).
+ * unique_id: 128-byte ncclUniqueId created on rank 0 with cmlba_nccl_unique_id and broadcast by the
+ * caller's own plumbing (e.g. torch.distributed). */
+int cmlba_nccl_unique_id(void *unique_id_128);
+int cmlba_comm_init(cmlba_handle *h, const void *unique_id_128, int rank, int world_size);
+
+/* library / build info: "libcmlba <version> sm_100a" */
+const char *cmlba_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMLBA_H */

@@ -1,0 +1,252 @@
+"""ctypes binding of libcmlba.so + a host-side mirror of the reference operator interface.
+
+`DSOBundleAdjustment` below has the public methods of CML::Optimization::DSOBundleAdjustment
+(reference: src/cml/optimization/dso/DSOBundleAdjustment.h:26-101) with the same names, argument meaning
+and error behaviour (run() returns False where the reference returns false).  Frames and points are
+identified by integer ids instead of CML's Ptr<Frame>/Ptr<MapPoint>; INTEGRATION.md shows the C++ adapter
+that does the same translation inside CML.  Everything here is plumbing: the arithmetic lives in the CUDA
+kernels of csrc/kernels.cuh.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "libcmlba.so")
+
+
+class CmlbaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cmlba error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("huber_threshold", C.c_float), ("outlier_th_sum", C.c_float), ("th_opt_iterations", C.c_float),
+                ("scale_rotation", C.c_float), ("scale_translation", C.c_float), ("scale_light_a", C.c_float), ("scale_light_b", C.c_float),
+                ("scale_f", C.c_float), ("scale_c", C.c_float), ("force_accept", C.c_int), ("fix_lambda", C.c_int), ("fixed_lambda", C.c_float),
+                ("idepth_fix_prior", C.c_int), ("solver_mode_delta", C.c_float), ("optimize_light_a", C.c_int), ("optimize_light_b", C.c_int),
+                ("disable_marginalization", C.c_int), ("max_frames", C.c_int)]
+
+
+class RunResult(C.Structure):
+    _fields_ = [("iterations_done", C.c_int), ("num_residuals", C.c_int), ("num_dropped", C.c_int), ("num_outliers", C.c_int),
+                ("energy_first", C.c_double), ("energy_last", C.c_double), ("gpu_ms", C.c_double), ("kernel_launches", C.c_int)]
+
+
+# every symbol include/cmlba.h declares (tests/test_abi.py checks the .so exports all of them)
+SYMBOLS = ["cmlba_default_config", "cmlba_create", "cmlba_destroy", "cmlba_last_error", "cmlba_set_calib", "cmlba_add_frame", "cmlba_add_points",
+           "cmlba_remove_point", "cmlba_remove_frame", "cmlba_run", "cmlba_num_frames", "cmlba_num_points", "cmlba_num_residuals", "cmlba_get_frames",
+           "cmlba_get_points", "cmlba_get_outliers", "cmlba_get_residuals", "cmlba_prepare", "cmlba_linearize", "cmlba_apply", "cmlba_solve", "cmlba_step",
+           "cmlba_read", "cmlba_nccl_unique_id", "cmlba_comm_init", "cmlba_version"]
+
+_lib = None
+
+
+def load_library():
+    """Loads libcmlba.so (built by `make -C libcml_b200/csrc` or __graft_entry__.build()).  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError(f"{p} is missing: build it with `make -C libcml_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    vp, dp, fp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int)
+    lib.cmlba_version.restype = C.c_char_p
+    lib.cmlba_last_error.restype = C.c_char_p
+    lib.cmlba_last_error.argtypes = [vp]
+    lib.cmlba_default_config.argtypes = [C.POINTER(Config)]
+    lib.cmlba_create.argtypes = [C.POINTER(Config), C.c_int, C.POINTER(vp)]
+    lib.cmlba_destroy.argtypes = [vp]
+    lib.cmlba_set_calib.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.cmlba_add_frame.argtypes = [vp, C.c_int64, dp, C.c_double, C.c_double, C.c_double, fp, C.c_int]
+    lib.cmlba_add_points.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), fp, dp]
+    lib.cmlba_remove_point.argtypes = [vp, C.c_int64]
+    lib.cmlba_remove_frame.argtypes = [vp, C.c_int64]
+    lib.cmlba_run.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(RunResult)]
+    for f in ("cmlba_num_frames", "cmlba_num_points", "cmlba_num_residuals"):
+        getattr(lib, f).argtypes = [vp]
+    lib.cmlba_get_frames.argtypes = [vp, C.POINTER(C.c_int64), dp, dp, dp, dp, dp]
+    lib.cmlba_get_points.argtypes = [vp, C.POINTER(C.c_int64), dp, dp, fp, fp, ip, ip]
+    lib.cmlba_get_outliers.argtypes = [vp, C.POINTER(C.c_int64), ip]
+    lib.cmlba_get_residuals.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), ip, dp]
+    lib.cmlba_prepare.argtypes = [vp, dp]
+    lib.cmlba_linearize.argtypes = [vp, C.c_int, dp]
+    lib.cmlba_apply.argtypes = [vp]
+    lib.cmlba_solve.argtypes = [vp, C.c_int]
+    lib.cmlba_step.argtypes = [vp, C.c_int, ip]
+    lib.cmlba_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.cmlba_nccl_unique_id.argtypes = [vp]
+    lib.cmlba_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    _lib = lib
+    return lib
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def default_config():
+    cfg = Config()
+    load_library().cmlba_default_config(C.byref(cfg))
+    return cfg
+
+
+class DSOBundleAdjustment:
+    """Mirror of CML::Optimization::DSOBundleAdjustment over the C ABI (one handle = one BA instance)."""
+
+    def __init__(self, device=0, **params):
+        self.lib = load_library()
+        cfg = default_config()
+        for k, v in params.items():
+            if not hasattr(cfg, k):
+                raise KeyError(f"unknown BA parameter {k}")
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.lib.cmlba_create(C.byref(cfg), device, C.byref(self.h))
+        if rc != 0:
+            raise CmlbaError(rc, self.lib.cmlba_last_error(None).decode())
+        self.last_result = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cmlba_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CmlbaError(rc, self.lib.cmlba_last_error(self.h).decode())
+
+    # ---- reference surface (DSOBundleAdjustment.h:26-101)
+    def setCalibration(self, fx, fy, cx, cy, width, height):
+        """mPinhole/mWidth/mHeight cached by addNewFrame (BA:419-425)."""
+        self._ck(self.lib.cmlba_set_calib(self.h, fx, fy, cx, cy, int(width), int(height)))
+
+    def addNewFrame(self, frame_id, world_to_cam, aff_a, aff_b, exposure_time, grad_image, is_init_frame=False):
+        """addNewFrame(PFrame, immatureGroup) (BA:417-462). grad_image: [H,W,3] fp32 (I,dx,dy)."""
+        w2c = np.ascontiguousarray(world_to_cam, dtype=np.float64).reshape(12)
+        g = np.ascontiguousarray(grad_image, dtype=np.float32)
+        self._ck(self.lib.cmlba_add_frame(self.h, int(frame_id), _ptr(w2c, C.c_double), float(aff_a), float(aff_b), float(exposure_time),
+                                          _ptr(g, C.c_float), int(bool(is_init_frame))))
+
+    def addPoints(self, point_ids, host_frame_ids, xy, idepth):
+        """addPoints(const PointSet&) (BA:382-415)."""
+        pid = np.ascontiguousarray(point_ids, dtype=np.int64); hid = np.ascontiguousarray(host_frame_ids, dtype=np.int64)
+        xyf = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2); idp = np.ascontiguousarray(idepth, dtype=np.float64)
+        self._ck(self.lib.cmlba_add_points(self.h, int(pid.size), _ptr(pid, C.c_int64), _ptr(hid, C.c_int64), _ptr(xyf, C.c_float), _ptr(idp, C.c_double)))
+
+    def removePoint(self, point_id):
+        self._ck(self.lib.cmlba_remove_point(self.h, int(point_id)))
+
+    def removeFrame(self, frame_id):
+        self._ck(self.lib.cmlba_remove_frame(self.h, int(frame_id)))
+
+    def run(self, cams=None, updatePointsOnly=False, iterations=0):
+        """bool run(bool updatePointsOnly) (BA:744-910). cams: [N,12] current Frame::getCamera() per window frame."""
+        res = RunResult()
+        cp = None
+        if cams is not None:
+            cams = np.ascontiguousarray(cams, dtype=np.float64).reshape(-1, 12)
+            cp = _ptr(cams, C.c_double)
+        rc = self.lib.cmlba_run(self.h, cp, int(iterations), int(bool(updatePointsOnly)), C.byref(res))
+        self.last_result = res
+        if rc == -4:  # CMLBA_ERR_NUMERIC: the reference returns false
+            return False
+        self._ck(rc)
+        return True
+
+    def getOutliers(self):
+        n = C.c_int(0)
+        self._ck(self.lib.cmlba_get_outliers(self.h, None, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.int64)
+        m = C.c_int(n.value)
+        self._ck(self.lib.cmlba_get_outliers(self.h, _ptr(out, C.c_int64), C.byref(m)))
+        return out[:n.value]
+
+    def getFrames(self):
+        n = self.lib.cmlba_num_frames(self.h)
+        ids = np.zeros(n, np.int64); w2c = np.zeros((n, 12)); ab = np.zeros((n, 2)); st = np.zeros((n, 10)); ev = np.zeros((n, 12)); th = np.zeros(n)
+        self._ck(self.lib.cmlba_get_frames(self.h, _ptr(ids, C.c_int64), _ptr(w2c, C.c_double), _ptr(ab, C.c_double), _ptr(st, C.c_double), _ptr(ev, C.c_double), _ptr(th, C.c_double)))
+        return dict(id=ids, world_to_cam=w2c, affine=ab, state=st, evalpt=ev, energy_th=th)
+
+    def getPoints(self):
+        n = self.lib.cmlba_num_points(self.h)
+        ids = np.zeros(n, np.int64); idp = np.zeros(n); unc = np.zeros(n); idh = np.zeros(n, np.float32); mrb = np.zeros(n, np.float32)
+        ng = np.zeros(n, np.int32); gft = np.zeros(n, np.int32)
+        self._ck(self.lib.cmlba_get_points(self.h, _ptr(ids, C.c_int64), _ptr(idp, C.c_double), _ptr(unc, C.c_double), _ptr(idh, C.c_float), _ptr(mrb, C.c_float),
+                                           _ptr(ng, C.c_int), _ptr(gft, C.c_int)))
+        return dict(id=ids, idepth=idp, uncertainty=unc, idepth_hessian=idh, max_rel_baseline=mrb, num_good_residuals=ng, good_for_tracking=gft)
+
+    def getGoodPointsForTracking(self):
+        p = self.getPoints()
+        return p["id"][p["good_for_tracking"] != 0]
+
+    def getResiduals(self):
+        n = self.lib.cmlba_num_residuals(self.h)
+        pid = np.zeros(n, np.int64); tid = np.zeros(n, np.int64); st = np.zeros(n, np.int32); en = np.zeros(n)
+        self._ck(self.lib.cmlba_get_residuals(self.h, _ptr(pid, C.c_int64), _ptr(tid, C.c_int64), _ptr(st, C.c_int), _ptr(en, C.c_double)))
+        return dict(point_id=pid, target_frame_id=tid, state=st, energy=en)
+
+    # ---- stage entry points (protected members of the reference class)
+    def prepare(self, cams=None):
+        cp = None
+        if cams is not None:
+            cams = np.ascontiguousarray(cams, dtype=np.float64).reshape(-1, 12)
+            cp = _ptr(cams, C.c_double)
+        self._ck(self.lib.cmlba_prepare(self.h, cp))
+
+    def linearizeAll(self, fixLinearization=False):
+        e = C.c_double(0)
+        self._ck(self.lib.cmlba_linearize(self.h, int(bool(fixLinearization)), C.byref(e)))
+        return e.value
+
+    def applyActiveRes(self):
+        self._ck(self.lib.cmlba_apply(self.h))
+
+    def solveSystem(self, iteration):
+        self._ck(self.lib.cmlba_solve(self.h, int(iteration)))
+
+    def doStepFromBackup(self, updatePointsOnly=False):
+        cb = C.c_int(0)
+        self._ck(self.lib.cmlba_step(self.h, int(bool(updatePointsOnly)), C.byref(cb)))
+        return bool(cb.value)
+
+    def read(self, name, dtype, shape=None):
+        nb = C.c_size_t(0)
+        self._ck(self.lib.cmlba_read(self.h, name.encode(), None, 0, C.byref(nb)))
+        dt = np.dtype(dtype)
+        out = np.zeros(nb.value // dt.itemsize, dtype=dt)
+        if nb.value:
+            self._ck(self.lib.cmlba_read(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), nb.value, C.byref(nb)))
+        return out.reshape(shape) if shape is not None else out
+
+    def enableDebugDump(self):
+        self._ck(self.lib.cmlba_read(self.h, b"enable_dbg", None, 0, None))
+
+    # ---- convenience: build a window from a synthetic / snapshot dict (libcml_b200.synth / cmlw)
+    def loadWindow(self, win):
+        W, H = int(win["size"][0]), int(win["size"][1])
+        fx, fy, cx, cy = [float(v) for v in win["calib"]]
+        self.setCalibration(fx, fy, cx, cy, W, H)
+        N = win["frame_evalpt"].shape[0]
+        grad = win.get("grad")
+        if grad is None:
+            from .synth import gradient_image
+            grad = [gradient_image(win["gray"][i]) for i in range(N)]
+        init = win.get("frame_init", np.zeros(N, np.uint8))
+        for i in range(N):
+            self.addNewFrame(i, win["frame_evalpt"][i], win["frame_affine"][i, 0], win["frame_affine"][i, 1], win["frame_exposure"][i], grad[i], bool(init[i]))
+        P = win["pt_host"].size
+        self.addPoints(np.arange(P), win["pt_host"], win["pt_xy"], win["pt_idepth"])
+        return win["frame_cam"]

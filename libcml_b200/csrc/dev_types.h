@@ -1,0 +1,119 @@
+// dev_types.h -- device-side data layout of one BA window (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace cmlba {
+
+constexpr int MAXF = 16;          // CMLBA_MAX_FRAMES
+constexpr int RJ_STRIDE = 36;     // floats per residual Jacobian record (x[10] y[10] A[3] B[6] BR[6] pad)
+constexpr int T_STRIDE = 16;      // floats per (point,target) Schur row: JpJdF[8] bd Hdd Hcd[4] good pad
+constexpr int ACC_N = 96;         // 91 unique entries of the 13x13 block, padded to 3*32
+constexpr int LIN_THREADS = 128;  // linearize: one thread per residual
+constexpr int ACC_CHUNK = 128;    // residuals per accumulate CTA (all in one (h,t) bin)
+constexpr int SC_CHUNK = 64;      // points per Schur CTA (all hosted in one frame)
+
+enum : uint8_t { RES_IN = 0, RES_OOB = 1, RES_OUTLIER = 2 };
+
+// per (host h, target t) constants, index h*N+t.  DSOFramePrecomputed (DSOFrame.h:248-291)
+struct PairPre {
+    double R[9], t[3];    // current estimate  PRE_worldToCam_t * PRE_camToWorld_h  (trialRefToTarget)
+    double R0[9], t0[3];  // at the FEJ evaluation points (PRE_RTll_0 / PRE_tTll_0)
+    double a, b;          // exposure transition aff_h.to(aff_t)  (map/Exposure.h:119-123)
+    float b0;             // hostData->getB0(scaleB)  (DSOFrame.h:197-199)
+    float pad;
+};
+
+// DSOFrame (DSOFrame.h:17-246) as a POD
+struct FrameDev {
+    double evalR[9], evalt[3];   // worldToCam_evalPT
+    double preR[9], pret[3];     // PRE_worldToCam
+    double state[10], state_zero[10], state_backup[10], state_scaled[10], step[10];
+    double prior[8];
+    double exposure;             // ab_exposure
+    float energy_th;             // frameEnergyTH
+    int keyid;
+};
+
+struct Ctrl {
+    int cur;            // index of the committed buffer set (0/1); the other one holds the candidate linearization
+    int done;           // GN loop finished (canbreak && it>=1): later kernels of a pre-recorded run become no-ops
+    int canbreak;
+    int failed;         // non-finite energy / step
+    int iteration;      // GN iterations completed
+    int accepted;
+    int num_dropped;
+    int pad0;
+    double lambda;
+    double energy_last;     // energy of the committed linearization
+    double energy_new;      // energy of the candidate linearization
+    double energy_first;
+    float sumA, sumB, sumT, sumR;   // doStepFromBackup accumulators (BA:950-1018)
+    double sumNID;
+    int numID;
+    int sc_done_count;      // last-block counter (point step kernel)
+    double stats[16];       // ||HA|| ||Hsc|| ||bA|| ||bsc|| ||x|| ... (the Statistic series of BA.h:215-233)
+};
+
+struct DevWin {
+    // sizes
+    int N, P, R, W, H, n;          // n = 8N+4
+    int newest_begin;              // residuals [newest_begin, R) target the newest frame (sorted by bin t*N+h)
+    int n_lin_blocks, n_acc_chunks, n_sc_chunks;
+    // calibration / parameters
+    double fx, fy, cx, cy, fxi, fyi;
+    float huber, cth, scaleF, scaleC, scaleA, scaleB, scaleT, scaleR;
+    float th_opt;
+    int optA, optB, force_accept, fix_lambda, idepth_fix_prior;
+    double fixed_lambda;
+    // frames
+    const float4 *img[MAXF];       // level-0 (I,dx,dy,0) texels, row-major
+    FrameDev *frames;
+    PairPre *pairs;
+    Ctrl *ctrl;
+    const double *AH, *AT;         // [h*N+t][8][8] adjoints (BA:1071-1095)
+    const double *HM, *bM;         // marginalisation prior (n x n, n) or zero
+    const double *Pns;             // nullspace projector 0.5(NN+^T + ...) (BA:1247-1249), n x n
+    // points (sorted by host frame)
+    const int *pt_host;
+    const float *pt_x, *pt_y;
+    double *pt_idepth;
+    float *pt_idepth_zero, *pt_idepth_backup;
+    const float *pt_colors, *pt_weights;   // [P][8]
+    const float *pt_priorF;
+    float *pt_Hdd, *pt_bd, *pt_Hcd, *pt_HdiF, *pt_bdSumF, *pt_idepth_hessian, *pt_max_rel_bs;
+    int *pt_num_good;              // numGoodResiduals
+    int *pt_ngood_cur;             // good residuals in the committed linearization
+    double *pt_step;
+    // residuals (sorted by bin = t*N+h, then by point)
+    const int *r_point;
+    const uint8_t *r_host, *r_target;
+    uint8_t *r_state[2];
+    float *r_energy[2];
+    uint8_t *r_good[2];
+    uint8_t *r_new_state;
+    float *r_new_energy, *r_new_energy_wo;
+    uint8_t *r_alive;
+    float *r_center;               // [R][3] centerProjectedTo
+    float *rj;                     // [R][RJ_STRIDE] candidate Jacobian records
+    float *T[2];                   // [P][N][T_STRIDE]
+    float *dbg;                    // optional [R][40]: resF[8] JIdx[16] JabF[16]
+    // partial sums
+    double *energy_part;           // [n_lin_blocks]
+    float *acc_part[2];            // [n_acc_chunks][ACC_N]
+    const int *acc_chunk_bin, *acc_chunk_begin, *acc_chunk_count;
+    const int *bin_chunk_begin;    // [N*N+1] by bin = t*N+h
+    float *sc_part;                // [n_sc_chunks][sc_stride]
+    int sc_stride;                 // (8N)^2 + 32N + 8N + 16 + 4 (padded to 4)
+    const int *sc_chunk_host, *sc_chunk_begin, *sc_chunk_count;
+    const int *host_chunk_begin;   // [N+1]
+    double *HApart, *bApart, *HSpart, *bSpart;   // per host: [N][n*n], [N][n]
+    double *sys;                   // summed system: HA[n*n] bA[n] HS[n*n] bS[n]  (allreduce payload)
+    double *x;                     // [n]
+    double *xAd;                   // [h*N+t][8]
+    double *pt_part;               // point-step partial sums [blocks][2]
+    int n_pt_blocks;
+    int update_points_only;
+};
+
+}  // namespace cmlba

@@ -1,0 +1,1012 @@
+// engine.cu -- host side of libcmlba.so: window bookkeeping (the DSOContext role), device buffers,
+// the run() kernel sequence and the C ABI of include/cmlba.h.
+//
+// Host-side reference anchors (under /root/reference/src/cml/optimization/dso):
+//   Engine::add_frame   DSOBundleAdjustment.cpp:417-462 (addNewFrame), DSOFrame.h:98-106 (setEvalPT_scaled)
+//   Engine::add_points  DSOBundleAdjustment.cpp:382-415 (addPoints), :336-380 (createResidual), DSOContext.h:76-91
+//   Engine::prepare     DSOBundleAdjustment.cpp:753-782 (run prologue), :1030-1101 (computeAdjoints), :1103-1194
+//                       (computeDelta priors), :2365-2417 (computeNullspaces), :1196-1250 (nullspace projector)
+//   Engine::run         DSOBundleAdjustment.cpp:744-910
+//   Engine::finish_run  DSOBundleAdjustment.cpp:1613-1642 (residual dropping, outliers), DSOPoint.h:107-118
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cmlba.h"
+#include "kernels.cuh"
+
+namespace cmlba {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(_e));                         \
+            return CMLBA_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 16;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct FrameHost {
+    int64_t id = 0;
+    Pose evalpt;                 // worldToCam_evalPT
+    double state[10] = {0}, state_zero[10] = {0};
+    double prior[8] = {0};
+    double exposure = 1.0;
+    float energy_th = 8 * 8 * 8; // DSOFrame.h:35
+    int keyid = 0;
+    bool is_init = false;
+    float4 *d_img = nullptr;
+    Pose pre;                    // PRE_worldToCam (last known)
+    double aff_a = 0, aff_b = 0; // aff_g2l (scaled a,b)
+};
+
+struct PointHost {
+    int64_t id = 0;
+    int64_t host_id = 0;
+    float x = 0, y = 0;
+    double idepth = 0;
+    float idepth_zero = 0;
+    bool has_prior = false;
+    float colors[8], weights[8];
+    int num_good = 0;
+    float max_rel_bs = 0, idepth_hessian = 0;
+    int64_t last_frame[2] = {-1, -1};   // frames of lastResiduals[0/1] (DSOPoint.h:119-156); -1 = nullptr
+    int last_state[2] = {CMLBA_RES_OOB, CMLBA_RES_OOB};
+    bool alive = true;
+};
+
+struct ResHost {
+    int point;          // index into points_
+    int64_t target_id;
+    int state = CMLBA_RES_IN;
+    float energy = 0;
+};
+
+// --- NCCL through dlopen (multi-GPU only) -----------------------------------------------------
+struct NcclUid { char b[128]; };
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUid, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    bool load(std::string &err) {
+        if (lib) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { err = "cannot dlopen libnccl.so.2 (add torch's nvidia/nccl/lib to LD_LIBRARY_PATH or import torch first)"; return false; }
+        GetUniqueId = (decltype(GetUniqueId)) dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank)) dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce)) dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather)) dlsym(lib, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy)) dlsym(lib, "ncclCommDestroy");
+        if (!GetUniqueId || !CommInitRank || !AllReduce || !AllGather) { err = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+static NcclApi g_nccl;
+
+class Engine {
+public:
+    cmlba_config cfg;
+    int device = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool have_calib = false;
+    double fx = 0, fy = 0, cx = 0, cy = 0;
+    int W = 0, H = 0;
+    std::vector<FrameHost> frames_;
+    std::vector<PointHost> points_;
+    std::vector<ResHost> res_;
+    std::unordered_map<int64_t, int> point_index_;
+    std::vector<int64_t> outliers_;
+    int key_counter = 0;
+    bool dirty = true;            // device window must be rebuilt
+    bool prepared = false;
+    std::vector<double> HM, bM;   // marginalisation prior, (8N+4)^2 ; zero in this round
+    // device-window layout (host mirrors)
+    std::vector<int> pt_order;    // device point i -> points_ index
+    std::vector<int> res_order;   // device residual i -> res_ index
+    DevWin dw;
+    int launches = 0;
+    // multi-GPU
+    void *comm = nullptr; int rank = 0, world = 1;
+
+    // device buffers
+    DevBuf<FrameDev> d_frames; DevBuf<PairPre> d_pairs; DevBuf<Ctrl> d_ctrl;
+    DevBuf<double> d_AH, d_AT, d_HM, d_bM, d_Pns, d_pt_idepth, d_pt_step, d_energy_part, d_HApart, d_bApart, d_HSpart, d_bSpart, d_sys, d_x, d_xAd, d_pt_part;
+    DevBuf<int> d_pt_host, d_pt_num_good, d_pt_ngood_cur, d_r_point, d_acc_chunk_bin, d_acc_chunk_begin, d_acc_chunk_count, d_bin_chunk_begin, d_sc_chunk_host,
+        d_sc_chunk_begin, d_sc_chunk_count, d_host_chunk_begin;
+    DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
+        d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj, d_T0, d_T1, d_dbg, d_acc0, d_acc1, d_sc_part, d_stage;
+    DevBuf<uint8_t> d_r_host, d_r_target, d_r_state0, d_r_state1, d_r_good0, d_r_good1, d_r_new_state, d_r_alive;
+    bool want_dbg = false;
+    int n_acc_chunks = 0, n_sc_chunks = 0;
+    std::vector<int> h_bin_chunk_begin, h_host_chunk_begin;
+
+    void set_error(const std::string &s) { err = s; }
+
+    int init() {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0) { set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libcmlba has no CPU fallback)"); return CMLBA_ERR_CUDA; }
+        if (device < 0 || device >= ndev) { set_error("bad device ordinal"); return CMLBA_ERR_ARG; }
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+        // entry-offset table of the 13x13 accumulator (see accumulate_kernel)
+        uchar4 ofs[ACC_N];
+        int e_i = 0;
+        for (int r = 0; r < 10; r++) for (int c = r; c < 10; c++) ofs[e_i++] = make_uchar4(r, 36 + c, 10 + r, 46 + c);
+        for (int r = 0; r < 10; r++) for (int c = 0; c < 3; c++) ofs[e_i++] = make_uchar4(r, 23 + c, 10 + r, 26 + c);
+        for (int k = 0; k < 6; k++) ofs[e_i++] = make_uchar4(29 + k, 35, 56, 56);
+        while (e_i < ACC_N) ofs[e_i++] = make_uchar4(56, 56, 56, 56);
+        CK(cudaMemcpyToSymbol(c_acc_ofs, ofs, sizeof(ofs)));
+        CK(cudaFuncSetAttribute(stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CK(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        return CMLBA_OK;
+    }
+
+    ~Engine() {
+        cudaSetDevice(device);
+        for (auto &f : frames_) if (f.d_img) cudaFree(f.d_img);
+        if (stream) cudaStreamDestroy(stream);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        // DevBuf members leak-free:
+        DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_HApart, &d_bApart, &d_HSpart, &d_bSpart, &d_sys, &d_x, &d_xAd, &d_pt_part};
+        for (auto *b : dd) b->release();
+        DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_acc_chunk_bin, &d_acc_chunk_begin, &d_acc_chunk_count, &d_bin_chunk_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin};
+        for (auto *b : di) b->release();
+        DevBuf<float> *df[] = {&d_pt_x, &d_pt_y, &d_pt_idz, &d_pt_idb, &d_pt_colors, &d_pt_weights, &d_pt_priorF, &d_pt_Hdd, &d_pt_bd, &d_pt_Hcd, &d_pt_HdiF, &d_pt_bdSumF, &d_pt_idh, &d_pt_mrb,
+                               &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj, &d_T0, &d_T1, &d_dbg, &d_acc0, &d_acc1, &d_sc_part, &d_stage};
+        for (auto *b : df) b->release();
+        DevBuf<uint8_t> *du[] = {&d_r_host, &d_r_target, &d_r_state0, &d_r_state1, &d_r_good0, &d_r_good1, &d_r_new_state, &d_r_alive};
+        for (auto *b : du) b->release();
+        d_frames.release(); d_pairs.release(); d_ctrl.release();
+    }
+
+    int frame_index(int64_t id) const {
+        for (size_t i = 0; i < frames_.size(); i++) if (frames_[i].id == id) return (int) i;
+        return -1;
+    }
+
+    void scales(double *sc) const {
+        const double v[10] = {cfg.scale_translation, cfg.scale_translation, cfg.scale_translation, cfg.scale_rotation, cfg.scale_rotation, cfg.scale_rotation,
+                              cfg.scale_light_a, cfg.scale_light_b, cfg.scale_light_a, cfg.scale_light_b};
+        for (int k = 0; k < 10; k++) sc[k] = v[k];
+    }
+
+    // ------------------------------------------------------------------ window maintenance
+    int set_calib(double fx_, double fy_, double cx_, double cy_, int w, int h) {
+        if (w < 8 || h < 8 || fx_ <= 0 || fy_ <= 0) { set_error("bad calibration"); return CMLBA_ERR_ARG; }
+        if (have_calib && (w != W || h != H) && !frames_.empty()) { set_error("image size change with frames in the window"); return CMLBA_ERR_STATE; }
+        fx = fx_; fy = fy_; cx = cx_; cy = cy_; W = w; H = h; have_calib = true; dirty = true;
+        return CMLBA_OK;
+    }
+
+    int add_frame(int64_t id, const double *w2c, double a, double b, double exposure, const float *grad, int is_init) {
+        if (!have_calib) { set_error("cmlba_set_calib must be called before cmlba_add_frame"); return CMLBA_ERR_STATE; }
+        if (!w2c || !grad) { set_error("null pointer"); return CMLBA_ERR_ARG; }
+        if ((int) frames_.size() >= MAXF) { set_error("window full (CMLBA_MAX_FRAMES)"); return CMLBA_ERR_ARG; }
+        for (auto &f : frames_) if (id <= f.id) { set_error("frame ids must increase (DSOContext.h:139-143 aborts here)"); return CMLBA_ERR_ARG; }
+        if (exposure <= 0) { set_error("exposure must be > 0"); return CMLBA_ERR_ARG; }
+        CK(cudaSetDevice(device));
+        FrameHost f;
+        f.id = id;
+        for (int k = 0; k < 9; k++) f.evalpt.R[k] = w2c[k];
+        for (int k = 0; k < 3; k++) f.evalpt.t[k] = w2c[9 + k];
+        f.pre = f.evalpt;
+        double sc[10]; scales(sc);
+        // setEvalPT_scaled: state_scaled = (0,..,a,b), state = scaled / scale, state_zero = state
+        f.state[6] = a / sc[6]; f.state[7] = b / sc[7];
+        for (int k = 0; k < 10; k++) f.state_zero[k] = f.state[k];
+        f.aff_a = a; f.aff_b = b;
+        f.exposure = exposure;
+        f.keyid = key_counter++;
+        f.is_init = is_init != 0;
+        // image: AoS (I,dx,dy) -> float4 texels on the device
+        const size_t npix = (size_t) W * H;
+        CK(d_stage.reserve(npix * 3));
+        CK(cudaMalloc(&f.d_img, npix * sizeof(float4)));
+        CK(cudaMemcpyAsync(d_stage.p, grad, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        repack_image_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(d_stage.p, f.d_img, (int) npix);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        frames_.push_back(f);
+        // residuals from all existing points to the new frame (BA:455-460); lastResiduals slot 0 (BA:374-375)
+        for (size_t p = 0; p < points_.size(); p++) {
+            if (!points_[p].alive) continue;
+            res_.push_back(ResHost{(int) p, id});
+            points_[p].last_frame[1] = points_[p].last_frame[0]; points_[p].last_state[1] = points_[p].last_state[0];
+            points_[p].last_frame[0] = id; points_[p].last_state[0] = CMLBA_RES_IN;
+        }
+        dirty = true; prepared = false;
+        return CMLBA_OK;
+    }
+
+    int add_points(int n, const int64_t *pid, const int64_t *host_id, const float *xy, const double *idepth) {
+        if (n < 0 || (n > 0 && (!pid || !host_id || !xy || !idepth))) { set_error("null pointer"); return CMLBA_ERR_ARG; }
+        if (frames_.empty()) { set_error("no frames in the window"); return CMLBA_ERR_STATE; }
+        CK(cudaSetDevice(device));
+        const size_t first = points_.size();
+        for (int i = 0; i < n; i++) {
+            if (point_index_.count(pid[i])) continue;                 // BA:386-388
+            const int h = frame_index(host_id[i]);
+            if (h < 0) { set_error("point's host frame is not in the window"); points_.resize(first); return CMLBA_ERR_ARG; }
+            const float x = xy[2 * i], y = xy[2 * i + 1];
+            if (!(x >= 3 && y >= 3 && x < W - 4 && y < H - 4)) { set_error("point closer than 3 px to the image border"); points_.resize(first); return CMLBA_ERR_ARG; }
+            if (!(idepth[i] > 0) || !std::isfinite(idepth[i])) { set_error("inverse depth must be finite and > 0"); points_.resize(first); return CMLBA_ERR_ARG; }
+            PointHost p;
+            p.id = pid[i]; p.host_id = host_id[i]; p.x = x; p.y = y; p.idepth = idepth[i];
+            p.idepth_zero = (float) idepth[i];
+            p.has_prior = frames_[h].is_init;
+            points_.push_back(p);
+        }
+        const size_t nn = points_.size() - first;
+        if (nn == 0) return CMLBA_OK;
+        // colours + weights on the device from the host frames' images
+        std::vector<int> hh(nn); std::vector<float> xs(nn), ys(nn);
+        for (size_t i = 0; i < nn; i++) { hh[i] = frame_index(points_[first + i].host_id); xs[i] = points_[first + i].x; ys[i] = points_[first + i].y; }
+        DevBuf<int> th; DevBuf<float> tx, ty, tc, tw;
+        CK(th.reserve(nn)); CK(tx.reserve(nn)); CK(ty.reserve(nn)); CK(tc.reserve(nn * 8)); CK(tw.reserve(nn * 8));
+        CK(cudaMemcpyAsync(th.p, hh.data(), nn * sizeof(int), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(tx.p, xs.data(), nn * sizeof(float), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(ty.p, ys.data(), nn * sizeof(float), cudaMemcpyHostToDevice, stream));
+        DevWin t{};
+        t.W = W; t.H = H; t.cth = cfg.outlier_th_sum;
+        for (size_t i = 0; i < frames_.size(); i++) t.img[i] = frames_[i].d_img;
+        t.pt_host = th.p; t.pt_x = tx.p; t.pt_y = ty.p;
+        point_init_kernel<<<(unsigned) ((nn * 8 + 255) / 256), 256, 0, stream>>>(t, 0, (int) nn, tc.p, tw.p);
+        CK(cudaGetLastError());
+        std::vector<float> hc(nn * 8), hw(nn * 8);
+        CK(cudaMemcpyAsync(hc.data(), tc.p, nn * 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hw.data(), tw.p, nn * 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        th.release(); tx.release(); ty.release(); tc.release(); tw.release();
+        const int64_t newest = frames_.back().id, second = frames_.size() >= 2 ? frames_[frames_.size() - 2].id : -1;
+        for (size_t i = 0; i < nn; i++) {
+            PointHost &p = points_[first + i];
+            memcpy(p.colors, &hc[i * 8], 32); memcpy(p.weights, &hw[i * 8], 32);
+            point_index_[p.id] = (int) (first + i);
+            for (auto &f : frames_) {
+                if (f.id == p.host_id) continue;
+                res_.push_back(ResHost{(int) (first + i), f.id});
+                if (f.id == newest) { p.last_frame[0] = f.id; p.last_state[0] = CMLBA_RES_IN; }
+                else if (f.id == second) { p.last_frame[1] = f.id; p.last_state[1] = CMLBA_RES_IN; }
+            }
+        }
+        dirty = true; prepared = false;
+        return CMLBA_OK;
+    }
+
+    void compact() {   // drop dead points / residuals, rebuild indices
+        std::vector<int> remap(points_.size(), -1);
+        std::vector<PointHost> np;
+        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive) { remap[i] = (int) np.size(); np.push_back(points_[i]); }
+        std::vector<ResHost> nr;
+        for (auto &r : res_) if (remap[r.point] >= 0) { ResHost q = r; q.point = remap[r.point]; nr.push_back(q); }
+        points_.swap(np); res_.swap(nr);
+        point_index_.clear();
+        for (size_t i = 0; i < points_.size(); i++) point_index_[points_[i].id] = (int) i;
+        dirty = true; prepared = false;
+    }
+
+    int remove_point(int64_t id) {
+        auto it = point_index_.find(id);
+        if (it == point_index_.end()) return CMLBA_OK;   // DSOContext.h:95-97
+        points_[it->second].alive = false;
+        compact();
+        return CMLBA_OK;
+    }
+
+    int remove_frame(int64_t id) {
+        const int fi = frame_index(id);
+        if (fi < 0) { set_error("unknown frame id"); return CMLBA_ERR_ARG; }
+        for (auto &p : points_) if (p.host_id == id) p.alive = false;
+        std::vector<ResHost> nr;
+        for (auto &r : res_) if (r.target_id != id) nr.push_back(r);
+        res_.swap(nr);
+        // points left without residuals disappear as well (DSOContext.h:205-216)
+        std::vector<int> cnt(points_.size(), 0);
+        for (auto &r : res_) cnt[r.point]++;
+        for (size_t i = 0; i < points_.size(); i++) if (cnt[i] == 0) points_[i].alive = false;
+        cudaSetDevice(device);
+        if (frames_[fi].d_img) cudaFree(frames_[fi].d_img);
+        frames_.erase(frames_.begin() + fi);
+        compact();
+        return CMLBA_OK;
+    }
+
+    // ------------------------------------------------------------------ device window
+    int build_device_window() {
+        const int N = (int) frames_.size(), P = (int) points_.size(), R = (int) res_.size();
+        const int n = 8 * N + 4;
+        CK(cudaSetDevice(device));
+        std::unordered_map<int64_t, int> fidx;
+        for (int i = 0; i < N; i++) fidx[frames_[i].id] = i;
+        // points sorted by host (stable)
+        pt_order.resize(P);
+        for (int i = 0; i < P; i++) pt_order[i] = i;
+        std::vector<int> phost(P);
+        for (int i = 0; i < P; i++) phost[i] = fidx.at(points_[i].host_id);
+        std::stable_sort(pt_order.begin(), pt_order.end(), [&](int a, int b) { return phost[a] < phost[b]; });
+        std::vector<int> pos(P);
+        for (int i = 0; i < P; i++) pos[pt_order[i]] = i;
+        // residuals sorted by bin = t*N + h, then device point position
+        res_order.resize(R);
+        for (int i = 0; i < R; i++) res_order[i] = i;
+        std::vector<int64_t> key(R);
+        for (int i = 0; i < R; i++) {
+            const int t = fidx.at(res_[i].target_id), h = phost[res_[i].point];
+            key[i] = ((int64_t) (t * N + h) << 32) | (uint32_t) pos[res_[i].point];
+        }
+        std::sort(res_order.begin(), res_order.end(), [&](int a, int b) { return key[a] < key[b]; });
+        // host arrays
+        std::vector<int> h_pt_host(P); std::vector<float> h_x(P), h_y(P), h_idz(P), h_col((size_t) P * 8), h_wt((size_t) P * 8), h_prior(P), h_mrb(P), h_idh(P);
+        std::vector<double> h_id(P); std::vector<int> h_ng(P);
+        for (int i = 0; i < P; i++) {
+            const PointHost &p = points_[pt_order[i]];
+            h_pt_host[i] = phost[pt_order[i]]; h_x[i] = p.x; h_y[i] = p.y; h_id[i] = p.idepth; h_idz[i] = p.idepth_zero;
+            memcpy(&h_col[(size_t) i * 8], p.colors, 32); memcpy(&h_wt[(size_t) i * 8], p.weights, 32);
+            h_prior[i] = p.has_prior ? (float) cfg.idepth_fix_prior : 0.f;
+            h_ng[i] = p.num_good; h_mrb[i] = p.max_rel_bs; h_idh[i] = p.idepth_hessian;
+        }
+        std::vector<int> h_rp(R); std::vector<uint8_t> h_rh(R), h_rt(R);
+        int newest_begin = R;
+        for (int i = 0; i < R; i++) {
+            const ResHost &r = res_[res_order[i]];
+            h_rp[i] = pos[r.point]; h_rh[i] = (uint8_t) phost[r.point]; h_rt[i] = (uint8_t) fidx.at(r.target_id);
+            if (h_rt[i] == N - 1 && newest_begin == R) newest_begin = i;
+        }
+        // accumulate chunks: per bin
+        std::vector<int> cb, cbeg, ccnt; h_bin_chunk_begin.assign(N * N + 1, 0);
+        {
+            int i = 0;
+            for (int bin = 0; bin < N * N; bin++) {
+                h_bin_chunk_begin[bin] = (int) cb.size();
+                const int t = bin / N, h = bin % N;
+                int j = i;
+                while (j < R && h_rt[j] == t && h_rh[j] == h) j++;
+                for (int s = i; s < j; s += ACC_CHUNK) { cb.push_back(bin); cbeg.push_back(s); ccnt.push_back(std::min(ACC_CHUNK, j - s)); }
+                i = j;
+            }
+            h_bin_chunk_begin[N * N] = (int) cb.size();
+        }
+        n_acc_chunks = (int) cb.size();
+        // Schur chunks: per host
+        std::vector<int> sh, sbeg, scnt; h_host_chunk_begin.assign(N + 1, 0);
+        {
+            int i = 0;
+            for (int h = 0; h < N; h++) {
+                h_host_chunk_begin[h] = (int) sh.size();
+                int j = i;
+                while (j < P && h_pt_host[j] == h) j++;
+                for (int s = i; s < j; s += SC_CHUNK) { sh.push_back(h); sbeg.push_back(s); scnt.push_back(std::min(SC_CHUNK, j - s)); }
+                i = j;
+            }
+            h_host_chunk_begin[N] = (int) sh.size();
+        }
+        n_sc_chunks = (int) sh.size();
+        const int NB = 8 * N;
+        const int sc_stride = ((NB * NB + NB * 4 + NB + 20) + 3) & ~3;
+        const int n_lin_blocks = (R + LIN_THREADS - 1) / LIN_THREADS;
+        const int n_pt_blocks = (P + 255) / 256;
+        // allocate
+        const size_t Rz = std::max(R, 1), Pz = std::max(P, 1);
+        CK(d_frames.reserve(MAXF)); CK(d_pairs.reserve(MAXF * MAXF)); CK(d_ctrl.reserve(1));
+        CK(d_AH.reserve((size_t) N * N * 64)); CK(d_AT.reserve((size_t) N * N * 64)); CK(d_HM.reserve((size_t) n * n)); CK(d_bM.reserve(n)); CK(d_Pns.reserve((size_t) n * n));
+        CK(d_pt_host.reserve(Pz)); CK(d_pt_x.reserve(Pz)); CK(d_pt_y.reserve(Pz)); CK(d_pt_idepth.reserve(Pz)); CK(d_pt_idz.reserve(Pz)); CK(d_pt_idb.reserve(Pz));
+        CK(d_pt_colors.reserve(Pz * 8)); CK(d_pt_weights.reserve(Pz * 8)); CK(d_pt_priorF.reserve(Pz));
+        CK(d_pt_Hdd.reserve(Pz)); CK(d_pt_bd.reserve(Pz)); CK(d_pt_Hcd.reserve(Pz * 4)); CK(d_pt_HdiF.reserve(Pz)); CK(d_pt_bdSumF.reserve(Pz)); CK(d_pt_idh.reserve(Pz)); CK(d_pt_mrb.reserve(Pz));
+        CK(d_pt_num_good.reserve(Pz)); CK(d_pt_ngood_cur.reserve(Pz)); CK(d_pt_step.reserve(Pz));
+        CK(d_r_point.reserve(Rz)); CK(d_r_host.reserve(Rz)); CK(d_r_target.reserve(Rz));
+        CK(d_r_state0.reserve(Rz)); CK(d_r_state1.reserve(Rz)); CK(d_r_energy0.reserve(Rz)); CK(d_r_energy1.reserve(Rz)); CK(d_r_good0.reserve(Rz)); CK(d_r_good1.reserve(Rz));
+        CK(d_r_new_state.reserve(Rz)); CK(d_r_new_energy.reserve(Rz)); CK(d_r_new_energy_wo.reserve(Rz)); CK(d_r_alive.reserve(Rz)); CK(d_r_center.reserve(Rz * 3));
+        CK(d_rj.reserve(Rz * RJ_STRIDE)); CK(d_T0.reserve(Pz * N * T_STRIDE)); CK(d_T1.reserve(Pz * N * T_STRIDE));
+        if (want_dbg) CK(d_dbg.reserve(Rz * DBG_STRIDE));
+        CK(d_energy_part.reserve(std::max(n_lin_blocks, 1)));
+        CK(d_acc0.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N)); CK(d_acc1.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N));
+        CK(d_acc_chunk_bin.reserve(std::max(n_acc_chunks, 1))); CK(d_acc_chunk_begin.reserve(std::max(n_acc_chunks, 1))); CK(d_acc_chunk_count.reserve(std::max(n_acc_chunks, 1)));
+        CK(d_bin_chunk_begin.reserve(N * N + 1));
+        CK(d_sc_part.reserve((size_t) std::max(n_sc_chunks, 1) * sc_stride));
+        CK(d_sc_chunk_host.reserve(std::max(n_sc_chunks, 1))); CK(d_sc_chunk_begin.reserve(std::max(n_sc_chunks, 1))); CK(d_sc_chunk_count.reserve(std::max(n_sc_chunks, 1)));
+        CK(d_host_chunk_begin.reserve(N + 1));
+        CK(d_HApart.reserve((size_t) N * n * n)); CK(d_HSpart.reserve((size_t) N * n * n)); CK(d_bApart.reserve((size_t) N * n)); CK(d_bSpart.reserve((size_t) N * n));
+        CK(d_sys.reserve((size_t) 2 * n * n + 2 * n)); CK(d_x.reserve(n)); CK(d_xAd.reserve((size_t) N * N * 8)); CK(d_pt_part.reserve((size_t) std::max(n_pt_blocks, 1) * 3));
+        // upload
+#define UP(dst, src, cnt) if ((cnt) > 0) CK(cudaMemcpyAsync((dst).p, (src).data(), (size_t) (cnt) * sizeof(*(dst).p), cudaMemcpyHostToDevice, stream))
+        UP(d_pt_host, h_pt_host, P); UP(d_pt_x, h_x, P); UP(d_pt_y, h_y, P); UP(d_pt_idepth, h_id, P); UP(d_pt_idz, h_idz, P);
+        UP(d_pt_colors, h_col, (size_t) P * 8); UP(d_pt_weights, h_wt, (size_t) P * 8); UP(d_pt_priorF, h_prior, P);
+        UP(d_pt_num_good, h_ng, P); UP(d_pt_mrb, h_mrb, P); UP(d_pt_idh, h_idh, P);
+        UP(d_r_point, h_rp, R); UP(d_r_host, h_rh, R); UP(d_r_target, h_rt, R);
+        UP(d_acc_chunk_bin, cb, n_acc_chunks); UP(d_acc_chunk_begin, cbeg, n_acc_chunks); UP(d_acc_chunk_count, ccnt, n_acc_chunks);
+        UP(d_bin_chunk_begin, h_bin_chunk_begin, N * N + 1);
+        UP(d_sc_chunk_host, sh, n_sc_chunks); UP(d_sc_chunk_begin, sbeg, n_sc_chunks); UP(d_sc_chunk_count, scnt, n_sc_chunks);
+        UP(d_host_chunk_begin, h_host_chunk_begin, N + 1);
+#undef UP
+        CK(cudaStreamSynchronize(stream));   // host vectors go out of scope
+        // DevWin
+        DevWin &w = dw;
+        memset(&w, 0, sizeof(w));
+        w.N = N; w.P = P; w.R = R; w.W = W; w.H = H; w.n = n; w.newest_begin = newest_begin;
+        w.n_lin_blocks = n_lin_blocks; w.n_acc_chunks = n_acc_chunks; w.n_sc_chunks = n_sc_chunks;
+        w.fx = fx; w.fy = fy; w.cx = cx; w.cy = cy; w.fxi = 1.0 / fx; w.fyi = 1.0 / fy;
+        w.huber = cfg.huber_threshold; w.cth = cfg.outlier_th_sum; w.scaleF = cfg.scale_f; w.scaleC = cfg.scale_c;
+        w.scaleA = cfg.scale_light_a; w.scaleB = cfg.scale_light_b; w.scaleT = cfg.scale_translation; w.scaleR = cfg.scale_rotation;
+        w.th_opt = cfg.th_opt_iterations; w.optA = cfg.optimize_light_a; w.optB = cfg.optimize_light_b;
+        w.force_accept = cfg.force_accept; w.fix_lambda = cfg.fix_lambda; w.idepth_fix_prior = cfg.idepth_fix_prior; w.fixed_lambda = (double) cfg.fixed_lambda;
+        for (int i = 0; i < N; i++) w.img[i] = frames_[i].d_img;
+        w.frames = d_frames.p; w.pairs = d_pairs.p; w.ctrl = d_ctrl.p; w.AH = d_AH.p; w.AT = d_AT.p; w.HM = d_HM.p; w.bM = d_bM.p; w.Pns = d_Pns.p;
+        w.pt_host = d_pt_host.p; w.pt_x = d_pt_x.p; w.pt_y = d_pt_y.p; w.pt_idepth = d_pt_idepth.p; w.pt_idepth_zero = d_pt_idz.p; w.pt_idepth_backup = d_pt_idb.p;
+        w.pt_colors = d_pt_colors.p; w.pt_weights = d_pt_weights.p; w.pt_priorF = d_pt_priorF.p;
+        w.pt_Hdd = d_pt_Hdd.p; w.pt_bd = d_pt_bd.p; w.pt_Hcd = d_pt_Hcd.p; w.pt_HdiF = d_pt_HdiF.p; w.pt_bdSumF = d_pt_bdSumF.p; w.pt_idepth_hessian = d_pt_idh.p; w.pt_max_rel_bs = d_pt_mrb.p;
+        w.pt_num_good = d_pt_num_good.p; w.pt_ngood_cur = d_pt_ngood_cur.p; w.pt_step = d_pt_step.p;
+        w.r_point = d_r_point.p; w.r_host = d_r_host.p; w.r_target = d_r_target.p;
+        w.r_state[0] = d_r_state0.p; w.r_state[1] = d_r_state1.p; w.r_energy[0] = d_r_energy0.p; w.r_energy[1] = d_r_energy1.p; w.r_good[0] = d_r_good0.p; w.r_good[1] = d_r_good1.p;
+        w.r_new_state = d_r_new_state.p; w.r_new_energy = d_r_new_energy.p; w.r_new_energy_wo = d_r_new_energy_wo.p; w.r_alive = d_r_alive.p; w.r_center = d_r_center.p;
+        w.rj = d_rj.p; w.T[0] = d_T0.p; w.T[1] = d_T1.p; w.dbg = want_dbg ? d_dbg.p : nullptr;
+        w.energy_part = d_energy_part.p; w.acc_part[0] = d_acc0.p; w.acc_part[1] = d_acc1.p;
+        w.acc_chunk_bin = d_acc_chunk_bin.p; w.acc_chunk_begin = d_acc_chunk_begin.p; w.acc_chunk_count = d_acc_chunk_count.p; w.bin_chunk_begin = d_bin_chunk_begin.p;
+        w.sc_part = d_sc_part.p; w.sc_stride = sc_stride; w.sc_chunk_host = d_sc_chunk_host.p; w.sc_chunk_begin = d_sc_chunk_begin.p; w.sc_chunk_count = d_sc_chunk_count.p;
+        w.host_chunk_begin = d_host_chunk_begin.p;
+        w.HApart = d_HApart.p; w.bApart = d_bApart.p; w.HSpart = d_HSpart.p; w.bSpart = d_bSpart.p; w.sys = d_sys.p; w.x = d_x.p; w.xAd = d_xAd.p;
+        w.pt_part = d_pt_part.p; w.n_pt_blocks = n_pt_blocks;
+        dirty = false;
+        return CMLBA_OK;
+    }
+
+    // 7x7 symmetric eigen-decomposition (cyclic Jacobi), eigenvectors in columns of V
+    static void jacobi_eig(int k, double *A, double *V) {
+        for (int i = 0; i < k * k; i++) V[i] = (i % (k + 1) == 0) ? 1.0 : 0.0;
+        for (int sweep = 0; sweep < 60; sweep++) {
+            double off = 0;
+            for (int p = 0; p < k; p++) for (int q = p + 1; q < k; q++) off += A[p * k + q] * A[p * k + q];
+            if (off < 1e-30) break;
+            for (int p = 0; p < k; p++) for (int q = p + 1; q < k; q++) {
+                if (fabs(A[p * k + q]) < 1e-300) continue;
+                const double th = (A[q * k + q] - A[p * k + p]) / (2 * A[p * k + q]);
+                const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1));
+                const double c = 1 / sqrt(t * t + 1), s = t * c;
+                for (int i = 0; i < k; i++) { const double a = A[i * k + p], b = A[i * k + q]; A[i * k + p] = c * a - s * b; A[i * k + q] = s * a + c * b; }
+                for (int i = 0; i < k; i++) { const double a = A[p * k + i], b = A[q * k + i]; A[p * k + i] = c * a - s * b; A[q * k + i] = s * a + c * b; }
+                for (int i = 0; i < k; i++) { const double a = V[i * k + p], b = V[i * k + q]; V[i * k + p] = c * a - s * b; V[i * k + q] = s * a + c * b; }
+            }
+        }
+    }
+
+    // run() prologue: updateCamera, computeAdjoints, computeDelta (priors), nullspace projector; reset residuals
+    int prepare(const double *cams) {
+        if (!have_calib) { set_error("calibration not set"); return CMLBA_ERR_STATE; }
+        const int N = (int) frames_.size();
+        if (N < 1) { set_error("no frames"); return CMLBA_ERR_STATE; }
+        if (points_.empty()) { set_error("No points..."); return CMLBA_ERR_STATE; }   // BA:759-762
+        CK(cudaSetDevice(device));
+        if (dirty) { int rc = build_device_window(); if (rc) return rc; }
+        const int n = 8 * N + 4;
+        double sc[10]; scales(sc);
+        // updateCamera -> setStateFromCamera (DSOFrame.h:143-151)
+        for (int i = 0; i < N; i++) {
+            FrameHost &f = frames_[i];
+            if (cams) {
+                Pose c;
+                for (int k = 0; k < 9; k++) c.R[k] = cams[12 * i + k];
+                for (int k = 0; k < 3; k++) c.t[k] = cams[12 * i + 9 + k];
+                double xi[6];
+                se3_log(pose_mul(c, pose_inv(f.evalpt)), xi);
+                for (int k = 0; k < 6; k++) f.state[k] = xi[k] / sc[k];
+            }
+        }
+        // computeAdjoints (BA:1062-1097); stored [h*N+t]
+        std::vector<double> AH((size_t) N * N * 64, 0.0), AT((size_t) N * N * 64, 0.0);
+        for (int h = 0; h < N; h++) for (int t = 0; t < N; t++) {
+            Pose T0 = pose_mul(frames_[t].evalpt, pose_inv(frames_[h].evalpt));
+            double adj[36]; se3_adj(T0, adj);
+            const double a_h = frames_[h].state_zero[6] * sc[6], a_t = frames_[t].state_zero[6] * sc[6];
+            const double a0 = exp(a_t - a_h) * frames_[t].exposure / frames_[h].exposure;
+            double *ah = &AH[(size_t) (h * N + t) * 64], *at = &AT[(size_t) (h * N + t) * 64];
+            for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) ah[r * 8 + c] = -adj[c * 6 + r];
+            for (int r = 0; r < 6; r++) at[r * 8 + r] = 1.0;
+            at[6 * 8 + 6] = -a0; ah[6 * 8 + 6] = a0; at[7 * 8 + 7] = -1.0; ah[7 * 8 + 7] = a0;
+            for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) { ah[r * 8 + c] *= sc[r]; at[r * 8 + c] *= sc[r]; }
+        }
+        // priors (BA:1127-1170); float settings
+        const float pa = cfg.optimize_light_a ? 1e12f : 1e14f, pb = cfg.optimize_light_b ? 1e8f : 1e14f;
+        for (auto &f : frames_) {
+            for (int k = 0; k < 8; k++) f.prior[k] = 0;
+            if (f.keyid == 0) { for (int k = 0; k < 3; k++) { f.prior[k] = 1e10f; f.prior[3 + k] = 1e11f; } f.prior[6] = 1e14f; f.prior[7] = 1e14f; }
+            else { f.prior[6] = pa; f.prior[7] = pb; }
+        }
+        // nullspaces (DSOFrame.h:160-179) stacked as computeNullspaces does (BA:2372-2414) and the projector of orthogonalize (BA:1217-1249)
+        std::vector<double> Nm((size_t) n * 7, 0.0);
+        for (int i = 0; i < N; i++) {
+            const Pose &E = frames_[i].evalpt; const Pose Ei = pose_inv(E);
+            const int o = 4 + 8 * i;
+            for (int k = 0; k < 6; k++) {
+                double eps[6] = {0, 0, 0, 0, 0, 0}, lp[6], lm[6];
+                eps[k] = 1e-3; se3_log(pose_mul(pose_mul(E, se3_exp(eps)), Ei), lp);
+                eps[k] = -1e-3; se3_log(pose_mul(pose_mul(E, se3_exp(eps)), Ei), lm);
+                for (int r = 0; r < 6; r++) Nm[(size_t) (o + r) * 7 + k] = (lp[r] - lm[r]) / 2e-3 / sc[r];
+            }
+            Pose Pp = E, Pm = E; double lp[6], lm[6];
+            for (int k = 0; k < 3; k++) { Pp.t[k] *= 1.00001; Pm.t[k] /= 1.00001; }
+            se3_log(pose_mul(Pp, Ei), lp); se3_log(pose_mul(Pm, Ei), lm);
+            for (int r = 0; r < 6; r++) Nm[(size_t) (o + r) * 7 + 6] = (lp[r] - lm[r]) / 2e-3 / sc[r];
+        }
+        for (int k = 0; k < 7; k++) {   // normalised columns
+            double s = 0; for (int r = 0; r < n; r++) s += Nm[(size_t) r * 7 + k] * Nm[(size_t) r * 7 + k];
+            s = sqrt(s); if (s > 0) for (int r = 0; r < n; r++) Nm[(size_t) r * 7 + k] /= s;
+        }
+        // thin SVD through eig(N^T N): N = U S V^T ; N N+^T = N V S^-2 V^T N^T with the cut S_i > delta * S_max
+        double G[49], V[49];
+        for (int a = 0; a < 7; a++) for (int b = 0; b < 7; b++) { double s = 0; for (int r = 0; r < n; r++) s += Nm[(size_t) r * 7 + a] * Nm[(size_t) r * 7 + b]; G[a * 7 + b] = s; }
+        jacobi_eig(7, G, V);
+        double smax = 0; for (int k = 0; k < 7; k++) smax = std::max(smax, sqrt(std::max(G[k * 8], 0.0)));
+        std::vector<double> NV((size_t) n * 7, 0.0), Pns((size_t) n * n, 0.0);
+        for (int r = 0; r < n; r++) for (int k = 0; k < 7; k++) { double s = 0; for (int a = 0; a < 7; a++) s += Nm[(size_t) r * 7 + a] * V[a * 7 + k]; NV[(size_t) r * 7 + k] = s; }
+        for (int k = 0; k < 7; k++) {
+            const double sv = sqrt(std::max(G[k * 8], 0.0));
+            if (!(sv > (double) cfg.solver_mode_delta * smax)) continue;
+            const double inv = 1.0 / (sv * sv);
+            for (int r = 0; r < n; r++) { const double a = NV[(size_t) r * 7 + k] * inv; if (a == 0) continue; for (int c = 0; c < n; c++) Pns[(size_t) r * n + c] += a * NV[(size_t) c * 7 + k]; }
+        }
+        // frames -> device
+        std::vector<FrameDev> fd(N);
+        for (int i = 0; i < N; i++) {
+            FrameHost &f = frames_[i]; FrameDev &d = fd[i];
+            memset(&d, 0, sizeof(d));
+            for (int k = 0; k < 9; k++) d.evalR[k] = f.evalpt.R[k];
+            for (int k = 0; k < 3; k++) d.evalt[k] = f.evalpt.t[k];
+            double ss[10];
+            for (int k = 0; k < 10; k++) { d.state[k] = f.state[k]; d.state_zero[k] = f.state_zero[k]; d.state_backup[k] = f.state[k]; ss[k] = sc[k] * f.state[k]; d.state_scaled[k] = ss[k]; }
+            Pose P = pose_mul(se3_exp(ss), f.evalpt);
+            f.pre = P;
+            for (int k = 0; k < 9; k++) d.preR[k] = P.R[k];
+            for (int k = 0; k < 3; k++) d.pret[k] = P.t[k];
+            for (int k = 0; k < 8; k++) d.prior[k] = f.prior[k];
+            d.exposure = f.exposure; d.energy_th = f.energy_th; d.keyid = f.keyid;
+        }
+        if ((int) HM.size() != n * n) { HM.assign((size_t) n * n, 0.0); bM.assign(n, 0.0); }
+        if (cfg.disable_marginalization) { std::fill(HM.begin(), HM.end(), 0.0); std::fill(bM.begin(), bM.end(), 0.0); }   // BA:1395-1398
+        Ctrl c; memset(&c, 0, sizeof(c));
+        c.lambda = (double) cfg.fixed_lambda;
+        const int R = dw.R, P = dw.P;
+        CK(cudaMemcpyAsync(d_frames.p, fd.data(), N * sizeof(FrameDev), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_AH.p, AH.data(), AH.size() * 8, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_AT.p, AT.data(), AT.size() * 8, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_Pns.p, Pns.data(), Pns.size() * 8, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_HM.p, HM.data(), HM.size() * 8, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_bM.p, bM.data(), bM.size() * 8, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_ctrl.p, &c, sizeof(c), cudaMemcpyHostToDevice, stream));
+        // resetOOB on every active residual (BA:766-779, DSOResidual.h:81-86)
+        if (R > 0) {
+            CK(cudaMemsetAsync(d_r_state0.p, RES_IN, R, stream)); CK(cudaMemsetAsync(d_r_state1.p, RES_IN, R, stream));
+            CK(cudaMemsetAsync(d_r_energy0.p, 0, R * 4, stream)); CK(cudaMemsetAsync(d_r_energy1.p, 0, R * 4, stream));
+            CK(cudaMemsetAsync(d_r_good0.p, 0, R, stream)); CK(cudaMemsetAsync(d_r_good1.p, 0, R, stream));
+            CK(cudaMemsetAsync(d_r_new_state.p, RES_OUTLIER, R, stream)); CK(cudaMemsetAsync(d_r_new_energy.p, 0, R * 4, stream));
+            CK(cudaMemsetAsync(d_r_new_energy_wo.p, 0, R * 4, stream)); CK(cudaMemsetAsync(d_r_alive.p, 1, R, stream));
+            CK(cudaMemsetAsync(d_r_center.p, 0, (size_t) R * 12, stream));
+        }
+        CK(cudaMemsetAsync(d_T0.p, 0, (size_t) P * N * T_STRIDE * 4, stream)); CK(cudaMemsetAsync(d_T1.p, 0, (size_t) P * N * T_STRIDE * 4, stream));
+        CK(cudaMemsetAsync(d_pt_ngood_cur.p, 0, (size_t) P * 4, stream));
+        if (want_dbg && R > 0) CK(cudaMemsetAsync(d_dbg.p, 0, (size_t) R * DBG_STRIDE * 4, stream));
+        pairs_kernel<<<(N * N + 63) / 64, 64, 0, stream>>>(dw); launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));   // host vectors above are pageable stack/heap objects
+        prepared = true;
+        return CMLBA_OK;
+    }
+
+    // ------------------------------------------------------------------ kernel sequences
+    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) NB * NB + N * ACC_N + 8 * NB + 8 * NB + 4 * NB + NB + NB + 24); }
+    size_t solve_smem() const { const int n = dw.n; return sizeof(double) * ((size_t) n * n + 3 * n + 256); }
+    size_t schur_smem() const { return sizeof(float) * ((size_t) SC_CHUNK * 8 * dw.N + SC_CHUNK * 6); }
+
+    void launch_linearize(int fix, int respect_done) {
+        if (dw.R == 0) return;
+        if (want_dbg) linearize_kernel<true><<<dw.n_lin_blocks, LIN_THREADS, 0, stream>>>(dw, fix, respect_done);
+        else linearize_kernel<false><<<dw.n_lin_blocks, LIN_THREADS, 0, stream>>>(dw, fix, respect_done);
+        launches++;
+    }
+    void launch_accumulate(int respect_done) {
+        if (dw.n_acc_chunks == 0) return;
+        accumulate_kernel<<<dw.n_acc_chunks, 128, 0, stream>>>(dw, respect_done); launches++;
+    }
+    void launch_post(int mode, int respect_done) { post_linearize_kernel<<<1, 1024, 0, stream>>>(dw, mode, respect_done); launches++; }
+    int launch_solve_sequence(int respect_done) {
+        if (dw.n_sc_chunks > 0) { schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, respect_done); launches++; }
+        stitch_kernel<<<dw.N, 256, stitch_smem(), stream>>>(dw, respect_done); launches++;
+        sum_partials_kernel<<<32, 256, 0, stream>>>(dw, respect_done); launches++;
+        if (world > 1) { int rc = allreduce_system(); if (rc) return rc; }
+        solve_kernel<<<1, 256, solve_smem(), stream>>>(dw, respect_done); launches++;
+        if (dw.P > 0) { point_step_kernel<<<dw.n_pt_blocks, 256, 0, stream>>>(dw, respect_done); launches++; }
+        return CMLBA_OK;
+    }
+
+    int allreduce_system() {
+        const size_t cnt = (size_t) 2 * dw.n * dw.n + 2 * dw.n;
+        const int rc = g_nccl.AllReduce(d_sys.p, d_sys.p, cnt, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream);
+        if (rc != 0) { set_error("ncclAllReduce failed"); return CMLBA_ERR_CUDA; }
+        return CMLBA_OK;
+    }
+
+    int run(const double *cams, int iterations, int update_points_only, cmlba_run_result *out) {
+        if (!cfg.force_accept) { set_error("forceAccept=false (step rejection) is not implemented on the device path yet"); return CMLBA_ERR_UNSUPPORTED; }
+        int rc = prepare(cams);
+        if (rc) return rc;
+        if (iterations <= 0) iterations = cfg.iterations;
+        dw.update_points_only = update_points_only ? 1 : 0;
+        const int l0 = launches;
+        CK(cudaEventRecord(ev0, stream));
+        launch_linearize(0, 0); launch_accumulate(0); launch_post(0, 0);
+        for (int it = 0; it < iterations; it++) {
+            rc = launch_solve_sequence(1); if (rc) return rc;
+            launch_linearize(0, 1); launch_accumulate(1); launch_post(1, 1);
+        }
+        set_evalpt_newest_kernel<<<1, 32, 0, stream>>>(dw); launches++;
+        pairs_kernel<<<(dw.N * dw.N + 63) / 64, 64, 0, stream>>>(dw); launches++;
+        launch_linearize(1, 0); launch_post(2, 0);
+        CK(cudaEventRecord(ev1, stream));
+        CK(cudaGetLastError());
+        rc = finish_run(out);
+        if (out) {
+            float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
+            out->gpu_ms = ms; out->kernel_launches = launches - l0;
+        }
+        return rc;
+    }
+
+    // read results back, update the host bookkeeping (the "scatter" edge of the boundary)
+    int finish_run(cmlba_run_result *out) {
+        const int N = dw.N, P = dw.P, R = dw.R;
+        std::vector<FrameDev> fd(N); Ctrl c;
+        std::vector<double> id(P); std::vector<float> idz(P), idh(P), mrb(P); std::vector<int> ng(P);
+        std::vector<uint8_t> alive(R), st0(R), st1(R); std::vector<float> en0(R), en1(R);
+        CK(cudaMemcpyAsync(fd.data(), d_frames.p, N * sizeof(FrameDev), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(&c, d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost, stream));
+        if (P) {
+            CK(cudaMemcpyAsync(id.data(), d_pt_idepth.p, P * 8, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(idz.data(), d_pt_idz.p, P * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(idh.data(), d_pt_idh.p, P * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(mrb.data(), d_pt_mrb.p, P * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(ng.data(), d_pt_num_good.p, P * 4, cudaMemcpyDeviceToHost, stream));
+        }
+        if (R) {
+            CK(cudaMemcpyAsync(alive.data(), d_r_alive.p, R, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(st0.data(), d_r_state0.p, R, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(st1.data(), d_r_state1.p, R, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(en0.data(), d_r_energy0.p, R * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(en1.data(), d_r_energy1.p, R * 4, cudaMemcpyDeviceToHost, stream));
+        }
+        CK(cudaStreamSynchronize(stream));
+        CK(cudaGetLastError());
+        double sc[10]; scales(sc);
+        for (int i = 0; i < N; i++) {
+            FrameHost &f = frames_[i]; const FrameDev &d = fd[i];
+            for (int k = 0; k < 10; k++) { f.state[k] = d.state[k]; f.state_zero[k] = d.state_zero[k]; }
+            for (int k = 0; k < 9; k++) { f.evalpt.R[k] = d.evalR[k]; f.pre.R[k] = d.preR[k]; }
+            for (int k = 0; k < 3; k++) { f.evalpt.t[k] = d.evalt[k]; f.pre.t[k] = d.pret[k]; }
+            f.energy_th = d.energy_th;
+            f.aff_a = d.state_scaled[6]; f.aff_b = d.state_scaled[7];
+        }
+        for (int i = 0; i < P; i++) {
+            PointHost &p = points_[pt_order[i]];
+            p.idepth = id[i]; p.idepth_zero = idz[i]; p.idepth_hessian = idh[i]; p.max_rel_bs = mrb[i]; p.num_good = ng[i];
+        }
+        const uint8_t *st = c.cur ? st1.data() : st0.data(); const float *en = c.cur ? en1.data() : en0.data();
+        std::vector<ResHost> keep; keep.reserve(R);
+        std::vector<int> cnt(points_.size(), 0);
+        for (int i = 0; i < R; i++) {
+            ResHost r = res_[res_order[i]];
+            r.state = st[i]; r.energy = en[i];
+            PointHost &p = points_[r.point];
+            // setResidualState (BA:1616-1620) / cleared lastResiduals of deleted residuals (BA:1630-1633)
+            for (int s = 0; s < 2; s++) if (p.last_frame[s] == r.target_id) { if (alive[i]) p.last_state[s] = r.state; else p.last_frame[s] = -1; break; }
+            if (alive[i]) { keep.push_back(r); cnt[r.point]++; }
+        }
+        outliers_.clear();
+        int nout = 0;
+        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive && cnt[i] == 0) { points_[i].alive = false; outliers_.push_back(points_[i].id); nout++; }
+        const int dropped = R - (int) keep.size();
+        res_.swap(keep);
+        if (out) {
+            out->iterations_done = c.iteration; out->num_residuals = R; out->num_dropped = dropped; out->num_outliers = nout;
+            out->energy_first = c.energy_first; out->energy_last = c.energy_last;
+        }
+        if (dropped > 0 || nout > 0) compact(); else { dirty = false; }
+        prepared = false;
+        if (c.failed) { set_error("non-finite energy or step (reference run() returns false)"); return CMLBA_ERR_NUMERIC; }
+        return CMLBA_OK;
+    }
+
+    // ------------------------------------------------------------------ named read-back (parity tests)
+    template <typename T> int copy_out(const T *dev, size_t count, void *dst, size_t cap, size_t *bytes) {
+        const size_t nb = count * sizeof(T);
+        if (bytes) *bytes = nb;
+        if (dst && cap) { CK(cudaMemcpy(dst, dev, std::min(cap, nb), cudaMemcpyDeviceToHost)); }
+        return CMLBA_OK;
+    }
+    int host_out(const void *src, size_t nb, void *dst, size_t cap, size_t *bytes) {
+        if (bytes) *bytes = nb;
+        if (dst && cap) memcpy(dst, src, std::min(cap, nb));
+        return CMLBA_OK;
+    }
+    int read(const std::string &name, void *dst, size_t cap, size_t *bytes) {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamSynchronize(stream));
+        const int N = dw.N, P = dw.P, R = dw.R, n = dw.n;
+        Ctrl c; CK(cudaMemcpy(&c, d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost));
+        const int cur = c.cur;
+        if (name == "ctrl") return host_out(&c, sizeof(c), dst, cap, bytes);
+        if (name == "pt_order") return host_out(pt_order.data(), P * sizeof(int), dst, cap, bytes);
+        if (name == "res_order") return host_out(res_order.data(), R * sizeof(int), dst, cap, bytes);
+        if (name == "res_point") { std::vector<int> v(R); for (int i = 0; i < R; i++) v[i] = res_[res_order[i]].point; return host_out(v.data(), R * sizeof(int), dst, cap, bytes); }
+        if (name == "res_point_dev") return copy_out(d_r_point.p, R, dst, cap, bytes);
+        if (name == "res_host") return copy_out(d_r_host.p, R, dst, cap, bytes);
+        if (name == "res_target") return copy_out(d_r_target.p, R, dst, cap, bytes);
+        if (name == "res_state") return copy_out(cur ? d_r_state1.p : d_r_state0.p, R, dst, cap, bytes);
+        if (name == "res_state_cand") return copy_out(cur ? d_r_state0.p : d_r_state1.p, R, dst, cap, bytes);
+        if (name == "res_energy") return copy_out(cur ? d_r_energy1.p : d_r_energy0.p, R, dst, cap, bytes);
+        if (name == "res_good") return copy_out(cur ? d_r_good1.p : d_r_good0.p, R, dst, cap, bytes);
+        if (name == "res_good_cand") return copy_out(cur ? d_r_good0.p : d_r_good1.p, R, dst, cap, bytes);
+        if (name == "res_new_state") return copy_out(d_r_new_state.p, R, dst, cap, bytes);
+        if (name == "res_new_energy") return copy_out(d_r_new_energy.p, R, dst, cap, bytes);
+        if (name == "res_new_energy_wo") return copy_out(d_r_new_energy_wo.p, R, dst, cap, bytes);
+        if (name == "res_alive") return copy_out(d_r_alive.p, R, dst, cap, bytes);
+        if (name == "res_center") return copy_out(d_r_center.p, (size_t) R * 3, dst, cap, bytes);
+        if (name == "rj") return copy_out(d_rj.p, (size_t) R * RJ_STRIDE, dst, cap, bytes);
+        if (name == "dbg") { if (!want_dbg) { set_error("debug dump not enabled (cmlba_read(\"enable_dbg\") first)"); return CMLBA_ERR_STATE; } return copy_out(d_dbg.p, (size_t) R * DBG_STRIDE, dst, cap, bytes); }
+        if (name == "enable_dbg") { want_dbg = true; dirty = true; prepared = false; if (bytes) *bytes = 0; return CMLBA_OK; }
+        if (name == "T") return copy_out(cur ? d_T1.p : d_T0.p, (size_t) P * N * T_STRIDE, dst, cap, bytes);
+        if (name == "T_cand") return copy_out(cur ? d_T0.p : d_T1.p, (size_t) P * N * T_STRIDE, dst, cap, bytes);
+        if (name == "pt_idepth") return copy_out(d_pt_idepth.p, P, dst, cap, bytes);
+        if (name == "pt_step") return copy_out(d_pt_step.p, P, dst, cap, bytes);
+        if (name == "pt_Hdd") return copy_out(d_pt_Hdd.p, P, dst, cap, bytes);
+        if (name == "pt_bd") return copy_out(d_pt_bd.p, P, dst, cap, bytes);
+        if (name == "pt_Hcd") return copy_out(d_pt_Hcd.p, (size_t) P * 4, dst, cap, bytes);
+        if (name == "pt_HdiF") return copy_out(d_pt_HdiF.p, P, dst, cap, bytes);
+        if (name == "pt_bdSumF") return copy_out(d_pt_bdSumF.p, P, dst, cap, bytes);
+        if (name == "pt_idepth_hessian") return copy_out(d_pt_idh.p, P, dst, cap, bytes);
+        if (name == "pt_max_rel_baseline") return copy_out(d_pt_mrb.p, P, dst, cap, bytes);
+        if (name == "pt_num_good") return copy_out(d_pt_num_good.p, P, dst, cap, bytes);
+        if (name == "pt_colors") return copy_out(d_pt_colors.p, (size_t) P * 8, dst, cap, bytes);
+        if (name == "pt_weights") return copy_out(d_pt_weights.p, (size_t) P * 8, dst, cap, bytes);
+        if (name == "frames") return copy_out(d_frames.p, N, dst, cap, bytes);
+        if (name == "pairs") return copy_out(d_pairs.p, (size_t) N * N, dst, cap, bytes);
+        if (name == "AH") return copy_out(d_AH.p, (size_t) N * N * 64, dst, cap, bytes);
+        if (name == "AT") return copy_out(d_AT.p, (size_t) N * N * 64, dst, cap, bytes);
+        if (name == "Pns") return copy_out(d_Pns.p, (size_t) n * n, dst, cap, bytes);
+        if (name == "sys") return copy_out(d_sys.p, (size_t) 2 * n * n + 2 * n, dst, cap, bytes);
+        if (name == "x") return copy_out(d_x.p, n, dst, cap, bytes);
+        if (name == "xAd") return copy_out(d_xAd.p, (size_t) N * N * 8, dst, cap, bytes);
+        if (name == "acc" || name == "acc_cand") {   // per bin (t*N+h) packed 96 doubles, chunk partials summed in order
+            const bool cand = name == "acc_cand";
+            const float *src = (cur ^ (cand ? 1 : 0)) ? d_acc1.p : d_acc0.p;
+            std::vector<float> part((size_t) n_acc_chunks * ACC_N);
+            if (n_acc_chunks) CK(cudaMemcpy(part.data(), src, part.size() * 4, cudaMemcpyDeviceToHost));
+            std::vector<double> acc((size_t) N * N * ACC_N, 0.0);
+            for (int b = 0; b < N * N; b++) for (int ch = h_bin_chunk_begin[b]; ch < h_bin_chunk_begin[b + 1]; ch++) for (int k = 0; k < ACC_N; k++) acc[(size_t) b * ACC_N + k] += part[(size_t) ch * ACC_N + k];
+            return host_out(acc.data(), acc.size() * 8, dst, cap, bytes);
+        }
+        if (name == "sc") {   // per host: D[(8N)^2] E[32N] EB[8N] Hcc[16] bc[4] doubles
+            const int NB = 8 * N, tot = NB * NB + NB * 5 + 20;
+            std::vector<float> part((size_t) n_sc_chunks * dw.sc_stride);
+            if (n_sc_chunks) CK(cudaMemcpy(part.data(), d_sc_part.p, part.size() * 4, cudaMemcpyDeviceToHost));
+            std::vector<double> s((size_t) N * tot, 0.0);
+            for (int h = 0; h < N; h++) for (int ch = h_host_chunk_begin[h]; ch < h_host_chunk_begin[h + 1]; ch++) for (int k = 0; k < tot; k++) s[(size_t) h * tot + k] += part[(size_t) ch * dw.sc_stride + k];
+            return host_out(s.data(), s.size() * 8, dst, cap, bytes);
+        }
+        set_error("unknown buffer name: " + name);
+        return CMLBA_ERR_ARG;
+    }
+};
+
+}  // namespace cmlba
+
+// =================================================================================================
+using cmlba::Engine;
+struct cmlba_handle { Engine eng; };
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+const char *cmlba_version(void) { return "libcmlba 0.1 sm_100a"; }
+
+int cmlba_default_config(cmlba_config *c) {
+    if (!c) return CMLBA_ERR_ARG;
+    c->iterations = 4; c->huber_threshold = 9.f; c->outlier_th_sum = 2500.f; c->th_opt_iterations = 1.2f;
+    c->scale_rotation = 1.f; c->scale_translation = 0.5f; c->scale_light_a = 10.f; c->scale_light_b = 1000.f; c->scale_f = 50.f; c->scale_c = 50.f;
+    c->force_accept = 1; c->fix_lambda = 1; c->fixed_lambda = 1e-5f; c->idepth_fix_prior = 2500; c->solver_mode_delta = 1e-5f;
+    c->optimize_light_a = 1; c->optimize_light_b = 1; c->disable_marginalization = 1; c->max_frames = 6;
+    return CMLBA_OK;
+}
+
+int cmlba_create(const cmlba_config *cfg, int device, cmlba_handle **out) {
+    if (!out) return CMLBA_ERR_ARG;
+    *out = nullptr;
+    cmlba_handle *h = new (std::nothrow) cmlba_handle;
+    if (!h) return CMLBA_ERR_ARG;
+    if (cfg) h->eng.cfg = *cfg; else cmlba_default_config(&h->eng.cfg);
+    h->eng.device = device;
+    int rc = h->eng.init();
+    if (rc) { g_create_error = h->eng.err; delete h; return rc; }
+    *out = h;
+    return CMLBA_OK;
+}
+
+int cmlba_destroy(cmlba_handle *h) { delete h; return CMLBA_OK; }
+
+const char *cmlba_last_error(const cmlba_handle *h) { return h ? h->eng.err.c_str() : g_create_error.c_str(); }
+
+#define HCHK if (!h) return CMLBA_ERR_ARG
+
+int cmlba_set_calib(cmlba_handle *h, double fx, double fy, double cx, double cy, int w, int hh) { HCHK; return h->eng.set_calib(fx, fy, cx, cy, w, hh); }
+int cmlba_add_frame(cmlba_handle *h, int64_t id, const double w2c[12], double a, double b, double exposure, const float *grad, int is_init) { HCHK; return h->eng.add_frame(id, w2c, a, b, exposure, grad, is_init); }
+int cmlba_add_points(cmlba_handle *h, int n, const int64_t *pid, const int64_t *host, const float *xy, const double *idepth) { HCHK; return h->eng.add_points(n, pid, host, xy, idepth); }
+int cmlba_remove_point(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove_point(id); }
+int cmlba_remove_frame(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove_frame(id); }
+int cmlba_run(cmlba_handle *h, const double *cams, int iterations, int upo, cmlba_run_result *r) { HCHK; return h->eng.run(cams, iterations, upo, r); }
+int cmlba_num_frames(const cmlba_handle *h) { return h ? (int) h->eng.frames_.size() : CMLBA_ERR_ARG; }
+int cmlba_num_points(const cmlba_handle *h) { return h ? (int) h->eng.points_.size() : CMLBA_ERR_ARG; }
+int cmlba_num_residuals(const cmlba_handle *h) { return h ? (int) h->eng.res_.size() : CMLBA_ERR_ARG; }
+
+int cmlba_get_frames(const cmlba_handle *h, int64_t *id, double *w2c, double *ab, double *state, double *evalpt, double *th) {
+    HCHK;
+    const auto &fr = h->eng.frames_;
+    for (size_t i = 0; i < fr.size(); i++) {
+        if (id) id[i] = fr[i].id;
+        if (w2c) { memcpy(w2c + 12 * i, fr[i].pre.R, 72); memcpy(w2c + 12 * i + 9, fr[i].pre.t, 24); }
+        if (ab) { ab[2 * i] = fr[i].aff_a; ab[2 * i + 1] = fr[i].aff_b; }
+        if (state) memcpy(state + 10 * i, fr[i].state, 80);
+        if (evalpt) { memcpy(evalpt + 12 * i, fr[i].evalpt.R, 72); memcpy(evalpt + 12 * i + 9, fr[i].evalpt.t, 24); }
+        if (th) th[i] = fr[i].energy_th;
+    }
+    return CMLBA_OK;
+}
+
+int cmlba_get_points(const cmlba_handle *h, int64_t *id, double *idepth, double *unc, float *idh, float *mrb, int32_t *ng, int32_t *gft) {
+    HCHK;
+    const auto &pts = h->eng.points_;
+    for (size_t i = 0; i < pts.size(); i++) {
+        const auto &p = pts[i];
+        if (id) id[i] = p.id;
+        if (idepth) idepth[i] = p.idepth;
+        if (unc) unc[i] = 1.0 / ((double) p.idepth_hessian + 0.01);    // updatePointUncertainty (DSOPoint.h:107-118)
+        if (idh) idh[i] = p.idepth_hessian;
+        if (mrb) mrb[i] = p.max_rel_bs;
+        if (ng) ng[i] = p.num_good;
+        if (gft) gft[i] = (p.last_frame[0] >= 0 && p.last_state[0] == CMLBA_RES_IN) ? 1 : 0;   // getGoodPointsForTracking (BA.h:76-85)
+    }
+    return CMLBA_OK;
+}
+
+int cmlba_get_outliers(const cmlba_handle *h, int64_t *id, int *n) {
+    HCHK; if (!n) return CMLBA_ERR_ARG;
+    const auto &o = h->eng.outliers_;
+    const int cap = *n;
+    *n = (int) o.size();
+    if (id) for (int i = 0; i < cap && i < (int) o.size(); i++) id[i] = o[i];
+    return CMLBA_OK;
+}
+
+int cmlba_get_residuals(const cmlba_handle *h, int64_t *pid, int64_t *tid, int32_t *state, double *energy) {
+    HCHK;
+    const auto &rs = h->eng.res_;
+    for (size_t i = 0; i < rs.size(); i++) {
+        if (pid) pid[i] = h->eng.points_[rs[i].point].id;
+        if (tid) tid[i] = rs[i].target_id;
+        if (state) state[i] = rs[i].state;
+        if (energy) energy[i] = rs[i].energy;
+    }
+    return CMLBA_OK;
+}
+
+// ---- stage entry points
+int cmlba_prepare(cmlba_handle *h, const double *cams) { HCHK; return h->eng.prepare(cams); }
+
+int cmlba_linearize(cmlba_handle *h, int fix, double *energy) {
+    HCHK; Engine &e = h->eng;
+    if (!e.prepared) { e.set_error("cmlba_prepare first"); return CMLBA_ERR_STATE; }
+    cudaSetDevice(e.device);
+    if (fix) {
+        cmlba::set_evalpt_newest_kernel<<<1, 32, 0, e.stream>>>(e.dw);
+        cmlba::pairs_kernel<<<(e.dw.N * e.dw.N + 63) / 64, 64, 0, e.stream>>>(e.dw);
+        e.launch_linearize(1, 0); e.launch_post(2, 0);
+    } else {
+        e.launch_linearize(0, 0); e.launch_accumulate(0); e.launch_post(3, 0);
+    }
+    cmlba::Ctrl c;
+    if (cudaMemcpyAsync(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost, e.stream) != cudaSuccess || cudaStreamSynchronize(e.stream) != cudaSuccess) {
+        e.set_error(std::string("linearize: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA;
+    }
+    if (energy) *energy = c.energy_new;
+    return c.failed ? CMLBA_ERR_NUMERIC : CMLBA_OK;
+}
+
+int cmlba_apply(cmlba_handle *h) {
+    HCHK; Engine &e = h->eng;
+    if (!e.prepared) { e.set_error("cmlba_prepare first"); return CMLBA_ERR_STATE; }
+    cudaSetDevice(e.device);
+    cmlba::Ctrl c;
+    cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost);
+    c.cur ^= 1; c.energy_last = c.energy_new;
+    cudaMemcpy(e.d_ctrl.p, &c, sizeof(c), cudaMemcpyHostToDevice);
+    return CMLBA_OK;
+}
+
+int cmlba_solve(cmlba_handle *h, int iteration) {
+    HCHK; Engine &e = h->eng;
+    if (!e.prepared) { e.set_error("cmlba_prepare first"); return CMLBA_ERR_STATE; }
+    cudaSetDevice(e.device);
+    cmlba::Ctrl c;
+    cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost);
+    c.iteration = iteration;
+    cudaMemcpy(e.d_ctrl.p, &c, sizeof(c), cudaMemcpyHostToDevice);
+    int rc = e.launch_solve_sequence(0);
+    if (rc) return rc;
+    if (cudaStreamSynchronize(e.stream) != cudaSuccess) { e.set_error(std::string("solve: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA; }
+    cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost);
+    return c.failed ? CMLBA_ERR_NUMERIC : CMLBA_OK;
+}
+
+int cmlba_step(cmlba_handle *h, int update_points_only, int *can_break) {
+    HCHK; Engine &e = h->eng;
+    (void) update_points_only;   // the step is applied on the device inside cmlba_solve (solve_kernel / point_step_kernel)
+    cmlba::Ctrl c;
+    cudaSetDevice(e.device);
+    cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost);
+    if (can_break) *can_break = c.canbreak;
+    return CMLBA_OK;
+}
+
+int cmlba_read(cmlba_handle *h, const char *name, void *dst, size_t cap, size_t *bytes) { HCHK; if (!name) return CMLBA_ERR_ARG; return h->eng.read(name, dst, cap, bytes); }
+
+int cmlba_nccl_unique_id(void *uid) {
+    std::string err;
+    if (!uid) return CMLBA_ERR_ARG;
+    if (!cmlba::g_nccl.load(err)) { g_create_error = err; return CMLBA_ERR_UNSUPPORTED; }
+    return cmlba::g_nccl.GetUniqueId(uid) == 0 ? CMLBA_OK : CMLBA_ERR_CUDA;
+}
+
+int cmlba_comm_init(cmlba_handle *h, const void *uid, int rank, int world) {
+    HCHK; Engine &e = h->eng;
+    if (!uid || world < 1 || rank < 0 || rank >= world) { e.set_error("bad communicator arguments"); return CMLBA_ERR_ARG; }
+    if (world == 1) { e.rank = 0; e.world = 1; return CMLBA_OK; }
+    if (!cmlba::g_nccl.load(e.err)) return CMLBA_ERR_UNSUPPORTED;
+    cudaSetDevice(e.device);
+    cmlba::NcclUid id;
+    memcpy(id.b, uid, 128);
+    if (cmlba::g_nccl.CommInitRank(&e.comm, world, id, rank) != 0) { e.set_error("ncclCommInitRank failed"); return CMLBA_ERR_CUDA; }
+    e.rank = rank; e.world = world;
+    return CMLBA_OK;
+}
+
+}  // extern "C"

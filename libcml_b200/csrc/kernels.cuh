@@ -1,0 +1,949 @@
+// kernels.cuh -- hand-written sm_100a kernels of the photometric-BA hot path.
+//
+// Reference behaviour restated on the device (file:line under /root/reference/src/cml):
+//   linearize_kernel    optimization/dso/DSOBundleAdjustment.cpp:62-316 (linearize) + :2051-2093 (applyRes, as a
+//                       double-buffered candidate) + :1568-1599 (fixLinearization bookkeeping)
+//   accumulate_kernel   :1648-1779 (addToHessianTop ACTIVE) + MatrixAccumulators.h:776-937 (AccumulatorApprox)
+//   schur_kernel        :1880-1937 (addToHessianSC)
+//   stitch_kernel       :1781-1878 (stitchDoubleTop) + :1939-2043 (stitchDoubleSC), one CTA per host frame
+//   solve_kernel        :1284-1337 (solveLevenbergMarquardt) + :1196-1261 (orthogonalize) + :1427-1451 (frame steps, xAd)
+//                       + DSOFrame.h:110-124 (setState) + :259-273 (pair precompute)
+//   point_step_kernel   :1455-1487 (point steps) + :976-1026 (doStepFromBackup, point part and convergence test)
+//   post_linearize_kernel  :2419-2464 (setNewFrameEnergyTH) + run() accept bookkeeping :843-879
+// No tensor cores: there is no dense contraction on this path (north_star).  All cross-thread reductions
+// use fixed-order trees, so results are bitwise reproducible run to run.
+#pragma once
+#include "dev_types.h"
+#include "se3.h"
+
+namespace cmlba {
+
+constexpr int DBG_STRIDE = 52;  // resF[8] JIdx[16] JabF[16] Jpdd[2] JIdx2[3] JabJIdx[4] Jab2[3]
+
+__constant__ int c_sx[8] = {0, -1, 1, -2, 0, 2, -1, 0};   // PredefinedPattern::star8 (types.h:1395-1407)
+__constant__ int c_sy[8] = {-2, -1, -1, 0, 0, 0, 1, 2};
+__constant__ uchar4 c_acc_ofs[ACC_N];                      // smem-record offsets of the two products of every 13x13 entry
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Frame state -> PRE_worldToCam (DSOFrame::setState, DSOFrame.h:110-124)
+__device__ inline void frame_set_state(FrameDev &f, const double *state, const DevWin &w) {
+    const double sc[10] = {w.scaleT, w.scaleT, w.scaleT, w.scaleR, w.scaleR, w.scaleR, w.scaleA, w.scaleB, w.scaleA, w.scaleB};
+    for (int k = 0; k < 10; k++) { f.state[k] = state[k]; f.state_scaled[k] = sc[k] * state[k]; }
+    Pose E; for (int k = 0; k < 9; k++) E.R[k] = f.evalR[k]; for (int k = 0; k < 3; k++) E.t[k] = f.evalt[k];
+    Pose P = pose_mul(se3_exp(f.state_scaled), E);
+    for (int k = 0; k < 9; k++) f.preR[k] = P.R[k];
+    for (int k = 0; k < 3; k++) f.pret[k] = P.t[k];
+}
+
+// DSOFramePrecomputed::precompute (DSOFrame.h:259-273) for pair (h,t)
+__device__ inline void pair_precompute(const DevWin &w, int h, int t) {
+    const FrameDev &fh = w.frames[h], &ft = w.frames[t];
+    PairPre &pp = w.pairs[h * w.N + t];
+    Pose Ph, Pt, Eh, Et;
+    for (int k = 0; k < 9; k++) { Ph.R[k] = fh.preR[k]; Pt.R[k] = ft.preR[k]; Eh.R[k] = fh.evalR[k]; Et.R[k] = ft.evalR[k]; }
+    for (int k = 0; k < 3; k++) { Ph.t[k] = fh.pret[k]; Pt.t[k] = ft.pret[k]; Eh.t[k] = fh.evalt[k]; Et.t[k] = ft.evalt[k]; }
+    Pose T = pose_mul(Pt, pose_inv(Ph));
+    Pose T0 = pose_mul(Et, pose_inv(Eh));
+    for (int k = 0; k < 9; k++) { pp.R[k] = T.R[k]; pp.R0[k] = T0.R[k]; }
+    for (int k = 0; k < 3; k++) { pp.t[k] = T.t[k]; pp.t0[k] = T0.t[k]; }
+    // aff_g2l() = (ab_exposure, state_scaled[6], state_scaled[7]); Exposure::to (map/Exposure.h:119-123)
+    double a = exp(ft.state_scaled[6] - fh.state_scaled[6]) * ft.exposure / fh.exposure;
+    pp.a = a;
+    pp.b = ft.state_scaled[7] - a * fh.state_scaled[7];
+    pp.b0 = (float) (fh.state_zero[7] * (double) w.scaleB);
+    pp.pad = 0.f;
+}
+
+__global__ void pairs_kernel(const DevWin w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.N * w.N) pair_precompute(w, i / w.N, i % w.N);
+}
+
+// run() epilogue BA:885-889: newest frame gets a new FEJ evaluation point, then pairs are refreshed
+__global__ void set_evalpt_newest_kernel(const DevWin w) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        FrameDev &f = w.frames[w.N - 1];
+        for (int k = 0; k < 9; k++) f.evalR[k] = f.preR[k];
+        for (int k = 0; k < 3; k++) f.evalt[k] = f.pret[k];
+        double nz[10];
+        for (int k = 0; k < 10; k++) nz[k] = 0.0;
+        nz[6] = f.state[6]; nz[7] = f.state[7];
+        frame_set_state(f, nz, w);
+        for (int k = 0; k < 10; k++) f.state_zero[k] = nz[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// HOT LOOP 1: one thread per residual.  Projection in fp64 (the reference's scalar_t), sampling and
+// Jacobians in fp32, exactly the reference's mixed precision.  Texels are float4 (I,dx,dy,0): one
+// 128-bit read-only load per bilinear tap, 32 independent loads in flight per thread.
+template <bool kDump>
+__global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, const int fix, const int respect_done) {
+    Ctrl *ctrl = w.ctrl;
+    if (respect_done && ctrl->done) return;
+    const int cur = ctrl->cur, nxt = cur ^ 1;
+    const int r = blockIdx.x * LIN_THREADS + threadIdx.x;
+    double ret = 0.0;
+    if (r < w.R && w.r_alive[r]) {
+        const int p = w.r_point[r];
+        const int h = w.r_host[r], t = w.r_target[r];
+        const uint8_t st = w.r_state[cur][r];
+        const float e_old = w.r_energy[cur][r];
+        uint8_t st_out = st;
+        float e_out = e_old;
+        bool good = false;
+        float rec[RJ_STRIDE];
+        float trow[T_STRIDE];
+#pragma unroll
+        for (int k = 0; k < RJ_STRIDE; k++) rec[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < T_STRIDE; k++) trow[k] = 0.f;
+        float neo = -1.f;                        // state_NewEnergyWithOutlier = -1 (BA:66)
+        uint8_t nst = w.r_new_state[r];
+        float ne = w.r_new_energy[r];
+        ret = (double) e_old;                    // every early exit returns state_energy
+
+        if (st != RES_OOB) {
+            const PairPre &pp = w.pairs[h * w.N + t];
+            const double rho = w.pt_idepth[p];
+            const double xc = (double) w.pt_x[p], yc = (double) w.pt_y[p];
+            const double Wm2 = (double) ((float) w.W - 2.f), Hm2 = (double) ((float) w.H - 2.f);
+            const double R0 = pp.R[0], R1 = pp.R[1], R2 = pp.R[2], R3 = pp.R[3], R4 = pp.R[4], R5 = pp.R[5], R6 = pp.R[6], R7 = pp.R[7], R8 = pp.R[8];
+            const double tx = pp.t[0] * rho, ty = pp.t[1] * rho, tz = pp.t[2] * rho;
+            float qx[8], qy[8];
+            bool inb = true;
+            double Pc0 = 0, Pc1 = 0, Pc2 = 1, Kuc = 0, Kvc = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const double kx = (xc + (double) c_sx[i] - w.cx) * w.fxi;
+                const double ky = (yc + (double) c_sy[i] - w.cy) * w.fyi;
+                const double P0 = R0 * kx + R1 * ky + R2 + tx;
+                const double P1 = R3 * kx + R4 * ky + R5 + ty;
+                const double P2 = R6 * kx + R7 * ky + R8 + tz;
+                const double Ku = (P0 / P2) * w.fx + w.cx;
+                const double Kv = (P1 / P2) * w.fy + w.cy;
+                inb = inb && (Ku >= 2.0 && Kv >= 2.0 && Ku < Wm2 && Kv < Hm2);
+                qx[i] = (float) Ku; qy[i] = (float) Kv;
+                if (i == 4) { Pc0 = P0; Pc1 = P1; Pc2 = P2; Kuc = Ku; Kvc = Kv; }
+            }
+            const bool center_in = (Kuc >= 2.0 && Kvc >= 2.0 && Kuc < Wm2 && Kvc < Hm2);
+            const float drescale = (float) (1.0 / Pc2);
+            const float new_idepth = (float) ((double) drescale * rho);
+            if (center_in) {   // setCenterProjectedTo (BA:131)
+                w.r_center[r * 3 + 0] = (float) Kuc; w.r_center[r * 3 + 1] = (float) Kvc; w.r_center[r * 3 + 2] = new_idepth;
+            }
+            if (!inb) {
+                nst = RES_OOB;                   // setNewState(OOB) (BA:116, 210); state_NewEnergy keeps its old value
+            } else {
+                // ---- 8 x bilinear sample of the target image (image/Array2D.h:265-286)
+                const float4 *__restrict__ img = w.img[t];
+                float4 tap[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int ix = (int) qx[i], iy = (int) qy[i];
+                    const float4 *q = img + (size_t) iy * w.W + ix;
+                    tap[i][0] = __ldg(q); tap[i][1] = __ldg(q + 1); tap[i][2] = __ldg(q + w.W); tap[i][3] = __ldg(q + w.W + 1);
+                }
+                const float4 *colp = reinterpret_cast<const float4 *>(w.pt_colors + (size_t) p * 8);
+                const float4 *wtp = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
+                const float4 c0 = __ldg(colp), c1 = __ldg(colp + 1), w0 = __ldg(wtp), w1 = __ldg(wtp + 1);
+                const float col[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const float wts[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                const float b0 = pp.b0;
+                float J00 = 0, J11 = 0, J10 = 0, A00 = 0, A01 = 0, A10 = 0, A11 = 0, B00 = 0, B01 = 0, B11 = 0, wJI2 = 0, E = 0;
+                float JIr0 = 0, JIr1 = 0, Jabr0 = 0, Jabr1 = 0, rr = 0;
+                bool finite = true;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int ix = (int) qx[i], iy = (int) qy[i];
+                    const float dx = qx[i] - (float) ix, dy = qy[i] - (float) iy;
+                    const float dxdy = dx * dy;
+                    const float w00 = 1.f - dx - dy + dxdy, w10 = dx - dxdy, w01 = dy - dxdy, w11 = dxdy;
+                    const float I = tap[i][0].x * w00 + tap[i][1].x * w10 + tap[i][2].x * w01 + tap[i][3].x * w11;
+                    const float gx = tap[i][0].y * w00 + tap[i][1].y * w10 + tap[i][2].y * w01 + tap[i][3].y * w11;
+                    const float gy = tap[i][0].z * w00 + tap[i][1].z * w10 + tap[i][2].z * w01 + tap[i][3].z * w11;
+                    finite = finite && isfinite(I) && isfinite(gx) && isfinite(gy);
+                    const float refReal = (float) (pp.a * (double) col[i] + pp.b);     // exposureTransition (BA:229)
+                    const float res = I - refReal;
+                    const float ar = fabsf(res);
+                    float hw = ar < w.huber ? 1.f : w.huber / ar;                      // BA:233
+                    float wg = sqrtf(w.cth / (w.cth + (gx * gx + gy * gy)));           // BA:234
+                    wg = 0.5f * (wg + wts[i]);                                         // BA:235
+                    E += wg * wg * hw * res * res * (2.f - hw);                        // BA:237
+                    if (hw < 1.f) hw = sqrtf(hw);
+                    hw = hw * wg;
+                    const float h1 = gx * hw, h2 = gy * hw, drdA = I - b0;
+                    const float rF = res * hw;
+                    const float ja = (w.optA ? drdA * hw : 0.f), jb = (w.optB ? hw : 0.f);   // BA:273-278 (zeroed after the sums below)
+                    J00 += h1 * h1; J11 += h2 * h2; J10 += h1 * h2;
+                    A00 += drdA * hw * h1; A01 += drdA * hw * h2; A10 += hw * h1; A11 += hw * h2;
+                    B00 += drdA * drdA * hw * hw; B01 += drdA * hw * hw; B11 += hw * hw;
+                    wJI2 += hw * hw * (h1 * h1 + h2 * h2);
+                    JIr0 += rF * h1; JIr1 += rF * h2; Jabr0 += rF * ja; Jabr1 += rF * jb; rr += rF * rF;   // BA:1722-1729
+                    if (kDump) {
+                        float *d = w.dbg + (size_t) r * DBG_STRIDE;
+                        d[i] = rF; d[8 + i] = h1; d[16 + i] = h2; d[24 + i] = ja; d[32 + i] = jb;
+                    }
+                }
+                if (!finite) {
+                    // BA:220-223 sets the *committed* state to OOB.  (The reference leaves a stale isActiveAndIsGoodNEW
+                    // behind in that case; only reachable with NaN/Inf texels, we clear it.)
+                    st_out = RES_OOB;
+                } else if (!isfinite(E)) {
+                    nst = RES_OOB;               // BA:297-300
+                } else {
+                    neo = E;
+                    const float th = fmaxf(w.frames[h].energy_th, w.frames[t].energy_th);
+                    if (E > th || wJI2 < 2.f) { E = th; nst = RES_OUTLIER; } else nst = RES_IN;   // BA:303-311
+                    ne = E;
+                    ret = (double) E;
+                    if (nst == RES_IN) {
+                        // ---- geometric Jacobians at the FEJ point (BA:120-188); note u,v are the UN-normalised P.xy (BA:121-122)
+                        const float u = (float) Pc0, v = (float) Pc1;
+                        const float fxf = (float) w.fx, fyf = (float) w.fy;
+                        const double ud = (double) u, vd = (double) v, dr = (double) drescale;
+                        const double klx = (xc - w.cx) * w.fxi, kly = (yc - w.cy) * w.fyi;      // KliP
+                        const float Jpdd0 = (float) (dr * (pp.t0[0] - pp.t0[2] * ud) * (double) fxf);
+                        const float Jpdd1 = (float) (dr * (pp.t0[1] - pp.t0[2] * vd) * (double) fyf);
+                        double dCx[4], dCy[4];
+                        dCx[2] = dr * (pp.R0[6] * ud - pp.R0[0]);
+                        dCx[3] = (double) (fxf * drescale) * (pp.R0[7] * ud - pp.R0[1]) / (double) fyf;
+                        dCx[0] = klx * dCx[2]; dCx[1] = kly * dCx[3];
+                        dCy[2] = (double) (fyf * drescale) * (pp.R0[6] * vd - pp.R0[3]) / (double) fxf;
+                        dCy[3] = dr * (pp.R0[7] * vd - pp.R0[4]);
+                        dCy[0] = klx * dCy[2]; dCy[1] = kly * dCy[3];
+                        const double sF = (double) w.scaleF, sC = (double) w.scaleC;
+                        dCx[0] = (dCx[0] + ud) * sF; dCx[1] *= sF; dCx[2] = (dCx[2] + 1.0) * sC; dCx[3] *= sC;
+                        dCy[0] *= sF; dCy[1] = (dCy[1] + vd) * sF; dCy[2] *= sC; dCy[3] = (dCy[3] + 1.0) * sC;
+                        // record: x = [Jpdc_x | Jpdxi_x], y = [Jpdc_y | Jpdxi_y]
+                        rec[0] = (float) dCx[0]; rec[1] = (float) dCx[1]; rec[2] = (float) dCx[2]; rec[3] = (float) dCx[3];
+                        rec[4] = new_idepth * fxf; rec[5] = 0.f; rec[6] = -new_idepth * u * fxf; rec[7] = -u * v * fxf; rec[8] = (1.f + u * u) * fxf; rec[9] = -v * fxf;
+                        rec[10] = (float) dCy[0]; rec[11] = (float) dCy[1]; rec[12] = (float) dCy[2]; rec[13] = (float) dCy[3];
+                        rec[14] = 0.f; rec[15] = new_idepth * fyf; rec[16] = -new_idepth * v * fyf; rec[17] = -(1.f + v * v) * fyf; rec[18] = u * v * fyf; rec[19] = u * fyf;
+                        rec[20] = J00; rec[21] = J10; rec[22] = J11;                    // JIdx2
+                        rec[23] = A00; rec[24] = A10; rec[25] = JIr0;                   // x-multipliers of columns a, b, r (BA:1740-1745)
+                        rec[26] = A01; rec[27] = A11; rec[28] = JIr1;                   // y-multipliers
+                        rec[29] = B00; rec[30] = B01; rec[31] = Jabr0; rec[32] = B11; rec[33] = Jabr1; rec[34] = rr;   // BA:1736-1738
+                        // applyRes (BA:2066-2080) and the per-point sums of addToHessianTop (BA:1747-1750)
+                        const float v0 = J00 * Jpdd0 + J10 * Jpdd1, v1 = J10 * Jpdd0 + J11 * Jpdd1;
+#pragma unroll
+                        for (int k = 0; k < 6; k++) trow[k] = rec[4 + k] * v0 + rec[14 + k] * v1;
+                        trow[6] = A00 * Jpdd0 + A01 * Jpdd1;
+                        trow[7] = A10 * Jpdd0 + A11 * Jpdd1;
+                        trow[8] = JIr0 * Jpdd0 + JIr1 * Jpdd1;                          // bd
+                        trow[9] = v0 * Jpdd0 + v1 * Jpdd1;                              // Hdd
+#pragma unroll
+                        for (int k = 0; k < 4; k++) trow[10 + k] = rec[k] * v0 + rec[10 + k] * v1;   // Hcd
+                        trow[14] = 1.f;
+                        good = true;
+                        if (kDump) {
+                            float *d = w.dbg + (size_t) r * DBG_STRIDE;
+                            d[40] = Jpdd0; d[41] = Jpdd1; d[42] = J00; d[43] = J10; d[44] = J11;
+                            d[45] = A00; d[46] = A01; d[47] = A10; d[48] = A11; d[49] = B00; d[50] = B01; d[51] = B11;
+                        }
+                        if (fix) {   // BA:1571-1592: relative baseline, numGoodResiduals
+                            const double Rk0 = R0 * klx + R1 * kly + R2, Rk1 = R3 * klx + R4 * kly + R5, Rk2 = R6 * klx + R7 * kly + R8;
+                            const double ix_ = (Rk0 / Rk2) * w.fx + w.cx, iy_ = (Rk1 / Rk2) * w.fy + w.cy;
+                            const double ddx = ix_ - Kuc, ddy = iy_ - Kvc;
+                            const float relBS = (float) (0.01 * sqrt(ddx * ddx + ddy * ddy));
+                            atomicMax(reinterpret_cast<int *>(w.pt_max_rel_bs + p), __float_as_int(relBS));
+                            atomicAdd(w.pt_num_good + p, 1);
+                        }
+                    }
+                }
+            }
+            // applyRes (BA:2051-2093), as the candidate that becomes current when the step is accepted
+            if (st_out != RES_OOB) { st_out = nst; e_out = ne; }
+        }
+        w.r_new_state[r] = nst; w.r_new_energy[r] = ne; w.r_new_energy_wo[r] = neo;
+        w.r_state[nxt][r] = st_out; w.r_energy[nxt][r] = e_out; w.r_good[nxt][r] = good ? 1 : 0;
+        float4 *rj4 = reinterpret_cast<float4 *>(w.rj + (size_t) r * RJ_STRIDE);
+#pragma unroll
+        for (int k = 0; k < RJ_STRIDE / 4; k++) rj4[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+        float4 *t4 = reinterpret_cast<float4 *>(w.T[nxt] + ((size_t) p * w.N + t) * T_STRIDE);
+#pragma unroll
+        for (int k = 0; k < T_STRIDE / 4; k++) t4[k] = make_float4(trow[4 * k], trow[4 * k + 1], trow[4 * k + 2], trow[4 * k + 3]);
+        if (fix && !good) {                      // BA:1595-1598, 1623-1640: non-good residuals are deleted
+            w.r_alive[r] = 0;
+            atomicAdd(&ctrl->num_dropped, 1);
+        }
+    }
+    // block energy (fp64, fixed order)
+    __shared__ double s_e[LIN_THREADS / 32];
+    double s = warp_sum_d(ret);
+    if ((threadIdx.x & 31) == 0) s_e[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0;
+        for (int k = 0; k < LIN_THREADS / 32; k++) tot += s_e[k];
+        w.energy_part[blockIdx.x] = tot;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// HOT LOOP 2: 13x13 block [C4 | xi6 | a b | r] of every (host,target) bin.  One CTA per chunk of <=128
+// residuals of ONE bin; records are staged in shared memory, every lane owns 3 of the 91 unique entries.
+constexpr int REC_S = 60;  // smem record: raw[36] (x y A B BR, [35]=1) | Qx[10] | Qy[10] | zero[4]
+__global__ void __launch_bounds__(128) accumulate_kernel(const DevWin w, const int respect_done) {
+    if (respect_done && w.ctrl->done) return;
+    const int nxt = w.ctrl->cur ^ 1;
+    __shared__ __align__(16) float rec[ACC_CHUNK * REC_S];
+    __shared__ float red[4][ACC_N];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int begin = w.acc_chunk_begin[c], cnt = w.acc_chunk_count[c];
+    const float4 *src = reinterpret_cast<const float4 *>(w.rj + (size_t) begin * RJ_STRIDE);
+    for (int i = tid; i < ACC_CHUNK * 9; i += 128) {
+        const int rr = i / 9, q = i - rr * 9;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rr < cnt) v = __ldg(src + i);
+        if (q == 8) v.w = (rr < cnt) ? 1.f : 0.f;
+        *reinterpret_cast<float4 *>(&rec[rr * REC_S + q * 4]) = v;
+    }
+    __syncthreads();
+    {   // Q = JIdx2 * Jp
+        float *m = &rec[tid * REC_S];
+        const float a00 = m[20], a01 = m[21], a11 = m[22];
+#pragma unroll
+        for (int k = 0; k < 10; k++) { const float x = m[k], y = m[10 + k]; m[36 + k] = a00 * x + a01 * y; m[46 + k] = a01 * x + a11 * y; }
+        m[56] = m[57] = m[58] = m[59] = 0.f;
+    }
+    __syncthreads();
+    const int wid = tid >> 5, lane = tid & 31;
+    const uchar4 o0 = c_acc_ofs[lane], o1 = c_acc_ofs[lane + 32], o2 = c_acc_ofs[lane + 64];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    const int rend = min(cnt, wid * 32 + 32);
+    for (int rr = wid * 32; rr < rend; rr++) {
+        const float *m = &rec[rr * REC_S];
+        a0 += m[o0.x] * m[o0.y] + m[o0.z] * m[o0.w];
+        a1 += m[o1.x] * m[o1.y] + m[o1.z] * m[o1.w];
+        a2 += m[o2.x] * m[o2.y] + m[o2.z] * m[o2.w];
+    }
+    red[wid][lane] = a0; red[wid][lane + 32] = a1; red[wid][lane + 64] = a2;
+    __syncthreads();
+    if (tid < ACC_N) w.acc_part[nxt][(size_t) c * ACC_N + tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// HOT LOOP 3: Schur complement of the inverse depths.  One CTA per chunk of <=64 points hosted in ONE
+// frame: per-point Hdd/bd/Hcd, Hdd^-1, then the (8N x 8N) outer-product sum D = sum_p HdiF * v_p v_p^T
+// (v_p = the point's JpJdF rows over all targets, zero where there is no good residual), E, EB, Hcc, bc.
+__global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int respect_done) {
+    if (respect_done && w.ctrl->done) return;
+    extern __shared__ __align__(16) float sm[];
+    const int N = w.N, NB = 8 * N;
+    const int cur = w.ctrl->cur;
+    float *sT = sm;                                  // [SC_CHUNK][N][8]  JpJdF rows
+    float *hdi = sT + SC_CHUNK * NB;                 // [SC_CHUNK]
+    float *bds = hdi + SC_CHUNK;                     // [SC_CHUNK] HdiF*bdSum
+    float *hcd = bds + SC_CHUNK;                     // [SC_CHUNK][4]
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int begin = w.sc_chunk_begin[c], cnt = w.sc_chunk_count[c];
+    const float *Tsrc = w.T[cur] + (size_t) begin * N * T_STRIDE;
+    // stage JpJdF (first 8 floats of every row)
+    for (int i = tid; i < SC_CHUNK * N * 2; i += 256) {
+        const int row = i >> 1, half = i & 1;        // row = p*N + t
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < cnt * N) v = __ldg(reinterpret_cast<const float4 *>(Tsrc + (size_t) row * T_STRIDE) + half);
+        *reinterpret_cast<float4 *>(&sT[row * 8 + half * 4]) = v;
+    }
+    // per point sums (BA:1895-1907)
+    if (tid < SC_CHUNK) {
+        float Hdd = 0.f, bd = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f; int ng = 0;
+        float hd = 0.f, bs = 0.f;
+        if (tid < cnt) {
+            const int p = begin + tid;
+            for (int t = 0; t < N; t++) {
+                const float4 *q = reinterpret_cast<const float4 *>(Tsrc + ((size_t) tid * N + t) * T_STRIDE);
+                const float4 a = __ldg(q + 2), b = __ldg(q + 3);   // bd Hdd Hcd0 Hcd1 | Hcd2 Hcd3 good pad
+                bd += a.x; Hdd += a.y; h0 += a.z; h1 += a.w; h2 += b.x; h3 += b.y; ng += (b.z != 0.f);
+            }
+            const float priorF = w.pt_priorF[p];
+            float idh = 0.f, bdSum = 0.f;
+            if (ng > 0) {
+                float Hs = Hdd + priorF;
+                if (Hs < 1e-10f) Hs = 1e-10f;
+                idh = Hs;
+                hd = (float) (1.0 / (double) Hs);
+                const float deltaF = (float) (w.pt_idepth[p] - (double) w.pt_idepth_zero[p]);
+                bdSum = bd + priorF * deltaF;
+                bs = hd * bdSum;
+            } else {
+                w.pt_max_rel_bs[p] = 0.f;        // BA:1885-1893
+            }
+            w.pt_Hdd[p] = Hdd; w.pt_bd[p] = bd;
+            w.pt_Hcd[p * 4 + 0] = h0; w.pt_Hcd[p * 4 + 1] = h1; w.pt_Hcd[p * 4 + 2] = h2; w.pt_Hcd[p * 4 + 3] = h3;
+            w.pt_HdiF[p] = hd; w.pt_bdSumF[p] = bdSum; w.pt_idepth_hessian[p] = idh; w.pt_ngood_cur[p] = ng;
+        }
+        hdi[tid] = hd; bds[tid] = bs;
+        hcd[tid * 4 + 0] = h0; hcd[tid * 4 + 1] = h1; hcd[tid * 4 + 2] = h2; hcd[tid * 4 + 3] = h3;
+    }
+    __syncthreads();
+    float *out = w.sc_part + (size_t) c * w.sc_stride;
+    // D: 4x4 register tiles; tile s -> (t1, t2, ti, tj)
+    const int ntiles = 4 * N * N;
+    for (int s = tid; s < ntiles; s += 256) {
+        const int tj = s & 1, ti = (s >> 1) & 1, t2 = (s >> 2) % N, t1 = (s >> 2) / N;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+        const float *pa = sT + t1 * 8 + ti * 4, *pb = sT + t2 * 8 + tj * 4;
+        for (int p = 0; p < cnt; p++) {
+            const float4 a = *reinterpret_cast<const float4 *>(pa + p * NB);
+            const float4 b = *reinterpret_cast<const float4 *>(pb + p * NB);
+            const float hh = hdi[p];
+            const float av[4] = {a.x * hh, a.y * hh, a.z * hh, a.w * hh};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bv[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float4 *o = reinterpret_cast<float4 *>(out + (size_t) (t1 * 8 + ti * 4 + i) * NB + t2 * 8 + tj * 4);
+            *o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+    }
+    // E (8N x 4), EB (8N), Hcc (4x4), bc (4)
+    float *oE = out + NB * NB, *oEB = oE + NB * 4, *oHcc = oEB + NB, *obc = oHcc + 16;
+    const int nsmall = NB * 4 + NB + 16 + 4;
+    for (int e = tid; e < nsmall; e += 256) {
+        float acc = 0.f;
+        if (e < NB * 4) {
+            const int row = e >> 2, cc = e & 3;
+            for (int p = 0; p < cnt; p++) acc += hdi[p] * sT[p * NB + row] * hcd[p * 4 + cc];
+            oE[e] = acc;
+        } else if (e < NB * 5) {
+            const int row = e - NB * 4;
+            for (int p = 0; p < cnt; p++) acc += bds[p] * sT[p * NB + row];
+            oEB[row] = acc;
+        } else if (e < NB * 5 + 16) {
+            const int k = e - NB * 5, i = k >> 2, j = k & 3;
+            for (int p = 0; p < cnt; p++) acc += hdi[p] * hcd[p * 4 + i] * hcd[p * 4 + j];
+            oHcc[k] = acc;
+        } else {
+            const int k = e - NB * 5 - 16;
+            for (int p = 0; p < cnt; p++) acc += bds[p] * hcd[p * 4 + k];
+            obc[k] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// index of entry (r,c), r<=c, of the packed 13x13 block
+__device__ __forceinline__ int acc_index(int r, int c) {
+    if (r > c) { int t = r; r = c; c = t; }
+    if (c < 10) return r * 10 - (r * (r - 1)) / 2 + (c - r);        // top-left 10x10, row-major upper triangle
+    if (r < 10) return 55 + r * 3 + (c - 10);                       // top-right 10x3
+    const int rr = r - 10, cc = c - 10;                             // bottom-right 3x3 upper triangle
+    return 85 + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5));
+}
+
+// Stitching (fp64): one CTA per host frame i.  Every output block of the per-host partial matrices is owned
+// by exactly one thread, so there are no atomics; partials are summed over hosts in solve_kernel.
+// AT is diagonal (identity pose block, -a, -1, row-scaled; BA:1075-1092): only its diagonal is used.
+__global__ void __launch_bounds__(256) stitch_kernel(const DevWin w, const int respect_done) {
+    if (respect_done && w.ctrl->done) return;
+    extern __shared__ __align__(16) double smd[];
+    const int N = w.N, NB = 8 * N, n = w.n, i = blockIdx.x, tid = threadIdx.x;
+    const int cur = w.ctrl->cur;
+    double *D = smd;                 // [NB][NB]
+    double *accA = D + NB * NB;      // [N][ACC_N]
+    double *G = accA + N * ACC_N;    // [8][NB]   G[r][k*8+m] = AH_ik[r][m]
+    double *Y = G + 8 * NB;          // [NB][8]
+    double *E = Y + NB * 8;          // [NB][4]
+    double *EB = E + NB * 4;         // [NB]
+    double *atd = EB + NB;           // [N][8]  diag(AT_ij)
+    double *small = atd + NB;        // Hcc[16] bc[4]
+    for (int e = tid; e < 8 * NB; e += 256) { const int r = e / NB, km = e % NB, k = km >> 3, m = km & 7; G[e] = w.AH[((size_t) (i * N + k)) * 64 + r * 8 + m]; }
+    for (int e = tid; e < NB; e += 256) { const int j = e >> 3, r = e & 7; atd[e] = w.AT[((size_t) (i * N + j)) * 64 + r * 8 + r]; }
+    // reduce the chunk partials of bins (host i, target t), bin = t*N + i
+    for (int e = tid; e < N * ACC_N; e += 256) {
+        const int t = e / ACC_N, k = e % ACC_N, bin = t * N + i;
+        double s = 0.0;
+        for (int c = w.bin_chunk_begin[bin]; c < w.bin_chunk_begin[bin + 1]; c++) s += (double) w.acc_part[cur][(size_t) c * ACC_N + k];
+        accA[e] = s;
+    }
+    // reduce the Schur partials of host i
+    const int cb = w.host_chunk_begin[i], ce = w.host_chunk_begin[i + 1];
+    const int tot = NB * NB + NB * 4 + NB + 20;
+    for (int e = tid; e < tot; e += 256) {
+        double s = 0.0;
+        for (int c = cb; c < ce; c++) s += (double) w.sc_part[(size_t) c * w.sc_stride + e];
+        if (e < NB * NB) D[e] = s;
+        else if (e < NB * NB + NB * 4) E[e - NB * NB] = s;
+        else if (e < NB * NB + NB * 5) EB[e - NB * NB - NB * 4] = s;
+        else small[e - NB * NB - NB * 5] = s;
+    }
+    double *HA = w.HApart + (size_t) i * n * n, *HS = w.HSpart + (size_t) i * n * n;
+    double *bA = w.bApart + (size_t) i * n, *bS = w.bSpart + (size_t) i * n;
+    for (int e = tid; e < n * n; e += 256) { HA[e] = 0.0; HS[e] = 0.0; }
+    for (int e = tid; e < n; e += 256) { bA[e] = 0.0; bS[e] = 0.0; }
+    __syncthreads();
+    // Y = D * G^T   (Y[(j r)][c] = sum_k (D_jk AH_ik^T)[r][c])
+    for (int e = tid; e < NB * 8; e += 256) {
+        const int row = e >> 3, c = e & 7;
+        double s = 0.0;
+        for (int km = 0; km < NB; km++) s += D[row * NB + km] * G[c * NB + km];
+        Y[e] = s;
+    }
+    __syncthreads();
+    const int iI = 4 + 8 * i;
+    // ---- Schur part (BA:1982-2011)
+    for (int e = tid; e < NB * NB; e += 256) {           // blocks (j,k), j,k != i: AT_ij D_jk AT_ik^T
+        const int row = e / NB, col = e % NB, j = row >> 3, k = col >> 3;
+        if (j != i && k != i) HS[(size_t) (4 + row) * n + 4 + col] = atd[row] * D[e] * atd[col];
+    }
+    for (int e = tid; e < NB * 8; e += 256) {            // blocks (j,i) = AT_ij Y_j and its transpose (i,j)
+        const int row = e >> 3, c = e & 7, j = row >> 3;
+        if (j != i) {
+            const double v = atd[row] * Y[e];
+            HS[(size_t) (4 + row) * n + iI + c] = v;
+            HS[(size_t) (iI + c) * n + 4 + row] = v;
+        }
+    }
+    for (int e = tid; e < 64; e += 256) {                // block (i,i) = sum_j AH_ij Y_j
+        const int r = e >> 3, c = e & 7;
+        double s = 0.0;
+        for (int km = 0; km < NB; km++) s += G[r * NB + km] * Y[km * 8 + c];
+        HS[(size_t) (iI + r) * n + iI + c] = s;
+    }
+    for (int e = tid; e < NB * 4; e += 256) {            // calibration columns: rows j != i
+        const int row = e >> 2, c = e & 3, j = row >> 3;
+        if (j != i) HS[(size_t) (4 + row) * n + c] = atd[row] * E[e];
+    }
+    for (int e = tid; e < 32; e += 256) {                // calibration columns: row block i
+        const int r = e >> 2, c = e & 3;
+        double s = 0.0;
+        for (int km = 0; km < NB; km++) s += G[r * NB + km] * E[km * 4 + c];
+        HS[(size_t) (iI + r) * n + c] = s;
+    }
+    for (int e = tid; e < NB; e += 256) { const int j = e >> 3; if (j != i) bS[4 + e] = atd[e] * EB[e]; }
+    for (int e = tid; e < 8; e += 256) {
+        double s = 0.0;
+        for (int km = 0; km < NB; km++) s += G[e * NB + km] * EB[km];
+        bS[iI + e] = s;
+    }
+    for (int e = tid; e < 16; e += 256) HS[(size_t) (e >> 2) * n + (e & 3)] = small[e];
+    for (int e = tid; e < 4; e += 256) bS[e] = small[16 + e];
+    // ---- active part (BA:1825-1843); A8 = acc[4:12,4:12], cC = acc[4:12,0:4], g = acc[4:12,12]
+    for (int e = tid; e < N * 64; e += 256) {            // (t,t) = AT A AT^T ; (i,t) = AH_it A AT^T
+        const int t = e >> 6, r = (e >> 3) & 7, c = e & 7;
+        if (t == i) continue;
+        const double *A = accA + t * ACC_N;
+        const int tI = 4 + 8 * t;
+        HA[(size_t) (tI + r) * n + tI + c] = atd[t * 8 + r] * A[acc_index(4 + r, 4 + c)] * atd[t * 8 + c];
+        double s = 0.0;
+        for (int m = 0; m < 8; m++) s += G[r * NB + t * 8 + m] * A[acc_index(4 + m, 4 + c)];
+        HA[(size_t) (iI + r) * n + tI + c] = s * atd[t * 8 + c];
+    }
+    for (int e = tid; e < 64; e += 256) {                // (i,i) = sum_t AH_it A AH_it^T
+        const int r = e >> 3, c = e & 7;
+        double s = 0.0;
+        for (int t = 0; t < N; t++) {
+            if (t == i) continue;
+            const double *A = accA + t * ACC_N;
+            for (int m = 0; m < 8; m++) {
+                double q = 0.0;
+                for (int l = 0; l < 8; l++) q += A[acc_index(4 + m, 4 + l)] * G[c * NB + t * 8 + l];
+                s += G[r * NB + t * 8 + m] * q;
+            }
+        }
+        HA[(size_t) (iI + r) * n + iI + c] = s;
+    }
+    for (int e = tid; e < N * 32; e += 256) {            // (t,C) = AT cC
+        const int t = e >> 5, r = (e >> 2) & 7, c = e & 3;
+        if (t == i) continue;
+        HA[(size_t) (4 + 8 * t + r) * n + c] = atd[t * 8 + r] * accA[t * ACC_N + acc_index(4 + r, c)];
+    }
+    for (int e = tid; e < 32; e += 256) {                // (i,C) = sum_t AH_it cC
+        const int r = e >> 2, c = e & 3;
+        double s = 0.0;
+        for (int t = 0; t < N; t++) { if (t == i) continue; for (int m = 0; m < 8; m++) s += G[r * NB + t * 8 + m] * accA[t * ACC_N + acc_index(4 + m, c)]; }
+        HA[(size_t) (iI + r) * n + c] = s;
+    }
+    for (int e = tid; e < 16; e += 256) {                // (C,C)
+        const int r = e >> 2, c = e & 3;
+        double s = 0.0;
+        for (int t = 0; t < N; t++) if (t != i) s += accA[t * ACC_N + acc_index(r, c)];
+        HA[(size_t) r * n + c] = s;
+    }
+    for (int e = tid; e < N * 8; e += 256) {             // b[t] = AT g
+        const int t = e >> 3, r = e & 7;
+        if (t != i) bA[4 + 8 * t + r] = atd[t * 8 + r] * accA[t * ACC_N + acc_index(4 + r, 12)];
+    }
+    for (int e = tid; e < 8; e += 256) {                 // b[i] = sum_t AH_it g
+        double s = 0.0;
+        for (int t = 0; t < N; t++) { if (t == i) continue; for (int m = 0; m < 8; m++) s += G[e * NB + t * 8 + m] * accA[t * ACC_N + acc_index(4 + m, 12)]; }
+        bA[iI + e] = s;
+    }
+    for (int e = tid; e < 4; e += 256) {
+        double s = 0.0;
+        for (int t = 0; t < N; t++) if (t != i) s += accA[t * ACC_N + acc_index(e, 12)];
+        bA[e] = s;
+    }
+}
+
+// sums the per-host partials into sys = [HA | bA | HS | bS] (the multi-GPU allreduce payload)
+__global__ void __launch_bounds__(256) sum_partials_kernel(const DevWin w, const int respect_done) {
+    if (respect_done && w.ctrl->done) return;
+    const int n = w.n, N = w.N, nn = n * n;
+    const int tot = 2 * nn + 2 * n;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
+        const double *src; int idx, stride;
+        if (e < nn) { src = w.HApart; idx = e; stride = nn; }
+        else if (e < nn + n) { src = w.bApart; idx = e - nn; stride = n; }
+        else if (e < 2 * nn + n) { src = w.HSpart; idx = e - nn - n; stride = nn; }
+        else { src = w.bSpart; idx = e - 2 * nn - n; stride = n; }
+        double s = 0.0;
+        for (int i = 0; i < N; i++) s += src[(size_t) i * stride + idx];
+        w.sys[e] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reduced camera system: assemble, damp, Jacobi-scale, LDL^T (lower triangle, like Eigen's default), solve,
+// orthogonalise against the gauge nullspaces, frame steps + new frame states + pair constants, xAd.
+__global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int respect_done) {
+    Ctrl *ctrl = w.ctrl;
+    if (respect_done && ctrl->done) return;
+    extern __shared__ __align__(16) double smd[];
+    const int N = w.N, n = w.n, m = 8 * N, tid = threadIdx.x, nn = n * n;
+    double *H = smd;            // [n][n]
+    double *b = H + nn;         // [n]
+    double *s = b + n;          // [n]
+    double *x = s + n;          // [n]
+    double *red = x + n;        // [256]
+    double *sysHA = w.sys, *sysbA = w.sys + nn, *sysHS = w.sys + nn + n, *sysbS = w.sys + 2 * nn + n;
+    // H <- HA, complete it exactly like stitchDoubleTop's tail (BA:1867-1876)
+    for (int e = tid; e < nn; e += 256) H[e] = sysHA[e];
+    __syncthreads();
+    for (int e = tid; e < N * 32; e += 256) { const int h = e >> 5, r = (e >> 2) & 7, c = e & 3; H[c * n + 4 + 8 * h + r] = H[(4 + 8 * h + r) * n + c]; }
+    for (int e = tid; e < N * N * 64; e += 256) {
+        const int h = e / (N * 64), t = (e / 64) % N, r = (e >> 3) & 7, c = e & 7;
+        if (t > h) {
+            const int a = (4 + 8 * h + r) * n + 4 + 8 * t + c, bb = (4 + 8 * t + c) * n + 4 + 8 * h + r;
+            const double v = H[a] + H[bb];
+            H[a] = v; H[bb] = v;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nn; e += 256) sysHA[e] = H[e];      // completed HA_top, for read-back / statistics
+    // Schur matrix: mirror the calibration rows (BA:2033-2037)
+    for (int e = tid; e < N * 32; e += 256) { const int h = e >> 5, r = (e >> 2) & 7, c = e & 3; sysHS[c * n + 4 + 8 * h + r] = sysHS[(4 + 8 * h + r) * n + c]; }
+    __syncthreads();
+    const double lambda = w.fix_lambda ? w.fixed_lambda : ctrl->lambda;
+    // b = bL + bM + bA - b_sc ; H = HL + HM + HA (BA:1299-1300); HL = diag(prior), bL = prior*delta_prior (BA:1857-1865)
+    for (int e = tid; e < n; e += 256) {
+        double v = sysbA[e] - sysbS[e] + w.bM[e];
+        if (e >= 4) {
+            const FrameDev &f = w.frames[(e - 4) >> 3];
+            const int k = (e - 4) & 7;
+            v += f.prior[k] * f.state[k];                       // delta_prior = state - prior_zero, prior_zero == 0
+        }
+        // bM_top = b_M + H_M * delta (BA:1401), delta = state - state_zero (calibration part 0)
+        double hm = 0.0;
+        for (int c = 4; c < n; c++) { const FrameDev &g = w.frames[(c - 4) >> 3]; const int k = (c - 4) & 7; hm += w.HM[(size_t) e * n + c] * (g.state[k] - g.state_zero[k]); }
+        b[e] = v + hm;
+    }
+    for (int e = tid; e < nn; e += 256) {
+        const int r = e / n, c = e % n;
+        double v = H[e] + w.HM[e];
+        if (r == c && r >= 4) v += w.frames[(r - 4) >> 3].prior[(r - 4) & 7];
+        if (r == c) v *= (1.0 + lambda);                        // BA:1306-1308
+        v -= sysHS[e] * (1.0 / (1.0 + lambda));                 // BA:1309
+        H[e] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < n; e += 256) s[e] = 1.0 / sqrt(H[e * n + e] + 10.0);   // BA:1312
+    __syncthreads();
+    // scaled system on the trailing m x m block (calibration fixed, BA:1319); only the lower triangle is read
+#define AA(r, c) H[(size_t) (4 + (r)) * n + 4 + (c)]
+    for (int e = tid; e < m * m; e += 256) { const int r = e / m, c = e % m; if (r >= c) AA(r, c) = AA(r, c) * s[4 + r] * s[4 + c]; }
+    for (int e = tid; e < m; e += 256) x[e] = s[4 + e] * b[4 + e];
+    __syncthreads();
+    // LDL^T, right-looking, no pivoting (SPD after damping + priors)
+    for (int k = 0; k < m; k++) {
+        const double d = AA(k, k);
+        __syncthreads();
+        for (int r = k + 1 + tid; r < m; r += 256) AA(r, k) = AA(r, k) / d;
+        __syncthreads();
+        const int rem = m - k - 1;
+        for (int e = tid; e < rem * rem; e += 256) {
+            const int r = k + 1 + e / rem, c = k + 1 + e % rem;
+            if (r >= c) AA(r, c) -= AA(r, k) * d * AA(c, k);
+        }
+        __syncthreads();
+    }
+    // forward L y = rhs ; z = y / d ; backward L^T x = z   (column-oriented, one sync per column)
+    for (int k = 0; k < m; k++) {
+        const double yk = x[k];
+        __syncthreads();
+        for (int r = k + 1 + tid; r < m; r += 256) x[r] -= AA(r, k) * yk;
+        __syncthreads();
+    }
+    for (int e = tid; e < m; e += 256) x[e] = x[e] / AA(e, e);
+    __syncthreads();
+    for (int k = m - 1; k >= 0; k--) {
+        // x[k] -= sum_{r>k} L[r][k] x[r]
+        double part = 0.0;
+        for (int r = k + 1 + tid; r < m; r += 256) part += AA(r, k) * x[r];
+        red[tid] = part;
+        __syncthreads();
+        if (tid < 32) {
+            double v = 0.0;
+            for (int q = tid; q < 256; q += 32) v += red[q];
+            v = warp_sum_d(v);
+            if (tid == 0) x[k] -= v;
+        }
+        __syncthreads();
+    }
+#undef AA
+    // x = SVecI * y, calibration entries 0 (BA:1314-1319)
+    for (int e = tid; e < n; e += 256) b[e] = (e >= 4) ? s[e] * x[e - 4] : 0.0;   // b now holds x
+    __syncthreads();
+    if (ctrl->iteration >= 2) {                                  // orthogonalize(x) (BA:1332-1334), projector precomputed on the host
+        for (int e = tid; e < n; e += 256) {
+            double v = 0.0;
+            for (int c = 0; c < n; c++) v += w.Pns[(size_t) e * n + c] * b[c];
+            s[e] = b[e] - v;
+        }
+        __syncthreads();
+        for (int e = tid; e < n; e += 256) b[e] = s[e];
+        __syncthreads();
+    }
+    for (int e = tid; e < n; e += 256) w.x[e] = b[e];
+    // statistics (BA:1415-1425)
+    if (tid < 32) {
+        double v = 0.0;
+        for (int e = tid; e < n; e += 32) v += b[e] * b[e];
+        v = warp_sum_d(v);
+        if (tid == 0) ctrl->stats[4] = sqrt(v);
+    }
+    // frame steps + states (BA:1433-1441, 957-973; DSOFrame::doStepFromBackup) and convergence sums
+    __shared__ int s_fail;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    if (tid < N) {
+        FrameDev &f = w.frames[tid];
+        double step[10];
+        bool fin = true;
+        for (int k = 0; k < 8; k++) { step[k] = -b[4 + 8 * tid + k]; fin = fin && isfinite(step[k]); }
+        step[8] = step[9] = 0.0;
+        if (!fin) for (int k = 0; k < 10; k++) step[k] = 0.0;    // DSOFrame::setStep (DSOFrame.h:205-214)
+        if (w.update_points_only) for (int k = 0; k < 6; k++) step[k] = 0.0;
+        double ns[10];
+        for (int k = 0; k < 10; k++) { f.state_backup[k] = f.state[k]; f.step[k] = step[k]; ns[k] = f.state[k] + step[k]; }
+        frame_set_state(f, ns, w);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float sumA = 0, sumB = 0, sumT = 0, sumR = 0;
+        for (int i = 0; i < N; i++) {
+            const double *st = w.frames[i].step;
+            sumA += (float) (st[6] * st[6]); sumB += (float) (st[7] * st[7]);
+            sumT += (float) (st[0] * st[0] + st[1] * st[1] + st[2] * st[2]);
+            sumR += (float) (st[3] * st[3] + st[4] * st[4] + st[5] * st[5]);
+        }
+        ctrl->sumA = sumA / N; ctrl->sumB = sumB / N; ctrl->sumT = sumT / N; ctrl->sumR = sumR / N;
+    }
+    // xAd[h*N+t] = x_h^T AH + x_t^T AT (BA:1447)
+    for (int e = tid; e < N * N * 8; e += 256) {
+        const int ht = e >> 3, c = e & 7, h = ht / N, t = ht % N;
+        const double *ah = w.AH + (size_t) ht * 64, *at = w.AT + (size_t) ht * 64;
+        double v = 0.0;
+        for (int r = 0; r < 8; r++) v += b[4 + 8 * h + r] * ah[r * 8 + c] + b[4 + 8 * t + r] * at[r * 8 + c];
+        w.xAd[e] = v;
+    }
+    for (int e = tid; e < N * N; e += 256) pair_precompute(w, e / N, e % N);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-point back-substitution and step (BA:1455-1487, 976-994) + convergence test (BA:1013-1026)
+__global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const int respect_done) {
+    Ctrl *ctrl = w.ctrl;
+    if (respect_done && ctrl->done) return;
+    const int N = w.N, cur = ctrl->cur;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    double nid = 0.0; int cntid = 0; int bad = 0;
+    if (p < w.P) {
+        double step = 0.0;
+        if (w.pt_ngood_cur[p] > 0) {
+            const int h = w.pt_host[p];
+            double bb = (double) w.pt_bdSumF[p];
+            for (int c = 0; c < 4; c++) bb -= (-w.x[c]) * (double) w.pt_Hcd[p * 4 + c];
+            const float *row = w.T[cur] + (size_t) p * N * T_STRIDE;
+            for (int t = 0; t < N; t++) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(row + t * T_STRIDE));
+                const float4 c = __ldg(reinterpret_cast<const float4 *>(row + t * T_STRIDE) + 1);
+                const double *xa = w.xAd + (size_t) (h * N + t) * 8;
+                bb -= xa[0] * a.x + xa[1] * a.y + xa[2] * a.z + xa[3] * a.w + xa[4] * c.x + xa[5] * c.y + xa[6] * c.z + xa[7] * c.w;
+            }
+            step = -bb * (double) w.pt_HdiF[p];
+            if (!isfinite(step)) bad = 1;
+        }
+        w.pt_step[p] = step;
+        const float backup = (float) w.pt_idepth[p];               // backupState (BA:919-922): idepth_backup is float
+        w.pt_idepth_backup[p] = backup;
+        const double newid = (double) backup + step;
+        if (isfinite(newid) && newid > 0.0) {
+            w.pt_idepth[p] = newid;
+            w.pt_idepth_zero[p] = (float) newid;
+            nid = (double) fabsf(backup); cntid = 1;
+        }
+    }
+    __shared__ double s_n[8]; __shared__ int s_c[8]; __shared__ int s_bad[8];
+    double sn = warp_sum_d(nid);
+    int sc = cntid, sb = bad;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sc += __shfl_down_sync(0xffffffffu, sc, o); sb += __shfl_down_sync(0xffffffffu, sb, o); }
+    if ((threadIdx.x & 31) == 0) { s_n[threadIdx.x >> 5] = sn; s_c[threadIdx.x >> 5] = sc; s_bad[threadIdx.x >> 5] = sb; }
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        double tn = 0; int tc = 0, tb = 0;
+        for (int k = 0; k < 8; k++) { tn += s_n[k]; tc += s_c[k]; tb += s_bad[k]; }
+        w.pt_part[blockIdx.x * 3 + 0] = tn; w.pt_part[blockIdx.x * 3 + 1] = (double) tc; w.pt_part[blockIdx.x * 3 + 2] = (double) tb;
+        __threadfence();
+        const int ticket = atomicAdd(&ctrl->sc_done_count, 1);
+        s_last = (ticket == (int) gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        double tn = 0, tc = 0, tb = 0;
+        for (int k = 0; k < (int) gridDim.x; k++) { tn += w.pt_part[k * 3]; tc += w.pt_part[k * 3 + 1]; tb += w.pt_part[k * 3 + 2]; }
+        const float sumNID = (float) (tn / (tc > 0 ? tc : 1.0));
+        ctrl->sumNID = tn; ctrl->numID = (int) tc;
+        const float th = w.th_opt;
+        ctrl->canbreak = (sqrtf(ctrl->sumA) < 0.0005f * th && sqrtf(ctrl->sumB) < 0.00005f * th && sqrtf(ctrl->sumR) < 0.00005f * th &&
+                          sqrtf(ctrl->sumT) * sumNID < 0.00005f * th) ? 1 : 0;
+        if (tb > 0) { ctrl->failed = 1; ctrl->done = 1; }            // BA:1489-1492
+        ctrl->sc_done_count = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// After every linearization: total energy, setNewFrameEnergyTH (exact k-th smallest by radix select, the value
+// std::nth_element leaves at index floor(0.7 n)), accept bookkeeping of run() (forceAccept path).
+// mode 0: first linearization of run() (+applyActiveRes)  1: GN iteration  2: final linearizeAll(true)  3: stage call (no flip)
+__global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, const int mode, const int respect_done) {
+    Ctrl *ctrl = w.ctrl;
+    if (respect_done && ctrl->done) return;
+    const int tid = threadIdx.x;
+    __shared__ double s_red[32];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_k, s_n;
+    // energy: fixed-order sum of the block partials
+    double e = 0.0;
+    for (int i = tid; i < w.n_lin_blocks; i += 1024) e += w.energy_part[i];
+    e = warp_sum_d(e);
+    if ((tid & 31) == 0) s_red[tid >> 5] = e;
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int k = 0; k < 32; k++) t += s_red[k]; s_red[0] = t; }
+    // count candidates (energies >= 0 of residuals whose target is the newest frame)
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const double energy = s_red[0];
+    unsigned int cnt = 0;
+    for (int i = w.newest_begin + tid; i < w.R; i += 1024) cnt += (w.r_alive[i] && w.r_new_energy_wo[i] >= 0.f) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0 && cnt) atomicAdd(&s_n, cnt);
+    __syncthreads();
+    const unsigned int nv = s_n;
+    float th_new;
+    if (nv == 0) {
+        th_new = 12.f * 12.f * 8.f;                                  // BA:2432-2436
+    } else {
+        if (tid == 0) { s_k = (unsigned int) (int) (0.7f * (float) nv); s_prefix = 0; }   // nthIdx (BA:2448)
+        __syncthreads();
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 24 - 8 * pass;
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            const unsigned int prefix = s_prefix;
+            const unsigned int mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+            for (int i = w.newest_begin + tid; i < w.R; i += 1024) {
+                const float v = w.r_new_energy_wo[i];
+                if (w.r_alive[i] && v >= 0.f) {
+                    const unsigned int u = __float_as_uint(v);
+                    if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned int k = s_k, acc = 0; int d = 0;
+                for (; d < 256; d++) { if (acc + hist[d] > k) break; acc += hist[d]; }
+                s_k = k - acc;
+                s_prefix = prefix | ((unsigned int) d << shift);
+            }
+            __syncthreads();
+        }
+        const float nth = sqrtf(__uint_as_float(s_prefix));          // BA:2455
+        float th = nth * 1.5f;
+        th = 26.0f * 0.5f + th * (1.f - 0.5f);
+        th_new = th * th;
+    }
+    if (tid == 0) {
+        w.frames[w.N - 1].energy_th = th_new;
+        ctrl->energy_new = energy;
+        if (!isfinite(energy)) { ctrl->failed = 1; ctrl->done = 1; }
+        else if (mode == 0) { ctrl->cur ^= 1; ctrl->energy_last = energy; ctrl->energy_first = energy; }
+        else if (mode == 1) {
+            // forceAccept (BA:843): applyActiveRes, lambda *= 0.25
+            ctrl->cur ^= 1; ctrl->energy_last = energy; ctrl->lambda *= 0.25; ctrl->accepted += 1;
+            const int it = ctrl->iteration;
+            ctrl->iteration = it + 1;
+            if (ctrl->canbreak && it >= 1) ctrl->done = 1;             // BA:879
+        } else if (mode == 2) { ctrl->cur ^= 1; ctrl->energy_last = energy; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// addPoints (BA:382-415, DSOContext.h:86-91): reference colours by INTEGER pixel read, weights from the
+// interpolated host gradient.  One thread per (point, pattern pixel).
+__global__ void point_init_kernel(const DevWin w, const int p_begin, const int p_count, float *colors, float *weights) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p_count * 8) return;
+    const int p = p_begin + (i >> 3), k = i & 7;
+    const float4 *img = w.img[w.pt_host[p]];
+    const float x = w.pt_x[p], y = w.pt_y[p];
+    const int ix0 = (int) x + c_sx[k], iy0 = (int) y + c_sy[k];
+    colors[(size_t) p * 8 + k] = img[(size_t) iy0 * w.W + ix0].x;
+    const float fx = x + (float) c_sx[k], fy = y + (float) c_sy[k];
+    const int ix = (int) fx, iy = (int) fy;
+    const float dx = fx - (float) ix, dy = fy - (float) iy, dxdy = dx * dy;
+    const float w00 = 1.f - dx - dy + dxdy, w10 = dx - dxdy, w01 = dy - dxdy, w11 = dxdy;
+    const float4 *q = img + (size_t) iy * w.W + ix;
+    const float4 a = q[0], b = q[1], c = q[w.W], d = q[w.W + 1];
+    const float gx = a.y * w00 + b.y * w10 + c.y * w01 + d.y * w11;
+    const float gy = a.z * w00 + b.z * w10 + c.z * w01 + d.z * w11;
+    const double g2 = (double) gx * (double) gx + (double) gy * (double) gy;
+    weights[(size_t) p * 8 + k] = (float) sqrt((double) w.cth / ((double) w.cth + g2));
+}
+
+// AoS (I,dx,dy) 12-byte texels -> float4 texels (one aligned 128-bit load per bilinear tap)
+__global__ void repack_image_kernel(const float *__restrict__ src, float4 *__restrict__ dst, const int npix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npix) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+}
+
+// writes >L2-size bytes: used by the benchmark to evict the window between timed passes
+__global__ void l2_flush_kernel(float4 *buf, const size_t n4) {
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n4; i += (size_t) gridDim.x * blockDim.x) buf[i] = make_float4(1.f, 2.f, 3.f, 4.f);
+}
+
+}  // namespace cmlba

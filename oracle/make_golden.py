@@ -1,0 +1,55 @@
+"""Generates the committed golden fixtures under tests/golden/ -- TEST INFRASTRUCTURE ONLY.
+
+Runs the UNMODIFIED reference (oracle/_ref/cmlba_ref, built by oracle/Makefile from /root/reference) on
+small synthetic windows and stores window + golden vectors.  Run in the build container (needs
+/root/reference only through the prebuilt binary):
+    python oracle/make_golden.py
+The big arrays that are recomputable (gradient images) are checked for equality and then dropped.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from libcml_b200 import cmlw, synth  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "cmlba_ref")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def run_ref(window_path, mode, out_path):
+    r = subprocess.run([REF, "--window", window_path, "--mode", mode, "--out", out_path], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"cmlba_ref failed: {r.stderr[-2000:]}")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    tmp = "/tmp/cmlba_golden"
+    os.makedirs(tmp, exist_ok=True)
+    for name in ("tiny", "tiny_affine"):
+        win = synth.make_config(name)
+        full = os.path.join(tmp, f"{name}.cmlw")
+        cmlw.save(full, win)
+        run_ref(full, "stages", os.path.join(tmp, f"{name}_stages.cmlw"))
+        run_ref(full, "run", os.path.join(tmp, f"{name}_run.cmlw"))
+        st = cmlw.load(os.path.join(tmp, f"{name}_stages.cmlw"))
+        rn = cmlw.load(os.path.join(tmp, f"{name}_run.cmlw"))
+        # the reference's own level-0 derivative image must equal our restatement bit for bit
+        assert np.array_equal(st["grad_images"], win["grad"]), "gradient image restatement differs from the reference"
+        del st["grad_images"]
+        # "stages" (replayed through the protected members) must equal the public run()
+        for k in ("fin_frame_state", "fin_frame_pre_w2c", "fin_pt_idepth", "fin_pt_num_good", "fin_frame_energy_th"):
+            assert np.array_equal(st[k], rn[k]), f"stages != run() for {k}"
+        slim = {k: v for k, v in win.items() if k not in ("grad", "truth_idepth")}
+        cmlw.save(os.path.join(OUT, f"{name}_window.cmlw"), slim)
+        cmlw.save(os.path.join(OUT, f"{name}_stages.cmlw"), st)
+        print(name, "window", os.path.getsize(os.path.join(OUT, f"{name}_window.cmlw")) // 1024, "KB  stages",
+              os.path.getsize(os.path.join(OUT, f"{name}_stages.cmlw")) // 1024, "KB")
+
+
+if __name__ == "__main__":
+    main()
