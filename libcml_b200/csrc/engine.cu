@@ -759,6 +759,8 @@ public:
         return CMLBA_OK;
     }
     int read(const std::string &name, void *dst, size_t cap, size_t *bytes) {
+        if (name == "enable_dbg") { want_dbg = true; dirty = true; prepared = false; if (bytes) *bytes = 0; return CMLBA_OK; }
+        if (dirty || !d_ctrl.p) { set_error("window not built yet (cmlba_prepare / cmlba_run first)"); return CMLBA_ERR_STATE; }
         CK(cudaSetDevice(device));
         CK(cudaStreamSynchronize(stream));
         const int N = dw.N, P = dw.P, R = dw.R, n = dw.n;
@@ -783,7 +785,6 @@ public:
         if (name == "res_center") return copy_out(d_r_center.p, (size_t) R * 3, dst, cap, bytes);
         if (name == "rj") return copy_out(d_rj.p, (size_t) R * RJ_STRIDE, dst, cap, bytes);
         if (name == "dbg") { if (!want_dbg) { set_error("debug dump not enabled (cmlba_read(\"enable_dbg\") first)"); return CMLBA_ERR_STATE; } return copy_out(d_dbg.p, (size_t) R * DBG_STRIDE, dst, cap, bytes); }
-        if (name == "enable_dbg") { want_dbg = true; dirty = true; prepared = false; if (bytes) *bytes = 0; return CMLBA_OK; }
         if (name == "T") return copy_out(cur ? d_T1.p : d_T0.p, (size_t) P * N * T_STRIDE, dst, cap, bytes);
         if (name == "T_cand") return copy_out(cur ? d_T0.p : d_T1.p, (size_t) P * N * T_STRIDE, dst, cap, bytes);
         if (name == "pt_idepth") return copy_out(d_pt_idepth.p, P, dst, cap, bytes);
