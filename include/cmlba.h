@@ -141,6 +141,19 @@ int cmlba_apply(cmlba_handle *h);
 int cmlba_solve(cmlba_handle *h, int iteration);
 int cmlba_step(cmlba_handle *h, int update_points_only, int *can_break);
 
+/* Empties the window (all frames, points, residuals) but keeps the handle and its device allocations. */
+int cmlba_reset(cmlba_handle *h);
+
+/* Benchmark helper (bench.py): `steps` device-timed passes of the Jacobian + Schur accumulation hot path
+ * (linearize -> accumulate -> Schur -> stitch) over the prepared window; CUDA events on the launching stream.
+ * flush_l2 != 0 evicts the window between passes by writing a buffer larger than L2 outside the timed region. */
+typedef struct cmlba_bench_result {
+    int steps, residuals, points, frames, launches_per_pass;
+    double ms_pass;         /* mean duration of one whole pass */
+    double ms_linearize, ms_accumulate, ms_schur, ms_stitch;   /* mean per-kernel durations (separate loop) */
+} cmlba_bench_result;
+int cmlba_bench_pass(cmlba_handle *h, int steps, int warmup, int flush_l2, cmlba_bench_result *out);
+
 /* Named read-back of internal buffers for parity tests (device -> host copy, residual arrays in the
  * order of cmlba_read("res_point")/("res_target")).  Returns the number of BYTES the buffer holds in
  * *bytes; copies min(capacity, bytes) into dst (dst may be NULL to query the size).  Names are listed in

@@ -37,11 +37,16 @@ class RunResult(C.Structure):
                 ("energy_first", C.c_double), ("energy_last", C.c_double), ("gpu_ms", C.c_double), ("kernel_launches", C.c_int)]
 
 
+class BenchResult(C.Structure):
+    _fields_ = [("steps", C.c_int), ("residuals", C.c_int), ("points", C.c_int), ("frames", C.c_int), ("launches_per_pass", C.c_int),
+                ("ms_pass", C.c_double), ("ms_linearize", C.c_double), ("ms_accumulate", C.c_double), ("ms_schur", C.c_double), ("ms_stitch", C.c_double)]
+
+
 # every symbol include/cmlba.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["cmlba_default_config", "cmlba_create", "cmlba_destroy", "cmlba_last_error", "cmlba_set_calib", "cmlba_add_frame", "cmlba_add_points",
            "cmlba_remove_point", "cmlba_remove_frame", "cmlba_run", "cmlba_num_frames", "cmlba_num_points", "cmlba_num_residuals", "cmlba_get_frames",
            "cmlba_get_points", "cmlba_get_outliers", "cmlba_get_residuals", "cmlba_prepare", "cmlba_linearize", "cmlba_apply", "cmlba_solve", "cmlba_step",
-           "cmlba_read", "cmlba_nccl_unique_id", "cmlba_comm_init", "cmlba_version"]
+           "cmlba_read", "cmlba_reset", "cmlba_bench_pass", "cmlba_nccl_unique_id", "cmlba_comm_init", "cmlba_version"]
 
 _lib = None
 
@@ -80,6 +85,8 @@ def load_library():
     lib.cmlba_solve.argtypes = [vp, C.c_int]
     lib.cmlba_step.argtypes = [vp, C.c_int, ip]
     lib.cmlba_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.cmlba_reset.argtypes = [vp]
+    lib.cmlba_bench_pass.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(BenchResult)]
     lib.cmlba_nccl_unique_id.argtypes = [vp]
     lib.cmlba_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     _lib = lib
@@ -230,6 +237,14 @@ class DSOBundleAdjustment:
         if nb.value:
             self._ck(self.lib.cmlba_read(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), nb.value, C.byref(nb)))
         return out.reshape(shape) if shape is not None else out
+
+    def reset(self):
+        self._ck(self.lib.cmlba_reset(self.h))
+
+    def benchPass(self, steps, warmup=3, flush_l2=True):
+        r = BenchResult()
+        self._ck(self.lib.cmlba_bench_pass(self.h, int(steps), int(warmup), int(bool(flush_l2)), C.byref(r)))
+        return r
 
     def enableDebugDump(self):
         self._ck(self.lib.cmlba_read(self.h, b"enable_dbg", None, 0, None))

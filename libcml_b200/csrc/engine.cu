@@ -146,6 +146,8 @@ public:
         d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj, d_T0, d_T1, d_dbg, d_acc0, d_acc1, d_sc_part, d_stage;
     DevBuf<uint8_t> d_r_host, d_r_target, d_r_state0, d_r_state1, d_r_good0, d_r_good1, d_r_new_state, d_r_alive;
     bool want_dbg = false;
+    DevBuf<float4> d_flush;
+    std::vector<float4 *> img_pool;   // recycled image allocations (reset())
     int n_acc_chunks = 0, n_sc_chunks = 0;
     std::vector<int> h_bin_chunk_begin, h_host_chunk_begin;
 
@@ -176,6 +178,8 @@ public:
     ~Engine() {
         cudaSetDevice(device);
         for (auto &f : frames_) if (f.d_img) cudaFree(f.d_img);
+        for (auto *p : img_pool) cudaFree(p);
+        d_flush.release();
         if (stream) cudaStreamDestroy(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -208,6 +212,7 @@ public:
     int set_calib(double fx_, double fy_, double cx_, double cy_, int w, int h) {
         if (w < 8 || h < 8 || fx_ <= 0 || fy_ <= 0) { set_error("bad calibration"); return CMLBA_ERR_ARG; }
         if (have_calib && (w != W || h != H) && !frames_.empty()) { set_error("image size change with frames in the window"); return CMLBA_ERR_STATE; }
+        if (w != W || h != H) { cudaSetDevice(device); for (auto *p : img_pool) cudaFree(p); img_pool.clear(); }
         fx = fx_; fy = fy_; cx = cx_; cy = cy_; W = w; H = h; have_calib = true; dirty = true;
         return CMLBA_OK;
     }
@@ -235,7 +240,7 @@ public:
         // image: AoS (I,dx,dy) -> float4 texels on the device
         const size_t npix = (size_t) W * H;
         CK(d_stage.reserve(npix * 3));
-        CK(cudaMalloc(&f.d_img, npix * sizeof(float4)));
+        if (!img_pool.empty()) { f.d_img = img_pool.back(); img_pool.pop_back(); } else CK(cudaMalloc(&f.d_img, npix * sizeof(float4)));
         CK(cudaMemcpyAsync(d_stage.p, grad, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
         repack_image_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(d_stage.p, f.d_img, (int) npix);
         CK(cudaGetLastError());
@@ -746,6 +751,63 @@ public:
         return CMLBA_OK;
     }
 
+    // drop the whole window but keep the allocations (used by streaming callers and the end-to-end benchmark)
+    int reset() {
+        cudaSetDevice(device);
+        for (auto &f : frames_) if (f.d_img) { img_pool.push_back(f.d_img); f.d_img = nullptr; }
+        frames_.clear(); points_.clear(); res_.clear(); point_index_.clear(); outliers_.clear();
+        key_counter = 0; dirty = true; prepared = false;
+        return CMLBA_OK;
+    }
+
+    // Benchmark helper: `steps` passes of the Jacobian + Schur accumulation hot path
+    // (linearize -> accumulate -> schur -> stitch) on the prepared window, CUDA events on the launching stream.
+    // flush_l2: evict the window between passes by writing a buffer larger than L2 (outside the timed region).
+    int bench_pass(int steps, int warmup, int flush_l2, cmlba_bench_result *out) {
+        if (!prepared) { set_error("cmlba_prepare first"); return CMLBA_ERR_STATE; }
+        if (!out || steps < 1) { set_error("bad arguments"); return CMLBA_ERR_ARG; }
+        CK(cudaSetDevice(device));
+        const size_t flush_bytes = (size_t) 384 << 20;
+        if (flush_l2) CK(d_flush.reserve(flush_bytes / sizeof(float4)));
+        cudaEvent_t ev[6];
+        for (auto &e : ev) CK(cudaEventCreate(&e));
+        auto flush = [&]() { if (flush_l2) l2_flush_kernel<<<148 * 8, 256, 0, stream>>>(d_flush.p, flush_bytes / sizeof(float4)); };
+        // the committed buffers must hold a linearization for schur/stitch to chew on
+        launch_linearize(0, 0); launch_accumulate(0); launch_post(0, 0);
+        for (int i = 0; i < warmup; i++) { flush(); launch_linearize(0, 0); launch_accumulate(0); schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, 0); stitch_kernel<<<dw.N, 256, stitch_smem(), stream>>>(dw, 0); }
+        CK(cudaStreamSynchronize(stream));
+        double tot = 0, tk[4] = {0, 0, 0, 0};
+        const int l0 = launches;
+        for (int i = 0; i < steps; i++) {          // whole pass, two events only
+            flush();
+            CK(cudaEventRecord(ev[0], stream));
+            launch_linearize(0, 0); launch_accumulate(0);
+            schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, 0); launches++;
+            stitch_kernel<<<dw.N, 256, stitch_smem(), stream>>>(dw, 0); launches++;
+            if (world > 1) { sum_partials_kernel<<<32, 256, 0, stream>>>(dw, 0); launches++; int rc = allreduce_system(); if (rc) return rc; }
+            CK(cudaEventRecord(ev[1], stream));
+            CK(cudaStreamSynchronize(stream));
+            float ms = 0; CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); tot += ms;
+        }
+        const int per_pass = (launches - l0) / steps;
+        for (int i = 0; i < steps; i++) {          // per-kernel breakdown
+            flush();
+            CK(cudaEventRecord(ev[0], stream)); launch_linearize(0, 0);
+            CK(cudaEventRecord(ev[1], stream)); launch_accumulate(0);
+            CK(cudaEventRecord(ev[2], stream)); schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, 0);
+            CK(cudaEventRecord(ev[3], stream)); stitch_kernel<<<dw.N, 256, stitch_smem(), stream>>>(dw, 0);
+            CK(cudaEventRecord(ev[4], stream));
+            CK(cudaStreamSynchronize(stream));
+            for (int k = 0; k < 4; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); tk[k] += ms; }
+        }
+        CK(cudaGetLastError());
+        for (auto &e : ev) cudaEventDestroy(e);
+        out->steps = steps; out->residuals = dw.R; out->points = dw.P; out->frames = dw.N;
+        out->ms_pass = tot / steps; out->ms_linearize = tk[0] / steps; out->ms_accumulate = tk[1] / steps; out->ms_schur = tk[2] / steps; out->ms_stitch = tk[3] / steps;
+        out->launches_per_pass = per_pass;
+        return CMLBA_OK;
+    }
+
     // ------------------------------------------------------------------ named read-back (parity tests)
     template <typename T> int copy_out(const T *dev, size_t count, void *dst, size_t cap, size_t *bytes) {
         const size_t nb = count * sizeof(T);
@@ -987,6 +1049,9 @@ int cmlba_step(cmlba_handle *h, int update_points_only, int *can_break) {
     if (can_break) *can_break = c.canbreak;
     return CMLBA_OK;
 }
+
+int cmlba_reset(cmlba_handle *h) { HCHK; return h->eng.reset(); }
+int cmlba_bench_pass(cmlba_handle *h, int steps, int warmup, int flush_l2, cmlba_bench_result *out) { HCHK; return h->eng.bench_pass(steps, warmup, flush_l2, out); }
 
 int cmlba_read(cmlba_handle *h, const char *name, void *dst, size_t cap, size_t *bytes) { HCHK; if (!name) return CMLBA_ERR_ARG; return h->eng.read(name, dst, cap, bytes); }
 

@@ -1,0 +1,63 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/cmlba.h declares, and fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cmlba.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cmlba_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"libcmlba.so does not export {s}"
+
+
+def test_binding_lists_every_symbol():
+    from libcml_b200 import binding
+    assert sorted(binding.SYMBOLS) == declared_symbols()
+
+
+def test_version_and_default_config(lib):
+    from libcml_b200 import binding
+    assert lib.cmlba_version().decode().endswith("sm_100a")
+    cfg = binding.default_config()
+    # reference defaults, DSOBundleAdjustment.h:235-288
+    assert cfg.iterations == 4 and cfg.huber_threshold == 9.0 and cfg.outlier_th_sum == 2500.0
+    assert cfg.scale_translation == 0.5 and cfg.scale_light_a == 10.0 and cfg.scale_light_b == 1000.0
+    assert cfg.force_accept == 1 and cfg.fix_lambda == 1 and abs(cfg.fixed_lambda - 1e-5) < 1e-12
+    assert cfg.idepth_fix_prior == 2500 and cfg.disable_marginalization == 1 and cfg.max_frames == 6
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device creation must fail loudly (CMLBA_ERR_CUDA), never fall back to the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = lib.cmlba_create(None, 0, C.byref(h))
+    assert rc == -2 and not h.value
+    assert b"no CUDA device" in lib.cmlba_last_error(None)
+
+
+def test_null_handle_is_an_error(lib):
+    assert lib.cmlba_set_calib(None, 1.0, 1.0, 1.0, 1.0, 64, 64) == -1
+    assert lib.cmlba_run(None, None, 1, 0, None) == -1
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/ (only tests, smoke() and bench.py's CPU legs may)."""
+    pkg = os.path.join(ROOT, "libcml_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "ba_oracle" not in txt and "oracle/" not in txt.replace("oracle/cmlw_io.h", "").replace("oracle/ref_driver.cpp", ""), f
