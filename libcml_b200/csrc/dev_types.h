@@ -107,6 +107,7 @@ struct DevWin {
     int sc_stride;                 // (8N)^2 + 32N + 8N + 16 + 4 (padded to 4)
     const int *sc_chunk_host, *sc_chunk_begin, *sc_chunk_count;
     const int *host_chunk_begin;   // [N+1]
+    double *accR, *scR;            // chunk partials summed in fixed order: [N*N][ACC_N] by bin, [N][(8N)^2+32N+8N+20] by host
     double *HApart, *bApart, *HSpart, *bSpart;   // per host: [N][n*n], [N][n]
     double *sys;                   // summed system: HA[n*n] bA[n] HS[n*n] bS[n]  (allreduce payload)
     double *x;                     // [n]

@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -34,19 +35,87 @@ namespace cmlba {
         }                                                                                          \
     } while (0)
 
+// host-side stage timers (cmlba_read "host_timing"): where an end-to-end call spends its wall time
+struct HostTimers {
+    std::map<std::string, std::pair<double, long>> acc;   // name -> (ms, calls)
+    struct Scope {
+        HostTimers &t; const char *name; std::chrono::steady_clock::time_point t0;
+        Scope(HostTimers &t_, const char *n) : t(t_), name(n), t0(std::chrono::steady_clock::now()) {}
+        ~Scope() { auto &e = t.acc[name]; e.first += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); e.second++; }
+    };
+    std::string text() const { std::string s; char b[160]; for (auto &kv : acc) { snprintf(b, sizeof b, "%-28s %10.3f ms %6ld calls\n", kv.first.c_str(), kv.second.first, kv.second.second); s += b; } return s; }
+};
+struct Lap {   // sequential section timer: lap("name") charges the time since the previous lap
+    HostTimers &t; std::chrono::steady_clock::time_point last;
+    explicit Lap(HostTimers &t_) : t(t_), last(std::chrono::steady_clock::now()) {}
+    void operator()(const char *name) { auto now = std::chrono::steady_clock::now(); auto &e = t.acc[name]; e.first += std::chrono::duration<double, std::milli>(now - last).count(); e.second++; last = now; }
+};
+#define TSCOPE(name) HostTimers::Scope _ts_##__LINE__(timers, name)
+
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
+    bool view = false;            // p points into an UploadArena: nothing to free
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        if (p && !view) cudaFree(p);
+        p = nullptr; cap = 0; view = false;
         size_t want = n + n / 4 + 16;
         cudaError_t e = cudaMalloc(&p, want * sizeof(T));
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; cap = 0; view = false; }
+};
+
+// page-locked host staging (async H2D/D2H without the driver's bounce buffer)
+template <typename T> struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 16;
+        cudaError_t e = cudaHostAlloc((void **) &p, want * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// One pinned host block mirrored by one device block: the window arrays are laid out once (256-byte aligned),
+// filled in place on the host and uploaded with a single copy.
+struct UploadArena {
+    PinnedBuf<char> h; DevBuf<char> d;
+    size_t used = 0;
+    void begin() { used = 0; }
+    template <typename T> size_t take(size_t count) { const size_t off = (used + 255) & ~(size_t) 255; used = off + std::max<size_t>(count, 1) * sizeof(T); return off; }
+    cudaError_t commit() { cudaError_t e = h.reserve(used); if (e != cudaSuccess) return e; return d.reserve(used); }
+    template <typename T> T *host(size_t off) { return reinterpret_cast<T *>(h.p + off); }
+    template <typename T> T *dev(size_t off) { return reinterpret_cast<T *>(d.p + off); }
+};
+
+// open-addressing map point id -> index (rebuilt wholesale on compaction; std::unordered_map cost ~1 ms per 16k points)
+struct IdMap {
+    std::vector<int64_t> keys; std::vector<int> vals; size_t n = 0, mask = 0;
+    static constexpr int64_t EMPTY = INT64_MIN;
+    static size_t hash(int64_t k) { uint64_t x = (uint64_t) k * 0x9E3779B97F4A7C15ull; return (size_t) (x ^ (x >> 29)); }
+    void clear() { keys.clear(); vals.clear(); n = 0; mask = 0; }
+    void rehash(size_t cap) {
+        std::vector<int64_t> ok; std::vector<int> ov; ok.swap(keys); ov.swap(vals);
+        keys.assign(cap, EMPTY); vals.assign(cap, -1); mask = cap - 1; n = 0;
+        for (size_t i = 0; i < ok.size(); i++) if (ok[i] != EMPTY) set(ok[i], ov[i]);
+    }
+    void reserve(size_t want) { size_t cap = 64; while (cap < want * 2) cap <<= 1; if (cap > keys.size()) rehash(cap); }
+    int find(int64_t k) const {
+        if (keys.empty()) return -1;
+        for (size_t i = hash(k) & mask;; i = (i + 1) & mask) { if (keys[i] == k) return vals[i]; if (keys[i] == EMPTY) return -1; }
+    }
+    void set(int64_t k, int v) {
+        if ((n + 1) * 2 > keys.size()) rehash(std::max<size_t>(64, keys.size() * 2));
+        for (size_t i = hash(k) & mask;; i = (i + 1) & mask) { if (keys[i] == k) { vals[i] = v; return; } if (keys[i] == EMPTY) { keys[i] = k; vals[i] = v; n++; return; } }
+    }
 };
 
 struct FrameHost {
@@ -66,6 +135,7 @@ struct FrameHost {
 struct PointHost {
     int64_t id = 0;
     int64_t host_id = 0;
+    int host = 0;                // index of the host frame in frames_
     float x = 0, y = 0;
     double idepth = 0;
     float idepth_zero = 0;
@@ -80,7 +150,7 @@ struct PointHost {
 
 struct ResHost {
     int point;          // index into points_
-    int64_t target_id;
+    int target;         // index of the target frame in frames_
     int state = CMLBA_RES_IN;
     float energy = 0;
 };
@@ -123,7 +193,7 @@ public:
     std::vector<FrameHost> frames_;
     std::vector<PointHost> points_;
     std::vector<ResHost> res_;
-    std::unordered_map<int64_t, int> point_index_;
+    IdMap point_index_;
     std::vector<int64_t> outliers_;
     int key_counter = 0;
     bool dirty = true;            // device window must be rebuilt
@@ -139,11 +209,15 @@ public:
 
     // device buffers
     DevBuf<FrameDev> d_frames; DevBuf<PairPre> d_pairs; DevBuf<Ctrl> d_ctrl;
-    DevBuf<double> d_AH, d_AT, d_HM, d_bM, d_Pns, d_pt_idepth, d_pt_step, d_energy_part, d_HApart, d_bApart, d_HSpart, d_bSpart, d_sys, d_x, d_xAd, d_pt_part;
+    DevBuf<double> d_AH, d_AT, d_HM, d_bM, d_Pns, d_pt_idepth, d_pt_step, d_energy_part, d_HApart, d_bApart, d_HSpart, d_bSpart, d_sys, d_x, d_xAd, d_pt_part, d_accR, d_scR;
     DevBuf<int> d_pt_host, d_pt_num_good, d_pt_ngood_cur, d_r_point, d_acc_chunk_bin, d_acc_chunk_begin, d_acc_chunk_count, d_bin_chunk_begin, d_sc_chunk_host,
         d_sc_chunk_begin, d_sc_chunk_count, d_host_chunk_begin;
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
-        d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj, d_T0, d_T1, d_dbg, d_acc0, d_acc1, d_sc_part, d_stage;
+        d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj, d_T0, d_T1, d_dbg, d_acc0, d_acc1, d_sc_part, d_stage[2];
+    int stage_flip = 0;
+    cudaEvent_t ev_copy = nullptr;
+    UploadArena up;                               // every array build_device_window uploads
+    PinnedBuf<char> pt_stage_h, fin_h; DevBuf<char> pt_stage_d;   // add_points round trip, finish_run read-back
     DevBuf<uint8_t> d_r_host, d_r_target, d_r_state0, d_r_state1, d_r_good0, d_r_good1, d_r_new_state, d_r_alive;
     bool want_dbg = false;
     DevBuf<float4> d_flush;
@@ -151,6 +225,7 @@ public:
     int n_acc_chunks = 0, n_sc_chunks = 0;
     std::vector<int> h_bin_chunk_begin, h_host_chunk_begin;
 
+    HostTimers timers;
     void set_error(const std::string &s) { err = s; }
 
     int init() {
@@ -160,7 +235,7 @@ public:
         if (device < 0 || device >= ndev) { set_error("bad device ordinal"); return CMLBA_ERR_ARG; }
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+        CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
         // entry-offset table of the 13x13 accumulator (see accumulate_kernel)
         uchar4 ofs[ACC_N];
         int e_i = 0;
@@ -183,14 +258,16 @@ public:
         if (stream) cudaStreamDestroy(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_copy) cudaEventDestroy(ev_copy);
+        up.h.release(); up.d.release(); pt_stage_h.release(); fin_h.release(); pt_stage_d.release();
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         // DevBuf members leak-free:
-        DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_HApart, &d_bApart, &d_HSpart, &d_bSpart, &d_sys, &d_x, &d_xAd, &d_pt_part};
+        DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_HApart, &d_bApart, &d_HSpart, &d_bSpart, &d_sys, &d_x, &d_xAd, &d_pt_part, &d_accR, &d_scR};
         for (auto *b : dd) b->release();
         DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_acc_chunk_bin, &d_acc_chunk_begin, &d_acc_chunk_count, &d_bin_chunk_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin};
         for (auto *b : di) b->release();
         DevBuf<float> *df[] = {&d_pt_x, &d_pt_y, &d_pt_idz, &d_pt_idb, &d_pt_colors, &d_pt_weights, &d_pt_priorF, &d_pt_Hdd, &d_pt_bd, &d_pt_Hcd, &d_pt_HdiF, &d_pt_bdSumF, &d_pt_idh, &d_pt_mrb,
-                               &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj, &d_T0, &d_T1, &d_dbg, &d_acc0, &d_acc1, &d_sc_part, &d_stage};
+                               &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj, &d_T0, &d_T1, &d_dbg, &d_acc0, &d_acc1, &d_sc_part, &d_stage[0], &d_stage[1]};
         for (auto *b : df) b->release();
         DevBuf<uint8_t> *du[] = {&d_r_host, &d_r_target, &d_r_state0, &d_r_state1, &d_r_good0, &d_r_good1, &d_r_new_state, &d_r_alive};
         for (auto *b : du) b->release();
@@ -218,6 +295,7 @@ public:
     }
 
     int add_frame(int64_t id, const double *w2c, double a, double b, double exposure, const float *grad, int is_init) {
+        TSCOPE("add_frame");
         if (!have_calib) { set_error("cmlba_set_calib must be called before cmlba_add_frame"); return CMLBA_ERR_STATE; }
         if (!w2c || !grad) { set_error("null pointer"); return CMLBA_ERR_ARG; }
         if ((int) frames_.size() >= MAXF) { set_error("window full (CMLBA_MAX_FRAMES)"); return CMLBA_ERR_ARG; }
@@ -237,97 +315,113 @@ public:
         f.exposure = exposure;
         f.keyid = key_counter++;
         f.is_init = is_init != 0;
-        // image: AoS (I,dx,dy) -> float4 texels on the device
+        // image: AoS (I,dx,dy) -> float4 texels on the device.  The caller's buffer is only ours for the duration
+        // of the call: wait for the H2D copy (event), the repack kernel stays asynchronous on the stream.
         const size_t npix = (size_t) W * H;
-        CK(d_stage.reserve(npix * 3));
+        const int sb = stage_flip; stage_flip ^= 1;                 // two staging buffers: the previous repack may still run
+        CK(d_stage[sb].reserve(npix * 3));
         if (!img_pool.empty()) { f.d_img = img_pool.back(); img_pool.pop_back(); } else CK(cudaMalloc(&f.d_img, npix * sizeof(float4)));
-        CK(cudaMemcpyAsync(d_stage.p, grad, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
-        repack_image_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(d_stage.p, f.d_img, (int) npix);
+        CK(cudaMemcpyAsync(d_stage[sb].p, grad, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(ev_copy, stream));
+        repack_image_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(d_stage[sb].p, f.d_img, (int) npix);
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(stream));
+        const int slot = (int) frames_.size();
         frames_.push_back(f);
         // residuals from all existing points to the new frame (BA:455-460); lastResiduals slot 0 (BA:374-375)
+        res_.reserve(res_.size() + points_.size());
         for (size_t p = 0; p < points_.size(); p++) {
             if (!points_[p].alive) continue;
-            res_.push_back(ResHost{(int) p, id});
+            res_.push_back(ResHost{(int) p, slot});
             points_[p].last_frame[1] = points_[p].last_frame[0]; points_[p].last_state[1] = points_[p].last_state[0];
             points_[p].last_frame[0] = id; points_[p].last_state[0] = CMLBA_RES_IN;
         }
+        CK(cudaEventSynchronize(ev_copy));
         dirty = true; prepared = false;
         return CMLBA_OK;
     }
 
     int add_points(int n, const int64_t *pid, const int64_t *host_id, const float *xy, const double *idepth) {
+        TSCOPE("add_points");
+        Lap lap(timers);
         if (n < 0 || (n > 0 && (!pid || !host_id || !xy || !idepth))) { set_error("null pointer"); return CMLBA_ERR_ARG; }
         if (frames_.empty()) { set_error("no frames in the window"); return CMLBA_ERR_STATE; }
         CK(cudaSetDevice(device));
         const size_t first = points_.size();
+        const int NF = (int) frames_.size();
+        points_.reserve(first + n);
+        point_index_.reserve(first + n);
+        int64_t last_hid = INT64_MIN; int last_h = -1;
         for (int i = 0; i < n; i++) {
-            if (point_index_.count(pid[i])) continue;                 // BA:386-388
-            const int h = frame_index(host_id[i]);
+            if (pid[i] == IdMap::EMPTY) { set_error("point id INT64_MIN is reserved"); points_.resize(first); return CMLBA_ERR_ARG; }
+            if (point_index_.find(pid[i]) >= 0) continue;             // BA:386-388
+            if (host_id[i] != last_hid) { last_hid = host_id[i]; last_h = frame_index(host_id[i]); }
+            const int h = last_h;
             if (h < 0) { set_error("point's host frame is not in the window"); points_.resize(first); return CMLBA_ERR_ARG; }
             const float x = xy[2 * i], y = xy[2 * i + 1];
             if (!(x >= 3 && y >= 3 && x < W - 4 && y < H - 4)) { set_error("point closer than 3 px to the image border"); points_.resize(first); return CMLBA_ERR_ARG; }
             if (!(idepth[i] > 0) || !std::isfinite(idepth[i])) { set_error("inverse depth must be finite and > 0"); points_.resize(first); return CMLBA_ERR_ARG; }
             PointHost p;
-            p.id = pid[i]; p.host_id = host_id[i]; p.x = x; p.y = y; p.idepth = idepth[i];
+            p.id = pid[i]; p.host_id = host_id[i]; p.host = h; p.x = x; p.y = y; p.idepth = idepth[i];
             p.idepth_zero = (float) idepth[i];
             p.has_prior = frames_[h].is_init;
             points_.push_back(p);
         }
         const size_t nn = points_.size() - first;
+        lap("addp.validate");
         if (nn == 0) return CMLBA_OK;
-        // colours + weights on the device from the host frames' images
-        std::vector<int> hh(nn); std::vector<float> xs(nn), ys(nn);
-        for (size_t i = 0; i < nn; i++) { hh[i] = frame_index(points_[first + i].host_id); xs[i] = points_[first + i].x; ys[i] = points_[first + i].y; }
-        DevBuf<int> th; DevBuf<float> tx, ty, tc, tw;
-        CK(th.reserve(nn)); CK(tx.reserve(nn)); CK(ty.reserve(nn)); CK(tc.reserve(nn * 8)); CK(tw.reserve(nn * 8));
-        CK(cudaMemcpyAsync(th.p, hh.data(), nn * sizeof(int), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(tx.p, xs.data(), nn * sizeof(float), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(ty.p, ys.data(), nn * sizeof(float), cudaMemcpyHostToDevice, stream));
+        // colours + weights on the device from the host frames' images (staging: [host|x|y] up, [colors|weights] down)
+        const size_t o_h = 0, o_x = nn * 4, o_y = nn * 8, o_c = nn * 12, o_w = nn * 12 + nn * 32, tot = nn * 12 + nn * 64;
+        CK(pt_stage_h.reserve(tot)); CK(pt_stage_d.reserve(tot));
+        int *hh = reinterpret_cast<int *>(pt_stage_h.p + o_h); float *xs = reinterpret_cast<float *>(pt_stage_h.p + o_x), *ys = reinterpret_cast<float *>(pt_stage_h.p + o_y);
+        for (size_t i = 0; i < nn; i++) { const PointHost &q = points_[first + i]; hh[i] = q.host; xs[i] = q.x; ys[i] = q.y; }
+        CK(cudaMemcpyAsync(pt_stage_d.p, pt_stage_h.p, nn * 12, cudaMemcpyHostToDevice, stream));
         DevWin t{};
         t.W = W; t.H = H; t.cth = cfg.outlier_th_sum;
         for (size_t i = 0; i < frames_.size(); i++) t.img[i] = frames_[i].d_img;
-        t.pt_host = th.p; t.pt_x = tx.p; t.pt_y = ty.p;
-        point_init_kernel<<<(unsigned) ((nn * 8 + 255) / 256), 256, 0, stream>>>(t, 0, (int) nn, tc.p, tw.p);
+        t.pt_host = reinterpret_cast<int *>(pt_stage_d.p + o_h); t.pt_x = reinterpret_cast<float *>(pt_stage_d.p + o_x); t.pt_y = reinterpret_cast<float *>(pt_stage_d.p + o_y);
+        point_init_kernel<<<(unsigned) ((nn * 8 + 255) / 256), 256, 0, stream>>>(t, 0, (int) nn, reinterpret_cast<float *>(pt_stage_d.p + o_c), reinterpret_cast<float *>(pt_stage_d.p + o_w));
         CK(cudaGetLastError());
-        std::vector<float> hc(nn * 8), hw(nn * 8);
-        CK(cudaMemcpyAsync(hc.data(), tc.p, nn * 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(hw.data(), tw.p, nn * 8 * sizeof(float), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        th.release(); tx.release(); ty.release(); tc.release(); tw.release();
-        const int64_t newest = frames_.back().id, second = frames_.size() >= 2 ? frames_[frames_.size() - 2].id : -1;
+        CK(cudaMemcpyAsync(pt_stage_h.p + o_c, pt_stage_d.p + o_c, nn * 64, cudaMemcpyDeviceToHost, stream));
+        // residual bookkeeping overlaps the device round trip
+        const int64_t newest = frames_.back().id, second = NF >= 2 ? frames_[NF - 2].id : -1;
+        res_.reserve(res_.size() + nn * (NF - 1));
         for (size_t i = 0; i < nn; i++) {
             PointHost &p = points_[first + i];
-            memcpy(p.colors, &hc[i * 8], 32); memcpy(p.weights, &hw[i * 8], 32);
-            point_index_[p.id] = (int) (first + i);
-            for (auto &f : frames_) {
-                if (f.id == p.host_id) continue;
-                res_.push_back(ResHost{(int) (first + i), f.id});
-                if (f.id == newest) { p.last_frame[0] = f.id; p.last_state[0] = CMLBA_RES_IN; }
-                else if (f.id == second) { p.last_frame[1] = f.id; p.last_state[1] = CMLBA_RES_IN; }
+            point_index_.set(p.id, (int) (first + i));
+            for (int f = 0; f < NF; f++) {
+                if (f == p.host) continue;
+                res_.push_back(ResHost{(int) (first + i), f});
             }
+            if (p.host != NF - 1) { p.last_frame[0] = newest; p.last_state[0] = CMLBA_RES_IN; }
+            if (NF >= 2 && p.host != NF - 2) { p.last_frame[1] = second; p.last_state[1] = CMLBA_RES_IN; }
         }
+        lap("addp.residuals");
+        CK(cudaStreamSynchronize(stream));
+        const float *hc = reinterpret_cast<const float *>(pt_stage_h.p + o_c), *hw = reinterpret_cast<const float *>(pt_stage_h.p + o_w);
+        for (size_t i = 0; i < nn; i++) { PointHost &p = points_[first + i]; memcpy(p.colors, &hc[i * 8], 32); memcpy(p.weights, &hw[i * 8], 32); }
+        lap("addp.device_init");
         dirty = true; prepared = false;
         return CMLBA_OK;
     }
 
-    void compact() {   // drop dead points / residuals, rebuild indices
+    // drop dead points (and their residuals), rebuild the id index
+    void compact() {
         std::vector<int> remap(points_.size(), -1);
-        std::vector<PointHost> np;
-        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive) { remap[i] = (int) np.size(); np.push_back(points_[i]); }
-        std::vector<ResHost> nr;
-        for (auto &r : res_) if (remap[r.point] >= 0) { ResHost q = r; q.point = remap[r.point]; nr.push_back(q); }
-        points_.swap(np); res_.swap(nr);
-        point_index_.clear();
-        for (size_t i = 0; i < points_.size(); i++) point_index_[points_[i].id] = (int) i;
+        size_t np = 0;
+        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive) { remap[i] = (int) np; if (np != i) points_[np] = points_[i]; np++; }
+        points_.resize(np);
+        size_t nr = 0;
+        for (size_t i = 0; i < res_.size(); i++) { const int q = remap[res_[i].point]; if (q >= 0) { res_[nr] = res_[i]; res_[nr].point = q; nr++; } }
+        res_.resize(nr);
+        point_index_.clear(); point_index_.reserve(np);
+        for (size_t i = 0; i < np; i++) point_index_.set(points_[i].id, (int) i);
         dirty = true; prepared = false;
     }
 
     int remove_point(int64_t id) {
-        auto it = point_index_.find(id);
-        if (it == point_index_.end()) return CMLBA_OK;   // DSOContext.h:95-97
-        points_[it->second].alive = false;
+        const int idx = point_index_.find(id);
+        if (idx < 0) return CMLBA_OK;   // DSOContext.h:95-97
+        points_[idx].alive = false;
         compact();
         return CMLBA_OK;
     }
@@ -335,129 +429,129 @@ public:
     int remove_frame(int64_t id) {
         const int fi = frame_index(id);
         if (fi < 0) { set_error("unknown frame id"); return CMLBA_ERR_ARG; }
-        for (auto &p : points_) if (p.host_id == id) p.alive = false;
-        std::vector<ResHost> nr;
-        for (auto &r : res_) if (r.target_id != id) nr.push_back(r);
-        res_.swap(nr);
+        for (auto &p : points_) { if (p.host == fi) p.alive = false; else if (p.host > fi) p.host--; }
+        size_t nr = 0;
+        for (size_t i = 0; i < res_.size(); i++) if (res_[i].target != fi) { res_[nr] = res_[i]; if (res_[nr].target > fi) res_[nr].target--; nr++; }
+        res_.resize(nr);
         // points left without residuals disappear as well (DSOContext.h:205-216)
         std::vector<int> cnt(points_.size(), 0);
         for (auto &r : res_) cnt[r.point]++;
         for (size_t i = 0; i < points_.size(); i++) if (cnt[i] == 0) points_[i].alive = false;
         cudaSetDevice(device);
-        if (frames_[fi].d_img) cudaFree(frames_[fi].d_img);
+        cudaStreamSynchronize(stream);
+        if (frames_[fi].d_img) img_pool.push_back(frames_[fi].d_img);
         frames_.erase(frames_.begin() + fi);
         compact();
         return CMLBA_OK;
     }
 
     // ------------------------------------------------------------------ device window
+    // Layout: points sorted by host frame, residuals sorted by bin = t*N+h then by device point
+    // position.  Both orders come from stable counting sorts (O(P+R)); every uploaded array lives in one pinned
+    // arena mirrored on the device and travels in a single copy.
     int build_device_window() {
+        TSCOPE("build_device_window");
+        Lap lap(timers);
         const int N = (int) frames_.size(), P = (int) points_.size(), R = (int) res_.size();
         const int n = 8 * N + 4;
         CK(cudaSetDevice(device));
-        std::unordered_map<int64_t, int> fidx;
-        for (int i = 0; i < N; i++) fidx[frames_[i].id] = i;
-        // points sorted by host (stable)
+        // points: stable counting sort by host
+        std::vector<int> hcnt(N + 1, 0);
+        for (int i = 0; i < P; i++) hcnt[points_[i].host + 1]++;
+        for (int h = 0; h < N; h++) hcnt[h + 1] += hcnt[h];
         pt_order.resize(P);
-        for (int i = 0; i < P; i++) pt_order[i] = i;
-        std::vector<int> phost(P);
-        for (int i = 0; i < P; i++) phost[i] = fidx.at(points_[i].host_id);
-        std::stable_sort(pt_order.begin(), pt_order.end(), [&](int a, int b) { return phost[a] < phost[b]; });
         std::vector<int> pos(P);
-        for (int i = 0; i < P; i++) pos[pt_order[i]] = i;
-        // residuals sorted by bin = t*N + h, then device point position
+        { std::vector<int> o(hcnt.begin(), hcnt.end() - 1); for (int i = 0; i < P; i++) { const int q = o[points_[i].host]++; pt_order[q] = i; pos[i] = q; } }
+        // residuals: LSD counting sort, first by device point position, then (stable) by bin
         res_order.resize(R);
-        for (int i = 0; i < R; i++) res_order[i] = i;
-        std::vector<int64_t> key(R);
-        for (int i = 0; i < R; i++) {
-            const int t = fidx.at(res_[i].target_id), h = phost[res_[i].point];
-            key[i] = ((int64_t) (t * N + h) << 32) | (uint32_t) pos[res_[i].point];
-        }
-        std::sort(res_order.begin(), res_order.end(), [&](int a, int b) { return key[a] < key[b]; });
-        // host arrays
-        std::vector<int> h_pt_host(P); std::vector<float> h_x(P), h_y(P), h_idz(P), h_col((size_t) P * 8), h_wt((size_t) P * 8), h_prior(P), h_mrb(P), h_idh(P);
-        std::vector<double> h_id(P); std::vector<int> h_ng(P);
-        for (int i = 0; i < P; i++) {
-            const PointHost &p = points_[pt_order[i]];
-            h_pt_host[i] = phost[pt_order[i]]; h_x[i] = p.x; h_y[i] = p.y; h_id[i] = p.idepth; h_idz[i] = p.idepth_zero;
-            memcpy(&h_col[(size_t) i * 8], p.colors, 32); memcpy(&h_wt[(size_t) i * 8], p.weights, 32);
-            h_prior[i] = p.has_prior ? (float) cfg.idepth_fix_prior : 0.f;
-            h_ng[i] = p.num_good; h_mrb[i] = p.max_rel_bs; h_idh[i] = p.idepth_hessian;
-        }
-        std::vector<int> h_rp(R); std::vector<uint8_t> h_rh(R), h_rt(R);
-        int newest_begin = R;
-        for (int i = 0; i < R; i++) {
-            const ResHost &r = res_[res_order[i]];
-            h_rp[i] = pos[r.point]; h_rh[i] = (uint8_t) phost[r.point]; h_rt[i] = (uint8_t) fidx.at(r.target_id);
-            if (h_rt[i] == N - 1 && newest_begin == R) newest_begin = i;
-        }
-        // accumulate chunks: per bin
-        std::vector<int> cb, cbeg, ccnt; h_bin_chunk_begin.assign(N * N + 1, 0);
+        std::vector<int> bcnt(N * N + 1, 0);
         {
-            int i = 0;
-            for (int bin = 0; bin < N * N; bin++) {
-                h_bin_chunk_begin[bin] = (int) cb.size();
-                const int t = bin / N, h = bin % N;
-                int j = i;
-                while (j < R && h_rt[j] == t && h_rh[j] == h) j++;
-                for (int s = i; s < j; s += ACC_CHUNK) { cb.push_back(bin); cbeg.push_back(s); ccnt.push_back(std::min(ACC_CHUNK, j - s)); }
-                i = j;
-            }
-            h_bin_chunk_begin[N * N] = (int) cb.size();
+            std::vector<int> pcnt(P + 1, 0), tmp(R);
+            for (int i = 0; i < R; i++) pcnt[pos[res_[i].point] + 1]++;
+            for (int i = 0; i < P; i++) pcnt[i + 1] += pcnt[i];
+            for (int i = 0; i < R; i++) tmp[pcnt[pos[res_[i].point]]++] = i;
+            for (int i = 0; i < R; i++) { const ResHost &r = res_[i]; bcnt[r.target * N + points_[r.point].host + 1]++; }
+            for (int b = 0; b < N * N; b++) bcnt[b + 1] += bcnt[b];
+            std::vector<int> o(bcnt.begin(), bcnt.end() - 1);
+            for (int k = 0; k < R; k++) { const ResHost &r = res_[tmp[k]]; res_order[o[r.target * N + points_[r.point].host]++] = tmp[k]; }
         }
-        n_acc_chunks = (int) cb.size();
-        // Schur chunks: per host
-        std::vector<int> sh, sbeg, scnt; h_host_chunk_begin.assign(N + 1, 0);
-        {
-            int i = 0;
-            for (int h = 0; h < N; h++) {
-                h_host_chunk_begin[h] = (int) sh.size();
-                int j = i;
-                while (j < P && h_pt_host[j] == h) j++;
-                for (int s = i; s < j; s += SC_CHUNK) { sh.push_back(h); sbeg.push_back(s); scnt.push_back(std::min(SC_CHUNK, j - s)); }
-                i = j;
-            }
-            h_host_chunk_begin[N] = (int) sh.size();
-        }
-        n_sc_chunks = (int) sh.size();
+        lap("bdw.sort");
+        // chunk tables: accumulate chunks per bin, Schur chunks per host
+        h_bin_chunk_begin.assign(N * N + 1, 0);
+        for (int b = 0; b < N * N; b++) h_bin_chunk_begin[b + 1] = h_bin_chunk_begin[b] + (bcnt[b + 1] - bcnt[b] + ACC_CHUNK - 1) / ACC_CHUNK;
+        n_acc_chunks = h_bin_chunk_begin[N * N];
+        h_host_chunk_begin.assign(N + 1, 0);
+        for (int h = 0; h < N; h++) h_host_chunk_begin[h + 1] = h_host_chunk_begin[h] + (hcnt[h + 1] - hcnt[h] + SC_CHUNK - 1) / SC_CHUNK;
+        n_sc_chunks = h_host_chunk_begin[N];
         const int NB = 8 * N;
         const int sc_stride = ((NB * NB + NB * 4 + NB + 20) + 3) & ~3;
         const int n_lin_blocks = (R + LIN_THREADS - 1) / LIN_THREADS;
         const int n_pt_blocks = (P + 255) / 256;
-        // allocate
+        // arena layout
+        up.begin();
+        const size_t o_pt_host = up.take<int>(P), o_x = up.take<float>(P), o_y = up.take<float>(P), o_idz = up.take<float>(P), o_prior = up.take<float>(P),
+                     o_mrb = up.take<float>(P), o_idh = up.take<float>(P), o_ng = up.take<int>(P), o_id = up.take<double>(P),
+                     o_col = up.take<float>((size_t) P * 8), o_wt = up.take<float>((size_t) P * 8),
+                     o_rp = up.take<int>(R), o_rh = up.take<uint8_t>(R), o_rt = up.take<uint8_t>(R),
+                     o_cb = up.take<int>(n_acc_chunks), o_cbeg = up.take<int>(n_acc_chunks), o_ccnt = up.take<int>(n_acc_chunks), o_bcb = up.take<int>(N * N + 1),
+                     o_sh = up.take<int>(n_sc_chunks), o_sbeg = up.take<int>(n_sc_chunks), o_scnt = up.take<int>(n_sc_chunks), o_hcb = up.take<int>(N + 1);
+        CK(up.commit());
+        {
+            int *h_pt_host = up.host<int>(o_pt_host), *h_ng = up.host<int>(o_ng);
+            float *h_x = up.host<float>(o_x), *h_y = up.host<float>(o_y), *h_idz = up.host<float>(o_idz), *h_prior = up.host<float>(o_prior), *h_mrb = up.host<float>(o_mrb),
+                  *h_idh = up.host<float>(o_idh), *h_col = up.host<float>(o_col), *h_wt = up.host<float>(o_wt);
+            double *h_id = up.host<double>(o_id);
+            for (int i = 0; i < P; i++) {
+                const PointHost &p = points_[pt_order[i]];
+                h_pt_host[i] = p.host; h_x[i] = p.x; h_y[i] = p.y; h_id[i] = p.idepth; h_idz[i] = p.idepth_zero;
+                memcpy(&h_col[(size_t) i * 8], p.colors, 32); memcpy(&h_wt[(size_t) i * 8], p.weights, 32);
+                h_prior[i] = p.has_prior ? (float) cfg.idepth_fix_prior : 0.f;
+                h_ng[i] = p.num_good; h_mrb[i] = p.max_rel_bs; h_idh[i] = p.idepth_hessian;
+            }
+            int *h_rp = up.host<int>(o_rp); uint8_t *h_rh = up.host<uint8_t>(o_rh), *h_rt = up.host<uint8_t>(o_rt);
+            for (int i = 0; i < R; i++) {
+                const ResHost &r = res_[res_order[i]];
+                h_rp[i] = pos[r.point]; h_rh[i] = (uint8_t) points_[r.point].host; h_rt[i] = (uint8_t) r.target;
+            }
+            int *cb = up.host<int>(o_cb), *cbeg = up.host<int>(o_cbeg), *ccnt = up.host<int>(o_ccnt);
+            for (int b = 0, c = 0; b < N * N; b++)
+                for (int s0 = bcnt[b]; s0 < bcnt[b + 1]; s0 += ACC_CHUNK, c++) { cb[c] = b; cbeg[c] = s0; ccnt[c] = std::min(ACC_CHUNK, bcnt[b + 1] - s0); }
+            int *sh = up.host<int>(o_sh), *sbeg = up.host<int>(o_sbeg), *scnt = up.host<int>(o_scnt);
+            for (int h = 0, c = 0; h < N; h++)
+                for (int s0 = hcnt[h]; s0 < hcnt[h + 1]; s0 += SC_CHUNK, c++) { sh[c] = h; sbeg[c] = s0; scnt[c] = std::min(SC_CHUNK, hcnt[h + 1] - s0); }
+            memcpy(up.host<int>(o_bcb), h_bin_chunk_begin.data(), (N * N + 1) * sizeof(int));
+            memcpy(up.host<int>(o_hcb), h_host_chunk_begin.data(), (N + 1) * sizeof(int));
+        }
+        const int newest_begin = N > 0 ? bcnt[(N - 1) * N] : R;   // bins are t-major: residuals targeting the newest frame are the tail
+        lap("bdw.pack");
+        // device-only buffers
         const size_t Rz = std::max(R, 1), Pz = std::max(P, 1);
         CK(d_frames.reserve(MAXF)); CK(d_pairs.reserve(MAXF * MAXF)); CK(d_ctrl.reserve(1));
         CK(d_AH.reserve((size_t) N * N * 64)); CK(d_AT.reserve((size_t) N * N * 64)); CK(d_HM.reserve((size_t) n * n)); CK(d_bM.reserve(n)); CK(d_Pns.reserve((size_t) n * n));
-        CK(d_pt_host.reserve(Pz)); CK(d_pt_x.reserve(Pz)); CK(d_pt_y.reserve(Pz)); CK(d_pt_idepth.reserve(Pz)); CK(d_pt_idz.reserve(Pz)); CK(d_pt_idb.reserve(Pz));
-        CK(d_pt_colors.reserve(Pz * 8)); CK(d_pt_weights.reserve(Pz * 8)); CK(d_pt_priorF.reserve(Pz));
-        CK(d_pt_Hdd.reserve(Pz)); CK(d_pt_bd.reserve(Pz)); CK(d_pt_Hcd.reserve(Pz * 4)); CK(d_pt_HdiF.reserve(Pz)); CK(d_pt_bdSumF.reserve(Pz)); CK(d_pt_idh.reserve(Pz)); CK(d_pt_mrb.reserve(Pz));
-        CK(d_pt_num_good.reserve(Pz)); CK(d_pt_ngood_cur.reserve(Pz)); CK(d_pt_step.reserve(Pz));
-        CK(d_r_point.reserve(Rz)); CK(d_r_host.reserve(Rz)); CK(d_r_target.reserve(Rz));
+        CK(d_pt_idb.reserve(Pz));
+        CK(d_pt_Hdd.reserve(Pz)); CK(d_pt_bd.reserve(Pz)); CK(d_pt_Hcd.reserve(Pz * 4)); CK(d_pt_HdiF.reserve(Pz)); CK(d_pt_bdSumF.reserve(Pz));
+        CK(d_pt_ngood_cur.reserve(Pz)); CK(d_pt_step.reserve(Pz));
         CK(d_r_state0.reserve(Rz)); CK(d_r_state1.reserve(Rz)); CK(d_r_energy0.reserve(Rz)); CK(d_r_energy1.reserve(Rz)); CK(d_r_good0.reserve(Rz)); CK(d_r_good1.reserve(Rz));
         CK(d_r_new_state.reserve(Rz)); CK(d_r_new_energy.reserve(Rz)); CK(d_r_new_energy_wo.reserve(Rz)); CK(d_r_alive.reserve(Rz)); CK(d_r_center.reserve(Rz * 3));
         CK(d_rj.reserve(Rz * RJ_STRIDE)); CK(d_T0.reserve(Pz * N * T_STRIDE)); CK(d_T1.reserve(Pz * N * T_STRIDE));
         if (want_dbg) CK(d_dbg.reserve(Rz * DBG_STRIDE));
         CK(d_energy_part.reserve(std::max(n_lin_blocks, 1)));
         CK(d_acc0.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N)); CK(d_acc1.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N));
-        CK(d_acc_chunk_bin.reserve(std::max(n_acc_chunks, 1))); CK(d_acc_chunk_begin.reserve(std::max(n_acc_chunks, 1))); CK(d_acc_chunk_count.reserve(std::max(n_acc_chunks, 1)));
-        CK(d_bin_chunk_begin.reserve(N * N + 1));
         CK(d_sc_part.reserve((size_t) std::max(n_sc_chunks, 1) * sc_stride));
-        CK(d_sc_chunk_host.reserve(std::max(n_sc_chunks, 1))); CK(d_sc_chunk_begin.reserve(std::max(n_sc_chunks, 1))); CK(d_sc_chunk_count.reserve(std::max(n_sc_chunks, 1)));
-        CK(d_host_chunk_begin.reserve(N + 1));
+        CK(d_accR.reserve((size_t) N * N * ACC_N)); CK(d_scR.reserve((size_t) N * sc_stride));
         CK(d_HApart.reserve((size_t) N * n * n)); CK(d_HSpart.reserve((size_t) N * n * n)); CK(d_bApart.reserve((size_t) N * n)); CK(d_bSpart.reserve((size_t) N * n));
         CK(d_sys.reserve((size_t) 2 * n * n + 2 * n)); CK(d_x.reserve(n)); CK(d_xAd.reserve((size_t) N * N * 8)); CK(d_pt_part.reserve((size_t) std::max(n_pt_blocks, 1) * 3));
-        // upload
-#define UP(dst, src, cnt) if ((cnt) > 0) CK(cudaMemcpyAsync((dst).p, (src).data(), (size_t) (cnt) * sizeof(*(dst).p), cudaMemcpyHostToDevice, stream))
-        UP(d_pt_host, h_pt_host, P); UP(d_pt_x, h_x, P); UP(d_pt_y, h_y, P); UP(d_pt_idepth, h_id, P); UP(d_pt_idz, h_idz, P);
-        UP(d_pt_colors, h_col, (size_t) P * 8); UP(d_pt_weights, h_wt, (size_t) P * 8); UP(d_pt_priorF, h_prior, P);
-        UP(d_pt_num_good, h_ng, P); UP(d_pt_mrb, h_mrb, P); UP(d_pt_idh, h_idh, P);
-        UP(d_r_point, h_rp, R); UP(d_r_host, h_rh, R); UP(d_r_target, h_rt, R);
-        UP(d_acc_chunk_bin, cb, n_acc_chunks); UP(d_acc_chunk_begin, cbeg, n_acc_chunks); UP(d_acc_chunk_count, ccnt, n_acc_chunks);
-        UP(d_bin_chunk_begin, h_bin_chunk_begin, N * N + 1);
-        UP(d_sc_chunk_host, sh, n_sc_chunks); UP(d_sc_chunk_begin, sbeg, n_sc_chunks); UP(d_sc_chunk_count, scnt, n_sc_chunks);
-        UP(d_host_chunk_begin, h_host_chunk_begin, N + 1);
-#undef UP
-        CK(cudaStreamSynchronize(stream));   // host vectors go out of scope
+        lap("bdw.alloc");
+        if (up.used) CK(cudaMemcpyAsync(up.d.p, up.h.p, up.used, cudaMemcpyHostToDevice, stream));
+        // views into the arena
+#define VIEW(buf, T, off) do { (buf).p = up.dev<T>(off); (buf).view = true; (buf).cap = 0; } while (0)
+        VIEW(d_pt_host, int, o_pt_host); VIEW(d_pt_x, float, o_x); VIEW(d_pt_y, float, o_y); VIEW(d_pt_idz, float, o_idz); VIEW(d_pt_priorF, float, o_prior);
+        VIEW(d_pt_mrb, float, o_mrb); VIEW(d_pt_idh, float, o_idh); VIEW(d_pt_num_good, int, o_ng); VIEW(d_pt_idepth, double, o_id);
+        VIEW(d_pt_colors, float, o_col); VIEW(d_pt_weights, float, o_wt); VIEW(d_r_point, int, o_rp); VIEW(d_r_host, uint8_t, o_rh); VIEW(d_r_target, uint8_t, o_rt);
+        VIEW(d_acc_chunk_bin, int, o_cb); VIEW(d_acc_chunk_begin, int, o_cbeg); VIEW(d_acc_chunk_count, int, o_ccnt); VIEW(d_bin_chunk_begin, int, o_bcb);
+        VIEW(d_sc_chunk_host, int, o_sh); VIEW(d_sc_chunk_begin, int, o_sbeg); VIEW(d_sc_chunk_count, int, o_scnt); VIEW(d_host_chunk_begin, int, o_hcb);
+#undef VIEW
+        lap("bdw.upload");
         // DevWin
         DevWin &w = dw;
         memset(&w, 0, sizeof(w));
@@ -482,6 +576,7 @@ public:
         w.acc_chunk_bin = d_acc_chunk_bin.p; w.acc_chunk_begin = d_acc_chunk_begin.p; w.acc_chunk_count = d_acc_chunk_count.p; w.bin_chunk_begin = d_bin_chunk_begin.p;
         w.sc_part = d_sc_part.p; w.sc_stride = sc_stride; w.sc_chunk_host = d_sc_chunk_host.p; w.sc_chunk_begin = d_sc_chunk_begin.p; w.sc_chunk_count = d_sc_chunk_count.p;
         w.host_chunk_begin = d_host_chunk_begin.p;
+        w.accR = d_accR.p; w.scR = d_scR.p;
         w.HApart = d_HApart.p; w.bApart = d_bApart.p; w.HSpart = d_HSpart.p; w.bSpart = d_bSpart.p; w.sys = d_sys.p; w.x = d_x.p; w.xAd = d_xAd.p;
         w.pt_part = d_pt_part.p; w.n_pt_blocks = n_pt_blocks;
         dirty = false;
@@ -509,6 +604,8 @@ public:
 
     // run() prologue: updateCamera, computeAdjoints, computeDelta (priors), nullspace projector; reset residuals
     int prepare(const double *cams) {
+        TSCOPE("prepare(total)");
+        Lap lap(timers);
         if (!have_calib) { set_error("calibration not set"); return CMLBA_ERR_STATE; }
         const int N = (int) frames_.size();
         if (N < 1) { set_error("no frames"); return CMLBA_ERR_STATE; }
@@ -517,6 +614,7 @@ public:
         if (dirty) { int rc = build_device_window(); if (rc) return rc; }
         const int n = 8 * N + 4;
         double sc[10]; scales(sc);
+        lap("prep.build");
         // updateCamera -> setStateFromCamera (DSOFrame.h:143-151)
         for (int i = 0; i < N; i++) {
             FrameHost &f = frames_[i];
@@ -603,6 +701,7 @@ public:
         Ctrl c; memset(&c, 0, sizeof(c));
         c.lambda = (double) cfg.fixed_lambda;
         const int R = dw.R, P = dw.P;
+        lap("prep.host_math");
         CK(cudaMemcpyAsync(d_frames.p, fd.data(), N * sizeof(FrameDev), cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(d_AH.p, AH.data(), AH.size() * 8, cudaMemcpyHostToDevice, stream));
         CK(cudaMemcpyAsync(d_AT.p, AT.data(), AT.size() * 8, cudaMemcpyHostToDevice, stream));
@@ -625,6 +724,7 @@ public:
         pairs_kernel<<<(N * N + 63) / 64, 64, 0, stream>>>(dw); launches++;
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(stream));   // host vectors above are pageable stack/heap objects
+        lap("prep.upload_reset");
         prepared = true;
         return CMLBA_OK;
     }
@@ -645,9 +745,19 @@ public:
         accumulate_kernel<<<dw.n_acc_chunks, 128, 0, stream>>>(dw, respect_done); launches++;
     }
     void launch_post(int mode, int respect_done) { post_linearize_kernel<<<1, 1024, 0, stream>>>(dw, mode, respect_done); launches++; }
-    int launch_solve_sequence(int respect_done) {
+    void launch_schur(int respect_done) {
         if (dw.n_sc_chunks > 0) { schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, respect_done); launches++; }
+    }
+    // fixed-order reduction of the chunk partials (wide grid), then one stitch CTA per host frame
+    void launch_stitch(int respect_done) {
+        const int N = dw.N, NB = 8 * N;
+        const int tot = N * N * ACC_N + N * (NB * NB + NB * 4 + NB + 20);
+        reduce_partials_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(dw, respect_done); launches++;
         stitch_kernel<<<dw.N, 256, stitch_smem(), stream>>>(dw, respect_done); launches++;
+    }
+    int launch_solve_sequence(int respect_done) {
+        launch_schur(respect_done);
+        launch_stitch(respect_done);
         sum_partials_kernel<<<32, 256, 0, stream>>>(dw, respect_done); launches++;
         if (world > 1) { int rc = allreduce_system(); if (rc) return rc; }
         solve_kernel<<<1, 256, solve_smem(), stream>>>(dw, respect_done); launches++;
@@ -663,6 +773,8 @@ public:
     }
 
     int run(const double *cams, int iterations, int update_points_only, cmlba_run_result *out) {
+        TSCOPE("run(total)");
+        Lap lap(timers);
         if (!cfg.force_accept) { set_error("forceAccept=false (step rejection) is not implemented on the device path yet"); return CMLBA_ERR_UNSUPPORTED; }
         int rc = prepare(cams);
         if (rc) return rc;
@@ -680,6 +792,7 @@ public:
         launch_linearize(1, 0); launch_post(2, 0);
         CK(cudaEventRecord(ev1, stream));
         CK(cudaGetLastError());
+        lap("run.launch");
         rc = finish_run(out);
         if (out) {
             float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
@@ -690,29 +803,43 @@ public:
 
     // read results back, update the host bookkeeping (the "scatter" edge of the boundary)
     int finish_run(cmlba_run_result *out) {
+        TSCOPE("finish_run");
+        Lap flap(timers);
         const int N = dw.N, P = dw.P, R = dw.R;
-        std::vector<FrameDev> fd(N); Ctrl c;
-        std::vector<double> id(P); std::vector<float> idz(P), idh(P), mrb(P); std::vector<int> ng(P);
-        std::vector<uint8_t> alive(R), st0(R), st1(R); std::vector<float> en0(R), en1(R);
-        CK(cudaMemcpyAsync(fd.data(), d_frames.p, N * sizeof(FrameDev), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(&c, d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost, stream));
+        // one pinned block: frames | ctrl | idepth | idz idh mrb | ng | alive st0 st1 | en0 en1
+        size_t off = 0;
+        auto take = [&](size_t nb) { const size_t o = (off + 15) & ~(size_t) 15; off = o + nb; return o; };
+        const size_t o_fd = take(N * sizeof(FrameDev)), o_c = take(sizeof(Ctrl)), o_id = take((size_t) P * 8), o_idz = take((size_t) P * 4), o_idh = take((size_t) P * 4),
+                     o_mrb = take((size_t) P * 4), o_ng = take((size_t) P * 4), o_al = take(R), o_s0 = take(R), o_s1 = take(R), o_e0 = take((size_t) R * 4), o_e1 = take((size_t) R * 4);
+        CK(fin_h.reserve(off));
+        char *hb = fin_h.p;
+        CK(cudaMemcpyAsync(hb + o_fd, d_frames.p, N * sizeof(FrameDev), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(hb + o_c, d_ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
         if (P) {
-            CK(cudaMemcpyAsync(id.data(), d_pt_idepth.p, P * 8, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(idz.data(), d_pt_idz.p, P * 4, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(idh.data(), d_pt_idh.p, P * 4, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(mrb.data(), d_pt_mrb.p, P * 4, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(ng.data(), d_pt_num_good.p, P * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_id, d_pt_idepth.p, (size_t) P * 8, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_idz, d_pt_idz.p, (size_t) P * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_idh, d_pt_idh.p, (size_t) P * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_mrb, d_pt_mrb.p, (size_t) P * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_ng, d_pt_num_good.p, (size_t) P * 4, cudaMemcpyDeviceToHost, stream));
         }
         if (R) {
-            CK(cudaMemcpyAsync(alive.data(), d_r_alive.p, R, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(st0.data(), d_r_state0.p, R, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(st1.data(), d_r_state1.p, R, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(en0.data(), d_r_energy0.p, R * 4, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(en1.data(), d_r_energy1.p, R * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_al, d_r_alive.p, R, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_s0, d_r_state0.p, R, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_s1, d_r_state1.p, R, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_e0, d_r_energy0.p, (size_t) R * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_e1, d_r_energy1.p, (size_t) R * 4, cudaMemcpyDeviceToHost, stream));
         }
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
-        double sc[10]; scales(sc);
+        flap("finish.wait_d2h");
+        const FrameDev *fd = reinterpret_cast<const FrameDev *>(hb + o_fd);
+        const Ctrl c = *reinterpret_cast<const Ctrl *>(hb + o_c);
+        const double *id = reinterpret_cast<const double *>(hb + o_id);
+        const float *idz = reinterpret_cast<const float *>(hb + o_idz), *idh = reinterpret_cast<const float *>(hb + o_idh), *mrb = reinterpret_cast<const float *>(hb + o_mrb);
+        const int *ng = reinterpret_cast<const int *>(hb + o_ng);
+        const uint8_t *alive = reinterpret_cast<const uint8_t *>(hb + o_al);
+        const uint8_t *st = reinterpret_cast<const uint8_t *>(hb + (c.cur ? o_s1 : o_s0));
+        const float *en = reinterpret_cast<const float *>(hb + (c.cur ? o_e1 : o_e0));
         for (int i = 0; i < N; i++) {
             FrameHost &f = frames_[i]; const FrameDev &d = fd[i];
             for (int k = 0; k < 10; k++) { f.state[k] = d.state[k]; f.state_zero[k] = d.state_zero[k]; }
@@ -725,27 +852,29 @@ public:
             PointHost &p = points_[pt_order[i]];
             p.idepth = id[i]; p.idepth_zero = idz[i]; p.idepth_hessian = idh[i]; p.max_rel_bs = mrb[i]; p.num_good = ng[i];
         }
-        const uint8_t *st = c.cur ? st1.data() : st0.data(); const float *en = c.cur ? en1.data() : en0.data();
-        std::vector<ResHost> keep; keep.reserve(R);
+        // residual states; dropped residuals (device order) are marked and squeezed out in host order afterwards
         std::vector<int> cnt(points_.size(), 0);
+        int dropped = 0;
         for (int i = 0; i < R; i++) {
-            ResHost r = res_[res_order[i]];
+            ResHost &r = res_[res_order[i]];
             r.state = st[i]; r.energy = en[i];
             PointHost &p = points_[r.point];
+            const int64_t tid = frames_[r.target].id;
             // setResidualState (BA:1616-1620) / cleared lastResiduals of deleted residuals (BA:1630-1633)
-            for (int s = 0; s < 2; s++) if (p.last_frame[s] == r.target_id) { if (alive[i]) p.last_state[s] = r.state; else p.last_frame[s] = -1; break; }
-            if (alive[i]) { keep.push_back(r); cnt[r.point]++; }
+            for (int s = 0; s < 2; s++) if (p.last_frame[s] == tid) { if (alive[i]) p.last_state[s] = r.state; else p.last_frame[s] = -1; break; }
+            if (alive[i]) cnt[r.point]++; else { r.point = -1; dropped++; }
         }
+        if (dropped) { size_t nr = 0; for (size_t i = 0; i < res_.size(); i++) if (res_[i].point >= 0) res_[nr++] = res_[i]; res_.resize(nr); }
         outliers_.clear();
         int nout = 0;
         for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive && cnt[i] == 0) { points_[i].alive = false; outliers_.push_back(points_[i].id); nout++; }
-        const int dropped = R - (int) keep.size();
-        res_.swap(keep);
         if (out) {
             out->iterations_done = c.iteration; out->num_residuals = R; out->num_dropped = dropped; out->num_outliers = nout;
             out->energy_first = c.energy_first; out->energy_last = c.energy_last;
         }
-        if (dropped > 0 || nout > 0) compact(); else { dirty = false; }
+        flap("finish.scatter");
+        if (nout > 0) compact(); else dirty = dropped > 0;
+        flap("finish.compact");
         prepared = false;
         if (c.failed) { set_error("non-finite energy or step (reference run() returns false)"); return CMLBA_ERR_NUMERIC; }
         return CMLBA_OK;
@@ -774,7 +903,7 @@ public:
         auto flush = [&]() { if (flush_l2) l2_flush_kernel<<<148 * 8, 256, 0, stream>>>(d_flush.p, flush_bytes / sizeof(float4)); };
         // the committed buffers must hold a linearization for schur/stitch to chew on
         launch_linearize(0, 0); launch_accumulate(0); launch_post(0, 0);
-        for (int i = 0; i < warmup; i++) { flush(); launch_linearize(0, 0); launch_accumulate(0); schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, 0); stitch_kernel<<<dw.N, 256, stitch_smem(), stream>>>(dw, 0); }
+        for (int i = 0; i < warmup; i++) { flush(); launch_linearize(0, 0); launch_accumulate(0); launch_schur(0); launch_stitch(0); }
         CK(cudaStreamSynchronize(stream));
         double tot = 0, tk[4] = {0, 0, 0, 0};
         const int l0 = launches;
@@ -782,8 +911,7 @@ public:
             flush();
             CK(cudaEventRecord(ev[0], stream));
             launch_linearize(0, 0); launch_accumulate(0);
-            schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, 0); launches++;
-            stitch_kernel<<<dw.N, 256, stitch_smem(), stream>>>(dw, 0); launches++;
+            launch_schur(0); launch_stitch(0);
             if (world > 1) { sum_partials_kernel<<<32, 256, 0, stream>>>(dw, 0); launches++; int rc = allreduce_system(); if (rc) return rc; }
             CK(cudaEventRecord(ev[1], stream));
             CK(cudaStreamSynchronize(stream));
@@ -794,8 +922,8 @@ public:
             flush();
             CK(cudaEventRecord(ev[0], stream)); launch_linearize(0, 0);
             CK(cudaEventRecord(ev[1], stream)); launch_accumulate(0);
-            CK(cudaEventRecord(ev[2], stream)); schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, 0);
-            CK(cudaEventRecord(ev[3], stream)); stitch_kernel<<<dw.N, 256, stitch_smem(), stream>>>(dw, 0);
+            CK(cudaEventRecord(ev[2], stream)); launch_schur(0);
+            CK(cudaEventRecord(ev[3], stream)); launch_stitch(0);
             CK(cudaEventRecord(ev[4], stream));
             CK(cudaStreamSynchronize(stream));
             for (int k = 0; k < 4; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); tk[k] += ms; }
@@ -821,6 +949,8 @@ public:
         return CMLBA_OK;
     }
     int read(const std::string &name, void *dst, size_t cap, size_t *bytes) {
+        if (name == "host_timing") { const std::string t = timers.text(); return host_out(t.data(), t.size(), dst, cap, bytes); }
+        if (name == "host_timing_reset") { timers.acc.clear(); if (bytes) *bytes = 0; return CMLBA_OK; }
         if (name == "enable_dbg") { want_dbg = true; dirty = true; prepared = false; if (bytes) *bytes = 0; return CMLBA_OK; }
         if (dirty || !d_ctrl.p) { set_error("window not built yet (cmlba_prepare / cmlba_run first)"); return CMLBA_ERR_STATE; }
         CK(cudaSetDevice(device));
@@ -985,7 +1115,7 @@ int cmlba_get_residuals(const cmlba_handle *h, int64_t *pid, int64_t *tid, int32
     const auto &rs = h->eng.res_;
     for (size_t i = 0; i < rs.size(); i++) {
         if (pid) pid[i] = h->eng.points_[rs[i].point].id;
-        if (tid) tid[i] = rs[i].target_id;
+        if (tid) tid[i] = h->eng.frames_[rs[i].target].id;
         if (state) state[i] = rs[i].state;
         if (energy) energy[i] = rs[i].energy;
     }

@@ -452,6 +452,35 @@ __device__ __forceinline__ int acc_index(int r, int c) {
     return 85 + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5));
 }
 
+// Fixed-order sums of the chunk partials, one thread per output element (wide grid: the per-host stitch CTAs
+// would otherwise walk ~32 chunks x 17 elements per thread with exposed load latency).
+//   accR[bin][ACC_N]  (bin = t*N+h)  = sum_c acc_part[cur][c][:]   for the chunks c of the bin
+//   scR[h][sc_tot]                   = sum_c sc_part[c][:]         for the chunks c of host h
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const DevWin w, const int respect_done) {
+    if (respect_done && w.ctrl->done) return;
+    const int N = w.N, NB = 8 * N;
+    const int cur = w.ctrl->cur;
+    const int n_acc = N * N * ACC_N, sc_tot = NB * NB + NB * 4 + NB + 20;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e < n_acc) {
+        const int bin = e / ACC_N, k = e - bin * ACC_N;
+        const int cb = w.bin_chunk_begin[bin], ce = w.bin_chunk_begin[bin + 1];
+        const float *src = w.acc_part[cur] + (size_t) cb * ACC_N + k;
+        double s = 0.0;
+#pragma unroll 8
+        for (int c = cb; c < ce; c++, src += ACC_N) s += (double) __ldg(src);
+        w.accR[e] = s;
+    } else if (e < n_acc + N * sc_tot) {
+        const int q = e - n_acc, h = q / sc_tot, k = q - h * sc_tot;
+        const int cb = w.host_chunk_begin[h], ce = w.host_chunk_begin[h + 1];
+        const float *src = w.sc_part + (size_t) cb * w.sc_stride + k;
+        double s = 0.0;
+#pragma unroll 8
+        for (int c = cb; c < ce; c++, src += w.sc_stride) s += (double) __ldg(src);
+        w.scR[q] = s;
+    }
+}
+
 // Stitching (fp64): one CTA per host frame i.  Every output block of the per-host partial matrices is owned
 // by exactly one thread, so there are no atomics; partials are summed over hosts in solve_kernel.
 // AT is diagonal (identity pose block, -a, -1, row-scaled; BA:1075-1092): only its diagonal is used.
@@ -459,7 +488,6 @@ __global__ void __launch_bounds__(256) stitch_kernel(const DevWin w, const int r
     if (respect_done && w.ctrl->done) return;
     extern __shared__ __align__(16) double smd[];
     const int N = w.N, NB = 8 * N, n = w.n, i = blockIdx.x, tid = threadIdx.x;
-    const int cur = w.ctrl->cur;
     double *D = smd;                 // [NB][NB]
     double *accA = D + NB * NB;      // [N][ACC_N]
     double *G = accA + N * ACC_N;    // [8][NB]   G[r][k*8+m] = AH_ik[r][m]
@@ -470,19 +498,12 @@ __global__ void __launch_bounds__(256) stitch_kernel(const DevWin w, const int r
     double *small = atd + NB;        // Hcc[16] bc[4]
     for (int e = tid; e < 8 * NB; e += 256) { const int r = e / NB, km = e % NB, k = km >> 3, m = km & 7; G[e] = w.AH[((size_t) (i * N + k)) * 64 + r * 8 + m]; }
     for (int e = tid; e < NB; e += 256) { const int j = e >> 3, r = e & 7; atd[e] = w.AT[((size_t) (i * N + j)) * 64 + r * 8 + r]; }
-    // reduce the chunk partials of bins (host i, target t), bin = t*N + i
-    for (int e = tid; e < N * ACC_N; e += 256) {
-        const int t = e / ACC_N, k = e % ACC_N, bin = t * N + i;
-        double s = 0.0;
-        for (int c = w.bin_chunk_begin[bin]; c < w.bin_chunk_begin[bin + 1]; c++) s += (double) w.acc_part[cur][(size_t) c * ACC_N + k];
-        accA[e] = s;
-    }
-    // reduce the Schur partials of host i
-    const int cb = w.host_chunk_begin[i], ce = w.host_chunk_begin[i + 1];
+    // reduced partials (reduce_partials_kernel): bins (host i, target t) = t*N + i, Schur blocks of host i
+    for (int e = tid; e < N * ACC_N; e += 256) { const int t = e / ACC_N, k = e % ACC_N; accA[e] = w.accR[(size_t) (t * N + i) * ACC_N + k]; }
     const int tot = NB * NB + NB * 4 + NB + 20;
+    const double *scr = w.scR + (size_t) i * tot;
     for (int e = tid; e < tot; e += 256) {
-        double s = 0.0;
-        for (int c = cb; c < ce; c++) s += (double) w.sc_part[(size_t) c * w.sc_stride + e];
+        const double s = scr[e];
         if (e < NB * NB) D[e] = s;
         else if (e < NB * NB + NB * 4) E[e - NB * NB] = s;
         else if (e < NB * NB + NB * 5) EB[e - NB * NB - NB * 4] = s;

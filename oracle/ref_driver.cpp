@@ -521,7 +521,8 @@ int main(int argc, char **argv) {
             RefWindow *w2 = buildWindow(in);
             a = now_s(); w2->ba->run(w2->updatePointsOnly); b = now_s();
             tRun = std::min(tRun, b - a);
-            itDone = w2->iterations;
+            // GN iterations actually executed (run() leaves early on convergence, BA:879): one P-energy sample before the loop (BA:798) + one per accepted iteration (BA:847)
+            itDone = (int) w2->ba->mStatisticEnergyP->mWaitingValues.size() - 1;
         }
         printf("{\"residuals\": %zu, \"t_linearize\": %.6f, \"t_top\": %.6f, \"t_sc\": %.6f, \"t_run\": %.6f, \"iterations\": %d, \"threads\": 1, \"repeat\": %d}\n",
                R, tLin, tTop, tSC, tRun, itDone, repeat);
