@@ -136,6 +136,7 @@ struct PointHost {
     int64_t id = 0;
     int64_t host_id = 0;
     int host = 0;                // index of the host frame in frames_
+    uint16_t res_mask = 0;       // bit t: residual to frames_[t]
     float x = 0, y = 0;
     double idepth = 0;
     float idepth_zero = 0;
@@ -148,11 +149,15 @@ struct PointHost {
     bool alive = true;
 };
 
-struct ResHost {
-    int point;          // index into points_
-    int target;         // index of the target frame in frames_
-    int state = CMLBA_RES_IN;
-    float energy = 0;
+// Residual bookkeeping: a residual (point, target frame) exists iff bit `target slot` of PointHost::res_mask is set
+// (DSOContext keeps a pointer set per point, DSOContext.h:58-75).  State/energy of the last run() live in a
+// device-order snapshot (ResSnapshot) that cmlba_get_residuals decodes on demand.
+struct ResSnapshot {
+    bool valid = false;
+    std::vector<int64_t> frame_id, point_id;       // frame ids by slot, point ids by device position, at run() time
+    std::vector<int> r_point;                      // device point position per residual
+    std::vector<uint8_t> r_target, state, alive;
+    std::vector<float> energy;
 };
 
 // --- NCCL through dlopen (multi-GPU only) -----------------------------------------------------
@@ -192,7 +197,7 @@ public:
     int W = 0, H = 0;
     std::vector<FrameHost> frames_;
     std::vector<PointHost> points_;
-    std::vector<ResHost> res_;
+    ResSnapshot snap;
     IdMap point_index_;
     std::vector<int64_t> outliers_;
     int key_counter = 0;
@@ -201,7 +206,6 @@ public:
     std::vector<double> HM, bM;   // marginalisation prior, (8N+4)^2 ; zero in this round
     // device-window layout (host mirrors)
     std::vector<int> pt_order;    // device point i -> points_ index
-    std::vector<int> res_order;   // device residual i -> res_ index
     DevWin dw;
     int launches = 0;
     // multi-GPU
@@ -217,6 +221,7 @@ public:
     int stage_flip = 0;
     cudaEvent_t ev_copy = nullptr;
     UploadArena up;                               // every array build_device_window uploads
+    size_t up_o_rp = 0, up_o_rt = 0;              // arena offsets of r_point / r_target (host mirrors stay valid until the next build)
     PinnedBuf<char> pt_stage_h, fin_h; DevBuf<char> pt_stage_d;   // add_points round trip, finish_run read-back
     DevBuf<uint8_t> d_r_host, d_r_target, d_r_state0, d_r_state1, d_r_good0, d_r_good1, d_r_new_state, d_r_alive;
     bool want_dbg = false;
@@ -328,10 +333,9 @@ public:
         const int slot = (int) frames_.size();
         frames_.push_back(f);
         // residuals from all existing points to the new frame (BA:455-460); lastResiduals slot 0 (BA:374-375)
-        res_.reserve(res_.size() + points_.size());
         for (size_t p = 0; p < points_.size(); p++) {
             if (!points_[p].alive) continue;
-            res_.push_back(ResHost{(int) p, slot});
+            points_[p].res_mask |= (uint16_t) (1u << slot);
             points_[p].last_frame[1] = points_[p].last_frame[0]; points_[p].last_state[1] = points_[p].last_state[0];
             points_[p].last_frame[0] = id; points_[p].last_state[0] = CMLBA_RES_IN;
         }
@@ -384,14 +388,11 @@ public:
         CK(cudaMemcpyAsync(pt_stage_h.p + o_c, pt_stage_d.p + o_c, nn * 64, cudaMemcpyDeviceToHost, stream));
         // residual bookkeeping overlaps the device round trip
         const int64_t newest = frames_.back().id, second = NF >= 2 ? frames_[NF - 2].id : -1;
-        res_.reserve(res_.size() + nn * (NF - 1));
+        const uint16_t all = (uint16_t) ((1u << NF) - 1u);
         for (size_t i = 0; i < nn; i++) {
             PointHost &p = points_[first + i];
             point_index_.set(p.id, (int) (first + i));
-            for (int f = 0; f < NF; f++) {
-                if (f == p.host) continue;
-                res_.push_back(ResHost{(int) (first + i), f});
-            }
+            p.res_mask = (uint16_t) (all & ~(1u << p.host));      // createResidual towards every other frame (BA:399-403)
             if (p.host != NF - 1) { p.last_frame[0] = newest; p.last_state[0] = CMLBA_RES_IN; }
             if (NF >= 2 && p.host != NF - 2) { p.last_frame[1] = second; p.last_state[1] = CMLBA_RES_IN; }
         }
@@ -406,13 +407,9 @@ public:
 
     // drop dead points (and their residuals), rebuild the id index
     void compact() {
-        std::vector<int> remap(points_.size(), -1);
         size_t np = 0;
-        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive) { remap[i] = (int) np; if (np != i) points_[np] = points_[i]; np++; }
+        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive) { if (np != i) points_[np] = points_[i]; np++; }
         points_.resize(np);
-        size_t nr = 0;
-        for (size_t i = 0; i < res_.size(); i++) { const int q = remap[res_[i].point]; if (q >= 0) { res_[nr] = res_[i]; res_[nr].point = q; nr++; } }
-        res_.resize(nr);
         point_index_.clear(); point_index_.reserve(np);
         for (size_t i = 0; i < np; i++) point_index_.set(points_[i].id, (int) i);
         dirty = true; prepared = false;
@@ -429,14 +426,12 @@ public:
     int remove_frame(int64_t id) {
         const int fi = frame_index(id);
         if (fi < 0) { set_error("unknown frame id"); return CMLBA_ERR_ARG; }
-        for (auto &p : points_) { if (p.host == fi) p.alive = false; else if (p.host > fi) p.host--; }
-        size_t nr = 0;
-        for (size_t i = 0; i < res_.size(); i++) if (res_[i].target != fi) { res_[nr] = res_[i]; if (res_[nr].target > fi) res_[nr].target--; nr++; }
-        res_.resize(nr);
-        // points left without residuals disappear as well (DSOContext.h:205-216)
-        std::vector<int> cnt(points_.size(), 0);
-        for (auto &r : res_) cnt[r.point]++;
-        for (size_t i = 0; i < points_.size(); i++) if (cnt[i] == 0) points_[i].alive = false;
+        const uint16_t low = (uint16_t) ((1u << fi) - 1u);
+        for (auto &p : points_) {
+            if (p.host == fi) p.alive = false; else if (p.host > fi) p.host--;
+            p.res_mask = (uint16_t) ((p.res_mask & low) | ((p.res_mask >> (fi + 1)) << fi));   // squeeze slot fi out
+            if (p.res_mask == 0) p.alive = false;     // points left without residuals disappear as well (DSOContext.h:205-216)
+        }
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
         if (frames_[fi].d_img) img_pool.push_back(frames_[fi].d_img);
@@ -452,7 +447,7 @@ public:
     int build_device_window() {
         TSCOPE("build_device_window");
         Lap lap(timers);
-        const int N = (int) frames_.size(), P = (int) points_.size(), R = (int) res_.size();
+        const int N = (int) frames_.size(), P = (int) points_.size();
         const int n = 8 * N + 4;
         CK(cudaSetDevice(device));
         // points: stable counting sort by host
@@ -460,21 +455,17 @@ public:
         for (int i = 0; i < P; i++) hcnt[points_[i].host + 1]++;
         for (int h = 0; h < N; h++) hcnt[h + 1] += hcnt[h];
         pt_order.resize(P);
-        std::vector<int> pos(P);
-        { std::vector<int> o(hcnt.begin(), hcnt.end() - 1); for (int i = 0; i < P; i++) { const int q = o[points_[i].host]++; pt_order[q] = i; pos[i] = q; } }
-        // residuals: LSD counting sort, first by device point position, then (stable) by bin
-        res_order.resize(R);
+        { std::vector<int> o(hcnt.begin(), hcnt.end() - 1); for (int i = 0; i < P; i++) pt_order[o[points_[i].host]++] = i; }
+        // residuals per bin = t*N+h from the per-point masks (device order inside a bin = device point order: no sort)
         std::vector<int> bcnt(N * N + 1, 0);
-        {
-            std::vector<int> pcnt(P + 1, 0), tmp(R);
-            for (int i = 0; i < R; i++) pcnt[pos[res_[i].point] + 1]++;
-            for (int i = 0; i < P; i++) pcnt[i + 1] += pcnt[i];
-            for (int i = 0; i < R; i++) tmp[pcnt[pos[res_[i].point]]++] = i;
-            for (int i = 0; i < R; i++) { const ResHost &r = res_[i]; bcnt[r.target * N + points_[r.point].host + 1]++; }
-            for (int b = 0; b < N * N; b++) bcnt[b + 1] += bcnt[b];
-            std::vector<int> o(bcnt.begin(), bcnt.end() - 1);
-            for (int k = 0; k < R; k++) { const ResHost &r = res_[tmp[k]]; res_order[o[r.target * N + points_[r.point].host]++] = tmp[k]; }
+        std::vector<uint16_t> dmask(P);
+        for (int i = 0; i < P; i++) {
+            const PointHost &p = points_[pt_order[i]];
+            dmask[i] = p.res_mask;
+            for (unsigned m = p.res_mask; m; m &= m - 1) bcnt[__builtin_ctz(m) * N + p.host + 1]++;
         }
+        for (int b = 0; b < N * N; b++) bcnt[b + 1] += bcnt[b];
+        const int R = bcnt[N * N];
         lap("bdw.sort");
         // chunk tables: accumulate chunks per bin, Schur chunks per host
         h_bin_chunk_begin.assign(N * N + 1, 0);
@@ -496,6 +487,7 @@ public:
                      o_cb = up.take<int>(n_acc_chunks), o_cbeg = up.take<int>(n_acc_chunks), o_ccnt = up.take<int>(n_acc_chunks), o_bcb = up.take<int>(N * N + 1),
                      o_sh = up.take<int>(n_sc_chunks), o_sbeg = up.take<int>(n_sc_chunks), o_scnt = up.take<int>(n_sc_chunks), o_hcb = up.take<int>(N + 1);
         CK(up.commit());
+        up_o_rp = o_rp; up_o_rt = o_rt;
         {
             int *h_pt_host = up.host<int>(o_pt_host), *h_ng = up.host<int>(o_ng);
             float *h_x = up.host<float>(o_x), *h_y = up.host<float>(o_y), *h_idz = up.host<float>(o_idz), *h_prior = up.host<float>(o_prior), *h_mrb = up.host<float>(o_mrb),
@@ -509,9 +501,12 @@ public:
                 h_ng[i] = p.num_good; h_mrb[i] = p.max_rel_bs; h_idh[i] = p.idepth_hessian;
             }
             int *h_rp = up.host<int>(o_rp); uint8_t *h_rh = up.host<uint8_t>(o_rh), *h_rt = up.host<uint8_t>(o_rt);
-            for (int i = 0; i < R; i++) {
-                const ResHost &r = res_[res_order[i]];
-                h_rp[i] = pos[r.point]; h_rh[i] = (uint8_t) points_[r.point].host; h_rt[i] = (uint8_t) r.target;
+            for (int t = 0; t < N; t++) for (int h = 0; h < N; h++) {
+                int k = bcnt[t * N + h];
+                const int ke = bcnt[t * N + h + 1];
+                if (k == ke) continue;
+                memset(h_rh + k, h, ke - k); memset(h_rt + k, t, ke - k);
+                for (int i = hcnt[h]; i < hcnt[h + 1]; i++) if ((dmask[i] >> t) & 1) h_rp[k++] = i;
             }
             int *cb = up.host<int>(o_cb), *cbeg = up.host<int>(o_cbeg), *ccnt = up.host<int>(o_ccnt);
             for (int b = 0, c = 0; b < N * N; b++)
@@ -852,22 +847,25 @@ public:
             PointHost &p = points_[pt_order[i]];
             p.idepth = id[i]; p.idepth_zero = idz[i]; p.idepth_hessian = idh[i]; p.max_rel_bs = mrb[i]; p.num_good = ng[i];
         }
-        // residual states; dropped residuals (device order) are marked and squeezed out in host order afterwards
-        std::vector<int> cnt(points_.size(), 0);
+        // residuals (device order): dropped ones leave the masks; lastResiduals bookkeeping (BA:1616-1620, 1630-1633)
+        const int *r_point = up.host<int>(up_o_rp); const uint8_t *r_target = up.host<uint8_t>(up_o_rt);
         int dropped = 0;
         for (int i = 0; i < R; i++) {
-            ResHost &r = res_[res_order[i]];
-            r.state = st[i]; r.energy = en[i];
-            PointHost &p = points_[r.point];
-            const int64_t tid = frames_[r.target].id;
-            // setResidualState (BA:1616-1620) / cleared lastResiduals of deleted residuals (BA:1630-1633)
-            for (int s = 0; s < 2; s++) if (p.last_frame[s] == tid) { if (alive[i]) p.last_state[s] = r.state; else p.last_frame[s] = -1; break; }
-            if (alive[i]) cnt[r.point]++; else { r.point = -1; dropped++; }
+            PointHost &p = points_[pt_order[r_point[i]]];
+            const int t = r_target[i];
+            const int64_t tid = frames_[t].id;
+            for (int s2 = 0; s2 < 2; s2++) if (p.last_frame[s2] == tid) { if (alive[i]) p.last_state[s2] = st[i]; else p.last_frame[s2] = -1; break; }
+            if (!alive[i]) { p.res_mask &= (uint16_t) ~(1u << t); dropped++; }
         }
-        if (dropped) { size_t nr = 0; for (size_t i = 0; i < res_.size(); i++) if (res_[i].point >= 0) res_[nr++] = res_[i]; res_.resize(nr); }
+        // snapshot for cmlba_get_residuals (plain copies of the device-order arrays)
+        snap.valid = true;
+        snap.frame_id.resize(N); for (int i = 0; i < N; i++) snap.frame_id[i] = frames_[i].id;
+        snap.point_id.resize(P); for (int i = 0; i < P; i++) snap.point_id[i] = points_[pt_order[i]].id;
+        snap.r_point.assign(r_point, r_point + R); snap.r_target.assign(r_target, r_target + R);
+        snap.state.assign(st, st + R); snap.alive.assign(alive, alive + R); snap.energy.assign(en, en + R);
         outliers_.clear();
         int nout = 0;
-        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive && cnt[i] == 0) { points_[i].alive = false; outliers_.push_back(points_[i].id); nout++; }
+        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive && points_[i].res_mask == 0) { points_[i].alive = false; outliers_.push_back(points_[i].id); nout++; }
         if (out) {
             out->iterations_done = c.iteration; out->num_residuals = R; out->num_dropped = dropped; out->num_outliers = nout;
             out->energy_first = c.energy_first; out->energy_last = c.energy_last;
@@ -884,7 +882,7 @@ public:
     int reset() {
         cudaSetDevice(device);
         for (auto &f : frames_) if (f.d_img) { img_pool.push_back(f.d_img); f.d_img = nullptr; }
-        frames_.clear(); points_.clear(); res_.clear(); point_index_.clear(); outliers_.clear();
+        frames_.clear(); points_.clear(); snap.valid = false; point_index_.clear(); outliers_.clear();
         key_counter = 0; dirty = true; prepared = false;
         return CMLBA_OK;
     }
@@ -960,8 +958,7 @@ public:
         const int cur = c.cur;
         if (name == "ctrl") return host_out(&c, sizeof(c), dst, cap, bytes);
         if (name == "pt_order") return host_out(pt_order.data(), P * sizeof(int), dst, cap, bytes);
-        if (name == "res_order") return host_out(res_order.data(), R * sizeof(int), dst, cap, bytes);
-        if (name == "res_point") { std::vector<int> v(R); for (int i = 0; i < R; i++) v[i] = res_[res_order[i]].point; return host_out(v.data(), R * sizeof(int), dst, cap, bytes); }
+        if (name == "res_point") { const int *rp = up.host<int>(up_o_rp); std::vector<int> v(R); for (int i = 0; i < R; i++) v[i] = pt_order[rp[i]]; return host_out(v.data(), R * sizeof(int), dst, cap, bytes); }
         if (name == "res_point_dev") return copy_out(d_r_point.p, R, dst, cap, bytes);
         if (name == "res_host") return copy_out(d_r_host.p, R, dst, cap, bytes);
         if (name == "res_target") return copy_out(d_r_target.p, R, dst, cap, bytes);
@@ -1069,7 +1066,12 @@ int cmlba_remove_frame(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove
 int cmlba_run(cmlba_handle *h, const double *cams, int iterations, int upo, cmlba_run_result *r) { HCHK; return h->eng.run(cams, iterations, upo, r); }
 int cmlba_num_frames(const cmlba_handle *h) { return h ? (int) h->eng.frames_.size() : CMLBA_ERR_ARG; }
 int cmlba_num_points(const cmlba_handle *h) { return h ? (int) h->eng.points_.size() : CMLBA_ERR_ARG; }
-int cmlba_num_residuals(const cmlba_handle *h) { return h ? (int) h->eng.res_.size() : CMLBA_ERR_ARG; }
+int cmlba_num_residuals(const cmlba_handle *h) {
+    if (!h) return CMLBA_ERR_ARG;
+    int n = 0;
+    for (auto &p : h->eng.points_) if (p.alive) n += __builtin_popcount(p.res_mask);
+    return n;
+}
 
 int cmlba_get_frames(const cmlba_handle *h, int64_t *id, double *w2c, double *ab, double *state, double *evalpt, double *th) {
     HCHK;
@@ -1112,12 +1114,23 @@ int cmlba_get_outliers(const cmlba_handle *h, int64_t *id, int *n) {
 
 int cmlba_get_residuals(const cmlba_handle *h, int64_t *pid, int64_t *tid, int32_t *state, double *energy) {
     HCHK;
-    const auto &rs = h->eng.res_;
-    for (size_t i = 0; i < rs.size(); i++) {
-        if (pid) pid[i] = h->eng.points_[rs[i].point].id;
-        if (tid) tid[i] = h->eng.frames_[rs[i].target].id;
-        if (state) state[i] = rs[i].state;
-        if (energy) energy[i] = rs[i].energy;
+    const Engine &e = h->eng;
+    // (point id, frame id) -> device residual index of the last run(), decoded from the snapshot on demand (O(R))
+    std::unordered_map<int64_t, std::unordered_map<int64_t, int>> last;
+    if (e.snap.valid) for (size_t i = 0; i < e.snap.r_point.size(); i++) if (e.snap.alive[i]) last[e.snap.point_id[e.snap.r_point[i]]][e.snap.frame_id[e.snap.r_target[i]]] = (int) i;
+    size_t k = 0;
+    for (auto &p : e.points_) {
+        if (!p.alive) continue;
+        auto lp = last.find(p.id);
+        for (unsigned m = p.res_mask; m; m &= m - 1, k++) {
+            const int64_t f = e.frames_[__builtin_ctz(m)].id;
+            int st = CMLBA_RES_IN; double en = 0.0;           // residuals created since the last run (DSOResidual.h:81-86)
+            if (lp != last.end()) { auto it = lp->second.find(f); if (it != lp->second.end()) { st = e.snap.state[it->second]; en = e.snap.energy[it->second]; } }
+            if (pid) pid[k] = p.id;
+            if (tid) tid[k] = f;
+            if (state) state[k] = st;
+            if (energy) energy[k] = en;
+        }
     }
     return CMLBA_OK;
 }
