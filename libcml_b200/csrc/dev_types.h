@@ -73,6 +73,7 @@ struct DevWin {
     Ctrl *ctrl;
     const double *AH, *AT;         // [h*N+t][8][8] adjoints (BA:1071-1095)
     const double *HM, *bM;         // marginalisation prior (n x n, n) or zero
+    int has_HM;                    // 0: the prior is all zero (disableMarginalization, BA:1395-1398) and is skipped
     const double *Pns;             // nullspace projector 0.5(NN+^T + ...) (BA:1247-1249), n x n
     // points (sorted by host frame)
     const int *pt_host;
@@ -107,8 +108,7 @@ struct DevWin {
     int sc_stride;                 // (8N)^2 + 32N + 8N + 16 + 4 (padded to 4)
     const int *sc_chunk_host, *sc_chunk_begin, *sc_chunk_count;
     const int *host_chunk_begin;   // [N+1]
-    double *accR, *scR;            // chunk partials summed in fixed order: [N*N][ACC_N] by bin, [N][(8N)^2+32N+8N+20] by host
-    double *HApart, *bApart, *HSpart, *bSpart;   // per host: [N][n*n], [N][n]
+    double *st_out;                // [N*N][st_stride(N)] block products of every ordered frame pair (stitch_pair_kernel)
     double *sys;                   // summed system: HA[n*n] bA[n] HS[n*n] bS[n]  (allreduce payload)
     double *x;                     // [n]
     double *xAd;                   // [h*N+t][8]

@@ -213,7 +213,7 @@ public:
 
     // device buffers
     DevBuf<FrameDev> d_frames; DevBuf<PairPre> d_pairs; DevBuf<Ctrl> d_ctrl;
-    DevBuf<double> d_AH, d_AT, d_HM, d_bM, d_Pns, d_pt_idepth, d_pt_step, d_energy_part, d_HApart, d_bApart, d_HSpart, d_bSpart, d_sys, d_x, d_xAd, d_pt_part, d_accR, d_scR;
+    DevBuf<double> d_AH, d_AT, d_HM, d_bM, d_Pns, d_pt_idepth, d_pt_step, d_energy_part, d_st_out, d_sys, d_x, d_xAd, d_pt_part;
     DevBuf<int> d_pt_host, d_pt_num_good, d_pt_ngood_cur, d_r_point, d_acc_chunk_bin, d_acc_chunk_begin, d_acc_chunk_count, d_bin_chunk_begin, d_sc_chunk_host,
         d_sc_chunk_begin, d_sc_chunk_count, d_host_chunk_begin;
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
@@ -249,7 +249,6 @@ public:
         for (int k = 0; k < 6; k++) ofs[e_i++] = make_uchar4(29 + k, 35, 56, 56);
         while (e_i < ACC_N) ofs[e_i++] = make_uchar4(56, 56, 56, 56);
         CK(cudaMemcpyToSymbol(c_acc_ofs, ofs, sizeof(ofs)));
-        CK(cudaFuncSetAttribute(stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         return CMLBA_OK;
@@ -267,7 +266,7 @@ public:
         up.h.release(); up.d.release(); pt_stage_h.release(); fin_h.release(); pt_stage_d.release();
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         // DevBuf members leak-free:
-        DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_HApart, &d_bApart, &d_HSpart, &d_bSpart, &d_sys, &d_x, &d_xAd, &d_pt_part, &d_accR, &d_scR};
+        DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_st_out, &d_sys, &d_x, &d_xAd, &d_pt_part};
         for (auto *b : dd) b->release();
         DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_acc_chunk_bin, &d_acc_chunk_begin, &d_acc_chunk_count, &d_bin_chunk_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin};
         for (auto *b : di) b->release();
@@ -533,8 +532,7 @@ public:
         CK(d_energy_part.reserve(std::max(n_lin_blocks, 1)));
         CK(d_acc0.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N)); CK(d_acc1.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N));
         CK(d_sc_part.reserve((size_t) std::max(n_sc_chunks, 1) * sc_stride));
-        CK(d_accR.reserve((size_t) N * N * ACC_N)); CK(d_scR.reserve((size_t) N * sc_stride));
-        CK(d_HApart.reserve((size_t) N * n * n)); CK(d_HSpart.reserve((size_t) N * n * n)); CK(d_bApart.reserve((size_t) N * n)); CK(d_bSpart.reserve((size_t) N * n));
+        CK(d_st_out.reserve((size_t) N * N * st_stride(N)));
         CK(d_sys.reserve((size_t) 2 * n * n + 2 * n)); CK(d_x.reserve(n)); CK(d_xAd.reserve((size_t) N * N * 8)); CK(d_pt_part.reserve((size_t) std::max(n_pt_blocks, 1) * 3));
         lap("bdw.alloc");
         if (up.used) CK(cudaMemcpyAsync(up.d.p, up.h.p, up.used, cudaMemcpyHostToDevice, stream));
@@ -571,8 +569,7 @@ public:
         w.acc_chunk_bin = d_acc_chunk_bin.p; w.acc_chunk_begin = d_acc_chunk_begin.p; w.acc_chunk_count = d_acc_chunk_count.p; w.bin_chunk_begin = d_bin_chunk_begin.p;
         w.sc_part = d_sc_part.p; w.sc_stride = sc_stride; w.sc_chunk_host = d_sc_chunk_host.p; w.sc_chunk_begin = d_sc_chunk_begin.p; w.sc_chunk_count = d_sc_chunk_count.p;
         w.host_chunk_begin = d_host_chunk_begin.p;
-        w.accR = d_accR.p; w.scR = d_scR.p;
-        w.HApart = d_HApart.p; w.bApart = d_bApart.p; w.HSpart = d_HSpart.p; w.bSpart = d_bSpart.p; w.sys = d_sys.p; w.x = d_x.p; w.xAd = d_xAd.p;
+        w.st_out = d_st_out.p; w.sys = d_sys.p; w.x = d_x.p; w.xAd = d_xAd.p;
         w.pt_part = d_pt_part.p; w.n_pt_blocks = n_pt_blocks;
         dirty = false;
         return CMLBA_OK;
@@ -693,6 +690,9 @@ public:
         }
         if ((int) HM.size() != n * n) { HM.assign((size_t) n * n, 0.0); bM.assign(n, 0.0); }
         if (cfg.disable_marginalization) { std::fill(HM.begin(), HM.end(), 0.0); std::fill(bM.begin(), bM.end(), 0.0); }   // BA:1395-1398
+        dw.has_HM = 0;
+        for (double v : HM) if (v != 0.0) { dw.has_HM = 1; break; }
+        for (double v : bM) if (v != 0.0) { dw.has_HM = 1; break; }
         Ctrl c; memset(&c, 0, sizeof(c));
         c.lambda = (double) cfg.fixed_lambda;
         const int R = dw.R, P = dw.P;
@@ -725,7 +725,7 @@ public:
     }
 
     // ------------------------------------------------------------------ kernel sequences
-    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) NB * NB + N * ACC_N + 8 * NB + 8 * NB + 4 * NB + NB + NB + 24); }
+    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128); }
     size_t solve_smem() const { const int n = dw.n; return sizeof(double) * ((size_t) n * n + 3 * n + 256); }
     size_t schur_smem() const { return sizeof(float) * ((size_t) SC_CHUNK * 8 * dw.N + SC_CHUNK * 6); }
 
@@ -743,17 +743,15 @@ public:
     void launch_schur(int respect_done) {
         if (dw.n_sc_chunks > 0) { schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, respect_done); launches++; }
     }
-    // fixed-order reduction of the chunk partials (wide grid), then one stitch CTA per host frame
+    // one CTA per ordered frame pair, then the gather into sys = [HA | bA | H_sc | b_sc]
     void launch_stitch(int respect_done) {
-        const int N = dw.N, NB = 8 * N;
-        const int tot = N * N * ACC_N + N * (NB * NB + NB * 4 + NB + 20);
-        reduce_partials_kernel<<<(tot + 255) / 256, 256, 0, stream>>>(dw, respect_done); launches++;
-        stitch_kernel<<<dw.N, 256, stitch_smem(), stream>>>(dw, respect_done); launches++;
+        const int N = dw.N, n = dw.n;
+        stitch_pair_kernel<<<N * N, 128, stitch_smem(), stream>>>(dw, respect_done); launches++;
+        assemble_kernel<<<(2 * n * n + 2 * n + 255) / 256, 256, 0, stream>>>(dw, respect_done); launches++;
     }
     int launch_solve_sequence(int respect_done) {
         launch_schur(respect_done);
         launch_stitch(respect_done);
-        sum_partials_kernel<<<32, 256, 0, stream>>>(dw, respect_done); launches++;
         if (world > 1) { int rc = allreduce_system(); if (rc) return rc; }
         solve_kernel<<<1, 256, solve_smem(), stream>>>(dw, respect_done); launches++;
         if (dw.P > 0) { point_step_kernel<<<dw.n_pt_blocks, 256, 0, stream>>>(dw, respect_done); launches++; }
@@ -910,7 +908,7 @@ public:
             CK(cudaEventRecord(ev[0], stream));
             launch_linearize(0, 0); launch_accumulate(0);
             launch_schur(0); launch_stitch(0);
-            if (world > 1) { sum_partials_kernel<<<32, 256, 0, stream>>>(dw, 0); launches++; int rc = allreduce_system(); if (rc) return rc; }
+            if (world > 1) { int rc = allreduce_system(); if (rc) return rc; }
             CK(cudaEventRecord(ev[1], stream));
             CK(cudaStreamSynchronize(stream));
             float ms = 0; CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); tot += ms;

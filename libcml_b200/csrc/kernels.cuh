@@ -452,187 +452,160 @@ __device__ __forceinline__ int acc_index(int r, int c) {
     return 85 + (rr == 0 ? cc : (rr == 1 ? 2 + cc : 5));
 }
 
-// Fixed-order sums of the chunk partials, one thread per output element (wide grid: the per-host stitch CTAs
-// would otherwise walk ~32 chunks x 17 elements per thread with exposed load latency).
-//   accR[bin][ACC_N]  (bin = t*N+h)  = sum_c acc_part[cur][c][:]   for the chunks c of the bin
-//   scR[h][sc_tot]                   = sum_c sc_part[c][:]         for the chunks c of host h
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const DevWin w, const int respect_done) {
+// Stitching (fp64), fully parallel: one CTA per ordered frame pair (host i, other frame j).  It sums the chunk
+// partials it needs in fixed order (13x13 block of bin i->j; rows j of the host's Schur blocks D, E, EB), applies the
+// adjoints and writes every block product that involves this pair to its own slot of st_out; assemble_kernel
+// then gathers the slots into the reduced system.  No atomics, no zero-filled per-host matrices.
+// AT is diagonal (identity pose block, -a, -1, row-scaled; BA:1075-1092): only its diagonal is used.
+//   slot layout (doubles):  A_tt[64] A_it[64] A_ii[64] A_tC[32] A_iC[32] A_CC[16] bA_t[8] bA_i[8] bA_C[4] pad[4]
+//                           S_ji[64] S_ii[64] S_jC[32] S_iC[32] bS_j[8] bS_i[8] | S_jk[N][64]
+//   slot (i,i) holds Hcc[16] bc[4] of host i instead.
+constexpr int ST_A_TT = 0, ST_A_IT = 64, ST_A_II = 128, ST_A_TC = 192, ST_A_IC = 224, ST_A_CC = 256, ST_BA_T = 272, ST_BA_I = 280, ST_BA_C = 288,
+              ST_S_JI = 296, ST_S_II = 360, ST_S_JC = 424, ST_S_IC = 456, ST_BS_J = 488, ST_BS_I = 496, ST_S_JK = 504;
+__host__ __device__ __forceinline__ int st_stride(int N) { return ST_S_JK + 64 * N; }
+
+__global__ void __launch_bounds__(128) stitch_pair_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
-    const int N = w.N, NB = 8 * N;
+    extern __shared__ __align__(16) double smd[];
+    const int N = w.N, NB = 8 * N, tid = threadIdx.x;
+    const int i = blockIdx.x / N, j = blockIdx.x % N;
     const int cur = w.ctrl->cur;
-    const int n_acc = N * N * ACC_N, sc_tot = NB * NB + NB * 4 + NB + 20;
-    const int e = blockIdx.x * 256 + threadIdx.x;
-    if (e < n_acc) {
-        const int bin = e / ACC_N, k = e - bin * ACC_N;
-        const int cb = w.bin_chunk_begin[bin], ce = w.bin_chunk_begin[bin + 1];
-        const float *src = w.acc_part[cur] + (size_t) cb * ACC_N + k;
-        double s = 0.0;
-#pragma unroll 8
-        for (int c = cb; c < ce; c++, src += ACC_N) s += (double) __ldg(src);
-        w.accR[e] = s;
-    } else if (e < n_acc + N * sc_tot) {
-        const int q = e - n_acc, h = q / sc_tot, k = q - h * sc_tot;
-        const int cb = w.host_chunk_begin[h], ce = w.host_chunk_begin[h + 1];
-        const float *src = w.sc_part + (size_t) cb * w.sc_stride + k;
+    double *out = w.st_out + (size_t) blockIdx.x * st_stride(N);
+    const int cb = w.host_chunk_begin[i], ce = w.host_chunk_begin[i + 1];
+    if (i == j) {   // calibration block of host i's Schur complement (BA:1908-1909, 2026-2027)
+        if (tid < 20) {
+            const float *src = w.sc_part + (size_t) cb * w.sc_stride + NB * NB + NB * 5 + tid;
+            double s = 0.0;
+            for (int c = cb; c < ce; c++, src += w.sc_stride) s += (double) __ldg(src);
+            out[tid] = s;
+        }
+        return;
+    }
+    double *Dj = smd;              // [8][NB]  rows of frame j of D_i
+    double *Ej = Dj + 8 * NB;      // [8][4]   (Dj, Ej, EBj contiguous: filled by one loop)
+    double *EBj = Ej + 32;         // [8]
+    double *G = EBj + 8;           // [N][8][8] AH_ik
+    double *atd = G + N * 64;      // [N][8]   diag(AT_ik)
+    double *A = atd + NB;          // [ACC_N]  packed 13x13 block of bin (i -> j)
+    double *Y = A + ACC_N;         // [8][8]   sum_k D_jk AH_ik^T
+    double *M = Y + 64;            // [8][8]   AH_ij A8
+    for (int e = tid; e < 8 * NB + 40; e += 128) {
+        int off;
+        if (e < 8 * NB) off = j * 8 * NB + e;
+        else if (e < 8 * NB + 32) off = NB * NB + j * 32 + (e - 8 * NB);
+        else off = NB * NB + NB * 4 + j * 8 + (e - 8 * NB - 32);
+        const float *src = w.sc_part + (size_t) cb * w.sc_stride + off;
         double s = 0.0;
 #pragma unroll 8
         for (int c = cb; c < ce; c++, src += w.sc_stride) s += (double) __ldg(src);
-        w.scR[q] = s;
+        Dj[e] = s;                 // Dj, Ej, EBj are contiguous
+    }
+    if (tid < ACC_N) {
+        const int bin = j * N + i;
+        const int b0 = w.bin_chunk_begin[bin], b1 = w.bin_chunk_begin[bin + 1];
+        const float *src = w.acc_part[cur] + (size_t) b0 * ACC_N + tid;
+        double s = 0.0;
+#pragma unroll 8
+        for (int c = b0; c < b1; c++, src += ACC_N) s += (double) __ldg(src);
+        A[tid] = s;
+    }
+    for (int e = tid; e < N * 64; e += 128) G[e] = w.AH[(size_t) (i * N) * 64 + e];
+    for (int e = tid; e < NB; e += 128) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
+    __syncthreads();
+    const double *AHj = G + j * 64, *atj = atd + j * 8;
+    {
+        const int r = (tid >> 3) & 7, c = tid & 7;
+        double s = 0.0;
+        if (tid < 64) { for (int k = 0; k < N; k++) for (int m = 0; m < 8; m++) s += Dj[r * NB + k * 8 + m] * G[k * 64 + c * 8 + m]; Y[tid] = s; }
+        else { for (int m = 0; m < 8; m++) s += AHj[r * 8 + m] * A[acc_index(4 + m, 4 + c)]; M[tid - 64] = s; }
+    }
+    __syncthreads();
+    const int tot = st_stride(N);
+    for (int e = tid; e < tot; e += 128) {
+        double v = 0.0;
+        if (e < ST_A_TC) {                       // 8x8 active blocks
+            const int q = e & 63, r = q >> 3, c = q & 7;
+            if (e < ST_A_IT) v = atj[r] * A[acc_index(4 + r, 4 + c)] * atj[c];
+            else if (e < ST_A_II) v = M[q] * atj[c];
+            else for (int l = 0; l < 8; l++) v += M[r * 8 + l] * AHj[c * 8 + l];
+        } else if (e < ST_A_CC) {                // 8x4 calibration columns
+            const int q = (e - ST_A_TC) & 31, r = q >> 2, c = q & 3;
+            if (e < ST_A_IC) v = atj[r] * A[acc_index(4 + r, c)];
+            else for (int m = 0; m < 8; m++) v += AHj[r * 8 + m] * A[acc_index(4 + m, c)];
+        } else if (e < ST_BA_T) { const int q = e - ST_A_CC; v = A[acc_index(q >> 2, q & 3)]; }
+        else if (e < ST_BA_I) { const int r = e - ST_BA_T; v = atj[r] * A[acc_index(4 + r, 12)]; }
+        else if (e < ST_BA_C) { const int r = e - ST_BA_I; for (int m = 0; m < 8; m++) v += AHj[r * 8 + m] * A[acc_index(4 + m, 12)]; }
+        else if (e < ST_S_JI) { const int q = e - ST_BA_C; v = q < 4 ? A[acc_index(q, 12)] : 0.0; }
+        else if (e < ST_S_II) { const int q = e - ST_S_JI; v = atj[q >> 3] * Y[q]; }
+        else if (e < ST_S_JC) { const int q = e - ST_S_II, r = q >> 3, c = q & 7; for (int m = 0; m < 8; m++) v += AHj[r * 8 + m] * Y[m * 8 + c]; }
+        else if (e < ST_S_IC) { const int q = e - ST_S_JC; v = atj[q >> 2] * Ej[q]; }
+        else if (e < ST_BS_J) { const int q = e - ST_S_IC, r = q >> 2, c = q & 3; for (int m = 0; m < 8; m++) v += AHj[r * 8 + m] * Ej[m * 4 + c]; }
+        else if (e < ST_BS_I) { const int r = e - ST_BS_J; v = atj[r] * EBj[r]; }
+        else if (e < ST_S_JK) { const int r = e - ST_BS_I; for (int m = 0; m < 8; m++) v += AHj[r * 8 + m] * EBj[m]; }
+        else { const int q = e - ST_S_JK, k = q >> 6, r = (q >> 3) & 7, c = q & 7; v = atj[r] * Dj[r * NB + k * 8 + c] * atd[k * 8 + c]; }
+        out[e] = v;
     }
 }
 
-// Stitching (fp64): one CTA per host frame i.  Every output block of the per-host partial matrices is owned
-// by exactly one thread, so there are no atomics; partials are summed over hosts in solve_kernel.
-// AT is diagonal (identity pose block, -a, -1, row-scaled; BA:1075-1092): only its diagonal is used.
-__global__ void __launch_bounds__(256) stitch_kernel(const DevWin w, const int respect_done) {
+// Gathers the pair slots into sys = [HA | bA | H_sc | b_sc] (the multi-GPU allreduce payload), one thread per
+// element, fixed summation order.  Both matrices come out completed exactly like the tails of stitchDoubleTop
+// (BA:1857-1876: H[h,t] += H[t,h]^T, calibration rows mirrored) and stitchDoubleSC (BA:2033-2037).
+__global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
-    extern __shared__ __align__(16) double smd[];
-    const int N = w.N, NB = 8 * N, n = w.n, i = blockIdx.x, tid = threadIdx.x;
-    double *D = smd;                 // [NB][NB]
-    double *accA = D + NB * NB;      // [N][ACC_N]
-    double *G = accA + N * ACC_N;    // [8][NB]   G[r][k*8+m] = AH_ik[r][m]
-    double *Y = G + 8 * NB;          // [NB][8]
-    double *E = Y + NB * 8;          // [NB][4]
-    double *EB = E + NB * 4;         // [NB]
-    double *atd = EB + NB;           // [N][8]  diag(AT_ij)
-    double *small = atd + NB;        // Hcc[16] bc[4]
-    for (int e = tid; e < 8 * NB; e += 256) { const int r = e / NB, km = e % NB, k = km >> 3, m = km & 7; G[e] = w.AH[((size_t) (i * N + k)) * 64 + r * 8 + m]; }
-    for (int e = tid; e < NB; e += 256) { const int j = e >> 3, r = e & 7; atd[e] = w.AT[((size_t) (i * N + j)) * 64 + r * 8 + r]; }
-    // reduced partials (reduce_partials_kernel): bins (host i, target t) = t*N + i, Schur blocks of host i
-    for (int e = tid; e < N * ACC_N; e += 256) { const int t = e / ACC_N, k = e % ACC_N; accA[e] = w.accR[(size_t) (t * N + i) * ACC_N + k]; }
-    const int tot = NB * NB + NB * 4 + NB + 20;
-    const double *scr = w.scR + (size_t) i * tot;
-    for (int e = tid; e < tot; e += 256) {
-        const double s = scr[e];
-        if (e < NB * NB) D[e] = s;
-        else if (e < NB * NB + NB * 4) E[e - NB * NB] = s;
-        else if (e < NB * NB + NB * 5) EB[e - NB * NB - NB * 4] = s;
-        else small[e - NB * NB - NB * 5] = s;
-    }
-    double *HA = w.HApart + (size_t) i * n * n, *HS = w.HSpart + (size_t) i * n * n;
-    double *bA = w.bApart + (size_t) i * n, *bS = w.bSpart + (size_t) i * n;
-    for (int e = tid; e < n * n; e += 256) { HA[e] = 0.0; HS[e] = 0.0; }
-    for (int e = tid; e < n; e += 256) { bA[e] = 0.0; bS[e] = 0.0; }
-    __syncthreads();
-    // Y = D * G^T   (Y[(j r)][c] = sum_k (D_jk AH_ik^T)[r][c])
-    for (int e = tid; e < NB * 8; e += 256) {
-        const int row = e >> 3, c = e & 7;
-        double s = 0.0;
-        for (int km = 0; km < NB; km++) s += D[row * NB + km] * G[c * NB + km];
-        Y[e] = s;
-    }
-    __syncthreads();
-    const int iI = 4 + 8 * i;
-    // ---- Schur part (BA:1982-2011)
-    for (int e = tid; e < NB * NB; e += 256) {           // blocks (j,k), j,k != i: AT_ij D_jk AT_ik^T
-        const int row = e / NB, col = e % NB, j = row >> 3, k = col >> 3;
-        if (j != i && k != i) HS[(size_t) (4 + row) * n + 4 + col] = atd[row] * D[e] * atd[col];
-    }
-    for (int e = tid; e < NB * 8; e += 256) {            // blocks (j,i) = AT_ij Y_j and its transpose (i,j)
-        const int row = e >> 3, c = e & 7, j = row >> 3;
-        if (j != i) {
-            const double v = atd[row] * Y[e];
-            HS[(size_t) (4 + row) * n + iI + c] = v;
-            HS[(size_t) (iI + c) * n + 4 + row] = v;
-        }
-    }
-    for (int e = tid; e < 64; e += 256) {                // block (i,i) = sum_j AH_ij Y_j
-        const int r = e >> 3, c = e & 7;
-        double s = 0.0;
-        for (int km = 0; km < NB; km++) s += G[r * NB + km] * Y[km * 8 + c];
-        HS[(size_t) (iI + r) * n + iI + c] = s;
-    }
-    for (int e = tid; e < NB * 4; e += 256) {            // calibration columns: rows j != i
-        const int row = e >> 2, c = e & 3, j = row >> 3;
-        if (j != i) HS[(size_t) (4 + row) * n + c] = atd[row] * E[e];
-    }
-    for (int e = tid; e < 32; e += 256) {                // calibration columns: row block i
-        const int r = e >> 2, c = e & 3;
-        double s = 0.0;
-        for (int km = 0; km < NB; km++) s += G[r * NB + km] * E[km * 4 + c];
-        HS[(size_t) (iI + r) * n + c] = s;
-    }
-    for (int e = tid; e < NB; e += 256) { const int j = e >> 3; if (j != i) bS[4 + e] = atd[e] * EB[e]; }
-    for (int e = tid; e < 8; e += 256) {
-        double s = 0.0;
-        for (int km = 0; km < NB; km++) s += G[e * NB + km] * EB[km];
-        bS[iI + e] = s;
-    }
-    for (int e = tid; e < 16; e += 256) HS[(size_t) (e >> 2) * n + (e & 3)] = small[e];
-    for (int e = tid; e < 4; e += 256) bS[e] = small[16 + e];
-    // ---- active part (BA:1825-1843); A8 = acc[4:12,4:12], cC = acc[4:12,0:4], g = acc[4:12,12]
-    for (int e = tid; e < N * 64; e += 256) {            // (t,t) = AT A AT^T ; (i,t) = AH_it A AT^T
-        const int t = e >> 6, r = (e >> 3) & 7, c = e & 7;
-        if (t == i) continue;
-        const double *A = accA + t * ACC_N;
-        const int tI = 4 + 8 * t;
-        HA[(size_t) (tI + r) * n + tI + c] = atd[t * 8 + r] * A[acc_index(4 + r, 4 + c)] * atd[t * 8 + c];
-        double s = 0.0;
-        for (int m = 0; m < 8; m++) s += G[r * NB + t * 8 + m] * A[acc_index(4 + m, 4 + c)];
-        HA[(size_t) (iI + r) * n + tI + c] = s * atd[t * 8 + c];
-    }
-    for (int e = tid; e < 64; e += 256) {                // (i,i) = sum_t AH_it A AH_it^T
-        const int r = e >> 3, c = e & 7;
-        double s = 0.0;
-        for (int t = 0; t < N; t++) {
-            if (t == i) continue;
-            const double *A = accA + t * ACC_N;
-            for (int m = 0; m < 8; m++) {
-                double q = 0.0;
-                for (int l = 0; l < 8; l++) q += A[acc_index(4 + m, 4 + l)] * G[c * NB + t * 8 + l];
-                s += G[r * NB + t * 8 + m] * q;
+    const int N = w.N, n = w.n, nn = n * n, S = st_stride(N);
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= 2 * nn + 2 * n) return;
+    const double *st = w.st_out;
+#define SLOT(i, j) (st + (size_t) ((i) * N + (j)) * S)
+    const bool schur = e >= nn + n;
+    const int q = schur ? e - nn - n : e;
+    double v = 0.0;
+    if (q < nn) {
+        int r = q / n, c = q - r * n;
+        if (r < 4 && c >= 4) { const int t = r; r = c; c = t; }          // calibration rows mirror the columns
+        if (r < 4) {                                                      // (C,C)
+            if (!schur) { for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) if (i != j) v += SLOT(i, j)[ST_A_CC + r * 4 + c]; }
+            else for (int i = 0; i < N; i++) v += SLOT(i, i)[r * 4 + c];
+        } else if (c < 4) {                                               // (frame a, C)
+            const int a = (r - 4) >> 3, rr = (r - 4) & 7;
+            const int o_i = (schur ? ST_S_IC : ST_A_IC) + rr * 4 + c, o_t = (schur ? ST_S_JC : ST_A_TC) + rr * 4 + c;
+            for (int k = 0; k < N; k++) if (k != a) v += SLOT(a, k)[o_i];
+            for (int k = 0; k < N; k++) if (k != a) v += SLOT(k, a)[o_t];
+        } else {
+            const int a = (r - 4) >> 3, rr = (r - 4) & 7, b = (c - 4) >> 3, cc = (c - 4) & 7;
+            if (a == b) {
+                if (!schur) {
+                    for (int k = 0; k < N; k++) if (k != a) v += SLOT(a, k)[ST_A_II + rr * 8 + cc];
+                    for (int k = 0; k < N; k++) if (k != a) v += SLOT(k, a)[ST_A_TT + rr * 8 + cc];
+                } else {
+                    for (int k = 0; k < N; k++) if (k != a) v += SLOT(a, k)[ST_S_II + rr * 8 + cc];
+                    for (int k = 0; k < N; k++) if (k != a) v += SLOT(k, a)[ST_S_JK + a * 64 + rr * 8 + cc];
+                }
+            } else {
+                // the (lo,hi) orientation is summed the same way from both sides: the result is bitwise symmetric
+                const int lo = a < b ? a : b, hi = a < b ? b : a, rl = a < b ? rr : cc, rh = a < b ? cc : rr;   // element (lo rl, hi rh)
+                if (!schur) v = SLOT(lo, hi)[ST_A_IT + rl * 8 + rh] + SLOT(hi, lo)[ST_A_IT + rh * 8 + rl];
+                else {
+                    for (int k = 0; k < N; k++) if (k != lo && k != hi) v += SLOT(k, lo)[ST_S_JK + hi * 64 + rl * 8 + rh];
+                    v += SLOT(hi, lo)[ST_S_JI + rl * 8 + rh];
+                    v += SLOT(lo, hi)[ST_S_JI + rh * 8 + rl];
+                }
             }
         }
-        HA[(size_t) (iI + r) * n + iI + c] = s;
+    } else {
+        const int r = q - nn;
+        if (r < 4) {
+            if (!schur) { for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) if (i != j) v += SLOT(i, j)[ST_BA_C + r]; }
+            else for (int i = 0; i < N; i++) v += SLOT(i, i)[16 + r];
+        } else {
+            const int a = (r - 4) >> 3, rr = (r - 4) & 7;
+            const int o_i = (schur ? ST_BS_I : ST_BA_I) + rr, o_t = (schur ? ST_BS_J : ST_BA_T) + rr;
+            for (int k = 0; k < N; k++) if (k != a) v += SLOT(a, k)[o_i];
+            for (int k = 0; k < N; k++) if (k != a) v += SLOT(k, a)[o_t];
+        }
     }
-    for (int e = tid; e < N * 32; e += 256) {            // (t,C) = AT cC
-        const int t = e >> 5, r = (e >> 2) & 7, c = e & 3;
-        if (t == i) continue;
-        HA[(size_t) (4 + 8 * t + r) * n + c] = atd[t * 8 + r] * accA[t * ACC_N + acc_index(4 + r, c)];
-    }
-    for (int e = tid; e < 32; e += 256) {                // (i,C) = sum_t AH_it cC
-        const int r = e >> 2, c = e & 3;
-        double s = 0.0;
-        for (int t = 0; t < N; t++) { if (t == i) continue; for (int m = 0; m < 8; m++) s += G[r * NB + t * 8 + m] * accA[t * ACC_N + acc_index(4 + m, c)]; }
-        HA[(size_t) (iI + r) * n + c] = s;
-    }
-    for (int e = tid; e < 16; e += 256) {                // (C,C)
-        const int r = e >> 2, c = e & 3;
-        double s = 0.0;
-        for (int t = 0; t < N; t++) if (t != i) s += accA[t * ACC_N + acc_index(r, c)];
-        HA[(size_t) r * n + c] = s;
-    }
-    for (int e = tid; e < N * 8; e += 256) {             // b[t] = AT g
-        const int t = e >> 3, r = e & 7;
-        if (t != i) bA[4 + 8 * t + r] = atd[t * 8 + r] * accA[t * ACC_N + acc_index(4 + r, 12)];
-    }
-    for (int e = tid; e < 8; e += 256) {                 // b[i] = sum_t AH_it g
-        double s = 0.0;
-        for (int t = 0; t < N; t++) { if (t == i) continue; for (int m = 0; m < 8; m++) s += G[e * NB + t * 8 + m] * accA[t * ACC_N + acc_index(4 + m, 12)]; }
-        bA[iI + e] = s;
-    }
-    for (int e = tid; e < 4; e += 256) {
-        double s = 0.0;
-        for (int t = 0; t < N; t++) if (t != i) s += accA[t * ACC_N + acc_index(e, 12)];
-        bA[e] = s;
-    }
-}
-
-// sums the per-host partials into sys = [HA | bA | HS | bS] (the multi-GPU allreduce payload)
-__global__ void __launch_bounds__(256) sum_partials_kernel(const DevWin w, const int respect_done) {
-    if (respect_done && w.ctrl->done) return;
-    const int n = w.n, N = w.N, nn = n * n;
-    const int tot = 2 * nn + 2 * n;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
-        const double *src; int idx, stride;
-        if (e < nn) { src = w.HApart; idx = e; stride = nn; }
-        else if (e < nn + n) { src = w.bApart; idx = e - nn; stride = n; }
-        else if (e < 2 * nn + n) { src = w.HSpart; idx = e - nn - n; stride = nn; }
-        else { src = w.bSpart; idx = e - 2 * nn - n; stride = n; }
-        double s = 0.0;
-        for (int i = 0; i < N; i++) s += src[(size_t) i * stride + idx];
-        w.sys[e] = s;
-    }
+#undef SLOT
+    w.sys[e] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -649,40 +622,35 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
     double *x = s + n;          // [n]
     double *red = x + n;        // [256]
     double *sysHA = w.sys, *sysbA = w.sys + nn, *sysHS = w.sys + nn + n, *sysbS = w.sys + 2 * nn + n;
-    // H <- HA, complete it exactly like stitchDoubleTop's tail (BA:1867-1876)
+    // H <- HA (already completed by assemble_kernel)
     for (int e = tid; e < nn; e += 256) H[e] = sysHA[e];
     __syncthreads();
-    for (int e = tid; e < N * 32; e += 256) { const int h = e >> 5, r = (e >> 2) & 7, c = e & 3; H[c * n + 4 + 8 * h + r] = H[(4 + 8 * h + r) * n + c]; }
-    for (int e = tid; e < N * N * 64; e += 256) {
-        const int h = e / (N * 64), t = (e / 64) % N, r = (e >> 3) & 7, c = e & 7;
-        if (t > h) {
-            const int a = (4 + 8 * h + r) * n + 4 + 8 * t + c, bb = (4 + 8 * t + c) * n + 4 + 8 * h + r;
-            const double v = H[a] + H[bb];
-            H[a] = v; H[bb] = v;
-        }
-    }
-    __syncthreads();
-    for (int e = tid; e < nn; e += 256) sysHA[e] = H[e];      // completed HA_top, for read-back / statistics
-    // Schur matrix: mirror the calibration rows (BA:2033-2037)
-    for (int e = tid; e < N * 32; e += 256) { const int h = e >> 5, r = (e >> 2) & 7, c = e & 3; sysHS[c * n + 4 + 8 * h + r] = sysHS[(4 + 8 * h + r) * n + c]; }
-    __syncthreads();
     const double lambda = w.fix_lambda ? w.fixed_lambda : ctrl->lambda;
+    const int wid = tid >> 5, lane = tid & 31;
     // b = bL + bM + bA - b_sc ; H = HL + HM + HA (BA:1299-1300); HL = diag(prior), bL = prior*delta_prior (BA:1857-1865)
     for (int e = tid; e < n; e += 256) {
-        double v = sysbA[e] - sysbS[e] + w.bM[e];
+        double v = sysbA[e] - sysbS[e];
         if (e >= 4) {
             const FrameDev &f = w.frames[(e - 4) >> 3];
             const int k = (e - 4) & 7;
             v += f.prior[k] * f.state[k];                       // delta_prior = state - prior_zero, prior_zero == 0
+            s[e] = f.state[k] - f.state_zero[k];                // delta (BA:1401), staged for the H_M product
+        } else s[e] = 0.0;
+        b[e] = v;
+    }
+    __syncthreads();
+    if (w.has_HM) {   // bM_top = b_M + H_M * delta (BA:1401); zero when disableMarginalization (BA:1395-1398)
+        for (int e = wid; e < n; e += 8) {
+            double hm = 0.0;
+            for (int c = lane; c < n; c += 32) hm += w.HM[(size_t) e * n + c] * s[c];
+            hm = warp_sum_d(hm);
+            if (lane == 0) b[e] += w.bM[e] + hm;
         }
-        // bM_top = b_M + H_M * delta (BA:1401), delta = state - state_zero (calibration part 0)
-        double hm = 0.0;
-        for (int c = 4; c < n; c++) { const FrameDev &g = w.frames[(c - 4) >> 3]; const int k = (c - 4) & 7; hm += w.HM[(size_t) e * n + c] * (g.state[k] - g.state_zero[k]); }
-        b[e] = v + hm;
     }
     for (int e = tid; e < nn; e += 256) {
         const int r = e / n, c = e % n;
-        double v = H[e] + w.HM[e];
+        double v = H[e];
+        if (w.has_HM) v += w.HM[e];
         if (r == c && r >= 4) v += w.frames[(r - 4) >> 3].prior[(r - 4) & 7];
         if (r == c) v *= (1.0 + lambda);                        // BA:1306-1308
         v -= sysHS[e] * (1.0 / (1.0 + lambda));                 // BA:1309
@@ -696,39 +664,103 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
     for (int e = tid; e < m * m; e += 256) { const int r = e / m, c = e % m; if (r >= c) AA(r, c) = AA(r, c) * s[4 + r] * s[4 + c]; }
     for (int e = tid; e < m; e += 256) x[e] = s[4 + e] * b[4 + e];
     __syncthreads();
-    // LDL^T, right-looking, no pivoting (SPD after damping + priors)
-    for (int k = 0; k < m; k++) {
-        const double d = AA(k, k);
+    // LDL^T without pivoting (SPD after damping + priors), right-looking in panels of 8 columns (= one frame):
+    //   (1) one warp factors the 8x8 diagonal block in registers, (2) one thread per row below solves its panel row,
+    //   (3) rank-8 update of the trailing lower triangle in 4x4 register tiles.  Three barriers per panel.
+    for (int k0 = 0; k0 < m; k0 += 8) {
+        if (wid == 0) {
+            double a[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) a[c] = (lane < 8 && c <= lane) ? AA(k0 + lane, k0 + c) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double dk = __shfl_sync(0xffffffffu, a[k], k);
+                const double lrk = a[k] / dk;
+                if (lane > k) a[k] = lrk;
+#pragma unroll
+                for (int c = k + 1; c < 8; c++) {
+                    const double lck = __shfl_sync(0xffffffffu, a[k], c);
+                    if (lane >= c) a[c] -= lrk * dk * lck;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) if (lane < 8 && c <= lane) AA(k0 + lane, k0 + c) = a[c];
+        }
         __syncthreads();
-        for (int r = k + 1 + tid; r < m; r += 256) AA(r, k) = AA(r, k) / d;
+        const int rem = m - k0 - 8;
+        if (tid < rem) {
+            const int r = k0 + 8 + tid;
+            double l[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                double v = AA(r, k0 + c);
+#pragma unroll
+                for (int jj = 0; jj < c; jj++) v -= l[jj] * AA(k0 + jj, k0 + jj) * AA(k0 + c, k0 + jj);
+                l[c] = v / AA(k0 + c, k0 + c);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c++) AA(r, k0 + c) = l[c];
+        }
         __syncthreads();
-        const int rem = m - k - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int r = k + 1 + e / rem, c = k + 1 + e % rem;
-            if (r >= c) AA(r, c) -= AA(r, k) * d * AA(c, k);
+        const int nt = rem >> 2, ntiles = nt * (nt + 1) / 2;
+        for (int id = tid; id < ntiles; id += 256) {
+            int tr = (int) ((sqrtf(8.f * (float) id + 1.f) - 1.f) * 0.5f);
+            while (tr * (tr + 1) / 2 > id) tr--;
+            while ((tr + 1) * (tr + 2) / 2 <= id) tr++;
+            const int tc = id - tr * (tr + 1) / 2;
+            const int r0 = k0 + 8 + 4 * tr, c0 = k0 + 8 + 4 * tc;
+            double acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) acc[i][jj] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double dk = AA(k0 + k, k0 + k);
+                double lr[4], lc[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { lr[i] = AA(r0 + i, k0 + k); lc[i] = AA(c0 + i, k0 + k) * dk; }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) acc[i][jj] += lr[i] * lc[jj];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) if (r0 + i >= c0 + jj) AA(r0 + i, c0 + jj) -= acc[i][jj];
         }
         __syncthreads();
     }
-    // forward L y = rhs ; z = y / d ; backward L^T x = z   (column-oriented, one sync per column)
-    for (int k = 0; k < m; k++) {
-        const double yk = x[k];
+    // forward L y = rhs (panel by panel), z = y / d, backward L^T x = z
+    for (int k0 = 0; k0 < m; k0 += 8) {
+        if (tid == 0) {
+#pragma unroll
+            for (int c = 1; c < 8; c++) { double v = x[k0 + c]; for (int jj = 0; jj < c; jj++) v -= AA(k0 + c, k0 + jj) * x[k0 + jj]; x[k0 + c] = v; }
+        }
         __syncthreads();
-        for (int r = k + 1 + tid; r < m; r += 256) x[r] -= AA(r, k) * yk;
+        const int r = k0 + 8 + tid;
+        if (r < m) {
+            double v = x[r];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) v -= AA(r, k0 + jj) * x[k0 + jj];
+            x[r] = v;
+        }
         __syncthreads();
     }
     for (int e = tid; e < m; e += 256) x[e] = x[e] / AA(e, e);
     __syncthreads();
-    for (int k = m - 1; k >= 0; k--) {
-        // x[k] -= sum_{r>k} L[r][k] x[r]
-        double part = 0.0;
-        for (int r = k + 1 + tid; r < m; r += 256) part += AA(r, k) * x[r];
-        red[tid] = part;
+    for (int k0 = m - 8; k0 >= 0; k0 -= 8) {
+        {   // warp c: x[k0+c] -= sum_{r >= k0+8} L[r][k0+c] x[r]
+            double part = 0.0;
+            for (int r = k0 + 8 + lane; r < m; r += 32) part += AA(r, k0 + wid) * x[r];
+            part = warp_sum_d(part);
+            if (lane == 0) red[wid] = part;
+        }
         __syncthreads();
-        if (tid < 32) {
-            double v = 0.0;
-            for (int q = tid; q < 256; q += 32) v += red[q];
-            v = warp_sum_d(v);
-            if (tid == 0) x[k] -= v;
+        if (tid == 0) {
+#pragma unroll
+            for (int c = 7; c >= 0; c--) { double v = x[k0 + c] - red[c]; for (int jj = c + 1; jj < 8; jj++) v -= AA(k0 + jj, k0 + c) * x[k0 + jj]; x[k0 + c] = v; }
         }
         __syncthreads();
     }
@@ -737,10 +769,11 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
     for (int e = tid; e < n; e += 256) b[e] = (e >= 4) ? s[e] * x[e - 4] : 0.0;   // b now holds x
     __syncthreads();
     if (ctrl->iteration >= 2) {                                  // orthogonalize(x) (BA:1332-1334), projector precomputed on the host
-        for (int e = tid; e < n; e += 256) {
+        for (int e = wid; e < n; e += 8) {
             double v = 0.0;
-            for (int c = 0; c < n; c++) v += w.Pns[(size_t) e * n + c] * b[c];
-            s[e] = b[e] - v;
+            for (int c = lane; c < n; c += 32) v += w.Pns[(size_t) e * n + c] * b[c];
+            v = warp_sum_d(v);
+            if (lane == 0) s[e] = b[e] - v;
         }
         __syncthreads();
         for (int e = tid; e < n; e += 256) b[e] = s[e];
