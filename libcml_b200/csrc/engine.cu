@@ -241,14 +241,8 @@ public:
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
-        // entry-offset table of the 13x13 accumulator (see accumulate_kernel)
-        uchar4 ofs[ACC_N];
-        int e_i = 0;
-        for (int r = 0; r < 10; r++) for (int c = r; c < 10; c++) ofs[e_i++] = make_uchar4(r, 36 + c, 10 + r, 46 + c);
-        for (int r = 0; r < 10; r++) for (int c = 0; c < 3; c++) ofs[e_i++] = make_uchar4(r, 23 + c, 10 + r, 26 + c);
-        for (int k = 0; k < 6; k++) ofs[e_i++] = make_uchar4(29 + k, 35, 56, 56);
-        while (e_i < ACC_N) ofs[e_i++] = make_uchar4(56, 56, 56, 56);
-        CK(cudaMemcpyToSymbol(c_acc_ofs, ofs, sizeof(ofs)));
+        CK(cudaFuncSetAttribute(linearize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) LIN_SMEM));
+        CK(cudaFuncSetAttribute(linearize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) LIN_SMEM));
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         return CMLBA_OK;
@@ -475,7 +469,7 @@ public:
         n_sc_chunks = h_host_chunk_begin[N];
         const int NB = 8 * N;
         const int sc_stride = ((NB * NB + NB * 4 + NB + 20) + 3) & ~3;
-        const int n_lin_blocks = (R + LIN_THREADS - 1) / LIN_THREADS;
+        const int n_lin_blocks = n_acc_chunks;   // the fused linearize+accumulate kernel runs one CTA per accumulate chunk
         const int n_pt_blocks = (P + 255) / 256;
         // arena layout
         up.begin();
@@ -731,13 +725,9 @@ public:
 
     void launch_linearize(int fix, int respect_done) {
         if (dw.R == 0) return;
-        if (want_dbg) linearize_kernel<true><<<dw.n_lin_blocks, LIN_THREADS, 0, stream>>>(dw, fix, respect_done);
-        else linearize_kernel<false><<<dw.n_lin_blocks, LIN_THREADS, 0, stream>>>(dw, fix, respect_done);
+        if (want_dbg) linearize_kernel<true><<<dw.n_acc_chunks, LIN_THREADS, LIN_SMEM, stream>>>(dw, fix, respect_done);
+        else linearize_kernel<false><<<dw.n_acc_chunks, LIN_THREADS, LIN_SMEM, stream>>>(dw, fix, respect_done);
         launches++;
-    }
-    void launch_accumulate(int respect_done) {
-        if (dw.n_acc_chunks == 0) return;
-        accumulate_kernel<<<dw.n_acc_chunks, 128, 0, stream>>>(dw, respect_done); launches++;
     }
     void launch_post(int mode, int respect_done) { post_linearize_kernel<<<1, 1024, 0, stream>>>(dw, mode, respect_done); launches++; }
     void launch_schur(int respect_done) {
@@ -746,7 +736,7 @@ public:
     // one CTA per ordered frame pair, then the gather into sys = [HA | bA | H_sc | b_sc]
     void launch_stitch(int respect_done) {
         const int N = dw.N, n = dw.n;
-        stitch_pair_kernel<<<N * N, 128, stitch_smem(), stream>>>(dw, respect_done); launches++;
+        stitch_pair_kernel<<<N * N, ST_THREADS, stitch_smem(), stream>>>(dw, respect_done); launches++;
         assemble_kernel<<<(2 * n * n + 2 * n + 255) / 256, 256, 0, stream>>>(dw, respect_done); launches++;
     }
     int launch_solve_sequence(int respect_done) {
@@ -775,10 +765,10 @@ public:
         dw.update_points_only = update_points_only ? 1 : 0;
         const int l0 = launches;
         CK(cudaEventRecord(ev0, stream));
-        launch_linearize(0, 0); launch_accumulate(0); launch_post(0, 0);
+        launch_linearize(0, 0); launch_post(0, 0);
         for (int it = 0; it < iterations; it++) {
             rc = launch_solve_sequence(1); if (rc) return rc;
-            launch_linearize(0, 1); launch_accumulate(1); launch_post(1, 1);
+            launch_linearize(0, 1); launch_post(1, 1);
         }
         set_evalpt_newest_kernel<<<1, 32, 0, stream>>>(dw); launches++;
         pairs_kernel<<<(dw.N * dw.N + 63) / 64, 64, 0, stream>>>(dw); launches++;
@@ -898,15 +888,15 @@ public:
         for (auto &e : ev) CK(cudaEventCreate(&e));
         auto flush = [&]() { if (flush_l2) l2_flush_kernel<<<148 * 8, 256, 0, stream>>>(d_flush.p, flush_bytes / sizeof(float4)); };
         // the committed buffers must hold a linearization for schur/stitch to chew on
-        launch_linearize(0, 0); launch_accumulate(0); launch_post(0, 0);
-        for (int i = 0; i < warmup; i++) { flush(); launch_linearize(0, 0); launch_accumulate(0); launch_schur(0); launch_stitch(0); }
+        launch_linearize(0, 0); launch_post(0, 0);
+        for (int i = 0; i < warmup; i++) { flush(); launch_linearize(0, 0); launch_schur(0); launch_stitch(0); }
         CK(cudaStreamSynchronize(stream));
         double tot = 0, tk[4] = {0, 0, 0, 0};
         const int l0 = launches;
         for (int i = 0; i < steps; i++) {          // whole pass, two events only
             flush();
             CK(cudaEventRecord(ev[0], stream));
-            launch_linearize(0, 0); launch_accumulate(0);
+            launch_linearize(0, 0);
             launch_schur(0); launch_stitch(0);
             if (world > 1) { int rc = allreduce_system(); if (rc) return rc; }
             CK(cudaEventRecord(ev[1], stream));
@@ -917,7 +907,7 @@ public:
         for (int i = 0; i < steps; i++) {          // per-kernel breakdown
             flush();
             CK(cudaEventRecord(ev[0], stream)); launch_linearize(0, 0);
-            CK(cudaEventRecord(ev[1], stream)); launch_accumulate(0);
+            CK(cudaEventRecord(ev[1], stream));
             CK(cudaEventRecord(ev[2], stream)); launch_schur(0);
             CK(cudaEventRecord(ev[3], stream)); launch_stitch(0);
             CK(cudaEventRecord(ev[4], stream));
@@ -1145,7 +1135,7 @@ int cmlba_linearize(cmlba_handle *h, int fix, double *energy) {
         cmlba::pairs_kernel<<<(e.dw.N * e.dw.N + 63) / 64, 64, 0, e.stream>>>(e.dw);
         e.launch_linearize(1, 0); e.launch_post(2, 0);
     } else {
-        e.launch_linearize(0, 0); e.launch_accumulate(0); e.launch_post(3, 0);
+        e.launch_linearize(0, 0); e.launch_post(3, 0);
     }
     cmlba::Ctrl c;
     if (cudaMemcpyAsync(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost, e.stream) != cudaSuccess || cudaStreamSynchronize(e.stream) != cudaSuccess) {

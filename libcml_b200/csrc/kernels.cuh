@@ -22,7 +22,6 @@ constexpr int DBG_STRIDE = 52;  // resF[8] JIdx[16] JabF[16] Jpdd[2] JIdx2[3] Ja
 
 __constant__ int c_sx[8] = {0, -1, 1, -2, 0, 2, -1, 0};   // PredefinedPattern::star8 (types.h:1395-1407)
 __constant__ int c_sy[8] = {-2, -1, -1, 0, 0, 0, 1, 2};
-__constant__ uchar4 c_acc_ofs[ACC_N];                      // smem-record offsets of the two products of every 13x13 entry
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -85,45 +84,107 @@ __global__ void set_evalpt_newest_kernel(const DevWin w) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// HOT LOOP 1: one thread per residual.  Projection in fp64 (the reference's scalar_t), sampling and
-// Jacobians in fp32, exactly the reference's mixed precision.  Texels are float4 (I,dx,dy,0): one
-// 128-bit read-only load per bilinear tap, 32 independent loads in flight per thread.
+// HOT LOOPS 1+2 fused: linearize (BA:62-316) + applyRes (BA:2051-2093) + addToHessianTop(ACTIVE) (BA:1648-1779).
+// One CTA = one chunk of <=128 residuals of ONE (host,target) bin; one thread per residual.
+//   phase 1  projection of the 8 pattern pixels in fp64 (the reference's scalar_t)
+//   phase 2  warp-cooperative tap fetch: for residual j of the warp, lane l fetches tap (pixel l>>2, corner l&3) with one
+//            16-byte cp.async into the warp's staging rows.  One warp-wide request then covers the 32 taps of ONE residual
+//            (6-8 distinct 128-byte lines) instead of one tap of 32 unrelated residuals (32 lines): the L1 wavefront count,
+//            which bounded the thread-per-tap version, drops ~4x, and DRAM still sees only the sectors that are needed.
+//   phase 3  every lane reads its own 32 taps back (row stride 33 float4: conflict-free LDS.128), fp32 bilinear sampling,
+//            Huber/gradient weights, the Jacobian record and the Schur row, exactly the reference's mixed precision
+//   phase 4  13x13 block [C4 | xi6 | a b | r] of the bin: the 91 products of every lane are summed over the warp by a
+//            transposing butterfly (31 shuffles per 32 entries, lane L ends up owning entry L), then over the 4 warps
+//            in fixed order -> acc_part[chunk] (fixed-order: bitwise reproducible)
+constexpr int TAP_ROW = 33;
+constexpr int LIN_WARPS = LIN_THREADS / 32;
+constexpr size_t LIN_SMEM = (size_t) LIN_WARPS * 32 * TAP_ROW * 16 + (size_t) LIN_WARPS * 32 * 8 * 4 + (size_t) LIN_WARPS * ACC_N * 4 + LIN_WARPS * 8 + sizeof(PairPre);
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// entry e (0..95) of the packed 13x13 block as a product of record fields; x = Jp_x[10], y = Jp_y[10], Q = JIdx2 * Jp,
+// B = the 2x3 top-right multipliers, BR = the 6 bottom-right sums.  e is a compile-time constant after unrolling.
+__device__ __forceinline__ float acc_entry(const int e, const float *x, const float *y, const float *Qx, const float *Qy, const float *Bx, const float *By, const float *BR) {
+    if (e < 55) {
+        int r = 0, base = 0;
+        while (e >= base + (10 - r)) { base += 10 - r; r++; }
+        const int c = r + (e - base);
+        return x[r] * Qx[c] + y[r] * Qy[c];
+    }
+    if (e < 85) { const int r = (e - 55) / 3, k = (e - 55) % 3; return x[r] * Bx[k] + y[r] * By[k]; }
+    if (e < 91) return BR[e - 85];
+    return 0.f;
+}
+
+// sum over the warp of 32 per-lane values v[0..31]; lane L returns the total of entry L
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], const int lane) {
+#pragma unroll
+    for (int hsz = 16; hsz >= 1; hsz >>= 1) {
+        const bool up = (lane & hsz) != 0;
+#pragma unroll
+        for (int k = 0; k < hsz; k++) {
+            const float keep = up ? v[k + hsz] : v[k];
+            const float send = up ? v[k] : v[k + hsz];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, hsz);
+        }
+    }
+    return v[0];
+}
+
 template <bool kDump>
 __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, const int fix, const int respect_done) {
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
+    extern __shared__ __align__(16) unsigned char lin_smem[];
+    float4 *s_taps = reinterpret_cast<float4 *>(lin_smem);                         // [warps][32][TAP_ROW]
+    int *s_offs = reinterpret_cast<int *>(s_taps + LIN_WARPS * 32 * TAP_ROW);      // [warps][32][8]
+    float *s_red = reinterpret_cast<float *>(s_offs + LIN_WARPS * 32 * 8);         // [warps][ACC_N]
+    double *s_e = reinterpret_cast<double *>(s_red + LIN_WARPS * ACC_N);           // [warps]
+    PairPre *s_pp = reinterpret_cast<PairPre *>(s_e + LIN_WARPS);
+    const int chunk = blockIdx.x, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int begin = w.acc_chunk_begin[chunk], cnt = w.acc_chunk_count[chunk], bin = w.acc_chunk_bin[chunk];
+    const int t = bin / w.N, h = bin - t * w.N;
+    {
+        const double *src = reinterpret_cast<const double *>(&w.pairs[h * w.N + t]);
+        double *dst = reinterpret_cast<double *>(s_pp);
+        for (int k = tid; k < (int) (sizeof(PairPre) / 8); k += LIN_THREADS) dst[k] = src[k];
+    }
+    __syncthreads();
+    const PairPre &pp = *s_pp;
     const int cur = ctrl->cur, nxt = cur ^ 1;
-    const int r = blockIdx.x * LIN_THREADS + threadIdx.x;
+    const int r = begin + tid;
+    // all per-residual scalars are requested together (one exposed latency), then the point record
+    const bool in_chunk = tid < cnt;
+    const int r_ld = in_chunk ? r : begin;
+    const uint8_t alive_ld = w.r_alive[r_ld];
+    const int p = w.r_point[r_ld];
+    const uint8_t st = in_chunk ? w.r_state[cur][r_ld] : (uint8_t) RES_OOB;
+    const float e_old = w.r_energy[cur][r_ld];
+    uint8_t nst = w.r_new_state[r_ld];
+    float ne = w.r_new_energy[r_ld];
+    const bool valid = in_chunk && alive_ld;
+    const double rho = w.pt_idepth[p];
+    const double xc = (double) w.pt_x[p], yc = (double) w.pt_y[p];
+    const float4 *colp = reinterpret_cast<const float4 *>(w.pt_colors + (size_t) p * 8);
+    const float4 *wtp = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
+    const float4 c0 = __ldg(colp), c1 = __ldg(colp + 1), w0 = __ldg(wtp), w1 = __ldg(wtp + 1);
     double ret = 0.0;
-    if (r < w.R && w.r_alive[r]) {
-        const int p = w.r_point[r];
-        const int h = w.r_host[r], t = w.r_target[r];
-        const uint8_t st = w.r_state[cur][r];
-        const float e_old = w.r_energy[cur][r];
-        uint8_t st_out = st;
-        float e_out = e_old;
-        bool good = false;
-        float rec[RJ_STRIDE];
-        float trow[T_STRIDE];
-#pragma unroll
-        for (int k = 0; k < RJ_STRIDE; k++) rec[k] = 0.f;
-#pragma unroll
-        for (int k = 0; k < T_STRIDE; k++) trow[k] = 0.f;
-        float neo = -1.f;                        // state_NewEnergyWithOutlier = -1 (BA:66)
-        uint8_t nst = w.r_new_state[r];
-        float ne = w.r_new_energy[r];
+    uint8_t st_out = st;
+    float e_out = e_old, neo = -1.f;             // state_NewEnergyWithOutlier = -1 (BA:66)
+    bool good = false, sample = false;
+    float qx[8], qy[8];
+    double Pc0 = 0, Pc1 = 0, Pc2 = 1, Kuc = 0, Kvc = 0;
+    if (valid) {
         ret = (double) e_old;                    // every early exit returns state_energy
-
         if (st != RES_OOB) {
-            const PairPre &pp = w.pairs[h * w.N + t];
-            const double rho = w.pt_idepth[p];
-            const double xc = (double) w.pt_x[p], yc = (double) w.pt_y[p];
             const double Wm2 = (double) ((float) w.W - 2.f), Hm2 = (double) ((float) w.H - 2.f);
             const double R0 = pp.R[0], R1 = pp.R[1], R2 = pp.R[2], R3 = pp.R[3], R4 = pp.R[4], R5 = pp.R[5], R6 = pp.R[6], R7 = pp.R[7], R8 = pp.R[8];
             const double tx = pp.t[0] * rho, ty = pp.t[1] * rho, tz = pp.t[2] * rho;
-            float qx[8], qy[8];
             bool inb = true;
-            double Pc0 = 0, Pc1 = 0, Pc2 = 1, Kuc = 0, Kvc = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const double kx = (xc + (double) c_sx[i] - w.cx) * w.fxi;
@@ -131,146 +192,172 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
                 const double P0 = R0 * kx + R1 * ky + R2 + tx;
                 const double P1 = R3 * kx + R4 * ky + R5 + ty;
                 const double P2 = R6 * kx + R7 * ky + R8 + tz;
-                const double Ku = (P0 / P2) * w.fx + w.cx;
-                const double Kv = (P1 / P2) * w.fy + w.cy;
+                const double iP2 = 1.0 / P2;     // one reciprocal instead of two divisions (<= 1 ulp of fp64 before the cast to float)
+                const double Ku = (P0 * iP2) * w.fx + w.cx;
+                const double Kv = (P1 * iP2) * w.fy + w.cy;
                 inb = inb && (Ku >= 2.0 && Kv >= 2.0 && Ku < Wm2 && Kv < Hm2);
                 qx[i] = (float) Ku; qy[i] = (float) Kv;
                 if (i == 4) { Pc0 = P0; Pc1 = P1; Pc2 = P2; Kuc = Ku; Kvc = Kv; }
             }
-            const bool center_in = (Kuc >= 2.0 && Kvc >= 2.0 && Kuc < Wm2 && Kvc < Hm2);
-            const float drescale = (float) (1.0 / Pc2);
-            const float new_idepth = (float) ((double) drescale * rho);
-            if (center_in) {   // setCenterProjectedTo (BA:131)
-                w.r_center[r * 3 + 0] = (float) Kuc; w.r_center[r * 3 + 1] = (float) Kvc; w.r_center[r * 3 + 2] = new_idepth;
+            if (Kuc >= 2.0 && Kvc >= 2.0 && Kuc < Wm2 && Kvc < Hm2) {   // setCenterProjectedTo (BA:131)
+                w.r_center[r * 3 + 0] = (float) Kuc; w.r_center[r * 3 + 1] = (float) Kvc; w.r_center[r * 3 + 2] = (float) ((double) (float) (1.0 / Pc2) * rho);
             }
-            if (!inb) {
-                nst = RES_OOB;                   // setNewState(OOB) (BA:116, 210); state_NewEnergy keeps its old value
-            } else {
-                // ---- 8 x bilinear sample of the target image (image/Array2D.h:265-286)
-                const float4 *__restrict__ img = w.img[t];
-                float4 tap[8][4];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int ix = (int) qx[i], iy = (int) qy[i];
-                    const float4 *q = img + (size_t) iy * w.W + ix;
-                    tap[i][0] = __ldg(q); tap[i][1] = __ldg(q + 1); tap[i][2] = __ldg(q + w.W); tap[i][3] = __ldg(q + w.W + 1);
-                }
-                const float4 *colp = reinterpret_cast<const float4 *>(w.pt_colors + (size_t) p * 8);
-                const float4 *wtp = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
-                const float4 c0 = __ldg(colp), c1 = __ldg(colp + 1), w0 = __ldg(wtp), w1 = __ldg(wtp + 1);
-                const float col[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                const float wts[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                const float b0 = pp.b0;
-                float J00 = 0, J11 = 0, J10 = 0, A00 = 0, A01 = 0, A10 = 0, A11 = 0, B00 = 0, B01 = 0, B11 = 0, wJI2 = 0, E = 0;
-                float JIr0 = 0, JIr1 = 0, Jabr0 = 0, Jabr1 = 0, rr = 0;
-                bool finite = true;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int ix = (int) qx[i], iy = (int) qy[i];
-                    const float dx = qx[i] - (float) ix, dy = qy[i] - (float) iy;
-                    const float dxdy = dx * dy;
-                    const float w00 = 1.f - dx - dy + dxdy, w10 = dx - dxdy, w01 = dy - dxdy, w11 = dxdy;
-                    const float I = tap[i][0].x * w00 + tap[i][1].x * w10 + tap[i][2].x * w01 + tap[i][3].x * w11;
-                    const float gx = tap[i][0].y * w00 + tap[i][1].y * w10 + tap[i][2].y * w01 + tap[i][3].y * w11;
-                    const float gy = tap[i][0].z * w00 + tap[i][1].z * w10 + tap[i][2].z * w01 + tap[i][3].z * w11;
-                    finite = finite && isfinite(I) && isfinite(gx) && isfinite(gy);
-                    const float refReal = (float) (pp.a * (double) col[i] + pp.b);     // exposureTransition (BA:229)
-                    const float res = I - refReal;
-                    const float ar = fabsf(res);
-                    float hw = ar < w.huber ? 1.f : w.huber / ar;                      // BA:233
-                    float wg = sqrtf(w.cth / (w.cth + (gx * gx + gy * gy)));           // BA:234
-                    wg = 0.5f * (wg + wts[i]);                                         // BA:235
-                    E += wg * wg * hw * res * res * (2.f - hw);                        // BA:237
-                    if (hw < 1.f) hw = sqrtf(hw);
-                    hw = hw * wg;
-                    const float h1 = gx * hw, h2 = gy * hw, drdA = I - b0;
-                    const float rF = res * hw;
-                    const float ja = (w.optA ? drdA * hw : 0.f), jb = (w.optB ? hw : 0.f);   // BA:273-278 (zeroed after the sums below)
-                    J00 += h1 * h1; J11 += h2 * h2; J10 += h1 * h2;
-                    A00 += drdA * hw * h1; A01 += drdA * hw * h2; A10 += hw * h1; A11 += hw * h2;
-                    B00 += drdA * drdA * hw * hw; B01 += drdA * hw * hw; B11 += hw * hw;
-                    wJI2 += hw * hw * (h1 * h1 + h2 * h2);
-                    JIr0 += rF * h1; JIr1 += rF * h2; Jabr0 += rF * ja; Jabr1 += rF * jb; rr += rF * rF;   // BA:1722-1729
-                    if (kDump) {
-                        float *d = w.dbg + (size_t) r * DBG_STRIDE;
-                        d[i] = rF; d[8 + i] = h1; d[16 + i] = h2; d[24 + i] = ja; d[32 + i] = jb;
-                    }
-                }
-                if (!finite) {
-                    // BA:220-223 sets the *committed* state to OOB.  (The reference leaves a stale isActiveAndIsGoodNEW
-                    // behind in that case; only reachable with NaN/Inf texels, we clear it.)
-                    st_out = RES_OOB;
-                } else if (!isfinite(E)) {
-                    nst = RES_OOB;               // BA:297-300
-                } else {
-                    neo = E;
-                    const float th = fmaxf(w.frames[h].energy_th, w.frames[t].energy_th);
-                    if (E > th || wJI2 < 2.f) { E = th; nst = RES_OUTLIER; } else nst = RES_IN;   // BA:303-311
-                    ne = E;
-                    ret = (double) E;
-                    if (nst == RES_IN) {
-                        // ---- geometric Jacobians at the FEJ point (BA:120-188); note u,v are the UN-normalised P.xy (BA:121-122)
-                        const float u = (float) Pc0, v = (float) Pc1;
-                        const float fxf = (float) w.fx, fyf = (float) w.fy;
-                        const double ud = (double) u, vd = (double) v, dr = (double) drescale;
-                        const double klx = (xc - w.cx) * w.fxi, kly = (yc - w.cy) * w.fyi;      // KliP
-                        const float Jpdd0 = (float) (dr * (pp.t0[0] - pp.t0[2] * ud) * (double) fxf);
-                        const float Jpdd1 = (float) (dr * (pp.t0[1] - pp.t0[2] * vd) * (double) fyf);
-                        double dCx[4], dCy[4];
-                        dCx[2] = dr * (pp.R0[6] * ud - pp.R0[0]);
-                        dCx[3] = (double) (fxf * drescale) * (pp.R0[7] * ud - pp.R0[1]) / (double) fyf;
-                        dCx[0] = klx * dCx[2]; dCx[1] = kly * dCx[3];
-                        dCy[2] = (double) (fyf * drescale) * (pp.R0[6] * vd - pp.R0[3]) / (double) fxf;
-                        dCy[3] = dr * (pp.R0[7] * vd - pp.R0[4]);
-                        dCy[0] = klx * dCy[2]; dCy[1] = kly * dCy[3];
-                        const double sF = (double) w.scaleF, sC = (double) w.scaleC;
-                        dCx[0] = (dCx[0] + ud) * sF; dCx[1] *= sF; dCx[2] = (dCx[2] + 1.0) * sC; dCx[3] *= sC;
-                        dCy[0] *= sF; dCy[1] = (dCy[1] + vd) * sF; dCy[2] *= sC; dCy[3] = (dCy[3] + 1.0) * sC;
-                        // record: x = [Jpdc_x | Jpdxi_x], y = [Jpdc_y | Jpdxi_y]
-                        rec[0] = (float) dCx[0]; rec[1] = (float) dCx[1]; rec[2] = (float) dCx[2]; rec[3] = (float) dCx[3];
-                        rec[4] = new_idepth * fxf; rec[5] = 0.f; rec[6] = -new_idepth * u * fxf; rec[7] = -u * v * fxf; rec[8] = (1.f + u * u) * fxf; rec[9] = -v * fxf;
-                        rec[10] = (float) dCy[0]; rec[11] = (float) dCy[1]; rec[12] = (float) dCy[2]; rec[13] = (float) dCy[3];
-                        rec[14] = 0.f; rec[15] = new_idepth * fyf; rec[16] = -new_idepth * v * fyf; rec[17] = -(1.f + v * v) * fyf; rec[18] = u * v * fyf; rec[19] = u * fyf;
-                        rec[20] = J00; rec[21] = J10; rec[22] = J11;                    // JIdx2
-                        rec[23] = A00; rec[24] = A10; rec[25] = JIr0;                   // x-multipliers of columns a, b, r (BA:1740-1745)
-                        rec[26] = A01; rec[27] = A11; rec[28] = JIr1;                   // y-multipliers
-                        rec[29] = B00; rec[30] = B01; rec[31] = Jabr0; rec[32] = B11; rec[33] = Jabr1; rec[34] = rr;   // BA:1736-1738
-                        // applyRes (BA:2066-2080) and the per-point sums of addToHessianTop (BA:1747-1750)
-                        const float v0 = J00 * Jpdd0 + J10 * Jpdd1, v1 = J10 * Jpdd0 + J11 * Jpdd1;
-#pragma unroll
-                        for (int k = 0; k < 6; k++) trow[k] = rec[4 + k] * v0 + rec[14 + k] * v1;
-                        trow[6] = A00 * Jpdd0 + A01 * Jpdd1;
-                        trow[7] = A10 * Jpdd0 + A11 * Jpdd1;
-                        trow[8] = JIr0 * Jpdd0 + JIr1 * Jpdd1;                          // bd
-                        trow[9] = v0 * Jpdd0 + v1 * Jpdd1;                              // Hdd
-#pragma unroll
-                        for (int k = 0; k < 4; k++) trow[10 + k] = rec[k] * v0 + rec[10 + k] * v1;   // Hcd
-                        trow[14] = 1.f;
-                        good = true;
-                        if (kDump) {
-                            float *d = w.dbg + (size_t) r * DBG_STRIDE;
-                            d[40] = Jpdd0; d[41] = Jpdd1; d[42] = J00; d[43] = J10; d[44] = J11;
-                            d[45] = A00; d[46] = A01; d[47] = A10; d[48] = A11; d[49] = B00; d[50] = B01; d[51] = B11;
-                        }
-                        if (fix) {   // BA:1571-1592: relative baseline, numGoodResiduals
-                            const double Rk0 = R0 * klx + R1 * kly + R2, Rk1 = R3 * klx + R4 * kly + R5, Rk2 = R6 * klx + R7 * kly + R8;
-                            const double ix_ = (Rk0 / Rk2) * w.fx + w.cx, iy_ = (Rk1 / Rk2) * w.fy + w.cy;
-                            const double ddx = ix_ - Kuc, ddy = iy_ - Kvc;
-                            const float relBS = (float) (0.01 * sqrt(ddx * ddx + ddy * ddy));
-                            atomicMax(reinterpret_cast<int *>(w.pt_max_rel_bs + p), __float_as_int(relBS));
-                            atomicAdd(w.pt_num_good + p, 1);
-                        }
-                    }
-                }
-            }
-            // applyRes (BA:2051-2093), as the candidate that becomes current when the step is accepted
-            if (st_out != RES_OOB) { st_out = nst; e_out = ne; }
+            if (!inb) nst = RES_OOB;             // setNewState(OOB) (BA:116, 210); state_NewEnergy keeps its old value
+            else sample = true;
         }
+    }
+    // ---- phase 2: cooperative tap fetch of the target image (image/Array2D.h:265-286 reads (ix,iy) (ix+1,iy) (ix,iy+1) (ix+1,iy+1))
+    int *woffs = s_offs + wid * 256;             // [pixel i][residual j]: lane j writes a column, lane l reads row l>>2
+    if (sample) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) woffs[i * 32 + lane] = (int) qy[i] * w.W + (int) qx[i];
+    }
+    __syncwarp();
+    const unsigned smask = __ballot_sync(0xffffffffu, sample);
+    {
+        const float4 *__restrict__ img = w.img[t] + ((lane & 1) + ((lane & 2) ? w.W : 0));
+        float4 *rowbase = s_taps + (size_t) wid * 32 * TAP_ROW + lane;
+        const int4 *orow = reinterpret_cast<const int4 *>(woffs + (lane >> 2) * 32);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+            const int4 o = orow[j4];
+            if ((smask >> (4 * j4 + 0)) & 1u) cp_async16(rowbase + (4 * j4 + 0) * TAP_ROW, img + o.x);
+            if ((smask >> (4 * j4 + 1)) & 1u) cp_async16(rowbase + (4 * j4 + 1) * TAP_ROW, img + o.y);
+            if ((smask >> (4 * j4 + 2)) & 1u) cp_async16(rowbase + (4 * j4 + 2) * TAP_ROW, img + o.z);
+            if ((smask >> (4 * j4 + 3)) & 1u) cp_async16(rowbase + (4 * j4 + 3) * TAP_ROW, img + o.w);
+        }
+        cp_async_wait_all();
+    }
+    __syncwarp();
+    // ---- phase 3: per-residual sampling + Jacobians
+    float rec[RJ_STRIDE];
+    float trow[T_STRIDE];
+#pragma unroll
+    for (int k = 0; k < RJ_STRIDE; k++) rec[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < T_STRIDE; k++) trow[k] = 0.f;
+    if (sample) {
+        const float4 *mytaps = s_taps + (size_t) (wid * 32 + lane) * TAP_ROW;
+        const float col[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float wts[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float b0 = pp.b0;
+        const float sqrt_cth = sqrtf(w.cth);
+        float J00 = 0, J11 = 0, J10 = 0, A00 = 0, A01 = 0, A10 = 0, A11 = 0, B00 = 0, B01 = 0, B11 = 0, wJI2 = 0, E = 0;
+        float JIr0 = 0, JIr1 = 0, Jabr0 = 0, Jabr1 = 0, rr = 0;
+        bool finite = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 t00 = mytaps[i * 4 + 0], t10 = mytaps[i * 4 + 1], t01 = mytaps[i * 4 + 2], t11 = mytaps[i * 4 + 3];
+            const int ix = (int) qx[i], iy = (int) qy[i];
+            const float dx = qx[i] - (float) ix, dy = qy[i] - (float) iy;
+            const float dxdy = dx * dy;
+            const float w00 = 1.f - dx - dy + dxdy, w10 = dx - dxdy, w01 = dy - dxdy, w11 = dxdy;
+            const float I = t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
+            const float gx = t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
+            const float gy = t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
+            finite = finite && isfinite(I) && isfinite(gx) && isfinite(gy);
+            const float refReal = (float) (pp.a * (double) col[i] + pp.b);     // exposureTransition (BA:229)
+            const float res = I - refReal;
+            const float ar = fabsf(res);
+            // MUFU-based division / rsqrt / sqrt (<= 2 ulp, ~2e-7 relative; the parity tolerance is 1e-4)
+            float hw = ar < w.huber ? 1.f : __fdividef(w.huber, ar);           // BA:233
+            float wg = sqrt_cth * rsqrtf(w.cth + (gx * gx + gy * gy));         // BA:234  sqrt(c / (c + |grad|^2))
+            wg = 0.5f * (wg + wts[i]);                                         // BA:235
+            E += wg * wg * hw * res * res * (2.f - hw);                        // BA:237
+            if (hw < 1.f) hw = __fsqrt_rn(hw);
+            hw = hw * wg;
+            const float h1 = gx * hw, h2 = gy * hw, drdA = I - b0;
+            const float rF = res * hw;
+            const float ja = (w.optA ? drdA * hw : 0.f), jb = (w.optB ? hw : 0.f);   // BA:273-278 (zeroed after the sums below)
+            J00 += h1 * h1; J11 += h2 * h2; J10 += h1 * h2;
+            A00 += drdA * hw * h1; A01 += drdA * hw * h2; A10 += hw * h1; A11 += hw * h2;
+            B00 += drdA * drdA * hw * hw; B01 += drdA * hw * hw; B11 += hw * hw;
+            wJI2 += hw * hw * (h1 * h1 + h2 * h2);
+            JIr0 += rF * h1; JIr1 += rF * h2; Jabr0 += rF * ja; Jabr1 += rF * jb; rr += rF * rF;   // BA:1722-1729
+            if (kDump) {
+                float *d = w.dbg + (size_t) r * DBG_STRIDE;
+                d[i] = rF; d[8 + i] = h1; d[16 + i] = h2; d[24 + i] = ja; d[32 + i] = jb;
+            }
+        }
+        if (!finite) {
+            // BA:220-223 sets the *committed* state to OOB.  (The reference leaves a stale isActiveAndIsGoodNEW
+            // behind in that case; only reachable with NaN/Inf texels, we clear it.)
+            st_out = RES_OOB;
+        } else if (!isfinite(E)) {
+            nst = RES_OOB;               // BA:297-300
+        } else {
+            neo = E;
+            const float th = fmaxf(w.frames[h].energy_th, w.frames[t].energy_th);
+            if (E > th || wJI2 < 2.f) { E = th; nst = RES_OUTLIER; } else nst = RES_IN;   // BA:303-311
+            ne = E;
+            ret = (double) E;
+            if (nst == RES_IN) {
+                // ---- geometric Jacobians at the FEJ point (BA:120-188); note u,v are the UN-normalised P.xy (BA:121-122)
+                const float drescale = (float) (1.0 / Pc2);
+                const float new_idepth = (float) ((double) drescale * rho);
+                const float u = (float) Pc0, v = (float) Pc1;
+                const float fxf = (float) w.fx, fyf = (float) w.fy;
+                const double ud = (double) u, vd = (double) v, dr = (double) drescale;
+                const double klx = (xc - w.cx) * w.fxi, kly = (yc - w.cy) * w.fyi;      // KliP
+                const float Jpdd0 = (float) (dr * (pp.t0[0] - pp.t0[2] * ud) * (double) fxf);
+                const float Jpdd1 = (float) (dr * (pp.t0[1] - pp.t0[2] * vd) * (double) fyf);
+                double dCx[4], dCy[4];
+                dCx[2] = dr * (pp.R0[6] * ud - pp.R0[0]);
+                dCx[3] = (double) (fxf * drescale) * (pp.R0[7] * ud - pp.R0[1]) / (double) fyf;
+                dCx[0] = klx * dCx[2]; dCx[1] = kly * dCx[3];
+                dCy[2] = (double) (fyf * drescale) * (pp.R0[6] * vd - pp.R0[3]) / (double) fxf;
+                dCy[3] = dr * (pp.R0[7] * vd - pp.R0[4]);
+                dCy[0] = klx * dCy[2]; dCy[1] = kly * dCy[3];
+                const double sF = (double) w.scaleF, sC = (double) w.scaleC;
+                dCx[0] = (dCx[0] + ud) * sF; dCx[1] *= sF; dCx[2] = (dCx[2] + 1.0) * sC; dCx[3] *= sC;
+                dCy[0] *= sF; dCy[1] = (dCy[1] + vd) * sF; dCy[2] *= sC; dCy[3] = (dCy[3] + 1.0) * sC;
+                // record: x = [Jpdc_x | Jpdxi_x], y = [Jpdc_y | Jpdxi_y]
+                rec[0] = (float) dCx[0]; rec[1] = (float) dCx[1]; rec[2] = (float) dCx[2]; rec[3] = (float) dCx[3];
+                rec[4] = new_idepth * fxf; rec[5] = 0.f; rec[6] = -new_idepth * u * fxf; rec[7] = -u * v * fxf; rec[8] = (1.f + u * u) * fxf; rec[9] = -v * fxf;
+                rec[10] = (float) dCy[0]; rec[11] = (float) dCy[1]; rec[12] = (float) dCy[2]; rec[13] = (float) dCy[3];
+                rec[14] = 0.f; rec[15] = new_idepth * fyf; rec[16] = -new_idepth * v * fyf; rec[17] = -(1.f + v * v) * fyf; rec[18] = u * v * fyf; rec[19] = u * fyf;
+                rec[20] = J00; rec[21] = J10; rec[22] = J11;                    // JIdx2
+                rec[23] = A00; rec[24] = A10; rec[25] = JIr0;                   // x-multipliers of columns a, b, r (BA:1740-1745)
+                rec[26] = A01; rec[27] = A11; rec[28] = JIr1;                   // y-multipliers
+                rec[29] = B00; rec[30] = B01; rec[31] = Jabr0; rec[32] = B11; rec[33] = Jabr1; rec[34] = rr;   // BA:1736-1738
+                // applyRes (BA:2066-2080) and the per-point sums of addToHessianTop (BA:1747-1750)
+                const float v0 = J00 * Jpdd0 + J10 * Jpdd1, v1 = J10 * Jpdd0 + J11 * Jpdd1;
+#pragma unroll
+                for (int k = 0; k < 6; k++) trow[k] = rec[4 + k] * v0 + rec[14 + k] * v1;
+                trow[6] = A00 * Jpdd0 + A01 * Jpdd1;
+                trow[7] = A10 * Jpdd0 + A11 * Jpdd1;
+                trow[8] = JIr0 * Jpdd0 + JIr1 * Jpdd1;                          // bd
+                trow[9] = v0 * Jpdd0 + v1 * Jpdd1;                              // Hdd
+#pragma unroll
+                for (int k = 0; k < 4; k++) trow[10 + k] = rec[k] * v0 + rec[10 + k] * v1;   // Hcd
+                trow[14] = 1.f;
+                good = true;
+                if (kDump) {
+                    float *d = w.dbg + (size_t) r * DBG_STRIDE;
+                    d[40] = Jpdd0; d[41] = Jpdd1; d[42] = J00; d[43] = J10; d[44] = J11;
+                    d[45] = A00; d[46] = A01; d[47] = A10; d[48] = A11; d[49] = B00; d[50] = B01; d[51] = B11;
+                }
+                if (fix) {   // BA:1571-1592: relative baseline, numGoodResiduals
+                    const double Rk0 = pp.R[0] * klx + pp.R[1] * kly + pp.R[2], Rk1 = pp.R[3] * klx + pp.R[4] * kly + pp.R[5], Rk2 = pp.R[6] * klx + pp.R[7] * kly + pp.R[8];
+                    const double ix_ = (Rk0 / Rk2) * w.fx + w.cx, iy_ = (Rk1 / Rk2) * w.fy + w.cy;
+                    const double ddx = ix_ - Kuc, ddy = iy_ - Kvc;
+                    const float relBS = (float) (0.01 * sqrt(ddx * ddx + ddy * ddy));
+                    atomicMax(reinterpret_cast<int *>(w.pt_max_rel_bs + p), __float_as_int(relBS));
+                    atomicAdd(w.pt_num_good + p, 1);
+                }
+            }
+        }
+    }
+    if (valid) {
+        // applyRes (BA:2051-2093), as the candidate that becomes current when the step is accepted
+        if (st != RES_OOB && st_out != RES_OOB) { st_out = nst; e_out = ne; }
         w.r_new_state[r] = nst; w.r_new_energy[r] = ne; w.r_new_energy_wo[r] = neo;
         w.r_state[nxt][r] = st_out; w.r_energy[nxt][r] = e_out; w.r_good[nxt][r] = good ? 1 : 0;
-        float4 *rj4 = reinterpret_cast<float4 *>(w.rj + (size_t) r * RJ_STRIDE);
+        if (kDump) {
+            float4 *rj4 = reinterpret_cast<float4 *>(w.rj + (size_t) r * RJ_STRIDE);
 #pragma unroll
-        for (int k = 0; k < RJ_STRIDE / 4; k++) rj4[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+            for (int k = 0; k < RJ_STRIDE / 4; k++) rj4[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+        }
         float4 *t4 = reinterpret_cast<float4 *>(w.T[nxt] + ((size_t) p * w.N + t) * T_STRIDE);
 #pragma unroll
         for (int k = 0; k < T_STRIDE / 4; k++) t4[k] = make_float4(trow[4 * k], trow[4 * k + 1], trow[4 * k + 2], trow[4 * k + 3]);
@@ -279,59 +366,35 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
             atomicAdd(&ctrl->num_dropped, 1);
         }
     }
-    // block energy (fp64, fixed order)
-    __shared__ double s_e[LIN_THREADS / 32];
-    double s = warp_sum_d(ret);
-    if ((threadIdx.x & 31) == 0) s_e[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot = 0;
-        for (int k = 0; k < LIN_THREADS / 32; k++) tot += s_e[k];
-        w.energy_part[blockIdx.x] = tot;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// HOT LOOP 2: 13x13 block [C4 | xi6 | a b | r] of every (host,target) bin.  One CTA per chunk of <=128
-// residuals of ONE bin; records are staged in shared memory, every lane owns 3 of the 91 unique entries.
-constexpr int REC_S = 60;  // smem record: raw[36] (x y A B BR, [35]=1) | Qx[10] | Qy[10] | zero[4]
-__global__ void __launch_bounds__(128) accumulate_kernel(const DevWin w, const int respect_done) {
-    if (respect_done && w.ctrl->done) return;
-    const int nxt = w.ctrl->cur ^ 1;
-    __shared__ __align__(16) float rec[ACC_CHUNK * REC_S];
-    __shared__ float red[4][ACC_N];
-    const int c = blockIdx.x, tid = threadIdx.x;
-    const int begin = w.acc_chunk_begin[c], cnt = w.acc_chunk_count[c];
-    const float4 *src = reinterpret_cast<const float4 *>(w.rj + (size_t) begin * RJ_STRIDE);
-    for (int i = tid; i < ACC_CHUNK * 9; i += 128) {
-        const int rr = i / 9, q = i - rr * 9;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr < cnt) v = __ldg(src + i);
-        if (q == 8) v.w = (rr < cnt) ? 1.f : 0.f;
-        *reinterpret_cast<float4 *>(&rec[rr * REC_S + q * 4]) = v;
-    }
-    __syncthreads();
-    {   // Q = JIdx2 * Jp
-        float *m = &rec[tid * REC_S];
-        const float a00 = m[20], a01 = m[21], a11 = m[22];
+    // ---- phase 4: 13x13 block of the bin (records of non-good residuals are all zero)
+    {
+        float Qx[10], Qy[10];
+        const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
 #pragma unroll
-        for (int k = 0; k < 10; k++) { const float x = m[k], y = m[10 + k]; m[36 + k] = a00 * x + a01 * y; m[46 + k] = a01 * x + a11 * y; }
-        m[56] = m[57] = m[58] = m[59] = 0.f;
+        for (int k = 0; k < 10; k++) { Qx[k] = a00 * rec[k] + a01 * rec[10 + k]; Qy[k] = a01 * rec[k] + a11 * rec[10 + k]; }
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) v[k] = acc_entry(g * 32 + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
+            s_red[wid * ACC_N + g * 32 + lane] = warp_transpose_sum(v, lane);
+        }
     }
+    // block energy (fp64, fixed order)
+    const double es = warp_sum_d(ret);
+    if (lane == 0) s_e[wid] = es;
     __syncthreads();
-    const int wid = tid >> 5, lane = tid & 31;
-    const uchar4 o0 = c_acc_ofs[lane], o1 = c_acc_ofs[lane + 32], o2 = c_acc_ofs[lane + 64];
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    const int rend = min(cnt, wid * 32 + 32);
-    for (int rr = wid * 32; rr < rend; rr++) {
-        const float *m = &rec[rr * REC_S];
-        a0 += m[o0.x] * m[o0.y] + m[o0.z] * m[o0.w];
-        a1 += m[o1.x] * m[o1.y] + m[o1.z] * m[o1.w];
-        a2 += m[o2.x] * m[o2.y] + m[o2.z] * m[o2.w];
+    if (tid < ACC_N) {
+        float a = s_red[tid];
+#pragma unroll
+        for (int k = 1; k < LIN_WARPS; k++) a += s_red[k * ACC_N + tid];
+        w.acc_part[nxt][(size_t) chunk * ACC_N + tid] = a;
     }
-    red[wid][lane] = a0; red[wid][lane + 32] = a1; red[wid][lane + 64] = a2;
-    __syncthreads();
-    if (tid < ACC_N) w.acc_part[nxt][(size_t) c * ACC_N + tid] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    if (tid == 0) {
+        double tot = 0;
+        for (int k = 0; k < LIN_WARPS; k++) tot += s_e[k];
+        w.energy_part[chunk] = tot;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -463,8 +526,9 @@ __device__ __forceinline__ int acc_index(int r, int c) {
 constexpr int ST_A_TT = 0, ST_A_IT = 64, ST_A_II = 128, ST_A_TC = 192, ST_A_IC = 224, ST_A_CC = 256, ST_BA_T = 272, ST_BA_I = 280, ST_BA_C = 288,
               ST_S_JI = 296, ST_S_II = 360, ST_S_JC = 424, ST_S_IC = 456, ST_BS_J = 488, ST_BS_I = 496, ST_S_JK = 504;
 __host__ __device__ __forceinline__ int st_stride(int N) { return ST_S_JK + 64 * N; }
+constexpr int ST_THREADS = 512;
 
-__global__ void __launch_bounds__(128) stitch_pair_kernel(const DevWin w, const int respect_done) {
+__global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
     extern __shared__ __align__(16) double smd[];
     const int N = w.N, NB = 8 * N, tid = threadIdx.x;
@@ -489,14 +553,14 @@ __global__ void __launch_bounds__(128) stitch_pair_kernel(const DevWin w, const 
     double *A = atd + NB;          // [ACC_N]  packed 13x13 block of bin (i -> j)
     double *Y = A + ACC_N;         // [8][8]   sum_k D_jk AH_ik^T
     double *M = Y + 64;            // [8][8]   AH_ij A8
-    for (int e = tid; e < 8 * NB + 40; e += 128) {
+    for (int e = tid; e < 8 * NB + 40; e += ST_THREADS) {
         int off;
         if (e < 8 * NB) off = j * 8 * NB + e;
         else if (e < 8 * NB + 32) off = NB * NB + j * 32 + (e - 8 * NB);
         else off = NB * NB + NB * 4 + j * 8 + (e - 8 * NB - 32);
         const float *src = w.sc_part + (size_t) cb * w.sc_stride + off;
         double s = 0.0;
-#pragma unroll 8
+#pragma unroll 16
         for (int c = cb; c < ce; c++, src += w.sc_stride) s += (double) __ldg(src);
         Dj[e] = s;                 // Dj, Ej, EBj are contiguous
     }
@@ -509,19 +573,19 @@ __global__ void __launch_bounds__(128) stitch_pair_kernel(const DevWin w, const 
         for (int c = b0; c < b1; c++, src += ACC_N) s += (double) __ldg(src);
         A[tid] = s;
     }
-    for (int e = tid; e < N * 64; e += 128) G[e] = w.AH[(size_t) (i * N) * 64 + e];
-    for (int e = tid; e < NB; e += 128) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
+    for (int e = tid; e < N * 64; e += ST_THREADS) G[e] = w.AH[(size_t) (i * N) * 64 + e];
+    for (int e = tid; e < NB; e += ST_THREADS) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
     __syncthreads();
     const double *AHj = G + j * 64, *atj = atd + j * 8;
     {
         const int r = (tid >> 3) & 7, c = tid & 7;
         double s = 0.0;
         if (tid < 64) { for (int k = 0; k < N; k++) for (int m = 0; m < 8; m++) s += Dj[r * NB + k * 8 + m] * G[k * 64 + c * 8 + m]; Y[tid] = s; }
-        else { for (int m = 0; m < 8; m++) s += AHj[r * 8 + m] * A[acc_index(4 + m, 4 + c)]; M[tid - 64] = s; }
+        else if (tid < 128) { for (int m = 0; m < 8; m++) s += AHj[r * 8 + m] * A[acc_index(4 + m, 4 + c)]; M[tid - 64] = s; }
     }
     __syncthreads();
     const int tot = st_stride(N);
-    for (int e = tid; e < tot; e += 128) {
+    for (int e = tid; e < tot; e += ST_THREADS) {
         double v = 0.0;
         if (e < ST_A_TC) {                       // 8x8 active blocks
             const int q = e & 63, r = q >> 3, c = q & 7;
