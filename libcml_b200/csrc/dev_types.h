@@ -9,8 +9,8 @@ constexpr int MAXF = 16;          // CMLBA_MAX_FRAMES
 constexpr int RJ_STRIDE = 36;     // floats per residual Jacobian record (x[10] y[10] A[3] B[6] BR[6] pad)
 constexpr int T_STRIDE = 16;      // floats per (point,target) Schur row: JpJdF[8] bd Hdd Hcd[4] good pad
 constexpr int ACC_N = 96;         // 91 unique entries of the 13x13 block, padded to 3*32
-constexpr int LIN_THREADS = 128;  // linearize: one thread per residual
-constexpr int ACC_CHUNK = 128;    // residuals per accumulate CTA (all in one (h,t) bin)
+constexpr int LIN_THREADS = 32;   // linearize+accumulate: one warp-CTA per chunk, one thread per residual
+constexpr int ACC_CHUNK = 32;     // residuals per linearize+accumulate CTA (all in one (h,t) bin)
 constexpr int SC_CHUNK = 64;      // points per Schur CTA (all hosted in one frame)
 
 enum : uint8_t { RES_IN = 0, RES_OOB = 1, RES_OUTLIER = 2 };

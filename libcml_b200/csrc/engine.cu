@@ -241,8 +241,8 @@ public:
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
-        CK(cudaFuncSetAttribute(linearize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) LIN_SMEM));
-        CK(cudaFuncSetAttribute(linearize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) LIN_SMEM));
+        CK(cudaFuncSetAttribute(linearize_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(linearize_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         return CMLBA_OK;
@@ -719,9 +719,9 @@ public:
     }
 
     // ------------------------------------------------------------------ kernel sequences
-    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128); }
+    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128 + 4 * ACC_N); }
     size_t solve_smem() const { const int n = dw.n; return sizeof(double) * ((size_t) n * n + 3 * n + 256); }
-    size_t schur_smem() const { return sizeof(float) * ((size_t) SC_CHUNK * 8 * dw.N + SC_CHUNK * 6); }
+    size_t schur_smem() const { return schur_smem_bytes(dw.N); }
 
     void launch_linearize(int fix, int respect_done) {
         if (dw.R == 0) return;
@@ -999,6 +999,8 @@ public:
             if (n_sc_chunks) CK(cudaMemcpy(part.data(), d_sc_part.p, part.size() * 4, cudaMemcpyDeviceToHost));
             std::vector<double> s((size_t) N * tot, 0.0);
             for (int h = 0; h < N; h++) for (int ch = h_host_chunk_begin[h]; ch < h_host_chunk_begin[h + 1]; ch++) for (int k = 0; k < tot; k++) s[(size_t) h * tot + k] += part[(size_t) ch * dw.sc_stride + k];
+            // schur_kernel stores only the 4x4 tiles on or below the diagonal of D: mirror them
+            for (int h = 0; h < N; h++) for (int r = 0; r < NB; r++) for (int cc = 0; cc < NB; cc++) if ((r >> 2) < (cc >> 2)) s[(size_t) h * tot + r * NB + cc] = s[(size_t) h * tot + cc * NB + r];
             return host_out(s.data(), s.size() * 8, dst, cap, bytes);
         }
         set_error("unknown buffer name: " + name);

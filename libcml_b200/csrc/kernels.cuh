@@ -96,9 +96,8 @@ __global__ void set_evalpt_newest_kernel(const DevWin w) {
 //   phase 4  13x13 block [C4 | xi6 | a b | r] of the bin: the 91 products of every lane are summed over the warp by a
 //            transposing butterfly (31 shuffles per 32 entries, lane L ends up owning entry L), then over the 4 warps
 //            in fixed order -> acc_part[chunk] (fixed-order: bitwise reproducible)
-constexpr int TAP_ROW = 33;
-constexpr int LIN_WARPS = LIN_THREADS / 32;
-constexpr size_t LIN_SMEM = (size_t) LIN_WARPS * 32 * TAP_ROW * 16 + (size_t) LIN_WARPS * 32 * 8 * 4 + (size_t) LIN_WARPS * ACC_N * 4 + LIN_WARPS * 8 + sizeof(PairPre);
+constexpr int TAP_ROW = 32;          // float4 per staged residual; column index is XOR-swizzled with the row (conflict-free without padding)
+constexpr size_t LIN_SMEM = (size_t) 32 * TAP_ROW * 16;   // 16 KB per warp-CTA: 13 CTAs fit one SM (228 KB, 1 KB reserved per CTA)
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
@@ -140,21 +139,12 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     extern __shared__ __align__(16) unsigned char lin_smem[];
-    float4 *s_taps = reinterpret_cast<float4 *>(lin_smem);                         // [warps][32][TAP_ROW]
-    int *s_offs = reinterpret_cast<int *>(s_taps + LIN_WARPS * 32 * TAP_ROW);      // [warps][32][8]
-    float *s_red = reinterpret_cast<float *>(s_offs + LIN_WARPS * 32 * 8);         // [warps][ACC_N]
-    double *s_e = reinterpret_cast<double *>(s_red + LIN_WARPS * ACC_N);           // [warps]
-    PairPre *s_pp = reinterpret_cast<PairPre *>(s_e + LIN_WARPS);
-    const int chunk = blockIdx.x, tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    float4 *s_taps = reinterpret_cast<float4 *>(lin_smem);                         // [32 residuals][TAP_ROW], swizzled
+    int *s_offs = reinterpret_cast<int *>(lin_smem);                               // [8][32] texel offsets: consumed before the taps land (aliased)
+    const int chunk = blockIdx.x, tid = threadIdx.x, lane = tid;
     const int begin = w.acc_chunk_begin[chunk], cnt = w.acc_chunk_count[chunk], bin = w.acc_chunk_bin[chunk];
     const int t = bin / w.N, h = bin - t * w.N;
-    {
-        const double *src = reinterpret_cast<const double *>(&w.pairs[h * w.N + t]);
-        double *dst = reinterpret_cast<double *>(s_pp);
-        for (int k = tid; k < (int) (sizeof(PairPre) / 8); k += LIN_THREADS) dst[k] = src[k];
-    }
-    __syncthreads();
-    const PairPre &pp = *s_pp;
+    const PairPre &pp = w.pairs[h * w.N + t];                                      // warp-uniform: broadcast loads
     const int cur = ctrl->cur, nxt = cur ^ 1;
     const int r = begin + tid;
     // all per-residual scalars are requested together (one exposed latency), then the point record
@@ -207,7 +197,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
         }
     }
     // ---- phase 2: cooperative tap fetch of the target image (image/Array2D.h:265-286 reads (ix,iy) (ix+1,iy) (ix,iy+1) (ix+1,iy+1))
-    int *woffs = s_offs + wid * 256;             // [pixel i][residual j]: lane j writes a column, lane l reads row l>>2
+    int *woffs = s_offs;                         // [pixel i][residual j]: lane j writes a column, lane l reads row l>>2
     if (sample) {
 #pragma unroll
         for (int i = 0; i < 8; i++) woffs[i * 32 + lane] = (int) qy[i] * w.W + (int) qx[i];
@@ -216,15 +206,18 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
     const unsigned smask = __ballot_sync(0xffffffffu, sample);
     {
         const float4 *__restrict__ img = w.img[t] + ((lane & 1) + ((lane & 2) ? w.W : 0));
-        float4 *rowbase = s_taps + (size_t) wid * 32 * TAP_ROW + lane;
         const int4 *orow = reinterpret_cast<const int4 *>(woffs + (lane >> 2) * 32);
+        int4 o[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) o[j4] = orow[j4];
+        __syncwarp();                                // every lane holds its 32 offsets: the table may be overwritten by the taps
+        // tap l of residual j lives at s_taps[j][l ^ j]
 #pragma unroll
         for (int j4 = 0; j4 < 8; j4++) {
-            const int4 o = orow[j4];
-            if ((smask >> (4 * j4 + 0)) & 1u) cp_async16(rowbase + (4 * j4 + 0) * TAP_ROW, img + o.x);
-            if ((smask >> (4 * j4 + 1)) & 1u) cp_async16(rowbase + (4 * j4 + 1) * TAP_ROW, img + o.y);
-            if ((smask >> (4 * j4 + 2)) & 1u) cp_async16(rowbase + (4 * j4 + 2) * TAP_ROW, img + o.z);
-            if ((smask >> (4 * j4 + 3)) & 1u) cp_async16(rowbase + (4 * j4 + 3) * TAP_ROW, img + o.w);
+            if ((smask >> (4 * j4 + 0)) & 1u) cp_async16(s_taps + (4 * j4 + 0) * TAP_ROW + (lane ^ (4 * j4 + 0)), img + o[j4].x);
+            if ((smask >> (4 * j4 + 1)) & 1u) cp_async16(s_taps + (4 * j4 + 1) * TAP_ROW + (lane ^ (4 * j4 + 1)), img + o[j4].y);
+            if ((smask >> (4 * j4 + 2)) & 1u) cp_async16(s_taps + (4 * j4 + 2) * TAP_ROW + (lane ^ (4 * j4 + 2)), img + o[j4].z);
+            if ((smask >> (4 * j4 + 3)) & 1u) cp_async16(s_taps + (4 * j4 + 3) * TAP_ROW + (lane ^ (4 * j4 + 3)), img + o[j4].w);
         }
         cp_async_wait_all();
     }
@@ -237,7 +230,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
 #pragma unroll
     for (int k = 0; k < T_STRIDE; k++) trow[k] = 0.f;
     if (sample) {
-        const float4 *mytaps = s_taps + (size_t) (wid * 32 + lane) * TAP_ROW;
+        const float4 *mytaps = s_taps + lane * TAP_ROW;
         const float col[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
         const float wts[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         const float b0 = pp.b0;
@@ -247,7 +240,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
         bool finite = true;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const float4 t00 = mytaps[i * 4 + 0], t10 = mytaps[i * 4 + 1], t01 = mytaps[i * 4 + 2], t11 = mytaps[i * 4 + 3];
+            const float4 t00 = mytaps[(i * 4 + 0) ^ lane], t10 = mytaps[(i * 4 + 1) ^ lane], t01 = mytaps[(i * 4 + 2) ^ lane], t11 = mytaps[(i * 4 + 3) ^ lane];
             const int ix = (int) qx[i], iy = (int) qy[i];
             const float dx = qx[i] - (float) ix, dy = qy[i] - (float) iy;
             const float dxdy = dx * dy;
@@ -372,67 +365,61 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
         const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
 #pragma unroll
         for (int k = 0; k < 10; k++) { Qx[k] = a00 * rec[k] + a01 * rec[10 + k]; Qy[k] = a01 * rec[k] + a11 * rec[10 + k]; }
+        float *out = w.acc_part[nxt] + (size_t) chunk * ACC_N;
 #pragma unroll
         for (int g = 0; g < 3; g++) {
             float v[32];
 #pragma unroll
             for (int k = 0; k < 32; k++) v[k] = acc_entry(g * 32 + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
-            s_red[wid * ACC_N + g * 32 + lane] = warp_transpose_sum(v, lane);
+            out[g * 32 + lane] = warp_transpose_sum(v, lane);
         }
     }
-    // block energy (fp64, fixed order)
+    // chunk energy (fp64, fixed order)
     const double es = warp_sum_d(ret);
-    if (lane == 0) s_e[wid] = es;
-    __syncthreads();
-    if (tid < ACC_N) {
-        float a = s_red[tid];
-#pragma unroll
-        for (int k = 1; k < LIN_WARPS; k++) a += s_red[k * ACC_N + tid];
-        w.acc_part[nxt][(size_t) chunk * ACC_N + tid] = a;
-    }
-    if (tid == 0) {
-        double tot = 0;
-        for (int k = 0; k < LIN_WARPS; k++) tot += s_e[k];
-        w.energy_part[chunk] = tot;
-    }
+    if (lane == 0) w.energy_part[chunk] = es;
 }
 
 // ------------------------------------------------------------------------------------------------
-// HOT LOOP 3: Schur complement of the inverse depths.  One CTA per chunk of <=64 points hosted in ONE
-// frame: per-point Hdd/bd/Hcd, Hdd^-1, then the (8N x 8N) outer-product sum D = sum_p HdiF * v_p v_p^T
-// (v_p = the point's JpJdF rows over all targets, zero where there is no good residual), E, EB, Hcc, bc.
+// HOT LOOP 3: Schur complement of the inverse depths (addToHessianSC, BA:1880-1937).  One CTA per chunk of <=64
+// points hosted in ONE frame.  With s = sqrt(Hdd^-1) every accumulator of the reference is one block of a single
+// symmetric rank update of the augmented per-point vector z = s * [ JpJdF over all targets (8N) | Hcd (4) | bdSum ]:
+//   D = sum z_u z_u^T   E = sum z_u z_c^T   EB = sum z_u z_b   Hcc = sum z_c z_c^T   bc = sum z_c z_b
+// (the N^3 8x8 accumulators of BA:1040 per host are the (8N)^2 matrix D).  4x4 register tiles, 2 LDS.128 per 16 FMA;
+// only tiles on or below the diagonal of D are computed and stored (sc_tile_index reads the mirror image).
+constexpr int SCZ_PAD = 8;     // z_c (4) z_b (1) pad (3)
+__host__ __device__ __forceinline__ size_t schur_smem_bytes(int N) { return sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * (8 * N + SCZ_PAD)); }
+// element (row, col) of the stored D: lower 4x4-tile triangle only
+__device__ __forceinline__ int sc_d_index(int row, int col, int NB) { return ((row >> 2) >= (col >> 2)) ? row * NB + col : col * NB + row; }
+
 __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
     extern __shared__ __align__(16) float sm[];
-    const int N = w.N, NB = 8 * N;
+    const int N = w.N, NB = 8 * N, ZS = NB + SCZ_PAD;
     const int cur = w.ctrl->cur;
-    float *sT = sm;                                  // [SC_CHUNK][N][8]  JpJdF rows
-    float *hdi = sT + SC_CHUNK * NB;                 // [SC_CHUNK]
-    float *bds = hdi + SC_CHUNK;                     // [SC_CHUNK] HdiF*bdSum
-    float *hcd = bds + SC_CHUNK;                     // [SC_CHUNK][4]
+    float *sT = sm;                                  // [SC_CHUNK][N][T_STRIDE] raw Schur rows
+    float *sZ = sT + SC_CHUNK * N * T_STRIDE;        // [SC_CHUNK][ZS]         augmented, scaled
     const int c = blockIdx.x, tid = threadIdx.x;
     const int begin = w.sc_chunk_begin[c], cnt = w.sc_chunk_count[c];
-    const float *Tsrc = w.T[cur] + (size_t) begin * N * T_STRIDE;
-    // stage JpJdF (first 8 floats of every row)
-    for (int i = tid; i < SC_CHUNK * N * 2; i += 256) {
-        const int row = i >> 1, half = i & 1;        // row = p*N + t
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < cnt * N) v = __ldg(reinterpret_cast<const float4 *>(Tsrc + (size_t) row * T_STRIDE) + half);
-        *reinterpret_cast<float4 *>(&sT[row * 8 + half * 4]) = v;
+    {   // stage the rows of the chunk's points (contiguous in T)
+        const float4 *src = reinterpret_cast<const float4 *>(w.T[cur] + (size_t) begin * N * T_STRIDE);
+        float4 *dst = reinterpret_cast<float4 *>(sT);
+        const int n4 = cnt * N * (T_STRIDE / 4), tot4 = SC_CHUNK * N * (T_STRIDE / 4);
+        for (int i = tid; i < tot4; i += 256) dst[i] = i < n4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // per point sums (BA:1895-1907)
+    __syncthreads();
+    // per point sums (BA:1895-1907), one thread per point
     if (tid < SC_CHUNK) {
-        float Hdd = 0.f, bd = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f; int ng = 0;
-        float hd = 0.f, bs = 0.f;
+        float sh = 0.f, hc0 = 0.f, hc1 = 0.f, hc2 = 0.f, hc3 = 0.f, bs = 0.f;
         if (tid < cnt) {
             const int p = begin + tid;
+            float Hdd = 0.f, bd = 0.f, h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f; int ng = 0;
             for (int t = 0; t < N; t++) {
-                const float4 *q = reinterpret_cast<const float4 *>(Tsrc + ((size_t) tid * N + t) * T_STRIDE);
-                const float4 a = __ldg(q + 2), b = __ldg(q + 3);   // bd Hdd Hcd0 Hcd1 | Hcd2 Hcd3 good pad
+                const float4 a = *reinterpret_cast<const float4 *>(sT + (tid * N + t) * T_STRIDE + 8);    // bd Hdd Hcd0 Hcd1
+                const float4 b = *reinterpret_cast<const float4 *>(sT + (tid * N + t) * T_STRIDE + 12);   // Hcd2 Hcd3 good pad
                 bd += a.x; Hdd += a.y; h0 += a.z; h1 += a.w; h2 += b.x; h3 += b.y; ng += (b.z != 0.f);
             }
             const float priorF = w.pt_priorF[p];
-            float idh = 0.f, bdSum = 0.f;
+            float idh = 0.f, bdSum = 0.f, hd = 0.f;
             if (ng > 0) {
                 float Hs = Hdd + priorF;
                 if (Hs < 1e-10f) Hs = 1e-10f;
@@ -440,68 +427,73 @@ __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int re
                 hd = (float) (1.0 / (double) Hs);
                 const float deltaF = (float) (w.pt_idepth[p] - (double) w.pt_idepth_zero[p]);
                 bdSum = bd + priorF * deltaF;
-                bs = hd * bdSum;
+                sh = sqrtf(hd);
             } else {
                 w.pt_max_rel_bs[p] = 0.f;        // BA:1885-1893
             }
             w.pt_Hdd[p] = Hdd; w.pt_bd[p] = bd;
             w.pt_Hcd[p * 4 + 0] = h0; w.pt_Hcd[p * 4 + 1] = h1; w.pt_Hcd[p * 4 + 2] = h2; w.pt_Hcd[p * 4 + 3] = h3;
             w.pt_HdiF[p] = hd; w.pt_bdSumF[p] = bdSum; w.pt_idepth_hessian[p] = idh; w.pt_ngood_cur[p] = ng;
+            hc0 = sh * h0; hc1 = sh * h1; hc2 = sh * h2; hc3 = sh * h3; bs = sh * bdSum;
         }
-        hdi[tid] = hd; bds[tid] = bs;
-        hcd[tid * 4 + 0] = h0; hcd[tid * 4 + 1] = h1; hcd[tid * 4 + 2] = h2; hcd[tid * 4 + 3] = h3;
+        float *z = sZ + tid * ZS;
+        z[NB + 0] = hc0; z[NB + 1] = hc1; z[NB + 2] = hc2; z[NB + 3] = hc3; z[NB + 4] = bs; z[NB + 5] = 0.f; z[NB + 6] = 0.f; z[NB + 7] = 0.f;
+        sT[tid * N * T_STRIDE + 15] = sh;            // pad slot of the point's first row carries the scale to the next phase
+    }
+    __syncthreads();
+    for (int i = tid; i < SC_CHUNK * N * 2; i += 256) {      // z_u = s * JpJdF
+        const int row = i >> 1, half = i & 1, pnt = row / N, t = row - pnt * N;
+        const float sh = sT[pnt * N * T_STRIDE + 15];
+        float4 v = *reinterpret_cast<const float4 *>(sT + row * T_STRIDE + half * 4);
+        v.x *= sh; v.y *= sh; v.z *= sh; v.w *= sh;
+        *reinterpret_cast<float4 *>(sZ + pnt * ZS + t * 8 + half * 4) = v;
     }
     __syncthreads();
     float *out = w.sc_part + (size_t) c * w.sc_stride;
-    // D: 4x4 register tiles; tile s -> (t1, t2, ti, tj)
-    const int ntiles = 4 * N * N;
-    for (int s = tid; s < ntiles; s += 256) {
-        const int tj = s & 1, ti = (s >> 1) & 1, t2 = (s >> 2) % N, t1 = (s >> 2) / N;
+    float *oE = out + NB * NB, *oEB = oE + NB * 4, *oHcc = oEB + NB, *obc = oHcc + 16;
+    // tiles: (tr, tc), tc <= tr over the 2N x 2N tile grid of D, then tile columns 2N (z_c) and 2N+1 (z_b) for every tr
+    const int ntr = 2 * N, ntri = ntr * (ntr + 1) / 2, ntiles = ntri + 2 * ntr;
+    for (int id = tid; id < ntiles; id += 256) {
+        int tr, tc;
+        if (id < ntri) {
+            tr = (int) ((sqrtf(8.f * (float) id + 1.f) - 1.f) * 0.5f);
+            while (tr * (tr + 1) / 2 > id) tr--;
+            while ((tr + 1) * (tr + 2) / 2 <= id) tr++;
+            tc = id - tr * (tr + 1) / 2;
+        } else { tr = (id - ntri) >> 1; tc = ntr + ((id - ntri) & 1); }
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
-        const float *pa = sT + t1 * 8 + ti * 4, *pb = sT + t2 * 8 + tj * 4;
-        for (int p = 0; p < cnt; p++) {
-            const float4 a = *reinterpret_cast<const float4 *>(pa + p * NB);
-            const float4 b = *reinterpret_cast<const float4 *>(pb + p * NB);
-            const float hh = hdi[p];
-            const float av[4] = {a.x * hh, a.y * hh, a.z * hh, a.w * hh};
-            const float bv[4] = {b.x, b.y, b.z, b.w};
+        const float *pa = sZ + tr * 4, *pb = sZ + tc * 4;
+#pragma unroll 4
+        for (int pnt = 0; pnt < SC_CHUNK; pnt++) {
+            const float4 a = *reinterpret_cast<const float4 *>(pa + pnt * ZS);
+            const float4 b = *reinterpret_cast<const float4 *>(pb + pnt * ZS);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bv[j];
         }
+        if (tc < ntr) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float4 *o = reinterpret_cast<float4 *>(out + (size_t) (t1 * 8 + ti * 4 + i) * NB + t2 * 8 + tj * 4);
-            *o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            for (int i = 0; i < 4; i++) *reinterpret_cast<float4 *>(out + (size_t) (tr * 4 + i) * NB + tc * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        } else if (tc == ntr) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) *reinterpret_cast<float4 *>(oE + (tr * 4 + i) * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) oEB[tr * 4 + i] = acc[i][0];
         }
     }
-    // E (8N x 4), EB (8N), Hcc (4x4), bc (4)
-    float *oE = out + NB * NB, *oEB = oE + NB * 4, *oHcc = oEB + NB, *obc = oHcc + 16;
-    const int nsmall = NB * 4 + NB + 16 + 4;
-    for (int e = tid; e < nsmall; e += 256) {
+    if (tid >= 224 && tid < 244) {       // Hcc (4x4), bc (4): last warp, otherwise idle in the tile loop when N <= 8
+        const int k = tid - 224;
         float acc = 0.f;
-        if (e < NB * 4) {
-            const int row = e >> 2, cc = e & 3;
-            for (int p = 0; p < cnt; p++) acc += hdi[p] * sT[p * NB + row] * hcd[p * 4 + cc];
-            oE[e] = acc;
-        } else if (e < NB * 5) {
-            const int row = e - NB * 4;
-            for (int p = 0; p < cnt; p++) acc += bds[p] * sT[p * NB + row];
-            oEB[row] = acc;
-        } else if (e < NB * 5 + 16) {
-            const int k = e - NB * 5, i = k >> 2, j = k & 3;
-            for (int p = 0; p < cnt; p++) acc += hdi[p] * hcd[p * 4 + i] * hcd[p * 4 + j];
-            oHcc[k] = acc;
-        } else {
-            const int k = e - NB * 5 - 16;
-            for (int p = 0; p < cnt; p++) acc += bds[p] * hcd[p * 4 + k];
-            obc[k] = acc;
-        }
+        const int i = k < 16 ? (k >> 2) : (k - 16), j = k < 16 ? (k & 3) : 4;
+        for (int pnt = 0; pnt < SC_CHUNK; pnt++) acc += sZ[pnt * ZS + NB + i] * sZ[pnt * ZS + NB + j];
+        if (k < 16) oHcc[k] = acc; else obc[k - 16] = acc;
     }
 }
 
@@ -553,9 +545,10 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
     double *A = atd + NB;          // [ACC_N]  packed 13x13 block of bin (i -> j)
     double *Y = A + ACC_N;         // [8][8]   sum_k D_jk AH_ik^T
     double *M = Y + 64;            // [8][8]   AH_ij A8
+    double *Apart = M + 64;        // [4][ACC_N] partial sums of A
     for (int e = tid; e < 8 * NB + 40; e += ST_THREADS) {
         int off;
-        if (e < 8 * NB) off = j * 8 * NB + e;
+        if (e < 8 * NB) off = sc_d_index(j * 8 + e / NB, e % NB, NB);      // only the lower tile triangle of D is stored
         else if (e < 8 * NB + 32) off = NB * NB + j * 32 + (e - 8 * NB);
         else off = NB * NB + NB * 4 + j * 8 + (e - 8 * NB - 32);
         const float *src = w.sc_part + (size_t) cb * w.sc_stride + off;
@@ -564,17 +557,20 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
         for (int c = cb; c < ce; c++, src += w.sc_stride) s += (double) __ldg(src);
         Dj[e] = s;                 // Dj, Ej, EBj are contiguous
     }
-    if (tid < ACC_N) {
-        const int bin = j * N + i;
-        const int b0 = w.bin_chunk_begin[bin], b1 = w.bin_chunk_begin[bin + 1];
-        const float *src = w.acc_part[cur] + (size_t) b0 * ACC_N + tid;
+    if (tid < 4 * ACC_N) {         // 13x13 block of bin (i -> j): four threads per entry over contiguous chunk ranges, fixed tree
+        const int bin = j * N + i, e = tid % ACC_N, q = tid / ACC_N;
+        const int b0 = w.bin_chunk_begin[bin], b1 = w.bin_chunk_begin[bin + 1], len = (b1 - b0 + 3) >> 2;
+        const int c0 = min(b0 + q * len, b1), c1 = min(c0 + len, b1);
+        const float *src = w.acc_part[cur] + (size_t) c0 * ACC_N + e;
         double s = 0.0;
 #pragma unroll 8
-        for (int c = b0; c < b1; c++, src += ACC_N) s += (double) __ldg(src);
-        A[tid] = s;
+        for (int c = c0; c < c1; c++, src += ACC_N) s += (double) __ldg(src);
+        Apart[tid] = s;
     }
     for (int e = tid; e < N * 64; e += ST_THREADS) G[e] = w.AH[(size_t) (i * N) * 64 + e];
     for (int e = tid; e < NB; e += ST_THREADS) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
+    __syncthreads();
+    if (tid < ACC_N) A[tid] = (Apart[tid] + Apart[ACC_N + tid]) + (Apart[2 * ACC_N + tid] + Apart[3 * ACC_N + tid]);
     __syncthreads();
     const double *AHj = G + j * 64, *atj = atd + j * 8;
     {
@@ -614,6 +610,16 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
 // Gathers the pair slots into sys = [HA | bA | H_sc | b_sc] (the multi-GPU allreduce payload), one thread per
 // element, fixed summation order.  Both matrices come out completed exactly like the tails of stitchDoubleTop
 // (BA:1857-1876: H[h,t] += H[t,h]^T, calibration rows mirrored) and stitchDoubleSC (BA:2033-2037).
+// sum_k!=a slot(a,k)[o_row] + sum_k!=a slot(k,a)[o_col], all loads issued before the (fixed-order) adds
+__device__ __forceinline__ double sum_slots(const double *st, const int N, const int S, const int a, const int o_row, const int o_col) {
+    double v = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < N; k++) { const double x = st[(size_t) (a * N + (k != a ? k : (a + 1) % N)) * S + o_row]; v += (k != a) ? x : 0.0; }
+#pragma unroll 8
+    for (int k = 0; k < N; k++) { const double x = st[(size_t) ((k != a ? k : (a + 1) % N) * N + a) * S + o_col]; v += (k != a) ? x : 0.0; }
+    return v;
+}
+
 __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
     const int N = w.N, n = w.n, nn = n * n, S = st_stride(N);
@@ -633,18 +639,12 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int
         } else if (c < 4) {                                               // (frame a, C)
             const int a = (r - 4) >> 3, rr = (r - 4) & 7;
             const int o_i = (schur ? ST_S_IC : ST_A_IC) + rr * 4 + c, o_t = (schur ? ST_S_JC : ST_A_TC) + rr * 4 + c;
-            for (int k = 0; k < N; k++) if (k != a) v += SLOT(a, k)[o_i];
-            for (int k = 0; k < N; k++) if (k != a) v += SLOT(k, a)[o_t];
+            v = sum_slots(st, N, S, a, o_i, o_t);
         } else {
             const int a = (r - 4) >> 3, rr = (r - 4) & 7, b = (c - 4) >> 3, cc = (c - 4) & 7;
             if (a == b) {
-                if (!schur) {
-                    for (int k = 0; k < N; k++) if (k != a) v += SLOT(a, k)[ST_A_II + rr * 8 + cc];
-                    for (int k = 0; k < N; k++) if (k != a) v += SLOT(k, a)[ST_A_TT + rr * 8 + cc];
-                } else {
-                    for (int k = 0; k < N; k++) if (k != a) v += SLOT(a, k)[ST_S_II + rr * 8 + cc];
-                    for (int k = 0; k < N; k++) if (k != a) v += SLOT(k, a)[ST_S_JK + a * 64 + rr * 8 + cc];
-                }
+                if (!schur) v = sum_slots(st, N, S, a, ST_A_II + rr * 8 + cc, ST_A_TT + rr * 8 + cc);
+                else v = sum_slots(st, N, S, a, ST_S_II + rr * 8 + cc, ST_S_JK + a * 64 + rr * 8 + cc);
             } else {
                 // the (lo,hi) orientation is summed the same way from both sides: the result is bitwise symmetric
                 const int lo = a < b ? a : b, hi = a < b ? b : a, rl = a < b ? rr : cc, rh = a < b ? cc : rr;   // element (lo rl, hi rh)
@@ -664,8 +664,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int
         } else {
             const int a = (r - 4) >> 3, rr = (r - 4) & 7;
             const int o_i = (schur ? ST_BS_I : ST_BA_I) + rr, o_t = (schur ? ST_BS_J : ST_BA_T) + rr;
-            for (int k = 0; k < N; k++) if (k != a) v += SLOT(a, k)[o_i];
-            for (int k = 0; k < N; k++) if (k != a) v += SLOT(k, a)[o_t];
+            v = sum_slots(st, N, S, a, o_i, o_t);
         }
     }
 #undef SLOT
