@@ -112,6 +112,11 @@ struct IdMap {
         if (keys.empty()) return -1;
         for (size_t i = hash(k) & mask;; i = (i + 1) & mask) { if (keys[i] == k) return vals[i]; if (keys[i] == EMPTY) return -1; }
     }
+    // returns the stored value if k is present, else inserts (k, v) and returns -1
+    int find_or_insert(int64_t k, int v) {
+        if ((n + 1) * 2 > keys.size()) rehash(std::max<size_t>(64, keys.size() * 2));
+        for (size_t i = hash(k) & mask;; i = (i + 1) & mask) { if (keys[i] == k) return vals[i]; if (keys[i] == EMPTY) { keys[i] = k; vals[i] = v; n++; return -1; } }
+    }
     void set(int64_t k, int v) {
         if ((n + 1) * 2 > keys.size()) rehash(std::max<size_t>(64, keys.size() * 2));
         for (size_t i = hash(k) & mask;; i = (i + 1) & mask) { if (keys[i] == k) { vals[i] = v; return; } if (keys[i] == EMPTY) { keys[i] = k; vals[i] = v; n++; return; } }
@@ -154,10 +159,13 @@ struct PointHost {
 // device-order snapshot (ResSnapshot) that cmlba_get_residuals decodes on demand.
 struct ResSnapshot {
     bool valid = false;
+    bool own_map = false;                          // r_point / r_target copied out of the upload arena (done lazily, before the arena is rebuilt)
+    int R = 0;
     std::vector<int64_t> frame_id, point_id;       // frame ids by slot, point ids by device position, at run() time
     std::vector<int> r_point;                      // device point position per residual
-    std::vector<uint8_t> r_target, state, alive;
-    std::vector<float> energy;
+    std::vector<uint8_t> r_target;
+    const uint8_t *state = nullptr, *alive = nullptr;   // into the pinned read-back block of the last finish_run
+    const float *energy = nullptr;
 };
 
 // --- NCCL through dlopen (multi-GPU only) -----------------------------------------------------
@@ -196,7 +204,8 @@ public:
     double fx = 0, fy = 0, cx = 0, cy = 0;
     int W = 0, H = 0;
     std::vector<FrameHost> frames_;
-    std::vector<PointHost> points_;
+    std::vector<PointHost> points_;   // dead points stay in place (alive = false) until a quarter of the slots is dead
+    size_t n_dead = 0;
     ResSnapshot snap;
     IdMap point_index_;
     std::vector<int64_t> outliers_;
@@ -221,6 +230,8 @@ public:
     int stage_flip = 0;
     cudaEvent_t ev_copy = nullptr;
     UploadArena up;                               // every array build_device_window uploads
+    UploadArena prep;                             // per-run constants uploaded by prepare()
+    std::vector<int> res_bin_begin;               // [N*N+1] first device residual of every bin (t*N+h)
     size_t up_o_rp = 0, up_o_rt = 0;              // arena offsets of r_point / r_target (host mirrors stay valid until the next build)
     PinnedBuf<char> pt_stage_h, fin_h; DevBuf<char> pt_stage_d;   // add_points round trip, finish_run read-back
     DevBuf<uint8_t> d_r_host, d_r_target, d_r_state0, d_r_state1, d_r_good0, d_r_good1, d_r_new_state, d_r_alive;
@@ -257,7 +268,7 @@ public:
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_copy) cudaEventDestroy(ev_copy);
-        up.h.release(); up.d.release(); pt_stage_h.release(); fin_h.release(); pt_stage_d.release();
+        up.h.release(); up.d.release(); prep.h.release(); prep.d.release(); pt_stage_h.release(); fin_h.release(); pt_stage_d.release();
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         // DevBuf members leak-free:
         DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_st_out, &d_sys, &d_x, &d_xAd, &d_pt_part};
@@ -349,14 +360,17 @@ public:
         point_index_.reserve(first + n);
         int64_t last_hid = INT64_MIN; int last_h = -1;
         for (int i = 0; i < n; i++) {
-            if (pid[i] == IdMap::EMPTY) { set_error("point id INT64_MIN is reserved"); points_.resize(first); return CMLBA_ERR_ARG; }
-            if (point_index_.find(pid[i]) >= 0) continue;             // BA:386-388
+            if (pid[i] == IdMap::EMPTY) { set_error("point id INT64_MIN is reserved"); points_.resize(first); reindex(); return CMLBA_ERR_ARG; }
+            {   // BA:386-388: a point that is already in the window is skipped (a removed one may come back)
+                const int prev = point_index_.find_or_insert(pid[i], (int) points_.size());
+                if (prev >= 0) { if (points_[prev].alive) continue; point_index_.set(pid[i], (int) points_.size()); }
+            }
             if (host_id[i] != last_hid) { last_hid = host_id[i]; last_h = frame_index(host_id[i]); }
             const int h = last_h;
-            if (h < 0) { set_error("point's host frame is not in the window"); points_.resize(first); return CMLBA_ERR_ARG; }
+            if (h < 0) { set_error("point's host frame is not in the window"); points_.resize(first); reindex(); return CMLBA_ERR_ARG; }
             const float x = xy[2 * i], y = xy[2 * i + 1];
-            if (!(x >= 3 && y >= 3 && x < W - 4 && y < H - 4)) { set_error("point closer than 3 px to the image border"); points_.resize(first); return CMLBA_ERR_ARG; }
-            if (!(idepth[i] > 0) || !std::isfinite(idepth[i])) { set_error("inverse depth must be finite and > 0"); points_.resize(first); return CMLBA_ERR_ARG; }
+            if (!(x >= 3 && y >= 3 && x < W - 4 && y < H - 4)) { set_error("point closer than 3 px to the image border"); points_.resize(first); reindex(); return CMLBA_ERR_ARG; }
+            if (!(idepth[i] > 0) || !std::isfinite(idepth[i])) { set_error("inverse depth must be finite and > 0"); points_.resize(first); reindex(); return CMLBA_ERR_ARG; }
             PointHost p;
             p.id = pid[i]; p.host_id = host_id[i]; p.host = h; p.x = x; p.y = y; p.idepth = idepth[i];
             p.idepth_zero = (float) idepth[i];
@@ -384,7 +398,6 @@ public:
         const uint16_t all = (uint16_t) ((1u << NF) - 1u);
         for (size_t i = 0; i < nn; i++) {
             PointHost &p = points_[first + i];
-            point_index_.set(p.id, (int) (first + i));
             p.res_mask = (uint16_t) (all & ~(1u << p.host));      // createResidual towards every other frame (BA:399-403)
             if (p.host != NF - 1) { p.last_frame[0] = newest; p.last_state[0] = CMLBA_RES_IN; }
             if (NF >= 2 && p.host != NF - 2) { p.last_frame[1] = second; p.last_state[1] = CMLBA_RES_IN; }
@@ -398,21 +411,33 @@ public:
         return CMLBA_OK;
     }
 
-    // drop dead points (and their residuals), rebuild the id index
+    void materialize_snapshot() {
+        if (!snap.valid || snap.own_map) return;
+        const int *rp = up.host<int>(up_o_rp); const uint8_t *rt = up.host<uint8_t>(up_o_rt);
+        snap.r_point.assign(rp, rp + snap.R); snap.r_target.assign(rt, rt + snap.R);
+        snap.own_map = true;
+    }
+    void reindex() {
+        point_index_.clear(); point_index_.reserve(points_.size());
+        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive) point_index_.set(points_[i].id, (int) i);
+    }
+    // squeeze dead points out and rebuild the id index
     void compact() {
         size_t np = 0;
         for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive) { if (np != i) points_[np] = points_[i]; np++; }
         points_.resize(np);
-        point_index_.clear(); point_index_.reserve(np);
-        for (size_t i = 0; i < np; i++) point_index_.set(points_[i].id, (int) i);
+        n_dead = 0;
+        reindex();
         dirty = true; prepared = false;
     }
+    void kill_point(size_t idx) { if (points_[idx].alive) { points_[idx].alive = false; n_dead++; } }
+    void maybe_compact() { if (n_dead * 4 > points_.size()) compact(); dirty = true; prepared = false; }
 
     int remove_point(int64_t id) {
         const int idx = point_index_.find(id);
-        if (idx < 0) return CMLBA_OK;   // DSOContext.h:95-97
-        points_[idx].alive = false;
-        compact();
+        if (idx < 0 || !points_[idx].alive) return CMLBA_OK;   // DSOContext.h:95-97
+        kill_point(idx);
+        maybe_compact();
         return CMLBA_OK;
     }
 
@@ -420,16 +445,18 @@ public:
         const int fi = frame_index(id);
         if (fi < 0) { set_error("unknown frame id"); return CMLBA_ERR_ARG; }
         const uint16_t low = (uint16_t) ((1u << fi) - 1u);
-        for (auto &p : points_) {
-            if (p.host == fi) p.alive = false; else if (p.host > fi) p.host--;
+        for (size_t i = 0; i < points_.size(); i++) {
+            PointHost &p = points_[i];
+            if (!p.alive) continue;
+            if (p.host == fi) kill_point(i); else if (p.host > fi) p.host--;
             p.res_mask = (uint16_t) ((p.res_mask & low) | ((p.res_mask >> (fi + 1)) << fi));   // squeeze slot fi out
-            if (p.res_mask == 0) p.alive = false;     // points left without residuals disappear as well (DSOContext.h:205-216)
+            if (p.res_mask == 0) kill_point(i);       // points left without residuals disappear as well (DSOContext.h:205-216)
         }
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
         if (frames_[fi].d_img) img_pool.push_back(frames_[fi].d_img);
         frames_.erase(frames_.begin() + fi);
-        compact();
+        maybe_compact();
         return CMLBA_OK;
     }
 
@@ -440,15 +467,15 @@ public:
     int build_device_window() {
         TSCOPE("build_device_window");
         Lap lap(timers);
-        const int N = (int) frames_.size(), P = (int) points_.size();
+        const int N = (int) frames_.size(), PA = (int) points_.size(), P = PA - (int) n_dead;
         const int n = 8 * N + 4;
         CK(cudaSetDevice(device));
-        // points: stable counting sort by host
+        // alive points: stable counting sort by host
         std::vector<int> hcnt(N + 1, 0);
-        for (int i = 0; i < P; i++) hcnt[points_[i].host + 1]++;
+        for (int i = 0; i < PA; i++) if (points_[i].alive) hcnt[points_[i].host + 1]++;
         for (int h = 0; h < N; h++) hcnt[h + 1] += hcnt[h];
         pt_order.resize(P);
-        { std::vector<int> o(hcnt.begin(), hcnt.end() - 1); for (int i = 0; i < P; i++) pt_order[o[points_[i].host]++] = i; }
+        { std::vector<int> o(hcnt.begin(), hcnt.end() - 1); for (int i = 0; i < PA; i++) if (points_[i].alive) pt_order[o[points_[i].host]++] = i; }
         // residuals per bin = t*N+h from the per-point masks (device order inside a bin = device point order: no sort)
         std::vector<int> bcnt(N * N + 1, 0);
         std::vector<uint16_t> dmask(P);
@@ -459,6 +486,7 @@ public:
         }
         for (int b = 0; b < N * N; b++) bcnt[b + 1] += bcnt[b];
         const int R = bcnt[N * N];
+        res_bin_begin = bcnt;
         lap("bdw.sort");
         // chunk tables: accumulate chunks per bin, Schur chunks per host
         h_bin_chunk_begin.assign(N * N + 1, 0);
@@ -479,6 +507,8 @@ public:
                      o_rp = up.take<int>(R), o_rh = up.take<uint8_t>(R), o_rt = up.take<uint8_t>(R),
                      o_cb = up.take<int>(n_acc_chunks), o_cbeg = up.take<int>(n_acc_chunks), o_ccnt = up.take<int>(n_acc_chunks), o_bcb = up.take<int>(N * N + 1),
                      o_sh = up.take<int>(n_sc_chunks), o_sbeg = up.take<int>(n_sc_chunks), o_scnt = up.take<int>(n_sc_chunks), o_hcb = up.take<int>(N + 1);
+        CK(cudaStreamSynchronize(stream));          // the previous upload from this pinned block must have landed
+        materialize_snapshot();                     // the residual snapshot of the last run() still points into this block
         CK(up.commit());
         up_o_rp = o_rp; up_o_rt = o_rt;
         {
@@ -514,8 +544,7 @@ public:
         lap("bdw.pack");
         // device-only buffers
         const size_t Rz = std::max(R, 1), Pz = std::max(P, 1);
-        CK(d_frames.reserve(MAXF)); CK(d_pairs.reserve(MAXF * MAXF)); CK(d_ctrl.reserve(1));
-        CK(d_AH.reserve((size_t) N * N * 64)); CK(d_AT.reserve((size_t) N * N * 64)); CK(d_HM.reserve((size_t) n * n)); CK(d_bM.reserve(n)); CK(d_Pns.reserve((size_t) n * n));
+        CK(d_pairs.reserve(MAXF * MAXF));
         CK(d_pt_idb.reserve(Pz));
         CK(d_pt_Hdd.reserve(Pz)); CK(d_pt_bd.reserve(Pz)); CK(d_pt_Hcd.reserve(Pz * 4)); CK(d_pt_HdiF.reserve(Pz)); CK(d_pt_bdSumF.reserve(Pz));
         CK(d_pt_ngood_cur.reserve(Pz)); CK(d_pt_step.reserve(Pz));
@@ -595,7 +624,7 @@ public:
         if (!have_calib) { set_error("calibration not set"); return CMLBA_ERR_STATE; }
         const int N = (int) frames_.size();
         if (N < 1) { set_error("no frames"); return CMLBA_ERR_STATE; }
-        if (points_.empty()) { set_error("No points..."); return CMLBA_ERR_STATE; }   // BA:759-762
+        if (points_.size() == n_dead) { set_error("No points..."); return CMLBA_ERR_STATE; }   // BA:759-762
         CK(cudaSetDevice(device));
         if (dirty) { int rc = build_device_window(); if (rc) return rc; }
         const int n = 8 * N + 4;
@@ -689,30 +718,27 @@ public:
         for (double v : bM) if (v != 0.0) { dw.has_HM = 1; break; }
         Ctrl c; memset(&c, 0, sizeof(c));
         c.lambda = (double) cfg.fixed_lambda;
-        const int R = dw.R, P = dw.P;
         lap("prep.host_math");
-        CK(cudaMemcpyAsync(d_frames.p, fd.data(), N * sizeof(FrameDev), cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_AH.p, AH.data(), AH.size() * 8, cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_AT.p, AT.data(), AT.size() * 8, cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_Pns.p, Pns.data(), Pns.size() * 8, cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_HM.p, HM.data(), HM.size() * 8, cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_bM.p, bM.data(), bM.size() * 8, cudaMemcpyHostToDevice, stream));
-        CK(cudaMemcpyAsync(d_ctrl.p, &c, sizeof(c), cudaMemcpyHostToDevice, stream));
-        // resetOOB on every active residual (BA:766-779, DSOResidual.h:81-86)
-        if (R > 0) {
-            CK(cudaMemsetAsync(d_r_state0.p, RES_IN, R, stream)); CK(cudaMemsetAsync(d_r_state1.p, RES_IN, R, stream));
-            CK(cudaMemsetAsync(d_r_energy0.p, 0, R * 4, stream)); CK(cudaMemsetAsync(d_r_energy1.p, 0, R * 4, stream));
-            CK(cudaMemsetAsync(d_r_good0.p, 0, R, stream)); CK(cudaMemsetAsync(d_r_good1.p, 0, R, stream));
-            CK(cudaMemsetAsync(d_r_new_state.p, RES_OUTLIER, R, stream)); CK(cudaMemsetAsync(d_r_new_energy.p, 0, R * 4, stream));
-            CK(cudaMemsetAsync(d_r_new_energy_wo.p, 0, R * 4, stream)); CK(cudaMemsetAsync(d_r_alive.p, 1, R, stream));
-            CK(cudaMemsetAsync(d_r_center.p, 0, (size_t) R * 12, stream));
-        }
-        CK(cudaMemsetAsync(d_T0.p, 0, (size_t) P * N * T_STRIDE * 4, stream)); CK(cudaMemsetAsync(d_T1.p, 0, (size_t) P * N * T_STRIDE * 4, stream));
-        CK(cudaMemsetAsync(d_pt_ngood_cur.p, 0, (size_t) P * 4, stream));
-        if (want_dbg && R > 0) CK(cudaMemsetAsync(d_dbg.p, 0, (size_t) R * DBG_STRIDE * 4, stream));
+        // one pinned block mirrored on the device: frames | AH | AT | Pns | ctrl | (HM | bM when there is a prior)
+        prep.begin();
+        const size_t o_fr = prep.take<FrameDev>(MAXF), o_ah = prep.take<double>(AH.size()), o_at = prep.take<double>(AT.size()), o_pns = prep.take<double>(Pns.size()),
+                     o_ctrl = prep.take<Ctrl>(1), o_hm = prep.take<double>(dw.has_HM ? HM.size() : 1), o_bm = prep.take<double>(dw.has_HM ? bM.size() : 1);
+        CK(cudaStreamSynchronize(stream));          // the previous upload from this pinned block must have landed
+        CK(prep.commit());
+        memcpy(prep.host<FrameDev>(o_fr), fd.data(), N * sizeof(FrameDev));
+        memcpy(prep.host<double>(o_ah), AH.data(), AH.size() * 8); memcpy(prep.host<double>(o_at), AT.data(), AT.size() * 8);
+        memcpy(prep.host<double>(o_pns), Pns.data(), Pns.size() * 8); memcpy(prep.host<Ctrl>(o_ctrl), &c, sizeof(c));
+        if (dw.has_HM) { memcpy(prep.host<double>(o_hm), HM.data(), HM.size() * 8); memcpy(prep.host<double>(o_bm), bM.data(), bM.size() * 8); }
+        CK(cudaMemcpyAsync(prep.d.p, prep.h.p, prep.used, cudaMemcpyHostToDevice, stream));
+#define PVIEW(buf, T, off) do { (buf).release(); (buf).p = prep.dev<T>(off); (buf).view = true; } while (0)
+        PVIEW(d_frames, FrameDev, o_fr); PVIEW(d_AH, double, o_ah); PVIEW(d_AT, double, o_at); PVIEW(d_Pns, double, o_pns); PVIEW(d_ctrl, Ctrl, o_ctrl);
+        PVIEW(d_HM, double, o_hm); PVIEW(d_bM, double, o_bm);
+#undef PVIEW
+        dw.frames = d_frames.p; dw.AH = d_AH.p; dw.AT = d_AT.p; dw.Pns = d_Pns.p; dw.ctrl = d_ctrl.p; dw.HM = d_HM.p; dw.bM = d_bM.p;
+        // resetOOB on every active residual (BA:766-779, DSOResidual.h:81-86), empty Schur tables
+        reset_window_kernel<<<148 * 4, 256, 0, stream>>>(dw); launches++;
         pairs_kernel<<<(N * N + 63) / 64, 64, 0, stream>>>(dw); launches++;
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(stream));   // host vectors above are pageable stack/heap objects
         lap("prep.upload_reset");
         prepared = true;
         return CMLBA_OK;
@@ -720,7 +746,7 @@ public:
 
     // ------------------------------------------------------------------ kernel sequences
     size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128 + 4 * ACC_N); }
-    size_t solve_smem() const { const int n = dw.n; return sizeof(double) * ((size_t) n * n + 3 * n + 256); }
+    size_t solve_smem() const { const int n = dw.n; return sizeof(double) * ((size_t) n * n + 4 * n + 256); }
     size_t schur_smem() const { return schur_smem_bytes(dw.N); }
 
     void launch_linearize(int fix, int respect_done) {
@@ -737,7 +763,7 @@ public:
     void launch_stitch(int respect_done) {
         const int N = dw.N, n = dw.n;
         stitch_pair_kernel<<<N * N, ST_THREADS, stitch_smem(), stream>>>(dw, respect_done); launches++;
-        assemble_kernel<<<(2 * n * n + 2 * n + 255) / 256, 256, 0, stream>>>(dw, respect_done); launches++;
+        assemble_kernel<<<(2 * n * n + 2 * n + 255) / 256 + 3, 256, 0, stream>>>(dw, respect_done); launches++;   // +3 CTAs: 20 warps for HA[C,C], bA[C]
     }
     int launch_solve_sequence(int respect_done) {
         launch_schur(respect_done);
@@ -831,35 +857,47 @@ public:
             f.energy_th = d.energy_th;
             f.aff_a = d.state_scaled[6]; f.aff_b = d.state_scaled[7];
         }
-        for (int i = 0; i < P; i++) {
-            PointHost &p = points_[pt_order[i]];
-            p.idepth = id[i]; p.idepth_zero = idz[i]; p.idepth_hessian = idh[i]; p.max_rel_bs = mrb[i]; p.num_good = ng[i];
-        }
-        // residuals (device order): dropped ones leave the masks; lastResiduals bookkeeping (BA:1616-1620, 1630-1633)
+        // residuals (device order).  Dropped ones leave the masks; lastResiduals bookkeeping (BA:1616-1620, 1630-1633) only
+        // concerns residuals towards the two newest frames (the only ids PointHost::last_frame can hold).
         const int *r_point = up.host<int>(up_o_rp); const uint8_t *r_target = up.host<uint8_t>(up_o_rt);
         int dropped = 0;
-        for (int i = 0; i < R; i++) {
-            PointHost &p = points_[pt_order[r_point[i]]];
-            const int t = r_target[i];
-            const int64_t tid = frames_[t].id;
-            for (int s2 = 0; s2 < 2; s2++) if (p.last_frame[s2] == tid) { if (alive[i]) p.last_state[s2] = st[i]; else p.last_frame[s2] = -1; break; }
-            if (!alive[i]) { p.res_mask &= (uint16_t) ~(1u << t); dropped++; }
+        {
+            int i = 0;
+            for (; i + 8 <= R; i += 8) {            // alive[] is almost all ones: test 8 flags at a time
+                uint64_t wd; memcpy(&wd, alive + i, 8);
+                if (wd == 0x0101010101010101ull) continue;
+                for (int k = i; k < i + 8; k++) if (!alive[k]) { points_[pt_order[r_point[k]]].res_mask &= (uint16_t) ~(1u << r_target[k]); dropped++; }
+            }
+            for (; i < R; i++) if (!alive[i]) { points_[pt_order[r_point[i]]].res_mask &= (uint16_t) ~(1u << r_target[i]); dropped++; }
         }
-        // snapshot for cmlba_get_residuals (plain copies of the device-order arrays)
-        snap.valid = true;
+        for (int t = std::max(0, N - 2); t < N; t++) {
+            const int64_t tid = frames_[t].id;
+            for (int i = res_bin_begin[t * N]; i < res_bin_begin[(t + 1) * N]; i++) {
+                PointHost &p = points_[pt_order[r_point[i]]];
+                for (int s2 = 0; s2 < 2; s2++) if (p.last_frame[s2] == tid) { if (alive[i]) p.last_state[s2] = st[i]; else p.last_frame[s2] = -1; break; }
+            }
+        }
+        // points: results, outliers (points left without residuals, BA:1636-1640) and the id list of the residual snapshot
+        snap.valid = true; snap.own_map = false; snap.R = R;
+        snap.state = st; snap.alive = alive; snap.energy = en;
         snap.frame_id.resize(N); for (int i = 0; i < N; i++) snap.frame_id[i] = frames_[i].id;
-        snap.point_id.resize(P); for (int i = 0; i < P; i++) snap.point_id[i] = points_[pt_order[i]].id;
-        snap.r_point.assign(r_point, r_point + R); snap.r_target.assign(r_target, r_target + R);
-        snap.state.assign(st, st + R); snap.alive.assign(alive, alive + R); snap.energy.assign(en, en + R);
+        snap.point_id.resize(P);
         outliers_.clear();
         int nout = 0;
-        for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive && points_[i].res_mask == 0) { points_[i].alive = false; outliers_.push_back(points_[i].id); nout++; }
+        for (int i = 0; i < P; i++) {
+            const int q = pt_order[i];
+            PointHost &p = points_[q];
+            p.idepth = id[i]; p.idepth_zero = idz[i]; p.idepth_hessian = idh[i]; p.max_rel_bs = mrb[i]; p.num_good = ng[i];
+            snap.point_id[i] = p.id;
+            if (p.res_mask == 0) { kill_point(q); outliers_.push_back(p.id); nout++; }
+        }
         if (out) {
             out->iterations_done = c.iteration; out->num_residuals = R; out->num_dropped = dropped; out->num_outliers = nout;
             out->energy_first = c.energy_first; out->energy_last = c.energy_last;
         }
         flap("finish.scatter");
-        if (nout > 0) compact(); else dirty = dropped > 0;
+        dirty = dropped > 0 || nout > 0;
+        if (n_dead * 4 > points_.size()) compact();
         flap("finish.compact");
         prepared = false;
         if (c.failed) { set_error("non-finite energy or step (reference run() returns false)"); return CMLBA_ERR_NUMERIC; }
@@ -870,7 +908,7 @@ public:
     int reset() {
         cudaSetDevice(device);
         for (auto &f : frames_) if (f.d_img) { img_pool.push_back(f.d_img); f.d_img = nullptr; }
-        frames_.clear(); points_.clear(); snap.valid = false; point_index_.clear(); outliers_.clear();
+        frames_.clear(); points_.clear(); n_dead = 0; snap.valid = false; point_index_.clear(); outliers_.clear();
         key_counter = 0; dirty = true; prepared = false;
         return CMLBA_OK;
     }
@@ -999,8 +1037,6 @@ public:
             if (n_sc_chunks) CK(cudaMemcpy(part.data(), d_sc_part.p, part.size() * 4, cudaMemcpyDeviceToHost));
             std::vector<double> s((size_t) N * tot, 0.0);
             for (int h = 0; h < N; h++) for (int ch = h_host_chunk_begin[h]; ch < h_host_chunk_begin[h + 1]; ch++) for (int k = 0; k < tot; k++) s[(size_t) h * tot + k] += part[(size_t) ch * dw.sc_stride + k];
-            // schur_kernel stores only the 4x4 tiles on or below the diagonal of D: mirror them
-            for (int h = 0; h < N; h++) for (int r = 0; r < NB; r++) for (int cc = 0; cc < NB; cc++) if ((r >> 2) < (cc >> 2)) s[(size_t) h * tot + r * NB + cc] = s[(size_t) h * tot + cc * NB + r];
             return host_out(s.data(), s.size() * 8, dst, cap, bytes);
         }
         set_error("unknown buffer name: " + name);
@@ -1055,7 +1091,7 @@ int cmlba_remove_point(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove
 int cmlba_remove_frame(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove_frame(id); }
 int cmlba_run(cmlba_handle *h, const double *cams, int iterations, int upo, cmlba_run_result *r) { HCHK; return h->eng.run(cams, iterations, upo, r); }
 int cmlba_num_frames(const cmlba_handle *h) { return h ? (int) h->eng.frames_.size() : CMLBA_ERR_ARG; }
-int cmlba_num_points(const cmlba_handle *h) { return h ? (int) h->eng.points_.size() : CMLBA_ERR_ARG; }
+int cmlba_num_points(const cmlba_handle *h) { return h ? (int) (h->eng.points_.size() - h->eng.n_dead) : CMLBA_ERR_ARG; }
 int cmlba_num_residuals(const cmlba_handle *h) {
     if (!h) return CMLBA_ERR_ARG;
     int n = 0;
@@ -1080,8 +1116,10 @@ int cmlba_get_frames(const cmlba_handle *h, int64_t *id, double *w2c, double *ab
 int cmlba_get_points(const cmlba_handle *h, int64_t *id, double *idepth, double *unc, float *idh, float *mrb, int32_t *ng, int32_t *gft) {
     HCHK;
     const auto &pts = h->eng.points_;
-    for (size_t i = 0; i < pts.size(); i++) {
-        const auto &p = pts[i];
+    size_t i = 0;
+    for (size_t q = 0; q < pts.size(); q++) {
+        const auto &p = pts[q];
+        if (!p.alive) continue;
         if (id) id[i] = p.id;
         if (idepth) idepth[i] = p.idepth;
         if (unc) unc[i] = 1.0 / ((double) p.idepth_hessian + 0.01);    // updatePointUncertainty (DSOPoint.h:107-118)
@@ -1089,6 +1127,7 @@ int cmlba_get_points(const cmlba_handle *h, int64_t *id, double *idepth, double 
         if (mrb) mrb[i] = p.max_rel_bs;
         if (ng) ng[i] = p.num_good;
         if (gft) gft[i] = (p.last_frame[0] >= 0 && p.last_state[0] == CMLBA_RES_IN) ? 1 : 0;   // getGoodPointsForTracking (BA.h:76-85)
+        i++;
     }
     return CMLBA_OK;
 }
@@ -1107,7 +1146,11 @@ int cmlba_get_residuals(const cmlba_handle *h, int64_t *pid, int64_t *tid, int32
     const Engine &e = h->eng;
     // (point id, frame id) -> device residual index of the last run(), decoded from the snapshot on demand (O(R))
     std::unordered_map<int64_t, std::unordered_map<int64_t, int>> last;
-    if (e.snap.valid) for (size_t i = 0; i < e.snap.r_point.size(); i++) if (e.snap.alive[i]) last[e.snap.point_id[e.snap.r_point[i]]][e.snap.frame_id[e.snap.r_target[i]]] = (int) i;
+    if (e.snap.valid) {
+        const int *rp = e.snap.own_map ? e.snap.r_point.data() : reinterpret_cast<const int *>(e.up.h.p + e.up_o_rp);
+        const uint8_t *rt = e.snap.own_map ? e.snap.r_target.data() : reinterpret_cast<const uint8_t *>(e.up.h.p + e.up_o_rt);
+        for (int i = 0; i < e.snap.R; i++) if (e.snap.alive[i]) last[e.snap.point_id[rp[i]]][e.snap.frame_id[rt[i]]] = i;
+    }
     size_t k = 0;
     for (auto &p : e.points_) {
         if (!p.alive) continue;

@@ -385,11 +385,9 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
 // symmetric rank update of the augmented per-point vector z = s * [ JpJdF over all targets (8N) | Hcd (4) | bdSum ]:
 //   D = sum z_u z_u^T   E = sum z_u z_c^T   EB = sum z_u z_b   Hcc = sum z_c z_c^T   bc = sum z_c z_b
 // (the N^3 8x8 accumulators of BA:1040 per host are the (8N)^2 matrix D).  4x4 register tiles, 2 LDS.128 per 16 FMA;
-// only tiles on or below the diagonal of D are computed and stored (sc_tile_index reads the mirror image).
+// only tiles on or below the diagonal of D are computed; each is stored together with its mirror image.
 constexpr int SCZ_PAD = 8;     // z_c (4) z_b (1) pad (3)
 __host__ __device__ __forceinline__ size_t schur_smem_bytes(int N) { return sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * (8 * N + SCZ_PAD)); }
-// element (row, col) of the stored D: lower 4x4-tile triangle only
-__device__ __forceinline__ int sc_d_index(int row, int col, int NB) { return ((row >> 2) >= (col >> 2)) ? row * NB + col : col * NB + row; }
 
 __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
@@ -480,6 +478,10 @@ __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int re
         if (tc < ntr) {
 #pragma unroll
             for (int i = 0; i < 4; i++) *reinterpret_cast<float4 *>(out + (size_t) (tr * 4 + i) * NB + tc * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (tc < tr) {   // mirror image, so that readers stream whole rows
+#pragma unroll
+                for (int j = 0; j < 4; j++) *reinterpret_cast<float4 *>(out + (size_t) (tc * 4 + j) * NB + tr * 4) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+            }
         } else if (tc == ntr) {
 #pragma unroll
             for (int i = 0; i < 4; i++) *reinterpret_cast<float4 *>(oE + (tr * 4 + i) * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
     double *Apart = M + 64;        // [4][ACC_N] partial sums of A
     for (int e = tid; e < 8 * NB + 40; e += ST_THREADS) {
         int off;
-        if (e < 8 * NB) off = sc_d_index(j * 8 + e / NB, e % NB, NB);      // only the lower tile triangle of D is stored
+        if (e < 8 * NB) off = j * 8 * NB + e;
         else if (e < 8 * NB + 32) off = NB * NB + j * 32 + (e - 8 * NB);
         else off = NB * NB + NB * 4 + j * 8 + (e - 8 * NB - 32);
         const float *src = w.sc_part + (size_t) cb * w.sc_stride + off;
@@ -623,10 +625,22 @@ __device__ __forceinline__ double sum_slots(const double *st, const int N, const
 __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
     const int N = w.N, n = w.n, nn = n * n, S = st_stride(N);
-    const int e = blockIdx.x * 256 + threadIdx.x;
-    if (e >= 2 * nn + 2 * n) return;
     const double *st = w.st_out;
 #define SLOT(i, j) (st + (size_t) ((i) * N + (j)) * S)
+    const int nelem = 2 * nn + 2 * n;
+    if ((int) blockIdx.x * 256 >= nelem) {
+        // calibration block of the active part: HA[C,C] (16) and bA[C] (4) sum over all N(N-1) pairs -> one warp per entry
+        const int k = ((int) blockIdx.x * 256 - ((nelem + 255) / 256) * 256 + (int) threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        if (k >= 20) return;
+        const int off = k < 16 ? ST_A_CC + k : ST_BA_C + (k - 16);
+        double v = 0.0;
+        for (int q = lane; q < N * N; q += 32) { const int i = q / N, j = q - i * N; const double x = SLOT(i, i != j ? j : (i + 1) % N)[off]; v += (i != j) ? x : 0.0; }
+        v = warp_sum_d(v);
+        if (lane == 0) w.sys[k < 16 ? (k >> 2) * n + (k & 3) : nn + (k - 16)] = v;
+        return;
+    }
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= nelem) return;
     const bool schur = e >= nn + n;
     const int q = schur ? e - nn - n : e;
     double v = 0.0;
@@ -634,8 +648,8 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int
         int r = q / n, c = q - r * n;
         if (r < 4 && c >= 4) { const int t = r; r = c; c = t; }          // calibration rows mirror the columns
         if (r < 4) {                                                      // (C,C)
-            if (!schur) { for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) if (i != j) v += SLOT(i, j)[ST_A_CC + r * 4 + c]; }
-            else for (int i = 0; i < N; i++) v += SLOT(i, i)[r * 4 + c];
+            if (!schur) return;                                           // written by the warp-per-entry blocks above
+            for (int i = 0; i < N; i++) v += SLOT(i, i)[r * 4 + c];
         } else if (c < 4) {                                               // (frame a, C)
             const int a = (r - 4) >> 3, rr = (r - 4) & 7;
             const int o_i = (schur ? ST_S_IC : ST_A_IC) + rr * 4 + c, o_t = (schur ? ST_S_JC : ST_A_TC) + rr * 4 + c;
@@ -650,17 +664,19 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int
                 const int lo = a < b ? a : b, hi = a < b ? b : a, rl = a < b ? rr : cc, rh = a < b ? cc : rr;   // element (lo rl, hi rh)
                 if (!schur) v = SLOT(lo, hi)[ST_A_IT + rl * 8 + rh] + SLOT(hi, lo)[ST_A_IT + rh * 8 + rl];
                 else {
-                    for (int k = 0; k < N; k++) if (k != lo && k != hi) v += SLOT(k, lo)[ST_S_JK + hi * 64 + rl * 8 + rh];
-                    v += SLOT(hi, lo)[ST_S_JI + rl * 8 + rh];
-                    v += SLOT(lo, hi)[ST_S_JI + rh * 8 + rl];
+                    const double x1 = SLOT(hi, lo)[ST_S_JI + rl * 8 + rh], x2 = SLOT(lo, hi)[ST_S_JI + rh * 8 + rl];
+#pragma unroll 8
+                    for (int k = 0; k < N; k++) { const bool use = k != lo && k != hi; const double x = SLOT(use ? k : hi, lo)[ST_S_JK + hi * 64 + rl * 8 + rh]; v += use ? x : 0.0; }
+                    v += x1;
+                    v += x2;
                 }
             }
         }
     } else {
         const int r = q - nn;
         if (r < 4) {
-            if (!schur) { for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) if (i != j) v += SLOT(i, j)[ST_BA_C + r]; }
-            else for (int i = 0; i < N; i++) v += SLOT(i, i)[16 + r];
+            if (!schur) return;
+            for (int i = 0; i < N; i++) v += SLOT(i, i)[16 + r];
         } else {
             const int a = (r - 4) >> 3, rr = (r - 4) & 7;
             const int o_i = (schur ? ST_BS_I : ST_BA_I) + rr, o_t = (schur ? ST_BS_J : ST_BA_T) + rr;
@@ -684,6 +700,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
     double *s = b + n;          // [n]
     double *x = s + n;          // [n]
     double *red = x + n;        // [256]
+    double *invd = red + 256;   // [m] reciprocals of the LDL^T pivots
     double *sysHA = w.sys, *sysbA = w.sys + nn, *sysHS = w.sys + nn + n, *sysbS = w.sys + 2 * nn + n;
     // H <- HA (already completed by assemble_kernel)
     for (int e = tid; e < nn; e += 256) H[e] = sysHA[e];
@@ -738,7 +755,9 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const double dk = __shfl_sync(0xffffffffu, a[k], k);
-                const double lrk = a[k] / dk;
+                const double idk = 1.0 / dk;                       // one reciprocal per pivot; rows are scaled by multiplication
+                if (lane == k) invd[k0 + k] = idk;
+                const double lrk = a[k] * idk;
                 if (lane > k) a[k] = lrk;
 #pragma unroll
                 for (int c = k + 1; c < 8; c++) {
@@ -759,7 +778,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
                 double v = AA(r, k0 + c);
 #pragma unroll
                 for (int jj = 0; jj < c; jj++) v -= l[jj] * AA(k0 + jj, k0 + jj) * AA(k0 + c, k0 + jj);
-                l[c] = v / AA(k0 + c, k0 + c);
+                l[c] = v * invd[k0 + c];
             }
 #pragma unroll
             for (int c = 0; c < 8; c++) AA(r, k0 + c) = l[c];
@@ -811,7 +830,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
         }
         __syncthreads();
     }
-    for (int e = tid; e < m; e += 256) x[e] = x[e] / AA(e, e);
+    for (int e = tid; e < m; e += 256) x[e] = x[e] * invd[e];
     __syncthreads();
     for (int k0 = m - 8; k0 >= 0; k0 -= 8) {
         {   // warp c: x[k0+c] -= sum_{r >= k0+8} L[r][k0+c] x[r]
@@ -894,6 +913,9 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     const int N = w.N, cur = ctrl->cur;
+    __shared__ double s_xad[MAXF * MAXF * 8];
+    for (int e = threadIdx.x; e < N * N * 8; e += 256) s_xad[e] = w.xAd[e];
+    __syncthreads();
     const int p = blockIdx.x * 256 + threadIdx.x;
     double nid = 0.0; int cntid = 0; int bad = 0;
     if (p < w.P) {
@@ -902,12 +924,12 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
             const int h = w.pt_host[p];
             double bb = (double) w.pt_bdSumF[p];
             for (int c = 0; c < 4; c++) bb -= (-w.x[c]) * (double) w.pt_Hcd[p * 4 + c];
-            const float *row = w.T[cur] + (size_t) p * N * T_STRIDE;
+            const float4 *row = reinterpret_cast<const float4 *>(w.T[cur] + (size_t) p * N * T_STRIDE);
+            const double *xa = s_xad + (size_t) h * N * 8;
+#pragma unroll 4
             for (int t = 0; t < N; t++) {
-                const float4 a = __ldg(reinterpret_cast<const float4 *>(row + t * T_STRIDE));
-                const float4 c = __ldg(reinterpret_cast<const float4 *>(row + t * T_STRIDE) + 1);
-                const double *xa = w.xAd + (size_t) (h * N + t) * 8;
-                bb -= xa[0] * a.x + xa[1] * a.y + xa[2] * a.z + xa[3] * a.w + xa[4] * c.x + xa[5] * c.y + xa[6] * c.z + xa[7] * c.w;
+                const float4 a = __ldg(row + t * (T_STRIDE / 4)), c = __ldg(row + t * (T_STRIDE / 4) + 1);
+                bb -= xa[t * 8 + 0] * a.x + xa[t * 8 + 1] * a.y + xa[t * 8 + 2] * a.z + xa[t * 8 + 3] * a.w + xa[t * 8 + 4] * c.x + xa[t * 8 + 5] * c.y + xa[t * 8 + 6] * c.z + xa[t * 8 + 7] * c.w;
             }
             step = -bb * (double) w.pt_HdiF[p];
             if (!isfinite(step)) bad = 1;
@@ -939,10 +961,12 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
         s_last = (ticket == (int) gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last && threadIdx.x < 32) {
         __threadfence();
         double tn = 0, tc = 0, tb = 0;
-        for (int k = 0; k < (int) gridDim.x; k++) { tn += w.pt_part[k * 3]; tc += w.pt_part[k * 3 + 1]; tb += w.pt_part[k * 3 + 2]; }
+        for (int k = threadIdx.x; k < (int) gridDim.x; k += 32) { tn += w.pt_part[k * 3]; tc += w.pt_part[k * 3 + 1]; tb += w.pt_part[k * 3 + 2]; }
+        tn = warp_sum_d(tn); tc = warp_sum_d(tc); tb = warp_sum_d(tb);
+    if (threadIdx.x == 0) {
         const float sumNID = (float) (tn / (tc > 0 ? tc : 1.0));
         ctrl->sumNID = tn; ctrl->numID = (int) tc;
         const float th = w.th_opt;
@@ -950,6 +974,7 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
                           sqrtf(ctrl->sumT) * sumNID < 0.00005f * th) ? 1 : 0;
         if (tb > 0) { ctrl->failed = 1; ctrl->done = 1; }            // BA:1489-1492
         ctrl->sc_done_count = 0;
+    }
     }
 }
 
@@ -971,12 +996,25 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
     if ((tid & 31) == 0) s_red[tid >> 5] = e;
     __syncthreads();
     if (tid == 0) { double t = 0; for (int k = 0; k < 32; k++) t += s_red[k]; s_red[0] = t; }
-    // count candidates (energies >= 0 of residuals whose target is the newest frame)
+    // candidates: energies >= 0 of alive residuals whose target is the newest frame.  Each thread keeps up to PL_CACHE of
+    // them in registers (one exposed load latency for the count + the four radix passes); longer tails are re-read.
+    constexpr int PL_CACHE = 16;
     if (tid == 0) s_n = 0;
     __syncthreads();
     const double energy = s_red[0];
+    float cache[PL_CACHE];
     unsigned int cnt = 0;
-    for (int i = w.newest_begin + tid; i < w.R; i += 1024) cnt += (w.r_alive[i] && w.r_new_energy_wo[i] >= 0.f) ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < PL_CACHE; k++) {
+        const int i = w.newest_begin + tid + k * 1024;
+        const bool in = i < w.R;
+        const uint8_t al = in ? w.r_alive[i] : (uint8_t) 0;
+        const float v = in ? w.r_new_energy_wo[i] : -1.f;
+        cache[k] = al ? v : -1.f;
+    }
+#pragma unroll
+    for (int k = 0; k < PL_CACHE; k++) cnt += cache[k] >= 0.f ? 1u : 0u;
+    for (int i = w.newest_begin + tid + PL_CACHE * 1024; i < w.R; i += 1024) cnt += (w.r_alive[i] && w.r_new_energy_wo[i] >= 0.f) ? 1u : 0u;
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
     if ((tid & 31) == 0 && cnt) atomicAdd(&s_n, cnt);
     __syncthreads();
@@ -993,7 +1031,12 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
             __syncthreads();
             const unsigned int prefix = s_prefix;
             const unsigned int mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-            for (int i = w.newest_begin + tid; i < w.R; i += 1024) {
+#pragma unroll
+            for (int k = 0; k < PL_CACHE; k++) {
+                const unsigned int u = __float_as_uint(cache[k]);
+                if (cache[k] >= 0.f && (u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+            }
+            for (int i = w.newest_begin + tid + PL_CACHE * 1024; i < w.R; i += 1024) {
                 const float v = w.r_new_energy_wo[i];
                 if (w.r_alive[i] && v >= 0.f) {
                     const unsigned int u = __float_as_uint(v);
@@ -1001,11 +1044,23 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                unsigned int k = s_k, acc = 0; int d = 0;
-                for (; d < 256; d++) { if (acc + hist[d] > k) break; acc += hist[d]; }
-                s_k = k - acc;
-                s_prefix = prefix | ((unsigned int) d << shift);
+            if (tid < 32) {      // digit d with acc(d) <= k < acc(d) + hist[d]: warp scan over 8 digits per lane
+                unsigned int loc[8], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) { loc[q] = hist[tid * 8 + q]; sum += loc[q]; }
+                unsigned int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += y; }
+                unsigned int acc = incl - sum;
+                const unsigned int k = s_k;
+                __syncwarp();
+                if (k >= acc && k < incl) {
+                    int d = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { if (k >= acc + loc[q]) { acc += loc[q]; d = q + 1; } else break; }
+                    s_k = k - acc;
+                    s_prefix = prefix | ((unsigned int) (tid * 8 + d) << shift);
+                }
             }
             __syncthreads();
         }
@@ -1050,6 +1105,22 @@ __global__ void point_init_kernel(const DevWin w, const int p_begin, const int p
     const float gy = a.z * w00 + b.z * w10 + c.z * w01 + d.z * w11;
     const double g2 = (double) gx * (double) gx + (double) gy * (double) gy;
     weights[(size_t) p * 8 + k] = (float) sqrt((double) w.cth / ((double) w.cth + g2));
+}
+
+// run() prologue on the device: resetOOB on every residual (BA:766-779, DSOResidual.h:81-86), empty Schur tables
+__global__ void __launch_bounds__(256) reset_window_kernel(const DevWin w) {
+    const size_t tid = blockIdx.x * (size_t) blockDim.x + threadIdx.x, nth = (size_t) gridDim.x * blockDim.x;
+    const size_t nT4 = (size_t) w.P * w.N * (T_STRIDE / 4);
+    float4 *T0 = reinterpret_cast<float4 *>(w.T[0]), *T1 = reinterpret_cast<float4 *>(w.T[1]);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = tid; i < nT4; i += nth) { T0[i] = z; T1[i] = z; }
+    for (size_t i = tid; i < (size_t) w.R; i += nth) {
+        w.r_state[0][i] = RES_IN; w.r_state[1][i] = RES_IN; w.r_energy[0][i] = 0.f; w.r_energy[1][i] = 0.f; w.r_good[0][i] = 0; w.r_good[1][i] = 0;
+        w.r_new_state[i] = RES_OUTLIER; w.r_new_energy[i] = 0.f; w.r_new_energy_wo[i] = 0.f; w.r_alive[i] = 1;
+        w.r_center[3 * i] = 0.f; w.r_center[3 * i + 1] = 0.f; w.r_center[3 * i + 2] = 0.f;
+    }
+    for (size_t i = tid; i < (size_t) w.P; i += nth) w.pt_ngood_cur[i] = 0;
+    if (w.dbg) for (size_t i = tid; i < (size_t) w.R * DBG_STRIDE; i += nth) w.dbg[i] = 0.f;
 }
 
 // AoS (I,dx,dy) 12-byte texels -> float4 texels (one aligned 128-bit load per bilinear tap)
