@@ -62,7 +62,9 @@ typedef struct cmlba_config {
     int optimize_light_a;       /* "optimizeLightA" true */
     int optimize_light_b;       /* "optimizeLightB" true */
     int disable_marginalization;/* "disableMarginalization" true */
-    int max_frames;             /* "maxFrames" 6 (only bounds checking here) */
+    int max_frames;             /* "maxFrames" 6: flagFramesForMarginalization keeps at most this many frames (BA:649) */
+    int frame_min_age;          /* "frameMinAge" 1 (BA:658-680) */
+    float min_idepth_h_marg;    /* "Minimum iDepth Hessian Marginlaization" 50 (BA:2318) */
 } cmlba_config;
 
 /* Fills *cfg with the reference defaults. */
@@ -96,6 +98,29 @@ int cmlba_add_points(cmlba_handle *h, int n, const int64_t *point_id, const int6
 /* DSOContext::removePoint / frame removal without marginalisation prior (DSOContext.h:94-110, 152-172). */
 int cmlba_remove_point(cmlba_handle *h, int64_t point_id);
 int cmlba_remove_frame(cmlba_handle *h, int64_t frame_id);
+
+/* ---- window maintenance around run() (Hybrid::directMap, slam/modslam/direct/Mapping.cpp:61-100) ----
+ * The decisions (which frames / points leave the window, the per-frame counters they depend on) follow the reference
+ * exactly.  The marginalisation PRIOR H_M,b_M that marginalizePointsF / marginalizeFrame fold the leaving variables into
+ * (BA:2500-2508, 520-548) is not accumulated: with the default disableMarginalization=true the reference zeroes it
+ * before every solve (BA:1395-1398), so it never reaches a result.  cmlba_create fails with CMLBA_ERR_UNSUPPORTED when
+ * disable_marginalization == 0.
+ *
+ * cmlba_flag_frames_for_marginalization   flagFramesForMarginalization (BA:603-708).  The reference runs it at the top of
+ *      addNewFrame (BA:428), i.e. call it BEFORE cmlba_add_frame of the new keyframe.  cams = current Frame::getCamera()
+ *      of the window frames (NULL: last optimised poses); num_immature[i] = frame->getReferenceGroupMapPoints(immature)
+ *      .size() (NULL: zeros).  flagged_ids (capacity *n_flagged in, count out) lists every frame flagged so far.
+ * cmlba_try_marginalize     tryMarginalize (BA:2240-2363) + isOOB (BA:2515-2554): points to drop go to getOutliers()
+ *      and leave the window; points to marginalise are marked (DSOTOMARGINALIZE).
+ * cmlba_marginalize_points  marginalizePointsF (BA:2466-2513): marked points leave the window as marginalised
+ *      (numMarginalized / numResidualsOut counters of DSOContext.h:99-110, 221-229); ids out.
+ * cmlba_marginalize_frames  marginalizeFrames (BA:710-742) -> marginalizeFrame -> removeFrame: flagged frames leave,
+ *      with the points they host and the residuals that target them; ids out. */
+int cmlba_flag_frames_for_marginalization(cmlba_handle *h, const double *cams /*[n][12] or NULL*/, const int32_t *num_immature /*[n] or NULL*/,
+                                          int64_t *flagged_ids, int *n_flagged);
+int cmlba_try_marginalize(cmlba_handle *h, int *n_dropped, int *n_to_marginalize);
+int cmlba_marginalize_points(cmlba_handle *h, int64_t *point_ids, int *n);
+int cmlba_marginalize_frames(cmlba_handle *h, int64_t *frame_ids, int *n);
 
 /* bool run(bool updatePointsOnly) (BA:744-910).  cams = the graph's current Frame::getCamera() for every
  * window frame in window order (what updateCamera() reads, BA.h:54-60); NULL = keep current states.

@@ -29,7 +29,7 @@ class Config(C.Structure):
                 ("scale_rotation", C.c_float), ("scale_translation", C.c_float), ("scale_light_a", C.c_float), ("scale_light_b", C.c_float),
                 ("scale_f", C.c_float), ("scale_c", C.c_float), ("force_accept", C.c_int), ("fix_lambda", C.c_int), ("fixed_lambda", C.c_float),
                 ("idepth_fix_prior", C.c_int), ("solver_mode_delta", C.c_float), ("optimize_light_a", C.c_int), ("optimize_light_b", C.c_int),
-                ("disable_marginalization", C.c_int), ("max_frames", C.c_int)]
+                ("disable_marginalization", C.c_int), ("max_frames", C.c_int), ("frame_min_age", C.c_int), ("min_idepth_h_marg", C.c_float)]
 
 
 class RunResult(C.Structure):
@@ -44,7 +44,8 @@ class BenchResult(C.Structure):
 
 # every symbol include/cmlba.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = ["cmlba_default_config", "cmlba_create", "cmlba_destroy", "cmlba_last_error", "cmlba_set_calib", "cmlba_add_frame", "cmlba_add_points",
-           "cmlba_remove_point", "cmlba_remove_frame", "cmlba_run", "cmlba_num_frames", "cmlba_num_points", "cmlba_num_residuals", "cmlba_get_frames",
+           "cmlba_remove_point", "cmlba_remove_frame", "cmlba_flag_frames_for_marginalization", "cmlba_try_marginalize", "cmlba_marginalize_points",
+           "cmlba_marginalize_frames", "cmlba_run", "cmlba_num_frames", "cmlba_num_points", "cmlba_num_residuals", "cmlba_get_frames",
            "cmlba_get_points", "cmlba_get_outliers", "cmlba_get_residuals", "cmlba_prepare", "cmlba_linearize", "cmlba_apply", "cmlba_solve", "cmlba_step",
            "cmlba_read", "cmlba_reset", "cmlba_bench_pass", "cmlba_nccl_unique_id", "cmlba_comm_init", "cmlba_version"]
 
@@ -73,6 +74,10 @@ def load_library():
     lib.cmlba_remove_point.argtypes = [vp, C.c_int64]
     lib.cmlba_remove_frame.argtypes = [vp, C.c_int64]
     lib.cmlba_run.argtypes = [vp, dp, C.c_int, C.c_int, C.POINTER(RunResult)]
+    lib.cmlba_flag_frames_for_marginalization.argtypes = [vp, dp, ip, C.POINTER(C.c_int64), ip]
+    lib.cmlba_try_marginalize.argtypes = [vp, ip, ip]
+    lib.cmlba_marginalize_points.argtypes = [vp, C.POINTER(C.c_int64), ip]
+    lib.cmlba_marginalize_frames.argtypes = [vp, C.POINTER(C.c_int64), ip]
     for f in ("cmlba_num_frames", "cmlba_num_points", "cmlba_num_residuals"):
         getattr(lib, f).argtypes = [vp]
     lib.cmlba_get_frames.argtypes = [vp, C.POINTER(C.c_int64), dp, dp, dp, dp, dp]
@@ -158,6 +163,44 @@ class DSOBundleAdjustment:
 
     def removeFrame(self, frame_id):
         self._ck(self.lib.cmlba_remove_frame(self.h, int(frame_id)))
+
+    # ---- window maintenance (Hybrid::directMap, slam/modslam/direct/Mapping.cpp:61-100)
+    def flagFramesForMarginalization(self, cams=None, num_immature=None):
+        """flagFramesForMarginalization (BA:603-708); the reference calls it at the top of addNewFrame. Returns flagged frame ids."""
+        n = self.lib.cmlba_num_frames(self.h)
+        cp = None
+        if cams is not None:
+            cams = np.ascontiguousarray(cams, dtype=np.float64).reshape(-1, 12); cp = _ptr(cams, C.c_double)
+        ip = None
+        if num_immature is not None:
+            num_immature = np.ascontiguousarray(num_immature, dtype=np.int32); ip = _ptr(num_immature, C.c_int)
+        ids = np.zeros(max(n, 1), np.int64); cnt = C.c_int(n)
+        self._ck(self.lib.cmlba_flag_frames_for_marginalization(self.h, cp, ip, _ptr(ids, C.c_int64), C.byref(cnt)))
+        return ids[:cnt.value]
+
+    def tryMarginalize(self):
+        """tryMarginalize (BA:2240-2363). Returns (#points dropped -> getOutliers(), #points marked for marginalisation)."""
+        a, b = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.cmlba_try_marginalize(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def marginalizePointsF(self):
+        """marginalizePointsF (BA:2466-2513). Returns the ids of the points that left the window as marginalised."""
+        n = self.lib.cmlba_num_points(self.h)
+        ids = np.zeros(max(n, 1), np.int64); cnt = C.c_int(n)
+        self._ck(self.lib.cmlba_marginalize_points(self.h, _ptr(ids, C.c_int64), C.byref(cnt)))
+        return ids[:cnt.value]
+
+    def marginalizeFrames(self):
+        """marginalizeFrames (BA:710-742). Returns the ids of the removed frames."""
+        n = self.lib.cmlba_num_frames(self.h)
+        ids = np.zeros(max(n, 1), np.int64); cnt = C.c_int(n)
+        self._ck(self.lib.cmlba_marginalize_frames(self.h, _ptr(ids, C.c_int64), C.byref(cnt)))
+        return ids[:cnt.value]
+
+    def frameCounters(self):
+        """[N,4] int32: flaggedForMarginalization, numMarginalized, numResidualsOut, residuals targeting the frame."""
+        return self.read("frame_counters", np.int32).reshape(-1, 4)
 
     def run(self, cams=None, updatePointsOnly=False, iterations=0):
         """bool run(bool updatePointsOnly) (BA:744-910). cams: [N,12] current Frame::getCamera() per window frame."""

@@ -133,6 +133,8 @@ struct FrameHost {
     int keyid = 0;
     bool is_init = false;
     float4 *d_img = nullptr;
+    bool flagged = false;        // flaggedForMarginalization
+    int num_marginalized = 0, num_residuals_out = 0;   // DSOFrame counters fed by DSOContext::removePoint / removeResiduals
     Pose pre;                    // PRE_worldToCam (last known)
     double aff_a = 0, aff_b = 0; // aff_g2l (scaled a,b)
 };
@@ -152,6 +154,7 @@ struct PointHost {
     int64_t last_frame[2] = {-1, -1};   // frames of lastResiduals[0/1] (DSOPoint.h:119-156); -1 = nullptr
     int last_state[2] = {CMLBA_RES_OOB, CMLBA_RES_OOB};
     bool alive = true;
+    bool to_marginalize = false; // DSOTOMARGINALIZE
 };
 
 // Residual bookkeeping: a residual (point, target frame) exists iff bit `target slot` of PointHost::res_mask is set
@@ -431,12 +434,20 @@ public:
         dirty = true; prepared = false;
     }
     void kill_point(size_t idx) { if (points_[idx].alive) { points_[idx].alive = false; n_dead++; } }
+    // DSOContext::removePoint(point, marginalize) (DSOContext.h:94-110) -> removeResiduals (:207-218): counters of the target frames
+    void drop_point(size_t idx, bool marginalize) {
+        PointHost &p = points_[idx];
+        if (!p.alive) return;
+        for (unsigned m = p.res_mask; m; m &= m - 1) { FrameHost &f = frames_[__builtin_ctz(m)]; f.num_residuals_out++; if (marginalize) f.num_marginalized++; }
+        p.res_mask = 0;
+        kill_point(idx);
+    }
     void maybe_compact() { if (n_dead * 4 > points_.size()) compact(); dirty = true; prepared = false; }
 
     int remove_point(int64_t id) {
         const int idx = point_index_.find(id);
         if (idx < 0 || !points_[idx].alive) return CMLBA_OK;   // DSOContext.h:95-97
-        kill_point(idx);
+        drop_point(idx, false);
         maybe_compact();
         return CMLBA_OK;
     }
@@ -448,7 +459,8 @@ public:
         for (size_t i = 0; i < points_.size(); i++) {
             PointHost &p = points_[i];
             if (!p.alive) continue;
-            if (p.host == fi) kill_point(i); else if (p.host > fi) p.host--;
+            if (p.host == fi) { drop_point(i, false); continue; }          // removePoints(frame's points) (DSOContext.h:155-156)
+            if (p.host > fi) p.host--;
             p.res_mask = (uint16_t) ((p.res_mask & low) | ((p.res_mask >> (fi + 1)) << fi));   // squeeze slot fi out
             if (p.res_mask == 0) kill_point(i);       // points left without residuals disappear as well (DSOContext.h:205-216)
         }
@@ -457,6 +469,128 @@ public:
         if (frames_[fi].d_img) img_pool.push_back(frames_[fi].d_img);
         frames_.erase(frames_.begin() + fi);
         maybe_compact();
+        return CMLBA_OK;
+    }
+
+    // ------------------------------------------------------------------ window maintenance decisions (host, exact)
+    int frame_residual_count(int t) const { int c = 0; for (auto &p : points_) if (p.alive && ((p.res_mask >> t) & 1)) c++; return c; }
+
+    // flagFramesForMarginalization (BA:603-708)
+    int flag_frames(const double *cams, const int32_t *num_immature, int64_t *ids, int *n_ids) {
+        const int N = (int) frames_.size();
+        if (N == 0) { if (n_ids) *n_ids = 0; return CMLBA_OK; }
+        auto cam = [&](int i) { Pose c; if (cams) { for (int k = 0; k < 9; k++) c.R[k] = cams[12 * i + k]; for (int k = 0; k < 3; k++) c.t[k] = cams[12 * i + 9 + k]; } else c = frames_[i].pre; return c; };
+        int flagged = 0;
+        const FrameHost &back = frames_[N - 1];
+        for (int i = 0; i < N; i++) {
+            FrameHost &f = frames_[i];
+            const double in = (double) frame_residual_count(i) + (num_immature ? (double) num_immature[i] : 0.0);
+            const double out = (double) f.num_marginalized + (double) f.num_residuals_out;
+            // frameBack->getExposure().to(frame->getExposure()) (map/Exposure.h:119-123): a = exp(a_f - a_back) * tau_f / tau_back
+            const double ref_to_fh = exp(f.aff_a - back.aff_a) * f.exposure / back.exposure;
+            const bool not_enough = in < 0.05 * (in + out);
+            const bool too_big = fabs(log(ref_to_fh)) > 0.7 && N - flagged > cfg.max_frames - 2;
+            if (not_enough || too_big) { f.flagged = true; flagged++; }
+        }
+        if (N - flagged >= cfg.max_frames) {
+            double smallest = 1; int to_marg = -1;
+            const int latest_key = back.keyid;
+            const Pose cb = cam(N - 1);
+            for (int r = 0; r < N; r++) {
+                const FrameHost &ref = frames_[r];
+                if (ref.keyid > latest_key - cfg.frame_min_age || ref.keyid == 0) continue;
+                const Pose cr_inv = pose_inv(cam(r));
+                double score = 0;
+                for (int t = 0; t < N; t++) {
+                    if (t == r) continue;
+                    if (frames_[t].keyid > latest_key - cfg.frame_min_age + 1) continue;
+                    const Pose rel = pose_mul(cam(t), cr_inv);                 // reference->getCamera().to(target->getCamera())
+                    score += 1.0 / (1e-5 + sqrt(rel.t[0] * rel.t[0] + rel.t[1] * rel.t[1] + rel.t[2] * rel.t[2]));
+                }
+                const Pose relb = pose_mul(cb, cr_inv);
+                score *= -sqrt(sqrt(relb.t[0] * relb.t[0] + relb.t[1] * relb.t[1] + relb.t[2] * relb.t[2]));
+                if (score < smallest) { smallest = score; to_marg = r; }
+            }
+            if (to_marg >= 0) { frames_[to_marg].flagged = true; flagged++; }
+        }
+        if (n_ids) {
+            const int cap = *n_ids; int k = 0;
+            for (auto &f : frames_) if (f.flagged) { if (ids && k < cap) ids[k] = f.id; k++; }
+            *n_ids = k;
+        }
+        return CMLBA_OK;
+    }
+
+    // tryMarginalize (BA:2240-2363) with isOOB (BA:2515-2554); residual states are those of the last run()
+    int try_marginalize(int *n_dropped, int *n_to_marg) {
+        const int N = (int) frames_.size();
+        const size_t PA = points_.size();
+        std::vector<int> num_in(PA, 0), vis(PA, 0);
+        std::vector<uint16_t> seen(PA, 0);
+        if (snap.valid) {
+            const int *rp = snap.own_map ? snap.r_point.data() : up.host<int>(up_o_rp);
+            const uint8_t *rt = snap.own_map ? snap.r_target.data() : up.host<uint8_t>(up_o_rt);
+            std::vector<int> pidx(snap.point_id.size()), fslot(snap.frame_id.size());
+            for (size_t i = 0; i < pidx.size(); i++) pidx[i] = point_index_.find(snap.point_id[i]);
+            for (size_t i = 0; i < fslot.size(); i++) fslot[i] = frame_index(snap.frame_id[i]);
+            for (int i = 0; i < snap.R; i++) {
+                if (!snap.alive[i]) continue;
+                const int q = pidx[rp[i]], t = fslot[rt[i]];
+                if (q < 0 || t < 0 || !points_[q].alive || !((points_[q].res_mask >> t) & 1)) continue;
+                seen[q] |= (uint16_t) (1u << t);
+                if (snap.state[i] == RES_IN) { num_in[q]++; if (frames_[t].flagged) vis[q]++; }
+            }
+        }
+        int dropped = 0, tomarg = 0;
+        std::vector<size_t> to_drop;
+        for (size_t q = 0; q < PA; q++) {
+            PointHost &p = points_[q];
+            if (!p.alive) continue;
+            // residuals created since the last run() are in state IN (DSOResidual.h:81-86)
+            for (unsigned m = p.res_mask & ~seen[q]; m; m &= m - 1) { num_in[q]++; if (frames_[__builtin_ctz(m)].flagged) vis[q]++; }
+            const int nres = __builtin_popcount(p.res_mask);
+            if (p.idepth < 0 || nres == 0) { to_drop.push_back(q); continue; }
+            bool oob;
+            if (num_in[q] >= 3 && p.num_good > 4 + 10 && num_in[q] - vis[q] < 3) oob = true;
+            else if (p.last_state[0] == CMLBA_RES_OOB) oob = true;
+            else if (num_in[q] < 2) oob = false;
+            else oob = p.last_state[0] == CMLBA_RES_OUTLIER && p.last_state[1] == CMLBA_RES_OUTLIER;
+            if (oob || frames_[p.host].flagged) {
+                if (nres >= 3 && p.num_good >= 4 && p.idepth_hessian > cfg.min_idepth_h_marg) { p.to_marginalize = true; tomarg++; }
+                else to_drop.push_back(q);
+            }
+        }
+        for (size_t q : to_drop) { outliers_.push_back(points_[q].id); drop_point(q, false); dropped++; }
+        (void) N;
+        if (n_dropped) *n_dropped = dropped;
+        if (n_to_marg) *n_to_marg = tomarg;
+        if (dropped) maybe_compact();
+        return CMLBA_OK;
+    }
+
+    // marginalizePointsF (BA:2466-2513): structural part (see include/cmlba.h for the prior)
+    int marginalize_points(int64_t *ids, int *n) {
+        const int cap = n ? *n : 0; int k = 0;
+        for (size_t q = 0; q < points_.size(); q++) {
+            PointHost &p = points_[q];
+            if (!p.alive || !p.to_marginalize) continue;
+            if (ids && k < cap) ids[k] = p.id;
+            k++;
+            p.to_marginalize = false;
+            drop_point(q, true);
+        }
+        if (n) *n = k;
+        if (k) maybe_compact();
+        return CMLBA_OK;
+    }
+
+    // marginalizeFrames (BA:710-742)
+    int marginalize_frames(int64_t *ids, int *n) {
+        const int cap = n ? *n : 0; int k = 0;
+        std::vector<int64_t> gone;
+        for (auto &f : frames_) if (f.flagged) gone.push_back(f.id);
+        for (int64_t id : gone) { if (ids && k < cap) ids[k] = id; k++; int rc = remove_frame(id); if (rc) return rc; }
+        if (n) *n = k;
         return CMLBA_OK;
     }
 
@@ -866,15 +1000,15 @@ public:
             for (; i + 8 <= R; i += 8) {            // alive[] is almost all ones: test 8 flags at a time
                 uint64_t wd; memcpy(&wd, alive + i, 8);
                 if (wd == 0x0101010101010101ull) continue;
-                for (int k = i; k < i + 8; k++) if (!alive[k]) { points_[pt_order[r_point[k]]].res_mask &= (uint16_t) ~(1u << r_target[k]); dropped++; }
+                for (int k = i; k < i + 8; k++) if (!alive[k]) { points_[pt_order[r_point[k]]].res_mask &= (uint16_t) ~(1u << r_target[k]); frames_[r_target[k]].num_residuals_out++; dropped++; }
             }
-            for (; i < R; i++) if (!alive[i]) { points_[pt_order[r_point[i]]].res_mask &= (uint16_t) ~(1u << r_target[i]); dropped++; }
+            for (; i < R; i++) if (!alive[i]) { points_[pt_order[r_point[i]]].res_mask &= (uint16_t) ~(1u << r_target[i]); frames_[r_target[i]].num_residuals_out++; dropped++; }
         }
         for (int t = std::max(0, N - 2); t < N; t++) {
             const int64_t tid = frames_[t].id;
             for (int i = res_bin_begin[t * N]; i < res_bin_begin[(t + 1) * N]; i++) {
                 PointHost &p = points_[pt_order[r_point[i]]];
-                for (int s2 = 0; s2 < 2; s2++) if (p.last_frame[s2] == tid) { if (alive[i]) p.last_state[s2] = st[i]; else p.last_frame[s2] = -1; break; }
+                for (int s2 = 0; s2 < 2; s2++) if (p.last_frame[s2] == tid) { p.last_state[s2] = st[i]; if (!alive[i]) p.last_frame[s2] = -1; break; }   // setResidualState for every active residual, then first = nullptr for the deleted ones
             }
         }
         // points: results, outliers (points left without residuals, BA:1636-1640) and the id list of the residual snapshot
@@ -975,6 +1109,11 @@ public:
     int read(const std::string &name, void *dst, size_t cap, size_t *bytes) {
         if (name == "host_timing") { const std::string t = timers.text(); return host_out(t.data(), t.size(), dst, cap, bytes); }
         if (name == "host_timing_reset") { timers.acc.clear(); if (bytes) *bytes = 0; return CMLBA_OK; }
+        if (name == "frame_counters") {   // [N][4] int32: flagged, numMarginalized, numResidualsOut, residuals targeting the frame
+            std::vector<int32_t> v;
+            for (size_t i = 0; i < frames_.size(); i++) { v.push_back(frames_[i].flagged); v.push_back(frames_[i].num_marginalized); v.push_back(frames_[i].num_residuals_out); v.push_back(frame_residual_count((int) i)); }
+            return host_out(v.data(), v.size() * 4, dst, cap, bytes);
+        }
         if (name == "enable_dbg") { want_dbg = true; dirty = true; prepared = false; if (bytes) *bytes = 0; return CMLBA_OK; }
         if (dirty || !d_ctrl.p) { set_error("window not built yet (cmlba_prepare / cmlba_run first)"); return CMLBA_ERR_STATE; }
         CK(cudaSetDevice(device));
@@ -1061,7 +1200,7 @@ int cmlba_default_config(cmlba_config *c) {
     c->iterations = 4; c->huber_threshold = 9.f; c->outlier_th_sum = 2500.f; c->th_opt_iterations = 1.2f;
     c->scale_rotation = 1.f; c->scale_translation = 0.5f; c->scale_light_a = 10.f; c->scale_light_b = 1000.f; c->scale_f = 50.f; c->scale_c = 50.f;
     c->force_accept = 1; c->fix_lambda = 1; c->fixed_lambda = 1e-5f; c->idepth_fix_prior = 2500; c->solver_mode_delta = 1e-5f;
-    c->optimize_light_a = 1; c->optimize_light_b = 1; c->disable_marginalization = 1; c->max_frames = 6;
+    c->optimize_light_a = 1; c->optimize_light_b = 1; c->disable_marginalization = 1; c->max_frames = 6; c->frame_min_age = 1; c->min_idepth_h_marg = 50.f;
     return CMLBA_OK;
 }
 
@@ -1072,6 +1211,7 @@ int cmlba_create(const cmlba_config *cfg, int device, cmlba_handle **out) {
     if (!h) return CMLBA_ERR_ARG;
     if (cfg) h->eng.cfg = *cfg; else cmlba_default_config(&h->eng.cfg);
     h->eng.device = device;
+    if (!h->eng.cfg.disable_marginalization) { g_create_error = "disableMarginalization=false (accumulating the marginalisation prior H_M) is not implemented"; delete h; return CMLBA_ERR_UNSUPPORTED; }
     int rc = h->eng.init();
     if (rc) { g_create_error = h->eng.err; delete h; return rc; }
     *out = h;
@@ -1089,6 +1229,10 @@ int cmlba_add_frame(cmlba_handle *h, int64_t id, const double w2c[12], double a,
 int cmlba_add_points(cmlba_handle *h, int n, const int64_t *pid, const int64_t *host, const float *xy, const double *idepth) { HCHK; return h->eng.add_points(n, pid, host, xy, idepth); }
 int cmlba_remove_point(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove_point(id); }
 int cmlba_remove_frame(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove_frame(id); }
+int cmlba_flag_frames_for_marginalization(cmlba_handle *h, const double *cams, const int32_t *num_immature, int64_t *ids, int *n) { HCHK; return h->eng.flag_frames(cams, num_immature, ids, n); }
+int cmlba_try_marginalize(cmlba_handle *h, int *n_dropped, int *n_to_marg) { HCHK; return h->eng.try_marginalize(n_dropped, n_to_marg); }
+int cmlba_marginalize_points(cmlba_handle *h, int64_t *ids, int *n) { HCHK; return h->eng.marginalize_points(ids, n); }
+int cmlba_marginalize_frames(cmlba_handle *h, int64_t *ids, int *n) { HCHK; return h->eng.marginalize_frames(ids, n); }
 int cmlba_run(cmlba_handle *h, const double *cams, int iterations, int upo, cmlba_run_result *r) { HCHK; return h->eng.run(cams, iterations, upo, r); }
 int cmlba_num_frames(const cmlba_handle *h) { return h ? (int) h->eng.frames_.size() : CMLBA_ERR_ARG; }
 int cmlba_num_points(const cmlba_handle *h) { return h ? (int) (h->eng.points_.size() - h->eng.n_dead) : CMLBA_ERR_ARG; }

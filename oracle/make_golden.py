@@ -51,5 +51,28 @@ def main():
               os.path.getsize(os.path.join(OUT, f"{name}_stages.cmlw")) // 1024, "KB")
 
 
+def maintenance():
+    """Window-maintenance flow (flag / tryMarginalize / marginalizePointsF / marginalizeFrames) of the reference on a 6-frame window."""
+    tmp = "/tmp/cmlba_golden"
+    os.makedirs(tmp, exist_ok=True)
+    win = synth.make_window(160, 120, 6, 60, 4, False, seed=77)
+    win["max_frames"] = np.array([5], np.int32)     # the 6th addNewFrame flags one frame by the distance score (BA:649-700)
+    win["runs"] = np.array([3], np.int32)           # numGoodResiduals must pass 14 for the first isOOB rule (BA:2532-2536)
+    full = os.path.join(tmp, "maint.cmlw")
+    cmlw.save(full, win)
+    run_ref(full, "maintain", os.path.join(tmp, "maint_out.cmlw"))
+    g = cmlw.load(os.path.join(tmp, "maint_out.cmlw"))
+    keep = {k: v for k, v in g.items() if k.startswith(("m1_", "m2_", "m3_", "m4_", "runs_ok")) or k in (
+        "m0_frame_in_window", "m0_frame_flagged", "m0_frame_num_marginalized", "m0_frame_num_residuals_out", "m0_frame_num_residuals", "m0_frame_keyid",
+        "m0_pt_alive", "m0_pt_outlier", "m0_pt_num_good", "m0_pt_idepth_hessian", "m0_pt_last0_state", "m0_pt_last1_state", "m0_res_point", "m0_res_target",
+        "m0_res_state", "m0_frame_pre_w2c", "m0_frame_state", "m0_pt_idepth", "m0_frame_energy_th")}
+    slim = {k: v for k, v in win.items() if k not in ("grad", "truth_idepth")}
+    cmlw.save(os.path.join(OUT, "maint_window.cmlw"), slim)
+    cmlw.save(os.path.join(OUT, "maint_golden.cmlw"), keep)
+    print("maint window", os.path.getsize(os.path.join(OUT, "maint_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "maint_golden.cmlw")) // 1024, "KB")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "maintenance":
+        maintenance(); sys.exit(0)
     main()

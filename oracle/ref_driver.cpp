@@ -6,7 +6,7 @@
 // Nothing here is linked into, imported by, or executed from the product (libcml_b200/, include/);
 // only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs run it.
 //
-//   cmlba_ref --window in.cmlw --mode stages|run|bench --out out.cmlw [--repeat K]
+//   cmlba_ref --window in.cmlw --mode stages|run|maintain|bench --out out.cmlw [--repeat K]
 //
 // mode stages : replays DSOBundleAdjustment::run (BA:744-910) call by call through the class's own
 //               (protected) methods and dumps every intermediate quantity SURVEY.md section 8(d) lists.
@@ -116,7 +116,8 @@ static RefWindow *buildWindow(const cmlw::File &in) {
     w->calib = new InternalCalibration(PinholeUndistorter(Vector2(K[0], K[1]), Vector2(K[2], K[3])), Vector2(w->W, w->H));
     w->gen = new CaptureImageGenerator(w->W, w->H, w->N + 2, w->N + 2);
     w->ba = new DSOBundleAdjustment(w->root);
-    w->ba->setNumFrames(w->N + 2);
+    // maxFrames: N+2 keeps flagFramesForMarginalization quiet (BA:649); the maintenance goldens set it lower
+    w->ba->setNumFrames(in.has("max_frames") ? in.get("max_frames").as<int32_t>()[0] : w->N + 2);
     w->ba->setNumIterations(w->iterations);
     if (in.has("optimize_a")) w->ba->mOptimizeA.set(in.get("optimize_a").as<int32_t>()[0] != 0);
     if (in.has("optimize_b")) w->ba->mOptimizeB.set(in.get("optimize_b").as<int32_t>()[0] != 0);
@@ -463,6 +464,78 @@ static int runStages(RefWindow *w, cmlw::File &out) {
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// mode maintain: the window-maintenance flow of Hybrid::directMap (slam/modslam/direct/Mapping.cpp:61-100):
+// run() x runs, tryMarginalize, removePoint(outliers), computeNullspaces, marginalizePointsF, marginalizeFrames,
+// then one more run() on the reduced window.  Dumps every decision (which frames / points go, counters).
+static void dumpMaintState(RefWindow *w, cmlw::File &out, const std::string &pre) {
+    auto *ba = w->ba;
+    int N = w->N, P = w->P;
+    std::vector<int32_t> inWin(N, 0), flagged(N, 0), nMarg(N, 0), nOut(N, 0), nRes(N, 0), keyid(N, 0);
+    for (auto f : ba->getFrames()) {
+        int i = w->frameIndex.at(f.p()); auto d = ba->get(f);
+        inWin[i] = 1; flagged[i] = d->flaggedForMarginalization ? 1 : 0; nMarg[i] = (int) d->getNumMarginalized(); nOut[i] = (int) d->getNumResidualsOut();
+        nRes[i] = (int) d->getResiduals().size(); keyid[i] = (int) d->keyid;
+    }
+    out.put1<int32_t>(pre + "frame_in_window", inWin); out.put1<int32_t>(pre + "frame_flagged", flagged); out.put1<int32_t>(pre + "frame_num_marginalized", nMarg);
+    out.put1<int32_t>(pre + "frame_num_residuals_out", nOut); out.put1<int32_t>(pre + "frame_num_residuals", nRes); out.put1<int32_t>(pre + "frame_keyid", keyid);
+    std::vector<int32_t> alive(P, 0), outl(P, 0), toMarg(P, 0), marg(P, 0), ngood(P, 0), last0(P, -2), last1(P, -2);
+    std::vector<float> idh(P, 0.f);
+    for (int p = 0; p < P; p++) {
+        PPoint mp = w->points[p];
+        alive[p] = ba->getPoints().count(mp) > 0;
+        outl[p] = ba->mOutliers.count(mp) > 0;
+        toMarg[p] = mp->isGroup(ba->DSOTOMARGINALIZE) ? 1 : 0;
+        marg[p] = mp->isGroup(ba->DSOMARGINALIZED) ? 1 : 0;
+        if (alive[p]) { auto d = ba->get(mp); ngood[p] = d->numGoodResiduals; idh[p] = d->getInverseDepthHessian(); last0[p] = (int) d->getLastResidual(0).second; last1[p] = (int) d->getLastResidual(1).second; }
+    }
+    out.put1<int32_t>(pre + "pt_alive", alive); out.put1<int32_t>(pre + "pt_outlier", outl); out.put1<int32_t>(pre + "pt_to_marginalize", toMarg);
+    out.put1<int32_t>(pre + "pt_marginalized", marg); out.put1<int32_t>(pre + "pt_num_good", ngood); out.put1<float>(pre + "pt_idepth_hessian", idh);
+    out.put1<int32_t>(pre + "pt_last0_state", last0); out.put1<int32_t>(pre + "pt_last1_state", last1);
+    std::vector<int32_t> rp, rt, rs;
+    for (auto r : ba->getResiduals()) { rp.push_back(w->pointIndex.at(r->elements.mapPoint.p())); rt.push_back(w->frameIndex.at(r->elements.frame.p())); rs.push_back((int) r->getState()); }
+    out.put1<int32_t>(pre + "res_point", rp); out.put1<int32_t>(pre + "res_target", rt); out.put1<int32_t>(pre + "res_state", rs);
+}
+
+static int runMaintain(RefWindow *w, const cmlw::File &in, cmlw::File &out) {
+    auto *ba = w->ba;
+    const int runs = in.has("runs") ? in.get("runs").as<int32_t>()[0] : 1;
+    bool ok = true;
+    for (int k = 0; k < runs; k++) { ok = ba->run(w->updatePointsOnly) && ok; ba->mActiveResiduals.clear(); }
+    out.scalar<int32_t>("runs_ok", ok ? 1 : 0);
+    dumpMaintState(w, out, "m0_");                 // after the runs (flags were set inside addNewFrame)
+    dumpFrames(w, out, "m0_"); dumpPoints(w, out, "m0_");
+    ba->tryMarginalize();
+    dumpMaintState(w, out, "m1_");                 // after tryMarginalize
+    { std::vector<PPoint> o(ba->getOutliers().begin(), ba->getOutliers().end()); for (auto pnt : o) ba->removePoint(pnt); }
+    ba->computeNullspaces();
+    ba->marginalizePointsF();
+    dumpMaintState(w, out, "m2_");                 // after marginalizePointsF
+    auto removed = ba->marginalizeFrames();
+    std::vector<int32_t> rem; for (auto f : removed) rem.push_back(w->frameIndex.at(f.p()));
+    out.put1<int32_t>("m3_removed_frames", rem);
+    dumpMaintState(w, out, "m3_");                 // after marginalizeFrames
+    // one more run() on the reduced window: the reduced window's frames keep their original indices in the dump
+    ok = ba->run(w->updatePointsOnly); ba->mActiveResiduals.clear();
+    out.scalar<int32_t>("m4_ok", ok ? 1 : 0);
+    dumpMaintState(w, out, "m4_");
+    {   // final states of the frames that are still in the window + inverse depths
+        std::vector<double> pre_w2c(w->N * 12, 0.0), aff(w->N * 2, 0.0), idepth(w->P, 0.0);
+        for (auto f : ba->getFrames()) {
+            int i = w->frameIndex.at(f.p()); auto d = ba->get(f);
+            Matrix33 R1 = d->PRE_worldToCam.rotationMatrix(); Vector3 t1 = d->PRE_worldToCam.translation();
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) pre_w2c[i * 12 + r * 3 + c] = R1(r, c);
+            for (int r = 0; r < 3; r++) pre_w2c[i * 12 + 9 + r] = t1[r];
+            aff[i * 2] = f->getExposure().getParameters()[0]; aff[i * 2 + 1] = f->getExposure().getParameters()[1];
+        }
+        for (int p = 0; p < w->P; p++) idepth[p] = w->points[p]->getReferenceInverseDepth();
+        out.put<double>("m4_frame_pre_w2c", pre_w2c, {(uint64_t) w->N, 12}); out.put<double>("m4_frame_affine", aff, {(uint64_t) w->N, 2});
+        out.put1<double>("m4_pt_idepth", idepth);
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     std::string window, mode = "stages", outPath;
     int repeat = 3;
@@ -493,6 +566,11 @@ int main(int argc, char **argv) {
         w->ba->mActiveResiduals.clear();
         out.scalar<double>("run_seconds", t1 - t0);
         dumpFinal(w, out, "fin_", ok);
+        if (!outPath.empty()) out.save(outPath);
+    } else if (mode == "maintain") {
+        RefWindow *w = buildWindow(in);
+        cmlw::File out;
+        rc = runMaintain(w, in, out);
         if (!outPath.empty()) out.save(outPath);
     } else if (mode == "bench") {
         // min over `repeat` freshly built windows, 1 thread (the reference BA is single-threaded)

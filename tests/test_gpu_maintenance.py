@@ -1,0 +1,91 @@
+"""GPU (-m gpu): the window-maintenance flow through the C ABI against the reference's golden (tests/golden/maint_*):
+addNewFrame with flagging, three consecutive run() calls, tryMarginalize, marginalizePointsF, marginalizeFrames, run() again
+(Hybrid::directMap, slam/modslam/direct/Mapping.cpp:61-100).  Decisions and counters must match exactly, poses to 1e-4."""
+import os
+import numpy as np
+import pytest
+from parity_util import GOLDEN, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _load():
+    from libcml_b200 import cmlw, synth
+    win = cmlw.load(os.path.join(GOLDEN, "maint_window.cmlw"))
+    win["grad"] = np.stack([synth.gradient_image(win["gray"][i]) for i in range(win["gray"].shape[0])])
+    return win, cmlw.load(os.path.join(GOLDEN, "maint_golden.cmlw"))
+
+
+def _counters(ba, g, pre, ids):
+    c = ba.frameCounters()
+    assert np.array_equal(c[:, 0], g[pre + "frame_flagged"][ids]), pre + "flagged"
+    assert np.array_equal(c[:, 1], g[pre + "frame_num_marginalized"][ids]), pre + "numMarginalized"
+    assert np.array_equal(c[:, 2], g[pre + "frame_num_residuals_out"][ids]), pre + "numResidualsOut"
+    assert np.array_equal(c[:, 3], g[pre + "frame_num_residuals"][ids]), pre + "residuals per frame"
+
+
+def _res_set(ba):
+    rs = ba.getResiduals()
+    return set(zip(rs["point_id"].tolist(), rs["target_frame_id"].tolist()))
+
+
+def test_maintenance_flow_matches_reference():
+    from libcml_b200 import DSOBundleAdjustment
+    win, g = _load()
+    N = win["frame_evalpt"].shape[0]; P = win["pt_host"].size
+    W, H = int(win["size"][0]), int(win["size"][1])
+    ba = DSOBundleAdjustment(device=0, iterations=int(win["iterations"][0]), max_frames=int(win["max_frames"][0]))
+    ba.setCalibration(*[float(v) for v in win["calib"]], W, H)
+    for i in range(N):      # addNewFrame = flagFramesForMarginalization + addFrame (BA:417-462)
+        ba.flagFramesForMarginalization(cams=win["frame_evalpt"][:i] if i else None)
+        ba.addNewFrame(i, win["frame_evalpt"][i], win["frame_affine"][i, 0], win["frame_affine"][i, 1], win["frame_exposure"][i], win["grad"][i], False)
+    ba.addPoints(np.arange(P), win["pt_host"], win["pt_xy"], win["pt_idepth"])
+    assert ba.run(win["frame_cam"])
+    for _ in range(int(win["runs"][0]) - 1):
+        assert ba.run(None)
+    # ---- m0: after the runs
+    ids = np.arange(N)
+    _counters(ba, g, "m0_", ids)
+    pts = ba.getPoints()
+    assert np.array_equal(np.sort(pts["id"]), np.nonzero(g["m0_pt_alive"])[0])
+    assert np.array_equal(pts["num_good_residuals"], g["m0_pt_num_good"][pts["id"]])
+    assert rel(pts["idepth_hessian"], g["m0_pt_idepth_hessian"][pts["id"]]) < 1e-3
+    assert rel(pts["idepth"], g["m0_pt_idepth"][pts["id"]]) < 1e-3
+    fr = ba.getFrames()
+    assert rel(fr["world_to_cam"], g["m0_frame_pre_w2c"]) < 1e-4
+    assert _res_set(ba) == set(zip(g["m0_res_point"].tolist(), g["m0_res_target"].tolist()))
+    rs = ba.getResiduals()
+    gold_state = {(p, t): s for p, t, s in zip(g["m0_res_point"].tolist(), g["m0_res_target"].tolist(), g["m0_res_state"].tolist())}
+    mism = sum(gold_state[(p, t)] != s for p, t, s in zip(rs["point_id"].tolist(), rs["target_frame_id"].tolist(), rs["state"].tolist()))
+    assert mism == 0, f"{mism} residual states differ after three runs"
+    # ---- m1: tryMarginalize
+    n_drop, n_marg = ba.tryMarginalize()
+    dropped = np.nonzero(g["m1_pt_outlier"])[0]
+    assert np.array_equal(np.sort(ba.getOutliers()), dropped) and n_drop == dropped.size
+    assert n_marg == int(g["m1_pt_to_marginalize"].sum())
+    _counters(ba, g, "m1_", ids)
+    for o in ba.getOutliers():
+        ba.removePoint(int(o))                      # Mapping.cpp:90-93 (no-op: already gone)
+    # ---- m2: marginalizePointsF
+    marg = ba.marginalizePointsF()
+    assert np.array_equal(np.sort(marg), np.nonzero(g["m2_pt_marginalized"])[0])
+    _counters(ba, g, "m2_", ids)
+    assert np.array_equal(np.sort(ba.getPoints()["id"]), np.nonzero(g["m2_pt_alive"])[0])
+    assert _res_set(ba) == set(zip(g["m2_res_point"].tolist(), g["m2_res_target"].tolist()))
+    # ---- m3: marginalizeFrames
+    removed = ba.marginalizeFrames()
+    assert list(removed) == list(g["m3_removed_frames"])
+    keep = np.nonzero(g["m3_frame_in_window"])[0]
+    assert np.array_equal(ba.getFrames()["id"], keep)
+    _counters(ba, g, "m3_", keep)
+    assert np.array_equal(np.sort(ba.getPoints()["id"]), np.nonzero(g["m3_pt_alive"])[0])
+    assert _res_set(ba) == set(zip(g["m3_res_point"].tolist(), g["m3_res_target"].tolist()))
+    # ---- m4: run() on the reduced window
+    assert ba.run(None) == bool(g["m4_ok"][0])
+    fr = ba.getFrames(); pts = ba.getPoints()
+    assert rel(fr["world_to_cam"], g["m4_frame_pre_w2c"][keep]) < 1e-4
+    assert np.abs(fr["affine"] - g["m4_frame_affine"][keep]).max() < 1e-4 * max(1.0, np.abs(g["m4_frame_affine"]).max())
+    assert np.array_equal(np.sort(pts["id"]), np.nonzero(g["m4_pt_alive"])[0])
+    assert rel(pts["idepth"], g["m4_pt_idepth"][pts["id"]]) < 1e-3
+    assert _res_set(ba) == set(zip(g["m4_res_point"].tolist(), g["m4_res_target"].tolist()))
+    ba.close()
