@@ -134,6 +134,7 @@ typedef struct cmlba_run_result {
     double energy_last;         /* energy of the final linearizeAll(true) */
     double gpu_ms;              /* device time of the whole run (CUDA events) */
     int kernel_launches;        /* kernels launched by this run */
+    int num_rejected;           /* GN steps undone because the energy did not decrease (forceAccept = false, BA:866-876) */
 } cmlba_run_result;
 int cmlba_run(cmlba_handle *h, const double *cams /* [n_frames][12] or NULL */, int iterations, int update_points_only,
               cmlba_run_result *result);

@@ -34,7 +34,7 @@ class Config(C.Structure):
 
 class RunResult(C.Structure):
     _fields_ = [("iterations_done", C.c_int), ("num_residuals", C.c_int), ("num_dropped", C.c_int), ("num_outliers", C.c_int),
-                ("energy_first", C.c_double), ("energy_last", C.c_double), ("gpu_ms", C.c_double), ("kernel_launches", C.c_int)]
+                ("energy_first", C.c_double), ("energy_last", C.c_double), ("gpu_ms", C.c_double), ("kernel_launches", C.c_int), ("num_rejected", C.c_int)]
 
 
 class BenchResult(C.Structure):

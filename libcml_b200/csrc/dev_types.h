@@ -53,6 +53,11 @@ struct Ctrl {
     int numID;
     int sc_done_count;      // last-block counter (point step kernel)
     double stats[16];       // ||HA|| ||Hsc|| ||bA|| ||bsc|| ||x|| ... (the Statistic series of BA.h:215-233)
+    // step rejection (forceAccept = false, BA:843-877): linearized energies of calcLEnergy (BA:2118-2208)
+    double energyL_last, energyL_new;
+    double prior_energy_pts;    // sum_p deltaF^2 * priorF (BA:2200) of the current point states
+    int rejected_at;            // value of `iteration` right after the last rejected step (restore_state_kernel keys on it)
+    int rejected;               // number of rejected steps
 };
 
 struct DevWin {

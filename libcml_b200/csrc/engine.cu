@@ -690,7 +690,7 @@ public:
         CK(d_acc0.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N)); CK(d_acc1.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N));
         CK(d_sc_part.reserve((size_t) std::max(n_sc_chunks, 1) * sc_stride));
         CK(d_st_out.reserve((size_t) N * N * st_stride(N)));
-        CK(d_sys.reserve((size_t) 2 * n * n + 2 * n)); CK(d_x.reserve(n)); CK(d_xAd.reserve((size_t) N * N * 8)); CK(d_pt_part.reserve((size_t) std::max(n_pt_blocks, 1) * 3));
+        CK(d_sys.reserve((size_t) 2 * n * n + 2 * n)); CK(d_x.reserve(n)); CK(d_xAd.reserve((size_t) N * N * 8)); CK(d_pt_part.reserve((size_t) std::max(n_pt_blocks, 1) * 4));
         lap("bdw.alloc");
         if (up.used) CK(cudaMemcpyAsync(up.d.p, up.h.p, up.used, cudaMemcpyHostToDevice, stream));
         // views into the arena
@@ -918,17 +918,18 @@ public:
     int run(const double *cams, int iterations, int update_points_only, cmlba_run_result *out) {
         TSCOPE("run(total)");
         Lap lap(timers);
-        if (!cfg.force_accept) { set_error("forceAccept=false (step rejection) is not implemented on the device path yet"); return CMLBA_ERR_UNSUPPORTED; }
         int rc = prepare(cams);
         if (rc) return rc;
         if (iterations <= 0) iterations = cfg.iterations;
         dw.update_points_only = update_points_only ? 1 : 0;
         const int l0 = launches;
         CK(cudaEventRecord(ev0, stream));
+        if (!cfg.force_accept) { point_prior_energy_kernel<<<1, 256, 0, stream>>>(dw); launches++; }
         launch_linearize(0, 0); launch_post(0, 0);
         for (int it = 0; it < iterations; it++) {
             rc = launch_solve_sequence(1); if (rc) return rc;
             launch_linearize(0, 1); launch_post(1, 1);
+            if (!cfg.force_accept) { restore_state_kernel<<<std::max(dw.n_pt_blocks, 1), 256, 0, stream>>>(dw, it + 1); launches++; }   // no-op unless the step was rejected
         }
         set_evalpt_newest_kernel<<<1, 32, 0, stream>>>(dw); launches++;
         pairs_kernel<<<(dw.N * dw.N + 63) / 64, 64, 0, stream>>>(dw); launches++;
@@ -1027,7 +1028,7 @@ public:
         }
         if (out) {
             out->iterations_done = c.iteration; out->num_residuals = R; out->num_dropped = dropped; out->num_outliers = nout;
-            out->energy_first = c.energy_first; out->energy_last = c.energy_last;
+            out->energy_first = c.energy_first; out->energy_last = c.energy_last; out->num_rejected = c.rejected;
         }
         flap("finish.scatter");
         dirty = dropped > 0 || nout > 0;

@@ -917,7 +917,7 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
     for (int e = threadIdx.x; e < N * N * 8; e += 256) s_xad[e] = w.xAd[e];
     __syncthreads();
     const int p = blockIdx.x * 256 + threadIdx.x;
-    double nid = 0.0; int cntid = 0; int bad = 0;
+    double nid = 0.0, pe = 0.0; int cntid = 0; int bad = 0;
     if (p < w.P) {
         double step = 0.0;
         if (w.pt_ngood_cur[p] > 0) {
@@ -943,19 +943,22 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
             w.pt_idepth_zero[p] = (float) newid;
             nid = (double) fabsf(backup); cntid = 1;
         }
+        const float deltaF = (float) (w.pt_idepth[p] - (double) w.pt_idepth_zero[p]);   // computeDelta (BA:1180-1190) after the step
+        pe = (double) (deltaF * deltaF * w.pt_priorF[p]);
     }
-    __shared__ double s_n[8]; __shared__ int s_c[8]; __shared__ int s_bad[8];
+    __shared__ double s_n[8]; __shared__ double s_pe[8]; __shared__ int s_c[8]; __shared__ int s_bad[8];
     double sn = warp_sum_d(nid);
+    const double spe = warp_sum_d(pe);
     int sc = cntid, sb = bad;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sc += __shfl_down_sync(0xffffffffu, sc, o); sb += __shfl_down_sync(0xffffffffu, sb, o); }
-    if ((threadIdx.x & 31) == 0) { s_n[threadIdx.x >> 5] = sn; s_c[threadIdx.x >> 5] = sc; s_bad[threadIdx.x >> 5] = sb; }
+    if ((threadIdx.x & 31) == 0) { s_n[threadIdx.x >> 5] = sn; s_pe[threadIdx.x >> 5] = spe; s_c[threadIdx.x >> 5] = sc; s_bad[threadIdx.x >> 5] = sb; }
     __syncthreads();
     __shared__ int s_last;
     if (threadIdx.x == 0) {
-        double tn = 0; int tc = 0, tb = 0;
-        for (int k = 0; k < 8; k++) { tn += s_n[k]; tc += s_c[k]; tb += s_bad[k]; }
-        w.pt_part[blockIdx.x * 3 + 0] = tn; w.pt_part[blockIdx.x * 3 + 1] = (double) tc; w.pt_part[blockIdx.x * 3 + 2] = (double) tb;
+        double tn = 0, tpe = 0; int tc = 0, tb = 0;
+        for (int k = 0; k < 8; k++) { tn += s_n[k]; tpe += s_pe[k]; tc += s_c[k]; tb += s_bad[k]; }
+        w.pt_part[blockIdx.x * 4 + 0] = tn; w.pt_part[blockIdx.x * 4 + 1] = (double) tc; w.pt_part[blockIdx.x * 4 + 2] = (double) tb; w.pt_part[blockIdx.x * 4 + 3] = tpe;
         __threadfence();
         const int ticket = atomicAdd(&ctrl->sc_done_count, 1);
         s_last = (ticket == (int) gridDim.x - 1);
@@ -963,10 +966,11 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
     __syncthreads();
     if (s_last && threadIdx.x < 32) {
         __threadfence();
-        double tn = 0, tc = 0, tb = 0;
-        for (int k = threadIdx.x; k < (int) gridDim.x; k += 32) { tn += w.pt_part[k * 3]; tc += w.pt_part[k * 3 + 1]; tb += w.pt_part[k * 3 + 2]; }
-        tn = warp_sum_d(tn); tc = warp_sum_d(tc); tb = warp_sum_d(tb);
+        double tn = 0, tc = 0, tb = 0, tpe = 0;
+        for (int k = threadIdx.x; k < (int) gridDim.x; k += 32) { tn += w.pt_part[k * 4]; tc += w.pt_part[k * 4 + 1]; tb += w.pt_part[k * 4 + 2]; tpe += w.pt_part[k * 4 + 3]; }
+        tn = warp_sum_d(tn); tc = warp_sum_d(tc); tb = warp_sum_d(tb); tpe = warp_sum_d(tpe);
     if (threadIdx.x == 0) {
+        ctrl->prior_energy_pts = tpe;
         const float sumNID = (float) (tn / (tc > 0 ? tc : 1.0));
         ctrl->sumNID = tn; ctrl->numID = (int) tc;
         const float th = w.th_opt;
@@ -1070,18 +1074,59 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
         th_new = th * th;
     }
     if (tid == 0) {
-        w.frames[w.N - 1].energy_th = th_new;
         ctrl->energy_new = energy;
+        // calcLEnergy (BA:2118-2208) without linearized residuals: frame priors + point priors; calcMEnergy (BA:2095-2116) is 0 (H_M = 0)
+        double EL = 0.0;
+        if (!w.force_accept) {
+            for (int i = 0; i < w.N; i++) for (int k = 0; k < 8; k++) { const double d = w.frames[i].state[k]; EL += d * w.frames[i].prior[k] * d; }
+            EL += ctrl->prior_energy_pts;
+        }
+        ctrl->energyL_new = EL;
+        bool keep_th = false;
         if (!isfinite(energy)) { ctrl->failed = 1; ctrl->done = 1; }
-        else if (mode == 0) { ctrl->cur ^= 1; ctrl->energy_last = energy; ctrl->energy_first = energy; }
+        else if (mode == 0) { ctrl->cur ^= 1; ctrl->energy_last = energy; ctrl->energy_first = energy; ctrl->energyL_last = EL; }
         else if (mode == 1) {
-            // forceAccept (BA:843): applyActiveRes, lambda *= 0.25
-            ctrl->cur ^= 1; ctrl->energy_last = energy; ctrl->lambda *= 0.25; ctrl->accepted += 1;
             const int it = ctrl->iteration;
+            if (w.force_accept || energy + EL < ctrl->energy_last + ctrl->energyL_last) {
+                // applyActiveRes, lambda *= 0.25 (BA:843-864)
+                ctrl->cur ^= 1; ctrl->energy_last = energy; ctrl->energyL_last = EL; ctrl->lambda *= 0.25; ctrl->accepted += 1;
+            } else {
+                // loadSateBackup + re-linearization at the backup = the committed linearization stays (BA:866-876); restore_state_kernel undoes the step
+                ctrl->lambda *= 1e2; ctrl->rejected += 1; ctrl->rejected_at = it + 1; keep_th = true;
+            }
             ctrl->iteration = it + 1;
             if (ctrl->canbreak && it >= 1) ctrl->done = 1;             // BA:879
         } else if (mode == 2) { ctrl->cur ^= 1; ctrl->energy_last = energy; }
+        if (!keep_th) w.frames[w.N - 1].energy_th = th_new;            // a rejected linearization leaves frameEnergyTH as the re-linearization would
     }
+}
+
+// forceAccept = false: undo a rejected step (loadSateBackup, BA:928-946).  `it1` = the iteration counter value the step belongs to.
+__global__ void __launch_bounds__(256) restore_state_kernel(const DevWin w, const int it1) {
+    Ctrl *ctrl = w.ctrl;
+    if (ctrl->rejected_at != it1) return;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p < w.P) { const float b = w.pt_idepth_backup[p]; w.pt_idepth[p] = (double) b; w.pt_idepth_zero[p] = b; }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < w.N) { FrameDev &f = w.frames[threadIdx.x]; double st[10]; for (int k = 0; k < 10; k++) st[k] = f.state_backup[k]; frame_set_state(f, st, w); }
+        __syncthreads();
+        for (int e = threadIdx.x; e < w.N * w.N; e += 256) pair_precompute(w, e / w.N, e % w.N);
+        if (threadIdx.x == 0) {
+            double pe = 0.0;   // point prior energy of the restored state is recomputed lazily: deltaF = 0 after loadSateBackup (idepth_zero = idepth_backup)
+            ctrl->prior_energy_pts = pe;
+        }
+    }
+}
+
+// sum_p deltaF^2 * priorF at the start of run() (forceAccept = false only)
+__global__ void __launch_bounds__(256) point_prior_energy_kernel(const DevWin w) {
+    __shared__ double s[8];
+    double pe = 0.0;
+    for (int p = threadIdx.x; p < w.P; p += 256) { const float d = (float) (w.pt_idepth[p] - (double) w.pt_idepth_zero[p]); pe += (double) (d * d * w.pt_priorF[p]); }
+    pe = warp_sum_d(pe);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = pe;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int k = 0; k < 8; k++) t += s[k]; w.ctrl->prior_energy_pts = t; }
 }
 
 // ------------------------------------------------------------------------------------------------

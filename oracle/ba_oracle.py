@@ -692,6 +692,15 @@ def do_step_from_backup(w, fix_camera=False):
     return bool(np.sqrt(sumA) < 0.0005 * th and np.sqrt(sumB) < 0.00005 * th and np.sqrt(sumR) < 0.00005 * th and np.sqrt(sumT) * sumNID < 0.00005 * th)
 
 
+def calc_l_energy(w):
+    """calcLEnergy BA:2118-2208 for a window without linearized residuals: frame priors + point priors; 0 when forceAccept (BA:2123).
+    calcMEnergy (BA:2095-2116) is 0 as long as the marginalisation prior H_M, b_M is zero."""
+    if w.p["force_accept"]:
+        return 0.0
+    F = float(np.sum(w.delta_prior * w.prior * w.delta_prior))           # BA:2130-2133 (compute_delta keeps delta_prior current)
+    return F + float(np.sum(np.asarray(w.deltaF, np.float64) ** 2 * np.asarray(w.priorF, np.float64)))   # BA:2200
+
+
 def run(w, hook=None):
     """DSOBundleAdjustment::run BA:744-910 (forceAccept path; the reject branch re-linearizes at the backup)."""
     hook = hook or (lambda *a: None)
@@ -703,6 +712,8 @@ def run(w, hook=None):
     hook("app0", w)
     lam = w.p["fixed_lambda"]
     w.iterations_done = 0
+    w.accepted = []
+    lastL = calc_l_energy(w)
     for it in range(w.iterations):
         backup_state(w)
         if not solve_system(w, it, lam): return False
@@ -711,15 +722,18 @@ def run(w, hook=None):
         w.canbreak = canbreak
         hook(f"step{it}", w)
         new = linearize_all(w, False)
+        newL = calc_l_energy(w)
         hook(f"lin{it + 1}", w)
-        if not np.isfinite(new): return False
-        if new < last or w.p["force_accept"]:
-            apply_active_res(w); last = new; lam *= 0.25
+        if not np.isfinite(new + newL): return False
+        if new + newL < last + lastL or w.p["force_accept"]:
+            apply_active_res(w); last = new; lastL = newL; lam *= 0.25
+            w.accepted.append(1)
         else:
             for i in range(w.N): w._set_state(i, w.state_backup[i])
             w.idepth = w.idepth_backup.astype(np.float64); w.idepth_zero = w.idepth_backup.copy()
             compute_delta(w)
-            last = linearize_all(w, False); lam *= 1e2
+            last = linearize_all(w, False); lastL = calc_l_energy(w); lam *= 1e2
+            w.accepted.append(0)
         w.iterations_done = it + 1
         if canbreak and it >= 1: break
     # epilogue BA:885-896

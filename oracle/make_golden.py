@@ -72,7 +72,28 @@ def maintenance():
     print("maint window", os.path.getsize(os.path.join(OUT, "maint_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "maint_golden.cmlw")) // 1024, "KB")
 
 
+def rejection():
+    """forceAccept = false on a noisy window: the reference accepts two steps and rejects the rest (BA:843-877)."""
+    tmp = "/tmp/cmlba_golden"
+    os.makedirs(tmp, exist_ok=True)
+    win = synth.make_window(160, 120, 4, 60, 6, True, seed=5, pose_noise=3e-3, idepth_noise=0.05)
+    win["force_accept"] = np.array([0], np.int32)
+    full = os.path.join(tmp, "reject.cmlw")
+    cmlw.save(full, win)
+    run_ref(full, "run", os.path.join(tmp, "reject_run.cmlw"))
+    g = cmlw.load(os.path.join(tmp, "reject_run.cmlw"))
+    assert 0 < int(g["accepted_count"][0]) < 6, "the scenario must contain accepted AND rejected steps"
+    keep = {k: g[k] for k in ("accepted_count", "fin_ok", "fin_frame_pre_w2c", "fin_frame_affine", "fin_frame_state", "fin_frame_energy_th", "fin_pt_idepth", "fin_pt_alive",
+                              "fin_pt_num_good", "fin_pt_outlier", "fin_alive_res_point", "fin_alive_res_target", "fin_alive_res_state")}
+    slim = {k: v for k, v in win.items() if k not in ("grad", "truth_idepth")}
+    cmlw.save(os.path.join(OUT, "reject_window.cmlw"), slim)
+    cmlw.save(os.path.join(OUT, "reject_golden.cmlw"), keep)
+    print("reject window", os.path.getsize(os.path.join(OUT, "reject_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "reject_golden.cmlw")) // 1024, "KB")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "maintenance":
         maintenance(); sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "rejection":
+        rejection(); sys.exit(0)
     main()

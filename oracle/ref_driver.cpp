@@ -565,6 +565,8 @@ int main(int argc, char **argv) {
         double t1 = now_s();
         w->ba->mActiveResiduals.clear();
         out.scalar<double>("run_seconds", t1 - t0);
+        // one P-energy sample before the loop (BA:798) + one per ACCEPTED iteration (BA:847)
+        out.scalar<int32_t>("accepted_count", (int) w->ba->mStatisticEnergyP->mWaitingValues.size() - 1);
         dumpFinal(w, out, "fin_", ok);
         if (!outPath.empty()) out.save(outPath);
     } else if (mode == "maintain") {

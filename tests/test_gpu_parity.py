@@ -244,3 +244,26 @@ def test_empty_and_edge_windows():
     # a second run() on the surviving window keeps working (dropped residuals are gone, like the reference)
     assert ba.run(None, iterations=2)
     ba.close()
+
+
+def test_step_rejection_against_reference_golden():
+    """forceAccept = false (BA:843-877): accepted / rejected step counts and the final state vs the reference's run()."""
+    from libcml_b200 import cmlw, synth
+    from parity_util import GOLDEN
+    win = cmlw.load(os.path.join(GOLDEN, "reject_window.cmlw")); g = cmlw.load(os.path.join(GOLDEN, "reject_golden.cmlw"))
+    win["grad"] = np.stack([synth.gradient_image(win["gray"][i]) for i in range(win["gray"].shape[0])])
+    from libcml_b200 import DSOBundleAdjustment
+    ba = DSOBundleAdjustment(device=0, force_accept=0)
+    cams = ba.loadWindow(win)
+    assert ba.run(cams, iterations=int(win["iterations"][0])) == bool(g["fin_ok"][0])
+    r = ba.last_result
+    assert r.iterations_done - r.num_rejected == int(g["accepted_count"][0]) and r.num_rejected > 0
+    fr = ba.getFrames(); pts = ba.getPoints(); rs = ba.getResiduals()
+    assert rel(fr["world_to_cam"], g["fin_frame_pre_w2c"]) < 1e-4
+    assert np.abs(fr["affine"] - g["fin_frame_affine"]).max() < 1e-4 * max(1.0, np.abs(g["fin_frame_affine"]).max())
+    assert rel(fr["energy_th"], g["fin_frame_energy_th"]) < 1e-4
+    assert np.array_equal(np.sort(pts["id"]), np.nonzero(g["fin_pt_alive"])[0])
+    assert rel(pts["idepth"], g["fin_pt_idepth"][pts["id"]]) < 1e-3
+    assert np.array_equal(pts["num_good_residuals"], g["fin_pt_num_good"][pts["id"]])
+    assert set(zip(rs["point_id"].tolist(), rs["target_frame_id"].tolist())) == set(zip(g["fin_alive_res_point"].tolist(), g["fin_alive_res_target"].tolist()))
+    ba.close()

@@ -120,3 +120,19 @@ def test_gradient_image_definition():
     d = synth.gradient_image(g)
     assert d.shape == (5, 6, 3) and np.all(d[0] == 0) and np.all(d[:, 0] == 0) and np.all(d[-1] == 0) and np.all(d[:, -1] == 0)
     assert d[2, 2, 0] == g[2, 2] and d[2, 2, 1] == (g[2, 3] - g[2, 1]) * 0.5 and d[2, 2, 2] == (g[3, 2] - g[1, 2]) * 0.5
+
+
+def test_step_rejection_matches_reference():
+    """forceAccept = false: the restatement takes the reference's accept / reject decisions (BA:843-877, calcLEnergy BA:2118-2208)."""
+    import os
+    from libcml_b200 import cmlw
+    from parity_util import GOLDEN
+    from libcml_b200 import synth
+    win = cmlw.load(os.path.join(GOLDEN, "reject_window.cmlw")); g = cmlw.load(os.path.join(GOLDEN, "reject_golden.cmlw"))
+    win["grad"] = np.stack([synth.gradient_image(win["gray"][i]) for i in range(win["gray"].shape[0])])
+    w = O.Window(win)
+    assert O.run(w) == bool(g["fin_ok"][0])
+    assert sum(w.accepted) == int(g["accepted_count"][0]) and 0 in w.accepted
+    mine = np.stack([np.concatenate([R.ravel(), t]) for R, t in w.pre_w2c])
+    assert rel(mine, g["fin_frame_pre_w2c"]) < 1e-4
+    assert rel(w.idepth, g["fin_pt_idepth"]) < 1e-3
