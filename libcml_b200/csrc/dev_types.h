@@ -58,6 +58,7 @@ struct Ctrl {
     double prior_energy_pts;    // sum_p deltaF^2 * priorF (BA:2200) of the current point states
     int rejected_at;            // value of `iteration` right after the last rejected step (restore_state_kernel keys on it)
     int rejected;               // number of rejected steps
+    int pt_bad, pad1;           // non-finite point steps of this rank (point_step_kernel)
 };
 
 struct DevWin {
@@ -120,6 +121,11 @@ struct DevWin {
     double *pt_part;               // point-step partial sums [blocks][2]
     int n_pt_blocks;
     int update_points_only;
+    // multi-GPU (points sharded, frames replicated): every linearization all-gathers one record per rank
+    //   [energy, sumNID, numID, bad, prior_energy, 0, 0, 0 (doubles) | cand_cap candidate energies of the newest frame (floats, -1 = none)]
+    int world, rank, cand_cap;
+    double *post_send;             // this rank's record
+    const double *post_recv;       // world records
 };
 
 }  // namespace cmlba

@@ -222,6 +222,7 @@ public:
     int launches = 0;
     // multi-GPU
     void *comm = nullptr; int rank = 0, world = 1;
+    DevBuf<double> d_post_send, d_post_recv; DevBuf<int> d_cap;   // multi-GPU post-linearize exchange
 
     // device buffers
     DevBuf<FrameDev> d_frames; DevBuf<PairPre> d_pairs; DevBuf<Ctrl> d_ctrl;
@@ -276,6 +277,7 @@ public:
         // DevBuf members leak-free:
         DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_st_out, &d_sys, &d_x, &d_xAd, &d_pt_part};
         for (auto *b : dd) b->release();
+        d_post_send.release(); d_post_recv.release(); d_cap.release();
         DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_acc_chunk_bin, &d_acc_chunk_begin, &d_acc_chunk_count, &d_bin_chunk_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin};
         for (auto *b : di) b->release();
         DevBuf<float> *df[] = {&d_pt_x, &d_pt_y, &d_pt_idz, &d_pt_idb, &d_pt_colors, &d_pt_weights, &d_pt_priorF, &d_pt_Hdd, &d_pt_bd, &d_pt_Hcd, &d_pt_HdiF, &d_pt_bdSumF, &d_pt_idh, &d_pt_mrb,
@@ -728,6 +730,20 @@ public:
         w.host_chunk_begin = d_host_chunk_begin.p;
         w.st_out = d_st_out.p; w.sys = d_sys.p; w.x = d_x.p; w.xAd = d_xAd.p;
         w.pt_part = d_pt_part.p; w.n_pt_blocks = n_pt_blocks;
+        w.world = world; w.rank = rank; w.cand_cap = 0;
+        if (world > 1) {
+            // record capacity = the largest per-rank count of residuals towards the newest frame (one small all-reduce per window build)
+            int mine = R - newest_begin, cap = 0;
+            CK(d_cap.reserve(1));
+            CK(cudaMemcpyAsync(d_cap.p, &mine, sizeof(int), cudaMemcpyHostToDevice, stream));
+            if (g_nccl.AllReduce(d_cap.p, d_cap.p, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, comm, stream) != 0) { set_error("ncclAllReduce(max) failed"); return CMLBA_ERR_CUDA; }
+            CK(cudaMemcpyAsync(&cap, d_cap.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            w.cand_cap = std::max(cap, 1);
+            const size_t rec_d = 8 + (size_t) (w.cand_cap + 1) / 2;
+            CK(d_post_send.reserve(rec_d)); CK(d_post_recv.reserve(rec_d * world));
+            w.post_send = d_post_send.p; w.post_recv = d_post_recv.p;
+        }
         dirty = false;
         return CMLBA_OK;
     }
@@ -889,7 +905,14 @@ public:
         else linearize_kernel<false><<<dw.n_acc_chunks, LIN_THREADS, LIN_SMEM, stream>>>(dw, fix, respect_done);
         launches++;
     }
-    void launch_post(int mode, int respect_done) { post_linearize_kernel<<<1, 1024, 0, stream>>>(dw, mode, respect_done); launches++; }
+    void launch_post(int mode, int respect_done) {
+        if (world > 1) {   // energy, convergence sums and the 0.7-quantile inputs of ALL ranks: one all-gather per linearization
+            pack_post_kernel<<<1, 1024, 0, stream>>>(dw, respect_done); launches++;
+            const size_t rec_d = 8 + (size_t) (dw.cand_cap + 1) / 2;
+            if (g_nccl.AllGather(d_post_send.p, d_post_recv.p, rec_d, /*ncclDouble*/ 8, comm, stream) != 0) set_error("ncclAllGather failed");
+        }
+        post_linearize_kernel<<<1, 1024, 0, stream>>>(dw, mode, respect_done); launches++;
+    }
     void launch_schur(int respect_done) {
         if (dw.n_sc_chunks > 0) { schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, respect_done); launches++; }
     }

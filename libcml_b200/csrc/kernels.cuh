@@ -971,8 +971,9 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
         tn = warp_sum_d(tn); tc = warp_sum_d(tc); tb = warp_sum_d(tb); tpe = warp_sum_d(tpe);
     if (threadIdx.x == 0) {
         ctrl->prior_energy_pts = tpe;
+        ctrl->sumNID = tn; ctrl->numID = (int) tc; ctrl->pt_bad = (int) tb;
+        if (w.world > 1) { ctrl->sc_done_count = 0; return; }          // decided on the all-gathered sums in post_linearize_kernel
         const float sumNID = (float) (tn / (tc > 0 ? tc : 1.0));
-        ctrl->sumNID = tn; ctrl->numID = (int) tc;
         const float th = w.th_opt;
         ctrl->canbreak = (sqrtf(ctrl->sumA) < 0.0005f * th && sqrtf(ctrl->sumB) < 0.00005f * th && sqrtf(ctrl->sumR) < 0.00005f * th &&
                           sqrtf(ctrl->sumT) * sumNID < 0.00005f * th) ? 1 : 0;
@@ -993,13 +994,24 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
     __shared__ double s_red[32];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_prefix, s_k, s_n;
-    // energy: fixed-order sum of the block partials
+    const bool multi = w.world > 1;
+    const size_t rec_d = 8 + (size_t) (w.cand_cap + 1) / 2;             // doubles per rank record
+    // energy: fixed-order sum of the block partials (multi-GPU: of the ranks' sums, all-gathered by pack_post_kernel)
     double e = 0.0;
-    for (int i = tid; i < w.n_lin_blocks; i += 1024) e += w.energy_part[i];
+    if (!multi) for (int i = tid; i < w.n_lin_blocks; i += 1024) e += w.energy_part[i];
+    else if (tid < w.world) e = w.post_recv[tid * rec_d];
     e = warp_sum_d(e);
     if ((tid & 31) == 0) s_red[tid >> 5] = e;
     __syncthreads();
     if (tid == 0) { double t = 0; for (int k = 0; k < 32; k++) t += s_red[k]; s_red[0] = t; }
+    // candidate list: local residuals towards the newest frame, or the gathered records
+    const int c_begin = multi ? 0 : w.newest_begin, c_end = multi ? w.world * w.cand_cap : w.R;
+    auto cand_at = [&](int i, bool &alive_i) -> float {
+        if (!multi) { alive_i = w.r_alive[i] != 0; return w.r_new_energy_wo[i]; }
+        const int rk = i / w.cand_cap, k = i - rk * w.cand_cap;
+        alive_i = true;
+        return reinterpret_cast<const float *>(w.post_recv + rk * rec_d + 8)[k];
+    };
     // candidates: energies >= 0 of alive residuals whose target is the newest frame.  Each thread keeps up to PL_CACHE of
     // them in registers (one exposed load latency for the count + the four radix passes); longer tails are re-read.
     constexpr int PL_CACHE = 16;
@@ -1010,15 +1022,14 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
     unsigned int cnt = 0;
 #pragma unroll
     for (int k = 0; k < PL_CACHE; k++) {
-        const int i = w.newest_begin + tid + k * 1024;
-        const bool in = i < w.R;
-        const uint8_t al = in ? w.r_alive[i] : (uint8_t) 0;
-        const float v = in ? w.r_new_energy_wo[i] : -1.f;
+        const int i = c_begin + tid + k * 1024;
+        bool al = false; float v = -1.f;
+        if (i < c_end) v = cand_at(i, al);
         cache[k] = al ? v : -1.f;
     }
 #pragma unroll
     for (int k = 0; k < PL_CACHE; k++) cnt += cache[k] >= 0.f ? 1u : 0u;
-    for (int i = w.newest_begin + tid + PL_CACHE * 1024; i < w.R; i += 1024) cnt += (w.r_alive[i] && w.r_new_energy_wo[i] >= 0.f) ? 1u : 0u;
+    for (int i = c_begin + tid + PL_CACHE * 1024; i < c_end; i += 1024) { bool al; const float v = cand_at(i, al); cnt += (al && v >= 0.f) ? 1u : 0u; }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
     if ((tid & 31) == 0 && cnt) atomicAdd(&s_n, cnt);
     __syncthreads();
@@ -1040,9 +1051,9 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
                 const unsigned int u = __float_as_uint(cache[k]);
                 if (cache[k] >= 0.f && (u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
             }
-            for (int i = w.newest_begin + tid + PL_CACHE * 1024; i < w.R; i += 1024) {
-                const float v = w.r_new_energy_wo[i];
-                if (w.r_alive[i] && v >= 0.f) {
+            for (int i = c_begin + tid + PL_CACHE * 1024; i < c_end; i += 1024) {
+                bool al; const float v = cand_at(i, al);
+                if (al && v >= 0.f) {
                     const unsigned int u = __float_as_uint(v);
                     if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
                 }
@@ -1075,6 +1086,17 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
     }
     if (tid == 0) {
         ctrl->energy_new = energy;
+        if (multi && mode == 1) {
+            // doStepFromBackup's convergence test (BA:1013-1026) and failure flag on the sums over all ranks
+            double tn = 0, tc = 0, tb = 0, tpe = 0;
+            for (int rk = 0; rk < w.world; rk++) { const double *h = w.post_recv + rk * rec_d; tn += h[1]; tc += h[2]; tb += h[3]; tpe += h[4]; }
+            const float sumNID = (float) (tn / (tc > 0 ? tc : 1.0));
+            const float th = w.th_opt;
+            ctrl->canbreak = (sqrtf(ctrl->sumA) < 0.0005f * th && sqrtf(ctrl->sumB) < 0.00005f * th && sqrtf(ctrl->sumR) < 0.00005f * th &&
+                              sqrtf(ctrl->sumT) * sumNID < 0.00005f * th) ? 1 : 0;
+            ctrl->prior_energy_pts = tpe;
+            if (tb > 0) { ctrl->failed = 1; ctrl->done = 1; }
+        }
         // calcLEnergy (BA:2118-2208) without linearized residuals: frame priors + point priors; calcMEnergy (BA:2095-2116) is 0 (H_M = 0)
         double EL = 0.0;
         if (!w.force_accept) {
@@ -1098,6 +1120,31 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
             if (ctrl->canbreak && it >= 1) ctrl->done = 1;             // BA:879
         } else if (mode == 2) { ctrl->cur ^= 1; ctrl->energy_last = energy; }
         if (!keep_th) w.frames[w.N - 1].energy_th = th_new;            // a rejected linearization leaves frameEnergyTH as the re-linearization would
+    }
+}
+
+// multi-GPU: this rank's record for the all-gather that precedes post_linearize_kernel (see DevWin::post_send)
+__global__ void __launch_bounds__(1024) pack_post_kernel(const DevWin w, const int respect_done) {
+    Ctrl *ctrl = w.ctrl;
+    (void) respect_done;   // always packs: every rank must feed the collective, even after its own early exit
+    const int tid = threadIdx.x;
+    __shared__ double s_red[32];
+    double e = 0.0;
+    for (int i = tid; i < w.n_lin_blocks; i += 1024) e += w.energy_part[i];
+    e = warp_sum_d(e);
+    if ((tid & 31) == 0) s_red[tid >> 5] = e;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0; for (int k = 0; k < 32; k++) t += s_red[k];
+        double *h = w.post_send;
+        h[0] = t; h[1] = ctrl->sumNID; h[2] = (double) ctrl->numID; h[3] = (double) ctrl->pt_bad; h[4] = ctrl->prior_energy_pts; h[5] = h[6] = h[7] = 0.0;
+    }
+    float *c = reinterpret_cast<float *>(w.post_send + 8);
+    const int nloc = w.R - w.newest_begin;
+    for (int k = tid; k < w.cand_cap; k += 1024) {
+        float v = -1.f;
+        if (k < nloc) { const int i = w.newest_begin + k; v = w.r_alive[i] ? w.r_new_energy_wo[i] : -1.f; }
+        c[k] = v;
     }
 }
 

@@ -1,0 +1,83 @@
+"""Multi-GPU parity (run under torchrun, one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/multi_gpu_check.py
+Points are sharded over the ranks, frames/images replicated.  Every rank must take exactly the decisions of the
+single-GPU run (iterations, residual states, outliers) and land on the same poses / inverse depths up to summation order."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+from libcml_b200 import DSOBundleAdjustment, synth
+
+
+def comm_init(ba, rank, world):
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = np.zeros(128, dtype=np.uint8)
+        ba._ck(ba.lib.cmlba_nccl_unique_id(buf.ctypes.data))
+        uid = torch.from_numpy(buf)
+    uid = uid.cuda()
+    dist.broadcast(uid, 0)
+    ub = uid.cpu().numpy()
+    ba._ck(ba.lib.cmlba_comm_init(ba.h, ub.ctypes.data, rank, world))
+
+
+def build(ba, win, sel):
+    W, H = int(win["size"][0]), int(win["size"][1])
+    ba.setCalibration(*[float(v) for v in win["calib"]], W, H)
+    N = win["frame_evalpt"].shape[0]
+    for i in range(N):
+        ba.addNewFrame(i, win["frame_evalpt"][i], win["frame_affine"][i, 0], win["frame_affine"][i, 1], win["frame_exposure"][i], win["grad"][i], False)
+    ba.addPoints(sel, win["pt_host"][sel], win["pt_xy"][sel], win["pt_idepth"][sel])
+
+
+def main():
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    win = synth.make_window(W=320, H=240, N=5, pts_per_kf=400, iterations=5, affine=True, seed=11, pose_noise=2e-3, idepth_noise=0.02)
+    P = win["pt_host"].size
+    sel = np.arange(P)[np.arange(P) % world == rank]
+    ba = DSOBundleAdjustment(device=local, iterations=5)
+    comm_init(ba, rank, world)
+    build(ba, win, sel)
+    ok = ba.run(win["frame_cam"])
+    r = ba.last_result
+    fr = ba.getFrames(); pts = ba.getPoints(); rs = ba.getResiduals()
+    # single-GPU truth on every rank (no communicator)
+    ref = DSOBundleAdjustment(device=local, iterations=5)
+    build(ref, win, np.arange(P))
+    ok1 = ref.run(win["frame_cam"])
+    r1 = ref.last_result
+    fr1 = ref.getFrames(); pts1 = ref.getPoints(); rs1 = ref.getResiduals()
+    rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-30))
+    errs = []
+    if ok != ok1: errs.append("ok flag")
+    if r.iterations_done != r1.iterations_done: errs.append(f"iterations {r.iterations_done} vs {r1.iterations_done}")
+    e_pose = rel(fr["world_to_cam"], fr1["world_to_cam"]); e_aff = float(np.abs(fr["affine"] - fr1["affine"]).max()); e_th = rel(fr["energy_th"], fr1["energy_th"])
+    if e_pose > 1e-6: errs.append(f"poses {e_pose:.2e}")
+    if e_aff > 1e-6: errs.append(f"affine {e_aff:.2e}")
+    if e_th > 1e-6: errs.append(f"frameEnergyTH {e_th:.2e}")
+    idx1 = {int(i): k for k, i in enumerate(pts1["id"])}
+    mine_ids = [int(i) for i in pts["id"]]
+    missing = [i for i in mine_ids if i not in idx1]
+    if missing: errs.append(f"{len(missing)} points alive here but not in the single-GPU run")
+    sel1 = np.array([idx1[i] for i in mine_ids if i in idx1], dtype=np.int64)
+    e_id = rel(pts["idepth"][[k for k, i in enumerate(mine_ids) if i in idx1]], pts1["idepth"][sel1]) if sel1.size else 0.0
+    if e_id > 1e-5: errs.append(f"idepth {e_id:.2e}")
+    own = set(int(i) for i in sel)
+    mine_res = set(zip(rs["point_id"].tolist(), rs["target_frame_id"].tolist()))
+    their_res = set((p, t) for p, t in zip(rs1["point_id"].tolist(), rs1["target_frame_id"].tolist()) if p in own)
+    if len(mine_res ^ their_res) > 0: errs.append(f"{len(mine_res ^ their_res)} residuals differ")
+    e_en = abs(r.energy_last - r1.energy_last) / r1.energy_last
+    if e_en > 1e-6: errs.append(f"energy {e_en:.2e}")
+    print(f"rank {rank}/{world}: iterations {r.iterations_done}, poses {e_pose:.2e}, affine {e_aff:.2e}, th {e_th:.2e}, idepth {e_id:.2e}, energy {e_en:.2e}, "
+          f"residuals {len(mine_res)} (diff {len(mine_res ^ their_res)}), launches {r.kernel_launches}: {'OK' if not errs else 'FAIL ' + '; '.join(errs)}", flush=True)
+    flag = torch.tensor([len(errs)], device="cuda"); dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(1 if int(flag.item()) else 0)
+
+
+if __name__ == "__main__":
+    main()
