@@ -65,6 +65,11 @@ typedef struct cmlba_config {
     int max_frames;             /* "maxFrames" 6: flagFramesForMarginalization keeps at most this many frames (BA:649) */
     int frame_min_age;          /* "frameMinAge" 1 (BA:658-680) */
     float min_idepth_h_marg;    /* "Minimum iDepth Hessian Marginlaization" 50 (BA:2318) */
+    int async_image_upload;     /* not a reference parameter.  0 (default): cmlba_add_frame returns after the image has left the caller's
+                                 * buffer.  1: the host->device copy is only enqueued; the caller keeps `grad` valid and unmodified until
+                                 * the next cmlba_add_points / cmlba_prepare / cmlba_run returns (CML pins a keyframe's GradientImage for as
+                                 * long as the frame is active, capture/CaptureImage.cpp:269-362), so uploads overlap the host bookkeeping.
+                                 * Needs page-locked memory to have an effect. */
 } cmlba_config;
 
 /* Fills *cfg with the reference defaults. */

@@ -29,7 +29,7 @@ class Config(C.Structure):
                 ("scale_rotation", C.c_float), ("scale_translation", C.c_float), ("scale_light_a", C.c_float), ("scale_light_b", C.c_float),
                 ("scale_f", C.c_float), ("scale_c", C.c_float), ("force_accept", C.c_int), ("fix_lambda", C.c_int), ("fixed_lambda", C.c_float),
                 ("idepth_fix_prior", C.c_int), ("solver_mode_delta", C.c_float), ("optimize_light_a", C.c_int), ("optimize_light_b", C.c_int),
-                ("disable_marginalization", C.c_int), ("max_frames", C.c_int), ("frame_min_age", C.c_int), ("min_idepth_h_marg", C.c_float)]
+                ("disable_marginalization", C.c_int), ("max_frames", C.c_int), ("frame_min_age", C.c_int), ("min_idepth_h_marg", C.c_float), ("async_image_upload", C.c_int)]
 
 
 class RunResult(C.Structure):

@@ -230,7 +230,7 @@ public:
     DevBuf<int> d_pt_host, d_pt_num_good, d_pt_ngood_cur, d_r_point, d_acc_chunk_bin, d_acc_chunk_begin, d_acc_chunk_count, d_bin_chunk_begin, d_sc_chunk_host,
         d_sc_chunk_begin, d_sc_chunk_count, d_host_chunk_begin;
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
-        d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj, d_T0, d_T1, d_dbg, d_acc0, d_acc1, d_sc_part, d_stage[2];
+        d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj, d_T0, d_T1, d_dbg, d_acc0, d_acc1, d_sc_part, d_stage[MAXF];
     int stage_flip = 0;
     cudaEvent_t ev_copy = nullptr;
     UploadArena up;                               // every array build_device_window uploads
@@ -281,8 +281,9 @@ public:
         DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_acc_chunk_bin, &d_acc_chunk_begin, &d_acc_chunk_count, &d_bin_chunk_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin};
         for (auto *b : di) b->release();
         DevBuf<float> *df[] = {&d_pt_x, &d_pt_y, &d_pt_idz, &d_pt_idb, &d_pt_colors, &d_pt_weights, &d_pt_priorF, &d_pt_Hdd, &d_pt_bd, &d_pt_Hcd, &d_pt_HdiF, &d_pt_bdSumF, &d_pt_idh, &d_pt_mrb,
-                               &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj, &d_T0, &d_T1, &d_dbg, &d_acc0, &d_acc1, &d_sc_part, &d_stage[0], &d_stage[1]};
+                               &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj, &d_T0, &d_T1, &d_dbg, &d_acc0, &d_acc1, &d_sc_part};
         for (auto *b : df) b->release();
+        for (auto &b : d_stage) b.release();
         DevBuf<uint8_t> *du[] = {&d_r_host, &d_r_target, &d_r_state0, &d_r_state1, &d_r_good0, &d_r_good1, &d_r_new_state, &d_r_alive};
         for (auto *b : du) b->release();
         d_frames.release(); d_pairs.release(); d_ctrl.release();
@@ -332,7 +333,9 @@ public:
         // image: AoS (I,dx,dy) -> float4 texels on the device.  The caller's buffer is only ours for the duration
         // of the call: wait for the H2D copy (event), the repack kernel stays asynchronous on the stream.
         const size_t npix = (size_t) W * H;
-        const int sb = stage_flip; stage_flip ^= 1;                 // two staging buffers: the previous repack may still run
+        // staging buffers: with synchronous uploads two alternate (the previous repack may still run); asynchronous uploads
+        // keep one per window slot, because several copies are in flight
+        const int sb = cfg.async_image_upload ? (int) frames_.size() : (stage_flip ^= 1);
         CK(d_stage[sb].reserve(npix * 3));
         if (!img_pool.empty()) { f.d_img = img_pool.back(); img_pool.pop_back(); } else CK(cudaMalloc(&f.d_img, npix * sizeof(float4)));
         CK(cudaMemcpyAsync(d_stage[sb].p, grad, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
@@ -348,7 +351,7 @@ public:
             points_[p].last_frame[1] = points_[p].last_frame[0]; points_[p].last_state[1] = points_[p].last_state[0];
             points_[p].last_frame[0] = id; points_[p].last_state[0] = CMLBA_RES_IN;
         }
-        CK(cudaEventSynchronize(ev_copy));
+        if (!cfg.async_image_upload) CK(cudaEventSynchronize(ev_copy));
         dirty = true; prepared = false;
         return CMLBA_OK;
     }
@@ -1224,7 +1227,7 @@ int cmlba_default_config(cmlba_config *c) {
     c->iterations = 4; c->huber_threshold = 9.f; c->outlier_th_sum = 2500.f; c->th_opt_iterations = 1.2f;
     c->scale_rotation = 1.f; c->scale_translation = 0.5f; c->scale_light_a = 10.f; c->scale_light_b = 1000.f; c->scale_f = 50.f; c->scale_c = 50.f;
     c->force_accept = 1; c->fix_lambda = 1; c->fixed_lambda = 1e-5f; c->idepth_fix_prior = 2500; c->solver_mode_delta = 1e-5f;
-    c->optimize_light_a = 1; c->optimize_light_b = 1; c->disable_marginalization = 1; c->max_frames = 6; c->frame_min_age = 1; c->min_idepth_h_marg = 50.f;
+    c->optimize_light_a = 1; c->optimize_light_b = 1; c->disable_marginalization = 1; c->max_frames = 6; c->frame_min_age = 1; c->min_idepth_h_marg = 50.f; c->async_image_upload = 0;
     return CMLBA_OK;
 }
 

@@ -744,14 +744,18 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
     for (int e = tid; e < m * m; e += 256) { const int r = e / m, c = e % m; if (r >= c) AA(r, c) = AA(r, c) * s[4 + r] * s[4 + c]; }
     for (int e = tid; e < m; e += 256) x[e] = s[4 + e] * b[4 + e];
     __syncthreads();
-    // LDL^T without pivoting (SPD after damping + priors), right-looking in panels of 8 columns (= one frame):
-    //   (1) one warp factors the 8x8 diagonal block in registers, (2) one thread per row below solves its panel row,
+    // LDL^T without pivoting (SPD after damping + priors), right-looking in panels of 8 columns (= one frame).  The right-hand
+    // side rides along as an extra row, so the forward substitution L y = rhs costs no pass of its own:
+    //   (1) warp 0 factors the 8x8 diagonal block in registers (shuffles) and forward-substitutes the panel's 8 rhs entries,
+    //   (2) one thread per row below solves its panel row (operands preloaded: the chain is 36 dependent FMAs) and updates its rhs,
     //   (3) rank-8 update of the trailing lower triangle in 4x4 register tiles.  Three barriers per panel.
+    double *blk = red;          // [64] L11[c][j] * d_j of the current panel (j < c), reused every panel
     for (int k0 = 0; k0 < m; k0 += 8) {
         if (wid == 0) {
             double a[8];
 #pragma unroll
             for (int c = 0; c < 8; c++) a[c] = (lane < 8 && c <= lane) ? AA(k0 + lane, k0 + c) : 0.0;
+            double xv = lane < 8 ? x[k0 + lane] : 0.0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const double dk = __shfl_sync(0xffffffffu, a[k], k);
@@ -759,6 +763,9 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
                 if (lane == k) invd[k0 + k] = idk;
                 const double lrk = a[k] * idk;
                 if (lane > k) a[k] = lrk;
+                const double yk = __shfl_sync(0xffffffffu, xv, k);  // y_k is final once the pivots 0..k-1 have been applied
+                if (lane > k && lane < 8) xv -= lrk * yk;
+                if (lane > k && lane < 8) blk[lane * 8 + k] = lrk * dk;
 #pragma unroll
                 for (int c = k + 1; c < 8; c++) {
                     const double lck = __shfl_sync(0xffffffffu, a[k], c);
@@ -767,21 +774,31 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
             }
 #pragma unroll
             for (int c = 0; c < 8; c++) if (lane < 8 && c <= lane) AA(k0 + lane, k0 + c) = a[c];
+            if (lane < 8) x[k0 + lane] = xv;
         }
         __syncthreads();
         const int rem = m - k0 - 8;
         if (tid < rem) {
             const int r = k0 + 8 + tid;
-            double l[8];
+            double ld[28], idv[8], yv[8], l[8], ar[8];
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                double v = AA(r, k0 + c);
+            for (int c = 1, q = 0; c < 8; c++)
 #pragma unroll
-                for (int jj = 0; jj < c; jj++) v -= l[jj] * AA(k0 + jj, k0 + jj) * AA(k0 + c, k0 + jj);
-                l[c] = v * invd[k0 + c];
+                for (int jj = 0; jj < c; jj++, q++) ld[q] = blk[c * 8 + jj];
+#pragma unroll
+            for (int c = 0; c < 8; c++) { idv[c] = invd[k0 + c]; yv[c] = x[k0 + c]; ar[c] = AA(r, k0 + c); }
+            double xr = x[r];
+#pragma unroll
+            for (int c = 0, q = 0; c < 8; c++) {
+                double v = ar[c];
+#pragma unroll
+                for (int jj = 0; jj < c; jj++, q++) v -= l[jj] * ld[q];
+                l[c] = v * idv[c];
+                xr -= l[c] * yv[c];
             }
 #pragma unroll
             for (int c = 0; c < 8; c++) AA(r, k0 + c) = l[c];
+            x[r] = xr;
         }
         __syncthreads();
         const int nt = rem >> 2, ntiles = nt * (nt + 1) / 2;
@@ -814,35 +831,28 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
         }
         __syncthreads();
     }
-    // forward L y = rhs (panel by panel), z = y / d, backward L^T x = z
-    for (int k0 = 0; k0 < m; k0 += 8) {
-        if (tid == 0) {
-#pragma unroll
-            for (int c = 1; c < 8; c++) { double v = x[k0 + c]; for (int jj = 0; jj < c; jj++) v -= AA(k0 + c, k0 + jj) * x[k0 + jj]; x[k0 + c] = v; }
-        }
-        __syncthreads();
-        const int r = k0 + 8 + tid;
-        if (r < m) {
-            double v = x[r];
-#pragma unroll
-            for (int jj = 0; jj < 8; jj++) v -= AA(r, k0 + jj) * x[k0 + jj];
-            x[r] = v;
-        }
-        __syncthreads();
-    }
+    // z = y / d, then backward L^T x = z: column dots over the rows below (one warp per column), 8x8 block by shuffles
     for (int e = tid; e < m; e += 256) x[e] = x[e] * invd[e];
     __syncthreads();
     for (int k0 = m - 8; k0 >= 0; k0 -= 8) {
-        {   // warp c: x[k0+c] -= sum_{r >= k0+8} L[r][k0+c] x[r]
+        {   // warp c: sum_{r >= k0+8} L[r][k0+c] x[r]
             double part = 0.0;
             for (int r = k0 + 8 + lane; r < m; r += 32) part += AA(r, k0 + wid) * x[r];
             part = warp_sum_d(part);
-            if (lane == 0) red[wid] = part;
+            if (lane == 0) red[128 + wid] = part;
         }
         __syncthreads();
-        if (tid == 0) {
+        if (wid == 0) {
+            double lc[8];   // column `lane` of the unit lower block: L[j][lane], j > lane
 #pragma unroll
-            for (int c = 7; c >= 0; c--) { double v = x[k0 + c] - red[c]; for (int jj = c + 1; jj < 8; jj++) v -= AA(k0 + jj, k0 + c) * x[k0 + jj]; x[k0 + c] = v; }
+            for (int j = 1; j < 8; j++) lc[j] = (lane < 8 && j > lane) ? AA(k0 + j, k0 + lane) : 0.0;
+            double v = lane < 8 ? x[k0 + lane] - red[128 + lane] : 0.0;
+#pragma unroll
+            for (int j = 7; j >= 1; j--) {
+                const double xj = __shfl_sync(0xffffffffu, v, j);
+                if (lane < j) v -= lc[j] * xj;
+            }
+            if (lane < 8) x[k0 + lane] = v;
         }
         __syncthreads();
     }
@@ -900,8 +910,11 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
     for (int e = tid; e < N * N * 8; e += 256) {
         const int ht = e >> 3, c = e & 7, h = ht / N, t = ht % N;
         const double *ah = w.AH + (size_t) ht * 64, *at = w.AT + (size_t) ht * 64;
-        double v = 0.0;
-        for (int r = 0; r < 8; r++) v += b[4 + 8 * h + r] * ah[r * 8 + c] + b[4 + 8 * t + r] * at[r * 8 + c];
+        double v = 0.0, pa[8], pt[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) { pa[r] = ah[r * 8 + c]; pt[r] = at[r * 8 + c]; }      // 16 independent loads in flight
+#pragma unroll
+        for (int r = 0; r < 8; r++) v += b[4 + 8 * h + r] * pa[r] + b[4 + 8 * t + r] * pt[r];
         w.xAd[e] = v;
     }
     for (int e = tid; e < N * N; e += 256) pair_precompute(w, e / N, e % N);
