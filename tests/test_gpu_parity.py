@@ -162,9 +162,9 @@ def _ref_runs():
         return False
 
 
-@pytest.mark.parametrize("cfg", ["c1", "c2"])
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4"])
 def test_against_reference_binary_full_size(cfg, tmp_path):
-    """BASELINE.json configs[0] and configs[1] at full size against the reference binary run HERE on the host CPU."""
+    """BASELINE.json configs[0..3] at full size (c4: 16 KF, 720 000 residuals) against the reference binary run HERE on the host CPU."""
     if not _ref_runs():
         pytest.skip("oracle/_ref/cmlba_ref not runnable on this host")
     from libcml_b200 import cmlw, synth
