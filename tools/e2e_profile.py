@@ -12,7 +12,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 W, H, N, ppk, iters, affine = synth.CONFIGS[wl]
 win = synth.make_config(wl, seed=1234)
 P = win["pt_host"].size
-ba = DSOBundleAdjustment(device=0, iterations=iters)
+ba = DSOBundleAdjustment(device=0, iterations=iters, async_image_upload=1)
 cams = win["frame_cam"]
 gnp = torch.from_numpy(win["grad"]).pin_memory().numpy()
 acc = {}
