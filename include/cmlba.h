@@ -107,9 +107,8 @@ int cmlba_remove_frame(cmlba_handle *h, int64_t frame_id);
 /* ---- window maintenance around run() (Hybrid::directMap, slam/modslam/direct/Mapping.cpp:61-100) ----
  * The decisions (which frames / points leave the window, the per-frame counters they depend on) follow the reference
  * exactly.  The marginalisation PRIOR H_M,b_M that marginalizePointsF / marginalizeFrame fold the leaving variables into
- * (BA:2500-2508, 520-548) is not accumulated: with the default disableMarginalization=true the reference zeroes it
- * before every solve (BA:1395-1398), so it never reaches a result.  cmlba_create fails with CMLBA_ERR_UNSUPPORTED when
- * disable_marginalization == 0.
+ * (BA:2500-2508, 520-548) is only maintained when disable_marginalization == 0: with the default (true) the reference
+ * zeroes it before every solve (BA:1395-1398), so it never reaches a result and is skipped here.
  *
  * cmlba_flag_frames_for_marginalization   flagFramesForMarginalization (BA:603-708).  The reference runs it at the top of
  *      addNewFrame (BA:428), i.e. call it BEFORE cmlba_add_frame of the new keyframe.  cams = current Frame::getCamera()
@@ -118,9 +117,11 @@ int cmlba_remove_frame(cmlba_handle *h, int64_t frame_id);
  * cmlba_try_marginalize     tryMarginalize (BA:2240-2363) + isOOB (BA:2515-2554): points to drop go to getOutliers()
  *      and leave the window; points to marginalise are marked (DSOTOMARGINALIZE).
  * cmlba_marginalize_points  marginalizePointsF (BA:2466-2513): marked points leave the window as marginalised
- *      (numMarginalized / numResidualsOut counters of DSOContext.h:99-110, 221-229); ids out.
+ *      (numMarginalized / numResidualsOut counters of DSOContext.h:99-110, 221-229); ids out.  With a live prior they are
+ *      first re-linearised and accumulated in MARGINALIZED mode on the device: H_M += 1/4 (M - M_sc).
  * cmlba_marginalize_frames  marginalizeFrames (BA:710-742) -> marginalizeFrame -> removeFrame: flagged frames leave,
- *      with the points they host and the residuals that target them; ids out. */
+ *      with the points they host and the residuals that target them; ids out.  With a live prior the frame's block is
+ *      Schur-complemented out of H_M first (BA:464-548). */
 int cmlba_flag_frames_for_marginalization(cmlba_handle *h, const double *cams /*[n][12] or NULL*/, const int32_t *num_immature /*[n] or NULL*/,
                                           int64_t *flagged_ids, int *n_flagged);
 int cmlba_try_marginalize(cmlba_handle *h, int *n_dropped, int *n_to_marginalize);

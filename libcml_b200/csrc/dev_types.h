@@ -121,6 +121,8 @@ struct DevWin {
     double *pt_part;               // point-step partial sums [blocks][2]
     int n_pt_blocks;
     int update_points_only;
+    int marg_mode;                 // 1: marginalizePointsF pass (BA:2466-2513): residual vectors res_toZeroF = resF - J*delta (fixLinearization, BA:2210-2238), no prior shift in the Schur step
+    const float *pair_delta;       // [h*N+t][8] adHTdeltaF (computeDelta, BA:1105-1117)
     // multi-GPU (points sharded, frames replicated): every linearization all-gathers one record per rank
     //   [energy, sumNID, numID, bad, prior_energy, 0, 0, 0 (doubles) | cand_cap candidate energies of the newest frame (floats, -1 = none)]
     int world, rank, cand_cap;

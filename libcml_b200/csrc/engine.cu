@@ -215,7 +215,9 @@ public:
     int key_counter = 0;
     bool dirty = true;            // device window must be rebuilt
     bool prepared = false;
-    std::vector<double> HM, bM;   // marginalisation prior, (8N+4)^2 ; zero in this round
+    std::vector<double> HM, bM;   // marginalisation prior mMarginalizedHessian / mMarginalizedB, (8N+4)^2 and 8N+4 (only kept when !disable_marginalization)
+    bool hm_frame_done = false;           // marginalize_frames already folded the frame into H_M (remove_frame must not drop the block again)
+    bool subset_to_marginalize = false;   // build_device_window keeps only the points marked DSOTOMARGINALIZE (marginalize_points)
     // device-window layout (host mirrors)
     std::vector<int> pt_order;    // device point i -> points_ index
     DevWin dw;
@@ -344,6 +346,7 @@ public:
         CK(cudaGetLastError());
         const int slot = (int) frames_.size();
         frames_.push_back(f);
+        if (keep_prior()) hm_grow();
         // residuals from all existing points to the new frame (BA:455-460); lastResiduals slot 0 (BA:374-375)
         for (size_t p = 0; p < points_.size(); p++) {
             if (!points_[p].alive) continue;
@@ -471,10 +474,67 @@ public:
         }
         cudaSetDevice(device);
         cudaStreamSynchronize(stream);
+        if (keep_prior() && !hm_frame_done) hm_drop(fi, 8 * (int) frames_.size() + 4);
         if (frames_[fi].d_img) img_pool.push_back(frames_[fi].d_img);
         frames_.erase(frames_.begin() + fi);
         maybe_compact();
         return CMLBA_OK;
+    }
+
+    // ------------------------------------------------------------------ marginalisation prior H_M, b_M (host, fp64)
+    bool keep_prior() const { return !cfg.disable_marginalization; }
+    void hm_fit(int n) { if ((int) HM.size() != n * n) { HM.assign((size_t) n * n, 0.0); bM.assign(n, 0.0); } }
+    // addNewFrame: conservativeResize + zero tail (BA:438-443)
+    void hm_grow() {
+        const int n = 8 * (int) frames_.size() + 4, o = n - 8;
+        std::vector<double> H((size_t) n * n, 0.0), b(n, 0.0);
+        if ((int) HM.size() == o * o) { for (int r = 0; r < o; r++) { memcpy(&H[(size_t) r * n], &HM[(size_t) r * o], o * sizeof(double)); b[r] = bM[r]; } }
+        HM.swap(H); bM.swap(b);
+    }
+    // plain removal of a frame's 8 rows / columns (cmlba_remove_frame)
+    void hm_drop(int fi, int n) {
+        if ((int) HM.size() != n * n) return;
+        const int io = 4 + 8 * fi, m = n - 8;
+        std::vector<double> H((size_t) m * m), b(m);
+        auto src = [&](int i) { return i < io ? i : i + 8; };
+        for (int r = 0; r < m; r++) { b[r] = bM[src(r)]; for (int c = 0; c < m; c++) H[(size_t) r * m + c] = HM[(size_t) src(r) * n + src(c)]; }
+        HM.swap(H); bM.swap(b);
+    }
+    // marginalizeFrame (BA:464-548): move the frame's block to the end, add its prior, Jacobi-scale, Schur-complement the
+    // 8x8 block out, unscale, symmetrise.
+    void hm_marginalize_frame(int fi) {
+        const int N = (int) frames_.size(), n = 8 * N + 4, m = n - 8, io = 4 + 8 * fi;
+        hm_fit(n);
+        std::vector<int> perm(n);
+        for (int i = 0; i < n; i++) perm[i] = i < io ? i : (i < m ? i + 8 : io + (i - m));
+        std::vector<double> H((size_t) n * n), b(n);
+        for (int r = 0; r < n; r++) { b[r] = bM[perm[r]]; for (int c = 0; c < n; c++) H[(size_t) r * n + c] = HM[(size_t) perm[r] * n + perm[c]]; }
+        const FrameHost &f = frames_[fi];
+        for (int k = 0; k < 8; k++) { H[(size_t) (m + k) * n + m + k] += f.prior[k]; b[m + k] += f.prior[k] * f.state[k]; }   // delta_prior = state - prior_zero, prior_zero = 0
+        std::vector<double> sv(n), si(n);
+        for (int i = 0; i < n; i++) { sv[i] = sqrt(fabs(H[(size_t) i * n + i]) + 10.0); si[i] = 1.0 / sv[i]; }
+        for (int r = 0; r < n; r++) { b[r] *= si[r]; for (int c = 0; c < n; c++) H[(size_t) r * n + c] *= si[r] * si[c]; }
+        // hpi = inverse of the bottom-right 8x8 block (Gauss-Jordan, partial pivoting)
+        double A[8][16];
+        for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) { A[r][c] = H[(size_t) (m + r) * n + m + c]; A[r][8 + c] = r == c ? 1.0 : 0.0; }
+        for (int k = 0; k < 8; k++) {
+            int piv = k; for (int r = k + 1; r < 8; r++) if (fabs(A[r][k]) > fabs(A[piv][k])) piv = r;
+            if (piv != k) for (int c = 0; c < 16; c++) std::swap(A[k][c], A[piv][c]);
+            const double d = 1.0 / A[k][k];
+            for (int c = 0; c < 16; c++) A[k][c] *= d;
+            for (int r = 0; r < 8; r++) if (r != k) { const double fct = A[r][k]; if (fct != 0.0) for (int c = 0; c < 16; c++) A[r][c] -= fct * A[k][c]; }
+        }
+        // bli = bottomLeft^T * hpi (m x 8); top-left -= bli * bottomLeft; b.head -= bli * b.tail
+        std::vector<double> bli((size_t) m * 8);
+        for (int r = 0; r < m; r++) for (int c = 0; c < 8; c++) { double s = 0; for (int k = 0; k < 8; k++) s += H[(size_t) (m + k) * n + r] * A[k][8 + c]; bli[(size_t) r * 8 + c] = s; }
+        std::vector<double> Hn((size_t) m * m), bn(m);
+        for (int r = 0; r < m; r++) {
+            double s = b[r]; for (int k = 0; k < 8; k++) s -= bli[(size_t) r * 8 + k] * b[m + k];
+            bn[r] = s * sv[r];
+            for (int c = 0; c < m; c++) { double v = H[(size_t) r * n + c]; for (int k = 0; k < 8; k++) v -= bli[(size_t) r * 8 + k] * H[(size_t) (m + k) * n + c]; Hn[(size_t) r * m + c] = v * sv[r] * sv[c]; }
+        }
+        HM.assign((size_t) m * m, 0.0); bM = bn;
+        for (int r = 0; r < m; r++) for (int c = 0; c < m; c++) HM[(size_t) r * m + c] = 0.5 * (Hn[(size_t) r * m + c] + Hn[(size_t) c * m + r]);
     }
 
     // ------------------------------------------------------------------ window maintenance decisions (host, exact)
@@ -573,9 +633,34 @@ public:
         return CMLBA_OK;
     }
 
-    // marginalizePointsF (BA:2466-2513): structural part (see include/cmlba.h for the prior)
+    // marginalizePointsF (BA:2466-2513).  With a live prior (disableMarginalization = false) the marked points are first
+    // accumulated in MARGINALIZED mode on a device window that holds only them, and H_M += 1/4 (M - M_sc), b_M += 1/4 (b - b_sc).
     int marginalize_points(int64_t *ids, int *n) {
         const int cap = n ? *n : 0; int k = 0;
+        bool any = false;
+        for (auto &p : points_) if (p.alive && p.to_marginalize) { any = true; break; }
+        if (any && keep_prior()) {
+            subset_to_marginalize = true; dirty = true;
+            int rc = prepare(nullptr);                                   // setZero, computeAdjoints, computeDelta on the subset window (BA:2474-2486)
+            if (rc == CMLBA_OK) {
+                dw.marg_mode = 1;
+                launch_linearize(0, 0);                                  // tryMarginalize's resetOOB + linearize + applyRes + fixLinearization (BA:2289-2300)
+                commit_candidate_kernel<<<1, 32, 0, stream>>>(dw); launches++;
+                launch_schur(0); launch_stitch(0);
+                const int nn_ = dw.n * dw.n, n_ = dw.n;
+                std::vector<double> sys((size_t) 2 * nn_ + 2 * n_);
+                if (cudaMemcpyAsync(sys.data(), d_sys.p, sys.size() * 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { set_error("marginalize_points: device error"); rc = CMLBA_ERR_CUDA; }
+                else {
+                    hm_fit(n_);
+                    const double *HA = sys.data(), *bA = HA + nn_, *HS = bA + n_, *bS = HS + nn_;
+                    for (int i = 0; i < nn_; i++) HM[i] += 0.25 * (HA[i] - HS[i]);          // setting_margWeightFac = 0.5 * 0.5 (BA:2505-2508)
+                    for (int i = 0; i < n_; i++) bM[i] += 0.25 * (bA[i] - bS[i]);
+                }
+                dw.marg_mode = 0;
+            }
+            subset_to_marginalize = false; dirty = true; prepared = false;
+            if (rc) return rc;
+        }
         for (size_t q = 0; q < points_.size(); q++) {
             PointHost &p = points_[q];
             if (!p.alive || !p.to_marginalize) continue;
@@ -594,7 +679,14 @@ public:
         const int cap = n ? *n : 0; int k = 0;
         std::vector<int64_t> gone;
         for (auto &f : frames_) if (f.flagged) gone.push_back(f.id);
-        for (int64_t id : gone) { if (ids && k < cap) ids[k] = id; k++; int rc = remove_frame(id); if (rc) return rc; }
+        for (int64_t id : gone) {
+            if (ids && k < cap) ids[k] = id;
+            k++;
+            if (keep_prior()) { hm_marginalize_frame(frame_index(id)); hm_frame_done = true; }
+            int rc = remove_frame(id);
+            hm_frame_done = false;
+            if (rc) return rc;
+        }
         if (n) *n = k;
         return CMLBA_OK;
     }
@@ -606,15 +698,17 @@ public:
     int build_device_window() {
         TSCOPE("build_device_window");
         Lap lap(timers);
-        const int N = (int) frames_.size(), PA = (int) points_.size(), P = PA - (int) n_dead;
+        const int N = (int) frames_.size(), PA = (int) points_.size();
         const int n = 8 * N + 4;
         CK(cudaSetDevice(device));
-        // alive points: stable counting sort by host
+        // alive points (or, for marginalize_points, only the marked ones): stable counting sort by host
+        auto in_window = [&](const PointHost &p) { return p.alive && (!subset_to_marginalize || p.to_marginalize); };
         std::vector<int> hcnt(N + 1, 0);
-        for (int i = 0; i < PA; i++) if (points_[i].alive) hcnt[points_[i].host + 1]++;
+        for (int i = 0; i < PA; i++) if (in_window(points_[i])) hcnt[points_[i].host + 1]++;
         for (int h = 0; h < N; h++) hcnt[h + 1] += hcnt[h];
+        const int P = hcnt[N];
         pt_order.resize(P);
-        { std::vector<int> o(hcnt.begin(), hcnt.end() - 1); for (int i = 0; i < PA; i++) if (points_[i].alive) pt_order[o[points_[i].host]++] = i; }
+        { std::vector<int> o(hcnt.begin(), hcnt.end() - 1); for (int i = 0; i < PA; i++) if (in_window(points_[i])) pt_order[o[points_[i].host]++] = i; }
         // residuals per bin = t*N+h from the per-point masks (device order inside a bin = device point order: no sort)
         std::vector<int> bcnt(N * N + 1, 0);
         std::vector<uint16_t> dmask(P);
@@ -864,30 +958,43 @@ public:
             for (int k = 0; k < 8; k++) d.prior[k] = f.prior[k];
             d.exposure = f.exposure; d.energy_th = f.energy_th; d.keyid = f.keyid;
         }
-        if ((int) HM.size() != n * n) { HM.assign((size_t) n * n, 0.0); bM.assign(n, 0.0); }
+        hm_fit(n);
         if (cfg.disable_marginalization) { std::fill(HM.begin(), HM.end(), 0.0); std::fill(bM.begin(), bM.end(), 0.0); }   // BA:1395-1398
         dw.has_HM = 0;
         for (double v : HM) if (v != 0.0) { dw.has_HM = 1; break; }
         for (double v : bM) if (v != 0.0) { dw.has_HM = 1; break; }
+        // adHTdeltaF (computeDelta, BA:1105-1117): delta_h^T AH + delta_t^T AT per pair, stored as float like the reference's casts
+        std::vector<float> pdel((size_t) N * N * 8, 0.f);
+        for (int h = 0; h < N; h++) for (int t = 0; t < N; t++) {
+            const double *ah = &AH[(size_t) (h * N + t) * 64], *at = &AT[(size_t) (h * N + t) * 64];
+            for (int c2 = 0; c2 < 8; c2++) {
+                double v = 0;
+                for (int r2 = 0; r2 < 8; r2++) v += (frames_[h].state[r2] - frames_[h].state_zero[r2]) * ah[r2 * 8 + c2] + (frames_[t].state[r2] - frames_[t].state_zero[r2]) * at[r2 * 8 + c2];
+                pdel[(size_t) (h * N + t) * 8 + c2] = (float) v;
+            }
+        }
         Ctrl c; memset(&c, 0, sizeof(c));
         c.lambda = (double) cfg.fixed_lambda;
         lap("prep.host_math");
         // one pinned block mirrored on the device: frames | AH | AT | Pns | ctrl | (HM | bM when there is a prior)
         prep.begin();
         const size_t o_fr = prep.take<FrameDev>(MAXF), o_ah = prep.take<double>(AH.size()), o_at = prep.take<double>(AT.size()), o_pns = prep.take<double>(Pns.size()),
-                     o_ctrl = prep.take<Ctrl>(1), o_hm = prep.take<double>(dw.has_HM ? HM.size() : 1), o_bm = prep.take<double>(dw.has_HM ? bM.size() : 1);
+                     o_ctrl = prep.take<Ctrl>(1), o_hm = prep.take<double>(dw.has_HM ? HM.size() : 1), o_bm = prep.take<double>(dw.has_HM ? bM.size() : 1),
+                     o_pdel = prep.take<float>(pdel.size());
         CK(cudaStreamSynchronize(stream));          // the previous upload from this pinned block must have landed
         CK(prep.commit());
         memcpy(prep.host<FrameDev>(o_fr), fd.data(), N * sizeof(FrameDev));
         memcpy(prep.host<double>(o_ah), AH.data(), AH.size() * 8); memcpy(prep.host<double>(o_at), AT.data(), AT.size() * 8);
         memcpy(prep.host<double>(o_pns), Pns.data(), Pns.size() * 8); memcpy(prep.host<Ctrl>(o_ctrl), &c, sizeof(c));
         if (dw.has_HM) { memcpy(prep.host<double>(o_hm), HM.data(), HM.size() * 8); memcpy(prep.host<double>(o_bm), bM.data(), bM.size() * 8); }
+        memcpy(prep.host<float>(o_pdel), pdel.data(), pdel.size() * 4);
         CK(cudaMemcpyAsync(prep.d.p, prep.h.p, prep.used, cudaMemcpyHostToDevice, stream));
 #define PVIEW(buf, T, off) do { (buf).release(); (buf).p = prep.dev<T>(off); (buf).view = true; } while (0)
         PVIEW(d_frames, FrameDev, o_fr); PVIEW(d_AH, double, o_ah); PVIEW(d_AT, double, o_at); PVIEW(d_Pns, double, o_pns); PVIEW(d_ctrl, Ctrl, o_ctrl);
         PVIEW(d_HM, double, o_hm); PVIEW(d_bM, double, o_bm);
 #undef PVIEW
         dw.frames = d_frames.p; dw.AH = d_AH.p; dw.AT = d_AT.p; dw.Pns = d_Pns.p; dw.ctrl = d_ctrl.p; dw.HM = d_HM.p; dw.bM = d_bM.p;
+        dw.pair_delta = prep.dev<float>(o_pdel); dw.marg_mode = 0;
         // resetOOB on every active residual (BA:766-779, DSOResidual.h:81-86), empty Schur tables
         reset_window_kernel<<<148 * 4, 256, 0, stream>>>(dw); launches++;
         pairs_kernel<<<(N * N + 63) / 64, 64, 0, stream>>>(dw); launches++;
@@ -1069,7 +1176,7 @@ public:
     int reset() {
         cudaSetDevice(device);
         for (auto &f : frames_) if (f.d_img) { img_pool.push_back(f.d_img); f.d_img = nullptr; }
-        frames_.clear(); points_.clear(); n_dead = 0; snap.valid = false; point_index_.clear(); outliers_.clear();
+        frames_.clear(); points_.clear(); n_dead = 0; HM.clear(); bM.clear(); snap.valid = false; point_index_.clear(); outliers_.clear();
         key_counter = 0; dirty = true; prepared = false;
         return CMLBA_OK;
     }
@@ -1136,6 +1243,8 @@ public:
     int read(const std::string &name, void *dst, size_t cap, size_t *bytes) {
         if (name == "host_timing") { const std::string t = timers.text(); return host_out(t.data(), t.size(), dst, cap, bytes); }
         if (name == "host_timing_reset") { timers.acc.clear(); if (bytes) *bytes = 0; return CMLBA_OK; }
+        if (name == "HM") return host_out(HM.data(), HM.size() * 8, dst, cap, bytes);
+        if (name == "bM") return host_out(bM.data(), bM.size() * 8, dst, cap, bytes);
         if (name == "frame_counters") {   // [N][4] int32: flagged, numMarginalized, numResidualsOut, residuals targeting the frame
             std::vector<int32_t> v;
             for (size_t i = 0; i < frames_.size(); i++) { v.push_back(frames_[i].flagged); v.push_back(frames_[i].num_marginalized); v.push_back(frames_[i].num_residuals_out); v.push_back(frame_residual_count((int) i)); }
@@ -1238,7 +1347,6 @@ int cmlba_create(const cmlba_config *cfg, int device, cmlba_handle **out) {
     if (!h) return CMLBA_ERR_ARG;
     if (cfg) h->eng.cfg = *cfg; else cmlba_default_config(&h->eng.cfg);
     h->eng.device = device;
-    if (!h->eng.cfg.disable_marginalization) { g_create_error = "disableMarginalization=false (accumulating the marginalisation prior H_M) is not implemented"; delete h; return CMLBA_ERR_UNSUPPORTED; }
     int rc = h->eng.init();
     if (rc) { g_create_error = h->eng.err; delete h; return rc; }
     *out = h;

@@ -309,6 +309,23 @@ __global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, 
                 rec[4] = new_idepth * fxf; rec[5] = 0.f; rec[6] = -new_idepth * u * fxf; rec[7] = -u * v * fxf; rec[8] = (1.f + u * u) * fxf; rec[9] = -v * fxf;
                 rec[10] = (float) dCy[0]; rec[11] = (float) dCy[1]; rec[12] = (float) dCy[2]; rec[13] = (float) dCy[3];
                 rec[14] = 0.f; rec[15] = new_idepth * fyf; rec[16] = -new_idepth * v * fyf; rec[17] = -(1.f + v * v) * fyf; rec[18] = u * v * fyf; rec[19] = u * fyf;
+                if (w.marg_mode) {
+                    // MARGINALIZED accumulation (BA:1686-1690): the residual vector is res_toZeroF = resF - [JI*Jp Jab]*delta
+                    // (fixLinearization, BA:2210-2238).  Its moments follow from the sums above; JabF is zeroed for a fixed a / b.
+                    const float *dp = w.pair_delta + (size_t) (h * w.N + t) * 8;
+                    const float dF = (float) (rho - (double) w.pt_idepth_zero[p]);
+                    float jx = Jpdd0 * dF, jy = Jpdd1 * dF;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { jx += rec[4 + k] * dp[k]; jy += rec[14 + k] * dp[k]; }
+                    const float da = dp[6], db = dp[7];
+                    const float a00 = w.optA ? A00 : 0.f, a01 = w.optA ? A01 : 0.f, a10 = w.optB ? A10 : 0.f, a11 = w.optB ? A11 : 0.f;
+                    const float b00 = w.optA ? B00 : 0.f, b01 = (w.optA && w.optB) ? B01 : 0.f, b11 = w.optB ? B11 : 0.f;
+                    const float cross = JIr0 * jx + JIr1 * jy + Jabr0 * da + Jabr1 * db;
+                    const float gx_ = J00 * jx + J10 * jy + a00 * da + a10 * db, gy_ = J10 * jx + J11 * jy + a01 * da + a11 * db;
+                    const float ga = a00 * jx + a01 * jy + b00 * da + b01 * db, gb = a10 * jx + a11 * jy + b01 * da + b11 * db;
+                    rr = rr - 2.f * cross + (jx * gx_ + jy * gy_ + da * ga + db * gb);
+                    JIr0 -= gx_; JIr1 -= gy_; Jabr0 -= ga; Jabr1 -= gb;
+                }
                 rec[20] = J00; rec[21] = J10; rec[22] = J11;                    // JIdx2
                 rec[23] = A00; rec[24] = A10; rec[25] = JIr0;                   // x-multipliers of columns a, b, r (BA:1740-1745)
                 rec[26] = A01; rec[27] = A11; rec[28] = JIr1;                   // y-multipliers
@@ -424,7 +441,7 @@ __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int re
                 idh = Hs;
                 hd = (float) (1.0 / (double) Hs);
                 const float deltaF = (float) (w.pt_idepth[p] - (double) w.pt_idepth_zero[p]);
-                bdSum = bd + priorF * deltaF;
+                bdSum = w.marg_mode ? bd : bd + priorF * deltaF;       // addToHessianSC(shiftPriorToZero) (BA:1902)
                 sh = sqrtf(hd);
             } else {
                 w.pt_max_rel_bs[p] = 0.f;        // BA:1885-1893
@@ -1112,6 +1129,15 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
         }
         // calcLEnergy (BA:2118-2208) without linearized residuals: frame priors + point priors; calcMEnergy (BA:2095-2116) is 0 (H_M = 0)
         double EL = 0.0;
+        if (!w.force_accept && w.has_HM) {   // calcMEnergy (BA:2095-2116): |delta . (2 b_M + H_M delta)|
+            double em = 0.0;
+            for (int r = 0; r < w.n; r++) {
+                double row = 2.0 * w.bM[r];
+                for (int c = 4; c < w.n; c++) { const FrameDev &g = w.frames[(c - 4) >> 3]; const int k = (c - 4) & 7; row += w.HM[(size_t) r * w.n + c] * (g.state[k] - g.state_zero[k]); }
+                if (r >= 4) { const FrameDev &g = w.frames[(r - 4) >> 3]; const int k = (r - 4) & 7; em += (g.state[k] - g.state_zero[k]) * row; }
+            }
+            EL += fabs(em);
+        }
         if (!w.force_accept) {
             for (int i = 0; i < w.N; i++) for (int k = 0; k < 8; k++) { const double d = w.frames[i].state[k]; EL += d * w.frames[i].prior[k] * d; }
             EL += ctrl->prior_energy_pts;
@@ -1160,6 +1186,9 @@ __global__ void __launch_bounds__(1024) pack_post_kernel(const DevWin w, const i
         c[k] = v;
     }
 }
+
+// applyRes without the bookkeeping of run(): the candidate linearization becomes the committed one
+__global__ void commit_candidate_kernel(const DevWin w) { if (threadIdx.x == 0 && blockIdx.x == 0) w.ctrl->cur ^= 1; }
 
 // forceAccept = false: undo a rejected step (loadSateBackup, BA:928-946).  `it1` = the iteration counter value the step belongs to.
 __global__ void __launch_bounds__(256) restore_state_kernel(const DevWin w, const int it1) {

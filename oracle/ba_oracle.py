@@ -745,3 +745,33 @@ def run(w, hook=None):
     w.fin_energy = linearize_all(w, True)
     hook("fin", w)
     return bool(np.isfinite(w.fin_energy))
+
+
+def marginalize_points_prior(w, marg):
+    """Contribution of the points `marg` (bool[P]) to the marginalisation prior: tryMarginalize's re-linearization of their
+    residuals (resetOOB + linearize + applyRes + fixLinearization, BA:2289-2300, 2210-2238) followed by marginalizePointsF
+    (addToHessianTop(MARGINALIZED) + addToHessianSC(false) + stitch, BA:2466-2513).  Returns (dH_M, db_M) = 1/4 (M - M_sc, b - b_sc).
+    The window is left with only those residuals alive (the caller removes the points afterwards anyway)."""
+    compute_adjoints(w); compute_delta(w)
+    th_keep = w.frame_energy_th.copy()
+    w.res_alive = w.res_alive & marg[w.res_point]
+    act = np.nonzero(w.res_alive)[0]
+    w.res_state[act] = IN; w.res_energy[act] = 0                          # resetOOB (DSOResidual.h:81-86)
+    linearize_all(w, False)
+    w.frame_energy_th = th_keep                                           # the per-residual linearize of tryMarginalize never touches frameEnergyTH
+    apply_active_res(w)
+    g = np.nonzero(w.res_good & w.res_alive)[0]
+    J = w.efsJ
+    dp = w.ad_ht_delta[w.res_host[g] + w.N * w.res_target[g]].astype(F32)
+    dF = w.deltaF[w.res_point[g]].astype(F32)
+    jx = ((J["Jpdxi"][g, 0] * dp[:, :6]).sum(1, dtype=F32) + J["Jpdd"][g, 0] * dF).astype(F32)     # Jpdc . dc = 0 (calibration fixed)
+    jy = ((J["Jpdxi"][g, 1] * dp[:, :6]).sum(1, dtype=F32) + J["Jpdd"][g, 1] * dF).astype(F32)
+    rtz = (J["resF"][g] - J["JIdx"][g, 0] * jx[:, None] - J["JIdx"][g, 1] * jy[:, None] - J["JabF"][g, 0] * dp[:, 6:7] - J["JabF"][g, 1] * dp[:, 7:8]).astype(F32)
+    keep = J["resF"][g].copy()
+    J["resF"][g] = rtz                                                    # MARGINALIZED mode accumulates res_toZeroF (BA:1686-1690)
+    acc = accumulate_top(w)
+    M, Mb = stitch_top(w, acc, False)
+    accumulate_sc(w, False)
+    Msc, Mbsc = stitch_sc(w)
+    J["resF"][g] = keep
+    return 0.25 * (M - Msc), 0.25 * (Mb - Mbsc)

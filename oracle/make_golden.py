@@ -51,13 +51,25 @@ def main():
               os.path.getsize(os.path.join(OUT, f"{name}_stages.cmlw")) // 1024, "KB")
 
 
-def maintenance():
-    """Window-maintenance flow (flag / tryMarginalize / marginalizePointsF / marginalizeFrames) of the reference on a 6-frame window."""
+def maintenance(prior=False):
+    """Window-maintenance flow (flag / tryMarginalize / marginalizePointsF / marginalizeFrames) of the reference on a 6-frame window.
+    prior=True: disableMarginalization = false, i.e. the marginalisation prior H_M, b_M is live (golden `maintp`: only what differs)."""
     tmp = "/tmp/cmlba_golden"
     os.makedirs(tmp, exist_ok=True)
     win = synth.make_window(160, 120, 6, 60, 4, False, seed=77)
     win["max_frames"] = np.array([5], np.int32)     # the 6th addNewFrame flags one frame by the distance score (BA:649-700)
     win["runs"] = np.array([3], np.int32)           # numGoodResiduals must pass 14 for the first isOOB rule (BA:2532-2536)
+    if prior:
+        win["disable_marginalization"] = np.array([0], np.int32)
+        full = os.path.join(tmp, "maintp.cmlw")
+        cmlw.save(full, win)
+        run_ref(full, "maintain", os.path.join(tmp, "maintp_out.cmlw"))
+        g = cmlw.load(os.path.join(tmp, "maintp_out.cmlw"))
+        keep = {k: g[k] for k in ("m2_HM", "m2_bM", "m3_HM", "m3_bM", "m2_pt_marginalized", "m1_pt_outlier", "m3_removed_frames", "m3_frame_in_window", "m4_ok",
+                                  "m4_frame_pre_w2c", "m4_frame_affine", "m4_pt_idepth", "m4_pt_alive", "m4_res_point", "m4_res_target")}
+        cmlw.save(os.path.join(OUT, "maintp_golden.cmlw"), keep)     # the window is maint_window.cmlw + disable_marginalization = 0
+        print("maintp golden", os.path.getsize(os.path.join(OUT, "maintp_golden.cmlw")) // 1024, "KB")
+        return
     full = os.path.join(tmp, "maint.cmlw")
     cmlw.save(full, win)
     run_ref(full, "maintain", os.path.join(tmp, "maint_out.cmlw"))
@@ -93,7 +105,7 @@ def rejection():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "maintenance":
-        maintenance(); sys.exit(0)
+        maintenance(); maintenance(prior=True); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "rejection":
         rejection(); sys.exit(0)
     main()

@@ -122,6 +122,7 @@ static RefWindow *buildWindow(const cmlw::File &in) {
     if (in.has("optimize_a")) w->ba->mOptimizeA.set(in.get("optimize_a").as<int32_t>()[0] != 0);
     if (in.has("optimize_b")) w->ba->mOptimizeB.set(in.get("optimize_b").as<int32_t>()[0] != 0);
     if (in.has("force_accept")) w->ba->mForceAccept.set(in.get("force_accept").as<int32_t>()[0] != 0);
+    if (in.has("disable_marginalization")) w->ba->mDisableMarginalization.set(in.get("disable_marginalization").as<int32_t>()[0] != 0);
     if (in.has("fixed_lambda")) w->ba->mFixedLambda.set((float) in.get("fixed_lambda").as<double>()[0]);
 
     Map &map = w->root->getMap();
@@ -512,9 +513,11 @@ static int runMaintain(RefWindow *w, const cmlw::File &in, cmlw::File &out) {
     ba->computeNullspaces();
     ba->marginalizePointsF();
     dumpMaintState(w, out, "m2_");                 // after marginalizePointsF
+    putMat(out, "m2_HM", ba->mMarginalizedHessian); putMat(out, "m2_bM", ba->mMarginalizedB);
     auto removed = ba->marginalizeFrames();
     std::vector<int32_t> rem; for (auto f : removed) rem.push_back(w->frameIndex.at(f.p()));
     out.put1<int32_t>("m3_removed_frames", rem);
+    putMat(out, "m3_HM", ba->mMarginalizedHessian); putMat(out, "m3_bM", ba->mMarginalizedB);
     dumpMaintState(w, out, "m3_");                 // after marginalizeFrames
     // one more run() on the reduced window: the reduced window's frames keep their original indices in the dump
     ok = ba->run(w->updatePointsOnly); ba->mActiveResiduals.clear();

@@ -89,3 +89,48 @@ def test_maintenance_flow_matches_reference():
     assert rel(pts["idepth"], g["m4_pt_idepth"][pts["id"]]) < 1e-3
     assert _res_set(ba) == set(zip(g["m4_res_point"].tolist(), g["m4_res_target"].tolist()))
     ba.close()
+
+
+def test_marginalisation_prior_matches_reference():
+    """disableMarginalization = false: H_M, b_M after marginalizePointsF (MARGINALIZED accumulation of the leaving points on the
+    device, BA:2466-2513) and after marginalizeFrames (Schur complement of the frame block, BA:464-548), and the next run() that uses them."""
+    from libcml_b200 import DSOBundleAdjustment, cmlw
+    win, g0 = _load()
+    g = cmlw.load(os.path.join(GOLDEN, "maintp_golden.cmlw"))
+    N = win["frame_evalpt"].shape[0]; P = win["pt_host"].size
+    W, H = int(win["size"][0]), int(win["size"][1])
+    ba = DSOBundleAdjustment(device=0, iterations=int(win["iterations"][0]), max_frames=int(win["max_frames"][0]), disable_marginalization=0)
+    ba.setCalibration(*[float(v) for v in win["calib"]], W, H)
+    for i in range(N):
+        ba.flagFramesForMarginalization(cams=win["frame_evalpt"][:i] if i else None)
+        ba.addNewFrame(i, win["frame_evalpt"][i], win["frame_affine"][i, 0], win["frame_affine"][i, 1], win["frame_exposure"][i], win["grad"][i], False)
+    ba.addPoints(np.arange(P), win["pt_host"], win["pt_xy"], win["pt_idepth"])
+    assert ba.run(win["frame_cam"])
+    for _ in range(int(win["runs"][0]) - 1):
+        assert ba.run(None)
+    ba.tryMarginalize()
+    assert np.array_equal(np.sort(ba.getOutliers()), np.nonzero(g["m1_pt_outlier"])[0])
+    marg = ba.marginalizePointsF()
+    assert np.array_equal(np.sort(marg), np.nonzero(g["m2_pt_marginalized"])[0])
+    n = 8 * N + 4
+    HM = ba.read("HM", np.float64).reshape(n, n); bM = ba.read("bM", np.float64)
+    assert np.linalg.norm(HM - g["m2_HM"]) / np.linalg.norm(g["m2_HM"]) < 1e-4          # fp32 accumulators of ~130 points
+    assert rel(HM[4:, 4:], g["m2_HM"][4:, 4:]) < 1e-4
+    # b_M = 1/4 sum J^T (resF - J delta) cancels heavily near convergence: a 1e-6 difference of the frame states after three
+    # runs moves it by ~1e-3 (the faithful numpy restatement, tests/test_oracle_golden.py, sits 7e-4 from the reference too)
+    assert np.linalg.norm(bM - g["m2_bM"][:, 0]) / np.linalg.norm(g["m2_bM"]) < 3e-3
+    removed = ba.marginalizeFrames()
+    assert list(removed) == list(g["m3_removed_frames"])
+    n3 = n - 8 * len(removed)
+    HM3 = ba.read("HM", np.float64).reshape(n3, n3); bM3 = ba.read("bM", np.float64)
+    assert np.linalg.norm(HM3 - g["m3_HM"]) / np.linalg.norm(g["m3_HM"]) < 1e-4
+    assert np.linalg.norm(bM3 - g["m3_bM"][:, 0]) / np.linalg.norm(g["m3_bM"]) < 3e-3
+    keep = np.nonzero(g["m3_frame_in_window"])[0]
+    assert ba.run(None) == bool(g["m4_ok"][0])
+    fr = ba.getFrames(); pts = ba.getPoints()
+    assert rel(fr["world_to_cam"], g["m4_frame_pre_w2c"][keep]) < 1e-4
+    assert np.array_equal(np.sort(pts["id"]), np.nonzero(g["m4_pt_alive"])[0])
+    assert rel(pts["idepth"], g["m4_pt_idepth"][pts["id"]]) < 1e-3
+    # the prior must matter in this scenario: the run without it lands elsewhere
+    assert rel(g0["m4_frame_pre_w2c"][keep], g["m4_frame_pre_w2c"][keep]) > 1e-4
+    ba.close()

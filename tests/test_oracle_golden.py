@@ -136,3 +136,20 @@ def test_step_rejection_matches_reference():
     mine = np.stack([np.concatenate([R.ravel(), t]) for R, t in w.pre_w2c])
     assert rel(mine, g["fin_frame_pre_w2c"]) < 1e-4
     assert rel(w.idepth, g["fin_pt_idepth"]) < 1e-3
+
+
+def test_marginalisation_prior_restatement_matches_reference():
+    """marginalize_points_prior (tryMarginalize's re-linearization + marginalizePointsF, BA:2289-2300, 2466-2513) against H_M, b_M of the
+    reference (disableMarginalization = false) after three run() calls."""
+    import os
+    from libcml_b200 import cmlw, synth
+    from parity_util import GOLDEN
+    win = cmlw.load(os.path.join(GOLDEN, "maint_window.cmlw")); g = cmlw.load(os.path.join(GOLDEN, "maintp_golden.cmlw"))
+    win["grad"] = np.stack([synth.gradient_image(win["gray"][i]) for i in range(win["gray"].shape[0])])
+    w = O.Window(win)
+    for _ in range(int(win["runs"][0])):
+        assert O.run(w)
+    dH, db = O.marginalize_points_prior(w, g["m2_pt_marginalized"].astype(bool))
+    assert np.linalg.norm(dH - g["m2_HM"]) / np.linalg.norm(g["m2_HM"]) < 1e-5
+    # b_M cancels heavily near convergence (J^T resF against J^T J delta): 1e-6 state differences after three runs show up at ~1e-3
+    assert np.linalg.norm(db.ravel() - g["m2_bM"][:, 0]) / np.linalg.norm(g["m2_bM"]) < 3e-3
