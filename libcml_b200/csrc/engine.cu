@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -52,6 +53,7 @@ struct Lap {   // sequential section timer: lap("name") charges the time since t
 };
 #define TSCOPE(name) HostTimers::Scope _ts_##__LINE__(timers, name)
 
+static long g_dev_mallocs = 0, g_pin_mallocs = 0;   // allocation counters (cmlba_read "host_timing")
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
@@ -61,6 +63,7 @@ template <typename T> struct DevBuf {
         if (p && !view) cudaFree(p);
         p = nullptr; cap = 0; view = false;
         size_t want = n + n / 4 + 16;
+        g_dev_mallocs++;
         cudaError_t e = cudaMalloc(&p, want * sizeof(T));
         if (e == cudaSuccess) cap = want;
         return e;
@@ -77,6 +80,7 @@ template <typename T> struct PinnedBuf {
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = n + n / 4 + 16;
+        g_pin_mallocs++;
         cudaError_t e = cudaHostAlloc((void **) &p, want * sizeof(T), cudaHostAllocDefault);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -148,7 +152,6 @@ struct PointHost {
     double idepth = 0;
     float idepth_zero = 0;
     bool has_prior = false;
-    float colors[8], weights[8];
     int num_good = 0;
     float max_rel_bs = 0, idepth_hessian = 0;
     int64_t last_frame[2] = {-1, -1};   // frames of lastResiduals[0/1] (DSOPoint.h:119-156); -1 = nullptr
@@ -239,7 +242,8 @@ public:
     UploadArena prep;                             // per-run constants uploaded by prepare()
     std::vector<int> res_bin_begin;               // [N*N+1] first device residual of every bin (t*N+h)
     size_t up_o_rp = 0, up_o_rt = 0;              // arena offsets of r_point / r_target (host mirrors stay valid until the next build)
-    PinnedBuf<char> pt_stage_h, fin_h; DevBuf<char> pt_stage_d;   // add_points round trip, finish_run read-back
+    PinnedBuf<char> fin_h;                        // finish_run read-back
+    PinnedBuf<int> peek_h;                        // Ctrl.done peeked between iteration batches
     DevBuf<uint8_t> d_r_host, d_r_target, d_r_state0, d_r_state1, d_r_good0, d_r_good1, d_r_new_state, d_r_alive;
     bool want_dbg = false;
     DevBuf<float4> d_flush;
@@ -274,7 +278,7 @@ public:
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_copy) cudaEventDestroy(ev_copy);
-        up.h.release(); up.d.release(); prep.h.release(); prep.d.release(); pt_stage_h.release(); fin_h.release(); pt_stage_d.release();
+        up.h.release(); up.d.release(); prep.h.release(); prep.d.release(); fin_h.release(); peek_h.release();
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         // DevBuf members leak-free:
         DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_st_out, &d_sys, &d_x, &d_xAd, &d_pt_part};
@@ -391,20 +395,8 @@ public:
         const size_t nn = points_.size() - first;
         lap("addp.validate");
         if (nn == 0) return CMLBA_OK;
-        // colours + weights on the device from the host frames' images (staging: [host|x|y] up, [colors|weights] down)
-        const size_t o_h = 0, o_x = nn * 4, o_y = nn * 8, o_c = nn * 12, o_w = nn * 12 + nn * 32, tot = nn * 12 + nn * 64;
-        CK(pt_stage_h.reserve(tot)); CK(pt_stage_d.reserve(tot));
-        int *hh = reinterpret_cast<int *>(pt_stage_h.p + o_h); float *xs = reinterpret_cast<float *>(pt_stage_h.p + o_x), *ys = reinterpret_cast<float *>(pt_stage_h.p + o_y);
-        for (size_t i = 0; i < nn; i++) { const PointHost &q = points_[first + i]; hh[i] = q.host; xs[i] = q.x; ys[i] = q.y; }
-        CK(cudaMemcpyAsync(pt_stage_d.p, pt_stage_h.p, nn * 12, cudaMemcpyHostToDevice, stream));
-        DevWin t{};
-        t.W = W; t.H = H; t.cth = cfg.outlier_th_sum;
-        for (size_t i = 0; i < frames_.size(); i++) t.img[i] = frames_[i].d_img;
-        t.pt_host = reinterpret_cast<int *>(pt_stage_d.p + o_h); t.pt_x = reinterpret_cast<float *>(pt_stage_d.p + o_x); t.pt_y = reinterpret_cast<float *>(pt_stage_d.p + o_y);
-        point_init_kernel<<<(unsigned) ((nn * 8 + 255) / 256), 256, 0, stream>>>(t, 0, (int) nn, reinterpret_cast<float *>(pt_stage_d.p + o_c), reinterpret_cast<float *>(pt_stage_d.p + o_w));
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(pt_stage_h.p + o_c, pt_stage_d.p + o_c, nn * 64, cudaMemcpyDeviceToHost, stream));
-        // residual bookkeeping overlaps the device round trip
+        // residual bookkeeping (reference colours and gradient weights of addPoint, DSOContext.h:86-91 / BA:405-411, are computed on
+        // the device when the window is built: they only depend on the host image and the pixel)
         const int64_t newest = frames_.back().id, second = NF >= 2 ? frames_[NF - 2].id : -1;
         const uint16_t all = (uint16_t) ((1u << NF) - 1u);
         for (size_t i = 0; i < nn; i++) {
@@ -414,10 +406,6 @@ public:
             if (NF >= 2 && p.host != NF - 2) { p.last_frame[1] = second; p.last_state[1] = CMLBA_RES_IN; }
         }
         lap("addp.residuals");
-        CK(cudaStreamSynchronize(stream));
-        const float *hc = reinterpret_cast<const float *>(pt_stage_h.p + o_c), *hw = reinterpret_cast<const float *>(pt_stage_h.p + o_w);
-        for (size_t i = 0; i < nn; i++) { PointHost &p = points_[first + i]; memcpy(p.colors, &hc[i * 8], 32); memcpy(p.weights, &hw[i * 8], 32); }
-        lap("addp.device_init");
         dirty = true; prepared = false;
         return CMLBA_OK;
     }
@@ -736,7 +724,6 @@ public:
         up.begin();
         const size_t o_pt_host = up.take<int>(P), o_x = up.take<float>(P), o_y = up.take<float>(P), o_idz = up.take<float>(P), o_prior = up.take<float>(P),
                      o_mrb = up.take<float>(P), o_idh = up.take<float>(P), o_ng = up.take<int>(P), o_id = up.take<double>(P),
-                     o_col = up.take<float>((size_t) P * 8), o_wt = up.take<float>((size_t) P * 8),
                      o_rp = up.take<int>(R), o_rh = up.take<uint8_t>(R), o_rt = up.take<uint8_t>(R),
                      o_cb = up.take<int>(n_acc_chunks), o_cbeg = up.take<int>(n_acc_chunks), o_ccnt = up.take<int>(n_acc_chunks), o_bcb = up.take<int>(N * N + 1),
                      o_sh = up.take<int>(n_sc_chunks), o_sbeg = up.take<int>(n_sc_chunks), o_scnt = up.take<int>(n_sc_chunks), o_hcb = up.take<int>(N + 1);
@@ -747,12 +734,11 @@ public:
         {
             int *h_pt_host = up.host<int>(o_pt_host), *h_ng = up.host<int>(o_ng);
             float *h_x = up.host<float>(o_x), *h_y = up.host<float>(o_y), *h_idz = up.host<float>(o_idz), *h_prior = up.host<float>(o_prior), *h_mrb = up.host<float>(o_mrb),
-                  *h_idh = up.host<float>(o_idh), *h_col = up.host<float>(o_col), *h_wt = up.host<float>(o_wt);
+                  *h_idh = up.host<float>(o_idh);
             double *h_id = up.host<double>(o_id);
             for (int i = 0; i < P; i++) {
                 const PointHost &p = points_[pt_order[i]];
                 h_pt_host[i] = p.host; h_x[i] = p.x; h_y[i] = p.y; h_id[i] = p.idepth; h_idz[i] = p.idepth_zero;
-                memcpy(&h_col[(size_t) i * 8], p.colors, 32); memcpy(&h_wt[(size_t) i * 8], p.weights, 32);
                 h_prior[i] = p.has_prior ? (float) cfg.idepth_fix_prior : 0.f;
                 h_ng[i] = p.num_good; h_mrb[i] = p.max_rel_bs; h_idh[i] = p.idepth_hessian;
             }
@@ -778,7 +764,7 @@ public:
         // device-only buffers
         const size_t Rz = std::max(R, 1), Pz = std::max(P, 1);
         CK(d_pairs.reserve(MAXF * MAXF));
-        CK(d_pt_idb.reserve(Pz));
+        CK(d_pt_idb.reserve(Pz)); CK(d_pt_colors.reserve(Pz * 8)); CK(d_pt_weights.reserve(Pz * 8));
         CK(d_pt_Hdd.reserve(Pz)); CK(d_pt_bd.reserve(Pz)); CK(d_pt_Hcd.reserve(Pz * 4)); CK(d_pt_HdiF.reserve(Pz)); CK(d_pt_bdSumF.reserve(Pz));
         CK(d_pt_ngood_cur.reserve(Pz)); CK(d_pt_step.reserve(Pz));
         CK(d_r_state0.reserve(Rz)); CK(d_r_state1.reserve(Rz)); CK(d_r_energy0.reserve(Rz)); CK(d_r_energy1.reserve(Rz)); CK(d_r_good0.reserve(Rz)); CK(d_r_good1.reserve(Rz));
@@ -796,7 +782,7 @@ public:
 #define VIEW(buf, T, off) do { (buf).p = up.dev<T>(off); (buf).view = true; (buf).cap = 0; } while (0)
         VIEW(d_pt_host, int, o_pt_host); VIEW(d_pt_x, float, o_x); VIEW(d_pt_y, float, o_y); VIEW(d_pt_idz, float, o_idz); VIEW(d_pt_priorF, float, o_prior);
         VIEW(d_pt_mrb, float, o_mrb); VIEW(d_pt_idh, float, o_idh); VIEW(d_pt_num_good, int, o_ng); VIEW(d_pt_idepth, double, o_id);
-        VIEW(d_pt_colors, float, o_col); VIEW(d_pt_weights, float, o_wt); VIEW(d_r_point, int, o_rp); VIEW(d_r_host, uint8_t, o_rh); VIEW(d_r_target, uint8_t, o_rt);
+        VIEW(d_r_point, int, o_rp); VIEW(d_r_host, uint8_t, o_rh); VIEW(d_r_target, uint8_t, o_rt);
         VIEW(d_acc_chunk_bin, int, o_cb); VIEW(d_acc_chunk_begin, int, o_cbeg); VIEW(d_acc_chunk_count, int, o_ccnt); VIEW(d_bin_chunk_begin, int, o_bcb);
         VIEW(d_sc_chunk_host, int, o_sh); VIEW(d_sc_chunk_begin, int, o_sbeg); VIEW(d_sc_chunk_count, int, o_scnt); VIEW(d_host_chunk_begin, int, o_hcb);
 #undef VIEW
@@ -827,6 +813,8 @@ public:
         w.host_chunk_begin = d_host_chunk_begin.p;
         w.st_out = d_st_out.p; w.sys = d_sys.p; w.x = d_x.p; w.xAd = d_xAd.p;
         w.pt_part = d_pt_part.p; w.n_pt_blocks = n_pt_blocks;
+        // addPoint's reference colours (integer-pixel read) and gradient weights (DSOContext.h:86-91, BA:405-411) from the host images
+        if (P > 0) { point_init_kernel<<<(unsigned) (((size_t) P * 8 + 255) / 256), 256, 0, stream>>>(w, 0, P, d_pt_colors.p, d_pt_weights.p); launches++; CK(cudaGetLastError()); }
         w.world = world; w.rank = rank; w.cand_cap = 0;
         if (world > 1) {
             // record capacity = the largest per-rank count of residuals towards the newest frame (one small all-reduce per window build)
@@ -1059,10 +1047,21 @@ public:
         CK(cudaEventRecord(ev0, stream));
         if (!cfg.force_accept) { point_prior_energy_kernel<<<1, 256, 0, stream>>>(dw); launches++; }
         launch_linearize(0, 0); launch_post(0, 0);
-        for (int it = 0; it < iterations; it++) {
-            rc = launch_solve_sequence(1); if (rc) return rc;
-            launch_linearize(0, 1); launch_post(1, 1);
-            if (!cfg.force_accept) { restore_state_kernel<<<std::max(dw.n_pt_blocks, 1), 256, 0, stream>>>(dw, it + 1); launches++; }   // no-op unless the step was rejected
+        // GN iterations are enqueued two at a time (run() cannot stop before it = 1, BA:879); between batches the host peeks at
+        // Ctrl.done instead of enqueueing up to 7 no-op launches per iteration that the window no longer needs.
+        CK(peek_h.reserve(1));
+        for (int it = 0; it < iterations;) {
+            const int batch_end = std::min(iterations, it + 2);
+            for (; it < batch_end; it++) {
+                rc = launch_solve_sequence(1); if (rc) return rc;
+                launch_linearize(0, 1); launch_post(1, 1);
+                if (!cfg.force_accept) { restore_state_kernel<<<std::max(dw.n_pt_blocks, 1), 256, 0, stream>>>(dw, it + 1); launches++; }   // no-op unless the step was rejected
+            }
+            if (it < iterations) {
+                CK(cudaMemcpyAsync(peek_h.p, reinterpret_cast<const char *>(d_ctrl.p) + offsetof(Ctrl, done), sizeof(int), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                if (*peek_h.p) break;
+            }
         }
         set_evalpt_newest_kernel<<<1, 32, 0, stream>>>(dw); launches++;
         pairs_kernel<<<(dw.N * dw.N + 63) / 64, 64, 0, stream>>>(dw); launches++;
@@ -1241,7 +1240,7 @@ public:
         return CMLBA_OK;
     }
     int read(const std::string &name, void *dst, size_t cap, size_t *bytes) {
-        if (name == "host_timing") { const std::string t = timers.text(); return host_out(t.data(), t.size(), dst, cap, bytes); }
+        if (name == "host_timing") { const std::string t = timers.text() + "device allocations " + std::to_string(g_dev_mallocs) + ", pinned allocations " + std::to_string(g_pin_mallocs) + "\n"; return host_out(t.data(), t.size(), dst, cap, bytes); }
         if (name == "host_timing_reset") { timers.acc.clear(); if (bytes) *bytes = 0; return CMLBA_OK; }
         if (name == "HM") return host_out(HM.data(), HM.size() * 8, dst, cap, bytes);
         if (name == "bM") return host_out(bM.data(), bM.size() * 8, dst, cap, bytes);
