@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--nccl-only", action="store_true", help="N>1: all-reduce the reduced system with NCCL instead of the peer-memory exchange")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -182,15 +183,7 @@ def main():
     # async_image_upload: add_frame only enqueues the H2D copy of the (pinned) image; it still completes inside the timed region, before run()
     ba = DSOBundleAdjustment(device=local_rank, iterations=iters, async_image_upload=1)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = np.zeros(128, dtype=np.uint8)
-            ba._ck(ba.lib.cmlba_nccl_unique_id(buf.ctypes.data))
-            uid = torch.from_numpy(buf)
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        ub = uid.cpu().numpy()
-        ba._ck(ba.lib.cmlba_comm_init(ba.h, ub.ctypes.data, rank, world))
+        ba.initCommunicator(rank, world, peer_memory=not args.nccl_only)
 
     # ---------------- device-resident hot-path passes
     cams = ba.loadWindow(win)
@@ -254,7 +247,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_pass,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (projection f64)", "data": "synthetic",
            "config": {"workload": f"{args.workload}: {N} KF x {ppk} pts/KF per GPU, {W}x{H} level 0, {iters} GN iterations", "residuals_per_gpu": R,
-                      "l2": "flushed between timed passes (384 MB write outside the timed region)", "parallelism": f"points sharded x{world}, frames replicated",
+                      "l2": "flushed between timed passes (384 MB write outside the timed region)", "parallelism": f"points sharded x{world}, frames replicated" + ("" if world == 1 else (", reduced system summed by ncclAllReduce" if args.nccl_only else ", reduced system summed over NVLink peer memory")),
                       "pass": "linearize+accumulate+schur+stitch"},
            "ms_per_step_l2_warm": ms_pass_warm, "value_l2_warm": world * R / (ms_pass_warm * 1e-3),
            "kernel_ms": {"linearize": br.ms_linearize, "accumulate": br.ms_accumulate, "schur": br.ms_schur, "stitch": br.ms_stitch,

@@ -200,6 +200,13 @@ int cmlba_read(cmlba_handle *h, const char *name, void *dst, size_t capacity, si
  * caller's own plumbing (e.g. torch.distributed). */
 int cmlba_nccl_unique_id(void *unique_id_128);
 int cmlba_comm_init(cmlba_handle *h, const void *unique_id_128, int rank, int world_size);
+/* Optional, after cmlba_comm_init (one process per GPU on one NVLink/NVSwitch node): exchange of the reduced system through
+ * cudaIpc-mapped peer memory instead of ncclAllReduce.  Every rank calls cmlba_comm_ipc_handle (64-byte cudaIpcMemHandle_t of
+ * its exchange buffer), the caller all-gathers the handles in rank order, every rank calls cmlba_comm_ipc_open with all of
+ * them.  From then on assemble_kernel writes the rank's partial system into its buffer and signals the peers, and
+ * solve_kernel sums the ranks' buffers with NVLink loads in its prologue (one kernel for the collective + the solve). */
+int cmlba_comm_ipc_handle(cmlba_handle *h, void *handle_64);
+int cmlba_comm_ipc_open(cmlba_handle *h, const void *handles /* [world_size][64] */);
 
 /* library / build info: "libcmlba <version> sm_100a" */
 const char *cmlba_version(void);

@@ -47,7 +47,7 @@ SYMBOLS = ["cmlba_default_config", "cmlba_create", "cmlba_destroy", "cmlba_last_
            "cmlba_remove_point", "cmlba_remove_frame", "cmlba_flag_frames_for_marginalization", "cmlba_try_marginalize", "cmlba_marginalize_points",
            "cmlba_marginalize_frames", "cmlba_run", "cmlba_num_frames", "cmlba_num_points", "cmlba_num_residuals", "cmlba_get_frames",
            "cmlba_get_points", "cmlba_get_outliers", "cmlba_get_residuals", "cmlba_prepare", "cmlba_linearize", "cmlba_apply", "cmlba_solve", "cmlba_step",
-           "cmlba_read", "cmlba_reset", "cmlba_bench_pass", "cmlba_nccl_unique_id", "cmlba_comm_init", "cmlba_version"]
+           "cmlba_read", "cmlba_reset", "cmlba_bench_pass", "cmlba_nccl_unique_id", "cmlba_comm_init", "cmlba_comm_ipc_handle", "cmlba_comm_ipc_open", "cmlba_version"]
 
 _lib = None
 
@@ -94,6 +94,8 @@ def load_library():
     lib.cmlba_bench_pass.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(BenchResult)]
     lib.cmlba_nccl_unique_id.argtypes = [vp]
     lib.cmlba_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.cmlba_comm_ipc_handle.argtypes = [vp, vp]
+    lib.cmlba_comm_ipc_open.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -280,6 +282,28 @@ class DSOBundleAdjustment:
         if nb.value:
             self._ck(self.lib.cmlba_read(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), nb.value, C.byref(nb)))
         return out.reshape(shape) if shape is not None else out
+
+    def initCommunicator(self, rank, world, peer_memory=True):
+        """One process per GPU: NCCL communicator (unique id broadcast through torch.distributed) and, optionally, the peer-memory
+        exchange of the reduced system (cudaIpc handles all-gathered through torch.distributed)."""
+        import torch
+        import torch.distributed as dist
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = np.zeros(128, dtype=np.uint8)
+            self._ck(self.lib.cmlba_nccl_unique_id(buf.ctypes.data))
+            uid = torch.from_numpy(buf)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        ub = uid.cpu().numpy()
+        self._ck(self.lib.cmlba_comm_init(self.h, ub.ctypes.data, rank, world))
+        if peer_memory and world > 1:
+            mine = np.zeros(64, dtype=np.uint8)
+            self._ck(self.lib.cmlba_comm_ipc_handle(self.h, mine.ctypes.data))
+            allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, torch.from_numpy(mine).cuda())
+            packed = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
+            self._ck(self.lib.cmlba_comm_ipc_open(self.h, packed.ctypes.data))
 
     def reset(self):
         self._ck(self.lib.cmlba_reset(self.h))

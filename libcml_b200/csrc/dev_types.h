@@ -11,6 +11,7 @@ constexpr int T_STRIDE = 16;      // floats per (point,target) Schur row: JpJdF[
 constexpr int ACC_N = 96;         // 91 unique entries of the 13x13 block, padded to 3*32
 constexpr int LIN_THREADS = 32;   // linearize+accumulate: one warp-CTA per chunk, one thread per residual
 constexpr int ACC_CHUNK = 32;     // residuals per linearize+accumulate CTA (all in one (h,t) bin)
+constexpr size_t P2P_SLOT_DOUBLES = 2 * (size_t) (8 * MAXF + 4) * (8 * MAXF + 4) + 2 * (8 * MAXF + 4);   // sys at the largest window
 constexpr int SC_CHUNK = 64;      // points per Schur CTA (all hosted in one frame)
 
 enum : uint8_t { RES_IN = 0, RES_OOB = 1, RES_OUTLIER = 2 };
@@ -58,7 +59,8 @@ struct Ctrl {
     double prior_energy_pts;    // sum_p deltaF^2 * priorF (BA:2200) of the current point states
     int rejected_at;            // value of `iteration` right after the last rejected step (restore_state_kernel keys on it)
     int rejected;               // number of rejected steps
-    int pt_bad, pad1;           // non-finite point steps of this rank (point_step_kernel)
+    int pt_bad;                 // non-finite point steps of this rank (point_step_kernel)
+    int asm_done_count;         // last-block counter of assemble_kernel (peer signalling)
 };
 
 struct DevWin {
@@ -126,6 +128,10 @@ struct DevWin {
     // multi-GPU (points sharded, frames replicated): every linearization all-gathers one record per rank
     //   [energy, sumNID, numID, bad, prior_energy, 0, 0, 0 (doubles) | cand_cap candidate energies of the newest frame (floats, -1 = none)]
     int world, rank, cand_cap;
+    // peer exchange of the reduced system over NVLink (cudaIpc-mapped buffers, see p2p_reduce in kernels.cuh); null = NCCL path
+    char *p2p_base[MAXF];          // every rank's exchange buffer: [flags u64[16] | pad to 256 B | slot 0 | slot 1]
+    unsigned long long p2p_epoch;  // number of this exchange (same on every rank); slot = epoch & 1
+    int p2p_on;
     double *post_send;             // this rank's record
     const double *post_recv;       // world records
 };

@@ -228,6 +228,9 @@ public:
     // multi-GPU
     void *comm = nullptr; int rank = 0, world = 1;
     DevBuf<double> d_post_send, d_post_recv; DevBuf<int> d_cap;   // multi-GPU post-linearize exchange
+    // reduced-system exchange over NVLink peer memory (cudaIpc); falls back to ncclAllReduce when not opened
+    char *p2p_local = nullptr; char *p2p_peer[MAXF] = {nullptr}; bool p2p_ready = false; unsigned long long p2p_epoch = 0;
+    size_t p2p_bytes() const { return 256 + (size_t) 2 * world * P2P_SLOT_DOUBLES * sizeof(double); }   // flags | slots[2 epochs][world sources]
 
     // device buffers
     DevBuf<FrameDev> d_frames; DevBuf<PairPre> d_pairs; DevBuf<Ctrl> d_ctrl;
@@ -279,6 +282,8 @@ public:
         if (ev1) cudaEventDestroy(ev1);
         if (ev_copy) cudaEventDestroy(ev_copy);
         up.h.release(); up.d.release(); prep.h.release(); prep.d.release(); fin_h.release(); peek_h.release();
+        for (int q = 0; q < MAXF; q++) if (p2p_peer[q] && p2p_peer[q] != p2p_local) cudaIpcCloseMemHandle(p2p_peer[q]);
+        if (p2p_local) cudaFree(p2p_local);
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
         // DevBuf members leak-free:
         DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_st_out, &d_sys, &d_x, &d_xAd, &d_pt_part};
@@ -627,6 +632,7 @@ public:
         const int cap = n ? *n : 0; int k = 0;
         bool any = false;
         for (auto &p : points_) if (p.alive && p.to_marginalize) { any = true; break; }
+        if (any && keep_prior() && world > 1) { set_error("the marginalisation prior is not supported together with point sharding"); return CMLBA_ERR_UNSUPPORTED; }
         if (any && keep_prior()) {
             subset_to_marginalize = true; dirty = true;
             int rc = prepare(nullptr);                                   // setZero, computeAdjoints, computeDelta on the subset window (BA:2474-2486)
@@ -816,6 +822,8 @@ public:
         // addPoint's reference colours (integer-pixel read) and gradient weights (DSOContext.h:86-91, BA:405-411) from the host images
         if (P > 0) { point_init_kernel<<<(unsigned) (((size_t) P * 8 + 255) / 256), 256, 0, stream>>>(w, 0, P, d_pt_colors.p, d_pt_weights.p); launches++; CK(cudaGetLastError()); }
         w.world = world; w.rank = rank; w.cand_cap = 0;
+        w.p2p_on = (world > 1 && p2p_ready) ? 1 : 0;
+        for (int q = 0; q < MAXF; q++) w.p2p_base[q] = p2p_peer[q];
         if (world > 1) {
             // record capacity = the largest per-rank count of residuals towards the newest frame (one small all-reduce per window build)
             int mine = R - newest_begin, cap = 0;
@@ -1018,18 +1026,20 @@ public:
     void launch_stitch(int respect_done) {
         const int N = dw.N, n = dw.n;
         stitch_pair_kernel<<<N * N, ST_THREADS, stitch_smem(), stream>>>(dw, respect_done); launches++;
+        if (dw.p2p_on) dw.p2p_epoch = ++p2p_epoch;       // the same count on every rank: one exchange per stitched system
         assemble_kernel<<<(2 * n * n + 2 * n + 255) / 256 + 3, 256, 0, stream>>>(dw, respect_done); launches++;   // +3 CTAs: 20 warps for HA[C,C], bA[C]
     }
     int launch_solve_sequence(int respect_done) {
         launch_schur(respect_done);
         launch_stitch(respect_done);
-        if (world > 1) { int rc = allreduce_system(); if (rc) return rc; }
+        if (world > 1 && !dw.p2p_on) { int rc = allreduce_system(); if (rc) return rc; }      // with peer memory solve_kernel sums the ranks itself
         solve_kernel<<<1, 256, solve_smem(), stream>>>(dw, respect_done); launches++;
         if (dw.P > 0) { point_step_kernel<<<dw.n_pt_blocks, 256, 0, stream>>>(dw, respect_done); launches++; }
         return CMLBA_OK;
     }
 
     int allreduce_system() {
+        if (dw.p2p_on) { p2p_allreduce_kernel<<<(2 * dw.n * dw.n + 2 * dw.n + 255) / 256, 256, 0, stream>>>(dw, 0); launches++; return CMLBA_OK; }
         const size_t cnt = (size_t) 2 * dw.n * dw.n + 2 * dw.n;
         const int rc = g_nccl.AllReduce(d_sys.p, d_sys.p, cnt, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream);
         if (rc != 0) { set_error("ncclAllReduce failed"); return CMLBA_ERR_CUDA; }
@@ -1224,6 +1234,31 @@ public:
         out->steps = steps; out->residuals = dw.R; out->points = dw.P; out->frames = dw.N;
         out->ms_pass = tot / steps; out->ms_linearize = tk[0] / steps; out->ms_accumulate = tk[1] / steps; out->ms_schur = tk[2] / steps; out->ms_stitch = tk[3] / steps;
         out->launches_per_pass = per_pass;
+        return CMLBA_OK;
+    }
+
+    // ------------------------------------------------------------------ peer-memory exchange set-up
+    int comm_ipc_handle(void *out64) {
+        CK(cudaSetDevice(device));
+        if (world < 2) { set_error("cmlba_comm_init first"); return CMLBA_ERR_STATE; }
+        if (!p2p_local) { CK(cudaMalloc(&p2p_local, p2p_bytes())); CK(cudaMemset(p2p_local, 0, p2p_bytes())); CK(cudaDeviceSynchronize()); }
+        cudaIpcMemHandle_t hd;
+        CK(cudaIpcGetMemHandle(&hd, p2p_local));
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(out64, &hd, 64);
+        return CMLBA_OK;
+    }
+    int comm_ipc_open(const void *all) {
+        if (world < 2 || !p2p_local) { set_error("cmlba_comm_init and cmlba_comm_ipc_handle first"); return CMLBA_ERR_STATE; }
+        CK(cudaSetDevice(device));
+        for (int q = 0; q < world; q++) {
+            if (q == rank) { p2p_peer[q] = p2p_local; continue; }
+            cudaIpcMemHandle_t hd; memcpy(&hd, (const char *) all + 64 * q, 64);
+            void *ptr = nullptr;
+            CK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+            p2p_peer[q] = (char *) ptr;
+        }
+        p2p_ready = true; dirty = true; prepared = false;
         return CMLBA_OK;
     }
 
@@ -1515,6 +1550,9 @@ int cmlba_nccl_unique_id(void *uid) {
     if (!cmlba::g_nccl.load(err)) { g_create_error = err; return CMLBA_ERR_UNSUPPORTED; }
     return cmlba::g_nccl.GetUniqueId(uid) == 0 ? CMLBA_OK : CMLBA_ERR_CUDA;
 }
+
+int cmlba_comm_ipc_handle(cmlba_handle *h, void *handle_64) { HCHK; if (!handle_64) return CMLBA_ERR_ARG; return h->eng.comm_ipc_handle(handle_64); }
+int cmlba_comm_ipc_open(cmlba_handle *h, const void *handles) { HCHK; if (!handles) return CMLBA_ERR_ARG; return h->eng.comm_ipc_open(handles); }
 
 int cmlba_comm_init(cmlba_handle *h, const void *uid, int rank, int world) {
     HCHK; Engine &e = h->eng;

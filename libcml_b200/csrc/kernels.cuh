@@ -629,6 +629,54 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
 // Gathers the pair slots into sys = [HA | bA | H_sc | b_sc] (the multi-GPU allreduce payload), one thread per
 // element, fixed summation order.  Both matrices come out completed exactly like the tails of stitchDoubleTop
 // (BA:1857-1876: H[h,t] += H[t,h]^T, calibration rows mirrored) and stitchDoubleSC (BA:2033-2037).
+// ---- reduced-system exchange over NVLink peer memory ------------------------------------------------------------------
+// Every rank owns one cudaIpc-mapped buffer [flags u64[16] | pad | slots[2 epochs][world sources]].  assemble_kernel PUSHES
+// every element of this rank's partial sys into slot[epoch & 1][rank] of EVERY rank (P2P stores are fire-and-forget, no
+// remote latency on the critical path); its last CTA then stores the epoch into flags[rank] of every peer (release,
+// system scope).  The consumer (the prologue of solve_kernel, or p2p_allreduce_kernel) spins on its LOCAL flags and sums its
+// LOCAL slots in rank order: identical bits on every rank, no NCCL launch, no remote load.
+// Two epochs suffice: a rank can only be one exchange ahead of the slowest reader (its next signal needs every peer's flag).
+__device__ __forceinline__ unsigned long long *p2p_flags(const DevWin &w, int rk) { return reinterpret_cast<unsigned long long *>(w.p2p_base[rk]); }
+__device__ __forceinline__ double *p2p_slot(const DevWin &w, int owner, int src) {
+    return reinterpret_cast<double *>(w.p2p_base[owner] + 256) + ((size_t) (w.p2p_epoch & 1ull) * w.world + src) * P2P_SLOT_DOUBLES;
+}
+__device__ __forceinline__ void p2p_signal(const DevWin &w) {      // one thread, after a __threadfence_system() by the writers
+    for (int q = 0; q < w.world; q++) {
+        unsigned long long *f = p2p_flags(w, q) + w.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(f), "l"(w.p2p_epoch) : "memory");
+    }
+}
+// whole CTA (>= world threads).  Returns false on timeout (a peer never arrived): the caller flags the run as failed.
+__device__ __forceinline__ bool p2p_reduce(const DevWin &w, double *dst, const int count) {
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if ((int) threadIdx.x < w.world) {
+        const unsigned long long *f = p2p_flags(w, w.rank) + threadIdx.x;
+        unsigned long long v = 0; long spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(f) : "memory");
+            if (v >= w.p2p_epoch) break;
+            if (++spins > (1l << 23)) { s_ok = 0; break; }     // ~1 s: never hang the device on a protocol error
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    if (!s_ok) return false;
+    const double *base = p2p_slot(w, w.rank, 0);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+        double sum = 0.0;
+        for (int q = 0; q < w.world; q++) sum += __ldcg(base + (size_t) q * P2P_SLOT_DOUBLES + e);
+        dst[e] = sum;
+    }
+    __syncthreads();
+    return true;
+}
+__global__ void __launch_bounds__(256) p2p_allreduce_kernel(const DevWin w, const int respect_done) {
+    if (respect_done && w.ctrl->done) return;
+    if (!p2p_reduce(w, w.sys, 2 * w.n * w.n + 2 * w.n) && threadIdx.x == 0) { w.ctrl->failed = 1; w.ctrl->done = 1; }
+}
+
 // sum_k!=a slot(a,k)[o_row] + sum_k!=a slot(k,a)[o_col], all loads issued before the (fixed-order) adds
 __device__ __forceinline__ double sum_slots(const double *st, const int N, const int S, const int a, const int o_row, const int o_col) {
     double v = 0.0;
@@ -639,8 +687,12 @@ __device__ __forceinline__ double sum_slots(const double *st, const int N, const
     return v;
 }
 
-__global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int respect_done) {
-    if (respect_done && w.ctrl->done) return;
+// element e of this rank's sys: local buffer, or (peer exchange) the rank's slot in every rank's buffer
+__device__ __forceinline__ void sys_emit(const DevWin &w, const bool p2p, const int e, const double v) {
+    if (!p2p) { w.sys[e] = v; return; }
+    for (int q = 0; q < w.world; q++) p2p_slot(w, q, w.rank)[e] = v;
+}
+__device__ __forceinline__ void assemble_body(const DevWin &w, const bool p2p) {
     const int N = w.N, n = w.n, nn = n * n, S = st_stride(N);
     const double *st = w.st_out;
 #define SLOT(i, j) (st + (size_t) ((i) * N + (j)) * S)
@@ -653,7 +705,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int
         double v = 0.0;
         for (int q = lane; q < N * N; q += 32) { const int i = q / N, j = q - i * N; const double x = SLOT(i, i != j ? j : (i + 1) % N)[off]; v += (i != j) ? x : 0.0; }
         v = warp_sum_d(v);
-        if (lane == 0) w.sys[k < 16 ? (k >> 2) * n + (k & 3) : nn + (k - 16)] = v;
+        if (lane == 0) sys_emit(w, p2p, k < 16 ? (k >> 2) * n + (k & 3) : nn + (k - 16), v);
         return;
     }
     const int e = blockIdx.x * 256 + threadIdx.x;
@@ -701,7 +753,21 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int
         }
     }
 #undef SLOT
-    w.sys[e] = v;
+    sys_emit(w, p2p, e, v);
+}
+
+__global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int respect_done) {
+    if (respect_done && w.ctrl->done) return;
+    const bool p2p = w.p2p_on && w.world > 1;
+    assemble_body(w, p2p);
+    if (p2p) {   // the last CTA to finish publishes the epoch to every peer
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int ticket = atomicAdd(&w.ctrl->asm_done_count, 1);
+            if (ticket == (int) gridDim.x - 1) { w.ctrl->asm_done_count = 0; __threadfence_system(); p2p_signal(w); }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -719,6 +785,9 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
     double *red = x + n;        // [256]
     double *invd = red + 256;   // [m] reciprocals of the LDL^T pivots
     double *sysHA = w.sys, *sysbA = w.sys + nn, *sysHS = w.sys + nn + n, *sysbS = w.sys + 2 * nn + n;
+    if (w.p2p_on && w.world > 1) {   // sum of the ranks' partial systems over NVLink (replaces ncclAllReduce + its launch)
+        if (!p2p_reduce(w, w.sys, 2 * nn + 2 * n)) { if (tid == 0) { ctrl->failed = 1; ctrl->done = 1; } return; }
+    }
     // H <- HA (already completed by assemble_kernel)
     for (int e = tid; e < nn; e += 256) H[e] = sysHA[e];
     __syncthreads();

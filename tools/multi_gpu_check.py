@@ -40,7 +40,7 @@ def main():
     P = win["pt_host"].size
     sel = np.arange(P)[np.arange(P) % world == rank]
     ba = DSOBundleAdjustment(device=local, iterations=5)
-    comm_init(ba, rank, world)
+    ba.initCommunicator(rank, world, peer_memory=os.environ.get("CMLBA_NCCL_ONLY", "0") != "1")
     build(ba, win, sel)
     ok = ba.run(win["frame_cam"])
     r = ba.last_result
