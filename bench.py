@@ -247,7 +247,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_pass,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (projection f64)", "data": "synthetic",
            "config": {"workload": f"{args.workload}: {N} KF x {ppk} pts/KF per GPU, {W}x{H} level 0, {iters} GN iterations", "residuals_per_gpu": R,
-                      "l2": "flushed between timed passes (384 MB write outside the timed region)", "parallelism": f"points sharded x{world}, frames replicated" + ("" if world == 1 else (", reduced system summed by ncclAllReduce" if args.nccl_only else ", reduced system summed over NVLink peer memory")),
+                      "l2": "flushed between timed passes (384 MB write outside the timed region)", "parallelism": f"points sharded x{world}, frames replicated" + ("" if world == 1 else (", reduced system + post-linearize records over NVLink peer memory (cudaIpc)" if getattr(ba, "peer_memory", False) else ", reduced system by ncclAllReduce, post-linearize records by ncclAllGather")),
                       "pass": "linearize+accumulate+schur+stitch"},
            "ms_per_step_l2_warm": ms_pass_warm, "value_l2_warm": world * R / (ms_pass_warm * 1e-3),
            "kernel_ms": {"linearize": br.ms_linearize, "accumulate": br.ms_accumulate, "schur": br.ms_schur, "stitch": br.ms_stitch,

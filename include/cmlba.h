@@ -206,7 +206,7 @@ int cmlba_comm_init(cmlba_handle *h, const void *unique_id_128, int rank, int wo
  * them.  From then on assemble_kernel writes the rank's partial system into its buffer and signals the peers, and
  * solve_kernel sums the ranks' buffers with NVLink loads in its prologue (one kernel for the collective + the solve). */
 int cmlba_comm_ipc_handle(cmlba_handle *h, void *handle_64);
-int cmlba_comm_ipc_open(cmlba_handle *h, const void *handles /* [world_size][64] */);
+int cmlba_comm_ipc_open(cmlba_handle *h, const void *handles /* [world_size][64]; NULL switches back to NCCL (every rank must) */);
 
 /* library / build info: "libcmlba <version> sm_100a" */
 const char *cmlba_version(void);

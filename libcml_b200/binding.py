@@ -298,12 +298,23 @@ class DSOBundleAdjustment:
         ub = uid.cpu().numpy()
         self._ck(self.lib.cmlba_comm_init(self.h, ub.ctypes.data, rank, world))
         if peer_memory and world > 1:
+            # every rank must end up in the same mode: a failed cudaIpc mapping anywhere sends all ranks back to NCCL
+            ok = 1
             mine = np.zeros(64, dtype=np.uint8)
-            self._ck(self.lib.cmlba_comm_ipc_handle(self.h, mine.ctypes.data))
+            if self.lib.cmlba_comm_ipc_handle(self.h, mine.ctypes.data) != 0:
+                ok = 0
             allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(allh, torch.from_numpy(mine).cuda())
             packed = np.ascontiguousarray(torch.stack(allh).cpu().numpy())
-            self._ck(self.lib.cmlba_comm_ipc_open(self.h, packed.ctypes.data))
+            if ok and self.lib.cmlba_comm_ipc_open(self.h, packed.ctypes.data) != 0:
+                ok = 0
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            self.peer_memory = bool(flag.item())
+            if not self.peer_memory:
+                self._ck(self.lib.cmlba_comm_ipc_open(self.h, None))
+        else:
+            self.peer_memory = False
 
     def reset(self):
         self._ck(self.lib.cmlba_reset(self.h))

@@ -11,6 +11,8 @@ constexpr int T_STRIDE = 16;      // floats per (point,target) Schur row: JpJdF[
 constexpr int ACC_N = 96;         // 91 unique entries of the 13x13 block, padded to 3*32
 constexpr int LIN_THREADS = 32;   // linearize+accumulate: one warp-CTA per chunk, one thread per residual
 constexpr int ACC_CHUNK = 32;     // residuals per linearize+accumulate CTA (all in one (h,t) bin)
+constexpr int P2P_POST_CAND_MAX = 65536;      // candidates per rank record that fit the peer-memory exchange (else NCCL all-gather)
+constexpr size_t P2P_POST_DOUBLES = 8 + P2P_POST_CAND_MAX / 2;
 constexpr size_t P2P_SLOT_DOUBLES = 2 * (size_t) (8 * MAXF + 4) * (8 * MAXF + 4) + 2 * (8 * MAXF + 4);   // sys at the largest window
 constexpr int SC_CHUNK = 64;      // points per Schur CTA (all hosted in one frame)
 
@@ -131,7 +133,9 @@ struct DevWin {
     // peer exchange of the reduced system over NVLink (cudaIpc-mapped buffers, see p2p_reduce in kernels.cuh); null = NCCL path
     char *p2p_base[MAXF];          // every rank's exchange buffer: [flags u64[16] | pad to 256 B | slot 0 | slot 1]
     unsigned long long p2p_epoch;  // number of this exchange (same on every rank); slot = epoch & 1
-    int p2p_on;
+    unsigned long long p2p_post_epoch;   // same for the post-linearize records (flags u64[16] at byte 128)
+    int p2p_on, p2p_post_on;
+    int post_stride;               // doubles between the ranks' records in post_recv
     double *post_send;             // this rank's record
     const double *post_recv;       // world records
 };

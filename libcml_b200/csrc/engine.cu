@@ -230,7 +230,8 @@ public:
     DevBuf<double> d_post_send, d_post_recv; DevBuf<int> d_cap;   // multi-GPU post-linearize exchange
     // reduced-system exchange over NVLink peer memory (cudaIpc); falls back to ncclAllReduce when not opened
     char *p2p_local = nullptr; char *p2p_peer[MAXF] = {nullptr}; bool p2p_ready = false; unsigned long long p2p_epoch = 0;
-    size_t p2p_bytes() const { return 256 + (size_t) 2 * world * P2P_SLOT_DOUBLES * sizeof(double); }   // flags | slots[2 epochs][world sources]
+    size_t p2p_bytes() const { return 256 + (size_t) 2 * world * (P2P_SLOT_DOUBLES + P2P_POST_DOUBLES) * sizeof(double); }   // flags | sys slots[2][world] | post records[2][world]
+    unsigned long long p2p_post_epoch = 0;
 
     // device buffers
     DevBuf<FrameDev> d_frames; DevBuf<PairPre> d_pairs; DevBuf<Ctrl> d_ctrl;
@@ -835,7 +836,9 @@ public:
             w.cand_cap = std::max(cap, 1);
             const size_t rec_d = 8 + (size_t) (w.cand_cap + 1) / 2;
             CK(d_post_send.reserve(rec_d)); CK(d_post_recv.reserve(rec_d * world));
-            w.post_send = d_post_send.p; w.post_recv = d_post_recv.p;
+            w.post_send = d_post_send.p; w.post_recv = d_post_recv.p; w.post_stride = (int) rec_d;
+            w.p2p_post_on = (w.p2p_on && w.cand_cap <= P2P_POST_CAND_MAX) ? 1 : 0;
+            if (w.p2p_post_on) w.post_stride = (int) P2P_POST_DOUBLES;
         }
         dirty = false;
         return CMLBA_OK;
@@ -1013,9 +1016,15 @@ public:
     }
     void launch_post(int mode, int respect_done) {
         if (world > 1) {   // energy, convergence sums and the 0.7-quantile inputs of ALL ranks: one all-gather per linearization
-            pack_post_kernel<<<1, 1024, 0, stream>>>(dw, respect_done); launches++;
-            const size_t rec_d = 8 + (size_t) (dw.cand_cap + 1) / 2;
-            if (g_nccl.AllGather(d_post_send.p, d_post_recv.p, rec_d, /*ncclDouble*/ 8, comm, stream) != 0) set_error("ncclAllGather failed");
+            if (dw.p2p_post_on) {   // pushed through peer memory by pack_post_kernel itself
+                dw.p2p_post_epoch = ++p2p_post_epoch;
+                dw.post_recv = reinterpret_cast<const double *>(p2p_local + 256) + (size_t) 2 * world * P2P_SLOT_DOUBLES + (size_t) (dw.p2p_post_epoch & 1ull) * world * P2P_POST_DOUBLES;
+                pack_post_kernel<<<1, 1024, 0, stream>>>(dw, respect_done); launches++;
+            } else {
+                pack_post_kernel<<<1, 1024, 0, stream>>>(dw, respect_done); launches++;
+                const size_t rec_d = 8 + (size_t) (dw.cand_cap + 1) / 2;
+                if (g_nccl.AllGather(d_post_send.p, d_post_recv.p, rec_d, /*ncclDouble*/ 8, comm, stream) != 0) set_error("ncclAllGather failed");
+            }
         }
         post_linearize_kernel<<<1, 1024, 0, stream>>>(dw, mode, respect_done); launches++;
     }
@@ -1552,7 +1561,11 @@ int cmlba_nccl_unique_id(void *uid) {
 }
 
 int cmlba_comm_ipc_handle(cmlba_handle *h, void *handle_64) { HCHK; if (!handle_64) return CMLBA_ERR_ARG; return h->eng.comm_ipc_handle(handle_64); }
-int cmlba_comm_ipc_open(cmlba_handle *h, const void *handles) { HCHK; if (!handles) return CMLBA_ERR_ARG; return h->eng.comm_ipc_open(handles); }
+int cmlba_comm_ipc_open(cmlba_handle *h, const void *handles) {
+    HCHK;
+    if (!handles) { h->eng.p2p_ready = false; h->eng.dirty = true; h->eng.prepared = false; return CMLBA_OK; }   // NULL: back to ncclAllReduce
+    return h->eng.comm_ipc_open(handles);
+}
 
 int cmlba_comm_init(cmlba_handle *h, const void *uid, int rank, int world) {
     HCHK; Engine &e = h->eng;

@@ -640,6 +640,10 @@ __device__ __forceinline__ unsigned long long *p2p_flags(const DevWin &w, int rk
 __device__ __forceinline__ double *p2p_slot(const DevWin &w, int owner, int src) {
     return reinterpret_cast<double *>(w.p2p_base[owner] + 256) + ((size_t) (w.p2p_epoch & 1ull) * w.world + src) * P2P_SLOT_DOUBLES;
 }
+// post-linearize records: region after the sys slots, [2 epochs][world sources][P2P_POST_DOUBLES]; flags u64[16] at byte 128
+__device__ __forceinline__ double *p2p_post_slot(const DevWin &w, int owner, int src) {
+    return reinterpret_cast<double *>(w.p2p_base[owner] + 256) + (size_t) 2 * w.world * P2P_SLOT_DOUBLES + ((size_t) (w.p2p_post_epoch & 1ull) * w.world + src) * P2P_POST_DOUBLES;
+}
 __device__ __forceinline__ void p2p_signal(const DevWin &w) {      // one thread, after a __threadfence_system() by the writers
     for (int q = 0; q < w.world; q++) {
         unsigned long long *f = p2p_flags(w, q) + w.rank;
@@ -1094,7 +1098,24 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_prefix, s_k, s_n;
     const bool multi = w.world > 1;
-    const size_t rec_d = 8 + (size_t) (w.cand_cap + 1) / 2;             // doubles per rank record
+    const size_t rec_d = (size_t) w.post_stride;                        // doubles per rank record
+    if (multi && w.p2p_post_on) {   // records were pushed into this rank's buffer by every rank's pack_post_kernel: wait for all of them
+        __shared__ int s_ok;
+        if (tid == 0) s_ok = 1;
+        __syncthreads();
+        if (tid < w.world) {
+            const unsigned long long *f = p2p_flags(w, w.rank) + 16 + tid;
+            unsigned long long v = 0; long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(f) : "memory");
+                if (v >= w.p2p_post_epoch) break;
+                if (++spins > (1l << 23)) { s_ok = 0; break; }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        if (!s_ok) { if (tid == 0) { ctrl->failed = 1; ctrl->done = 1; } return; }
+    }
     // energy: fixed-order sum of the block partials (multi-GPU: of the ranks' sums, all-gathered by pack_post_kernel)
     double e = 0.0;
     if (!multi) for (int i = tid; i < w.n_lin_blocks; i += 1024) e += w.energy_part[i];
@@ -1242,13 +1263,36 @@ __global__ void __launch_bounds__(1024) pack_post_kernel(const DevWin w, const i
     e = warp_sum_d(e);
     if ((tid & 31) == 0) s_red[tid >> 5] = e;
     __syncthreads();
+    const int nloc = w.R - w.newest_begin;
+    if (w.p2p_post_on) {
+        // push this rank's record into every rank's buffer (fire-and-forget NVLink stores), then publish the epoch
+        for (int q = 0; q < w.world; q++) {
+            double *h = p2p_post_slot(w, q, w.rank);
+            if (tid == 0) {
+                double t = 0; for (int k = 0; k < 32; k++) t += s_red[k];
+                h[0] = t; h[1] = ctrl->sumNID; h[2] = (double) ctrl->numID; h[3] = (double) ctrl->pt_bad; h[4] = ctrl->prior_energy_pts; h[5] = h[6] = h[7] = 0.0;
+            }
+            float *c = reinterpret_cast<float *>(h + 8);
+            for (int k = tid; k < w.cand_cap; k += 1024) {
+                float v = -1.f;
+                if (k < nloc) { const int i = w.newest_begin + k; v = w.r_alive[i] ? w.r_new_energy_wo[i] : -1.f; }
+                c[k] = v;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) for (int q = 0; q < w.world; q++) {
+            unsigned long long *f = p2p_flags(w, q) + 16 + w.rank;
+            asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(f), "l"(w.p2p_post_epoch) : "memory");
+        }
+        return;
+    }
     if (tid == 0) {
         double t = 0; for (int k = 0; k < 32; k++) t += s_red[k];
         double *h = w.post_send;
         h[0] = t; h[1] = ctrl->sumNID; h[2] = (double) ctrl->numID; h[3] = (double) ctrl->pt_bad; h[4] = ctrl->prior_energy_pts; h[5] = h[6] = h[7] = 0.0;
     }
     float *c = reinterpret_cast<float *>(w.post_send + 8);
-    const int nloc = w.R - w.newest_begin;
     for (int k = tid; k < w.cand_cap; k += 1024) {
         float v = -1.f;
         if (k < nloc) { const int i = w.newest_begin + k; v = w.r_alive[i] ? w.r_new_energy_wo[i] : -1.f; }
