@@ -48,6 +48,22 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of linearize_kernel per launch, from the committed ncu --set full summary
+    (profiles/, captured on the c2 workload); None for other workloads or when the summary is absent."""
+    if workload != "c2":
+        return None, None
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernels_*.txt")), reverse=True):
+        txt = open(path).read()
+        m = re.search(r"== void linearize_kernel.*?dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+).*?dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", txt, re.S)
+        if m:
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            return float(m.group(1)) * unit.get(m.group(2), 1.0) + float(m.group(3)) * unit.get(m.group(4), 1.0), os.path.relpath(path, ROOT)
+    return None, None
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi SM clocks / throttle reasons during the timed region."""
 
@@ -244,17 +260,19 @@ def main():
 
     peak, peak_src = measured_peaks()
     achieved = R * b_alg(N) / (ms_lin * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(args.workload)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_pass,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (projection f64)", "data": "synthetic",
            "config": {"workload": f"{args.workload}: {N} KF x {ppk} pts/KF per GPU, {W}x{H} level 0, {iters} GN iterations", "residuals_per_gpu": R,
                       "l2": "flushed between timed passes (384 MB write outside the timed region)", "parallelism": f"points sharded x{world}, frames replicated" + ("" if world == 1 else (", reduced system + post-linearize records over NVLink peer memory (cudaIpc)" if getattr(ba, "peer_memory", False) else ", reduced system by ncclAllReduce, post-linearize records by ncclAllGather")),
                       "pass": "linearize+accumulate+schur+stitch"},
            "ms_per_step_l2_warm": ms_pass_warm, "value_l2_warm": world * R / (ms_pass_warm * 1e-3),
-           "kernel_ms": {"linearize": br.ms_linearize, "accumulate": br.ms_accumulate, "schur": br.ms_schur, "stitch": br.ms_stitch,
-                         "linearize_l2_warm": brw.ms_linearize},
+           "kernel_ms": {"linearize_accumulate": br.ms_linearize, "schur": br.ms_schur, "stitch_assemble": br.ms_stitch,
+                         "linearize_accumulate_l2_warm": brw.ms_linearize, "event_overhead_per_interval": br.ms_accumulate,
+                         "note": "event-to-event intervals of a separate loop; each includes one event-record overhead"},
            "run": {"gpu_ms": run_gpu_ms, "kernel_launches": run_launches, "iterations": e2e_iters},
            "roofline": {"bound": "hbm", "kernel": "linearize_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": peak_src, "bytes_per_unit": b_alg(N), "units_per_launch": R},
+                        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_unit": b_alg(N), "units_per_launch": R},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                    "what": f"reset + set_calib + {N} x add_frame (pinned host images, asynchronous upload) + add_points + run(up to {iters} GN iterations, {e2e_iters} executed) + get_frames/get_points"},
            "gpu_launches": int(br.launches_per_pass * args.steps),

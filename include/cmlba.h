@@ -182,7 +182,8 @@ int cmlba_reset(cmlba_handle *h);
 typedef struct cmlba_bench_result {
     int steps, residuals, points, frames, launches_per_pass;
     double ms_pass;         /* mean duration of one whole pass */
-    double ms_linearize, ms_accumulate, ms_schur, ms_stitch;   /* mean per-kernel durations (separate loop) */
+    double ms_linearize, ms_accumulate, ms_schur, ms_stitch;   /* mean event-to-event intervals of a separate loop: linearize+accumulate (fused),
+                                                                * an EMPTY interval (= the event overhead every interval carries), Schur, stitch+assemble */
 } cmlba_bench_result;
 int cmlba_bench_pass(cmlba_handle *h, int steps, int warmup, int flush_l2, cmlba_bench_result *out);
 

@@ -1228,7 +1228,7 @@ public:
             float ms = 0; CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); tot += ms;
         }
         const int per_pass = (launches - l0) / steps;
-        for (int i = 0; i < steps; i++) {          // per-kernel breakdown
+        for (int i = 0; i < steps; i++) {          // per-kernel breakdown (every interval carries one event-record overhead, reported as ms_accumulate)
             flush();
             CK(cudaEventRecord(ev[0], stream)); launch_linearize(0, 0);
             CK(cudaEventRecord(ev[1], stream));

@@ -970,9 +970,6 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
         if (tid == 0) ctrl->stats[4] = sqrt(v);
     }
     // frame steps + states (BA:1433-1441, 957-973; DSOFrame::doStepFromBackup) and convergence sums
-    __shared__ int s_fail;
-    if (tid == 0) s_fail = 0;
-    __syncthreads();
     if (tid < N) {
         FrameDev &f = w.frames[tid];
         double step[10];

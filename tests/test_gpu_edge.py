@@ -1,0 +1,133 @@
+"""GPU (-m gpu): options and edge cases of the path through the C ABI.  Checker = the numpy oracle (pinned against the reference's
+goldens in tests/test_oracle_golden.py) on the same inputs, or the reference's documented error behaviour."""
+import numpy as np
+import pytest
+
+import ba_oracle as O
+from parity_util import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _ba(**kw):
+    from libcml_b200 import DSOBundleAdjustment
+    return DSOBundleAdjustment(device=0, **kw)
+
+
+def _w2c(w):
+    return np.stack([np.concatenate([R.ravel(), t]) for R, t in w.pre_w2c])
+
+
+def _window(**kw):
+    from libcml_b200 import synth
+    args = dict(W=200, H=150, N=4, pts_per_kf=120, iterations=4, affine=True, seed=21)
+    args.update(kw)
+    return synth.make_window(**args)
+
+
+@pytest.mark.parametrize("opt_a,opt_b", [(0, 1), (1, 0), (0, 0)])
+def test_fixed_affine_parameters(opt_a, opt_b):
+    """optimizeLightA / optimizeLightB = false (BA:273-278, priors BA:1140-1164)."""
+    win = _window()
+    ba = _ba(optimize_light_a=opt_a, optimize_light_b=opt_b)
+    cams = ba.loadWindow(win)
+    assert ba.run(cams, iterations=4)
+    ow = O.Window(win, optimize_a=bool(opt_a), optimize_b=bool(opt_b))
+    assert O.run(ow)
+    fr = ba.getFrames(); pts = ba.getPoints()
+    assert rel(fr["world_to_cam"], _w2c(ow)) < 1e-4
+    aff = np.stack([ow.aff(i) for i in range(ow.N)])
+    assert np.abs(fr["affine"] - aff).max() < 1e-4 * max(1.0, np.abs(aff).max())
+    assert rel(pts["idepth"], ow.idepth[pts["id"]]) < 1e-3
+    assert abs(ba.last_result.energy_last - ow.fin_energy) / ow.fin_energy < 1e-4
+    ba.close()
+
+
+def test_update_points_only():
+    """run(updatePointsOnly = true): frame pose steps are zeroed (BA:957-964), points and affine still move."""
+    win = _window(seed=22)
+    win["update_points_only"] = np.array([1], np.int32)
+    ba = _ba()
+    cams = ba.loadWindow(win)
+    assert ba.run(cams, updatePointsOnly=True, iterations=4)
+    ow = O.Window(win)
+    assert O.run(ow)
+    fr = ba.getFrames(); pts = ba.getPoints()
+    assert rel(fr["world_to_cam"], _w2c(ow)) < 1e-6          # poses only change through setStateFromCamera
+    assert rel(pts["idepth"], ow.idepth[pts["id"]]) < 1e-3
+    assert ba.last_result.iterations_done == ow.iterations_done
+    ba.close()
+
+
+def test_large_motion_out_of_bounds_residuals():
+    """Strong motion on a small image: many residuals leave the image (OOB, BA:115-118, 209-212), points lose all residuals ->
+    getOutliers().  States, surviving residuals and outliers must agree with the oracle exactly."""
+    from libcml_b200 import synth
+    win = synth.make_window(W=120, H=90, N=5, pts_per_kf=80, iterations=3, affine=False, seed=5, pose_noise=2e-3)
+    win["frame_cam"] = win["frame_cam"].copy()
+    win["frame_cam"][:, 9] += np.linspace(0, 0.25, 5)        # drift along x: late frames see little of the early ones
+    win["frame_evalpt"] = win["frame_cam"].copy()
+    ba = _ba()
+    cams = ba.loadWindow(win)
+    ok = ba.run(cams, iterations=3)
+    ow = O.Window(win)
+    assert ok == O.run(ow)
+    rs = ba.getResiduals()
+    mine = set(zip(rs["point_id"].tolist(), rs["target_frame_id"].tolist()))
+    theirs = set(zip(ow.res_point[ow.res_alive].tolist(), ow.res_target[ow.res_alive].tolist()))
+    assert int((~ow.res_alive).sum()) > 50                   # the scenario must actually drop residuals
+    assert len(mine ^ theirs) <= max(1, len(theirs) // 500)
+    out_ref = set(np.nonzero(np.bincount(ow.res_point[ow.res_alive], minlength=ow.P) == 0)[0].tolist())
+    assert len(set(ba.getOutliers().tolist()) ^ out_ref) <= 1
+    ba.close()
+
+
+def test_frame_without_points_and_single_point():
+    """Ragged window: one frame hosts nothing, another a single point."""
+    from libcml_b200 import synth
+    win = synth.make_window(W=160, H=120, N=4, pts_per_kf=40, iterations=3, affine=False, seed=9)
+    keep = (win["pt_host"] != 2)
+    keep[np.nonzero(win["pt_host"] == 1)[0][1:]] = False      # frame 1 keeps exactly one point, frame 2 none
+    for k in ("pt_host", "pt_xy", "pt_idepth"):
+        win[k] = win[k][keep]
+    ba = _ba()
+    cams = ba.loadWindow(win)
+    assert ba.run(cams, iterations=3)
+    ow = O.Window(win)
+    assert O.run(ow)
+    fr = ba.getFrames(); pts = ba.getPoints()
+    assert rel(fr["world_to_cam"], _w2c(ow)) < 1e-4
+    assert rel(pts["idepth"], ow.idepth[pts["id"]]) < 1e-3
+    ba.close()
+
+
+def test_error_behaviour():
+    """Argument / state errors come back as status codes with a message; nothing aborts (SURVEY 8b error convention)."""
+    from libcml_b200 import CmlbaError, synth
+    win = synth.make_config("tiny")
+    ba = _ba()
+    with pytest.raises(CmlbaError) as e:                      # no calibration yet
+        ba.addNewFrame(0, win["frame_evalpt"][0], 0.0, 0.0, 1.0, win["grad"][0])
+    assert e.value.code == -3                                  # CMLBA_ERR_STATE
+    ba.loadWindow(win)
+    with pytest.raises(CmlbaError):                            # frame ids must increase (DSOContext.h:139-143 aborts)
+        ba.addNewFrame(1, win["frame_evalpt"][0], 0.0, 0.0, 1.0, win["grad"][0])
+    with pytest.raises(CmlbaError):                            # host frame not in the window
+        ba.addPoints([10_000], [77], [[20.0, 20.0]], [0.5])
+    with pytest.raises(CmlbaError):                            # too close to the border for the pattern + bilinear footprint
+        ba.addPoints([10_001], [0], [[1.0, 20.0]], [0.5])
+    n = ba.lib.cmlba_num_points(ba.h)
+    ba.addPoints([0], [0], [[20.0, 20.0]], [0.5])              # already in the window: skipped (BA:386-388)
+    assert ba.lib.cmlba_num_points(ba.h) == n
+    ba.removePoint(123456)                                     # unknown point: no-op (DSOContext.h:95-97)
+    assert ba.run(win["frame_cam"], iterations=2)
+    empty = _ba()
+    empty.setCalibration(*[float(v) for v in win["calib"]], int(win["size"][0]), int(win["size"][1]))
+    empty.addNewFrame(0, win["frame_evalpt"][0], 0.0, 0.0, 1.0, win["grad"][0])
+    with pytest.raises(CmlbaError):                            # "No points..." (BA:759-762 returns false)
+        empty.run(None)
+    for i in range(1, 16):
+        empty.addNewFrame(i, win["frame_evalpt"][0], 0.0, 0.0, 1.0, win["grad"][0])
+    with pytest.raises(CmlbaError):                            # CMLBA_MAX_FRAMES
+        empty.addNewFrame(16, win["frame_evalpt"][0], 0.0, 0.0, 1.0, win["grad"][0])
+    ba.close(); empty.close()
