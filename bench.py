@@ -222,7 +222,8 @@ def main():
     value = world * R / (ms_pass * 1e-3)
 
     # ---------------- end to end through the C ABI from pinned host buffers
-    grad_pinned = torch.from_numpy(win["grad"]).pin_memory()
+    # the rectified level-0 gray images (what CaptureImage::getGrayImage(0) holds); the derivative images are built on the device
+    grad_pinned = torch.from_numpy(np.ascontiguousarray(win["gray"], dtype=np.float32)).pin_memory()
     gnp = grad_pinned.numpy()
     h2d = gnp.nbytes + win["pt_xy"].nbytes + win["pt_idepth"].nbytes + 2 * 8 * P + cams.nbytes + 12 * 8 * N
     e2e_t, e2e_iters, d2h = [], 0, 0
@@ -234,7 +235,7 @@ def main():
         ba.reset()
         ba.setCalibration(*[float(v) for v in win["calib"]], W, H)
         for f in range(N):
-            ba.addNewFrame(f, win["frame_evalpt"][f], win["frame_affine"][f, 0], win["frame_affine"][f, 1], win["frame_exposure"][f], gnp[f], False)
+            ba.addNewFrameGray(f, win["frame_evalpt"][f], win["frame_affine"][f, 0], win["frame_affine"][f, 1], win["frame_exposure"][f], gnp[f], False)
         ba.addPoints(np.arange(P), win["pt_host"], win["pt_xy"], win["pt_idepth"])
         ok = ba.run(cams, iterations=iters)
         fr = ba.getFrames(); pts = ba.getPoints()
@@ -274,7 +275,7 @@ def main():
            "roofline": {"bound": "hbm", "kernel": "linearize_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_unit": b_alg(N), "units_per_launch": R},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
-                   "what": f"reset + set_calib + {N} x add_frame (pinned host images, asynchronous upload) + add_points + run(up to {iters} GN iterations, {e2e_iters} executed) + get_frames/get_points"},
+                   "what": f"reset + set_calib + {N} x add_frame_gray (pinned host gray images, asynchronous upload, derivative images built on the device) + add_points + run(up to {iters} GN iterations, {e2e_iters} executed) + get_frames/get_points"},
            "gpu_launches": int(br.launches_per_pass * args.steps),
            "clocks": clocks}
     # ---------------- CPU baseline: the reference itself on this box's host cores (rank 0, N=1 only)

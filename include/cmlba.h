@@ -93,6 +93,13 @@ int cmlba_set_calib(cmlba_handle *h, double fx, double fy, double cx, double cy,
 int cmlba_add_frame(cmlba_handle *h, int64_t frame_id, const double world_to_cam[12], double aff_a, double aff_b,
                     double exposure_time, const float *grad_aos, int is_init_frame);
 
+/* Same as cmlba_add_frame, but from the rectified level-0 GRAY image (frame->getCaptureFrame().getGrayImage(0): width*height floats).
+ * The derivative image (I, dI/dx, dI/dy) is built on the device exactly as CaptureImageGenerator::generate does
+ * (capture/CaptureImage.cpp:249 -> Array2D::gradientImage, image/Array2D.h:288-294, 314-331: central differences * 0.5, zero on the
+ * 1-pixel border) -- bit-identical texels, a third of the host->device traffic. */
+int cmlba_add_frame_gray(cmlba_handle *h, int64_t frame_id, const double world_to_cam[12], double aff_a, double aff_b,
+                         double exposure_time, const float *gray /* [height][width] */, int is_init_frame);
+
 /* addPoints(const PointSet&) (BA:382-415).  n points; host_frame_id[i] = getReferenceFrame()->getId(),
  * xy = getReferenceCorner() (float x,y), idepth = getReferenceInverseDepth().  Reference colours
  * (integer-pixel gray, MapObject.h:398-399) and gradient weights (BA:405-411) are computed on the

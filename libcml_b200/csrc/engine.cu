@@ -321,7 +321,8 @@ public:
         return CMLBA_OK;
     }
 
-    int add_frame(int64_t id, const double *w2c, double a, double b, double exposure, const float *grad, int is_init) {
+    // gray != 0: `grad` is the rectified level-0 gray image (W*H floats); the derivative image is built on the device
+    int add_frame(int64_t id, const double *w2c, double a, double b, double exposure, const float *grad, int is_init, int gray = 0) {
         TSCOPE("add_frame");
         if (!have_calib) { set_error("cmlba_set_calib must be called before cmlba_add_frame"); return CMLBA_ERR_STATE; }
         if (!w2c || !grad) { set_error("null pointer"); return CMLBA_ERR_ARG; }
@@ -348,11 +349,13 @@ public:
         // staging buffers: with synchronous uploads two alternate (the previous repack may still run); asynchronous uploads
         // keep one per window slot, because several copies are in flight
         const int sb = cfg.async_image_upload ? (int) frames_.size() : (stage_flip ^= 1);
-        CK(d_stage[sb].reserve(npix * 3));
+        const size_t nfl = gray ? npix : npix * 3;
+        CK(d_stage[sb].reserve(nfl));
         if (!img_pool.empty()) { f.d_img = img_pool.back(); img_pool.pop_back(); } else CK(cudaMalloc(&f.d_img, npix * sizeof(float4)));
-        CK(cudaMemcpyAsync(d_stage[sb].p, grad, npix * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_stage[sb].p, grad, nfl * sizeof(float), cudaMemcpyHostToDevice, stream));
         CK(cudaEventRecord(ev_copy, stream));
-        repack_image_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(d_stage[sb].p, f.d_img, (int) npix);
+        if (gray) gradient_texel_kernel<<<dim3((unsigned) ((W + 127) / 128), (unsigned) H), 128, 0, stream>>>(d_stage[sb].p, f.d_img, W, H);
+        else repack_image_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(d_stage[sb].p, f.d_img, (int) npix);
         CK(cudaGetLastError());
         const int slot = (int) frames_.size();
         frames_.push_back(f);
@@ -1286,6 +1289,12 @@ public:
     int read(const std::string &name, void *dst, size_t cap, size_t *bytes) {
         if (name == "host_timing") { const std::string t = timers.text() + "device allocations " + std::to_string(g_dev_mallocs) + ", pinned allocations " + std::to_string(g_pin_mallocs) + "\n"; return host_out(t.data(), t.size(), dst, cap, bytes); }
         if (name == "host_timing_reset") { timers.acc.clear(); if (bytes) *bytes = 0; return CMLBA_OK; }
+        if (name.rfind("image", 0) == 0) {   // "image<slot>": the float4 texels (I, dx, dy, 0) of a window frame
+            const int slot = atoi(name.c_str() + 5);
+            if (slot < 0 || slot >= (int) frames_.size() || !frames_[slot].d_img) { set_error("no such frame slot"); return CMLBA_ERR_ARG; }
+            CK(cudaSetDevice(device)); CK(cudaStreamSynchronize(stream));
+            return copy_out(frames_[slot].d_img, (size_t) W * H, dst, cap, bytes);
+        }
         if (name == "HM") return host_out(HM.data(), HM.size() * 8, dst, cap, bytes);
         if (name == "bM") return host_out(bM.data(), bM.size() * 8, dst, cap, bytes);
         if (name == "frame_counters") {   // [N][4] int32: flagged, numMarginalized, numResidualsOut, residuals targeting the frame
@@ -1404,6 +1413,7 @@ const char *cmlba_last_error(const cmlba_handle *h) { return h ? h->eng.err.c_st
 
 int cmlba_set_calib(cmlba_handle *h, double fx, double fy, double cx, double cy, int w, int hh) { HCHK; return h->eng.set_calib(fx, fy, cx, cy, w, hh); }
 int cmlba_add_frame(cmlba_handle *h, int64_t id, const double w2c[12], double a, double b, double exposure, const float *grad, int is_init) { HCHK; return h->eng.add_frame(id, w2c, a, b, exposure, grad, is_init); }
+int cmlba_add_frame_gray(cmlba_handle *h, int64_t id, const double w2c[12], double a, double b, double exposure, const float *gray, int is_init) { HCHK; return h->eng.add_frame(id, w2c, a, b, exposure, gray, is_init, 1); }
 int cmlba_add_points(cmlba_handle *h, int n, const int64_t *pid, const int64_t *host, const float *xy, const double *idepth) { HCHK; return h->eng.add_points(n, pid, host, xy, idepth); }
 int cmlba_remove_point(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove_point(id); }
 int cmlba_remove_frame(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove_frame(id); }

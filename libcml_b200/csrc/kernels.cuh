@@ -1367,6 +1367,22 @@ __global__ void __launch_bounds__(256) reset_window_kernel(const DevWin w) {
     if (w.dbg) for (size_t i = tid; i < (size_t) w.R * DBG_STRIDE; i += nth) w.dbg[i] = 0.f;
 }
 
+// Level-0 derivative image straight from the rectified gray image (CaptureImageGenerator::generate, capture/CaptureImage.cpp:249;
+// Array2D::gradientImage / gradient, image/Array2D.h:288-294, 314-331): (I, (I[x+1]-I[x-1])*0.5, (I[y+1]-I[y-1])*0.5), all three
+// channels zero on the 1-pixel border.  Bit-exact with the reference's GradientImage; a third of the upload volume.
+__global__ void gradient_texel_kernel(const float *__restrict__ gray, float4 *__restrict__ dst, const int W, const int H) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x >= 1 && y >= 1 && x < W - 1 && y < H - 1) {
+        const float *p = gray + (size_t) y * W + x;
+        t.x = p[0];
+        t.y = (p[1] - p[-1]) * 0.5f;
+        t.z = (p[W] - p[-W]) * 0.5f;
+    }
+    dst[(size_t) y * W + x] = t;
+}
+
 // AoS (I,dx,dy) 12-byte texels -> float4 texels (one aligned 128-bit load per bilinear tap)
 __global__ void repack_image_kernel(const float *__restrict__ src, float4 *__restrict__ dst, const int npix) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -131,3 +131,29 @@ def test_error_behaviour():
     with pytest.raises(CmlbaError):                            # CMLBA_MAX_FRAMES
         empty.addNewFrame(16, win["frame_evalpt"][0], 0.0, 0.0, 1.0, win["grad"][0])
     ba.close(); empty.close()
+
+
+def test_gray_upload_builds_identical_derivative_image():
+    """cmlba_add_frame_gray: the device-built level-0 derivative image equals the reference's GradientImage bit for bit
+    (capture/CaptureImage.cpp:249, image/Array2D.h:288-294, 314-331), so run() is bitwise the same as with the 3-channel upload."""
+    from libcml_b200 import synth
+    win = synth.make_config("tiny_affine")
+    N = win["frame_evalpt"].shape[0]; P = win["pt_host"].size
+    W, H = int(win["size"][0]), int(win["size"][1])
+    res = []
+    for gray in (False, True):
+        ba = _ba()
+        ba.setCalibration(*[float(v) for v in win["calib"]], W, H)
+        for i in range(N):
+            args = (i, win["frame_evalpt"][i], win["frame_affine"][i, 0], win["frame_affine"][i, 1], win["frame_exposure"][i])
+            if gray:
+                ba.addNewFrameGray(*args, win["gray"][i])
+            else:
+                ba.addNewFrame(*args, win["grad"][i])
+        tex = np.stack([ba.read(f"image{i}", np.float32).reshape(H, W, 4) for i in range(N)])
+        assert np.array_equal(tex[..., :3], win["grad"]) and not tex[..., 3].any()
+        ba.addPoints(np.arange(P), win["pt_host"], win["pt_xy"], win["pt_idepth"])
+        assert ba.run(win["frame_cam"], iterations=4)
+        res.append((ba.getFrames()["world_to_cam"].copy(), ba.getPoints()["idepth"].copy()))
+        ba.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
