@@ -40,7 +40,7 @@ def gradient_image(gray):
 
 
 def make_window(W=640, H=480, N=8, pts_per_kf=2000, iterations=6, affine=False, seed=1234,
-                idepth_noise=0.005, pose_noise=5e-4, fej_offset=True, with_gradients=True):
+                idepth_noise=0.005, pose_noise=5e-4, fej_offset=True, with_gradients=True, low_freq=False):
     rng = np.random.default_rng(seed)
     fx = fy = 0.78 * W
     cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
@@ -55,10 +55,20 @@ def make_window(W=640, H=480, N=8, pts_per_kf=2000, iterations=6, affine=False, 
     phx = rng.uniform(0, 2 * np.pi, nterm); phy = rng.uniform(0, 2 * np.pi, nterm)
     amp = rng.uniform(12.0, 17.5, nterm)
 
+    if low_freq:
+        # coarse-to-fine consumers (the tracker, SURVEY 8f NEXT #1) need structure that survives four halvings: periods 60-400 px
+        rl = np.random.default_rng(seed + 7919)
+        lwx = 2 * np.pi / (rl.uniform(60, 400, 5) * m_per_px); lwy = 2 * np.pi / (rl.uniform(60, 400, 5) * m_per_px)
+        lphx = rl.uniform(0, 2 * np.pi, 5); lphy = rl.uniform(0, 2 * np.pi, 5); lamp = rl.uniform(8.0, 14.0, 5)
+
     def texture(X, Y):
         T = np.full(X.shape, 127.5)
         for j in range(nterm):
             T = T + amp[j] * np.sin(wx[j] * X + phx[j]) * np.sin(wy[j] * Y + phy[j])
+        if low_freq:
+            T = 127.5 + 0.45 * (T - 127.5)
+            for j in range(5):
+                T = T + lamp[j] * np.sin(lwx[j] * X + lphx[j]) * np.sin(lwy[j] * Y + lphy[j])
         return T
 
     # truth trajectory (world -> camera)

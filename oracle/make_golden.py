@@ -103,7 +103,54 @@ def rejection():
     print("reject window", os.path.getsize(os.path.join(OUT, "reject_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "reject_golden.cmlw")) // 1024, "KB")
 
 
+def tracker():
+    """DSOTracker::makeCoarseDepthL0 + optimize of the reference (SURVEY 8f NEXT #1) on a 3-frame window: frame 1 is the tracking reference, frame 2 the
+    frame to track.  Case a: nominal; b: affine brightness start 60 grey levels off (every residual saturated at the coarsest level -> cutoff doubling and the
+    one-time level repeat, DSOTracker.cpp:72-76,198-201); c: start pose far off (fewer than 20 terms -> early exit, DSOTracker.cpp:65-69)."""
+    tmp = "/tmp/cmlba_golden"
+    os.makedirs(tmp, exist_ok=True)
+    N, seed = 3, 31
+    win = synth.make_window(256, 192, N, 400, 4, True, seed=seed, low_freq=True)
+    rng = np.random.default_rng(seed + 1)
+    win["track_ref"] = np.array([N - 2], np.int32); win["track_new"] = np.array([N - 1], np.int32)
+    cam = win["truth_frame"][N - 1].copy(); cam[9:] += 3e-3 * rng.standard_normal(3)
+    win["pt_uncertainty"] = 1.0 / (rng.uniform(50, 5000, win["pt_host"].size) + 0.01)
+    win["frame_cam"] = win["truth_frame"].copy(); win["frame_evalpt"] = win["truth_frame"].copy()
+    win["pt_idepth"] = win["truth_idepth"] * (1 + 0.01 * rng.standard_normal(win["pt_host"].size))
+    far = cam.copy(); far[9:] += np.array([4.0, 0.0, 0.0])
+    cases = {"a": (cam, (0.0, 0.0)), "b": (cam, (0.0, 60.0)), "c": (far, (0.0, 0.0))}
+    gold = {}
+    for name, (c, aff) in cases.items():
+        win["track_init_cam"] = c; win["track_new_affine"] = np.array(aff)
+        full = os.path.join(tmp, f"track_{name}.cmlw")
+        cmlw.save(full, {k: v for k, v in win.items() if k != "grad"})
+        run_ref(full, "track", os.path.join(tmp, f"track_{name}_out.cmlw"))
+        g = cmlw.load(os.path.join(tmp, f"track_{name}_out.cmlw"))
+        if name == "a":
+            import tracker_oracle as T
+            L = g["trk_K"].shape[0]
+            pyr = T.build_pyramid(win["gray"][N - 1], L)
+            for l in range(L):       # the reference's pyramid and derivative images must equal the restatement bit for bit; then they are dropped
+                assert np.array_equal(pyr[l][1], g[f"trk_grad{l}"]), f"pyramid level {l} differs from the reference"
+            for k in ("trk_K", "trk_levels_wh", "trk_pc_n"):
+                gold[k] = g[k]
+            for l in range(L):
+                gold[f"trk_pc{l}"] = g[f"trk_pc{l}"]
+        for k in ("trk_cam", "trk_affine", "trk_E", "trk_numTermsInE", "trk_numSaturated", "trk_numRobust", "trk_levelCutoffRepeat", "trk_flow", "trk_relAff", "trk_covariance",
+                  "trk_isCorrect", "trk_tooManySaturated"):
+            gold[f"{name}_{k}"] = g[k]
+        gold[f"{name}_init_cam"] = c; gold[f"{name}_new_affine"] = np.array(aff)
+    assert gold["a_trk_isCorrect"][0] == 1 and gold["b_trk_isCorrect"][0] == 1 and gold["c_trk_isCorrect"][0] == 0
+    slim = {k: v for k, v in win.items() if k not in ("grad", "truth_idepth", "track_init_cam", "track_new_affine")}
+    cmlw.save(os.path.join(OUT, "track_window.cmlw"), slim)
+    cmlw.save(os.path.join(OUT, "track_golden.cmlw"), gold)
+    print("track window", os.path.getsize(os.path.join(OUT, "track_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "track_golden.cmlw")) // 1024, "KB")
+
+
 if __name__ == "__main__":
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    if len(sys.argv) > 1 and sys.argv[1] == "tracker":
+        tracker(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "maintenance":
         maintenance(); maintenance(prior=True); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "rejection":

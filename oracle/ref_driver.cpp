@@ -6,7 +6,7 @@
 // Nothing here is linked into, imported by, or executed from the product (libcml_b200/, include/);
 // only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs run it.
 //
-//   cmlba_ref --window in.cmlw --mode stages|run|maintain|bench --out out.cmlw [--repeat K]
+//   cmlba_ref --window in.cmlw --mode stages|run|maintain|track|bench --out out.cmlw [--repeat K]
 //
 // mode stages : replays DSOBundleAdjustment::run (BA:744-910) call by call through the class's own
 //               (protected) methods and dumps every intermediate quantity SURVEY.md section 8(d) lists.
@@ -54,6 +54,7 @@
 #include <cml/map/Map.h>
 #include <cml/capture/CaptureImage.h>
 #include <cml/optimization/dso/DSOBundleAdjustment.h>
+#include <cml/optimization/dso/DSOTracker.h>
 #undef private
 #undef protected
 
@@ -539,6 +540,76 @@ static int runMaintain(RefWindow *w, const cmlw::File &in, cmlw::File &out) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// mode track: the coarse-to-fine direct image alignment of DSOTracker (NEXT #1): makeCoarseDepthL0 on the reference
+// keyframe (optimization/dso/DSOTracker.cpp:494-725) and optimize() of a new frame against it (:15-246).
+// Window keys: track_ref, track_new (frame indices), track_init_cam [12] (initial world->cam guess of the new frame),
+// pt_uncertainty [P], track_new_affine [2] (initial a,b of the new frame).  With --repeat K also times optimize().
+static int runTrack(RefWindow *w, const cmlw::File &in, cmlw::File &out, int repeat) {
+    const int refIdx = in.get("track_ref").as<int32_t>()[0], newIdx = in.get("track_new").as<int32_t>()[0];
+    PFrame ref = w->frames[refIdx], nf = w->frames[newIdx];
+    DSOTracker tracker(w->root);
+    const double *unc = in.get("pt_uncertainty").as<double>();
+    PointSet pts;
+    for (int p = 0; p < w->P; p++) {
+        if (w->frameIndex.at(w->points[p]->getReferenceFrame().p()) == newIdx) continue;      // points hosted in the frame to track do not exist yet
+        w->points[p]->setUncertainty(unc[p]);
+        pts.insert(w->points[p]);
+    }
+    tracker.makeCoarseDepthL0(ref, pts);
+    DSOTrackerPrivate *cd = tracker.get(ref);
+    const int L = nf->getCaptureFrame().getPyramidLevels();
+    std::vector<int32_t> wh(2 * L), npc(L);
+    std::vector<double> Ks(4 * L);
+    for (int l = 0; l < L; l++) {
+        wh[2 * l] = nf->getWidth(l); wh[2 * l + 1] = nf->getHeight(l);
+        Matrix33 K = nf->getK(l);
+        Ks[4 * l] = K(0, 0); Ks[4 * l + 1] = K(1, 1); Ks[4 * l + 2] = K(0, 2); Ks[4 * l + 3] = K(1, 2);
+        DSOTrackerPrivateLevel &lv = cd->level[l];
+        npc[l] = lv.n();
+        std::vector<float> pc((size_t) 4 * lv.n());
+        for (int i = 0; i < lv.n(); i++) { pc[4 * i] = lv.PCu(i); pc[4 * i + 1] = lv.PCv(i); pc[4 * i + 2] = lv.PCidepth(i); pc[4 * i + 3] = lv.PCcolor(i); }
+        out.put<float>("trk_pc" + std::to_string(l), pc, {(uint64_t) lv.n(), 4});
+        // the new frame's derivative image and the reference's gray image of the level (checked against the numpy restatement, then dropped)
+        const GradientImage &g = nf->getCaptureFrame().getDerivativeImage(l);
+        std::vector<float> gi((size_t) wh[2 * l] * wh[2 * l + 1] * 3);
+        for (int y = 0; y < wh[2 * l + 1]; y++) for (int x = 0; x < wh[2 * l]; x++) for (int c = 0; c < 3; c++) gi[((size_t) y * wh[2 * l] + x) * 3 + c] = g.get(x, y)[c];
+        out.put<float>("trk_grad" + std::to_string(l), gi, {(uint64_t) wh[2 * l + 1], (uint64_t) wh[2 * l], 3});
+    }
+    out.put1<int32_t>("trk_levels_wh", wh); out.put1<int32_t>("trk_pc_n", npc); out.put<double>("trk_K", Ks, {(uint64_t) L, 4});
+    const double *ic = in.get("track_init_cam").as<double>();
+    const double *na = in.get("track_new_affine").as<double>();
+    DSOTracker::Residual r;
+    Camera cam; Exposure ex(nf->getExposure().getExposureFromCamera(), na[0], na[1]);
+    double best = 1e30;
+    for (int rep = 0; rep < std::max(1, repeat); rep++) {
+        cam = cameraFromRt(ic);
+        ex.setParametersAndExposure(Exposure(nf->getExposure().getExposureFromCamera(), na[0], na[1]));
+        tracker.mLastResidual = DSOTracker::Residual();
+        double a = now_s();
+        r = tracker.optimize(0, nf, ref, cam, ex);
+        best = std::min(best, now_s() - a);
+    }
+    out.scalar<double>("trk_seconds", best);
+    std::vector<double> cm(12);
+    Matrix33 R = cam.getRotationMatrix(); Vector3 t = cam.getTranslation();
+    for (int rr = 0; rr < 3; rr++) for (int c = 0; c < 3; c++) cm[rr * 3 + c] = R(rr, c);
+    for (int k = 0; k < 3; k++) cm[9 + k] = t[k];
+    out.put1<double>("trk_cam", cm);
+    std::vector<double> ab = {ex.getParameters()[0], ex.getParameters()[1]};
+    out.put1<double>("trk_affine", ab);
+    std::vector<double> E(r.E.begin(), r.E.end()), rep_(r.levelCutoffRepeat.begin(), r.levelCutoffRepeat.end());
+    std::vector<int32_t> nT(r.numTermsInE.begin(), r.numTermsInE.end()), nS(r.numSaturated.begin(), r.numSaturated.end()), nR(r.numRobust.begin(), r.numRobust.end());
+    out.put1<double>("trk_E", E); out.put1<int32_t>("trk_numTermsInE", nT); out.put1<int32_t>("trk_numSaturated", nS); out.put1<int32_t>("trk_numRobust", nR);
+    out.put1<double>("trk_levelCutoffRepeat", rep_);
+    std::vector<double> fl = {r.flowVector[0], r.flowVector[1], r.flowVector[2]}, ra = {r.relAff[0], r.relAff[1]}, cov(6);
+    for (int k = 0; k < 6; k++) cov[k] = r.covariance[k];
+    out.put1<double>("trk_flow", fl); out.put1<double>("trk_relAff", ra); out.put1<double>("trk_covariance", cov);
+    out.scalar<int32_t>("trk_isCorrect", r.isCorrect ? 1 : 0); out.scalar<int32_t>("trk_tooManySaturated", r.tooManySaturated ? 1 : 0);
+    printf("{\"track_seconds\": %.6f, \"levels\": %d, \"points_l0\": %d}\n", best, L, npc[0]);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     std::string window, mode = "stages", outPath;
     int repeat = 3;
@@ -576,6 +647,11 @@ int main(int argc, char **argv) {
         RefWindow *w = buildWindow(in);
         cmlw::File out;
         rc = runMaintain(w, in, out);
+        if (!outPath.empty()) out.save(outPath);
+    } else if (mode == "track") {
+        RefWindow *w = buildWindow(in);
+        cmlw::File out;
+        rc = runTrack(w, in, out, repeat);
         if (!outPath.empty()) out.save(outPath);
     } else if (mode == "bench") {
         // min over `repeat` freshly built windows, 1 thread (the reference BA is single-threaded)
