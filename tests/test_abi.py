@@ -26,6 +26,32 @@ def test_binding_lists_every_symbol():
     assert sorted(binding.SYMBOLS) == declared_symbols()
 
 
+def test_tracker_header_symbols_exported(lib):
+    """include/cmltrk.h (coarse tracker boundary): every declared entry point is exported and listed by the binding."""
+    from libcml_b200 import tracker
+    src = open(os.path.join(ROOT, "include", "cmltrk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(cmltrk_[a-z_0-9]+)\s*\(", src)))
+    assert sorted(tracker.TRACKER_SYMBOLS) == syms and len(syms) == 10
+    for s in syms:
+        assert hasattr(lib, s), f"libcmlba.so does not export {s}"
+    cfg = tracker.TrackerConfig()
+    tracker._bind(lib).cmltrk_default_config(C.byref(cfg))
+    # reference defaults, DSOTracker.h:479-518
+    assert cfg.huber_threshold == 9.0 and cfg.cutoff_threshold == 20.0 and cfg.scale_translation == 0.5 and cfg.scale_light_a == 10.0
+    assert cfg.scale_light_b == 1000.0 and cfg.optimize_a == 1 and cfg.optimize_b == 1 and cfg.saturated_ratio_threshold == 0.33
+
+
+def test_tracker_has_no_cpu_fallback(lib):
+    import torch
+    from libcml_b200 import tracker
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = tracker._bind(lib).cmltrk_create(None, 0, 640, 480, 500.0, 500.0, 320.0, 240.0, C.byref(h))
+    assert rc == -2 and not h.value and b"no CUDA device" in lib.cmltrk_last_error(None)
+
+
 def test_version_and_default_config(lib):
     from libcml_b200 import binding
     assert lib.cmlba_version().decode().endswith("sm_100a")
