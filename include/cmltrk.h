@@ -43,7 +43,8 @@ typedef struct {
     int optimize_b;                    /* "optimizeLightB" true */
     double saturated_ratio_threshold;  /* "saturatedThreshold" 0.33 */
     int levels;                        /* pyramid levels; <= 0: the reference's rule (CaptureImage.cpp:39-72) */
-    int cluster_ctas;                  /* CTAs per tracking cluster (1..16; > 8 needs the non-portable cluster size), default 8 */
+    int cluster_ctas;                  /* CTAs per tracking cluster (1..16); default 16 = the non-portable cluster size, falls back to 8 where it cannot be scheduled */
+    int cta_threads;                   /* threads per CTA of the tracking kernel: 256, 384 (default) or 512 */
 } cmltrk_config;
 
 /* DSOTracker::Residual (DSOTracker.h:202-236) plus the optimised pose and brightness of one start pose. */
@@ -80,6 +81,11 @@ int cmltrk_make_coarse_depth(cmltrk_handle h, const float *ref_gray, const doubl
                              const double *frame_cams, int num_points, const int32_t *pt_frame, const float *pt_xy, const double *pt_idepth,
                              const double *pt_uncertainty);
 
+/* Page-locked staging image [height][width] float owned by the handle.  A producer (camera driver, undistorter) that writes the gray image
+ * straight into it and passes this pointer as `gray` to cmltrk_set_frame / cmltrk_track / cmltrk_make_coarse_depth skips the host-side copy;
+ * any other pointer is copied into it first.  Valid until cmltrk_destroy; do not write while a call is running. */
+float *cmltrk_frame_buffer(cmltrk_handle h);
+
 /* Uploads the frame to track (level-0 gray) and builds its gray pyramid and derivative images on the device. */
 int cmltrk_set_frame(cmltrk_handle h, const float *gray, double exposure_time);
 
@@ -94,7 +100,8 @@ int cmltrk_track(cmltrk_handle h, const float *gray, double exposure_time, int n
                  const double *last_rmse, cmltrk_result *results);
 
 /* Debug / test reads: "pc_n" (int32[levels]), "pc<l>" (float [n][4]), "grad<l>" (float [h][w][4] = I, dx, dy, 0 of the frame to track),
- * "levels_wh" (int32 [levels][2]), "K" (double [levels][4]).  Returns bytes written or a negative error. */
+ * "levels_wh" (int32 [levels][2]), "K" (double [levels][4]), "cycles" (int64 [4]: evaluations and SM cycles spent advancing the optimiser,
+ * evaluating points and reducing/exchanging sums in the last optimize, start pose 0).  Returns bytes written or a negative error. */
 int64_t cmltrk_read(cmltrk_handle h, const char *name, void *dst, int64_t capacity);
 
 /* Device-resident repeat of the last cmltrk_optimize (same start poses) for benchmarks: `repeats` launches, mean device ms per launch. */

@@ -40,7 +40,7 @@ struct Tracker {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     char *d_block = nullptr;
     char *h_block = nullptr;     // pinned staging
-    size_t h_bytes = 0;
+    size_t h_bytes = 0, stage_gray = 0;
     // device views
     float *gray_new[MAXL]{}, *gray_ref[MAXL]{};
     float4 *grad_new[MAXL]{}, *pc[MAXL]{};
@@ -54,7 +54,9 @@ struct Tracker {
     double ref_exposure[3]{1, 0, 0}, new_tau = 1.0;
     TrackParams params{};
     int last_K = 0;
-    int cluster = 8;
+    int cluster = 8, threads = 384;
+    typedef void (*TrackFn)(const TrackParams, const Candidate *, TrackOut *);
+    TrackFn kernel() const { return threads == 256 ? track_kernel<256> : threads == 512 ? track_kernel<512> : track_kernel<384>; }
     long launches = 0;
 
     ~Tracker() {
@@ -90,7 +92,8 @@ struct Tracker {
             const double s = std::ldexp(1.0, l);
             K[l][0] = fx / s; K[l][1] = fy / s; K[l][2] = (cx + 0.5) / s - 0.5; K[l][3] = (cy + 0.5) / s - 0.5;
         }
-        cluster = std::max(1, std::min(cfg.cluster_ctas > 0 ? cfg.cluster_ctas : 8, (int) TRK_MAX_CLUSTER));
+        threads = (cfg.cta_threads == 256 || cfg.cta_threads == 512) ? cfg.cta_threads : 384;
+        cluster = std::max(1, std::min(cfg.cluster_ctas > 0 ? cfg.cluster_ctas : 16, (int) TRK_MAX_CLUSTER));
         TCK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         TCK(cudaEventCreate(&ev0)); TCK(cudaEventCreate(&ev1));
         // one device block for everything that scales with the image
@@ -111,9 +114,24 @@ struct Tracker {
             row_count[l] = (int *) (d_block + o_rc[l]); row_offset[l] = (int *) (d_block + o_ro[l]);
         }
         pc_n = (int *) (d_block + o_n); d_cand = (Candidate *) (d_block + o_cand); d_out = (TrackOut *) (d_block + o_out);
-        h_bytes = std::max((size_t) W * H * 4, sizeof(TrackOut) * CMLTRK_MAX_CANDIDATES + sizeof(Candidate) * CMLTRK_MAX_CANDIDATES) + 4096;
+        // pinned staging: [start poses | results | gray image]; the image part is also handed out by cmltrk_frame_buffer (zero-copy producers)
+        stage_gray = ((sizeof(TrackOut) + sizeof(Candidate)) * CMLTRK_MAX_CANDIDATES + 4095) & ~(size_t) 4095;
+        h_bytes = stage_gray + (size_t) W * H * 4;
         TCK(cudaHostAlloc((void **) &h_block, h_bytes, cudaHostAllocDefault));
-        if (cluster > 8) TCK(cudaFuncSetAttribute(track_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        if (cluster > 8) {       // 16 CTAs per cluster is the non-portable size: take it when this device can co-schedule one, else fall back to 8
+            bool ok = cudaFuncSetAttribute(kernel(), cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+            if (ok) {
+                cudaLaunchConfig_t lc{};
+                lc.gridDim = dim3(cluster); lc.blockDim = dim3(threads);
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                int n = 0;
+                ok = cudaOccupancyMaxActiveClusters(&n, kernel(), &lc) == cudaSuccess && n >= 1;
+            }
+            if (!ok) { cudaGetLastError(); cluster = 8; }
+        }
         TCK(cudaStreamSynchronize(stream));
         return CMLTRK_OK;
     }
@@ -128,9 +146,12 @@ struct Tracker {
     // host gray -> pinned -> device level 0, then the pyramid (and the derivative texels for the frame to track)
     int upload_pyramid(const float *gray, float **dst, bool with_grad) {
         const size_t bytes = (size_t) W * H * 4;
-        TCK(cudaStreamSynchronize(stream));           // the staging block may still be in flight from the previous call
-        memcpy(h_block, gray, bytes);
-        TCK(cudaMemcpyAsync(dst[0], h_block, bytes, cudaMemcpyHostToDevice, stream));
+        float *stage = (float *) (h_block + stage_gray);
+        if (gray != stage) {
+            TCK(cudaStreamSynchronize(stream));       // a previous upload may still be reading the staging image
+            memcpy(stage, gray, bytes);
+        }
+        TCK(cudaMemcpyAsync(dst[0], stage, bytes, cudaMemcpyHostToDevice, stream));
         const PyrDev p = pyr(dst, with_grad);
         const dim3 tiles((W + PYR_TILE - 1) / PYR_TILE, (H + PYR_TILE - 1) / PYR_TILE);
         pyr_gray_kernel<<<tiles, 256, 0, stream>>>(p); launches++;
@@ -226,12 +247,12 @@ struct Tracker {
 
     int launch_track(int Kc) {
         cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3(Kc * cluster); lc.blockDim = dim3(TRK_THREADS); lc.dynamicSmemBytes = 0; lc.stream = stream;
+        lc.gridDim = dim3(Kc * cluster); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = 0; lc.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        TCK(cudaLaunchKernelEx(&lc, track_kernel, params, (const Candidate *) d_cand, d_out));
+        TCK(cudaLaunchKernelEx(&lc, kernel(), params, (const Candidate *) d_cand, d_out));
         launches++;
         return CMLTRK_OK;
     }
@@ -241,7 +262,6 @@ struct Tracker {
         if (Kc < 1 || Kc > CMLTRK_MAX_CANDIDATES || !cams || !aff || !res) { error = "bad candidate count or NULL argument"; return CMLTRK_ERR_ARG; }
         TCK(cudaSetDevice(device));
         fill_params(last_rmse);
-        TCK(cudaStreamSynchronize(stream));      // staging block free (set_frame's upload has been consumed)
         Candidate *hc = (Candidate *) h_block;
         TrackOut *ho = (TrackOut *) (h_block + sizeof(Candidate) * CMLTRK_MAX_CANDIDATES);
         const Pose ref_inv = cmlba::pose_inv(ref_pose);
@@ -306,6 +326,11 @@ struct Tracker {
         };
         if (cudaSetDevice(device) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { error = "device error"; return CMLTRK_ERR_CUDA; }
         if (n == "pc_n") return out(pc_n, (size_t) L * 4, true);
+        if (n == "cycles") {      // of the last optimize(), start pose 0: evaluations, then SM cycles in advance / evaluate / reduce+exchange
+            const TrackOut *ho = (const TrackOut *) (h_block + sizeof(Candidate) * CMLTRK_MAX_CANDIDATES);
+            const long long v[4] = {ho[0].evals, ho[0].cyc_advance, ho[0].cyc_eval, ho[0].cyc_reduce};
+            return out(v, sizeof v, false);
+        }
         if (n == "levels_wh") { int v[2 * MAXL]; for (int l = 0; l < L; l++) { v[2 * l] = w[l]; v[2 * l + 1] = h[l]; } return out(v, (size_t) L * 8, false); }
         if (n == "K") return out(K, (size_t) L * 32, false);
         if (n.size() >= 3 && n.compare(0, 2, "pc") == 0 && isdigit(n[2])) {
@@ -336,7 +361,7 @@ void cmltrk_default_config(cmltrk_config *c) {
     c->huber_threshold = 9.0; c->cutoff_threshold = 20.0;
     c->scale_rotation = 1.0; c->scale_translation = 0.5; c->scale_light_a = 10.0; c->scale_light_b = 1000.0;
     c->optimize_a = 1; c->optimize_b = 1; c->saturated_ratio_threshold = 0.33;
-    c->levels = 0; c->cluster_ctas = 8;
+    c->levels = 0; c->cluster_ctas = 16; c->cta_threads = 384;
 }
 
 int cmltrk_create(const cmltrk_config *cfg, int device, int width, int height, double fx, double fy, double cx, double cy, cmltrk_handle *out) {
@@ -380,6 +405,12 @@ int cmltrk_track(cmltrk_handle h, const float *gray, double exposure_time, int n
     const int rc = t->set_frame(gray, exposure_time);
     if (rc) return rc;
     return t->optimize(num_candidates, start_cams, start_affine, last_rmse, results, before);
+}
+
+float *cmltrk_frame_buffer(cmltrk_handle h) {
+    if (!h) return nullptr;
+    Tracker *t = reinterpret_cast<Tracker *>(h);
+    return (float *) (t->h_block + t->stage_gray);
 }
 
 int64_t cmltrk_read(cmltrk_handle h, const char *name, void *dst, int64_t capacity) {

@@ -28,8 +28,6 @@ using cmlba::Pose;
 
 constexpr int MAXL = 6;            // pyramid levels held
 constexpr int OPTL = 5;            // levels optimised (DSOTracker.cpp:23-24)
-constexpr int TRK_THREADS = 512;
-constexpr int TRK_WARPS = TRK_THREADS / 32;
 constexpr int TRK_SUMS = 64;       // E, 3 counters, 3 flow sums, pad, 44 Hessian sums, pad
 constexpr int TRK_MAX_CLUSTER = 16;
 constexpr int PYR_TILE = 32;
@@ -66,7 +64,8 @@ struct TrackOut {
     int nT[OPTL], nS[OPTL], nR[OPTL];
     double rep[OPTL];
     double flow[3], rel_aff[2], cov[6];
-    int is_correct, sat_ok, iterations, pad;
+    int is_correct, sat_ok, iterations, evals;
+    long long cyc_advance, cyc_eval, cyc_reduce;      // SM cycles of CTA 0 / thread 0 per phase (where the launch spends its time)
 };
 
 // ------------------------------------------------------------------------------------------------ pyramid
@@ -267,7 +266,9 @@ struct TrkState {
     EvalCmd cmd;
     Pose cur, cand;
     double a, b, an, bn;
-    double H[64], g[8], inc[8];
+    double Hb[2][72];     // [hsel]: Hessian (64) and gradient (8) of the accepted pose; [hsel ^ 1]: those of the pose just evaluated
+    int hsel;
+    double inc[8];
     double lambda;
     int it, level, phase, have_repeated, iterations, fail;
     double rep[OPTL];
@@ -280,27 +281,47 @@ struct TrkState {
 __host__ __device__ constexpr int h_index(int a, int b) { return 8 + a * 9 - (a * (a - 1)) / 2 + (b - a); }
 enum { S_E = 0, S_NT = 1, S_NSAT = 2, S_NROB = 3, S_FT = 4, S_FRT = 5, S_FNUM = 6, S_H = 8 };
 
-// LDL^T solve of the sub-system picked by idx[0..m): x[idx] = H[idx][idx]^-1 rhs[idx]
-__device__ __noinline__ void solve_sub(const double *H, const double *rhs, const int *idx, const int m, double *x) {
-    double A[64], y[8];
-    for (int r = 0; r < m; r++) {
-        for (int c = 0; c < m; c++) A[r * 8 + c] = H[idx[r] * 8 + idx[c]];
-        y[r] = rhs[idx[r]];
-    }
-    for (int k = 0; k < m; k++) {              // A = L D L^T in place (unit L below the diagonal, D on it)
-        const double d = A[k * 8 + k];
-        const double inv = 1.0 / d;
-        for (int r = k + 1; r < m; r++) {
-            const double f = A[r * 8 + k] * inv;
-            for (int c = k + 1; c <= r; c++) A[r * 8 + c] -= f * A[c * 8 + k];      // column k still holds the unscaled entries
+// 8x8 LDL^T kept in registers (every index is a compile-time constant after unrolling; only the lower triangle exists).
+// Dimensions with active[i] == 0 are decoupled (row/column dropped, x[i] = 0): identical to solving the reference's 7x7 / 6x6
+// sub-systems (DSOTracker.cpp:98-121).
+struct Ldlt8 {
+    double A[36];      // packed lower triangle, row r column c at r (r + 1) / 2 + c; after factor(): unit L below, 1 / D on the diagonal
+    __device__ __forceinline__ static constexpr int at(int r, int c) { return r * (r + 1) / 2 + c; }
+    __device__ __forceinline__ void factor(const double *H, const double damp, const unsigned active) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c <= r; c++) {
+                const bool on = ((active >> r) & 1u) && ((active >> c) & 1u);
+                A[at(r, c)] = (r == c) ? (on ? H[r * 9] * damp : 1.0) : (on ? H[r * 8 + c] : 0.0);
+            }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double inv = 1.0 / A[at(k, k)];
+#pragma unroll
+            for (int r = k + 1; r < 8; r++) {
+                const double f = A[at(r, k)] * inv;
+#pragma unroll
+                for (int c = k + 1; c <= r; c++) A[at(r, c)] -= f * A[at(c, k)];
+            }
+#pragma unroll
+            for (int r = k + 1; r < 8; r++) A[at(r, k)] *= inv;
+            A[at(k, k)] = inv;
         }
-        for (int r = k + 1; r < m; r++) A[r * 8 + k] *= inv;
     }
-    for (int r = 0; r < m; r++) for (int c = 0; c < r; c++) y[r] -= A[r * 8 + c] * y[c];
-    for (int r = 0; r < m; r++) y[r] /= A[r * 8 + r];
-    for (int r = m - 1; r >= 0; r--) for (int c = r + 1; c < m; c++) y[r] -= A[c * 8 + r] * y[c];
-    for (int r = 0; r < m; r++) x[idx[r]] = y[r];
-}
+    __device__ __forceinline__ void solve(double *y) const {      // in place
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int c = 0; c < r; c++) y[r] -= A[at(r, c)] * y[c];
+#pragma unroll
+        for (int r = 0; r < 8; r++) y[r] *= A[at(r, r)];
+#pragma unroll
+        for (int r = 7; r >= 0; r--)
+#pragma unroll
+            for (int c = r + 1; c < 8; c++) y[r] -= A[at(c, r)] * y[c];
+    }
+};
 
 __device__ __forceinline__ void exposure_to(const double a0, const double b0, const double t0, const double a1, const double b1, const double t1, double &a, double &b) {
     a = exp(a1 - a0) * t1 / t0;       // Exposure::to (map/Exposure.h)
@@ -326,16 +347,15 @@ __device__ void request_eval(TrkState &S, const TrackParams &P, const Pose &T, c
     c.maxE = 2.0f * P.huber * c.cut - P.huber * P.huber;
 }
 
-__device__ void hessian_from_sums(TrkState &S, const TrackParams &P, const double *sum) {
+// scaled Hessian / gradient entry e (0..63: H row-major, 64..71: g) of the pose just evaluated (computeHessian's epilogue, DSOTracker.cpp:466-491);
+// one thread per entry
+__device__ __forceinline__ double hessian_entry(const int e, const TrackParams &P, const double *sum) {
     const int nw = (int) (sum[S_NT] - sum[S_NSAT]);
     const double n = (double) ((nw + 3) & ~3);
-    double M[81];
-    for (int i = 0; i < 8; i++)
-        for (int j = i; j < 9; j++) M[i * 9 + j] = sum[h_index(i, j)];
-    for (int i = 0; i < 8; i++) {
-        for (int j = 0; j < 8; j++) S.H[i * 8 + j] = (i <= j ? M[i * 9 + j] : M[j * 9 + i]) / n * P.scale[i] * P.scale[j];
-        S.g[i] = M[i * 9 + 8] / n * P.scale[i];
-    }
+    const int i = e < 64 ? e >> 3 : e - 64, j = e < 64 ? e & 7 : 8;
+    const int a = i < j ? i : j, b = i < j ? j : i;
+    const double v = sum[8 + a * 9 - (a * (a - 1)) / 2 + (b - a)] / n * P.scale[i];
+    return e < 64 ? v * P.scale[j] : v;
 }
 
 __device__ void finish(TrkState &S, const TrackParams &P, const bool converged) {
@@ -345,16 +365,18 @@ __device__ void finish(TrkState &S, const TrackParams &P, const bool converged) 
 
 // one Gauss-Newton proposal from (H, g, lambda): DSOTracker.cpp:93-160
 __device__ void propose(TrkState &S, const TrackParams &P) {
-    double Hd[64];
-    for (int i = 0; i < 64; i++) Hd[i] = S.H[i];
-    for (int i = 0; i < 8; i++) Hd[i * 9] *= (1.0 + S.lambda);
-    double mg[8];
-    for (int i = 0; i < 8; i++) { mg[i] = -S.g[i]; S.inc[i] = 0.0; }
-    int idx[8], m = 0;
-    for (int i = 0; i < 6; i++) idx[m++] = i;
-    if (P.optimize_a) idx[m++] = 6;
-    if (P.optimize_b) idx[m++] = 7;
-    solve_sub(Hd, mg, idx, m, S.inc);
+    unsigned active = 0x3fu;
+    if (P.optimize_a) active |= 1u << 6;
+    if (P.optimize_b) active |= 1u << 7;
+    Ldlt8 F;
+    const double *H = S.Hb[S.hsel], *g = H + 64;
+    F.factor(H, 1.0 + S.lambda, active);
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = ((active >> i) & 1u) ? -g[i] : 0.0;
+    F.solve(x);
+#pragma unroll
+    for (int i = 0; i < 8; i++) S.inc[i] = x[i];
     bool finite = true;
     for (int i = 0; i < 8; i++) finite = finite && isfinite(S.inc[i]);
     if (!finite) { finish(S, P, false); return; }
@@ -400,7 +422,7 @@ __device__ __noinline__ void advance(TrkState &S, const TrackParams &P, const do
             return;
         }
         if (S.oT[lv] - S.oS[lv] < 10) { finish(S, P, false); return; }
-        hessian_from_sums(S, P, sum);
+        S.hsel ^= 1;        // the Hessian of this evaluation (computed by 72 threads after the reduction) becomes the current one
         S.lambda = 0.01; S.it = 0;
         propose(S, P);
         return;
@@ -411,7 +433,7 @@ __device__ __noinline__ void advance(TrkState &S, const TrackParams &P, const do
     S.iterations++;
     const bool accept = (S.nE[lv] / (double) S.nT[lv]) < (S.oE[lv] / (double) S.oT[lv]);
     if (accept) {
-        hessian_from_sums(S, P, sum);
+        S.hsel ^= 1;
         // `oldResidual = newResidual` copies every level: coarser levels inherit the last tried step there (DSOTracker.cpp:166)
         for (int l = 0; l < OPTL; l++) { S.oE[l] = S.nE[l]; S.oT[l] = S.nT[l]; S.oS[l] = S.nS[l]; S.oR[l] = S.nR[l]; }
         for (int k = 0; k < 3; k++) S.oFlow[k] = S.nFlow[k];
@@ -433,7 +455,7 @@ __device__ __noinline__ void write_out(const TrkState &S, const TrackParams &P, 
     o.a = S.a; o.b = S.b;
     for (int l = 0; l < OPTL; l++) { o.E[l] = S.oE[l]; o.nT[l] = S.oT[l]; o.nS[l] = S.oS[l]; o.nR[l] = S.oR[l]; o.rep[l] = S.rep[l]; }
     for (int k = 0; k < 3; k++) o.flow[k] = S.oFlow[k];
-    o.iterations = S.iterations; o.pad = 0;
+    o.iterations = S.iterations; o.evals = 0;
     o.is_correct = 0; o.sat_ok = 1; o.rel_aff[0] = o.rel_aff[1] = 0.0;
     for (int k = 0; k < 6; k++) o.cov[k] = 999999.0;
     if (S.fail) return;
@@ -447,24 +469,30 @@ __device__ __noinline__ void write_out(const TrkState &S, const TrackParams &P, 
     o.is_correct = good ? 1 : 0;
     o.sat_ok = ((double) S.oS[0] / (double) S.oT[0] > P.sat_th) ? 0 : 1;
     o.rel_aff[0] = ra; o.rel_aff[1] = rb;
-    const int idx[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-    for (int k = 0; k < 6; k++) {       // covariance = diag(H^-1)[0:6]
-        double e[8] = {0, 0, 0, 0, 0, 0, 0, 0}, x[8];
-        e[k] = 1.0;
-        solve_sub(S.H, e, idx, 8, x);
-        o.cov[k] = x[k];
+    Ldlt8 F;                              // covariance = diag(H^-1)[0:6]
+    F.factor(S.Hb[S.hsel], 1.0, 0xffu);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        double e[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) e[i] = (i == k) ? 1.0 : 0.0;
+        F.solve(e);
+        o.cov[k] = e[k];
     }
 }
 
+template <int TRK_THREADS>
 __global__ void __launch_bounds__(TRK_THREADS, 1) track_kernel(const TrackParams P, const Candidate *__restrict__ cands, TrackOut *__restrict__ outs) {
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int) cluster.num_blocks(), rank = (int) cluster.block_rank();
     const int cand = blockIdx.x / CL;
+    constexpr int TRK_WARPS = TRK_THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ TrkState S;
     __shared__ float s_warp[TRK_WARPS][TRK_SUMS];
     __shared__ double s_part[2][TRK_MAX_CLUSTER][TRK_SUMS];
     __shared__ double s_sum[TRK_SUMS];
+    __shared__ int s_n[OPTL];          // point counts of the levels (read once: a global load per evaluation is a full L2 round trip)
 
     if (tid == 0) {
         const Candidate &c = cands[cand];
@@ -474,35 +502,42 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_kernel(const TrackParams
         S.phase = 0; S.have_repeated = 0; S.iterations = 0; S.fail = 0; S.lambda = 0.01; S.it = 0;
         for (int l = 0; l < OPTL; l++) { S.rep[l] = 0.0; S.oE[l] = S.nE[l] = 0.0; S.oT[l] = S.oS[l] = S.oR[l] = S.nT[l] = S.nS[l] = S.nR[l] = 0; }
         for (int k = 0; k < 3; k++) S.oFlow[k] = S.nFlow[k] = 0.0;
-        for (int i = 0; i < 64; i++) S.H[i] = (i % 9 == 0) ? 1.0 : 0.0;
-        for (int i = 0; i < 8; i++) S.g[i] = S.inc[i] = 0.0;
+        S.hsel = 0;
+        for (int i = 0; i < 72; i++) S.Hb[0][i] = S.Hb[1][i] = (i < 64 && i % 9 == 0) ? 1.0 : 0.0;
+        for (int i = 0; i < 8; i++) S.inc[i] = 0.0;
     }
     if (tid < TRK_SUMS) s_sum[tid] = 0.0;
+    if (tid >= 64 && tid < 64 + OPTL) s_n[tid - 64] = *P.lv[tid - 64].pc_n;
     __syncthreads();
     cluster.sync();      // every CTA of the cluster is resident before anyone writes into its shared memory
 
-    int buf = 0;
+    int buf = 0, evals = 0;
+    long long cyc_adv = 0, cyc_eval = 0, cyc_red = 0, t_mark = clock64();
     for (;;) {
         if (tid == 0) advance(S, P, s_sum);
         __syncthreads();
+        if (tid == 0) { const long long t = clock64(); cyc_adv += t - t_mark; t_mark = t; }
         if (S.cmd.exit) break;
+        evals++;
 
         // ---- evaluate the requested pose on this CTA's share of the level's points (computeResidual + computeHessian in one pass)
         const EvalCmd &c = S.cmd;
         const LevelDev &L = P.lv[c.level];
-        const int n = *L.pc_n;
+        const int n = s_n[c.level];
         const float wl3 = (float) (L.w - 3), hl3 = (float) (L.h - 3);
         const float huber = P.huber, base_cut = P.cutoff;
         float acc[TRK_SUMS];
 #pragma unroll
         for (int k = 0; k < TRK_SUMS; k++) acc[k] = 0.f;
-        for (int i = rank * TRK_THREADS + tid; i < n; i += CL * TRK_THREADS) {
-            const float4 p = L.pc[i];
+        // two-stage software pipeline: while point i is reduced into the sums, the taps of point i + stride and the record of
+        // point i + 2 stride are in flight (the per-thread chain record -> projection -> taps is ~2 L2 latencies long)
+        struct Tap { float4 t00, t10, t01, t11; float u, v, id, dx, dy, col; bool ok; };
+        auto stage_a = [&](const float4 p, const int i, const bool in_range, Tap &o) {
             const float x = p.x, y = p.y, id = p.z, refColor = p.w;
-            if (!isfinite(refColor)) continue;
-            const float ptx = (c.RKi[0] * x + c.RKi[1] * y + c.RKi[2]) + c.t[0] * id;
-            const float pty = (c.RKi[3] * x + c.RKi[4] * y + c.RKi[5]) + c.t[1] * id;
-            const float ptz = (c.RKi[6] * x + c.RKi[7] * y + c.RKi[8]) + c.t[2] * id;
+            o.ok = false;
+            if (!in_range || !isfinite(refColor)) return;
+            const float rx = c.RKi[0] * x + c.RKi[1] * y + c.RKi[2], ry = c.RKi[3] * x + c.RKi[4] * y + c.RKi[5], rz = c.RKi[6] * x + c.RKi[7] * y + c.RKi[8];
+            const float ptx = rx + c.t[0] * id, pty = ry + c.t[1] * id, ptz = rz + c.t[2] * id;
             const float u = ptx / ptz, v = pty / ptz;
             const float Ku = L.fx * u + L.cx, Kv = L.fy * v + L.cy;
             const float new_id = id / ptz;
@@ -510,8 +545,7 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_kernel(const TrackParams
                 const float kx = c.Ki[0] * x + c.Ki[1] * y + c.Ki[2], ky = c.Ki[3] * x + c.Ki[4] * y + c.Ki[5], kz = c.Ki[6] * x + c.Ki[7] * y + c.Ki[8];
                 const float ax = kx + c.t[0] * id, ay = ky + c.t[1] * id, az = kz + c.t[2] * id;
                 const float bx = kx - c.t[0] * id, by = ky - c.t[1] * id, bz = kz - c.t[2] * id;
-                const float cx3 = (c.RKi[0] * x + c.RKi[1] * y + c.RKi[2]) - c.t[0] * id, cy3 = (c.RKi[3] * x + c.RKi[4] * y + c.RKi[5]) - c.t[1] * id,
-                            cz3 = (c.RKi[6] * x + c.RKi[7] * y + c.RKi[8]) - c.t[2] * id;
+                const float cx3 = rx - c.t[0] * id, cy3 = ry - c.t[1] * id, cz3 = rz - c.t[2] * id;
                 const float KuT = L.fx * (ax / az) + L.cx, KvT = L.fy * (ay / az) + L.cy;
                 const float KuT2 = L.fx * (bx / bz) + L.cx, KvT2 = L.fy * (by / bz) + L.cy;
                 const float Ku3 = L.fx * (cx3 / cz3) + L.cx, Kv3 = L.fy * (cy3 / cz3) + L.cy;
@@ -521,17 +555,22 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_kernel(const TrackParams
                 acc[S_FRT] += (Ku3 - x) * (Ku3 - x) + (Kv3 - y) * (Kv3 - y);
                 acc[S_FNUM] += 2.f;
             }
-            if (!(Ku > 2.f && Kv > 2.f && Ku < wl3 && Kv < hl3 && new_id > 0.f)) continue;
+            if (!(Ku > 2.f && Kv > 2.f && Ku < wl3 && Kv < hl3 && new_id > 0.f)) return;
             const int ix = (int) Ku, iy = (int) Kv;
-            const float dx = Ku - (float) ix, dy = Kv - (float) iy, dxdy = dx * dy;
             const float4 *g = L.grad + (size_t) iy * L.w + ix;
-            const float4 t00 = g[0], t10 = g[1], t01 = g[L.w], t11 = g[L.w + 1];
-            const float w00 = 1.f - dx - dy + dxdy, w10 = dx - dxdy, w01 = dy - dxdy;
-            const float hI = dxdy * t11.x + w01 * t01.x + w10 * t10.x + w00 * t00.x;
-            const float hx = dxdy * t11.y + w01 * t01.y + w10 * t10.y + w00 * t00.y;
-            const float hy = dxdy * t11.z + w01 * t01.z + w10 * t10.z + w00 * t00.z;
-            if (!(isfinite(hI) && isfinite(hx) && isfinite(hy))) continue;
-            const float r = hI - (c.aLL * refColor + c.bLL);
+            o.t00 = g[0]; o.t10 = g[1]; o.t01 = g[L.w]; o.t11 = g[L.w + 1];
+            o.u = u; o.v = v; o.id = new_id; o.dx = Ku - (float) ix; o.dy = Kv - (float) iy; o.col = refColor;
+            o.ok = true;
+        };
+        auto stage_b = [&](const Tap &q) {
+            if (!q.ok) return;
+            const float dxdy = q.dx * q.dy;
+            const float w00 = 1.f - q.dx - q.dy + dxdy, w10 = q.dx - dxdy, w01 = q.dy - dxdy;
+            const float hI = dxdy * q.t11.x + w01 * q.t01.x + w10 * q.t10.x + w00 * q.t00.x;
+            const float hx = dxdy * q.t11.y + w01 * q.t01.y + w10 * q.t10.y + w00 * q.t00.y;
+            const float hy = dxdy * q.t11.z + w01 * q.t01.z + w10 * q.t10.z + w00 * q.t00.z;
+            if (!(isfinite(hI) && isfinite(hx) && isfinite(hy))) return;
+            const float r = hI - (c.aLL * q.col + c.bLL);
             const float ar = fabsf(r);
             const float hw = ar < huber ? 1.f : huber / ar;
             acc[S_NT] += 1.f;
@@ -539,18 +578,18 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_kernel(const TrackParams
             if (ar > c.cut) {
                 acc[S_E] += c.maxE;
                 acc[S_NSAT] += 1.f;
-                continue;
+                return;
             }
             acc[S_E] += hw * r * r * (2.f - hw);
-            const float gx = hx * L.fx, gy = hy * L.fy;
+            const float gx = hx * L.fx, gy = hy * L.fy, u = q.u, v = q.v;
             float J[9];
-            J[0] = new_id * gx;
-            J[1] = new_id * gy;
-            J[2] = 0.f - (new_id * (u * gx + v * gy));
+            J[0] = q.id * gx;
+            J[1] = q.id * gy;
+            J[2] = 0.f - (q.id * (u * gx + v * gy));
             J[3] = 0.f - ((u * v * gx) + gy * (1.f + v * v));
             J[4] = (u * v * gy) + (gx * (1.f + u * u));
             J[5] = u * gy - v * gx;
-            J[6] = c.aLL * (c.b0 - refColor);
+            J[6] = c.aLL * (c.b0 - q.col);
             J[7] = -1.f;
             J[8] = r;
 #pragma unroll
@@ -559,7 +598,21 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_kernel(const TrackParams
 #pragma unroll
                 for (int b = a; b < 9; b++) acc[h_index(a, b)] += jw * J[b];
             }
+        };
+        const int i0 = rank * TRK_THREADS + tid, stride = CL * TRK_THREADS;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        Tap cur;
+        stage_a(i0 < n ? L.pc[i0] : zero4, i0, i0 < n, cur);
+        float4 p_next = (i0 + stride < n) ? L.pc[i0 + stride] : zero4;
+        for (int i = i0; i < n; i += stride) {
+            const int j = i + stride;
+            const float4 p_next2 = (j + stride < n) ? L.pc[j + stride] : zero4;
+            Tap nxt;
+            stage_a(p_next, j, j < n, nxt);
+            stage_b(cur);
+            cur = nxt; p_next = p_next2;
         }
+        if (tid == 0) { const long long t = clock64(); cyc_eval += t - t_mark; t_mark = t; }
         // ---- CTA partial: transposing butterfly inside each warp, fp64 across warps (fixed order)
         s_warp[warp][lane] = transpose_sum(acc, lane);
         s_warp[warp][32 + lane] = transpose_sum(acc + 32, lane);
@@ -578,8 +631,14 @@ __global__ void __launch_bounds__(TRK_THREADS, 1) track_kernel(const TrackParams
         }
         buf ^= 1;
         __syncthreads();
+        if (tid < 72) S.Hb[S.hsel ^ 1][tid] = hessian_entry(tid, P, s_sum);
+        __syncthreads();
+        if (tid == 0) { const long long t = clock64(); cyc_red += t - t_mark; t_mark = t; }
     }
-    if (rank == 0 && tid == 0) write_out(S, P, outs[cand]);
+    if (rank == 0 && tid == 0) {
+        write_out(S, P, outs[cand]);
+        outs[cand].evals = evals; outs[cand].cyc_advance = cyc_adv; outs[cand].cyc_eval = cyc_eval; outs[cand].cyc_reduce = cyc_red;
+    }
 }
 
 }  // namespace cmltrk

@@ -19,7 +19,7 @@ MAX_CANDIDATES = 32
 class TrackerConfig(C.Structure):
     _fields_ = [("huber_threshold", C.c_double), ("cutoff_threshold", C.c_double), ("scale_rotation", C.c_double), ("scale_translation", C.c_double),
                 ("scale_light_a", C.c_double), ("scale_light_b", C.c_double), ("optimize_a", C.c_int), ("optimize_b", C.c_int),
-                ("saturated_ratio_threshold", C.c_double), ("levels", C.c_int), ("cluster_ctas", C.c_int)]
+                ("saturated_ratio_threshold", C.c_double), ("levels", C.c_int), ("cluster_ctas", C.c_int), ("cta_threads", C.c_int)]
 
 
 class TrackerResult(C.Structure):
@@ -30,7 +30,7 @@ class TrackerResult(C.Structure):
 
 
 TRACKER_SYMBOLS = ["cmltrk_default_config", "cmltrk_create", "cmltrk_destroy", "cmltrk_last_error", "cmltrk_make_coarse_depth", "cmltrk_set_frame", "cmltrk_optimize",
-                   "cmltrk_track", "cmltrk_read", "cmltrk_bench_optimize"]
+                   "cmltrk_track", "cmltrk_read", "cmltrk_bench_optimize", "cmltrk_frame_buffer"]
 
 _bound = False
 
@@ -52,6 +52,8 @@ def _bind(lib):
     lib.cmltrk_read.restype = C.c_int64
     lib.cmltrk_read.argtypes = [vp, C.c_char_p, vp, C.c_int64]
     lib.cmltrk_bench_optimize.argtypes = [vp, C.c_int, fp]
+    lib.cmltrk_frame_buffer.restype = fp
+    lib.cmltrk_frame_buffer.argtypes = [vp]
     _bound = True
     return lib
 
@@ -151,6 +153,11 @@ class DSOTracker:
             raise ValueError("point arrays differ in length")
         self._ck(self.lib.cmltrk_make_coarse_depth(self.h, _fp(g), _dp(rc_), _dp(re_), fc.shape[0], _dp(fc), pf.size, pf.ctypes.data_as(C.POINTER(C.c_int32)), _fp(xy),
                                                    _dp(idp), _dp(unc)))
+
+    def frameBuffer(self):
+        """The handle's page-locked staging image as a numpy view: fill it in place and pass it as `gray` to skip the host-side copy."""
+        p = self.lib.cmltrk_frame_buffer(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width))
 
     def setFrame(self, gray, exposure_time=1.0):
         """Uploads the frame to track and builds its pyramid (the CaptureImage role)."""

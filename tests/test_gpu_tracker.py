@@ -51,7 +51,7 @@ def test_pyramid_and_coarse_depth_match_reference():
 
 
 @pytest.mark.parametrize("case", ["a", "b", "c"])
-@pytest.mark.parametrize("cluster", [8, 1])
+@pytest.mark.parametrize("cluster", [16, 8, 1])
 def test_optimize_matches_reference(case, cluster):
     win, g = load()
     trk, ref, new = make_tracker(win, cluster_ctas=cluster)

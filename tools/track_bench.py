@@ -32,12 +32,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--width", type=int, default=640); ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--frames", type=int, default=7); ap.add_argument("--points", type=int, default=2000)
-    ap.add_argument("--repeats", type=int, default=50); ap.add_argument("--cluster", type=int, default=8)
-    ap.add_argument("--candidates", type=int, default=8)
+    ap.add_argument("--repeats", type=int, default=50); ap.add_argument("--cluster", type=int, default=16)
+    ap.add_argument("--candidates", type=int, default=8); ap.add_argument("--threads", type=int, default=384)
     a = ap.parse_args()
     win = scenario(a.width, a.height, a.frames, a.points, 31)
     N = a.frames; ref, new = N - 2, N - 1
-    trk = DSOTracker(a.width, a.height, win["calib"], cluster_ctas=a.cluster)
+    trk = DSOTracker(a.width, a.height, win["calib"], cluster_ctas=a.cluster, cta_threads=a.threads)
     keep = win["pt_host"] != new
     ref_exp = (win["frame_exposure"][ref], win["frame_affine"][ref, 0], win["frame_affine"][ref, 1])
     t0 = time.perf_counter()
@@ -52,15 +52,28 @@ def main():
     for _ in range(a.repeats):
         r = trk.optimize(win["track_init_cam"], win["track_new_affine"], gray=gray, exposure_time=tau)
     e2e_ms = (time.perf_counter() - t0) / a.repeats * 1e3
+    stage = trk.frameBuffer()
+    t0 = time.perf_counter()
+    for _ in range(a.repeats):
+        stage[...] = gray                    # stands for the producer writing the image (not part of the tracker)
+    fill_ms = (time.perf_counter() - t0) / a.repeats * 1e3
+    for _ in range(3):
+        trk.optimize(win["track_init_cam"], win["track_new_affine"], gray=stage, exposure_time=tau)
+    t0 = time.perf_counter()
+    for _ in range(a.repeats):
+        rz = trk.optimize(win["track_init_cam"], win["track_new_affine"], gray=stage, exposure_time=tau)
+    e2e_pinned_ms = (time.perf_counter() - t0) / a.repeats * 1e3
+    assert np.array_equal(rz.camera, r.camera)
     dev_ms = trk.benchOptimize(a.repeats)
+    cyc = trk.read("cycles", np.int64)
     K = a.candidates
     cams = np.tile(win["track_init_cam"], (K, 1)); cams[:, 9:] += 1e-3 * np.random.default_rng(3).standard_normal((K, 3))
     trk.optimize(cams, np.zeros((K, 2)))
     devK_ms = trk.benchOptimize(a.repeats)
     out = {"workload": f"{a.width}x{a.height}, {N - 1} keyframes x {a.points} points, 5 levels", "pc_n": trk.read("pc_n", np.int32).tolist(),
            "iterations": int(r.iterations), "is_correct": bool(r.isCorrect), "cam_err_vs_truth": float(np.abs(r.camera - win["truth_frame"][new]).max()),
-           "cluster_ctas": a.cluster, "optimize_device_ms": round(dev_ms, 4), "us_per_gn_step": round(dev_ms * 1e3 / max(r.iterations + 5, 1), 3),
-           "track_e2e_ms": round(e2e_ms, 4), "h2d_bytes_per_track": int(gray.nbytes), "make_coarse_depth_e2e_ms": round(coarse_ms, 3),
+           "cluster_ctas": a.cluster, "cta_threads": a.threads, "optimize_device_ms": round(dev_ms, 4), "us_per_gn_step": round(dev_ms * 1e3 / max(r.iterations + 5, 1), 3),
+           "evals": int(cyc[0]), "kcycles_advance_eval_reduce": [round(float(c) / 1e3, 1) for c in cyc[1:]], "track_e2e_ms": round(e2e_ms, 4), "track_e2e_from_frame_buffer_ms": round(e2e_pinned_ms, 4), "optimize_gpu_ms_in_call": round(float(rz.gpu_ms), 4), "h2d_bytes_per_track": int(gray.nbytes), "make_coarse_depth_e2e_ms": round(coarse_ms, 3),
            f"optimize_{K}_candidates_device_ms": round(devK_ms, 4)}
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "cmlba_ref")
     if os.path.exists(ref_bin):
