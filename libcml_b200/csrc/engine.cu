@@ -1213,7 +1213,11 @@ public:
         if (flush_l2) CK(d_flush.reserve(flush_bytes / sizeof(float4)));
         cudaEvent_t ev[6];
         for (auto &e : ev) CK(cudaEventCreate(&e));
-        auto flush = [&]() { if (flush_l2) l2_flush_kernel<<<148 * 8, 256, 0, stream>>>(d_flush.p, flush_bytes / sizeof(float4)); };
+        // after the flush the ranks are re-aligned on the device (peer-memory barrier, outside the timed region): the flush lengths differ per rank
+        auto flush = [&]() {
+            if (flush_l2) l2_flush_kernel<<<148 * 8, 256, 0, stream>>>(d_flush.p, flush_bytes / sizeof(float4));
+            if (dw.p2p_on) { dw.p2p_epoch = ++p2p_epoch; p2p_barrier_kernel<<<1, 32, 0, stream>>>(dw); }
+        };
         // the committed buffers must hold a linearization for schur/stitch to chew on
         launch_linearize(0, 0); launch_post(0, 0);
         for (int i = 0; i < warmup; i++) { flush(); launch_linearize(0, 0); launch_schur(0); launch_stitch(0); }

@@ -681,6 +681,21 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const DevWin w, cons
     if (!p2p_reduce(w, w.sys, 2 * w.n * w.n + 2 * w.n) && threadIdx.x == 0) { w.ctrl->failed = 1; w.ctrl->done = 1; }
 }
 
+// cross-rank barrier on the same epoch flags (an exchange without payload): aligns the ranks before a timed pass so that a rank
+// whose L2 flush finished early does not charge its wait for the others to the pass.  Bounded spin like p2p_reduce.
+__global__ void __launch_bounds__(32) p2p_barrier_kernel(const DevWin w) {
+    if (threadIdx.x == 0) { __threadfence_system(); p2p_signal(w); }
+    if ((int) threadIdx.x < w.world) {
+        const unsigned long long *f = p2p_flags(w, w.rank) + threadIdx.x;
+        unsigned long long v = 0; long spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(f) : "memory");
+            if (v >= w.p2p_epoch || ++spins > (1l << 23)) break;
+            __nanosleep(100);
+        }
+    }
+}
+
 // sum_k!=a slot(a,k)[o_row] + sum_k!=a slot(k,a)[o_col], all loads issued before the (fixed-order) adds
 __device__ __forceinline__ double sum_slots(const double *st, const int N, const int S, const int a, const int o_row, const int o_col) {
     double v = 0.0;
