@@ -147,8 +147,45 @@ def tracker():
     print("track window", os.path.getsize(os.path.join(OUT, "track_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "track_golden.cmlw")) // 1024, "KB")
 
 
+def tracer():
+    """DSOTracer (SURVEY 8f NEXT #2) of the reference on a 5-frame window: 4 x 150 immature points created by makeNewTracesFrom, traced into every
+    later frame (trace(), all six statuses occur), then optimizeImmaturePoint on the points with a finite depth interval."""
+    tmp = "/tmp/cmlba_golden"
+    os.makedirs(tmp, exist_ok=True)
+    W, H, N, per, seed = 192, 144, 5, 150, 11
+    win = synth.make_window(W, H, N, 20, 4, True, seed=seed, low_freq=True)
+    rng = np.random.default_rng(seed + 5)
+    hosts, xy = [], []
+    for h in range(N - 1):
+        x = rng.integers(8, W - 8, per).astype(np.float32); y = rng.integers(8, H - 8, per).astype(np.float32)
+        hosts.append(np.full(per, h, np.int32)); xy.append(np.stack([x, y], 1))
+    win["im_host"] = np.concatenate(hosts); win["im_xy"] = np.concatenate(xy).astype(np.float32)
+    win["frame_cam"] = win["truth_frame"].copy()
+    full = os.path.join(tmp, "trace.cmlw")
+    keep = {k: win[k] for k in ("size", "calib", "frame_cam", "frame_affine", "frame_exposure", "gray", "im_host", "im_xy")}
+    cmlw.save(full, keep)
+    run_ref(full, "trace", os.path.join(tmp, "trace_out.cmlw"))
+    g = cmlw.load(os.path.join(tmp, "trace_out.cmlw"))
+    seen = np.concatenate([g[f"trc_status_f{f}"] for f in range(1, N)])
+    assert set(np.unique(seen[seen >= 0])) == {0, 1, 2, 3, 4, 5}, "the scenario must produce every trace status"
+    gold = {k: v for k, v in g.items() if not k.endswith("_seconds")}
+    # second run with "Min iDepth H Act" raised so that the Hdd gate (return 0, DSOTracer.cpp:321-324, 341-344) fires on part of the points
+    keep2 = dict(keep); keep2["min_idepth_h_act"] = np.array([3.0e4])
+    cmlw.save(os.path.join(tmp, "trace_hact.cmlw"), keep2)
+    run_ref(os.path.join(tmp, "trace_hact.cmlw"), "trace", os.path.join(tmp, "trace_hact_out.cmlw"))
+    g2 = cmlw.load(os.path.join(tmp, "trace_hact_out.cmlw"))
+    gold["hact_opt_rc"] = g2["trc_opt_rc"]; gold["hact_opt_idepth"] = g2["trc_opt_idepth"]; gold["hact_min_idepth_h_act"] = np.array([3.0e4])
+    assert set(np.unique(np.concatenate([gold["trc_opt_rc"], gold["hact_opt_rc"]]))) >= {-1, 0, 1}, "the scenario must produce every activation outcome"
+    print("activation rc", np.unique(gold["trc_opt_rc"], return_counts=True), "with raised gate", np.unique(gold["hact_opt_rc"], return_counts=True))
+    cmlw.save(os.path.join(OUT, "trace_window.cmlw"), keep)
+    cmlw.save(os.path.join(OUT, "trace_golden.cmlw"), gold)
+    print("trace window", os.path.getsize(os.path.join(OUT, "trace_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "trace_golden.cmlw")) // 1024, "KB")
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    if len(sys.argv) > 1 and sys.argv[1] == "tracer":
+        tracer(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tracker":
         tracker(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "maintenance":

@@ -55,6 +55,7 @@
 #include <cml/capture/CaptureImage.h>
 #include <cml/optimization/dso/DSOBundleAdjustment.h>
 #include <cml/optimization/dso/DSOTracker.h>
+#include <cml/optimization/dso/DSOTracer.h>
 #undef private
 #undef protected
 
@@ -610,6 +611,108 @@ static int runTrack(RefWindow *w, const cmlw::File &in, cmlw::File &out, int rep
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// mode trace: DSOTracer (SURVEY 8f NEXT #2).  Immature points `im_host` / `im_xy` are created by the reference's own
+// makeNewTracesFrom; every later frame f traces all points hosted before f (trace(), DSOTracer.cpp:585-832), the state of
+// every point is dumped after each pass; finally optimizeImmaturePoint (DSOTracer.cpp:280-411) on the points with a finite
+// depth interval.  Frames = the window's frames at `frame_cam`, exposures `frame_exposure`/`frame_affine`.
+static int runTrace(const cmlw::File &in, cmlw::File &out, int repeat) {
+    const int32_t *size = in.get("size").as<int32_t>();
+    const int W = size[0], H = size[1];
+    const double *K = in.get("calib").as<double>();
+    const int N = (int) in.get("frame_cam").dims[0];
+    const int P = (int) in.get("im_host").dims[0];
+    Root *root = new Root;
+    auto *calib = new InternalCalibration(PinholeUndistorter(Vector2(K[0], K[1]), Vector2(K[2], K[3])), Vector2(W, H));
+    auto *gen = new CaptureImageGenerator(W, H, N + 2, N + 2);
+    Map &map = root->getMap();
+    DSOTracer tracer(root);
+    if (in.has("min_idepth_h_act")) tracer.mMinIDepthHAct.set((float) in.get("min_idepth_h_act").as<double>()[0]);
+    const int fg = map.createFrameGroup("trace window");
+    const double *cam = in.get("frame_cam").as<double>();
+    const double *aff = in.get("frame_affine").as<double>();
+    const double *expo = in.get("frame_exposure").as<double>();
+    const float *gray = in.get("gray").as<float>();
+    std::vector<PFrame> frames;
+    for (int i = 0; i < N; i++) {
+        FloatImage img(W, H);
+        memcpy(img.data(), gray + (size_t) i * W * H, sizeof(float) * W * H);
+        auto cap = gen->create().setImage(img).setTime(i).setCalibration(calib).setExposure(expo[i]).generate();
+        PFrame f = map.createFrame(cap);
+        f->setCamera(cameraFromRt(cam + 12 * i));
+        f->setExposureParameters(Exposure(expo[i], aff[2 * i], aff[2 * i + 1]));
+        map.addFrame(f);
+        f->setGroup(fg, true);
+        frames.push_back(f);
+    }
+    const int32_t *host = in.get("im_host").as<int32_t>();
+    const float *xy = in.get("im_xy").as<float>();
+    std::vector<PPoint> pts(P, PPoint());
+    for (int h = 0; h < N; h++) {
+        std::vector<int> mine;
+        List<Corner> corners;
+        for (int p = 0; p < P; p++) if (host[p] == h) { mine.push_back(p); corners.emplace_back(Corner(DistortedVector2d(xy[2 * p], xy[2 * p + 1]))); }
+        if (mine.empty()) continue;
+        const int gid = frames[h]->addFeaturePoints(corners);
+        tracer.makeNewTracesFrom(frames[h], gid);
+        for (auto mp : map.getGroupMapPoints(tracer.IMMATUREPOINT)) {
+            if (mp->getReferenceFrame() != frames[h]) continue;
+            auto pd = tracer.getPrivateData(mp);
+            if (pd->referenceIndex.group != gid) continue;
+            pts[mine[pd->referenceIndex.index]] = mp;
+        }
+    }
+    // point initialisation (makeNewTracesFrom): gradH, weights, energyTH
+    {
+        std::vector<double> gh((size_t) P * 4), wt((size_t) P * 8), eth(P);
+        std::vector<int32_t> ok(P);
+        for (int p = 0; p < P; p++) {
+            ok[p] = pts[p].isNotNull() ? 1 : 0;
+            if (!ok[p]) continue;
+            auto pd = tracer.getPrivateData(pts[p]);
+            gh[4 * p] = pd->gradH(0, 0); gh[4 * p + 1] = pd->gradH(0, 1); gh[4 * p + 2] = pd->gradH(1, 0); gh[4 * p + 3] = pd->gradH(1, 1);
+            for (int k = 0; k < 8; k++) wt[8 * p + k] = pd->weights[k];
+            eth[p] = pd->energyTH;
+        }
+        out.put1<int32_t>("trc_created", ok); out.put<double>("trc_gradH", gh, {(uint64_t) P, 4}); out.put<double>("trc_weights", wt, {(uint64_t) P, 8});
+        out.put1<double>("trc_energyTH", eth);
+    }
+    double tTrace = 0; long nTraced = 0;
+    for (int f = 1; f < N; f++) {
+        double a = now_s();
+        for (int p = 0; p < P; p++) if (pts[p].isNotNull() && host[p] < f) { tracer.trace(frames[f], pts[p]); nTraced++; }
+        tTrace += now_s() - a;
+        std::vector<int32_t> st(P, -1);
+        std::vector<double> v((size_t) P * 6, 0.0);
+        for (int p = 0; p < P; p++) {
+            if (!pts[p].isNotNull()) continue;
+            auto pd = tracer.getPrivateData(pts[p]);
+            st[p] = (int32_t) pd->lastTraceStatus;
+            v[6 * p] = pd->iDepthMin; v[6 * p + 1] = pd->iDepthMax; v[6 * p + 2] = pd->lastTraceUV[0]; v[6 * p + 3] = pd->lastTraceUV[1];
+            v[6 * p + 4] = pd->lastTracePixelInterval; v[6 * p + 5] = pd->quality;
+        }
+        out.put1<int32_t>("trc_status_f" + std::to_string(f), st);
+        out.put<double>("trc_state_f" + std::to_string(f), v, {(uint64_t) P, 6});
+    }
+    // activation: optimizeImmaturePoint on every point with a finite interval
+    const int minObs = in.has("min_obs") ? in.get("min_obs").as<int32_t>()[0] : 1;
+    std::vector<int32_t> rc(P, -2);
+    std::vector<double> idp(P, 0.0);
+    double a = now_s(); long nOpt = 0;
+    for (int p = 0; p < P; p++) {
+        if (!pts[p].isNotNull()) continue;
+        auto pd = tracer.getPrivateData(pts[p]);
+        if (!std::isfinite(pd->iDepthMax) || !std::isfinite(pd->iDepthMin)) continue;
+        rc[p] = tracer.optimizeImmaturePoint(pts[p], minObs, fg); nOpt++;
+        if (rc[p] == 1) idp[p] = pts[p]->getReferenceInverseDepth();
+    }
+    const double tOpt = now_s() - a;
+    out.put1<int32_t>("trc_opt_rc", rc); out.put1<double>("trc_opt_idepth", idp);
+    out.scalar<double>("trc_trace_seconds", tTrace); out.scalar<double>("trc_opt_seconds", tOpt);
+    printf("{\"traces\": %ld, \"trace_seconds\": %.6f, \"optimized\": %ld, \"opt_seconds\": %.6f}\n", nTraced, tTrace, nOpt, tOpt);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     std::string window, mode = "stages", outPath;
     int repeat = 3;
@@ -626,6 +729,13 @@ int main(int argc, char **argv) {
     if (!in.load(window)) { fprintf(stderr, "cannot read %s\n", window.c_str()); return 2; }
 
     int rc = 0;
+    if (mode == "trace") {
+        cmlw::File out;
+        rc = runTrace(in, out, repeat);
+        if (!outPath.empty()) out.save(outPath);
+        fflush(stdout);
+        _exit(rc);
+    }
     if (mode == "stages") {
         RefWindow *w = buildWindow(in);
         cmlw::File out;
