@@ -8,3 +8,4 @@ There is no CPU fallback: without the compiled extension / a CUDA device every c
 from . import cmlw, synth  # noqa: F401
 from .binding import DSOBundleAdjustment, CmlbaError, load_library, lib_path  # noqa: F401
 from .tracker import DSOTracker  # noqa: F401
+from .tracer import DSOTracer  # noqa: F401

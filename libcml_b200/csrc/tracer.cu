@@ -1,0 +1,325 @@
+// tracer.cu -- host side of the immature-point tracer and the C ABI of include/cmltrc.h (SURVEY.md 8f NEXT #2).
+//
+// Host-side reference anchors (under /root/reference/src/cml/optimization/dso):
+//   Tracer::pair_table   DSOTracer.cpp:605-606 (hostToFrame_KRKi, hostToFrame_Kt), :431-432 (hostToTarget, exposure transition)
+//   Tracer::window_order Map::getGroupFrames -> OrderedSet<PFrame, Comparator>: newest frame first (types.h:996-1012)
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cmltrc.h"
+#include "se3.h"
+#include "tracer.cuh"
+
+namespace cmltrc {
+
+static thread_local std::string g_create_error;
+using cmlba::Pose;
+
+#define RCK(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            error = std::string(#call) + ": " + cudaGetErrorString(_e);                            \
+            return CMLTRC_ERR_CUDA;                                                                \
+        }                                                                                          \
+    } while (0)
+
+struct Tracer {
+    TrcParams P{};
+    int device = 0;
+    std::string error;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // frames
+    struct Slot { bool used = false; int64_t id = 0; Pose cam; double exposure[3]; float *gray = nullptr; float4 *grad = nullptr; };
+    Slot slots[TRC_MAXF];
+    FrameImg *d_frames = nullptr;
+    PairDev *d_pairs = nullptr;        // [TRC_MAXF * TRC_MAXF]
+    int *d_slots = nullptr, *d_counts = nullptr;
+    char *h_pin = nullptr; size_t pin_bytes = 0;
+    // points
+    PointsDev pts{};
+    size_t cap = 0; int64_t num = 0;
+    std::vector<int> host_slot;        // host mirror of pts.host
+    int *d_ids = nullptr; ActivateOut *d_out = nullptr; size_t act_cap = 0;
+
+    ~Tracer() {
+        for (auto &s : slots) { if (s.gray) cudaFree(s.gray); if (s.grad) cudaFree(s.grad); }
+        free_points();
+        if (d_frames) cudaFree(d_frames); if (d_pairs) cudaFree(d_pairs); if (d_slots) cudaFree(d_slots); if (d_counts) cudaFree(d_counts);
+        if (d_ids) cudaFree(d_ids); if (d_out) cudaFree(d_out);
+        if (h_pin) cudaFreeHost(h_pin);
+        if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    void free_points() {
+        void *v[] = {pts.host, pts.xy, pts.status, pts.idmin, pts.idmax, pts.u, pts.v, pts.interval, pts.quality, pts.gradH, pts.energyTH, pts.weights};
+        for (void *p : v) if (p) cudaFree(p);
+        pts = PointsDev{};
+    }
+
+    int create(const cmltrc_config &c, int dev, int W, int H, double fx, double fy, double cx, double cy) {
+        if (W < 16 || H < 16 || !(fx > 0) || !(fy > 0)) { error = "bad image size or calibration"; return CMLTRC_ERR_ARG; }
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || dev < 0 || dev >= count) { error = "no CUDA device " + std::to_string(dev) + " (the tracer has no CPU path)"; return CMLTRC_ERR_CUDA; }
+        device = dev;
+        RCK(cudaSetDevice(dev));
+        P.W = W; P.H = H; P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy;
+        P.huber = c.huber_threshold; P.outlier_th = c.outlier_th; P.outlier_th_sum = c.outlier_th_sum_component; P.max_pix_search = c.max_pix_search;
+        P.max_slack_interval = c.max_slack_interval; P.step_size = c.trace_step_size; P.min_improvement = c.min_improvement_factor; P.test_radius = c.min_trace_test_radius;
+        P.extra_slack = c.extra_slack_on_th; P.min_idepth_h_act = c.min_idepth_h_act; P.gn_iterations = c.gn_iterations;
+        RCK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        RCK(cudaEventCreate(&ev0)); RCK(cudaEventCreate(&ev1));
+        RCK(cudaMalloc(&d_frames, sizeof(FrameImg) * TRC_MAXF));
+        RCK(cudaMalloc(&d_pairs, sizeof(PairDev) * TRC_MAXF * TRC_MAXF));
+        RCK(cudaMalloc(&d_slots, sizeof(int) * TRC_MAXF));
+        RCK(cudaMalloc(&d_counts, sizeof(int) * 8));
+        pin_bytes = std::max((size_t) W * H * 4, sizeof(PairDev) * TRC_MAXF * TRC_MAXF + 4096) + 4096;
+        RCK(cudaHostAlloc((void **) &h_pin, pin_bytes, cudaHostAllocDefault));
+        return CMLTRC_OK;
+    }
+
+    int find(int64_t id) const { for (int s = 0; s < TRC_MAXF; s++) if (slots[s].used && slots[s].id == id) return s; return -1; }
+
+    int upload_frame_table() {
+        FrameImg f[TRC_MAXF];
+        for (int s = 0; s < TRC_MAXF; s++) { f[s].gray = slots[s].gray; f[s].grad = slots[s].grad; }
+        RCK(cudaMemcpyAsync(d_frames, f, sizeof f, cudaMemcpyHostToDevice, stream));
+        RCK(cudaStreamSynchronize(stream));
+        return CMLTRC_OK;
+    }
+
+    int add_frame(int64_t id, const float *gray, const double *cam, const double *expo) {
+        if (!gray || !cam || !expo) { error = "NULL argument"; return CMLTRC_ERR_ARG; }
+        if (find(id) >= 0) { error = "frame id already present"; return CMLTRC_ERR_ARG; }
+        int s = 0;
+        while (s < TRC_MAXF && slots[s].used) s++;
+        if (s == TRC_MAXF) { error = "frame group is full (16 frames)"; return CMLTRC_ERR_ARG; }
+        RCK(cudaSetDevice(device));
+        Slot &sl = slots[s];
+        const size_t px = (size_t) P.W * P.H;
+        if (!sl.gray) { RCK(cudaMalloc(&sl.gray, px * 4)); RCK(cudaMalloc(&sl.grad, px * 16)); }
+        RCK(cudaStreamSynchronize(stream));
+        memcpy(h_pin, gray, px * 4);
+        RCK(cudaMemcpyAsync(sl.gray, h_pin, px * 4, cudaMemcpyHostToDevice, stream));
+        trc_grad_kernel<<<std::min<int>(1184, (int) ((px + 255) / 256)), 256, 0, stream>>>(sl.gray, sl.grad, P.W, P.H);
+        RCK(cudaGetLastError());
+        sl.used = true; sl.id = id;
+        memcpy(sl.cam.R, cam, 72); memcpy(sl.cam.t, cam + 9, 24); memcpy(sl.exposure, expo, 24);
+        return upload_frame_table();
+    }
+    int set_pose(int64_t id, const double *cam, const double *expo) {
+        const int s = find(id);
+        if (s < 0 || !cam || !expo) { error = "unknown frame id or NULL argument"; return CMLTRC_ERR_ARG; }
+        memcpy(slots[s].cam.R, cam, 72); memcpy(slots[s].cam.t, cam + 9, 24); memcpy(slots[s].exposure, expo, 24);
+        return CMLTRC_OK;
+    }
+    int remove_frame(int64_t id) {
+        const int s = find(id);
+        if (s < 0) { error = "unknown frame id"; return CMLTRC_ERR_ARG; }
+        slots[s].used = false;
+        std::vector<int64_t> dead;
+        for (int64_t p = 0; p < num; p++) if (host_slot[p] == s) dead.push_back(p);
+        return dead.empty() ? CMLTRC_OK : remove_points((int) dead.size(), dead.data());
+    }
+
+    int grow(size_t want) {
+        if (want <= cap) return CMLTRC_OK;
+        const size_t ncap = std::max(want + want / 2, (size_t) 4096);
+        PointsDev n{};
+        auto mv = [&](auto *&dst, auto *src, size_t per) -> cudaError_t {
+            cudaError_t e = cudaMalloc((void **) &dst, ncap * per);
+            if (e != cudaSuccess) return e;
+            if (src && num) e = cudaMemcpyAsync(dst, src, (size_t) num * per, cudaMemcpyDeviceToDevice, stream);
+            return e;
+        };
+        RCK(mv(n.host, pts.host, 4)); RCK(mv(n.xy, pts.xy, 8)); RCK(mv(n.status, pts.status, 4));
+        RCK(mv(n.idmin, pts.idmin, 8)); RCK(mv(n.idmax, pts.idmax, 8)); RCK(mv(n.u, pts.u, 8)); RCK(mv(n.v, pts.v, 8));
+        RCK(mv(n.interval, pts.interval, 8)); RCK(mv(n.quality, pts.quality, 8)); RCK(mv(n.gradH, pts.gradH, 32)); RCK(mv(n.energyTH, pts.energyTH, 8));
+        RCK(mv(n.weights, pts.weights, 32));
+        RCK(cudaStreamSynchronize(stream));
+        free_points();
+        pts = n; cap = ncap;
+        return CMLTRC_OK;
+    }
+
+    int make_new_traces(int64_t id, int count, const float *xy, int64_t *first) {
+        const int s = find(id);
+        if (s < 0 || count < 0 || (count > 0 && !xy)) { error = "unknown frame id or bad arguments"; return CMLTRC_ERR_ARG; }
+        for (int i = 0; i < count; i++) {      // the pattern (|offset| <= 2) and its bilinear taps must stay inside the image
+            const float x = xy[2 * i], y = xy[2 * i + 1];
+            if (!(x >= 3 && y >= 3 && x < P.W - 4 && y < P.H - 4)) { error = "corner too close to the image border"; return CMLTRC_ERR_ARG; }
+        }
+        RCK(cudaSetDevice(device));
+        int rc = grow((size_t) num + count);
+        if (rc) return rc;
+        if (first) *first = num;
+        if (count == 0) return CMLTRC_OK;
+        RCK(cudaMemcpyAsync(pts.xy + num, xy, (size_t) count * 8, cudaMemcpyHostToDevice, stream));
+        const FrameImg img{slots[s].gray, slots[s].grad};
+        trc_init_kernel<<<(count + 127) / 128, 128, 0, stream>>>(P, pts, (int) num, count, s, img);
+        RCK(cudaGetLastError());
+        RCK(cudaStreamSynchronize(stream));
+        host_slot.resize((size_t) num + count, s);
+        num += count;
+        return CMLTRC_OK;
+    }
+
+    int remove_points(int count, const int64_t *ids) {
+        if (count < 0 || (count > 0 && !ids)) { error = "bad arguments"; return CMLTRC_ERR_ARG; }
+        RCK(cudaSetDevice(device));
+        const int minus1 = -1;
+        for (int i = 0; i < count; i++) {
+            if (ids[i] < 0 || ids[i] >= num) { error = "unknown point id"; return CMLTRC_ERR_ARG; }
+            if (host_slot[ids[i]] < 0) continue;
+            host_slot[ids[i]] = -1;
+            RCK(cudaMemcpyAsync(pts.host + ids[i], &minus1, 4, cudaMemcpyHostToDevice, stream));
+        }
+        RCK(cudaStreamSynchronize(stream));
+        return CMLTRC_OK;
+    }
+
+    // pair constants in fp64; for trace only the column `target` is needed, for activation the whole table
+    void fill_pair(PairDev &pd, const Slot &h, const Slot &t) {
+        const Pose rel = cmlba::pose_mul(t.cam, cmlba::pose_inv(h.cam));      // Camera::to
+        const double K[9] = {P.fx, 0, P.cx, 0, P.fy, P.cy, 0, 0, 1};
+        const double Ki[9] = {1.0 / P.fx, 0, -P.cx / P.fx, 0, 1.0 / P.fy, -P.cy / P.fy, 0, 0, 1};
+        double KR[9];
+        cmlba::mat3_mul(K, rel.R, KR);
+        cmlba::mat3_mul(KR, Ki, pd.KRKi);
+        cmlba::mat3_vec(K, rel.t, pd.Kt);
+        memcpy(pd.R, rel.R, 72); memcpy(pd.t, rel.t, 24);
+        pd.a = std::exp(t.exposure[1] - h.exposure[1]) * t.exposure[0] / h.exposure[0];       // Exposure::to
+        pd.b = t.exposure[2] - pd.a * h.exposure[2];
+    }
+
+    int trace(int64_t id, int32_t *hist, float *gpu_ms) {
+        const int tgt = find(id);
+        if (tgt < 0) { error = "unknown frame id"; return CMLTRC_ERR_ARG; }
+        RCK(cudaSetDevice(device));
+        RCK(cudaStreamSynchronize(stream));
+        PairDev *hp = (PairDev *) h_pin;
+        for (int s = 0; s < TRC_MAXF; s++) if (slots[s].used) fill_pair(hp[s], slots[s], slots[tgt]);
+        RCK(cudaMemcpyAsync(d_pairs, hp, sizeof(PairDev) * TRC_MAXF, cudaMemcpyHostToDevice, stream));
+        RCK(cudaMemsetAsync(d_counts, 0, 32, stream));
+        RCK(cudaEventRecord(ev0, stream));
+        if (num > 0) trc_trace_kernel<<<(int) ((num + 3) / 4), 128, 0, stream>>>(P, pts, (int) num, tgt, d_pairs, d_frames, d_counts);
+        RCK(cudaEventRecord(ev1, stream));
+        RCK(cudaGetLastError());
+        int32_t c[8];
+        RCK(cudaMemcpyAsync(c, d_counts, 32, cudaMemcpyDeviceToHost, stream));
+        RCK(cudaStreamSynchronize(stream));
+        if (hist) memcpy(hist, c, 24);
+        if (gpu_ms) RCK(cudaEventElapsedTime(gpu_ms, ev0, ev1));
+        return CMLTRC_OK;
+    }
+
+    int activate(int count, const int64_t *ids, int min_obs, cmltrc_activation *res, float *gpu_ms) {
+        if (count < 0 || (count > 0 && (!ids || !res))) { error = "bad arguments"; return CMLTRC_ERR_ARG; }
+        if (gpu_ms) *gpu_ms = 0.f;
+        if (count == 0) return CMLTRC_OK;
+        RCK(cudaSetDevice(device));
+        std::vector<int> id32(count);
+        for (int i = 0; i < count; i++) {
+            if (ids[i] < 0 || ids[i] >= num || host_slot[ids[i]] < 0) { error = "unknown or removed point id"; return CMLTRC_ERR_ARG; }
+            id32[i] = (int) ids[i];
+        }
+        // window order: newest frame first (OrderedSet<PFrame, Comparator> orders by descending id)
+        std::vector<int> order;
+        for (int s = 0; s < TRC_MAXF; s++) if (slots[s].used) order.push_back(s);
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return slots[a].id > slots[b].id; });
+        RCK(cudaStreamSynchronize(stream));
+        PairDev *hp = (PairDev *) h_pin;
+        for (int a : order) for (int b : order) if (a != b) fill_pair(hp[a * TRC_MAXF + b], slots[a], slots[b]);
+        RCK(cudaMemcpyAsync(d_pairs, hp, sizeof(PairDev) * TRC_MAXF * TRC_MAXF, cudaMemcpyHostToDevice, stream));
+        RCK(cudaMemcpyAsync(d_slots, order.data(), order.size() * 4, cudaMemcpyHostToDevice, stream));
+        if ((size_t) count > act_cap) {
+            if (d_ids) cudaFree(d_ids); if (d_out) cudaFree(d_out);
+            d_ids = nullptr; d_out = nullptr; act_cap = 0;
+            RCK(cudaMalloc(&d_ids, (size_t) count * 2 * 4)); RCK(cudaMalloc(&d_out, (size_t) count * 2 * sizeof(ActivateOut)));
+            act_cap = (size_t) count * 2;
+        }
+        RCK(cudaMemcpyAsync(d_ids, id32.data(), (size_t) count * 4, cudaMemcpyHostToDevice, stream));
+        RCK(cudaEventRecord(ev0, stream));
+        trc_activate_kernel<<<(count + 3) / 4, 128, 0, stream>>>(P, pts, count, d_ids, min_obs, (int) order.size(), d_slots, d_pairs, d_frames, d_out);
+        RCK(cudaEventRecord(ev1, stream));
+        RCK(cudaGetLastError());
+        std::vector<ActivateOut> ho(count);
+        RCK(cudaMemcpyAsync(ho.data(), d_out, (size_t) count * sizeof(ActivateOut), cudaMemcpyDeviceToHost, stream));
+        RCK(cudaStreamSynchronize(stream));
+        for (int i = 0; i < count; i++) { res[i].rc = ho[i].rc; res[i].idepth = ho[i].idepth; res[i].in_mask = ho[i].in_mask; }
+        if (gpu_ms) RCK(cudaEventElapsedTime(gpu_ms, ev0, ev1));
+        return CMLTRC_OK;
+    }
+
+    int get_points(int64_t first, int count, cmltrc_point *out) {
+        if (first < 0 || count < 0 || first + count > num || (count > 0 && !out)) { error = "bad range"; return CMLTRC_ERR_ARG; }
+        if (count == 0) return CMLTRC_OK;
+        RCK(cudaSetDevice(device));
+        RCK(cudaStreamSynchronize(stream));
+        std::vector<int> st(count), hs(count);
+        std::vector<double> a(count), b(count), u(count), v(count), iv(count), q(count), g((size_t) count * 4), e(count);
+        RCK(cudaMemcpy(st.data(), pts.status + first, (size_t) count * 4, cudaMemcpyDeviceToHost));
+        RCK(cudaMemcpy(hs.data(), pts.host + first, (size_t) count * 4, cudaMemcpyDeviceToHost));
+        RCK(cudaMemcpy(a.data(), pts.idmin + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
+        RCK(cudaMemcpy(b.data(), pts.idmax + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
+        RCK(cudaMemcpy(u.data(), pts.u + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
+        RCK(cudaMemcpy(v.data(), pts.v + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
+        RCK(cudaMemcpy(iv.data(), pts.interval + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
+        RCK(cudaMemcpy(q.data(), pts.quality + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
+        RCK(cudaMemcpy(g.data(), pts.gradH + first * 4, (size_t) count * 32, cudaMemcpyDeviceToHost));
+        RCK(cudaMemcpy(e.data(), pts.energyTH + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < count; i++) {
+            cmltrc_point &o = out[i];
+            o.status = st[i]; o.host_frame_slot = hs[i]; o.idepth_min = a[i]; o.idepth_max = b[i]; o.last_trace_uv[0] = u[i]; o.last_trace_uv[1] = v[i];
+            o.last_trace_pixel_interval = iv[i]; o.quality = q[i]; memcpy(o.grad_h, &g[(size_t) i * 4], 32); o.energy_th = e[i];
+        }
+        return CMLTRC_OK;
+    }
+};
+
+}  // namespace cmltrc
+
+using cmltrc::Tracer;
+#define TH(h) reinterpret_cast<Tracer *>(h)
+
+extern "C" {
+
+void cmltrc_default_config(cmltrc_config *c) {
+    if (!c) return;
+    c->min_idepth_h_act = 100.0f; c->gn_iterations = 3; c->huber_threshold = 9.0f; c->outlier_th = 12.0f * 12.0f; c->outlier_th_sum_component = 50.0f * 50.0f;
+    c->max_pix_search = 0.027f; c->max_slack_interval = 1.5f; c->trace_step_size = 1.0f; c->min_improvement_factor = 2.0f; c->min_trace_test_radius = 2.0f;
+    c->extra_slack_on_th = 1.2f;
+}
+
+int cmltrc_create(const cmltrc_config *cfg, int device, int width, int height, double fx, double fy, double cx, double cy, cmltrc_handle *out) {
+    if (!out) { cmltrc::g_create_error = "out is NULL"; return CMLTRC_ERR_ARG; }
+    *out = nullptr;
+    cmltrc_config c;
+    if (cfg) c = *cfg; else cmltrc_default_config(&c);
+    Tracer *t = new Tracer();
+    const int rc = t->create(c, device, width, height, fx, fy, cx, cy);
+    if (rc) { cmltrc::g_create_error = t->error; delete t; return rc; }
+    *out = reinterpret_cast<cmltrc_handle>(t);
+    return CMLTRC_OK;
+}
+void cmltrc_destroy(cmltrc_handle h) { delete TH(h); }
+const char *cmltrc_last_error(cmltrc_handle h) { return h ? TH(h)->error.c_str() : cmltrc::g_create_error.c_str(); }
+int cmltrc_add_frame(cmltrc_handle h, int64_t id, const float *gray, const double cam[12], const double exposure[3]) { return h ? TH(h)->add_frame(id, gray, cam, exposure) : CMLTRC_ERR_ARG; }
+int cmltrc_set_frame_pose(cmltrc_handle h, int64_t id, const double cam[12], const double exposure[3]) { return h ? TH(h)->set_pose(id, cam, exposure) : CMLTRC_ERR_ARG; }
+int cmltrc_remove_frame(cmltrc_handle h, int64_t id) { return h ? TH(h)->remove_frame(id) : CMLTRC_ERR_ARG; }
+int cmltrc_make_new_traces(cmltrc_handle h, int64_t id, int count, const float *xy, int64_t *first_id) { return h ? TH(h)->make_new_traces(id, count, xy, first_id) : CMLTRC_ERR_ARG; }
+int cmltrc_remove_points(cmltrc_handle h, int count, const int64_t *ids) { return h ? TH(h)->remove_points(count, ids) : CMLTRC_ERR_ARG; }
+int64_t cmltrc_num_points(cmltrc_handle h) { return h ? TH(h)->num : CMLTRC_ERR_ARG; }
+int cmltrc_trace_new_coarse(cmltrc_handle h, int64_t id, int32_t *hist, float *gpu_ms) { return h ? TH(h)->trace(id, hist, gpu_ms) : CMLTRC_ERR_ARG; }
+int cmltrc_optimize_immature(cmltrc_handle h, int count, const int64_t *ids, int min_obs, cmltrc_activation *results, float *gpu_ms) {
+    return h ? TH(h)->activate(count, ids, min_obs, results, gpu_ms) : CMLTRC_ERR_ARG;
+}
+int cmltrc_get_points(cmltrc_handle h, int64_t first_id, int count, cmltrc_point *out) { return h ? TH(h)->get_points(first_id, count, out) : CMLTRC_ERR_ARG; }
+
+}  // extern "C"

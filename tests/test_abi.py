@@ -42,6 +42,32 @@ def test_tracker_header_symbols_exported(lib):
     assert cfg.scale_light_b == 1000.0 and cfg.optimize_a == 1 and cfg.optimize_b == 1 and cfg.saturated_ratio_threshold == 0.33
 
 
+def test_tracer_header_symbols_exported(lib):
+    """include/cmltrc.h (immature-point tracer boundary)."""
+    from libcml_b200 import tracer
+    src = open(os.path.join(ROOT, "include", "cmltrc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(cmltrc_[a-z_0-9]+)\s*\(", src)))
+    assert sorted(tracer.TRACER_SYMBOLS) == syms and len(syms) == 13
+    for s in syms:
+        assert hasattr(lib, s), f"libcmlba.so does not export {s}"
+    cfg = tracer.TracerConfig()
+    tracer._bind(lib).cmltrc_default_config(C.byref(cfg))
+    # reference defaults, DSOTracer.h:186-203
+    assert cfg.min_idepth_h_act == 100.0 and cfg.gn_iterations == 3 and cfg.huber_threshold == 9.0 and cfg.outlier_th == 144.0
+    assert cfg.outlier_th_sum_component == 2500.0 and abs(cfg.max_pix_search - 0.027) < 1e-7 and cfg.max_slack_interval == 1.5
+    assert ctypes_sizeof_matches(tracer)
+    import torch
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert lib.cmltrc_create(None, 0, 640, 480, 500.0, 500.0, 320.0, 240.0, C.byref(h)) == -2 and b"no CUDA device" in lib.cmltrc_last_error(None)
+
+
+def ctypes_sizeof_matches(tracer):
+    # cmltrc_point: 2 x int32 + 11 doubles; cmltrc_activation: int32 + float + uint32
+    return tracer.POINT.itemsize == 96 and tracer.ACTIVATION.itemsize == 12
+
+
 def test_tracker_has_no_cpu_fallback(lib):
     import torch
     from libcml_b200 import tracker
