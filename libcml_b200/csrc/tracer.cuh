@@ -170,21 +170,31 @@ __global__ void __launch_bounds__(128) trc_trace_kernel(const TrcParams P, const
     double err[4] = {1e300, 1e300, 1e300, 1e300};       // this lane's steps: lane, lane + 32, lane + 64, lane + 96
     double bestE = 1e10, bestU = 0, bestV = 0;
     int bestI = -1;
+    // the search position is the reference's fp32 running sum `ptx += dx`: every lane walks the whole (cheap) recurrence and keeps
+    // the positions of its own steps, then all lanes evaluate their steps together
+    float sx[4] = {0.f, 0.f, 0.f, 0.f}, sy[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = 0; i < numSteps; i++) {
-        if ((i & 31) == lane) {
+        const bool mine = (i & 31) == lane;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (mine && (i >> 5) == j) { sx[j] = ptx; sy[j] = pty; }
+        ptx = (float) ((double) ptx + dx); pty = (float) ((double) pty + dy);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = lane + 32 * j;
+        if (i < numSteps) {
             double e = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const double qx = (double) ptx + rx[k], qy = (double) pty + ry[k];
+                const double qx = (double) sx[j] + rx[k], qy = (double) sy[j] + ry[k];
                 if (!inside(P, qx, qy, 3.0)) { e += 1e5; continue; }
                 const double r = (double) interp_gray(tf.gray, P.W, (float) qx, (float) qy) - refc[k];
                 const double hw = fabs(r) < huber ? 1.0 : huber / fabs(r);
                 e += hw * r * r * (2 - hw);
             }
-            err[i >> 5] = e;
-            if (e < bestE) { bestE = e; bestU = ptx; bestV = pty; bestI = i; }
+            err[j] = e;
+            if (e < bestE) { bestE = e; bestU = sx[j]; bestV = sy[j]; bestI = i; }
         }
-        ptx = (float) ((double) ptx + dx); pty = (float) ((double) pty + dy);
     }
     // first minimum over all steps = min energy, ties to the smaller index
 #pragma unroll
