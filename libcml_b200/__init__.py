@@ -9,3 +9,4 @@ from . import cmlw, synth  # noqa: F401
 from .binding import DSOBundleAdjustment, CmlbaError, load_library, lib_path  # noqa: F401
 from .tracker import DSOTracker  # noqa: F401
 from .tracer import DSOTracer  # noqa: F401
+from .imgprep import CaptureImageGenerator  # noqa: F401

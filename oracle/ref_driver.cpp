@@ -713,6 +713,62 @@ static int runTrace(const cmlw::File &in, cmlw::File &out, int repeat) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// mode prepare: image preparation (SURVEY 8f NEXT #3): CaptureImageGenerator::generate with a response LUT, an inverse vignette and a
+// radial-tangential pre-undistorter (CaptureImage.cpp:108-262): dumps the undistortion map and, per level, gray / derivative / weighted
+// gradient-norm images.
+static int runPrepare(const cmlw::File &in, cmlw::File &out, int repeat) {
+    const int32_t *sin = in.get("size_in").as<int32_t>(), *sout = in.get("size_out").as<int32_t>();
+    const double *kin = in.get("calib_in").as<double>(), *kout = in.get("calib_out").as<double>(), *rt = in.get("radtan").as<double>();
+    const int Wi = sin[0], Hi = sin[1], Wo = sout[0], Ho = sout[1];
+    auto *calib = new InternalCalibration(PinholeUndistorter(Vector2(kin[0], kin[1]), Vector2(kin[2], kin[3])), Vector2(Wi, Hi), new RadtanUndistorter(rt[0], rt[1], rt[2], rt[3]),
+                                          PinholeUndistorter(Vector2(kout[0], kout[1]), Vector2(kout[2], kout[3])), Vector2(Wo, Ho));
+    auto *gen = new CaptureImageGenerator(Wo, Ho, 4, 4);
+    GrayLookupTable *lut = nullptr;
+    if (in.has("lut")) { Vectorf<256> v; const float *l = in.get("lut").as<float>(); for (int i = 0; i < 256; i++) v[i] = l[i]; lut = new GrayLookupTable(v); }
+    FloatImage raw(Wi, Hi);
+    memcpy(raw.data(), in.get("raw").as<float>(), sizeof(float) * Wi * Hi);
+    Array2D<float> vig(Wi, Hi);
+    const bool hasVig = in.has("inv_vignette");
+    if (hasVig) memcpy(vig.data(), in.get("inv_vignette").as<float>(), sizeof(float) * Wi * Hi);
+    double best = 1e30;
+    Ptr<CaptureImage, NonNullable> cap = gen->create().setImage(raw).setTime(0).setCalibration(calib).setExposure(1).generate();
+    for (int rep = 0; rep < std::max(1, repeat); rep++) {
+        auto mk = gen->create();
+        mk.setImage(raw).setTime(rep + 1).setCalibration(calib).setExposure(1);
+        if (lut) mk.setLut(lut);
+        if (hasVig) mk.setInverseVignette(vig);
+        const double a = now_s();
+        cap = mk.generate();
+        best = std::min(best, now_s() - a);
+    }
+    {
+        std::vector<float> m((size_t) Wo * Ho * 2);
+        for (int y = 0; y < Ho; y++) for (int x = 0; x < Wo; x++) { const Vector2f v = calib->mUndistortMap(x, y); m[((size_t) y * Wo + x) * 2] = v[0]; m[((size_t) y * Wo + x) * 2 + 1] = v[1]; }
+        out.put<float>("prep_map", m, {(uint64_t) Ho, (uint64_t) Wo, 2});
+    }
+    const int L = cap->getPyramidLevels();
+    std::vector<int32_t> wh(2 * L);
+    for (int l = 0; l < L; l++) {
+        const int w = cap->getWidth(l), h = cap->getHeight(l);
+        wh[2 * l] = w; wh[2 * l + 1] = h;
+        std::vector<float> g((size_t) w * h), d((size_t) w * h * 3), n((size_t) w * h);
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+            g[(size_t) y * w + x] = cap->getGrayImage(l).get(x, y);
+            const Vector3f v = cap->getDerivativeImage(l).get(x, y);
+            for (int c = 0; c < 3; c++) d[((size_t) y * w + x) * 3 + c] = v[c];
+            n[(size_t) y * w + x] = cap->getWeightedGradientNorm(l).get(x, y);
+        }
+        out.put<float>("prep_gray" + std::to_string(l), g, {(uint64_t) h, (uint64_t) w});
+        out.put<float>("prep_grad" + std::to_string(l), d, {(uint64_t) h, (uint64_t) w, 3});
+        out.put<float>("prep_wgn" + std::to_string(l), n, {(uint64_t) h, (uint64_t) w});
+    }
+    out.put1<int32_t>("prep_levels_wh", wh);
+    out.scalar<double>("prep_seconds", best);
+    printf("{\"prepare_seconds\": %.6f, \"levels\": %d}\n", best, L);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     std::string window, mode = "stages", outPath;
     int repeat = 3;
@@ -729,6 +785,13 @@ int main(int argc, char **argv) {
     if (!in.load(window)) { fprintf(stderr, "cannot read %s\n", window.c_str()); return 2; }
 
     int rc = 0;
+    if (mode == "prepare") {
+        cmlw::File out;
+        rc = runPrepare(in, out, repeat);
+        if (!outPath.empty()) out.save(outPath);
+        fflush(stdout);
+        _exit(rc);
+    }
     if (mode == "trace") {
         cmlw::File out;
         rc = runTrace(in, out, repeat);

@@ -63,6 +63,21 @@ def test_tracer_header_symbols_exported(lib):
         assert lib.cmltrc_create(None, 0, 640, 480, 500.0, 500.0, 320.0, 240.0, C.byref(h)) == -2 and b"no CUDA device" in lib.cmltrc_last_error(None)
 
 
+def test_imgprep_header_symbols_exported(lib):
+    """include/cmlimg.h (image preparation boundary)."""
+    from libcml_b200 import imgprep
+    src = open(os.path.join(ROOT, "include", "cmlimg.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(cmlimg_[a-z_0-9]+)\s*\(", src)))
+    assert sorted(imgprep.IMG_SYMBOLS) == syms and len(syms) == 12
+    for s in syms:
+        assert hasattr(lib, s), f"libcmlba.so does not export {s}"
+    import torch
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert imgprep._bind(lib).cmlimg_create(0, 640, 480, 640, 480, 0, C.byref(h)) == -2 and b"no CUDA device" in lib.cmlimg_last_error(None)
+
+
 def ctypes_sizeof_matches(tracer):
     # cmltrc_point: 2 x int32 + 11 doubles; cmltrc_activation: int32 + float + uint32
     return tracer.POINT.itemsize == 96 and tracer.ACTIVATION.itemsize == 12

@@ -14,7 +14,7 @@ win = synth.make_config(wl, seed=1234)
 P = win["pt_host"].size
 ba = DSOBundleAdjustment(device=0, iterations=iters, async_image_upload=1)
 cams = win["frame_cam"]
-gnp = torch.from_numpy(win["grad"]).pin_memory().numpy()
+gray = torch.from_numpy(np.ascontiguousarray(win["gray"], dtype=np.float32)).pin_memory().numpy()
 acc = {}
 def lap(name, t0):
     t1 = time.perf_counter(); acc[name] = acc.get(name, 0.0) + (t1 - t0) * 1e3; return t1
@@ -26,7 +26,7 @@ for i in range(reps + 1):
     t = time.perf_counter(); t00 = t
     ba.reset(); ba.setCalibration(*[float(v) for v in win["calib"]], W, H); t = lap("py.reset+calib", t)
     for f in range(N):
-        ba.addNewFrame(f, win["frame_evalpt"][f], win["frame_affine"][f, 0], win["frame_affine"][f, 1], win["frame_exposure"][f], gnp[f], False)
+        ba.addNewFrameGray(f, win["frame_evalpt"][f], win["frame_affine"][f, 0], win["frame_affine"][f, 1], win["frame_exposure"][f], gray[f], False)
     t = lap("py.addNewFrame x N", t)
     ba.addPoints(ids, win["pt_host"], win["pt_xy"], win["pt_idepth"]); t = lap("py.addPoints", t)
     ok = ba.run(cams, iterations=iters); t = lap("py.run", t)
