@@ -99,6 +99,10 @@ int cmlba_add_frame(cmlba_handle *h, int64_t frame_id, const double world_to_cam
  * 1-pixel border) -- bit-identical texels, a third of the host->device traffic. */
 int cmlba_add_frame_gray(cmlba_handle *h, int64_t frame_id, const double world_to_cam[12], double aff_a, double aff_b,
                          double exposure_time, const float *gray /* [height][width] */, int is_init_frame);
+/* Same, from DEVICE memory: d_texels = level-0 float4 (I, dx, dy, *) texels on this handle's device, e.g. cmlimg_device_ptr(img, "texel0")
+ * (include/cmlimg.h).  One device-to-device copy, complete when the call returns (the source may be overwritten afterwards). */
+int cmlba_add_frame_device(cmlba_handle *h, int64_t frame_id, const double world_to_cam[12], double aff_a, double aff_b, double exposure_time,
+                           const void *d_texels, int is_init_frame);
 
 /* addPoints(const PointSet&) (BA:382-415).  n points; host_frame_id[i] = getReferenceFrame()->getId(),
  * xy = getReferenceCorner() (float x,y), idepth = getReferenceInverseDepth().  Reference colours

@@ -71,6 +71,8 @@ const char *cmltrc_last_error(cmltrc_handle h);   /* h may be NULL: error of the
 
 /* Frame group.  gray = level-0 gray image [height][width]; cam = world-to-camera [R(9) | t(3)]; exposure = (time, a, b). */
 int cmltrc_add_frame(cmltrc_handle h, int64_t frame_id, const float *gray, const double cam[12], const double exposure[3]);
+/* Same from DEVICE memory of this handle's device: level-0 fp32 gray and float4 (I, dx, dy, *) texels (e.g. cmlimg_device_ptr "gray0" / "texel0"); copied. */
+int cmltrc_add_frame_device(cmltrc_handle h, int64_t frame_id, const float *d_gray, const void *d_texels, const double cam[12], const double exposure[3]);
 int cmltrc_set_frame_pose(cmltrc_handle h, int64_t frame_id, const double cam[12], const double exposure[3]);
 int cmltrc_remove_frame(cmltrc_handle h, int64_t frame_id);   /* also removes the immature points hosted in it */
 

@@ -89,6 +89,15 @@ float *cmltrk_frame_buffer(cmltrk_handle h);
 /* Uploads the frame to track (level-0 gray) and builds its gray pyramid and derivative images on the device. */
 int cmltrk_set_frame(cmltrk_handle h, const float *gray, double exposure_time);
 
+/* Device-resident variants (same process, same device; e.g. the levels of include/cmlimg.h):
+ *   cmltrk_make_coarse_depth_device: d_gray_levels[l] = device pointer to the fp32 gray image of level l of the reference keyframe (copied);
+ *   cmltrk_set_frame_device: d_texel_levels[l] = device pointer to the float4 (I, dx, dy, *) texels of level l of the frame to track; they are
+ *   sampled IN PLACE by the following cmltrk_optimize calls and must stay valid and unchanged until then. */
+int cmltrk_make_coarse_depth_device(cmltrk_handle h, int levels, const float *const *d_gray_levels, const double ref_cam[12], const double ref_exposure[3], int num_frames,
+                                    const double *frame_cams, int num_points, const int32_t *pt_frame, const float *pt_xy, const double *pt_idepth,
+                                    const double *pt_uncertainty);
+int cmltrk_set_frame_device(cmltrk_handle h, int levels, const void *const *d_texel_levels, double exposure_time);
+
 /* optimize() for `num_candidates` start poses (world-to-camera, [K][12]) and start brightness ([K][2]) at once.
  * last_rmse: NULL, or [CMLTRK_OPT_LEVELS] = mLastResidual.rmse(level) for the rmse sanity check (DSOTracker.cpp:190-196).
  * results [K]. */

@@ -43,7 +43,7 @@ class BenchResult(C.Structure):
 
 
 # every symbol include/cmlba.h declares (tests/test_abi.py checks the .so exports all of them)
-SYMBOLS = ["cmlba_default_config", "cmlba_create", "cmlba_destroy", "cmlba_last_error", "cmlba_set_calib", "cmlba_add_frame", "cmlba_add_frame_gray", "cmlba_add_points",
+SYMBOLS = ["cmlba_default_config", "cmlba_create", "cmlba_destroy", "cmlba_last_error", "cmlba_set_calib", "cmlba_add_frame", "cmlba_add_frame_gray", "cmlba_add_frame_device", "cmlba_add_points",
            "cmlba_remove_point", "cmlba_remove_frame", "cmlba_flag_frames_for_marginalization", "cmlba_try_marginalize", "cmlba_marginalize_points",
            "cmlba_marginalize_frames", "cmlba_run", "cmlba_num_frames", "cmlba_num_points", "cmlba_num_residuals", "cmlba_get_frames",
            "cmlba_get_points", "cmlba_get_outliers", "cmlba_get_residuals", "cmlba_prepare", "cmlba_linearize", "cmlba_apply", "cmlba_solve", "cmlba_step",
@@ -71,6 +71,7 @@ def load_library():
     lib.cmlba_set_calib.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
     lib.cmlba_add_frame.argtypes = [vp, C.c_int64, dp, C.c_double, C.c_double, C.c_double, fp, C.c_int]
     lib.cmlba_add_frame_gray.argtypes = [vp, C.c_int64, dp, C.c_double, C.c_double, C.c_double, fp, C.c_int]
+    lib.cmlba_add_frame_device.argtypes = [vp, C.c_int64, dp, C.c_double, C.c_double, C.c_double, vp, C.c_int]
     lib.cmlba_add_points.argtypes = [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), fp, dp]
     lib.cmlba_remove_point.argtypes = [vp, C.c_int64]
     lib.cmlba_remove_frame.argtypes = [vp, C.c_int64]
@@ -161,6 +162,12 @@ class DSOBundleAdjustment:
         g = np.ascontiguousarray(gray_image, dtype=np.float32)
         self._ck(self.lib.cmlba_add_frame_gray(self.h, int(frame_id), _ptr(w2c, C.c_double), float(aff_a), float(aff_b), float(exposure_time),
                                                _ptr(g, C.c_float), int(bool(is_init_frame))))
+
+    def addNewFrameDevice(self, frame_id, w2c, aff_a, aff_b, exposure_time, d_texels, is_init_frame=False):
+        """addNewFrame from device-resident level-0 texels (an int device pointer, e.g. CaptureImage.devicePtr("texel0"))."""
+        w2c = np.ascontiguousarray(w2c, dtype=np.float64).reshape(12)
+        self._ck(self.lib.cmlba_add_frame_device(self.h, int(frame_id), _ptr(w2c, C.c_double), float(aff_a), float(aff_b), float(exposure_time),
+                                                 C.c_void_p(int(d_texels)), 1 if is_init_frame else 0))
 
     def addPoints(self, point_ids, host_frame_ids, xy, idepth):
         """addPoints(const PointSet&) (BA:382-415)."""

@@ -350,13 +350,18 @@ public:
         // keep one per window slot, because several copies are in flight
         const int sb = cfg.async_image_upload ? (int) frames_.size() : (stage_flip ^= 1);
         const size_t nfl = gray ? npix : npix * 3;
-        CK(d_stage[sb].reserve(nfl));
         if (!img_pool.empty()) { f.d_img = img_pool.back(); img_pool.pop_back(); } else CK(cudaMalloc(&f.d_img, npix * sizeof(float4)));
-        CK(cudaMemcpyAsync(d_stage[sb].p, grad, nfl * sizeof(float), cudaMemcpyHostToDevice, stream));
-        CK(cudaEventRecord(ev_copy, stream));
-        if (gray) gradient_texel_kernel<<<dim3((unsigned) ((W + 127) / 128), (unsigned) H), 128, 0, stream>>>(d_stage[sb].p, f.d_img, W, H);
-        else repack_image_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(d_stage[sb].p, f.d_img, (int) npix);
-        CK(cudaGetLastError());
+        if (gray == 2) {          // `grad` is a DEVICE pointer to float4 (I, dx, dy, *) texels of this device (cmlimg's level 0): one device-to-device copy
+            CK(cudaMemcpyAsync(f.d_img, grad, npix * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+            CK(cudaEventRecord(ev_copy, stream));
+        } else {
+            CK(d_stage[sb].reserve(nfl));
+            CK(cudaMemcpyAsync(d_stage[sb].p, grad, nfl * sizeof(float), cudaMemcpyHostToDevice, stream));
+            CK(cudaEventRecord(ev_copy, stream));
+            if (gray) gradient_texel_kernel<<<dim3((unsigned) ((W + 127) / 128), (unsigned) H), 128, 0, stream>>>(d_stage[sb].p, f.d_img, W, H);
+            else repack_image_kernel<<<(unsigned) ((npix + 255) / 256), 256, 0, stream>>>(d_stage[sb].p, f.d_img, (int) npix);
+            CK(cudaGetLastError());
+        }
         const int slot = (int) frames_.size();
         frames_.push_back(f);
         if (keep_prior()) hm_grow();
@@ -367,7 +372,7 @@ public:
             points_[p].last_frame[1] = points_[p].last_frame[0]; points_[p].last_state[1] = points_[p].last_state[0];
             points_[p].last_frame[0] = id; points_[p].last_state[0] = CMLBA_RES_IN;
         }
-        if (!cfg.async_image_upload) CK(cudaEventSynchronize(ev_copy));
+        if (!cfg.async_image_upload || gray == 2) CK(cudaEventSynchronize(ev_copy));     // a device source may be overwritten by its owner right after the call
         dirty = true; prepared = false;
         return CMLBA_OK;
     }
@@ -1418,6 +1423,9 @@ const char *cmlba_last_error(const cmlba_handle *h) { return h ? h->eng.err.c_st
 int cmlba_set_calib(cmlba_handle *h, double fx, double fy, double cx, double cy, int w, int hh) { HCHK; return h->eng.set_calib(fx, fy, cx, cy, w, hh); }
 int cmlba_add_frame(cmlba_handle *h, int64_t id, const double w2c[12], double a, double b, double exposure, const float *grad, int is_init) { HCHK; return h->eng.add_frame(id, w2c, a, b, exposure, grad, is_init); }
 int cmlba_add_frame_gray(cmlba_handle *h, int64_t id, const double w2c[12], double a, double b, double exposure, const float *gray, int is_init) { HCHK; return h->eng.add_frame(id, w2c, a, b, exposure, gray, is_init, 1); }
+int cmlba_add_frame_device(cmlba_handle *h, int64_t id, const double w2c[12], double a, double b, double exposure, const void *d_texels, int is_init) {
+    HCHK; return h->eng.add_frame(id, w2c, a, b, exposure, static_cast<const float *>(d_texels), is_init, 2);
+}
 int cmlba_add_points(cmlba_handle *h, int n, const int64_t *pid, const int64_t *host, const float *xy, const double *idepth) { HCHK; return h->eng.add_points(n, pid, host, xy, idepth); }
 int cmlba_remove_point(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove_point(id); }
 int cmlba_remove_frame(cmlba_handle *h, int64_t id) { HCHK; return h->eng.remove_frame(id); }

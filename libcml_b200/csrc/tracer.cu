@@ -94,7 +94,7 @@ struct Tracer {
         return CMLTRC_OK;
     }
 
-    int add_frame(int64_t id, const float *gray, const double *cam, const double *expo) {
+    int add_frame(int64_t id, const float *gray, const double *cam, const double *expo, const void *d_texels = nullptr) {
         if (!gray || !cam || !expo) { error = "NULL argument"; return CMLTRC_ERR_ARG; }
         if (find(id) >= 0) { error = "frame id already present"; return CMLTRC_ERR_ARG; }
         int s = 0;
@@ -104,11 +104,16 @@ struct Tracer {
         Slot &sl = slots[s];
         const size_t px = (size_t) P.W * P.H;
         if (!sl.gray) { RCK(cudaMalloc(&sl.gray, px * 4)); RCK(cudaMalloc(&sl.grad, px * 16)); }
-        RCK(cudaStreamSynchronize(stream));
-        memcpy(h_pin, gray, px * 4);
-        RCK(cudaMemcpyAsync(sl.gray, h_pin, px * 4, cudaMemcpyHostToDevice, stream));
-        trc_grad_kernel<<<std::min<int>(1184, (int) ((px + 255) / 256)), 256, 0, stream>>>(sl.gray, sl.grad, P.W, P.H);
-        RCK(cudaGetLastError());
+        if (d_texels) {           // `gray` and `d_texels` are DEVICE pointers (level 0 of cmlimg): two device-to-device copies
+            RCK(cudaMemcpyAsync(sl.gray, gray, px * 4, cudaMemcpyDeviceToDevice, stream));
+            RCK(cudaMemcpyAsync(sl.grad, d_texels, px * 16, cudaMemcpyDeviceToDevice, stream));
+        } else {
+            RCK(cudaStreamSynchronize(stream));
+            memcpy(h_pin, gray, px * 4);
+            RCK(cudaMemcpyAsync(sl.gray, h_pin, px * 4, cudaMemcpyHostToDevice, stream));
+            trc_grad_kernel<<<std::min<int>(1184, (int) ((px + 255) / 256)), 256, 0, stream>>>(sl.gray, sl.grad, P.W, P.H);
+            RCK(cudaGetLastError());
+        }
         sl.used = true; sl.id = id;
         memcpy(sl.cam.R, cam, 72); memcpy(sl.cam.t, cam + 9, 24); memcpy(sl.exposure, expo, 24);
         return upload_frame_table();
@@ -311,6 +316,10 @@ int cmltrc_create(const cmltrc_config *cfg, int device, int width, int height, d
 void cmltrc_destroy(cmltrc_handle h) { delete TH(h); }
 const char *cmltrc_last_error(cmltrc_handle h) { return h ? TH(h)->error.c_str() : cmltrc::g_create_error.c_str(); }
 int cmltrc_add_frame(cmltrc_handle h, int64_t id, const float *gray, const double cam[12], const double exposure[3]) { return h ? TH(h)->add_frame(id, gray, cam, exposure) : CMLTRC_ERR_ARG; }
+int cmltrc_add_frame_device(cmltrc_handle h, int64_t id, const float *d_gray, const void *d_texels, const double cam[12], const double exposure[3]) {
+    if (!h || !d_texels) return CMLTRC_ERR_ARG;
+    return TH(h)->add_frame(id, d_gray, cam, exposure, d_texels);
+}
 int cmltrc_set_frame_pose(cmltrc_handle h, int64_t id, const double cam[12], const double exposure[3]) { return h ? TH(h)->set_pose(id, cam, exposure) : CMLTRC_ERR_ARG; }
 int cmltrc_remove_frame(cmltrc_handle h, int64_t id) { return h ? TH(h)->remove_frame(id) : CMLTRC_ERR_ARG; }
 int cmltrc_make_new_traces(cmltrc_handle h, int64_t id, int count, const float *xy, int64_t *first_id) { return h ? TH(h)->make_new_traces(id, count, xy, first_id) : CMLTRC_ERR_ARG; }

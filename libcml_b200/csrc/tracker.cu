@@ -49,7 +49,8 @@ struct Tracker {
     Candidate *d_cand = nullptr;
     TrackOut *d_out = nullptr;
     char *d_pts = nullptr; size_t pts_cap = 0;
-    bool have_ref = false, have_frame = false;
+    bool have_ref = false, have_frame = false, frame_external = false, ref_levels_on_device = false;
+    const float4 *ext_grad[MAXL]{};
     Pose ref_pose{};
     double ref_exposure[3]{1, 0, 0}, new_tau = 1.0;
     TrackParams params{};
@@ -163,12 +164,21 @@ struct Tracker {
         return CMLTRK_OK;
     }
 
+    // frame to track from device-resident texel levels (float4 (I, dx, dy, *), e.g. cmlimg's): zero-copy, the pointers are sampled in place
+    int set_frame_device(int levels, const void *const *d_texels, double tau) {
+        if (levels < std::min(L, (int) OPTL) || !d_texels) { error = "need the texels of every level the optimisation uses"; return CMLTRK_ERR_ARG; }
+        for (int l = 0; l < std::min(L, (int) OPTL); l++) if (!d_texels[l]) { error = "NULL level"; return CMLTRK_ERR_ARG; }
+        for (int l = 0; l < MAXL; l++) ext_grad[l] = (l < levels && l < L) ? static_cast<const float4 *>(d_texels[l]) : nullptr;
+        new_tau = tau; have_frame = true; frame_external = true;
+        return CMLTRK_OK;
+    }
+
     int set_frame(const float *gray, double tau) {
         if (!gray) { error = "gray is NULL"; return CMLTRK_ERR_ARG; }
         TCK(cudaSetDevice(device));
         int rc = upload_pyramid(gray, gray_new, true);
         if (rc) return rc;
-        new_tau = tau; have_frame = true;
+        new_tau = tau; have_frame = true; frame_external = false;
         return CMLTRK_OK;
     }
 
@@ -177,8 +187,16 @@ struct Tracker {
         if (!ref_gray || !ref_cam || !ref_exp || F < 0 || P < 0 || (P > 0 && (!frame_cams || !pt_frame || !pt_xy || !pt_idepth || !pt_unc))) { error = "NULL argument"; return CMLTRK_ERR_ARG; }
         for (int i = 0; i < P; i++) if (pt_frame[i] < 0 || pt_frame[i] >= F) { error = "pt_frame out of range"; return CMLTRK_ERR_ARG; }
         TCK(cudaSetDevice(device));
-        int rc = upload_pyramid(ref_gray, gray_ref, false);
-        if (rc) return rc;
+        if (ref_levels_on_device) {       // ref_gray = array of L device pointers to the gray levels (cmlimg): device-to-device copies, no pyramid kernel
+            const float *const *lv = reinterpret_cast<const float *const *>(ref_gray);
+            for (int l = 0; l < L; l++) {
+                if (!lv[l]) { error = "NULL gray level"; return CMLTRK_ERR_ARG; }
+                TCK(cudaMemcpyAsync(gray_ref[l], lv[l], (size_t) w[l] * h[l] * 4, cudaMemcpyDeviceToDevice, stream));
+            }
+        } else {
+            int rc = upload_pyramid(ref_gray, gray_ref, false);
+            if (rc) return rc;
+        }
         memcpy(ref_pose.R, ref_cam, 72); memcpy(ref_pose.t, ref_cam + 9, 24);
         memcpy(ref_exposure, ref_exp, 24);
         // host-to-reference transforms in fp64 (Camera::to), one row of 12 per frame
@@ -233,7 +251,7 @@ struct Tracker {
         p.max_level = std::min(L - 1, 4);
         for (int l = 0; l < OPTL; l++) {
             const int s = std::min(l, L - 1);
-            p.lv[l] = LevelDev{w[s], h[s], (float) K[s][0], (float) K[s][1], (float) K[s][2], (float) K[s][3], pc[s], pc_n + s, grad_new[s]};
+            p.lv[l] = LevelDev{w[s], h[s], (float) K[s][0], (float) K[s][1], (float) K[s][2], (float) K[s][3], pc[s], pc_n + s, (frame_external && ext_grad[s]) ? ext_grad[s] : grad_new[s]};
         }
         p.huber = (float) cfg.huber_threshold; p.cutoff = (float) cfg.cutoff_threshold;
         const float sc[8] = {(float) cfg.scale_rotation, (float) cfg.scale_rotation, (float) cfg.scale_rotation, (float) cfg.scale_translation, (float) cfg.scale_translation,
@@ -384,6 +402,23 @@ int cmltrk_make_coarse_depth(cmltrk_handle h, const float *ref_gray, const doubl
                              int num_points, const int32_t *pt_frame, const float *pt_xy, const double *pt_idepth, const double *pt_uncertainty) {
     if (!h) return CMLTRK_ERR_ARG;
     return reinterpret_cast<Tracker *>(h)->make_coarse_depth(ref_gray, ref_cam, ref_exposure, num_frames, frame_cams, num_points, pt_frame, pt_xy, pt_idepth, pt_uncertainty);
+}
+
+int cmltrk_make_coarse_depth_device(cmltrk_handle h, int levels, const float *const *d_gray_levels, const double ref_cam[12], const double ref_exposure[3], int num_frames,
+                                    const double *frame_cams, int num_points, const int32_t *pt_frame, const float *pt_xy, const double *pt_idepth, const double *pt_uncertainty) {
+    if (!h || !d_gray_levels) return CMLTRK_ERR_ARG;
+    Tracker *t = reinterpret_cast<Tracker *>(h);
+    if (levels < t->L) { t->error = "need every pyramid level of the reference keyframe"; return CMLTRK_ERR_ARG; }
+    t->ref_levels_on_device = true;
+    const int rc = t->make_coarse_depth(reinterpret_cast<const float *>(d_gray_levels), ref_cam, ref_exposure, num_frames, frame_cams, num_points, pt_frame, pt_xy, pt_idepth,
+                                        pt_uncertainty);
+    t->ref_levels_on_device = false;
+    return rc;
+}
+
+int cmltrk_set_frame_device(cmltrk_handle h, int levels, const void *const *d_texel_levels, double exposure_time) {
+    if (!h) return CMLTRK_ERR_ARG;
+    return reinterpret_cast<Tracker *>(h)->set_frame_device(levels, d_texel_levels, exposure_time);
 }
 
 int cmltrk_set_frame(cmltrk_handle h, const float *gray, double exposure_time) {

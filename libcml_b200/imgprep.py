@@ -54,6 +54,13 @@ class CaptureImage:
     def getPyramidLevels(self):
         return len(self.gen.sizes)
 
+    def devicePtr(self, name):
+        """Device address (int) of "gray<l>" / "texel<l>" for the device-resident entry points of the tracker, the tracer and the BA."""
+        p = self.gen.lib.cmlimg_device_ptr(self.gen.h, name.encode())
+        if not p:
+            raise KeyError(name)
+        return int(p)
+
     def _texel(self, level):
         w, h = self.gen.sizes[level]
         return self.gen._read(f"texel{level}", (h, w, 4))

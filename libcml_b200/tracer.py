@@ -25,7 +25,7 @@ POINT = np.dtype([("status", "<i4"), ("host_frame_slot", "<i4"), ("idepth_min", 
                   ("last_trace_pixel_interval", "<f8"), ("quality", "<f8"), ("grad_h", "<f8", 4), ("energy_th", "<f8")])
 ACTIVATION = np.dtype([("rc", "<i4"), ("idepth", "<f4"), ("in_mask", "<u4")])
 
-TRACER_SYMBOLS = ["cmltrc_default_config", "cmltrc_create", "cmltrc_destroy", "cmltrc_last_error", "cmltrc_add_frame", "cmltrc_set_frame_pose", "cmltrc_remove_frame",
+TRACER_SYMBOLS = ["cmltrc_default_config", "cmltrc_create", "cmltrc_destroy", "cmltrc_last_error", "cmltrc_add_frame", "cmltrc_add_frame_device", "cmltrc_set_frame_pose", "cmltrc_remove_frame",
                   "cmltrc_make_new_traces", "cmltrc_remove_points", "cmltrc_num_points", "cmltrc_trace_new_coarse", "cmltrc_optimize_immature", "cmltrc_get_points"]
 
 _bound = False
@@ -42,6 +42,7 @@ def _bind(lib):
     lib.cmltrc_last_error.restype = C.c_char_p
     lib.cmltrc_last_error.argtypes = [vp]
     lib.cmltrc_add_frame.argtypes = [vp, i64, fp, dp, dp]
+    lib.cmltrc_add_frame_device.argtypes = [vp, i64, vp, vp, dp, dp]
     lib.cmltrc_set_frame_pose.argtypes = [vp, i64, dp, dp]
     lib.cmltrc_remove_frame.argtypes = [vp, i64]
     lib.cmltrc_make_new_traces.argtypes = [vp, i64, C.c_int, fp, C.POINTER(i64)]
@@ -100,6 +101,11 @@ class DSOTracer:
             raise ValueError(f"gray image must be [{self.height}][{self.width}]")
         cam = np.ascontiguousarray(camera, dtype=np.float64).reshape(12); ex = np.ascontiguousarray(exposure, dtype=np.float64).reshape(3)
         self._ck(self.lib.cmltrc_add_frame(self.h, int(frame_id), g.ctypes.data_as(C.POINTER(C.c_float)), _dp(cam), _dp(ex)))
+
+    def addFrameDevice(self, frame_id, capture, camera, exposure):
+        """addFrame from a device-resident CaptureImage (libcml_b200.imgprep): level-0 gray and texels are copied device to device."""
+        cam = np.ascontiguousarray(camera, dtype=np.float64).reshape(12); ex = np.ascontiguousarray(exposure, dtype=np.float64).reshape(3)
+        self._ck(self.lib.cmltrc_add_frame_device(self.h, int(frame_id), C.c_void_p(capture.devicePtr("gray0")), C.c_void_p(capture.devicePtr("texel0")), _dp(cam), _dp(ex)))
 
     def setFramePose(self, frame_id, camera, exposure):
         cam = np.ascontiguousarray(camera, dtype=np.float64).reshape(12); ex = np.ascontiguousarray(exposure, dtype=np.float64).reshape(3)

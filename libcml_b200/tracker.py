@@ -30,7 +30,7 @@ class TrackerResult(C.Structure):
 
 
 TRACKER_SYMBOLS = ["cmltrk_default_config", "cmltrk_create", "cmltrk_destroy", "cmltrk_last_error", "cmltrk_make_coarse_depth", "cmltrk_set_frame", "cmltrk_optimize",
-                   "cmltrk_track", "cmltrk_read", "cmltrk_bench_optimize", "cmltrk_frame_buffer"]
+                   "cmltrk_track", "cmltrk_read", "cmltrk_bench_optimize", "cmltrk_frame_buffer", "cmltrk_make_coarse_depth_device", "cmltrk_set_frame_device"]
 
 _bound = False
 
@@ -47,6 +47,8 @@ def _bind(lib):
     lib.cmltrk_last_error.argtypes = [vp]
     lib.cmltrk_make_coarse_depth.argtypes = [vp, fp, dp, dp, C.c_int, dp, C.c_int, C.POINTER(C.c_int32), fp, dp, dp]
     lib.cmltrk_set_frame.argtypes = [vp, fp, C.c_double]
+    lib.cmltrk_make_coarse_depth_device.argtypes = [vp, C.c_int, C.POINTER(vp), dp, dp, C.c_int, dp, C.c_int, C.POINTER(C.c_int32), fp, dp, dp]
+    lib.cmltrk_set_frame_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_double]
     lib.cmltrk_optimize.argtypes = [vp, C.c_int, dp, dp, dp, C.POINTER(TrackerResult)]
     lib.cmltrk_track.argtypes = [vp, fp, C.c_double, C.c_int, dp, dp, dp, C.POINTER(TrackerResult)]
     lib.cmltrk_read.restype = C.c_int64
@@ -153,6 +155,26 @@ class DSOTracker:
             raise ValueError("point arrays differ in length")
         self._ck(self.lib.cmltrk_make_coarse_depth(self.h, _fp(g), _dp(rc_), _dp(re_), fc.shape[0], _dp(fc), pf.size, pf.ctypes.data_as(C.POINTER(C.c_int32)), _fp(xy),
                                                    _dp(idp), _dp(unc)))
+
+    def makeCoarseDepthL0Device(self, ref_capture, ref_camera, ref_exposure, frame_cameras, pt_frame, pt_xy, pt_idepth, pt_uncertainty):
+        """makeCoarseDepthL0 with the reference keyframe's gray levels taken from a device-resident CaptureImage (libcml_b200.imgprep)."""
+        L = ref_capture.getPyramidLevels()
+        lv = (C.c_void_p * L)(*[ref_capture.devicePtr(f"gray{l}") for l in range(L)])
+        rc_ = np.ascontiguousarray(ref_camera, dtype=np.float64).reshape(12)
+        re_ = np.ascontiguousarray(ref_exposure, dtype=np.float64).reshape(3)
+        fc = np.ascontiguousarray(frame_cameras, dtype=np.float64).reshape(-1, 12)
+        pf = np.ascontiguousarray(pt_frame, dtype=np.int32)
+        xy = np.ascontiguousarray(pt_xy, dtype=np.float32).reshape(-1, 2)
+        idp = np.ascontiguousarray(pt_idepth, dtype=np.float64)
+        unc = np.ascontiguousarray(pt_uncertainty, dtype=np.float64)
+        self._ck(self.lib.cmltrk_make_coarse_depth_device(self.h, L, lv, _dp(rc_), _dp(re_), fc.shape[0], _dp(fc), pf.size, pf.ctypes.data_as(C.POINTER(C.c_int32)), _fp(xy),
+                                                          _dp(idp), _dp(unc)))
+
+    def setFrameDevice(self, capture, exposure_time=1.0):
+        """Frame to track = the texel levels of a device-resident CaptureImage, sampled in place (valid until the generator's next generate())."""
+        L = capture.getPyramidLevels()
+        lv = (C.c_void_p * L)(*[capture.devicePtr(f"texel{l}") for l in range(L)])
+        self._ck(self.lib.cmltrk_set_frame_device(self.h, L, lv, float(exposure_time)))
 
     def frameBuffer(self):
         """The handle's page-locked staging image as a numpy view: fill it in place and pass it as `gray` to skip the host-side copy."""

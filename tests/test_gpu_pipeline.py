@@ -1,0 +1,90 @@
+"""The device-resident hand-over between the components: a frame prepared once by cmlimg is consumed by the tracker (texels sampled in place),
+the tracer and the bundle adjustment (device-to-device copies) without going back to the host.  Every consumer must produce exactly the bits
+it produces from the host image."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from libcml_b200 import cmlw  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_tracker_from_device_levels_is_bit_identical():
+    from libcml_b200 import CaptureImageGenerator, DSOTracker
+    win = cmlw.load(os.path.join(GOLDEN, "track_window.cmlw")); g = cmlw.load(os.path.join(GOLDEN, "track_golden.cmlw"))
+    H, W = win["gray"].shape[1:]
+    ref, new = int(win["track_ref"][0]), int(win["track_new"][0])
+    keep = win["pt_host"] != new
+    ref_exp = (win["frame_exposure"][ref], win["frame_affine"][ref, 0], win["frame_affine"][ref, 1])
+    args = (win["frame_cam"][ref], ref_exp, win["frame_cam"], win["pt_host"][keep], win["pt_xy"][keep], win["pt_idepth"][keep], win["pt_uncertainty"][keep])
+    host = DSOTracker(W, H, win["calib"])
+    host.makeCoarseDepthL0(win["gray"][ref], *args)
+    a = host.optimize(g["a_init_cam"], g["a_new_affine"], gray=win["gray"][new], exposure_time=win["frame_exposure"][new])
+    gen_ref, gen_new = CaptureImageGenerator(W, H), CaptureImageGenerator(W, H)
+    dev = DSOTracker(W, H, win["calib"])
+    dev.makeCoarseDepthL0Device(gen_ref.generate(win["gray"][ref]), *args)
+    dev.setFrameDevice(gen_new.generate(win["gray"][new]), win["frame_exposure"][new])
+    b = dev.optimize(g["a_init_cam"], g["a_new_affine"])
+    assert np.array_equal(a.camera, b.camera) and np.array_equal(a.exposure, b.exposure) and np.array_equal(a.E, b.E) and a.iterations == b.iterations
+    assert b.kernel_launches == 1                          # the optimisation alone: no pyramid kernels on this path
+    for l in range(5):
+        assert np.array_equal(host.read(f"pc{l}", np.float32), dev.read(f"pc{l}", np.float32))
+
+
+def test_tracer_from_device_frame_is_bit_identical():
+    from libcml_b200 import CaptureImageGenerator, DSOTracer
+    win = cmlw.load(os.path.join(GOLDEN, "trace_window.cmlw"))
+    H, W = win["gray"].shape[1:]
+    N = 3
+    ex = [(win["frame_exposure"][i], win["frame_affine"][i, 0], win["frame_affine"][i, 1]) for i in range(N)]
+    gen = CaptureImageGenerator(W, H)
+
+    def flow(device_frames):
+        trc = DSOTracer(W, H, win["calib"])
+        for f in range(N):
+            if device_frames:
+                trc.addFrameDevice(f, gen.generate(win["gray"][f]), win["frame_cam"][f], ex[f])
+            else:
+                trc.addFrame(f, win["gray"][f], win["frame_cam"][f], ex[f])
+            if f > 0:
+                trc.traceNewCoarse(f)
+            sel = np.nonzero(win["im_host"] == f)[0]
+            trc.makeNewTracesFrom(f, win["im_xy"][sel])
+        pts = trc.getPoints()
+        cand = np.nonzero(np.isfinite(pts["idepth_max"]))[0]
+        return pts, trc.optimizeImmaturePoint(cand)
+    p0, r0 = flow(False)
+    p1, r1 = flow(True)
+    assert p0.tobytes() == p1.tobytes() and r0.tobytes() == r1.tobytes()
+
+
+def test_bundle_adjustment_from_device_texels_is_bit_identical():
+    from libcml_b200 import CaptureImageGenerator, DSOBundleAdjustment, synth
+    win = synth.make_config("tiny")
+    H, W = win["gray"].shape[1:]
+    N = win["frame_evalpt"].shape[0]
+    P = win["pt_host"].size
+    gen = CaptureImageGenerator(W, H)
+
+    def run(device_frames):
+        ba = DSOBundleAdjustment(device=0, iterations=int(win["iterations"][0]))
+        ba.setCalibration(*[float(v) for v in win["calib"]], W, H)
+        for f in range(N):
+            a = (f, win["frame_evalpt"][f], win["frame_affine"][f, 0], win["frame_affine"][f, 1], win["frame_exposure"][f])
+            if device_frames:
+                ba.addNewFrameDevice(*a, gen.generate(win["gray"][f]).devicePtr("texel0"), bool(win["frame_init"][f]) if "frame_init" in win else False)
+            else:
+                ba.addNewFrameGray(*a, win["gray"][f], bool(win["frame_init"][f]) if "frame_init" in win else False)
+        ba.addPoints(np.arange(P), win["pt_host"], win["pt_xy"], win["pt_idepth"])
+        assert ba.run(win["frame_cam"], iterations=int(win["iterations"][0]))
+        return ba.getFrames(), ba.getPoints()
+    f0, p0 = run(False)
+    f1, p1 = run(True)
+    assert np.array_equal(f0["world_to_cam"], f1["world_to_cam"]) and np.array_equal(f0["affine"], f1["affine"])
+    assert np.array_equal(p0["idepth"], p1["idepth"]) and np.array_equal(p0["id"], p1["id"])
