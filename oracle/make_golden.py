@@ -212,8 +212,29 @@ def prepare():
     print("prepare window", os.path.getsize(os.path.join(OUT, "prepare_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "prepare_golden.cmlw")) // 1024, "KB")
 
 
+def select():
+    """PixelSelector::compute of the reference (SURVEY 8f NEXT #4, PixelSelector part) on one 256x192 frame, five successive densities on the same
+    selector (the potential carries over; densities 150 and 2500 trigger the re-sampling recursion in both directions, 600 the random sub-sampling)."""
+    tmp = "/tmp/cmlba_golden"
+    os.makedirs(tmp, exist_ok=True)
+    W, H = 256, 192
+    win = synth.make_window(W, H, 2, 10, 1, False, seed=9, low_freq=True)
+    w = dict(size=np.array([W, H], np.int32), calib=win["calib"], gray=win["gray"][0], densities=np.array([600.0, 600.0, 150.0, 2500.0, 2500.0]))
+    cmlw.save(os.path.join(tmp, "select.cmlw"), w)
+    run_ref(os.path.join(tmp, "select.cmlw"), "select", os.path.join(tmp, "select_out.cmlw"))
+    g = cmlw.load(os.path.join(tmp, "select_out.cmlw"))
+    pots = [int(g[f"sel_pot_after{d}"][0]) for d in range(5)]
+    assert len(set(pots)) >= 3, "the potential must move in both directions"
+    gold = {k: v for k, v in g.items() if k != "sel_seconds"}
+    cmlw.save(os.path.join(OUT, "select_window.cmlw"), w)
+    cmlw.save(os.path.join(OUT, "select_golden.cmlw"), gold)
+    print("select window", os.path.getsize(os.path.join(OUT, "select_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "select_golden.cmlw")) // 1024, "KB", pots)
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    if len(sys.argv) > 1 and sys.argv[1] == "select":
+        select(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "prepare":
         prepare(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tracer":

@@ -56,6 +56,7 @@
 #include <cml/optimization/dso/DSOBundleAdjustment.h>
 #include <cml/optimization/dso/DSOTracker.h>
 #include <cml/optimization/dso/DSOTracer.h>
+#include <cml/features/corner/PixelSelector.h>
 #undef private
 #undef protected
 
@@ -769,6 +770,47 @@ static int runPrepare(const cmlw::File &in, cmlw::File &out, int repeat) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// mode select: DSO pixel selector (SURVEY 8f NEXT #4, PixelSelector part): PixelSelector::compute on the prepared frame `gray`
+// (features/corner/PixelSelector.cpp:367-384 -> makeMaps :121-213 -> makeHists :41-118, select :217-365), for every density in `densities`
+// on the SAME selector instance (currentPotential carries over, like successive keyframes).
+static int runSelect(const cmlw::File &in, cmlw::File &out, int repeat) {
+    const int32_t *size = in.get("size").as<int32_t>();
+    const int W = size[0], H = size[1];
+    const double *K = in.get("calib").as<double>();
+    Root *root = new Root;
+    auto *calib = new InternalCalibration(PinholeUndistorter(Vector2(K[0], K[1]), Vector2(K[2], K[3])), Vector2(W, H));
+    auto *gen = new CaptureImageGenerator(W, H, 4, 4);
+    FloatImage img(W, H);
+    memcpy(img.data(), in.get("gray").as<float>(), sizeof(float) * W * H);
+    auto cap = gen->create().setImage(img).setTime(0).setCalibration(calib).setExposure(1).generate();
+    Features::PixelSelector sel(root, W, H);
+    const double *dens = in.get("densities").as<double>();
+    const int nd = (int) in.get("densities").dims[0];
+    double best = 1e30;
+    for (int d = 0; d < nd; d++) {
+        List<Corner> corners; List<float> types;
+        const int potBefore = sel.currentPotential;
+        const double a = now_s();
+        sel.compute(*cap.p(), corners, types, (float) dens[d]);
+        best = std::min(best, now_s() - a);
+        std::vector<float> xy(corners.size() * 2), ty(types.begin(), types.end());
+        for (size_t i = 0; i < corners.size(); i++) { xy[2 * i] = corners[i].point(0).x(); xy[2 * i + 1] = corners[i].point(0).y(); }
+        out.put<float>("sel_xy" + std::to_string(d), xy, {(uint64_t) corners.size(), 2});
+        out.put1<float>("sel_type" + std::to_string(d), ty);
+        out.scalar<int32_t>("sel_pot_before" + std::to_string(d), potBefore);
+        out.scalar<int32_t>("sel_pot_after" + std::to_string(d), sel.currentPotential);
+        if (d == 0) {
+            const int w32 = W / 32, h32 = H / 32;
+            std::vector<float> ths(sel.ths, sel.ths + w32 * h32), sm(sel.thsSmoothed, sel.thsSmoothed + w32 * h32);
+            out.put<float>("sel_ths", ths, {(uint64_t) h32, (uint64_t) w32}); out.put<float>("sel_ths_smoothed", sm, {(uint64_t) h32, (uint64_t) w32});
+        }
+    }
+    out.scalar<double>("sel_seconds", best);
+    printf("{\"select_seconds\": %.6f}\n", best);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     std::string window, mode = "stages", outPath;
     int repeat = 3;
@@ -785,6 +827,13 @@ int main(int argc, char **argv) {
     if (!in.load(window)) { fprintf(stderr, "cannot read %s\n", window.c_str()); return 2; }
 
     int rc = 0;
+    if (mode == "select") {
+        cmlw::File out;
+        rc = runSelect(in, out, repeat);
+        if (!outPath.empty()) out.save(outPath);
+        fflush(stdout);
+        _exit(rc);
+    }
     if (mode == "prepare") {
         cmlw::File out;
         rc = runPrepare(in, out, repeat);
