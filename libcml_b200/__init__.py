@@ -10,3 +10,4 @@ from .binding import DSOBundleAdjustment, CmlbaError, load_library, lib_path  # 
 from .tracker import DSOTracker  # noqa: F401
 from .tracer import DSOTracer  # noqa: F401
 from .imgprep import CaptureImageGenerator  # noqa: F401
+from .selector import PixelSelector  # noqa: F401

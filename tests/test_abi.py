@@ -78,6 +78,21 @@ def test_imgprep_header_symbols_exported(lib):
         assert imgprep._bind(lib).cmlimg_create(0, 640, 480, 640, 480, 0, C.byref(h)) == -2 and b"no CUDA device" in lib.cmlimg_last_error(None)
 
 
+def test_selector_header_symbols_exported(lib):
+    """include/cmlsel.h (pixel selector boundary)."""
+    from libcml_b200 import selector
+    src = open(os.path.join(ROOT, "include", "cmlsel.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(cmlsel_[a-z_0-9]+)\s*\(", src)))
+    assert sorted(selector.SEL_SYMBOLS) == syms and len(syms) == 7
+    for s in syms:
+        assert hasattr(lib, s), f"libcmlba.so does not export {s}"
+    import torch
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert selector._bind(lib).cmlsel_create(0, 640, 480, C.byref(h)) == -2 and b"no CUDA device" in lib.cmlsel_last_error(None)
+
+
 def ctypes_sizeof_matches(tracer):
     # cmltrc_point: 2 x int32 + 11 doubles; cmltrc_activation: int32 + float + uint32
     return tracer.POINT.itemsize == 96 and tracer.ACTIVATION.itemsize == 12
