@@ -140,6 +140,81 @@ __global__ void __launch_bounds__(128) sel_block_kernel(const SelDev s, const in
     if (c4) atomicAdd(s.counters + 2, c4);
 }
 
+// The same block, one WARP per 4*pot block (used for pot >= 3, where a block has >= 144 pixels).  The sticky -2 flags of the reference reduce
+// to: a pot block selects its best level-1 candidate; a 2*pot block selects a level-2 point only if none of its pot blocks selected; the
+// 4*pot block selects a level-3 point only if nothing else was selected in it; "best" = largest |grad . dir| with the FIRST pixel in the
+// reference's traversal order winning ties (strict > in the sequential code).  The lanes stride the pixels of a pot block, keep running
+// bests with strict >, and the warp combines (value, traversal position) by shuffles.
+struct Best { float v; int pos, idx; };
+__device__ __forceinline__ Best warp_best(Best b) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, b.v, off);
+        const int op = __shfl_xor_sync(0xffffffffu, b.pos, off), oi = __shfl_xor_sync(0xffffffffu, b.idx, off);
+        if (oi >= 0 && (b.idx < 0 || ov > b.v || (ov == b.v && op < b.pos))) { b.v = ov; b.pos = op; b.idx = oi; }
+    }
+    return b;
+}
+__global__ void __launch_bounds__(128) sel_block_warp_kernel(const SelDev s, const int pot, const float thFactor, const int nbx, const int nblocks) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= nblocks) return;
+    const int w = s.w, h = s.h;
+    const int x4 = (b % nbx) * 4 * pot, y4 = (b / nbx) * 4 * pot;
+    const float dw1 = 0.75f, dw2 = dw1 * dw1;
+    int n2 = s.start[b], c2 = 0, c3 = 0, c4 = 0;
+    const int my3 = min(4 * pot, h - y4), mx3 = min(4 * pot, w - x4);
+    const int d4 = s.pattern[n2] & 0xF;
+    Best b4{0.f, 0, -1};
+    int seq = 0;
+    for (int y3 = 0; y3 < my3; y3 += 2 * pot) for (int x3 = 0; x3 < mx3; x3 += 2 * pot) {
+        const int x34 = x3 + x4, y34 = y3 + y4;
+        const int my2 = min(2 * pot, h - y34), mx2 = min(2 * pot, w - x34);
+        const int d3 = s.pattern[n2] & 0xF;
+        Best b3{0.f, 0, -1};
+        int c2_here = 0;
+        for (int y2 = 0; y2 < my2; y2 += pot) for (int x2 = 0; x2 < mx2; x2 += pot, seq++) {
+            const int x234 = x2 + x34, y234 = y2 + y34;
+            const int my1 = min(pot, h - y234), mx1 = min(pot, w - x234);
+            const int d2 = s.pattern[n2] & 0xF;
+            Best b2{0.f, 0, -1};
+            for (int k = lane; k < my1 * mx1; k += 32) {
+                const int y1 = k / mx1, x1 = k - y1 * mx1;
+                const int xf = x1 + x234, yf = y1 + y234, idx = xf + w * yf;
+                if (xf < 4 || xf >= w - 5 || yf < 4 || yf > h - 4) continue;
+                const float th0 = s.ths_smoothed[(xf >> 5) + (yf >> 5) * s.w32];
+                const float th1 = th0 * dw1, th2 = th1 * dw2;
+                const float4 t = s.t0[idx];
+                const int pos = (seq << 16) | k;
+                if (t.w > th0 * thFactor) {
+                    const float dn = fabsf(__fadd_rn(__fmul_rn(t.y, c_dir[d2][0]), __fmul_rn(t.z, c_dir[d2][1])));
+                    if (dn > b2.v) { b2.v = dn; b2.pos = pos; b2.idx = idx; }
+                }
+                const float ag1 = s.t1[(size_t) (int) ((float) yf * 0.5f + 0.25f) * s.w1 + (int) ((float) xf * 0.5f + 0.25f)].w;
+                if (ag1 > th1 * thFactor) {
+                    const float dn = fabsf(__fadd_rn(__fmul_rn(t.y, c_dir[d3][0]), __fmul_rn(t.z, c_dir[d3][1])));
+                    if (dn > b3.v) { b3.v = dn; b3.pos = pos; b3.idx = idx; }
+                }
+                const float ag2 = s.t2[(size_t) (int) ((double) ((float) yf * 0.25f) + 0.125) * s.w2 + (int) ((double) ((float) xf * 0.25f) + 0.125)].w;
+                if (ag2 > th2 * thFactor) {
+                    const float dn = fabsf(__fadd_rn(__fmul_rn(t.y, c_dir[d4][0]), __fmul_rn(t.z, c_dir[d4][1])));
+                    if (dn > b4.v) { b4.v = dn; b4.pos = pos; b4.idx = idx; }
+                }
+            }
+            b2 = warp_best(b2);
+            if (b2.idx > 0) { if (lane == 0) s.map[b2.idx] = 1.f; n2++; c2++; c2_here++; }
+        }
+        b3 = warp_best(b3);
+        if (c2_here == 0 && b3.idx > 0) { if (lane == 0) s.map[b3.idx] = 2.f; c3++; }
+    }
+    b4 = warp_best(b4);
+    if (c2 == 0 && c3 == 0 && b4.idx > 0) { if (lane == 0) s.map[b4.idx] = 4.f; c4++; }
+    if (lane != 0) return;
+    if (c2 != s.hits[b]) { s.hits[b] = c2; atomicAdd(s.counters + 3, 1); }
+    if (c2) atomicAdd(s.counters + 0, c2);
+    if (c3) atomicAdd(s.counters + 1, c3);
+    if (c4) atomicAdd(s.counters + 2, c4);
+}
+
 // exclusive prefix sum, one CTA (n <= a few 100k)
 __global__ void __launch_bounds__(1024) sel_scan_kernel(const int *__restrict__ in, int *__restrict__ out, const int n) {
     __shared__ int warp_tot[32];
@@ -283,7 +358,9 @@ struct Selector {
         for (int it = 0; it < nb + 2; it++) {
             SCK(cudaMemsetAsync(d_map, 0, (size_t) w * h * 4, stream));
             SCK(cudaMemsetAsync(d_counters, 0, 32, stream));
-            sel_block_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(s, pot, thf, nbx, nb); launches++;
+            if (pot >= 3) sel_block_warp_kernel<<<(nb + 3) / 4, 128, 0, stream>>>(s, pot, thf, nbx, nb);
+            else sel_block_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(s, pot, thf, nbx, nb);
+            launches++;
             SCK(cudaMemcpyAsync(h_pin, d_counters, 16, cudaMemcpyDeviceToHost, stream));
             SCK(cudaStreamSynchronize(stream));
             n[0] = h_pin[0]; n[1] = h_pin[1]; n[2] = h_pin[2];
