@@ -40,7 +40,7 @@ def gradient_image(gray):
 
 
 def make_window(W=640, H=480, N=8, pts_per_kf=2000, iterations=6, affine=False, seed=1234,
-                idepth_noise=0.005, pose_noise=5e-4, fej_offset=True, with_gradients=True, low_freq=False):
+                idepth_noise=0.005, pose_noise=5e-4, fej_offset=True, with_gradients=True, low_freq=False, with_depth=False):
     rng = np.random.default_rng(seed)
     fx = fy = 0.78 * W
     cx, cy = (W - 1) / 2.0, (H - 1) / 2.0
@@ -139,6 +139,8 @@ def make_window(W=640, H=480, N=8, pts_per_kf=2000, iterations=6, affine=False, 
     }
     if with_gradients:
         win["grad"] = np.stack([gradient_image(gray[i]) for i in range(N)])
+    if with_depth:
+        win["truth_depth"] = depth          # [N][H][W] depth of the plane along the optical axis (pipeline sanity checks)
     return win
 
 

@@ -88,3 +88,16 @@ def test_bundle_adjustment_from_device_texels_is_bit_identical():
     f1, p1 = run(True)
     assert np.array_equal(f0["world_to_cam"], f1["world_to_cam"]) and np.array_equal(f0["affine"], f1["affine"])
     assert np.array_equal(p0["idepth"], p1["idepth"]) and np.array_equal(p0["id"], p1["id"])
+
+
+def test_direct_pipeline_end_to_end_on_synthetic_truth():
+    """prepare -> select -> trace -> activate -> bundle adjustment -> track, all on the device, against the analytic truth of the synthetic scene
+    (tools/pipeline_demo.py): every stage must land where the geometry says."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import pipeline_demo
+    r = pipeline_demo.run()
+    assert min(r["selected_per_keyframe"]) > 100 and r["activated"] > 0.9 * r["traced_points"]
+    assert r["activation_idepth_median_rel_err"] < 5e-3 and r["activation_idepth_p90_rel_err"] < 2e-2          # tracer + activation recover the plane's depth
+    assert r["ba_ok"] and r["ba_energy_last"] < 0.1 * r["ba_energy_first"]
+    assert r["ba_reproj_px_after"] < 0.1 and r["ba_reproj_px_after"] < 0.25 * r["ba_reproj_px_before"]         # BA: 0.45 px -> 0.04 px
+    assert r["track_ok"] and r["track_reproj_px_after"] < 0.15 and r["track_reproj_px_after"] < 0.25 * r["track_reproj_px_before"]
