@@ -101,3 +101,30 @@ def test_direct_pipeline_end_to_end_on_synthetic_truth():
     assert r["ba_ok"] and r["ba_energy_last"] < 0.1 * r["ba_energy_first"]
     assert r["ba_reproj_px_after"] < 0.1 and r["ba_reproj_px_after"] < 0.25 * r["ba_reproj_px_before"]         # BA: 0.45 px -> 0.04 px
     assert r["track_ok"] and r["track_reproj_px_after"] < 0.15 and r["track_reproj_px_after"] < 0.25 * r["track_reproj_px_before"]
+
+
+def test_degenerate_inputs_fail_cleanly():
+    """Empty point sets and texture-less images: every component must return the reference's 'nothing to do' outcome, never hang or crash."""
+    from libcml_b200 import CaptureImageGenerator, DSOTracer, DSOTracker, PixelSelector
+    W, H = 128, 96
+    K = (100.0, 100.0, 63.5, 47.5)
+    flat = np.full((H, W), 100.0, np.float32)
+    cam = np.concatenate([np.eye(3).ravel(), np.zeros(3)])
+    cap = CaptureImageGenerator(W, H).generate(flat)
+    # selector: no gradient anywhere -> no corners, the potential walks down to 1 and stops
+    sel = PixelSelector(W, H)
+    xy, ty = sel.compute(cap, 500.0)
+    assert xy.shape == (0, 2) and ty.size == 0 and sel.currentPotential >= 1
+    # tracker: no points -> fewer than 20 terms at the coarsest level -> not correct, camera untouched (DSOTracker.cpp:65-69)
+    trk = DSOTracker(W, H, K)
+    trk.makeCoarseDepthL0(flat, cam, (1.0, 0.0, 0.0), cam[None], np.zeros(0, np.int32), np.zeros((0, 2), np.float32), np.zeros(0), np.zeros(0))
+    r = trk.optimize(cam, (0.0, 0.0), gray=flat)
+    assert not r.isCorrect and np.array_equal(r.camera, cam) and r.iterations == 0
+    # tracer: tracing / activating nothing
+    trc = DSOTracer(W, H, K)
+    trc.addFrame(0, flat, cam, (1.0, 0.0, 0.0)); trc.addFrame(1, flat, cam, (1.0, 0.0, 0.0))
+    assert trc.traceNewCoarse(1).sum() == 0 and trc.optimizeImmaturePoint([]).size == 0
+    ids = trc.makeNewTracesFrom(0, [[40.0, 40.0], [60.0, 50.0]])
+    hist = trc.traceNewCoarse(1)                              # identical pose: zero baseline, the search direction is undefined -> OOB like the reference
+    assert hist.sum() == 2
+    assert set(trc.getPoints()["status"][ids]) <= {1, 2, 3, 4}

@@ -11,8 +11,9 @@ kname = rows[0][1]
 mangled = None
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "libcml_b200", "libcmlba.so")], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+sass = []          # one cubin per translation unit: search all of them
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    sass += subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
 short = re.sub(r"\(.*", "", kname).split("::")[-1].replace("void ", "").split("<")[0]
 # pick the section whose name contains the short kernel name (first template instance = <false>)
 start = [i for i, l in enumerate(sass) if l.startswith("//-") and ".text." in l and short in l][0]
