@@ -358,7 +358,7 @@ __device__ __forceinline__ double hessian_entry(const int e, const TrackParams &
     return e < 64 ? v * P.scale[j] : v;
 }
 
-__device__ void finish(TrkState &S, const TrackParams &P, const bool converged) {
+__device__ void finish(TrkState &S, const bool converged) {
     S.cmd.exit = 1;
     S.fail = converged ? 0 : 1;
 }
@@ -379,7 +379,7 @@ __device__ void propose(TrkState &S, const TrackParams &P) {
     for (int i = 0; i < 8; i++) S.inc[i] = x[i];
     bool finite = true;
     for (int i = 0; i < 8; i++) finite = finite && isfinite(S.inc[i]);
-    if (!finite) { finish(S, P, false); return; }
+    if (!finite) { finish(S, false); return; }
     if (S.lambda < 0.001) {
         const double f = sqrt(sqrt(0.001 / S.lambda));
         for (int i = 0; i < 8; i++) S.inc[i] *= f;
@@ -400,10 +400,10 @@ __device__ void begin_level(TrkState &S, const TrackParams &P) {
 }
 
 __device__ void end_level(TrkState &S, const TrackParams &P) {
-    if (P.has_last && S.oE[S.level] / (double) S.oT[S.level] > 1.5 * P.last_rmse[S.level]) { finish(S, P, false); return; }
+    if (P.has_last && S.oE[S.level] / (double) S.oT[S.level] > 1.5 * P.last_rmse[S.level]) { finish(S, false); return; }
     if (S.rep[S.level] > 1.0 && !S.have_repeated) { S.level++; S.have_repeated = 1; }
     S.level--;
-    if (S.level < 0) { finish(S, P, true); return; }
+    if (S.level < 0) { finish(S, true); return; }
     begin_level(S, P);
 }
 
@@ -415,13 +415,13 @@ __device__ __noinline__ void advance(TrkState &S, const TrackParams &P, const do
     if (S.phase == 1) {
         S.oE[lv] = sum[S_E]; S.oT[lv] = (int) sum[S_NT]; S.oS[lv] = (int) sum[S_NSAT]; S.oR[lv] = (int) sum[S_NROB];
         S.oFlow[0] = fl0; S.oFlow[1] = 0.0; S.oFlow[2] = fl2;
-        if (S.oT[lv] < 20) { finish(S, P, false); return; }
+        if (S.oT[lv] < 20) { finish(S, false); return; }
         if ((double) S.oS[lv] / (double) S.oT[lv] > 0.6 && S.rep[lv] < 50.0) {
             S.rep[lv] *= 2.0;
             request_eval(S, P, S.cur, S.a, S.b, (double) P.cutoff * S.rep[lv]);
             return;
         }
-        if (S.oT[lv] - S.oS[lv] < 10) { finish(S, P, false); return; }
+        if (S.oT[lv] - S.oS[lv] < 10) { finish(S, false); return; }
         S.hsel ^= 1;        // the Hessian of this evaluation (computed by 72 threads after the reduction) becomes the current one
         S.lambda = 0.01; S.it = 0;
         propose(S, P);

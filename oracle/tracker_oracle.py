@@ -151,7 +151,7 @@ def compute_hessian(wp, K, ref_exp, new_exp, p):
     return H * s[:, None] * s[None, :], b * s
 
 
-def optimize(pcs, grads, Ks, ref_to_new, ref_exp, cur_exp, params=None):
+def optimize(pcs, grads, Ks, ref_to_new, ref_exp, cur_exp, params=None, last_rmse=None):
     """DSOTracker::optimize.  pcs[l] [n,4], grads[l] [h,w,3] of the NEW frame, Ks[l] (fx,fy,cx,cy), ref_to_new = (R,t) initial,
     ref_exp / cur_exp = (tau, a, b).  Returns dict with the final ref_to_new, exposure and the Residual fields."""
     p = dict(DEFAULTS); p.update(params or {})
@@ -225,6 +225,8 @@ def optimize(pcs, grads, Ks, ref_to_new, ref_exp, cur_exp, params=None):
                 lam *= 4
             if np.linalg.norm(inc) < 1e-3:
                 break
+        if last_rmse is not None and old["E"][level] / old["numTermsInE"][level] > 1.5 * last_rmse[level]:      # mLastResidual.isCorrect branch, DSOTracker.cpp:190-196
+            return dict(out, **old, R=R, t=t, exposure=cur, levelCutoffRepeat=rep)
         if rep[level] > 1 and not have_repeated:
             level += 1
             have_repeated = True
@@ -279,7 +281,7 @@ def make_coarse_depth(points_uv_idepth_unc, gray_pyr):
     for l in range(L):
         hl, wl = gray_pyr[l].shape
         offs = [wl + 1, -wl - 1, wl - 1, -wl + 1] if l < 2 else [1, -1, wl, -wl]
-        idf = idepth[l].ravel(); wf = wsum[l].ravel(); bak = wf.copy(); idb = idf  # depth is only read where bak > 0 and written where bak <= 0
+        idf = idepth[l].ravel(); wf = wsum[l].ravel(); bak = wf.copy()      # depth is only read where bak > 0 and written where bak <= 0
         size = wl * hl
         src_id = idf.copy()
         for i in range(wl, size - wl):

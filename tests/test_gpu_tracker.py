@@ -125,6 +125,39 @@ def test_oracle_agreement_on_fresh_window():
         np.testing.assert_allclose(r.E, o["E"], rtol=1e-3)
 
 
+def test_last_residual_rmse_gate():
+    """mLastResidual.isCorrect: a level whose rmse exceeds 1.5 x the last frame's aborts the optimisation (DSOTracker.cpp:190-196)."""
+    import tracker_oracle as T
+    win, g = load()
+    trk, ref, new = make_tracker(win)
+    trk.setFrame(win["gray"][new], win["frame_exposure"][new])
+    free = trk.optimize(g["a_init_cam"], g["a_new_affine"])
+    assert free.isCorrect
+    trk.mLastResidual = free                                  # same frame again: rmse equal to the last one -> passes, identical result
+    again = trk.optimize(g["a_init_cam"], g["a_new_affine"])
+    assert again.isCorrect and np.array_equal(again.camera, free.camera)
+
+    class Fake:                                               # a much better last frame: the coarsest level already fails the gate
+        isCorrect = True
+        E = free.E
+        def rmse(self, l):
+            return 0.1 * free.E[l] / free.numTermsInE[l]
+    trk.mLastResidual = Fake()
+    gated = trk.optimize(g["a_init_cam"], g["a_new_affine"])
+    assert not gated.isCorrect and 0 < gated.iterations < free.iterations and np.array_equal(gated.camera, g["a_init_cam"])
+    # the restatement stops at the same place
+    L = 5
+    pcs = [g[f"trk_pc{l}"] for l in range(L)]
+    pyr = T.build_pyramid(win["gray"][new], L)
+    Rr, tr = win["frame_cam"][ref][:9].reshape(3, 3), win["frame_cam"][ref][9:]
+    Rn, tn = g["a_init_cam"][:9].reshape(3, 3), g["a_init_cam"][9:]
+    R0 = Rn @ Rr.T
+    o = T.optimize(pcs, [p[1] for p in pyr], [g["trk_K"][l] for l in range(L)], (R0, tn - R0 @ tr),
+                   (win["frame_exposure"][ref], win["frame_affine"][ref, 0], win["frame_affine"][ref, 1]), (win["frame_exposure"][new], 0.0, 0.0),
+                   last_rmse=[Fake().rmse(l) for l in range(L)])
+    assert not o["isCorrect"] and o["iterations"] == gated.iterations and list(o["numTermsInE"]) == list(gated.numTermsInE)
+
+
 def test_error_paths():
     from libcml_b200 import DSOTracker, CmlbaError
     win, g = load()
