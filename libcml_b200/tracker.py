@@ -212,6 +212,46 @@ class DSOTracker:
         out = [Residual(r) for r in res]
         return out[0] if single else out
 
+    # ---- DSOTracker::trackWithMotionModel (DSOTracker.h:240-360): the candidate loop over motion-model poses
+    def trackWithMotionModel(self, cameras, initial_exposure=(0.0, 0.0), failure_mode=0):
+        """cameras [K][12] = the poses of Map::multiConstantVelocityMotionModel, tried in order on the frame given to setFrame / setFrameDevice.
+        Returns (ok, camera, exposure, residual) like the reference (frame->setCamera / setExposureParameters / residual); the candidates are
+        optimised one after the other because each run is gated by the best residual so far (mLastResidual = trackingResult) and the loop
+        stops at the first candidate that is good enough (achievedRes < 1.5 * mLastCoarseRMSE)."""
+        cams = np.ascontiguousarray(cameras, dtype=np.float64).reshape(-1, 12)
+        init = np.asarray(initial_exposure, dtype=np.float64).reshape(2)
+        have, best, camera, exposure = False, None, None, None
+        achieved = float("inf")
+        self.lastTriedCameras = 0
+        for i, cam in enumerate(cams):
+            self.lastTriedCameras = i + 1
+            self.mLastResidual = best
+            test = self.optimize(cam, init)
+            test_ok = test.isCorrect and test.numTermsInE[0] > 0 and np.isfinite(test.rmse())
+            best_sat = True if best is None else best.tooManySaturated              # Residual() default: tooManySaturated = true
+            if best_sat and not test.tooManySaturated and test_ok:
+                have, camera, exposure, best = True, test.camera, test.exposure, test
+            if test_ok and not (test.rmse() >= achieved):
+                if (True if best is None else best.tooManySaturated) or not test.tooManySaturated:
+                    have, camera, exposure, best = True, test.camera, test.exposure, test
+            if have and test.numTermsInE[0] > 0 and test.rmse() < achieved:
+                achieved = test.rmse()
+            if have and achieved < getattr(self, "mLastCoarseRMSE", float("inf")) * 1.5:
+                break
+            if have and i >= 50:
+                break
+        if not have:
+            if failure_mode != 1:
+                return False, None, None, best
+            self.mLastResidual = best
+            best = self.optimize(cams[0], init)
+            camera, exposure = best.camera, best.exposure
+            return True, camera, exposure, best
+        self.mLastCoarseRMSE = achieved
+        if getattr(self, "mFirstRMSE", -1.0) < 0:
+            self.mFirstRMSE = achieved
+        return True, camera, exposure, best
+
     def benchOptimize(self, repeats=20):
         ms = C.c_float()
         self._ck(self.lib.cmltrk_bench_optimize(self.h, int(repeats), C.byref(ms)))

@@ -158,6 +158,26 @@ def test_last_residual_rmse_gate():
     assert not o["isCorrect"] and o["iterations"] == gated.iterations and list(o["numTermsInE"]) == list(gated.numTermsInE)
 
 
+def test_track_with_motion_model_candidate_loop():
+    """The candidate loop of trackWithMotionModel (DSOTracker.h:240-360): a hopeless first pose is skipped, the loop stops at the first pose that
+    is good enough, and nothing is returned in failure mode 0 when every pose fails."""
+    win, g = load()
+    trk, ref, new = make_tracker(win)
+    trk.setFrame(win["gray"][new], win["frame_exposure"][new])
+    good, far = g["a_init_cam"], g["c_init_cam"]
+    single = trk.optimize(good, (0.0, 0.0))
+    trk.mLastResidual = None
+    ok, cam, ex, res = trk.trackWithMotionModel([far, good, good])
+    assert ok and trk.lastTriedCameras == 2 and np.array_equal(cam, single.camera) and np.array_equal(ex, single.exposure) and res.isCorrect
+    assert trk.mLastCoarseRMSE == single.rmse() and trk.mFirstRMSE == single.rmse()
+    ok, cam, ex, res = trk.trackWithMotionModel([good, far])                 # first pose already good enough: the loop stops after one optimisation
+    assert ok and trk.lastTriedCameras == 1
+    trk2, _, _ = make_tracker(win)
+    trk2.setFrame(win["gray"][new], win["frame_exposure"][new])
+    ok, cam, ex, res = trk2.trackWithMotionModel([far, far])
+    assert not ok and cam is None and trk2.lastTriedCameras == 2
+
+
 def test_error_paths():
     from libcml_b200 import DSOTracker, CmlbaError
     win, g = load()
