@@ -214,6 +214,9 @@ public:
     size_t n_dead = 0;
     ResSnapshot snap;
     IdMap point_index_;
+    // point ids usually arrive in increasing order (Map::createMapPoint counts up): then points_ is sorted by id, look-ups are a binary search and
+    // add_points skips the hash inserts (17 ns per point); the first id that breaks the order switches to the hash index for good (until reset)
+    bool ids_sorted = true;
     std::vector<int64_t> outliers_;
     int key_counter = 0;
     bool dirty = true;            // device window must be rebuilt
@@ -386,11 +389,17 @@ public:
         const size_t first = points_.size();
         const int NF = (int) frames_.size();
         points_.reserve(first + n);
-        point_index_.reserve(first + n);
+        if (ids_sorted) {          // still sorted after this batch?
+            int64_t prev = first ? points_[first - 1].id : INT64_MIN;
+            bool inc = true;
+            for (int i = 0; i < n && inc; i++) { inc = pid[i] > prev; prev = pid[i]; }
+            if (!inc) { ids_sorted = false; reindex(); }
+        }
+        if (!ids_sorted) point_index_.reserve(first + n);
         int64_t last_hid = INT64_MIN; int last_h = -1;
         for (int i = 0; i < n; i++) {
             if (pid[i] == IdMap::EMPTY) { set_error("point id INT64_MIN is reserved"); points_.resize(first); reindex(); return CMLBA_ERR_ARG; }
-            {   // BA:386-388: a point that is already in the window is skipped (a removed one may come back)
+            if (!ids_sorted) {   // BA:386-388: a point that is already in the window is skipped (a removed one may come back); increasing ids are new by construction
                 const int prev = point_index_.find_or_insert(pid[i], (int) points_.size());
                 if (prev >= 0) { if (points_[prev].alive) continue; point_index_.set(pid[i], (int) points_.size()); }
             }
@@ -430,7 +439,14 @@ public:
         snap.r_point.assign(rp, rp + snap.R); snap.r_target.assign(rt, rt + snap.R);
         snap.own_map = true;
     }
+    int find_point(int64_t id) const {
+        if (!ids_sorted) return point_index_.find(id);
+        size_t lo = 0, hi = points_.size();
+        while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (points_[mid].id < id) lo = mid + 1; else hi = mid; }
+        return (lo < points_.size() && points_[lo].id == id && points_[lo].alive) ? (int) lo : -1;
+    }
     void reindex() {
+        if (ids_sorted) return;
         point_index_.clear(); point_index_.reserve(points_.size());
         for (size_t i = 0; i < points_.size(); i++) if (points_[i].alive) point_index_.set(points_[i].id, (int) i);
     }
@@ -455,7 +471,7 @@ public:
     void maybe_compact() { if (n_dead * 4 > points_.size()) compact(); dirty = true; prepared = false; }
 
     int remove_point(int64_t id) {
-        const int idx = point_index_.find(id);
+        const int idx = find_point(id);
         if (idx < 0 || !points_[idx].alive) return CMLBA_OK;   // DSOContext.h:95-97
         drop_point(idx, false);
         maybe_compact();
@@ -598,7 +614,7 @@ public:
             const int *rp = snap.own_map ? snap.r_point.data() : up.host<int>(up_o_rp);
             const uint8_t *rt = snap.own_map ? snap.r_target.data() : up.host<uint8_t>(up_o_rt);
             std::vector<int> pidx(snap.point_id.size()), fslot(snap.frame_id.size());
-            for (size_t i = 0; i < pidx.size(); i++) pidx[i] = point_index_.find(snap.point_id[i]);
+            for (size_t i = 0; i < pidx.size(); i++) pidx[i] = find_point(snap.point_id[i]);
             for (size_t i = 0; i < fslot.size(); i++) fslot[i] = frame_index(snap.frame_id[i]);
             for (int i = 0; i < snap.R; i++) {
                 if (!snap.alive[i]) continue;
@@ -1202,7 +1218,7 @@ public:
     int reset() {
         cudaSetDevice(device);
         for (auto &f : frames_) if (f.d_img) { img_pool.push_back(f.d_img); f.d_img = nullptr; }
-        frames_.clear(); points_.clear(); n_dead = 0; HM.clear(); bM.clear(); snap.valid = false; point_index_.clear(); outliers_.clear();
+        frames_.clear(); points_.clear(); n_dead = 0; HM.clear(); bM.clear(); snap.valid = false; point_index_.clear(); ids_sorted = true; outliers_.clear();
         key_counter = 0; dirty = true; prepared = false;
         return CMLBA_OK;
     }

@@ -157,3 +157,42 @@ def test_gray_upload_builds_identical_derivative_image():
         res.append((ba.getFrames()["world_to_cam"].copy(), ba.getPoints()["idepth"].copy()))
         ba.close()
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_point_id_order_does_not_matter():
+    """Increasing point ids take the sorted fast path of add_points (binary-search look-ups); shuffled, batched and re-added ids take the hash
+    index.  Both must give the same window: identical poses and per-id inverse depths, and removePoint must find its point in either mode."""
+    win = _window(affine=False)
+    N = win["frame_evalpt"].shape[0]; P = win["pt_host"].size
+    H, W = win["gray"].shape[1:]
+
+    def run(ids, order, batches, drop):
+        ba = _ba(iterations=int(win["iterations"][0]))
+        ba.setCalibration(*[float(v) for v in win["calib"]], W, H)
+        for f in range(N):
+            ba.addNewFrameGray(f, win["frame_evalpt"][f], win["frame_affine"][f, 0], win["frame_affine"][f, 1], win["frame_exposure"][f], win["gray"][f], False)
+        for part in np.array_split(order, batches):
+            ba.addPoints(ids[part], win["pt_host"][part], win["pt_xy"][part], win["pt_idepth"][part])
+        for d in drop:
+            ba.removePoint(int(ids[d]))
+        ba.removePoint(10 ** 9)                                   # unknown id: ignored like the reference (DSOContext.h:95-97)
+        ba.addPoints(ids[drop[:1]], win["pt_host"][drop[:1]], win["pt_xy"][drop[:1]], win["pt_idepth"][drop[:1]])     # a removed point comes back (BA:386-388)
+        ba.addPoints(ids[:5], win["pt_host"][:5], win["pt_xy"][:5], win["pt_idepth"][:5])                            # already present: skipped
+        assert ba.run(win["frame_cam"], iterations=int(win["iterations"][0]))
+        fr, pts = ba.getFrames(), ba.getPoints()
+        return fr["world_to_cam"], dict(zip(pts["id"].tolist(), pts["idepth"].tolist()))
+    rng = np.random.default_rng(3)
+    drop = [7, 150, 301]
+    ids_sorted = np.arange(P, dtype=np.int64) * 3 + 100
+    cams_a, pts_a = run(ids_sorted, np.arange(P), 1, drop)                       # one increasing batch: sorted mode until the re-add
+    cams_b, pts_b = run(ids_sorted, rng.permutation(P), 3, drop)                 # shuffled batches: hash mode from the start
+    ids_rand = rng.permutation(P).astype(np.int64) * 7 + 5
+    cams_c, pts_c = run(ids_rand, np.arange(P), 2, drop)
+    assert len(pts_a) == P - len(drop) + 1 and set(pts_a) == set(pts_b)
+    # the device window is sorted by host frame in insertion order, so different insertion orders permute the fp32 reductions: compare within the fp tolerance
+    assert rel(cams_b, cams_a) < 1e-6 and rel(cams_c, cams_a) < 1e-6
+    for k in pts_a:
+        assert abs(pts_b[k] - pts_a[k]) <= 1e-5 * abs(pts_a[k])
+    by_index = {int(ids_rand[i]): i for i in range(P)}
+    for k, v in pts_c.items():
+        assert abs(v - pts_a[int(ids_sorted[by_index[k]])]) <= 1e-5 * abs(v)
