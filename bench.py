@@ -104,6 +104,23 @@ def run_reference_bench(win_path, repeat):
     return json.loads(line[-1])
 
 
+def reference_cpu(mode, window, repeat=3):
+    """The cpu_baseline leg of the widened components (bench.py --component tracker|tracer|prepare|select): runs the unmodified reference
+    (oracle/_ref/cmlba_ref --mode <mode>) on `window` and returns its output arrays, or None when the binary is not there.  The tools under
+    tools/ never touch oracle/ themselves; they receive this function from main()."""
+    if not os.path.exists(REF_BIN):
+        return None
+    from libcml_b200 import cmlw
+    src = f"/tmp/cmlba_bench_{mode}_{os.getpid()}.cmlw"; dst = f"/tmp/cmlba_bench_{mode}_{os.getpid()}_out.cmlw"
+    cmlw.save(src, window)
+    r = subprocess.run([REF_BIN, "--window", src, "--mode", mode, "--out", dst, "--repeat", str(repeat)], capture_output=True, text=True, timeout=1500)
+    out = cmlw.load(dst) if r.returncode == 0 and os.path.exists(dst) else None
+    for f in (src, dst):
+        if os.path.exists(f):
+            os.remove(f)
+    return out
+
+
 def cpu_model():
     try:
         for l in open("/proc/cpuinfo"):
@@ -166,7 +183,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--nccl-only", action="store_true", help="N>1: all-reduce the reduced system with NCCL instead of the peer-memory exchange")
-    args = ap.parse_args()
+    ap.add_argument("--component", default="ba", choices=["ba", "tracker", "tracer", "prepare", "select"],
+                    help="ba = the contract's headline line; the others = the measurement of a widened SURVEY 8f row (tools/<name>_bench.py), one JSON line each")
+    args, rest = ap.parse_known_args()
+    if args.component != "ba":
+        import importlib
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        name = {"tracker": "track_bench", "tracer": "trace_bench", "prepare": "prep_bench", "select": "select_bench"}[args.component]
+        return importlib.import_module(name).main(rest, reference=reference_cpu)
+    if rest:
+        ap.error("unrecognised arguments: " + " ".join(rest))
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

@@ -147,3 +147,39 @@ def make_window(W=640, H=480, N=8, pts_per_kf=2000, iterations=6, affine=False, 
 def make_config(name, seed=1234, **kw):
     W, H, N, ppk, iters, affine = CONFIGS[name]
     return make_window(W, H, N, ppk, iters, affine, seed=seed, **kw)
+
+
+def prepare_scenario(Wi, Hi, Wo, Ho, seed=3):
+    """Sensor image with a gamma response, a radial vignette and radial-tangential distortion, to be rectified to Wo x Ho (input of the image
+    preparation, SURVEY 8f NEXT #3)."""
+    win = make_window(Wi, Hi, 2, 10, 1, False, seed=seed, low_freq=True, with_gradients=False)
+    raw = np.clip(win["gray"][0], 0.0, 254.9).astype(np.float32)
+    i = np.arange(256, dtype=np.float32)
+    lut = (255.0 * (i / 255.0) ** 0.8).astype(np.float32)
+    yy, xx = np.mgrid[0:Hi, 0:Wi]
+    r2 = ((xx - Wi / 2) ** 2 + (yy - Hi / 2) ** 2) / ((Wi / 2) ** 2 + (Hi / 2) ** 2)
+    vig = (1.0 / (1.0 - 0.35 * r2)).astype(np.float32)
+    f = 0.9 * Wi
+    return dict(size_in=np.array([Wi, Hi], np.int32), size_out=np.array([Wo, Ho], np.int32), calib_in=np.array([f, f, Wi / 2 - 0.5, Hi / 2 - 0.5]),
+                calib_out=np.array([0.8 * f * Wo / Wi, 0.8 * f * Wo / Wi, Wo / 2 - 0.5, Ho / 2 - 0.5]), radtan=np.array([-0.28, 0.07, 0.0005, -0.0003]), raw=raw, lut=lut,
+                inv_vignette=vig)
+
+
+def radtan_undistort_map(scn):
+    """Source position of every rectified pixel for the scenario's radial-tangential camera (Brown-Conrady k1 k2 p1 p2), NaN outside the sensor:
+    the calibration-time input of cmlimg_set_undistort_map when no reference binary is around to provide InternalCalibration's own map."""
+    Wi, Hi = scn["size_in"]; Wo, Ho = scn["size_out"]
+    fxo, fyo, cxo, cyo = scn["calib_out"]; fxi, fyi, cxi, cyi = scn["calib_in"]
+    k1, k2, p1, p2 = scn["radtan"]
+    yy, xx = np.mgrid[0:Ho, 0:Wo].astype(np.float32)
+    x = (xx - np.float32(cxo)) / np.float32(fxo); y = (yy - np.float32(cyo)) / np.float32(fyo)
+    x = x.astype(np.float64); y = y.astype(np.float64)
+    r2 = x * x + y * y
+    rad = k1 * r2 + k2 * r2 * r2
+    xd = x + x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x)
+    yd = y + y * rad + 2.0 * p2 * x * y + p1 * (r2 + 2.0 * y * y)
+    u = (xd * fxi + cxi).astype(np.float32); v = (yd * fyi + cyi).astype(np.float32)
+    bad = (u < 0) | (v < 0) | (u >= Wi - 1) | (v >= Hi - 1)
+    m = np.stack([u, v], axis=-1)
+    m[bad] = np.nan
+    return m

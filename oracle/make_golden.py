@@ -182,26 +182,11 @@ def tracer():
     print("trace window", os.path.getsize(os.path.join(OUT, "trace_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "trace_golden.cmlw")) // 1024, "KB")
 
 
-def prepare_scenario(Wi, Hi, Wo, Ho, seed=3):
-    """Sensor image with a gamma response, a radial vignette and radial-tangential distortion, rectified to Wo x Ho."""
-    win = synth.make_window(Wi, Hi, 2, 10, 1, False, seed=seed, low_freq=True)
-    raw = np.clip(win["gray"][0], 0.0, 254.9).astype(np.float32)
-    i = np.arange(256, dtype=np.float32)
-    lut = (255.0 * (i / 255.0) ** 0.8).astype(np.float32)
-    yy, xx = np.mgrid[0:Hi, 0:Wi]
-    r2 = ((xx - Wi / 2) ** 2 + (yy - Hi / 2) ** 2) / ((Wi / 2) ** 2 + (Hi / 2) ** 2)
-    vig = (1.0 / (1.0 - 0.35 * r2)).astype(np.float32)
-    f = 0.9 * Wi
-    return dict(size_in=np.array([Wi, Hi], np.int32), size_out=np.array([Wo, Ho], np.int32), calib_in=np.array([f, f, Wi / 2 - 0.5, Hi / 2 - 0.5]),
-                calib_out=np.array([0.8 * f * Wo / Wi, 0.8 * f * Wo / Wi, Wo / 2 - 0.5, Ho / 2 - 0.5]), radtan=np.array([-0.28, 0.07, 0.0005, -0.0003]), raw=raw, lut=lut,
-                inv_vignette=vig)
-
-
 def prepare():
     """CaptureImageGenerator::generate of the reference (SURVEY 8f NEXT #3) with LUT, inverse vignette and a radtan pre-undistorter: 200x150 -> 160x120."""
     tmp = "/tmp/cmlba_golden"
     os.makedirs(tmp, exist_ok=True)
-    w = prepare_scenario(200, 150, 160, 120)
+    w = synth.prepare_scenario(200, 150, 160, 120)
     cmlw.save(os.path.join(tmp, "prepare.cmlw"), w)
     run_ref(os.path.join(tmp, "prepare.cmlw"), "prepare", os.path.join(tmp, "prepare_out.cmlw"))
     g = cmlw.load(os.path.join(tmp, "prepare_out.cmlw"))

@@ -1,6 +1,6 @@
 """CPU restatement of DSOTracer (immature-point tracing and activation) -- TEST INFRASTRUCTURE ONLY (NEXT #2).
 
-Only tests/ and tools/ benchmark legs may import this module; the product (libcml_b200/) never does.  Parity is pinned:
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may import or execute this; the product (libcml_b200/) and tools/ never do.  Parity is pinned:
 tests/test_tracer_oracle.py checks it against tests/golden/trace_golden.cmlw, produced by the unmodified reference
 (oracle/ref_driver.cpp --mode trace, oracle/make_golden.py tracer).
 

@@ -1,6 +1,6 @@
 """CPU restatement of DSOTracker's coarse-to-fine direct image alignment -- TEST INFRASTRUCTURE ONLY (NEXT #1).
 
-Only tests/ and tools/ benchmark legs may import this module; the product (libcml_b200/) never does.  Parity is pinned:
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may import or execute this; the product (libcml_b200/) and tools/ never do.  Parity is pinned:
 tests/test_tracker_oracle.py checks it against tests/golden/track_golden.cmlw, produced by the unmodified reference
 (oracle/ref_driver.cpp --mode track, oracle/make_golden.py tracker).
 

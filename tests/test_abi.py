@@ -135,6 +135,15 @@ def test_null_handle_is_an_error(lib):
     assert lib.cmlba_run(None, None, 1, 0, None) == -1
 
 
+def test_tools_do_not_touch_oracle():
+    """tools/ are measurement aids of the product: the reference CPU timings they report come through bench.py's cpu_baseline callback
+    (`python bench.py --component ...`), the one place outside tests/ and smoke() that may execute oracle/."""
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            txt = open(os.path.join(ROOT, "tools", f)).read()
+            assert "oracle" not in txt, f
+
+
 def test_product_does_not_import_oracle():
     """The product path must never route through oracle/ (only tests, smoke() and bench.py's CPU legs may)."""
     pkg = os.path.join(ROOT, "libcml_b200")

@@ -1,10 +1,9 @@
 """Measures the coarse tracker (SURVEY.md 8f NEXT #1) on a synthetic 640x480 window: device time of one optimize launch, end-to-end time of
-cmltrk_track (host gray image in, Residual out), K-candidate batches, and -- when oracle/_ref/cmlba_ref exists -- the unmodified reference's
-DSOTracker::optimize on the host CPU for the same inputs.  Prints one JSON line.  Not part of the product path."""
+cmltrk_track (host gray image in, Residual out), K-candidate batches.  Run as `python bench.py --component tracker` it also receives bench.py's
+cpu_baseline callback and times the unmodified reference's DSOTracker::optimize on the host CPU for the same inputs.  Prints one JSON line."""
 import argparse
 import json
 import os
-import subprocess
 import sys
 import time
 
@@ -12,7 +11,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from libcml_b200 import DSOTracker, cmlw, synth  # noqa: E402
+from libcml_b200 import DSOTracker, synth  # noqa: E402
 
 
 def scenario(W, H, N, ppk, seed):
@@ -28,13 +27,13 @@ def scenario(W, H, N, ppk, seed):
     return win
 
 
-def main():
+def main(argv=None, reference=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--width", type=int, default=640); ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--frames", type=int, default=7); ap.add_argument("--points", type=int, default=2000)
     ap.add_argument("--repeats", type=int, default=50); ap.add_argument("--cluster", type=int, default=16)
     ap.add_argument("--candidates", type=int, default=8); ap.add_argument("--threads", type=int, default=384)
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     win = scenario(a.width, a.height, a.frames, a.points, 31)
     N = a.frames; ref, new = N - 2, N - 1
     trk = DSOTracker(a.width, a.height, win["calib"], cluster_ctas=a.cluster, cta_threads=a.threads)
@@ -75,18 +74,11 @@ def main():
            "cluster_ctas": a.cluster, "cta_threads": a.threads, "optimize_device_ms": round(dev_ms, 4), "us_per_gn_step": round(dev_ms * 1e3 / max(r.iterations + 5, 1), 3),
            "evals": int(cyc[0]), "kcycles_advance_eval_reduce": [round(float(c) / 1e3, 1) for c in cyc[1:]], "track_e2e_ms": round(e2e_ms, 4), "track_e2e_from_frame_buffer_ms": round(e2e_pinned_ms, 4), "optimize_gpu_ms_in_call": round(float(rz.gpu_ms), 4), "h2d_bytes_per_track": int(gray.nbytes), "make_coarse_depth_e2e_ms": round(coarse_ms, 3),
            f"optimize_{K}_candidates_device_ms": round(devK_ms, 4)}
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "cmlba_ref")
-    if os.path.exists(ref_bin):
-        p = "/tmp/track_bench.cmlw"
-        cmlw.save(p, {k: v for k, v in win.items() if k != "grad"})
-        rr = subprocess.run([ref_bin, "--window", p, "--mode", "track", "--out", "/tmp/track_bench_out.cmlw", "--repeat", "5"], capture_output=True, text=True)
-        if rr.returncode == 0:
-            g = cmlw.load("/tmp/track_bench_out.cmlw")
-            out["reference_cpu_optimize_ms"] = round(float(g["trk_seconds"][0]) * 1e3, 4)
-            out["cam_diff_vs_reference"] = float(np.abs(r.camera - g["trk_cam"]).max())
-            out["speedup_e2e_vs_reference_cpu"] = round(out["reference_cpu_optimize_ms"] / e2e_ms, 2)
-        else:
-            out["reference_cpu"] = "failed: " + rr.stderr[-200:]
+    g = reference("track", {k: v for k, v in win.items() if k != "grad"}, 5) if reference else None
+    if g is not None:
+        out["reference_cpu_optimize_ms"] = round(float(g["trk_seconds"][0]) * 1e3, 4)
+        out["cam_diff_vs_reference"] = float(np.abs(r.camera - g["trk_cam"]).max())
+        out["speedup_e2e_vs_reference_cpu"] = round(out["reference_cpu_optimize_ms"] / e2e_ms, 2)
     print(json.dumps(out))
 
 
