@@ -7,10 +7,11 @@
  *   cmltrc_make_new_traces       DSOTracer::makeNewTracesFrom(frame, group)                  DSOTracer.cpp:538-583
  *   cmltrc_trace_new_coarse      DSOTracer::traceNewCoarse(frameToTrace, frameGroup) -> trace  DSOTracer.cpp:17-60, 585-832
  *   cmltrc_optimize_immature     DSOTracer::optimizeImmaturePoint(point, minObs, frameGroup) DSOTracer.cpp:280-411 (+ linearizeResidual :413-494)
+ *   cmltrc_activate_points       DSOTracer::activatePoints(frameGroup, pointGroup)            DSOTracer.cpp:62-278 (DistanceMap: utils/DistanceMap.h)
  *   cmltrc_get_points            DSOTracerPointPrivate fields (DSOTracer.h:14-32)
  *
  * Points, their state and the frames' images live on the device between calls; one warp per point.  There is NO CPU fallback.
- * Out of scope (host control flow above these calls): PixelSelector candidate selection, the DistanceMap gating of activatePoints.
+ * The pixel selection of makeNewTraces is include/cmlsel.h; the Map bookkeeping around activatePoints (setMapPoint, removeMapPoint) stays with the caller.
  */
 #ifndef CMLTRC_H
 #define CMLTRC_H
@@ -90,6 +91,27 @@ int cmltrc_trace_new_coarse(cmltrc_handle h, int64_t frame_id, int32_t *status_h
 int cmltrc_optimize_immature(cmltrc_handle h, int count, const int64_t *ids, int min_obs, cmltrc_activation *results, float *gpu_ms);
 
 int cmltrc_get_points(cmltrc_handle h, int64_t first_id, int count, cmltrc_point *out);
+
+/* Counters of one activatePoints call (the statistics the reference publishes, DSOTracer.cpp:106-115, 196-203, 226-262). */
+typedef struct {
+    double current_minimum_distance;   /* mCurrentMinimumDistance after the adaptation */
+    int32_t urgently_need_new_points;  /* mUrgentlyNeedNewPoints */
+    int32_t num_deleted_outlier, num_deleted_oob, num_skipped_status, num_skipped_pixel_interval, num_skipped_quality, num_skipped_depth;
+    int32_t num_to_optimize, num_mapped, num_non_mapped, num_dropped;
+} cmltrc_activate_stats;
+
+/* DSOTracer::activatePoints(frameGroup, pointGroup) DSOTracer.cpp:62-278.  last_frame_id = Map::getLastGroupFrame(frameGroup);
+ * active_xy [num_active][2] = the active points of pointGroup projected into that frame (distorted pixels; they seed the distance map and their
+ * number drives the minimum-distance adaptation against desired_point_density = "desiredPointDensity"); immature_ids = the immature points in the
+ * order the caller's set iterates them (the greedy distance-map gating depends on it), immature_types = my_type of each (NULL: 1).
+ * Outputs: activated_ids / activated (rc == 1 entries: inverse depth, frames that receive the apparition) up to `capacity`, removed_ids (points the
+ * reference hands to removeMapPoint) up to `capacity`.  Activated and removed points leave the handle's immature set.
+ * min_trace_quality = "Min Trace Quality" (3). */
+int cmltrc_activate_points(cmltrc_handle h, int64_t last_frame_id, int num_active, const double *active_xy, int desired_point_density, float min_trace_quality,
+                           int num_immature, const int64_t *immature_ids, const float *immature_types, int capacity, int64_t *activated_ids,
+                           cmltrc_activation *activated, int32_t *num_activated, int64_t *removed_ids, int32_t *num_removed, cmltrc_activate_stats *stats);
+/* mCurrentMinimumDistance (starts at 2). */
+int cmltrc_set_minimum_distance(cmltrc_handle h, double v);
 
 #ifdef __cplusplus
 }

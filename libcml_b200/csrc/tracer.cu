@@ -262,6 +262,110 @@ struct Tracer {
         return CMLTRC_OK;
     }
 
+    // ---- activatePoints: host control flow of DSOTracer.cpp:62-278 around the activation kernel
+    double min_distance = 2.0;         // mCurrentMinimumDistance
+
+    // utils/DistanceMap.h is an 8-neighbour BFS capped at maxDist = the Chebyshev distance to the nearest added integer pixel; a uniform grid of
+    // cells >= maxDist answers it from the 3x3 neighbourhood
+    struct ChebGrid {
+        int W, H, maxd, cell, gw, gh;
+        std::vector<std::vector<int>> cells;      // packed (y << 16 | x)
+        ChebGrid(int w, int h, int md) : W(w), H(h), maxd(md), cell(std::max(md, 8)), gw((w + cell - 1) / cell), gh((h + cell - 1) / cell), cells((size_t) gw * gh) {}
+        void add(double fx, double fy) {
+            const int x = (int) fx, y = (int) fy;                       // _add(point.x(), point.y()): truncation, out-of-image points are ignored by queue()
+            if (x < 0 || y < 0 || x >= W || y >= H) return;
+            cells[(size_t) (y / cell) * gw + x / cell].push_back((y << 16) | x);
+        }
+        int get(double fx, double fy) const {
+            const int x = (int) fx, y = (int) fy, cx = x / cell, cy = y / cell;
+            int best = maxd;
+            for (int gy = std::max(cy - 1, 0); gy <= std::min(cy + 1, gh - 1); gy++)
+                for (int gx = std::max(cx - 1, 0); gx <= std::min(cx + 1, gw - 1); gx++)
+                    for (int q : cells[(size_t) gy * gw + gx]) best = std::min(best, std::max(std::abs((q & 0xffff) - x), std::abs((q >> 16) - y)));
+            return best;
+        }
+    };
+
+    int activate_points(int64_t last_id, int nact, const double *axy, int desired, float min_quality, int nim, const int64_t *ids, const float *types, int capacity,
+                        int64_t *act_ids, cmltrc_activation *act, int32_t *n_act, int64_t *rem_ids, int32_t *n_rem, cmltrc_activate_stats *st) {
+        const int last = find(last_id);
+        if (last < 0 || nact < 0 || nim < 0 || (nact > 0 && !axy) || (nim > 0 && !ids) || !n_act || !n_rem || capacity < 0 || (capacity > 0 && (!act_ids || !act || !rem_ids))) {
+            error = "unknown frame id or bad arguments"; return CMLTRC_ERR_ARG;
+        }
+        for (int i = 0; i < nim; i++) if (ids[i] < 0 || ids[i] >= num || host_slot[ids[i]] < 0) { error = "unknown or removed point id"; return CMLTRC_ERR_ARG; }
+        cmltrc_activate_stats s{};
+        // minimum-distance adaptation (DSOTracer.cpp:62-85)
+        double md = min_distance;
+        const int n = nact;
+        if (n < desired * 0.66) md -= 0.8;
+        if (n < desired * 0.8) md -= 0.5; else if (n < desired * 0.9) md -= 0.2; else if (n < desired) md -= 0.1;
+        if (n > desired * 1.5) md += 0.8;
+        if (n > desired * 1.3) md += 0.5;
+        if (n > desired * 1.15) md += 0.2;
+        if (n > desired) md += 0.1;
+        s.urgently_need_new_points = md < 1 ? 1 : 0;
+        if (md < 0) md = 0;
+        if (md > 4) md = 4;
+        min_distance = md; s.current_minimum_distance = md;
+        const float maxType = 10;
+        ChebGrid dmap(P.W, P.H, (int) (md * maxType));
+        for (int i = 0; i < nact; i++) dmap.add(axy[2 * i], axy[2 * i + 1]);
+        // point states (one read-back), then the sequential gating in the caller's order
+        std::vector<cmltrc_point> pt((size_t) num);
+        if (num) { int rc = get_points(0, (int) num, pt.data()); if (rc) return rc; }
+        std::vector<float2> pxy((size_t) num);
+        if (num && cudaMemcpy(pxy.data(), pts.xy, (size_t) num * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) { error = "device read failed"; return CMLTRC_ERR_CUDA; }
+        std::vector<int64_t> to_opt, removed;
+        for (int i = 0; i < nim; i++) {
+            const int64_t id = ids[i];
+            const cmltrc_point &p = pt[id];
+            if (p.host_frame_slot == last) continue;
+            if (!std::isfinite(p.idepth_max) || p.status == IPS_OUTLIER) { removed.push_back(id); s.num_deleted_outlier++; continue; }
+            const bool okStatus = p.status == IPS_GOOD || p.status == IPS_SKIPPED || p.status == IPS_BADCONDITION || p.status == IPS_OOB;
+            const bool okInterval = p.last_trace_pixel_interval < 8, okQuality = p.quality > (double) min_quality, okDepth = (p.idepth_max + p.idepth_min) > 0;
+            if (!okStatus) s.num_skipped_status++;
+            if (!okInterval) s.num_skipped_pixel_interval++;
+            if (!okQuality) s.num_skipped_quality++;
+            if (!okDepth) s.num_skipped_depth++;
+            if (!(okStatus && okInterval && okQuality && okDepth)) {
+                if (p.status == IPS_OOB) { removed.push_back(id); s.num_deleted_oob++; }
+                continue;
+            }
+            // getWorldCoordinateIf(idepth).project(lastFrame): host pixel -> last frame
+            const double idepth = (p.idepth_min + p.idepth_max) / 2.0;
+            const Slot &hs = slots[p.host_frame_slot];
+            const Pose rel = cmlba::pose_mul(slots[last].cam, cmlba::pose_inv(hs.cam));
+            const float2 xy = pxy[id];
+            const double ray[3] = {((double) xy.x - P.cx) / P.fx / idepth, ((double) xy.y - P.cy) / P.fy / idepth, 1.0 / idepth};
+            double X[3];
+            cmlba::mat3_vec(rel.R, ray, X);
+            for (int k = 0; k < 3; k++) X[k] += rel.t[k];
+            const double px = P.fx * (X[0] / X[2]) + P.cx, py = P.fy * (X[1] / X[2]) + P.cy;
+            if (px >= 0 && py >= 0 && px < P.W && py < P.H) {
+                const double dist = dmap.get(px, py) + (px - std::floor(px));
+                if (dist >= md * (double) (types ? types[i] : 1.f)) { dmap.add(px, py); to_opt.push_back(id); }
+            } else removed.push_back(id);
+        }
+        s.num_to_optimize = (int) to_opt.size();
+        std::vector<cmltrc_activation> res(to_opt.size());
+        if (!to_opt.empty()) { int rc = activate((int) to_opt.size(), to_opt.data(), 1, res.data(), nullptr); if (rc) return rc; }
+        int na = 0;
+        std::vector<int64_t> gone;
+        for (size_t k = 0; k < to_opt.size(); k++) {
+            if (res[k].rc == 1) {
+                if (na < capacity) { act_ids[na] = to_opt[k]; act[na] = res[k]; }
+                na++; s.num_mapped++; gone.push_back(to_opt[k]);
+            } else if (res[k].rc == -1 || pt[to_opt[k]].status == IPS_OOB) { removed.push_back(to_opt[k]); s.num_dropped++; }
+            else s.num_non_mapped++;
+        }
+        for (size_t k = 0; k < removed.size() && (int) k < capacity; k++) rem_ids[k] = removed[k];
+        *n_act = na; *n_rem = (int32_t) removed.size();
+        gone.insert(gone.end(), removed.begin(), removed.end());
+        if (!gone.empty()) { int rc = remove_points((int) gone.size(), gone.data()); if (rc) return rc; }
+        if (st) *st = s;
+        return CMLTRC_OK;
+    }
+
     int get_points(int64_t first, int count, cmltrc_point *out) {
         if (first < 0 || count < 0 || first + count > num || (count > 0 && !out)) { error = "bad range"; return CMLTRC_ERR_ARG; }
         if (count == 0) return CMLTRC_OK;
@@ -330,5 +434,13 @@ int cmltrc_optimize_immature(cmltrc_handle h, int count, const int64_t *ids, int
     return h ? TH(h)->activate(count, ids, min_obs, results, gpu_ms) : CMLTRC_ERR_ARG;
 }
 int cmltrc_get_points(cmltrc_handle h, int64_t first_id, int count, cmltrc_point *out) { return h ? TH(h)->get_points(first_id, count, out) : CMLTRC_ERR_ARG; }
+int cmltrc_activate_points(cmltrc_handle h, int64_t last_frame_id, int num_active, const double *active_xy, int desired_point_density, float min_trace_quality, int num_immature,
+                           const int64_t *immature_ids, const float *immature_types, int capacity, int64_t *activated_ids, cmltrc_activation *activated, int32_t *num_activated,
+                           int64_t *removed_ids, int32_t *num_removed, cmltrc_activate_stats *stats) {
+    return h ? TH(h)->activate_points(last_frame_id, num_active, active_xy, desired_point_density, min_trace_quality, num_immature, immature_ids, immature_types, capacity,
+                                      activated_ids, activated, num_activated, removed_ids, num_removed, stats)
+             : CMLTRC_ERR_ARG;
+}
+int cmltrc_set_minimum_distance(cmltrc_handle h, double v) { if (!h) return CMLTRC_ERR_ARG; TH(h)->min_distance = v; return CMLTRC_OK; }
 
 }  // extern "C"

@@ -25,8 +25,14 @@ POINT = np.dtype([("status", "<i4"), ("host_frame_slot", "<i4"), ("idepth_min", 
                   ("last_trace_pixel_interval", "<f8"), ("quality", "<f8"), ("grad_h", "<f8", 4), ("energy_th", "<f8")])
 ACTIVATION = np.dtype([("rc", "<i4"), ("idepth", "<f4"), ("in_mask", "<u4")])
 
+
+class ActivateStats(C.Structure):
+    _fields_ = [("current_minimum_distance", C.c_double), ("urgently_need_new_points", C.c_int32), ("num_deleted_outlier", C.c_int32), ("num_deleted_oob", C.c_int32),
+                ("num_skipped_status", C.c_int32), ("num_skipped_pixel_interval", C.c_int32), ("num_skipped_quality", C.c_int32), ("num_skipped_depth", C.c_int32),
+                ("num_to_optimize", C.c_int32), ("num_mapped", C.c_int32), ("num_non_mapped", C.c_int32), ("num_dropped", C.c_int32)]
+
 TRACER_SYMBOLS = ["cmltrc_default_config", "cmltrc_create", "cmltrc_destroy", "cmltrc_last_error", "cmltrc_add_frame", "cmltrc_add_frame_device", "cmltrc_set_frame_pose", "cmltrc_remove_frame",
-                  "cmltrc_make_new_traces", "cmltrc_remove_points", "cmltrc_num_points", "cmltrc_trace_new_coarse", "cmltrc_optimize_immature", "cmltrc_get_points"]
+                  "cmltrc_make_new_traces", "cmltrc_remove_points", "cmltrc_num_points", "cmltrc_trace_new_coarse", "cmltrc_optimize_immature", "cmltrc_get_points", "cmltrc_activate_points", "cmltrc_set_minimum_distance"]
 
 _bound = False
 
@@ -52,6 +58,9 @@ def _bind(lib):
     lib.cmltrc_trace_new_coarse.argtypes = [vp, i64, C.POINTER(C.c_int32), fp]
     lib.cmltrc_optimize_immature.argtypes = [vp, C.c_int, C.POINTER(i64), C.c_int, vp, fp]
     lib.cmltrc_get_points.argtypes = [vp, i64, C.c_int, vp]
+    lib.cmltrc_activate_points.argtypes = [vp, i64, C.c_int, dp, C.c_int, C.c_float, C.c_int, C.POINTER(i64), fp, C.c_int, C.POINTER(i64), vp, C.POINTER(C.c_int32),
+                                           C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(ActivateStats)]
+    lib.cmltrc_set_minimum_distance.argtypes = [vp, C.c_double]
     _bound = True
     return lib
 
@@ -143,6 +152,25 @@ class DSOTracer:
         self._ck(self.lib.cmltrc_optimize_immature(self.h, a.size, a.ctypes.data_as(C.POINTER(C.c_int64)), int(minObs), out.ctypes.data_as(C.c_void_p), C.byref(ms)))
         self.last_gpu_ms = ms.value
         return out
+
+    # ---- DSOTracer::activatePoints(frameGroup, pointGroup)
+    def activatePoints(self, last_frame_id, active_xy, immature_ids, desiredPointDensity=800, types=None, minTraceQuality=3.0):
+        """active_xy [A][2]: the active points projected into the last frame; immature_ids: the immature points in the caller's iteration order.
+        Returns (activated ids, activation records (rc == 1), removed ids, stats); activated and removed points leave the immature set."""
+        axy = np.ascontiguousarray(active_xy, dtype=np.float64).reshape(-1, 2)
+        ids = np.ascontiguousarray(immature_ids, dtype=np.int64)
+        ty = None if types is None else np.ascontiguousarray(types, dtype=np.float32)
+        cap = max(ids.size, 1)
+        a_ids = np.zeros(cap, np.int64); act = np.zeros(cap, ACTIVATION); r_ids = np.zeros(cap, np.int64)
+        na, nr, st = C.c_int32(), C.c_int32(), ActivateStats()
+        self._ck(self.lib.cmltrc_activate_points(self.h, int(last_frame_id), axy.shape[0], _dp(axy), int(desiredPointDensity), float(minTraceQuality), ids.size,
+                                                 ids.ctypes.data_as(C.POINTER(C.c_int64)), None if ty is None else ty.ctypes.data_as(C.POINTER(C.c_float)), cap,
+                                                 a_ids.ctypes.data_as(C.POINTER(C.c_int64)), act.ctypes.data_as(C.c_void_p), C.byref(na),
+                                                 r_ids.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nr), C.byref(st)))
+        return a_ids[:na.value].copy(), act[:na.value].copy(), r_ids[:nr.value].copy(), st
+
+    def setMinimumDistance(self, v):
+        self._ck(self.lib.cmltrc_set_minimum_distance(self.h, float(v)))
 
     def getPoints(self, first=0, count=None):
         n = self.numPoints() - first if count is None else count

@@ -182,6 +182,30 @@ def tracer():
     print("trace window", os.path.getsize(os.path.join(OUT, "trace_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "trace_golden.cmlw")) // 1024, "KB")
 
 
+def activate():
+    """DSOTracer::activatePoints of the reference (DSOTracer.cpp:62-278) on the trace window (tests/golden/trace_window.cmlw) plus 120 active points
+    (distance map) with desiredPointDensity 300: minimum-distance adaptation, distance-map gating, activation, removal."""
+    tmp = "/tmp/cmlba_golden"
+    os.makedirs(tmp, exist_ok=True)
+    base = cmlw.load(os.path.join(OUT, "trace_window.cmlw"))
+    W, H = base["size"]; N = base["frame_cam"].shape[0]
+    win = synth.make_window(int(W), int(H), N, 20, 4, True, seed=11, low_freq=True, with_gradients=False, with_depth=True)
+    assert np.array_equal(win["gray"], base["gray"]), "the trace window must be reproducible"
+    rng = np.random.default_rng(2)
+    A = 120
+    ah = rng.integers(0, N - 1, A).astype(np.int32); ax = rng.integers(8, W - 8, A); ay = rng.integers(8, H - 8, A)
+    extra = dict(act_host=ah, act_xy=np.stack([ax, ay], 1).astype(np.float32), act_idepth=1.0 / win["truth_depth"][ah, ay, ax], desired_density=np.array([300], np.int32))
+    full = dict(base); full.update(extra)
+    cmlw.save(os.path.join(tmp, "activate.cmlw"), full)
+    run_ref(os.path.join(tmp, "activate.cmlw"), "trace", os.path.join(tmp, "activate_out.cmlw"))
+    g = cmlw.load(os.path.join(tmp, "activate_out.cmlw"))
+    assert 0 < g["act_mapped"].sum() < g["act_order"].size and 0 < g["act_still_immature"].sum()
+    gold = dict(extra)
+    gold.update({k: g[k] for k in ("act_order", "act_mapped", "act_still_immature", "act_idepth_out", "act_min_distance", "act_urgent")})
+    cmlw.save(os.path.join(OUT, "activate_golden.cmlw"), gold)       # inputs (act_*, desired_density) and outputs; the window is trace_window.cmlw
+    print("activate golden", os.path.getsize(os.path.join(OUT, "activate_golden.cmlw")) // 1024, "KB  mapped", int(g["act_mapped"].sum()), "kept", int(g["act_still_immature"].sum()))
+
+
 def prepare():
     """CaptureImageGenerator::generate of the reference (SURVEY 8f NEXT #3) with LUT, inverse vignette and a radtan pre-undistorter: 200x150 -> 160x120."""
     tmp = "/tmp/cmlba_golden"
@@ -220,6 +244,8 @@ if __name__ == "__main__":
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     if len(sys.argv) > 1 and sys.argv[1] == "select":
         select(); sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "activate":
+        activate(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "prepare":
         prepare(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tracer":

@@ -695,6 +695,45 @@ static int runTrace(const cmlw::File &in, cmlw::File &out, int repeat) {
         out.put1<int32_t>("trc_status_f" + std::to_string(f), st);
         out.put<double>("trc_state_f" + std::to_string(f), v, {(uint64_t) P, 6});
     }
+    if (in.has("act_host")) {
+        // activatePoints (DSOTracer.cpp:62-278): `act_*` = the active points of the window (their projections feed the distance map); the iteration order of
+        // the immature set (a hash set) is dumped so that the same order can be replayed
+        const int pg = map.createMapPointGroup("active");
+        const int32_t *ah = in.get("act_host").as<int32_t>();
+        const float *axy = in.get("act_xy").as<float>();
+        const double *aid = in.get("act_idepth").as<double>();
+        const int A = (int) in.get("act_host").dims[0];
+        if (in.has("desired_density")) tracer.mSettingsDesiredPointDensity.set(in.get("desired_density").as<int32_t>()[0]);
+        for (int h = 0; h < N; h++) {
+            List<Corner> corners; std::vector<int> mine;
+            for (int p = 0; p < A; p++) if (ah[p] == h) { mine.push_back(p); corners.emplace_back(Corner(DistortedVector2d(axy[2 * p], axy[2 * p + 1]))); }
+            if (mine.empty()) continue;
+            const int gid = frames[h]->addFeaturePoints(corners);
+            for (size_t k = 0; k < mine.size(); k++) {
+                PPoint mp = map.createMapPoint(frames[h], FeatureIndex(gid, (short) k), DIRECTTYPE);
+                mp->setReferenceInverseDepth(aid[mine[k]]);
+                mp->setGroup(pg, true);
+            }
+        }
+        std::unordered_map<MapPoint *, int> index;
+        for (int p = 0; p < P; p++) if (pts[p].isNotNull()) index[pts[p].p()] = p;
+        std::vector<int32_t> order, status_before(P, -1);
+        for (auto mp : map.getGroupMapPoints(tracer.IMMATUREPOINT)) order.push_back(index.at(mp.p()));
+        for (int p = 0; p < P; p++) if (pts[p].isNotNull()) status_before[p] = (int32_t) tracer.getPrivateData(pts[p])->lastTraceStatus;
+        const double a0 = now_s();
+        PointSet mapped = tracer.activatePoints(fg, pg);
+        const double tAct = now_s() - a0;
+        std::vector<int32_t> isMapped(P, 0), stillImmature(P, 0);
+        std::vector<double> idOut(P, 0.0);
+        for (auto mp : mapped) { const int p = index.at(mp.p()); isMapped[p] = 1; idOut[p] = mp->getReferenceInverseDepth(); }
+        for (auto mp : map.getGroupMapPoints(tracer.IMMATUREPOINT)) stillImmature[index.at(mp.p())] = 1;
+        out.put1<int32_t>("act_order", order); out.put1<int32_t>("act_mapped", isMapped); out.put1<int32_t>("act_still_immature", stillImmature);
+        out.put1<double>("act_idepth_out", idOut);
+        out.scalar<double>("act_min_distance", tracer.mCurrentMinimumDistance); out.scalar<int32_t>("act_urgent", tracer.mUrgentlyNeedNewPoints ? 1 : 0);
+        out.scalar<double>("act_seconds", tAct);
+        printf("{\"traces\": %ld, \"trace_seconds\": %.6f, \"activate_seconds\": %.6f, \"mapped\": %zu}\n", nTraced, tTrace, tAct, mapped.size());
+        return 0;
+    }
     // activation: optimizeImmaturePoint on every point with a finite interval
     const int minObs = in.has("min_obs") ? in.get("min_obs").as<int32_t>()[0] : 1;
     std::vector<int32_t> rc(P, -2);

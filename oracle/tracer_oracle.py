@@ -265,3 +265,74 @@ def optimize_immature_point(pt, K, cams, exposures, grads, window, min_obs=1, p=
     if good < min_obs or not math.isfinite(pt.energyTH):
         return -1, 0.0, [r["state"] for r in res]
     return 1, float(cur), [r["state"] for r in res]
+
+
+def adapt_minimum_distance(cur, num_active, desired):
+    """Head of activatePoints (DSOTracer.cpp:62-85): returns (mCurrentMinimumDistance, mUrgentlyNeedNewPoints)."""
+    n = num_active
+    if n < desired * 0.66: cur -= 0.8
+    if n < desired * 0.8: cur -= 0.5
+    elif n < desired * 0.9: cur -= 0.2
+    elif n < desired: cur -= 0.1
+    if n > desired * 1.5: cur += 0.8
+    if n > desired * 1.3: cur += 0.5
+    if n > desired * 1.15: cur += 0.2
+    if n > desired: cur += 0.1
+    urgent = cur < 1
+    return min(max(cur, 0.0), 4.0), urgent
+
+
+def activate_points(pts, order, types, active_xy, K, cams, exposures, grads, window, last_frame, min_distance, desired_density, min_quality=3.0, min_obs=1, p=DEFAULTS):
+    """DSOTracer::activatePoints (DSOTracer.cpp:62-278) for the immature points `pts` (dict id -> ImmaturePoint) visited in `order`; `active_xy` = the active
+    points projected into the last frame.  The distance map (utils/DistanceMap.h: 8-neighbour BFS capped at maxDist) is the Chebyshev distance to the
+    nearest added integer pixel.  Returns (mapped {id: idepth}, removed [ids], min_distance, urgent)."""
+    H, W = grads[last_frame].shape[:2]
+    fx, fy, cx, cy = K
+    min_distance, urgent = adapt_minimum_distance(min_distance, len(active_xy), desired_density)
+    max_dist = int(min_distance * float(F32(10)))
+    added = []
+
+    def add(x, y):
+        x, y = int(x), int(y)
+        if 0 <= x < W and 0 <= y < H:
+            added.append((x, y))
+
+    def get(x, y):
+        x, y = int(x), int(y)
+        if not added:
+            return max_dist
+        a = np.asarray(added)
+        return min(max_dist, int(np.maximum(np.abs(a[:, 0] - x), np.abs(a[:, 1] - y)).min()))
+
+    for q in active_xy:
+        add(q[0], q[1])
+    to_opt, removed = [], []
+    for i in order:
+        pt = pts[i]
+        if pt.host == last_frame:
+            continue
+        if not math.isfinite(pt.idmax) or pt.status == IPS_OUTLIER:
+            removed.append(i); continue
+        can = pt.status in (IPS_GOOD, IPS_SKIPPED, IPS_BADCONDITION, IPS_OOB) and pt.interval < 8 and pt.quality > float(F32(min_quality)) and (pt.idmax + pt.idmin) > 0
+        if not can:
+            if pt.status == IPS_OOB:
+                removed.append(i)
+            continue
+        idepth = (pt.idmin + pt.idmax) / 2.0
+        R, t = rel_pose(cams[pt.host], cams[last_frame])
+        X = R @ (np.array([(pt.xy[0] - cx) / fx, (pt.xy[1] - cy) / fy, 1.0]) / idepth) + t
+        px, py = fx * X[0] / X[2] + cx, fy * X[1] / X[2] + cy
+        if px >= 0 and py >= 0 and px < W and py < H:
+            dist = get(px, py) + (px - math.floor(px))
+            if dist >= min_distance * float(F32(types[i])):
+                add(px, py); to_opt.append(i)
+        else:
+            removed.append(i)
+    mapped = {}
+    for i in to_opt:
+        rc, idp, _ = optimize_immature_point(pts[i], K, cams, exposures, grads, window, min_obs, p)
+        if rc == 1:
+            mapped[i] = idp
+        elif rc == -1 or pts[i].status == IPS_OOB:
+            removed.append(i)
+    return mapped, removed, min_distance, urgent

@@ -48,7 +48,7 @@ def test_tracer_header_symbols_exported(lib):
     src = open(os.path.join(ROOT, "include", "cmltrc.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     syms = sorted(set(re.findall(r"\b(cmltrc_[a-z_0-9]+)\s*\(", src)))
-    assert sorted(tracer.TRACER_SYMBOLS) == syms and len(syms) == 14
+    assert sorted(tracer.TRACER_SYMBOLS) == syms and len(syms) == 16
     for s in syms:
         assert hasattr(lib, s), f"libcmlba.so does not export {s}"
     cfg = tracer.TracerConfig()

@@ -140,3 +140,29 @@ def test_oracle_agreement_and_bookkeeping():
         trc.traceNewCoarse(11)
     with pytest.raises(CmlbaError):
         trc.makeNewTracesFrom(10, [[1.0, 1.0]])                  # pattern would leave the image
+
+
+def test_activate_points_matches_reference():
+    """activatePoints: minimum-distance adaptation, distance-map gating in the reference's iteration order, activation, removals (integer outputs: exact)."""
+    win, g = load()
+    a = cmlw.load(os.path.join(GOLDEN, "activate_golden.cmlw"))
+    trc, ids, _ = run_flow(win, g)
+    N = win["frame_cam"].shape[0]; P = win["im_host"].size
+    fx, fy, cx, cy = win["calib"]
+    axy = []
+    for h, xy, idp in zip(a["act_host"], a["act_xy"], a["act_idepth"]):          # the caller projects its active points into the last frame
+        c0, c1 = win["frame_cam"][h], win["frame_cam"][N - 1]
+        R = c1[:9].reshape(3, 3) @ c0[:9].reshape(3, 3).T; t = c1[9:] - R @ c0[9:]
+        X = R @ (np.array([(xy[0] - cx) / fx, (xy[1] - cy) / fy, 1.0]) / idp) + t
+        axy.append((fx * X[0] / X[2] + cx, fy * X[1] / X[2] + cy))
+    back = {int(ids[p]): p for p in range(P)}
+    act_ids, act, rem_ids, st = trc.activatePoints(N - 1, axy, ids[a["act_order"]], desiredPointDensity=int(a["desired_density"][0]))
+    mapped = {back[int(i)] for i in act_ids}
+    assert mapped == set(np.nonzero(a["act_mapped"])[0])
+    assert set(range(P)) - mapped - {back[int(i)] for i in rem_ids} == set(np.nonzero(a["act_still_immature"])[0])
+    assert st.current_minimum_distance == a["act_min_distance"][0] and st.urgently_need_new_points == a["act_urgent"][0]
+    assert st.num_mapped == len(mapped) and st.num_to_optimize >= st.num_mapped and (act["rc"] == 1).all()
+    for i, r in zip(act_ids, act):
+        assert abs(r["idepth"] - a["act_idepth_out"][back[int(i)]]) <= 1e-4 * r["idepth"]
+    gone = np.concatenate([act_ids, rem_ids])
+    assert (trc.getPoints()["host_frame_slot"][gone] == -1).all()                     # they left the immature set

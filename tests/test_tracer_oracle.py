@@ -66,3 +66,28 @@ def test_activation_matches_reference():
             if rc == 1:
                 assert abs(idp - g[f"{key}_opt_idepth"][p]) <= 1e-4 * g[f"{key}_opt_idepth"][p]
         assert seen == ({-1, 1} if key == "trc" else {-1, 0, 1})
+
+
+def test_activate_points_matches_reference():
+    """activatePoints (minimum-distance adaptation, distance-map gating in the reference's iteration order, activation, removal)."""
+    win, g, N, grads, exps = load()
+    a = cmlw.load(os.path.join(GOLDEN, "activate_golden.cmlw"))
+    P = win["im_host"].size
+    pts = {p: T.ImmaturePoint(int(win["im_host"][p]), win["im_xy"][p], grads[win["im_host"][p]]) for p in range(P)}
+    for f in range(1, N):
+        for p in range(P):
+            if pts[p].host < f:
+                T.trace(pts[p], win["calib"], win["frame_cam"][pts[p].host], win["frame_cam"][f], exps[pts[p].host], exps[f], win["gray"][pts[p].host], win["gray"][f])
+    fx, fy, cx, cy = win["calib"]
+    axy = []
+    for h, xy, idp in zip(a["act_host"], a["act_xy"], a["act_idepth"]):
+        R, t = T.rel_pose(win["frame_cam"][h], win["frame_cam"][N - 1])
+        X = R @ (np.array([(xy[0] - cx) / fx, (xy[1] - cy) / fy, 1.0]) / idp) + t
+        axy.append((fx * X[0] / X[2] + cx, fy * X[1] / X[2] + cy))
+    mapped, removed, md, urgent = T.activate_points(pts, list(a["act_order"]), np.ones(P), axy, win["calib"], win["frame_cam"], exps, grads, range(N - 1, -1, -1), N - 1, 2.0,
+                                                    int(a["desired_density"][0]))
+    assert set(mapped) == set(np.nonzero(a["act_mapped"])[0])
+    assert set(range(P)) - set(mapped) - set(removed) == set(np.nonzero(a["act_still_immature"])[0])
+    assert md == a["act_min_distance"][0] and urgent == bool(a["act_urgent"][0])
+    for i, v in mapped.items():
+        assert abs(v - a["act_idepth_out"][i]) <= 1e-4 * v
