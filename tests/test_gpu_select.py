@@ -54,3 +54,27 @@ def test_selector_matches_oracle_on_quantised_image():
         PixelSelector(32, 32)
     with pytest.raises(ValueError):
         PixelSelector(W + 32, H).compute(cap, 100.0)
+
+
+@pytest.mark.parametrize("recursions,th_factor", [(0, 1.0), (2, 1.0), (1, 2.0), (1, 0.5)])
+def test_selector_options_against_oracle(recursions, th_factor):
+    """recursionsLeft and thFactor other than the defaults, 1-pixel potential (thread-per-block kernel) and large potentials (warp kernel)."""
+    import prepare_oracle as P
+    import select_oracle as S
+    from libcml_b200 import CaptureImageGenerator, PixelSelector, synth
+    W, H = 224, 160
+    win = synth.make_window(W, H, 2, 10, 1, False, seed=33, low_freq=True, with_gradients=False)
+    gray = win["gray"][0]
+    cap = CaptureImageGenerator(W, H).generate(gray)
+    lv = P.prepare(gray, None, None, None, 5)
+    levels = [(lv[l][1], lv[l][2]) for l in range(3)]
+    for pot0, dens in ((1, 5000.0), (2, 900.0), (3, 300.0), (7, 60.0)):
+        sel = PixelSelector(W, H); sel.setPotential(pot0)
+        ora = S.PixelSelector(W, H); ora.pot = pot0
+        xy, ty = sel.compute(cap, dens, recursionsLeft=recursions, thFactor=th_factor)
+        out = ora.make_maps(levels, dens, recursions, th_factor)
+        sub = out[32:H - 32, 32:W - 32]
+        ys, xs = np.nonzero(sub != 0)
+        order = np.lexsort((ys, xs))
+        oxy = np.stack([xs[order] + 32, ys[order] + 32], 1).astype(np.float32)
+        assert np.array_equal(xy, oxy) and np.array_equal(ty, out[ys[order] + 32, xs[order] + 32]) and sel.currentPotential == ora.pot, (pot0, dens)

@@ -166,3 +166,45 @@ def test_activate_points_matches_reference():
         assert abs(r["idepth"] - a["act_idepth_out"][back[int(i)]]) <= 1e-4 * r["idepth"]
     gone = np.concatenate([act_ids, rem_ids])
     assert (trc.getPoints()["host_frame_slot"][gone] == -1).all()                     # they left the immature set
+
+
+def test_non_default_parameters_against_oracle():
+    """Other thresholds / step sizes / search lengths and a 250x187 image: CUDA vs the numpy restatement on every third point."""
+    import tracer_oracle as T
+    from libcml_b200 import DSOTracer, synth
+    W, H, N, per = 250, 187, 4, 240
+    win = synth.make_window(W, H, N, 20, 4, True, seed=37, low_freq=True, with_gradients=False)
+    rng = np.random.default_rng(8)
+    cams = win["truth_frame"]
+    exps = [(win["frame_exposure"][i], win["frame_affine"][i, 0], win["frame_affine"][i, 1]) for i in range(N)]
+    grads = [synth.gradient_image(win["gray"][i]) for i in range(N)]
+    xy = {h: np.stack([rng.integers(8, W - 8, per), rng.integers(8, H - 8, per)], 1).astype(np.float32) for h in range(N - 1)}
+    dev = dict(huber_threshold=6.0, outlier_th=100.0, max_pix_search=0.05, max_slack_interval=2.5, trace_step_size=1.0, min_improvement_factor=1.5,
+               min_trace_test_radius=3.0, extra_slack_on_th=1.1, min_idepth_h_act=60.0, gn_iterations=2)
+    ora = dict(T.DEFAULTS, huber=6.0, outlier_th=100.0, max_pix_search=float(np.float32(0.05)), max_slack_interval=2.5, min_improvement=1.5, test_radius=3.0,
+               extra_slack=float(np.float32(1.1)), min_idepth_h_act=60.0, gn_iterations=2)
+    trc = DSOTracer(W, H, win["calib"], **dev)
+    ids = {}
+    for f in range(N):
+        trc.addFrame(f, win["gray"][f], cams[f], exps[f])
+        if f > 0:
+            trc.traceNewCoarse(f)
+        if f < N - 1:
+            ids[f] = trc.makeNewTracesFrom(f, xy[f])
+    pts = trc.getPoints()
+    seen = set()
+    for h in range(N - 1):
+        for k in range(0, per, 3):
+            o = T.ImmaturePoint(h, xy[h][k], grads[h], ora)
+            for f in range(h + 1, N):
+                T.trace(o, win["calib"], cams[h], cams[f], exps[h], exps[f], win["gray"][h], win["gray"][f], ora)
+            m = pts[ids[h][k]]
+            assert m["status"] == o.status and m["energy_th"] == o.energyTH
+            seen.add(o.status)
+            for a, b in ((m["idepth_min"], o.idmin), (m["idepth_max"], o.idmax), (m["quality"], o.quality)):
+                assert (np.isnan(a) and np.isnan(b)) or abs(a - b) <= 1e-4 * max(abs(b), 1e-3)
+            if np.isfinite(o.idmax):
+                rc, idp, _ = T.optimize_immature_point(o, win["calib"], cams, exps, grads, range(N - 1, -1, -1), p=ora)
+                r = trc.optimizeImmaturePoint([ids[h][k]])[0]
+                assert r["rc"] == rc and (rc != 1 or abs(r["idepth"] - idp) <= 1e-4 * idp)
+    assert len(seen) >= 3

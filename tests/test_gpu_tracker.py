@@ -189,3 +189,46 @@ def test_error_paths():
         trk.setFrame(np.zeros((H, W + 1), np.float32))
     with pytest.raises(CmlbaError):
         DSOTracker(4, 4, win["calib"])
+
+
+@pytest.mark.parametrize("W,H,levels", [(250, 187, 0), (200, 150, 3), (320, 240, 4)])
+def test_odd_sizes_and_fewer_levels_against_oracle(W, H, levels):
+    """Image sizes that are not multiples of 2^levels (floor halving, clipped pyramid tiles) and pyramids with fewer than five levels
+    (maxLevel = levels - 1, DSOTracker.cpp:24), non-default parameters: CUDA vs the numpy restatement."""
+    import tracker_oracle as T
+    from libcml_b200 import DSOTracker, synth
+    N, seed = 3, 13
+    win = synth.make_window(W, H, N, 350, 4, True, seed=seed, low_freq=True, with_gradients=False)
+    rng = np.random.default_rng(seed)
+    ref, new = N - 2, N - 1
+    cams = win["truth_frame"]
+    keep = win["pt_host"] != new
+    idepth = win["truth_idepth"] * (1 + 0.01 * rng.standard_normal(win["pt_host"].size))
+    unc = 1.0 / (rng.uniform(50, 5000, win["pt_host"].size) + 0.01)
+    start = cams[new].copy(); start[9:] += 2e-3 * rng.standard_normal(3)
+    ref_exp = (win["frame_exposure"][ref], win["frame_affine"][ref, 0], win["frame_affine"][ref, 1])
+    params = dict(huber_threshold=7.0, cutoff_threshold=15.0, scale_translation=0.4, scale_light_b=500.0)
+    trk = DSOTracker(W, H, win["calib"], levels=levels, **params)
+    trk.makeCoarseDepthL0(win["gray"][ref], cams[ref], ref_exp, cams, win["pt_host"][keep], win["pt_xy"][keep], idepth[keep], unc[keep])
+    r = trk.optimize(start, (0.0, 0.0), gray=win["gray"][new], exposure_time=win["frame_exposure"][new])
+    L = trk.read("pc_n", np.int32).size
+    assert L == (levels or 5)
+    wh = trk.read("levels_wh", np.int32).reshape(L, 2)
+    pyr = T.build_pyramid(win["gray"][new], L)
+    rows = T.project_to_reference(win["calib"], cams, cams[ref], win["pt_host"][keep], win["pt_xy"][keep], idepth[keep], unc[keep])
+    pcs_o = T.make_coarse_depth(rows, [p[0] for p in T.build_pyramid(win["gray"][ref], L)])
+    for l in range(L):
+        assert pyr[l][0].shape == (wh[l, 1], wh[l, 0])
+        assert np.array_equal(trk.read(f"grad{l}", np.float32).reshape(wh[l, 1], wh[l, 0], 4)[:, :, :3], pyr[l][1])
+        pc = trk.read(f"pc{l}", np.float32).reshape(-1, 4)
+        assert pc.shape == pcs_o[l].shape and np.array_equal(pc[:, [0, 1, 3]], pcs_o[l][:, [0, 1, 3]]) and np.abs(pc[:, 2] - pcs_o[l][:, 2]).max() <= 2 ** -22
+    Rr, tr = cams[ref][:9].reshape(3, 3), cams[ref][9:]
+    R0 = start[:9].reshape(3, 3) @ Rr.T
+    pcs = [trk.read(f"pc{l}", np.float32).reshape(-1, 4) for l in range(L)]
+    o = T.optimize(pcs, [p[1] for p in pyr], [T.level_K(win["calib"], l) for l in range(L)], (R0, start[9:] - R0 @ tr), ref_exp, (win["frame_exposure"][new], 0.0, 0.0),
+                   params=dict(huber=7.0, cutoff=15.0, scale_trans=0.4, scale_b=500.0))
+    assert r.isCorrect == o["isCorrect"] and r.iterations == o["iterations"]
+    assert list(r.numTermsInE) == list(o["numTermsInE"]) and list(r.numSaturated) == list(o["numSaturated"])
+    cam = np.concatenate([(o["R"] @ Rr).ravel(), o["R"] @ tr + o["t"]])
+    assert np.abs(r.camera - cam).max() < 2e-5
+    np.testing.assert_allclose(r.E, o["E"], rtol=1e-3)
