@@ -7,9 +7,9 @@
 //   Selector::compute                     :367-384
 //
 // B200 design.  select() is a sequential sweep: the random direction of every block is pattern[n2], n2 = the number of level-1
-// selections made so far.  Inside a 4*pot block everything else is local, so ONE THREAD simulates one 4*pot block exactly (including
-// the sticky -2 flags and the strict > comparisons), starting from the n2 of its block; those starting values are an exclusive prefix
-// sum of the per-block selection counts, which themselves depend (rarely: only when a candidate's gradient is exactly orthogonal to the
+// selections made so far.  Inside a 4*pot block everything else is local, so one warp evaluates one 4*pot block exactly (the sticky -2
+// flags reduce to nesting rules, the strict > comparisons to first-in-traversal-order arg-max), starting from the n2 of its block; those
+// starting values are an exclusive prefix sum of the per-block selection counts, which themselves depend (rarely: only when a candidate's gradient is exactly orthogonal to the
 // drawn direction) on the directions.  The host iterates simulate -> scan until the counts reproduce themselves; blocks before the first
 // disagreement are already final, so the iteration converges and the result is exactly the sequential one.
 #include <cuda_runtime.h>
@@ -85,62 +85,7 @@ __global__ void sel_smooth_kernel(const SelDev s) {
     s.ths_smoothed[i] = (sum / num) * (sum / num);
 }
 
-// one thread = one 4*pot block, simulated exactly like the reference's nested loops
-__global__ void __launch_bounds__(128) sel_block_kernel(const SelDev s, const int pot, const float thFactor, const int nbx, const int nblocks) {
-    const int b = blockIdx.x * 128 + threadIdx.x;
-    if (b >= nblocks) return;
-    const int w = s.w, h = s.h;
-    const int x4 = (b % nbx) * 4 * pot, y4 = (b / nbx) * 4 * pot;
-    const float dw1 = 0.75f, dw2 = dw1 * dw1;
-    int n2 = s.start[b], c2 = 0, c3 = 0, c4 = 0;
-    const int my3 = min(4 * pot, h - y4), mx3 = min(4 * pot, w - x4);
-    int best4 = -1; float val4 = 0.f;
-    const int d4 = s.pattern[n2] & 0xF;
-    for (int y3 = 0; y3 < my3; y3 += 2 * pot) for (int x3 = 0; x3 < mx3; x3 += 2 * pot) {
-        const int x34 = x3 + x4, y34 = y3 + y4;
-        const int my2 = min(2 * pot, h - y34), mx2 = min(2 * pot, w - x34);
-        int best3 = -1; float val3 = 0.f;
-        const int d3 = s.pattern[n2] & 0xF;
-        for (int y2 = 0; y2 < my2; y2 += pot) for (int x2 = 0; x2 < mx2; x2 += pot) {
-            const int x234 = x2 + x34, y234 = y2 + y34;
-            const int my1 = min(pot, h - y234), mx1 = min(pot, w - x234);
-            int best2 = -1; float val2 = 0.f;
-            const int d2 = s.pattern[n2] & 0xF;
-            for (int y1 = 0; y1 < my1; y1++) for (int x1 = 0; x1 < mx1; x1++) {
-                const int xf = x1 + x234, yf = y1 + y234, idx = xf + w * yf;
-                if (xf < 4 || xf >= w - 5 || yf < 4 || yf > h - 4) continue;
-                const float th0 = s.ths_smoothed[(xf >> 5) + (yf >> 5) * s.w32];
-                const float th1 = th0 * dw1, th2 = th1 * dw2;
-                const float4 t = s.t0[idx];
-                if (t.w > th0 * thFactor) {
-                    const float dn = fabsf(__fadd_rn(__fmul_rn(t.y, c_dir[d2][0]), __fmul_rn(t.z, c_dir[d2][1])));
-                    if (dn > val2) { val2 = dn; best2 = idx; best3 = -2; best4 = -2; }
-                }
-                if (best3 == -2) continue;
-                const float ag1 = s.t1[(size_t) (int) ((float) yf * 0.5f + 0.25f) * s.w1 + (int) ((float) xf * 0.5f + 0.25f)].w;
-                if (ag1 > th1 * thFactor) {
-                    const float dn = fabsf(__fadd_rn(__fmul_rn(t.y, c_dir[d3][0]), __fmul_rn(t.z, c_dir[d3][1])));
-                    if (dn > val3) { val3 = dn; best3 = idx; best4 = -2; }
-                }
-                if (best4 == -2) continue;
-                const float ag2 = s.t2[(size_t) (int) ((double) ((float) yf * 0.25f) + 0.125) * s.w2 + (int) ((double) ((float) xf * 0.25f) + 0.125)].w;
-                if (ag2 > th2 * thFactor) {
-                    const float dn = fabsf(__fadd_rn(__fmul_rn(t.y, c_dir[d4][0]), __fmul_rn(t.z, c_dir[d4][1])));
-                    if (dn > val4) { val4 = dn; best4 = idx; }
-                }
-            }
-            if (best2 > 0) { s.map[best2] = 1.f; val3 = 1e10f; n2++; c2++; }
-        }
-        if (best3 > 0) { s.map[best3] = 2.f; val4 = 1e10f; c3++; }
-    }
-    if (best4 > 0) { s.map[best4] = 4.f; c4++; }
-    if (c2 != s.hits[b]) { s.hits[b] = c2; atomicAdd(s.counters + 3, 1); }
-    if (c2) atomicAdd(s.counters + 0, c2);
-    if (c3) atomicAdd(s.counters + 1, c3);
-    if (c4) atomicAdd(s.counters + 2, c4);
-}
-
-// The same block, one WARP per 4*pot block (used for pot >= 3, where a block has >= 144 pixels).  The sticky -2 flags of the reference reduce
+// One WARP per 4*pot block.  The sticky -2 flags of the reference's sweep reduce
 // to: a pot block selects its best level-1 candidate; a 2*pot block selects a level-2 point only if none of its pot blocks selected; the
 // 4*pot block selects a level-3 point only if nothing else was selected in it; "best" = largest |grad . dir| with the FIRST pixel in the
 // reference's traversal order winning ties (strict > in the sequential code).  The lanes stride the pixels of a pot block, keep running
@@ -358,9 +303,7 @@ struct Selector {
         for (int it = 0; it < nb + 2; it++) {
             SCK(cudaMemsetAsync(d_map, 0, (size_t) w * h * 4, stream));
             SCK(cudaMemsetAsync(d_counters, 0, 32, stream));
-            if (pot >= 3) sel_block_warp_kernel<<<(nb + 3) / 4, 128, 0, stream>>>(s, pot, thf, nbx, nb);
-            else sel_block_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(s, pot, thf, nbx, nb);
-            launches++;
+            sel_block_warp_kernel<<<(nb + 3) / 4, 128, 0, stream>>>(s, pot, thf, nbx, nb); launches++;
             SCK(cudaMemcpyAsync(h_pin, d_counters, 16, cudaMemcpyDeviceToHost, stream));
             SCK(cudaStreamSynchronize(stream));
             n[0] = h_pin[0]; n[1] = h_pin[1]; n[2] = h_pin[2];
