@@ -96,7 +96,7 @@ def test_direct_pipeline_end_to_end_on_synthetic_truth():
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import pipeline_demo
     r = pipeline_demo.run()
-    assert min(r["selected_per_keyframe"]) > 100 and r["activated"] > 0.9 * r["traced_points"]
+    assert min(r["selected_per_keyframe"]) > 100 and r["activated"] > 0.5 * r["traced_points"] and r["activated"] + r["removed"] <= r["traced_points"]
     assert r["activation_idepth_median_rel_err"] < 5e-3 and r["activation_idepth_p90_rel_err"] < 2e-2          # tracer + activation recover the plane's depth
     assert r["ba_ok"] and r["ba_energy_last"] < 0.1 * r["ba_energy_first"]
     assert r["ba_reproj_px_after"] < 0.1 and r["ba_reproj_px_after"] < 0.25 * r["ba_reproj_px_before"]         # BA: 0.45 px -> 0.04 px

@@ -28,23 +28,26 @@ def run(W=320, H=240, N=6, density=400, seed=5):
     KF = N - 1                                                        # frames 0..N-2 are keyframes, frame N-1 is tracked at the end
     sel = PixelSelector(W, H)
     trc = DSOTracer(W, H, K)
-    ids, corners = {}, {}
+    ids, corners, types = {}, {}, {}
     for f in range(KF):
         t0 = time.perf_counter(); trc.addFrameDevice(f, caps[f], truth[f], ex[f]); lap("tracer.addFrame", t0)
         if f > 0:
             t0 = time.perf_counter(); trc.traceNewCoarse(f); lap("tracer.trace", t0)
         if f < KF - 1:
-            t0 = time.perf_counter(); xy, _ = sel.compute(caps[f], density); lap("selector", t0)
-            t0 = time.perf_counter(); ids[f] = trc.makeNewTracesFrom(f, xy); corners[f] = xy; lap("tracer.makeNewTraces", t0)
-    pts = trc.getPoints()
+            t0 = time.perf_counter(); xy, ty = sel.compute(caps[f], density); lap("selector", t0)
+            t0 = time.perf_counter(); ids[f] = trc.makeNewTracesFrom(f, xy); corners[f] = xy; types[f] = ty; lap("tracer.makeNewTraces", t0)
     all_ids = np.concatenate([ids[f] for f in ids]); all_xy = np.concatenate([corners[f] for f in corners]); all_host = np.concatenate([np.full(ids[f].size, f) for f in ids])
-    cand = np.isfinite(pts["idepth_max"][all_ids])
-    t0 = time.perf_counter(); act = trc.optimizeImmaturePoint(all_ids[cand]); lap("tracer.activate", t0)
-    ok = act["rc"] == 1
-    a_xy, a_host, a_id = all_xy[cand][ok], all_host[cand][ok], act["idepth"][ok].astype(np.float64)
+    all_ty = np.concatenate([types[f] for f in types])
+    # activatePoints: no active points yet (first window), so the distance map only spaces the new points among themselves
+    t0 = time.perf_counter(); act_ids, act, rem_ids, st = trc.activatePoints(KF - 1, np.zeros((0, 2)), all_ids, desiredPointDensity=2 * density, types=all_ty); lap("tracer.activatePoints", t0)
+    where = {int(i): k for k, i in enumerate(all_ids)}
+    sel_idx = np.array([where[int(i)] for i in act_ids])
+    a_xy, a_host, a_id = all_xy[sel_idx], all_host[sel_idx], act["idepth"].astype(np.float64)
+    ok = np.ones(a_id.size, bool)
     true_id = 1.0 / win["truth_depth"][a_host, a_xy[:, 1].astype(int), a_xy[:, 0].astype(int)]
     rel = np.abs(a_id - true_id) / true_id
-    out = {"frames": N, "selected_per_keyframe": [int(corners[f].shape[0]) for f in corners], "traced_points": int(all_ids.size), "activated": int(ok.sum()),
+    out = {"frames": N, "selected_per_keyframe": [int(corners[f].shape[0]) for f in corners], "traced_points": int(all_ids.size), "activated": int(ok.sum()), "removed": int(rem_ids.size),
+           "minimum_distance": float(st.current_minimum_distance),
            "activation_idepth_median_rel_err": float(np.median(rel)), "activation_idepth_p90_rel_err": float(np.quantile(rel, 0.9))}
     # bundle adjustment over the keyframes with the activated points, poses perturbed
     rng = np.random.default_rng(seed)
