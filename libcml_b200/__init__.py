@@ -11,3 +11,4 @@ from .tracker import DSOTracker  # noqa: F401
 from .tracer import DSOTracer  # noqa: F401
 from .imgprep import CaptureImageGenerator  # noqa: F401
 from .selector import PixelSelector  # noqa: F401
+from .fast import FAST  # noqa: F401

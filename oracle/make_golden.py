@@ -206,6 +206,28 @@ def activate():
     print("activate golden", os.path.getsize(os.path.join(OUT, "activate_golden.cmlw")) // 1024, "KB  mapped", int(g["act_mapped"].sum()), "kept", int(g["act_still_immature"].sum()))
 
 
+def fast():
+    """Features::FAST::compute of the reference (SURVEY 8f NEXT #4, first unit of the ORB extractor) on a noisy 200x150 8-bit image with pasted blobs,
+    thresholds 20 / 7 (ORB's iniThFAST / minThFAST) and 60."""
+    tmp = "/tmp/cmlba_golden"
+    os.makedirs(tmp, exist_ok=True)
+    W, H = 200, 150
+    win = synth.make_window(W, H, 2, 10, 1, False, seed=9, with_gradients=False)
+    rng = np.random.default_rng(1)
+    img = np.clip(win["gray"][0] + rng.normal(0, 6, (H, W)), 0, 255).astype(np.uint8)
+    for _ in range(40):
+        x, y = rng.integers(5, W - 10), rng.integers(5, H - 10)
+        img[y:y + rng.integers(2, 6), x:x + rng.integers(2, 6)] = rng.integers(0, 256)
+    w = dict(gray_u8=img, thresholds=np.array([20, 7, 60], np.int32))
+    cmlw.save(os.path.join(tmp, "fast.cmlw"), w)
+    run_ref(os.path.join(tmp, "fast.cmlw"), "fast", os.path.join(tmp, "fast_out.cmlw"))
+    g = cmlw.load(os.path.join(tmp, "fast_out.cmlw"))
+    assert all(g[f"fast_xy{k}"].shape[0] > 10 for k in range(3))
+    gold = dict(w); gold.update({k: v for k, v in g.items() if k != "fast_seconds"})
+    cmlw.save(os.path.join(OUT, "fast_golden.cmlw"), gold)
+    print("fast golden", os.path.getsize(os.path.join(OUT, "fast_golden.cmlw")) // 1024, "KB", [int(g[f"fast_xy{k}"].shape[0]) for k in range(3)])
+
+
 def prepare():
     """CaptureImageGenerator::generate of the reference (SURVEY 8f NEXT #3) with LUT, inverse vignette and a radtan pre-undistorter: 200x150 -> 160x120."""
     tmp = "/tmp/cmlba_golden"
@@ -244,6 +266,8 @@ if __name__ == "__main__":
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     if len(sys.argv) > 1 and sys.argv[1] == "select":
         select(); sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fast":
+        fast(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "activate":
         activate(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "prepare":

@@ -57,6 +57,7 @@
 #include <cml/optimization/dso/DSOTracker.h>
 #include <cml/optimization/dso/DSOTracer.h>
 #include <cml/features/corner/PixelSelector.h>
+#include <cml/features/corner/FAST.h>
 #undef private
 #undef protected
 
@@ -810,6 +811,35 @@ static int runPrepare(const cmlw::File &in, cmlw::File &out, int repeat) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// mode fast: Features::FAST::compute (features/corner/FAST.cpp:3-13: fast9_detect, fast9_score, nonmax_suppression) on the 8-bit image `gray_u8`
+// for every threshold in `thresholds`.
+static int runFast(const cmlw::File &in, cmlw::File &out, int repeat) {
+    const int H = (int) in.get("gray_u8").dims[0], W = (int) in.get("gray_u8").dims[1];
+    GrayImage img(W, H);
+    memcpy(img.data(), in.get("gray_u8").as<uint8_t>(), (size_t) W * H);
+    const int32_t *th = in.get("thresholds").as<int32_t>();
+    const int nt = (int) in.get("thresholds").dims[0];
+    double best = 1e30;
+    for (int k = 0; k < nt; k++) {
+        List<Corner> corners;
+        for (int rep = 0; rep < std::max(1, repeat); rep++) {
+            Features::FAST fast;
+            corners.clear();
+            const double a = now_s();
+            fast.compute(img, corners, th[k]);
+            best = std::min(best, now_s() - a);
+        }
+        std::vector<int32_t> xy(corners.size() * 2), sc(corners.size());
+        for (size_t i = 0; i < corners.size(); i++) { xy[2 * i] = (int32_t) corners[i].point(0).x(); xy[2 * i + 1] = (int32_t) corners[i].point(0).y(); sc[i] = (int32_t) corners[i].response(); }
+        out.put<int32_t>("fast_xy" + std::to_string(k), xy, {(uint64_t) corners.size(), 2});
+        out.put1<int32_t>("fast_score" + std::to_string(k), sc);
+    }
+    out.scalar<double>("fast_seconds", best);
+    printf("{\"fast_seconds\": %.6f}\n", best);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // mode select: DSO pixel selector (SURVEY 8f NEXT #4, PixelSelector part): PixelSelector::compute on the prepared frame `gray`
 // (features/corner/PixelSelector.cpp:367-384 -> makeMaps :121-213 -> makeHists :41-118, select :217-365), for every density in `densities`
 // on the SAME selector instance (currentPotential carries over, like successive keyframes).
@@ -866,6 +896,13 @@ int main(int argc, char **argv) {
     if (!in.load(window)) { fprintf(stderr, "cannot read %s\n", window.c_str()); return 2; }
 
     int rc = 0;
+    if (mode == "fast") {
+        cmlw::File out;
+        rc = runFast(in, out, repeat);
+        if (!outPath.empty()) out.save(outPath);
+        fflush(stdout);
+        _exit(rc);
+    }
     if (mode == "select") {
         cmlw::File out;
         rc = runSelect(in, out, repeat);

@@ -93,6 +93,21 @@ def test_selector_header_symbols_exported(lib):
         assert selector._bind(lib).cmlsel_create(0, 640, 480, C.byref(h)) == -2 and b"no CUDA device" in lib.cmlsel_last_error(None)
 
 
+def test_fast_header_symbols_exported(lib):
+    """include/cmlfast.h (FAST-9 boundary)."""
+    from libcml_b200 import fast
+    src = open(os.path.join(ROOT, "include", "cmlfast.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(cmlfast_[a-z_0-9]+)\s*\(", src)))
+    assert sorted(fast.FAST_SYMBOLS) == syms and len(syms) == 4
+    for s in syms:
+        assert hasattr(lib, s), f"libcmlba.so does not export {s}"
+    import torch
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert fast._bind(lib).cmlfast_create(0, 640, 480, C.byref(h)) == -2 and b"no CUDA device" in lib.cmlfast_last_error(None)
+
+
 def ctypes_sizeof_matches(tracer):
     # cmltrc_point: 2 x int32 + 11 doubles; cmltrc_activation: int32 + float + uint32
     return tracer.POINT.itemsize == 96 and tracer.ACTIVATION.itemsize == 12
