@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02)
 
     def stop(self):
         self._stop_evt.set()
@@ -239,7 +239,13 @@ def main():
     if world > 1:
         dist.barrier()
     brw = ba.benchPass(args.steps, args.warmup, False)    # L2-warm variant (window fits the 126 MB L2), reported for context
+    # the timed region lasts ~10 ms, shorter than one nvidia-smi query: keep the identical pass running (untimed, same count on every rank) so that
+    # the sampler sees the clocks and throttle reasons of exactly this load
+    if world > 1:
+        dist.barrier()
+    ba.benchPass(2000, 0, True)
     clocks = sampler.stop()
+    clocks["note"] = "sampled from the start of the timed passes to the end of 2000 further identical (untimed) passes"
     R = br.residuals
     ms = torch.tensor([br.ms_pass, br.ms_linearize, brw.ms_pass], dtype=torch.float64, device="cuda")
     if world > 1:
