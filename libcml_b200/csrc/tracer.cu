@@ -178,13 +178,13 @@ struct Tracer {
     int remove_points(int count, const int64_t *ids) {
         if (count < 0 || (count > 0 && !ids)) { error = "bad arguments"; return CMLTRC_ERR_ARG; }
         RCK(cudaSetDevice(device));
-        const int minus1 = -1;
+        bool any = false;
         for (int i = 0; i < count; i++) {
             if (ids[i] < 0 || ids[i] >= num) { error = "unknown point id"; return CMLTRC_ERR_ARG; }
             if (host_slot[ids[i]] < 0) continue;
-            host_slot[ids[i]] = -1;
-            RCK(cudaMemcpyAsync(pts.host + ids[i], &minus1, 4, cudaMemcpyHostToDevice, stream));
+            host_slot[ids[i]] = -1; any = true;
         }
+        if (any) RCK(cudaMemcpyAsync(pts.host, host_slot.data(), (size_t) num * sizeof(int), cudaMemcpyHostToDevice, stream));     // one copy of the mirror, not one per point
         RCK(cudaStreamSynchronize(stream));
         return CMLTRC_OK;
     }
