@@ -300,15 +300,21 @@ struct Selector {
         const int nbx = (w + 4 * pot - 1) / (4 * pot), nby = (h + 4 * pot - 1) / (4 * pot), nb = nbx * nby;
         SCK(cudaMemsetAsync(d_hits, 0, (size_t) nb * 4, stream));
         SCK(cudaMemsetAsync(d_start, 0, (size_t) nb * 4, stream));
-        for (int it = 0; it < nb + 2; it++) {
-            SCK(cudaMemsetAsync(d_map, 0, (size_t) w * h * 4, stream));
-            SCK(cudaMemsetAsync(d_counters, 0, 32, stream));
+        auto pass = [&]() -> cudaError_t {
+            cudaError_t e = cudaMemsetAsync(d_map, 0, (size_t) w * h * 4, stream);
+            if (e == cudaSuccess) e = cudaMemsetAsync(d_counters, 0, 32, stream);
+            if (e != cudaSuccess) return e;
             sel_block_warp_kernel<<<(nb + 3) / 4, 128, 0, stream>>>(s, pot, thf, nbx, nb); launches++;
+            return cudaGetLastError();
+        };
+        SCK(pass());                                                 // pass 1 (all starts 0) only produces the per-block counts: no read-back needed
+        for (int it = 0; it < nb + 2; it++) {
+            sel_scan_kernel<<<1, 1024, 0, stream>>>(d_hits, d_start, nb); launches++;
+            SCK(pass());
             SCK(cudaMemcpyAsync(h_pin, d_counters, 16, cudaMemcpyDeviceToHost, stream));
             SCK(cudaStreamSynchronize(stream));
             n[0] = h_pin[0]; n[1] = h_pin[1]; n[2] = h_pin[2];
             if (h_pin[3] == 0) return CMLSEL_OK;                 // every block reproduced the count its start value was built from
-            sel_scan_kernel<<<1, 1024, 0, stream>>>(d_hits, d_start, nb); launches++;
         }
         error = "select() did not reach its fixed point";
         return CMLSEL_ERR_STATE;
