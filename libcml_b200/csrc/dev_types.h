@@ -9,8 +9,15 @@ constexpr int MAXF = 16;          // CMLBA_MAX_FRAMES
 constexpr int RJ_STRIDE = 36;     // floats per residual Jacobian record (x[10] y[10] A[3] B[6] BR[6] pad)
 constexpr int T_STRIDE = 16;      // floats per (point,target) Schur row: JpJdF[8] bd Hdd Hcd[4] good pad
 constexpr int ACC_N = 96;         // 91 unique entries of the 13x13 block, padded to 3*32
-constexpr int LIN_THREADS = 32;   // linearize+accumulate: one warp-CTA per chunk, one thread per residual
-constexpr int ACC_CHUNK = 32;     // residuals per linearize+accumulate CTA (all in one (h,t) bin)
+constexpr int ACC_CHUNK = 32;     // residuals per linearize warp pass (one thread per residual; consecutive residuals of the tile-sorted order)
+// linearize_tile_kernel: target-image tiles staged by TMA (cp.async.bulk.tensor.2d) into a shared-memory ring
+constexpr int LT_TILE_W = 64, LT_TILE_H = 32;         // core tile of the target image that owns a residual (by its centre projection at bin time)
+constexpr int LT_HALO = 4;                            // pattern reach (2) + bilinear tap (1) + drift allowance since the binning
+constexpr int LT_BOX_W = LT_TILE_W + 2 * LT_HALO;     // 72 texels
+constexpr int LT_BOX_H = LT_TILE_H + 2 * LT_HALO;     // 40 rows
+constexpr int LT_TILE_BYTES = LT_BOX_W * LT_BOX_H * 16;   // 46 080 B of float4 texels per staged tile
+// ring depth and consumer warps per CTA (+1 producer warp) are template parameters of the kernel (Engine::launch_linearize picks the variant)
+constexpr int LT_SCR_STRIDE = 36;                     // floats per lane row of the per-warp reduction scratch (32 + pad, keeps 16-byte alignment)
 constexpr int P2P_POST_CAND_MAX = 65536;      // candidates per rank record that fit the peer-memory exchange (else NCCL all-gather)
 constexpr size_t P2P_POST_DOUBLES = 8 + P2P_POST_CAND_MAX / 2;
 constexpr size_t P2P_SLOT_DOUBLES = 2 * (size_t) (8 * MAXF + 4) * (8 * MAXF + 4) + 2 * (8 * MAXF + 4);   // sys at the largest window
@@ -25,6 +32,7 @@ struct PairPre {
     double a, b;          // exposure transition aff_h.to(aff_t)  (map/Exposure.h:119-123)
     float b0;             // hostData->getB0(scaleB)  (DSOFrame.h:197-199)
     float pad;
+    float Af[3], Bf[3];   // R[:,0]/fx, R[:,1]/fy: P(x+sx, y+sy) = P(x,y) + sx*A + sy*B  (pattern offsets in fp32, see linearize.cuh)
 };
 
 // DSOFrame (DSOFrame.h:17-246) as a POD
@@ -69,7 +77,7 @@ struct DevWin {
     // sizes
     int N, P, R, W, H, n;          // n = 8N+4
     int newest_begin;              // residuals [newest_begin, R) target the newest frame (sorted by bin t*N+h)
-    int n_lin_blocks, n_acc_chunks, n_sc_chunks;
+    int n_sc_chunks;
     // calibration / parameters
     double fx, fy, cx, cy, fxi, fyi;
     float huber, cth, scaleF, scaleC, scaleA, scaleB, scaleT, scaleR;
@@ -96,9 +104,32 @@ struct DevWin {
     int *pt_num_good;              // numGoodResiduals
     int *pt_ngood_cur;             // good residuals in the committed linearization
     double *pt_step;
-    // residuals (sorted by bin = t*N+h, then by point)
+    // residuals as the host lays them out (bin-major: bin = t*N+h, then by device point): inputs of the tile binning only
     const int *r_point;
     const uint8_t *r_host, *r_target;
+    const int *res_bin_begin;      // [N*N+1] first host-order residual of every bin
+    // tile binning, rebuilt on the device by every prepare() (bin_count / bin_scatter / bin_segments kernels, linearize.cuh):
+    // residuals sorted by (target, tile of the centre projection, host); every per-residual array below is in THIS order
+    int tiles_x, tiles_y, n_tiles; // LT_TILE_W x LT_TILE_H tiles per frame
+    int n_chunks;                  // ceil(R / 32) warp passes of linearize_tile_kernel
+    int tma_on;                    // tensor maps encoded: tiles are staged by TMA (else every tap is read from global memory)
+    int lt_mode;                   // development: 1 = the consumers only run the ring protocol (TMA streaming floor of the pass)
+    int lt_exact;                  // 1 = every pattern pixel is projected in fp64 like the reference (parity study; default: fp32 offsets from the fp64 centre)
+    int *bin_key;                  // [R] host order: ((t * n_tiles + tile) * N + h)
+    int *bin_hist;                 // [N * n_tiles * N] zero between uses
+    int *bin_offs;                 // [N * n_tiles * N] exclusive scan of the histogram
+    int *job_of_tile;              // [N * n_tiles] index of the (t, tile) job among the non-empty ones
+    uint32_t *job_desc;            // [jobs] t | tile_x << 4 | tile_y << 16
+    uint32_t *r_pht;               // [R] device point | host << 24 | target << 28
+    int *r_job;                    // [R] tile job of the residual
+    int *r_src;                    // [R] host-order index of the residual
+    int *seg_cnt, *seg_base;       // [n_chunks] (+1) segments (runs of one (h,t) pair) per warp pass and their exclusive scan; seg_base[n_chunks] = total
+    uint8_t *seg_hdr;              // [segments] h | t << 4 of every partial sum in acc_part
+    int *seg_t_begin;              // [N+1] first partial of every target frame (partials are sorted by target)
+    int *bin_ticket;               // last-block counters of the binning kernels
+    // final states in HOST order, written by the fixLinearization pass (what finish_run reads back)
+    uint8_t *fin_state, *fin_alive;
+    float *fin_energy;
     uint8_t *r_state[2];
     float *r_energy[2];
     uint8_t *r_good[2];
@@ -110,10 +141,8 @@ struct DevWin {
     float *T[2];                   // [P][N][T_STRIDE]
     float *dbg;                    // optional [R][40]: resF[8] JIdx[16] JabF[16]
     // partial sums
-    double *energy_part;           // [n_lin_blocks]
-    float *acc_part[2];            // [n_acc_chunks][ACC_N]
-    const int *acc_chunk_bin, *acc_chunk_begin, *acc_chunk_count;
-    const int *bin_chunk_begin;    // [N*N+1] by bin = t*N+h
+    double *energy_part;           // [n_chunks]
+    float *acc_part[2];            // [segments][ACC_N] partial 13x13 blocks, one per (warp pass, (h,t) run)
     float *sc_part;                // [n_sc_chunks][sc_stride]
     int sc_stride;                 // (8N)^2 + 32N + 8N + 16 + 4 (padded to 4)
     const int *sc_chunk_host, *sc_chunk_begin, *sc_chunk_count;

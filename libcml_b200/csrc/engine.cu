@@ -239,8 +239,17 @@ public:
     // device buffers
     DevBuf<FrameDev> d_frames; DevBuf<PairPre> d_pairs; DevBuf<Ctrl> d_ctrl;
     DevBuf<double> d_AH, d_AT, d_HM, d_bM, d_Pns, d_pt_idepth, d_pt_step, d_energy_part, d_st_out, d_sys, d_x, d_xAd, d_pt_part;
-    DevBuf<int> d_pt_host, d_pt_num_good, d_pt_ngood_cur, d_r_point, d_acc_chunk_bin, d_acc_chunk_begin, d_acc_chunk_count, d_bin_chunk_begin, d_sc_chunk_host,
+    DevBuf<int> d_pt_host, d_pt_num_good, d_pt_ngood_cur, d_r_point, d_res_bin_begin, d_sc_chunk_host,
         d_sc_chunk_begin, d_sc_chunk_count, d_host_chunk_begin;
+    // tile binning (linearize.cuh): sorted residual order, tile jobs, partial-block bookkeeping, final states in host order
+    DevBuf<int> d_bin_key, d_bin_hist, d_bin_offs, d_job_of_tile, d_r_job, d_r_src, d_seg_cnt, d_seg_base, d_seg_t_begin, d_bin_ticket;
+    DevBuf<uint32_t> d_job_desc, d_r_pht;
+    DevBuf<uint8_t> d_seg_hdr, d_fin_state, d_fin_alive;
+    DevBuf<float> d_fin_energy;
+    TileMaps tile_maps;           // one tensor map per window frame (re-encoded by build_device_window)
+    int n_sm = 148;
+    int lt_variant = 0, lt_mode = 0, lt_exact = 0;   // development switches (CMLBA_LT_VARIANT, CMLBA_LT_MODE): kernel shape, streaming-only mode
+    size_t seg_cap = 0;
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
         d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj, d_T0, d_T1, d_dbg, d_acc0, d_acc1, d_sc_part, d_stage[MAXF];
     int stage_flip = 0;
@@ -255,8 +264,8 @@ public:
     bool want_dbg = false;
     DevBuf<float4> d_flush;
     std::vector<float4 *> img_pool;   // recycled image allocations (reset())
-    int n_acc_chunks = 0, n_sc_chunks = 0;
-    std::vector<int> h_bin_chunk_begin, h_host_chunk_begin;
+    int n_chunks = 0, n_sc_chunks = 0;
+    std::vector<int> h_host_chunk_begin;
 
     HostTimers timers;
     void set_error(const std::string &s) { err = s; }
@@ -269,8 +278,16 @@ public:
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
-        CK(cudaFuncSetAttribute(linearize_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CK(cudaFuncSetAttribute(linearize_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+#define LT_ATTR(CW, ST)                                                                                                                                  \
+    CK(cudaFuncSetAttribute(linearize_tile_kernel<false, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lt_smem_bytes(MAXF, CW, ST))); \
+    CK(cudaFuncSetAttribute(linearize_tile_kernel<true, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lt_smem_bytes(MAXF, CW, ST)));
+        LT_ATTR(11, 3) LT_ATTR(7, 4) LT_ATTR(15, 3) LT_ATTR(15, 2)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
+#undef LT_ATTR
+        if (const char *v = getenv("CMLBA_LT_VARIANT")) lt_variant = atoi(v);
+        if (const char *v = getenv("CMLBA_LT_MODE")) lt_mode = atoi(v);
+        if (const char *v = getenv("CMLBA_LT_EXACT")) lt_exact = atoi(v);
+        CK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CK(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         return CMLBA_OK;
@@ -293,8 +310,10 @@ public:
         DevBuf<double> *dd[] = {&d_AH, &d_AT, &d_HM, &d_bM, &d_Pns, &d_pt_idepth, &d_pt_step, &d_energy_part, &d_st_out, &d_sys, &d_x, &d_xAd, &d_pt_part};
         for (auto *b : dd) b->release();
         d_post_send.release(); d_post_recv.release(); d_cap.release();
-        DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_acc_chunk_bin, &d_acc_chunk_begin, &d_acc_chunk_count, &d_bin_chunk_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin};
+        DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_res_bin_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin,
+                             &d_bin_key, &d_bin_hist, &d_bin_offs, &d_job_of_tile, &d_r_job, &d_r_src, &d_seg_cnt, &d_seg_base, &d_seg_t_begin, &d_bin_ticket};
         for (auto *b : di) b->release();
+        d_job_desc.release(); d_r_pht.release(); d_seg_hdr.release(); d_fin_state.release(); d_fin_alive.release(); d_fin_energy.release();
         DevBuf<float> *df[] = {&d_pt_x, &d_pt_y, &d_pt_idz, &d_pt_idb, &d_pt_colors, &d_pt_weights, &d_pt_priorF, &d_pt_Hdd, &d_pt_bd, &d_pt_Hcd, &d_pt_HdiF, &d_pt_bdSumF, &d_pt_idh, &d_pt_mrb,
                                &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj, &d_T0, &d_T1, &d_dbg, &d_acc0, &d_acc1, &d_sc_part};
         for (auto *b : df) b->release();
@@ -740,23 +759,24 @@ public:
         const int R = bcnt[N * N];
         res_bin_begin = bcnt;
         lap("bdw.sort");
-        // chunk tables: accumulate chunks per bin, Schur chunks per host
-        h_bin_chunk_begin.assign(N * N + 1, 0);
-        for (int b = 0; b < N * N; b++) h_bin_chunk_begin[b + 1] = h_bin_chunk_begin[b] + (bcnt[b + 1] - bcnt[b] + ACC_CHUNK - 1) / ACC_CHUNK;
-        n_acc_chunks = h_bin_chunk_begin[N * N];
+        if (P >= (1 << 24)) { set_error("more than 2^24 points in the window"); return CMLBA_ERR_ARG; }
+        // warp passes of the sampling kernel (32 consecutive residuals of the tile-sorted order), Schur chunks per host
+        n_chunks = (R + ACC_CHUNK - 1) / ACC_CHUNK;
+        const int tiles_x = (W + LT_TILE_W - 1) / LT_TILE_W, tiles_y = (H + LT_TILE_H - 1) / LT_TILE_H, n_tiles = tiles_x * tiles_y;
+        const size_t n_keys = (size_t) N * n_tiles * N;
+        seg_cap = std::min<size_t>((size_t) R, n_keys) + (size_t) n_chunks + 1;     // runs of one (h,t) pair: one per non-empty (t,tile,h) group, plus the cuts at pass boundaries
         h_host_chunk_begin.assign(N + 1, 0);
         for (int h = 0; h < N; h++) h_host_chunk_begin[h + 1] = h_host_chunk_begin[h] + (hcnt[h + 1] - hcnt[h] + SC_CHUNK - 1) / SC_CHUNK;
         n_sc_chunks = h_host_chunk_begin[N];
         const int NB = 8 * N;
         const int sc_stride = ((NB * NB + NB * 4 + NB + 20) + 3) & ~3;
-        const int n_lin_blocks = n_acc_chunks;   // the fused linearize+accumulate kernel runs one CTA per accumulate chunk
         const int n_pt_blocks = (P + 255) / 256;
         // arena layout
         up.begin();
         const size_t o_pt_host = up.take<int>(P), o_x = up.take<float>(P), o_y = up.take<float>(P), o_idz = up.take<float>(P), o_prior = up.take<float>(P),
                      o_mrb = up.take<float>(P), o_idh = up.take<float>(P), o_ng = up.take<int>(P), o_id = up.take<double>(P),
                      o_rp = up.take<int>(R), o_rh = up.take<uint8_t>(R), o_rt = up.take<uint8_t>(R),
-                     o_cb = up.take<int>(n_acc_chunks), o_cbeg = up.take<int>(n_acc_chunks), o_ccnt = up.take<int>(n_acc_chunks), o_bcb = up.take<int>(N * N + 1),
+                     o_rbb = up.take<int>(N * N + 1),
                      o_sh = up.take<int>(n_sc_chunks), o_sbeg = up.take<int>(n_sc_chunks), o_scnt = up.take<int>(n_sc_chunks), o_hcb = up.take<int>(N + 1);
         CK(cudaStreamSynchronize(stream));          // the previous upload from this pinned block must have landed
         materialize_snapshot();                     // the residual snapshot of the last run() still points into this block
@@ -781,13 +801,10 @@ public:
                 memset(h_rh + k, h, ke - k); memset(h_rt + k, t, ke - k);
                 for (int i = hcnt[h]; i < hcnt[h + 1]; i++) if ((dmask[i] >> t) & 1) h_rp[k++] = i;
             }
-            int *cb = up.host<int>(o_cb), *cbeg = up.host<int>(o_cbeg), *ccnt = up.host<int>(o_ccnt);
-            for (int b = 0, c = 0; b < N * N; b++)
-                for (int s0 = bcnt[b]; s0 < bcnt[b + 1]; s0 += ACC_CHUNK, c++) { cb[c] = b; cbeg[c] = s0; ccnt[c] = std::min(ACC_CHUNK, bcnt[b + 1] - s0); }
             int *sh = up.host<int>(o_sh), *sbeg = up.host<int>(o_sbeg), *scnt = up.host<int>(o_scnt);
             for (int h = 0, c = 0; h < N; h++)
                 for (int s0 = hcnt[h]; s0 < hcnt[h + 1]; s0 += SC_CHUNK, c++) { sh[c] = h; sbeg[c] = s0; scnt[c] = std::min(SC_CHUNK, hcnt[h + 1] - s0); }
-            memcpy(up.host<int>(o_bcb), h_bin_chunk_begin.data(), (N * N + 1) * sizeof(int));
+            memcpy(up.host<int>(o_rbb), bcnt.data(), (N * N + 1) * sizeof(int));
             memcpy(up.host<int>(o_hcb), h_host_chunk_begin.data(), (N + 1) * sizeof(int));
         }
         const int newest_begin = N > 0 ? bcnt[(N - 1) * N] : R;   // bins are t-major: residuals targeting the newest frame are the tail
@@ -802,8 +819,13 @@ public:
         CK(d_r_new_state.reserve(Rz)); CK(d_r_new_energy.reserve(Rz)); CK(d_r_new_energy_wo.reserve(Rz)); CK(d_r_alive.reserve(Rz)); CK(d_r_center.reserve(Rz * 3));
         CK(d_rj.reserve(Rz * RJ_STRIDE)); CK(d_T0.reserve(Pz * N * T_STRIDE)); CK(d_T1.reserve(Pz * N * T_STRIDE));
         if (want_dbg) CK(d_dbg.reserve(Rz * DBG_STRIDE));
-        CK(d_energy_part.reserve(std::max(n_lin_blocks, 1)));
-        CK(d_acc0.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N)); CK(d_acc1.reserve((size_t) std::max(n_acc_chunks, 1) * ACC_N));
+        CK(d_energy_part.reserve(std::max(n_chunks, 1)));
+        CK(d_acc0.reserve(seg_cap * ACC_N)); CK(d_acc1.reserve(seg_cap * ACC_N));
+        CK(d_bin_key.reserve(Rz)); CK(d_bin_hist.reserve(n_keys)); CK(d_bin_offs.reserve(n_keys)); CK(d_job_of_tile.reserve((size_t) N * n_tiles)); CK(d_job_desc.reserve((size_t) N * n_tiles));
+        CK(d_r_pht.reserve(Rz)); CK(d_r_job.reserve(Rz)); CK(d_r_src.reserve(Rz)); CK(d_seg_cnt.reserve(std::max(n_chunks, 1))); CK(d_seg_base.reserve(n_chunks + 1));
+        CK(d_seg_hdr.reserve(seg_cap)); CK(d_seg_t_begin.reserve(MAXF + 1));
+        CK(d_fin_state.reserve(Rz)); CK(d_fin_alive.reserve(Rz)); CK(d_fin_energy.reserve(Rz));
+        if (!d_bin_ticket.p) { CK(d_bin_ticket.reserve(2)); CK(cudaMemsetAsync(d_bin_ticket.p, 0, 2 * sizeof(int), stream)); }
         CK(d_sc_part.reserve((size_t) std::max(n_sc_chunks, 1) * sc_stride));
         CK(d_st_out.reserve((size_t) N * N * st_stride(N)));
         CK(d_sys.reserve((size_t) 2 * n * n + 2 * n)); CK(d_x.reserve(n)); CK(d_xAd.reserve((size_t) N * N * 8)); CK(d_pt_part.reserve((size_t) std::max(n_pt_blocks, 1) * 4));
@@ -814,7 +836,7 @@ public:
         VIEW(d_pt_host, int, o_pt_host); VIEW(d_pt_x, float, o_x); VIEW(d_pt_y, float, o_y); VIEW(d_pt_idz, float, o_idz); VIEW(d_pt_priorF, float, o_prior);
         VIEW(d_pt_mrb, float, o_mrb); VIEW(d_pt_idh, float, o_idh); VIEW(d_pt_num_good, int, o_ng); VIEW(d_pt_idepth, double, o_id);
         VIEW(d_r_point, int, o_rp); VIEW(d_r_host, uint8_t, o_rh); VIEW(d_r_target, uint8_t, o_rt);
-        VIEW(d_acc_chunk_bin, int, o_cb); VIEW(d_acc_chunk_begin, int, o_cbeg); VIEW(d_acc_chunk_count, int, o_ccnt); VIEW(d_bin_chunk_begin, int, o_bcb);
+        VIEW(d_res_bin_begin, int, o_rbb);
         VIEW(d_sc_chunk_host, int, o_sh); VIEW(d_sc_chunk_begin, int, o_sbeg); VIEW(d_sc_chunk_count, int, o_scnt); VIEW(d_host_chunk_begin, int, o_hcb);
 #undef VIEW
         lap("bdw.upload");
@@ -822,7 +844,8 @@ public:
         DevWin &w = dw;
         memset(&w, 0, sizeof(w));
         w.N = N; w.P = P; w.R = R; w.W = W; w.H = H; w.n = n; w.newest_begin = newest_begin;
-        w.n_lin_blocks = n_lin_blocks; w.n_acc_chunks = n_acc_chunks; w.n_sc_chunks = n_sc_chunks;
+        w.n_chunks = n_chunks; w.n_sc_chunks = n_sc_chunks;
+        w.tiles_x = tiles_x; w.tiles_y = tiles_y; w.n_tiles = n_tiles;
         w.fx = fx; w.fy = fy; w.cx = cx; w.cy = cy; w.fxi = 1.0 / fx; w.fyi = 1.0 / fy;
         w.huber = cfg.huber_threshold; w.cth = cfg.outlier_th_sum; w.scaleF = cfg.scale_f; w.scaleC = cfg.scale_c;
         w.scaleA = cfg.scale_light_a; w.scaleB = cfg.scale_light_b; w.scaleT = cfg.scale_translation; w.scaleR = cfg.scale_rotation;
@@ -834,12 +857,15 @@ public:
         w.pt_colors = d_pt_colors.p; w.pt_weights = d_pt_weights.p; w.pt_priorF = d_pt_priorF.p;
         w.pt_Hdd = d_pt_Hdd.p; w.pt_bd = d_pt_bd.p; w.pt_Hcd = d_pt_Hcd.p; w.pt_HdiF = d_pt_HdiF.p; w.pt_bdSumF = d_pt_bdSumF.p; w.pt_idepth_hessian = d_pt_idh.p; w.pt_max_rel_bs = d_pt_mrb.p;
         w.pt_num_good = d_pt_num_good.p; w.pt_ngood_cur = d_pt_ngood_cur.p; w.pt_step = d_pt_step.p;
-        w.r_point = d_r_point.p; w.r_host = d_r_host.p; w.r_target = d_r_target.p;
+        w.r_point = d_r_point.p; w.r_host = d_r_host.p; w.r_target = d_r_target.p; w.res_bin_begin = d_res_bin_begin.p;
+        w.bin_key = d_bin_key.p; w.bin_hist = d_bin_hist.p; w.bin_offs = d_bin_offs.p; w.job_of_tile = d_job_of_tile.p; w.job_desc = d_job_desc.p;
+        w.r_pht = d_r_pht.p; w.r_job = d_r_job.p; w.r_src = d_r_src.p; w.seg_cnt = d_seg_cnt.p; w.seg_base = d_seg_base.p; w.seg_hdr = d_seg_hdr.p; w.seg_t_begin = d_seg_t_begin.p;
+        w.bin_ticket = d_bin_ticket.p; w.fin_state = d_fin_state.p; w.fin_alive = d_fin_alive.p; w.fin_energy = d_fin_energy.p;
+        w.tma_on = encode_tile_maps() ? 1 : 0;
         w.r_state[0] = d_r_state0.p; w.r_state[1] = d_r_state1.p; w.r_energy[0] = d_r_energy0.p; w.r_energy[1] = d_r_energy1.p; w.r_good[0] = d_r_good0.p; w.r_good[1] = d_r_good1.p;
         w.r_new_state = d_r_new_state.p; w.r_new_energy = d_r_new_energy.p; w.r_new_energy_wo = d_r_new_energy_wo.p; w.r_alive = d_r_alive.p; w.r_center = d_r_center.p;
         w.rj = d_rj.p; w.T[0] = d_T0.p; w.T[1] = d_T1.p; w.dbg = want_dbg ? d_dbg.p : nullptr;
         w.energy_part = d_energy_part.p; w.acc_part[0] = d_acc0.p; w.acc_part[1] = d_acc1.p;
-        w.acc_chunk_bin = d_acc_chunk_bin.p; w.acc_chunk_begin = d_acc_chunk_begin.p; w.acc_chunk_count = d_acc_chunk_count.p; w.bin_chunk_begin = d_bin_chunk_begin.p;
         w.sc_part = d_sc_part.p; w.sc_stride = sc_stride; w.sc_chunk_host = d_sc_chunk_host.p; w.sc_chunk_begin = d_sc_chunk_begin.p; w.sc_chunk_count = d_sc_chunk_count.p;
         w.host_chunk_begin = d_host_chunk_begin.p;
         w.st_out = d_st_out.p; w.sys = d_sys.p; w.x = d_x.p; w.xAd = d_xAd.p;
@@ -866,6 +892,35 @@ public:
         }
         dirty = false;
         return CMLBA_OK;
+    }
+
+    // One CUtensorMap per window frame for the TMA box loads of linearize_tile_kernel: the image (H rows of W float4 texels) seen as a
+    // 2-D tensor of 8-byte elements (2W x H; a 16-byte element type does not exist), box = (2 * LT_BOX_W) x LT_BOX_H = 46 080 B,
+    // out-of-bounds elements zero-filled.  cuTensorMapEncodeTiled comes through cudaGetDriverEntryPoint (libcuda is not linked).
+    // false (-> every tap is read from global memory) if the driver entry point is missing, an encode fails, or CMLBA_NO_TMA is set.
+    bool encode_tile_maps() {
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        static bool tried = false;
+        if (!tried) {
+            tried = true;
+            void *fp = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) encode = (EncodeFn) fp;
+            cudaGetLastError();
+        }
+        if (!encode || getenv("CMLBA_NO_TMA")) return false;
+        for (size_t i = 0; i < frames_.size(); i++) {
+            const cuuint64_t gdim[2] = {(cuuint64_t) 2 * W, (cuuint64_t) H};
+            const cuuint64_t gstr[1] = {(cuuint64_t) W * 16};
+            const cuuint32_t box[2] = {2 * LT_BOX_W, LT_BOX_H};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult rc = encode(&tile_maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, frames_[i].d_img, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc != CUDA_SUCCESS) return false;
+        }
+        return true;
     }
 
     // 7x7 symmetric eigen-decomposition (cyclic Jacobi), eigenvectors in columns of V
@@ -1021,6 +1076,12 @@ public:
         // resetOOB on every active residual (BA:766-779, DSOResidual.h:81-86), empty Schur tables
         reset_window_kernel<<<148 * 4, 256, 0, stream>>>(dw); launches++;
         pairs_kernel<<<(N * N + 63) / 64, 64, 0, stream>>>(dw); launches++;
+        if (dw.R > 0) {   // tile binning at the poses this run() starts from: residuals sorted by (target, tile, host)
+            CK(cudaMemsetAsync(d_bin_hist.p, 0, (size_t) N * dw.n_tiles * N * sizeof(int), stream));
+            bin_count_kernel<<<(dw.R + 255) / 256, 256, 0, stream>>>(dw); launches++;
+            bin_scatter_kernel<<<N * N, 256, (size_t) 8 * dw.n_tiles * sizeof(int), stream>>>(dw); launches++;
+            bin_segments_kernel<<<(dw.n_chunks + 7) / 8, 256, 0, stream>>>(dw); launches++;
+        }
         CK(cudaGetLastError());
         lap("prep.upload_reset");
         prepared = true;
@@ -1034,8 +1095,20 @@ public:
 
     void launch_linearize(int fix, int respect_done) {
         if (dw.R == 0) return;
-        if (want_dbg) linearize_kernel<true><<<dw.n_acc_chunks, LIN_THREADS, LIN_SMEM, stream>>>(dw, fix, respect_done);
-        else linearize_kernel<false><<<dw.n_acc_chunks, LIN_THREADS, LIN_SMEM, stream>>>(dw, fix, respect_done);
+        const int grid = std::min(n_sm, dw.n_chunks);          // persistent CTAs: one per SM, a contiguous range of warp passes each
+        dw.lt_mode = lt_mode; dw.lt_exact = lt_exact;
+#define LT_LAUNCH(CW, ST)                                                                                                                                      \
+    do {                                                                                                                                                       \
+        if (want_dbg) linearize_tile_kernel<true, CW, ST><<<grid, (CW + 1) * 32, lt_smem_bytes(dw.N, CW, ST), stream>>>(dw, tile_maps, fix, respect_done);    \
+        else linearize_tile_kernel<false, CW, ST><<<grid, (CW + 1) * 32, lt_smem_bytes(dw.N, CW, ST), stream>>>(dw, tile_maps, fix, respect_done);            \
+    } while (0)
+        switch (lt_variant) {
+            case 1: LT_LAUNCH(7, 4); break;
+            case 2: LT_LAUNCH(15, 3); break;
+            case 3: LT_LAUNCH(15, 2); break;
+            default: LT_LAUNCH(11, 3); break;
+        }
+#undef LT_LAUNCH
         launches++;
     }
     void launch_post(int mode, int respect_done) {
@@ -1129,7 +1202,7 @@ public:
         size_t off = 0;
         auto take = [&](size_t nb) { const size_t o = (off + 15) & ~(size_t) 15; off = o + nb; return o; };
         const size_t o_fd = take(N * sizeof(FrameDev)), o_c = take(sizeof(Ctrl)), o_id = take((size_t) P * 8), o_idz = take((size_t) P * 4), o_idh = take((size_t) P * 4),
-                     o_mrb = take((size_t) P * 4), o_ng = take((size_t) P * 4), o_al = take(R), o_s0 = take(R), o_s1 = take(R), o_e0 = take((size_t) R * 4), o_e1 = take((size_t) R * 4);
+                     o_mrb = take((size_t) P * 4), o_ng = take((size_t) P * 4), o_al = take(R), o_s0 = take(R), o_e0 = take((size_t) R * 4);
         CK(fin_h.reserve(off));
         char *hb = fin_h.p;
         CK(cudaMemcpyAsync(hb + o_fd, d_frames.p, N * sizeof(FrameDev), cudaMemcpyDeviceToHost, stream));
@@ -1142,11 +1215,10 @@ public:
             CK(cudaMemcpyAsync(hb + o_ng, d_pt_num_good.p, (size_t) P * 4, cudaMemcpyDeviceToHost, stream));
         }
         if (R) {
-            CK(cudaMemcpyAsync(hb + o_al, d_r_alive.p, R, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(hb + o_s0, d_r_state0.p, R, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(hb + o_s1, d_r_state1.p, R, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(hb + o_e0, d_r_energy0.p, (size_t) R * 4, cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(hb + o_e1, d_r_energy1.p, (size_t) R * 4, cudaMemcpyDeviceToHost, stream));
+            // final residual states in the host's own order (written by the fixLinearization pass)
+            CK(cudaMemcpyAsync(hb + o_al, d_fin_alive.p, R, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_s0, d_fin_state.p, R, cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(hb + o_e0, d_fin_energy.p, (size_t) R * 4, cudaMemcpyDeviceToHost, stream));
         }
         CK(cudaStreamSynchronize(stream));
         CK(cudaGetLastError());
@@ -1157,8 +1229,8 @@ public:
         const float *idz = reinterpret_cast<const float *>(hb + o_idz), *idh = reinterpret_cast<const float *>(hb + o_idh), *mrb = reinterpret_cast<const float *>(hb + o_mrb);
         const int *ng = reinterpret_cast<const int *>(hb + o_ng);
         const uint8_t *alive = reinterpret_cast<const uint8_t *>(hb + o_al);
-        const uint8_t *st = reinterpret_cast<const uint8_t *>(hb + (c.cur ? o_s1 : o_s0));
-        const float *en = reinterpret_cast<const float *>(hb + (c.cur ? o_e1 : o_e0));
+        const uint8_t *st = reinterpret_cast<const uint8_t *>(hb + o_s0);
+        const float *en = reinterpret_cast<const float *>(hb + o_e0);
         for (int i = 0; i < N; i++) {
             FrameHost &f = frames_[i]; const FrameDev &d = fd[i];
             for (int k = 0; k < 10; k++) { f.state[k] = d.state[k]; f.state_zero[k] = d.state_zero[k]; }
@@ -1336,10 +1408,20 @@ public:
         const int cur = c.cur;
         if (name == "ctrl") return host_out(&c, sizeof(c), dst, cap, bytes);
         if (name == "pt_order") return host_out(pt_order.data(), P * sizeof(int), dst, cap, bytes);
-        if (name == "res_point") { const int *rp = up.host<int>(up_o_rp); std::vector<int> v(R); for (int i = 0; i < R; i++) v[i] = pt_order[rp[i]]; return host_out(v.data(), R * sizeof(int), dst, cap, bytes); }
-        if (name == "res_point_dev") return copy_out(d_r_point.p, R, dst, cap, bytes);
-        if (name == "res_host") return copy_out(d_r_host.p, R, dst, cap, bytes);
-        if (name == "res_target") return copy_out(d_r_target.p, R, dst, cap, bytes);
+        if (name == "res_point" || name == "res_point_dev" || name == "res_host" || name == "res_target") {   // decoded from the tile-sorted order of the device
+            std::vector<uint32_t> pht(R);
+            if (R) CK(cudaMemcpy(pht.data(), d_r_pht.p, (size_t) R * 4, cudaMemcpyDeviceToHost));
+            if (name == "res_point" || name == "res_point_dev") {
+                std::vector<int> v(R);
+                for (int i = 0; i < R; i++) { const int dp = (int) (pht[i] & 0xffffffu); v[i] = name == "res_point" ? pt_order[dp] : dp; }
+                return host_out(v.data(), R * sizeof(int), dst, cap, bytes);
+            }
+            std::vector<uint8_t> v(R);
+            for (int i = 0; i < R; i++) v[i] = (uint8_t) (name == "res_host" ? ((pht[i] >> 24) & 15u) : (pht[i] >> 28));
+            return host_out(v.data(), R, dst, cap, bytes);
+        }
+        if (name == "res_src") return copy_out(d_r_src.p, R, dst, cap, bytes);
+        if (name == "res_job") return copy_out(d_r_job.p, R, dst, cap, bytes);
         if (name == "res_state") return copy_out(cur ? d_r_state1.p : d_r_state0.p, R, dst, cap, bytes);
         if (name == "res_state_cand") return copy_out(cur ? d_r_state0.p : d_r_state1.p, R, dst, cap, bytes);
         if (name == "res_energy") return copy_out(cur ? d_r_energy1.p : d_r_energy0.p, R, dst, cap, bytes);
@@ -1377,10 +1459,13 @@ public:
         if (name == "acc" || name == "acc_cand") {   // per bin (t*N+h) packed 96 doubles, chunk partials summed in order
             const bool cand = name == "acc_cand";
             const float *src = (cur ^ (cand ? 1 : 0)) ? d_acc1.p : d_acc0.p;
-            std::vector<float> part((size_t) n_acc_chunks * ACC_N);
-            if (n_acc_chunks) CK(cudaMemcpy(part.data(), src, part.size() * 4, cudaMemcpyDeviceToHost));
+            int n_seg = 0;
+            if (n_chunks) CK(cudaMemcpy(&n_seg, d_seg_base.p + n_chunks, sizeof(int), cudaMemcpyDeviceToHost));
+            std::vector<float> part((size_t) n_seg * ACC_N);
+            std::vector<uint8_t> hdr(n_seg);
+            if (n_seg) { CK(cudaMemcpy(part.data(), src, part.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hdr.data(), d_seg_hdr.p, n_seg, cudaMemcpyDeviceToHost)); }
             std::vector<double> acc((size_t) N * N * ACC_N, 0.0);
-            for (int b = 0; b < N * N; b++) for (int ch = h_bin_chunk_begin[b]; ch < h_bin_chunk_begin[b + 1]; ch++) for (int k = 0; k < ACC_N; k++) acc[(size_t) b * ACC_N + k] += part[(size_t) ch * ACC_N + k];
+            for (int sg = 0; sg < n_seg; sg++) { const int b = (hdr[sg] >> 4) * N + (hdr[sg] & 15); for (int k = 0; k < ACC_N; k++) acc[(size_t) b * ACC_N + k] += part[(size_t) sg * ACC_N + k]; }
             return host_out(acc.data(), acc.size() * 8, dst, cap, bytes);
         }
         if (name == "sc") {   // per host: D[(8N)^2] E[32N] EB[8N] Hcc[16] bc[4] doubles

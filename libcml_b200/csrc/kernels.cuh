@@ -1,7 +1,7 @@
 // kernels.cuh -- hand-written sm_100a kernels of the photometric-BA hot path.
 //
 // Reference behaviour restated on the device (file:line under /root/reference/src/cml):
-//   linearize_kernel    optimization/dso/DSOBundleAdjustment.cpp:62-316 (linearize) + :2051-2093 (applyRes, as a
+//   linearize_tile_kernel (linearize.cuh)  optimization/dso/DSOBundleAdjustment.cpp:62-316 (linearize) + :2051-2093 (applyRes, as a
 //                       double-buffered candidate) + :1568-1599 (fixLinearization bookkeeping)
 //   accumulate_kernel   :1648-1779 (addToHessianTop ACTIVE) + MatrixAccumulators.h:776-937 (AccumulatorApprox)
 //   schur_kernel        :1880-1937 (addToHessianSC)
@@ -22,6 +22,9 @@ constexpr int DBG_STRIDE = 52;  // resF[8] JIdx[16] JabF[16] Jpdd[2] JIdx2[3] Ja
 
 __constant__ int c_sx[8] = {0, -1, 1, -2, 0, 2, -1, 0};   // PredefinedPattern::star8 (types.h:1395-1407)
 __constant__ int c_sy[8] = {-2, -1, -1, 0, 0, 0, 1, 2};
+// the same table as compile-time constants (folded after unrolling; the __constant__ copy costs one LDC per use)
+__host__ __device__ __forceinline__ constexpr int pat_sx(int i) { return i == 0 ? 0 : i == 1 ? -1 : i == 2 ? 1 : i == 3 ? -2 : i == 4 ? 0 : i == 5 ? 2 : i == 6 ? -1 : 0; }
+__host__ __device__ __forceinline__ constexpr int pat_sy(int i) { return i == 0 ? -2 : i == 1 ? -1 : i == 2 ? -1 : i == 3 ? 0 : i == 4 ? 0 : i == 5 ? 0 : i == 6 ? 1 : 2; }
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -62,6 +65,7 @@ __device__ inline void pair_precompute(const DevWin &w, int h, int t) {
     pp.b = ft.state_scaled[7] - a * fh.state_scaled[7];
     pp.b0 = (float) (fh.state_zero[7] * (double) w.scaleB);
     pp.pad = 0.f;
+    for (int k = 0; k < 3; k++) { pp.Af[k] = (float) (T.R[3 * k] * w.fxi); pp.Bf[k] = (float) (T.R[3 * k + 1] * w.fyi); }
 }
 
 __global__ void pairs_kernel(const DevWin w) {
@@ -84,27 +88,8 @@ __global__ void set_evalpt_newest_kernel(const DevWin w) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// HOT LOOPS 1+2 fused: linearize (BA:62-316) + applyRes (BA:2051-2093) + addToHessianTop(ACTIVE) (BA:1648-1779).
-// One CTA = one chunk of <=128 residuals of ONE (host,target) bin; one thread per residual.
-//   phase 1  projection of the 8 pattern pixels in fp64 (the reference's scalar_t)
-//   phase 2  warp-cooperative tap fetch: for residual j of the warp, lane l fetches tap (pixel l>>2, corner l&3) with one
-//            16-byte cp.async into the warp's staging rows.  One warp-wide request then covers the 32 taps of ONE residual
-//            (6-8 distinct 128-byte lines) instead of one tap of 32 unrelated residuals (32 lines): the L1 wavefront count,
-//            which bounded the thread-per-tap version, drops ~4x, and DRAM still sees only the sectors that are needed.
-//   phase 3  every lane reads its own 32 taps back (row stride 33 float4: conflict-free LDS.128), fp32 bilinear sampling,
-//            Huber/gradient weights, the Jacobian record and the Schur row, exactly the reference's mixed precision
-//   phase 4  13x13 block [C4 | xi6 | a b | r] of the bin: the 91 products of every lane are summed over the warp by a
-//            transposing butterfly (31 shuffles per 32 entries, lane L ends up owning entry L), then over the 4 warps
-//            in fixed order -> acc_part[chunk] (fixed-order: bitwise reproducible)
-constexpr int TAP_ROW = 32;          // float4 per staged residual; column index is XOR-swizzled with the row (conflict-free without padding)
-constexpr size_t LIN_SMEM = (size_t) 32 * TAP_ROW * 16;   // 16 KB per warp-CTA: 13 CTAs fit one SM (228 KB, 1 KB reserved per CTA)
-
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
+// HOT LOOPS 1+2 fused: linearize (BA:62-316) + applyRes (BA:2051-2093) + addToHessianTop(ACTIVE) (BA:1648-1779) live in
+// linearize.cuh (linearize_tile_kernel: TMA-staged target tiles, one residual per lane, per-(host,target)-run partial blocks).
 // entry e (0..95) of the packed 13x13 block as a product of record fields; x = Jp_x[10], y = Jp_y[10], Q = JIdx2 * Jp,
 // B = the 2x3 top-right multipliers, BR = the 6 bottom-right sums.  e is a compile-time constant after unrolling.
 __device__ __forceinline__ float acc_entry(const int e, const float *x, const float *y, const float *Qx, const float *Qy, const float *Bx, const float *By, const float *BR) {
@@ -134,267 +119,9 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], const int la
     return v[0];
 }
 
-template <bool kDump>
-__global__ void __launch_bounds__(LIN_THREADS) linearize_kernel(const DevWin w, const int fix, const int respect_done) {
-    Ctrl *ctrl = w.ctrl;
-    if (respect_done && ctrl->done) return;
-    extern __shared__ __align__(16) unsigned char lin_smem[];
-    float4 *s_taps = reinterpret_cast<float4 *>(lin_smem);                         // [32 residuals][TAP_ROW], swizzled
-    int *s_offs = reinterpret_cast<int *>(lin_smem);                               // [8][32] texel offsets: consumed before the taps land (aliased)
-    const int chunk = blockIdx.x, tid = threadIdx.x, lane = tid;
-    const int begin = w.acc_chunk_begin[chunk], cnt = w.acc_chunk_count[chunk], bin = w.acc_chunk_bin[chunk];
-    const int t = bin / w.N, h = bin - t * w.N;
-    const PairPre &pp = w.pairs[h * w.N + t];                                      // warp-uniform: broadcast loads
-    const int cur = ctrl->cur, nxt = cur ^ 1;
-    const int r = begin + tid;
-    // all per-residual scalars are requested together (one exposed latency), then the point record
-    const bool in_chunk = tid < cnt;
-    const int r_ld = in_chunk ? r : begin;
-    const uint8_t alive_ld = w.r_alive[r_ld];
-    const int p = w.r_point[r_ld];
-    const uint8_t st = in_chunk ? w.r_state[cur][r_ld] : (uint8_t) RES_OOB;
-    const float e_old = w.r_energy[cur][r_ld];
-    uint8_t nst = w.r_new_state[r_ld];
-    float ne = w.r_new_energy[r_ld];
-    const bool valid = in_chunk && alive_ld;
-    const double rho = w.pt_idepth[p];
-    const double xc = (double) w.pt_x[p], yc = (double) w.pt_y[p];
-    const float4 *colp = reinterpret_cast<const float4 *>(w.pt_colors + (size_t) p * 8);
-    const float4 *wtp = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
-    const float4 c0 = __ldg(colp), c1 = __ldg(colp + 1), w0 = __ldg(wtp), w1 = __ldg(wtp + 1);
-    double ret = 0.0;
-    uint8_t st_out = st;
-    float e_out = e_old, neo = -1.f;             // state_NewEnergyWithOutlier = -1 (BA:66)
-    bool good = false, sample = false;
-    float qx[8], qy[8];
-    double Pc0 = 0, Pc1 = 0, Pc2 = 1, Kuc = 0, Kvc = 0;
-    if (valid) {
-        ret = (double) e_old;                    // every early exit returns state_energy
-        if (st != RES_OOB) {
-            const double Wm2 = (double) ((float) w.W - 2.f), Hm2 = (double) ((float) w.H - 2.f);
-            const double R0 = pp.R[0], R1 = pp.R[1], R2 = pp.R[2], R3 = pp.R[3], R4 = pp.R[4], R5 = pp.R[5], R6 = pp.R[6], R7 = pp.R[7], R8 = pp.R[8];
-            const double tx = pp.t[0] * rho, ty = pp.t[1] * rho, tz = pp.t[2] * rho;
-            bool inb = true;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const double kx = (xc + (double) c_sx[i] - w.cx) * w.fxi;
-                const double ky = (yc + (double) c_sy[i] - w.cy) * w.fyi;
-                const double P0 = R0 * kx + R1 * ky + R2 + tx;
-                const double P1 = R3 * kx + R4 * ky + R5 + ty;
-                const double P2 = R6 * kx + R7 * ky + R8 + tz;
-                const double iP2 = 1.0 / P2;     // one reciprocal instead of two divisions (<= 1 ulp of fp64 before the cast to float)
-                const double Ku = (P0 * iP2) * w.fx + w.cx;
-                const double Kv = (P1 * iP2) * w.fy + w.cy;
-                inb = inb && (Ku >= 2.0 && Kv >= 2.0 && Ku < Wm2 && Kv < Hm2);
-                qx[i] = (float) Ku; qy[i] = (float) Kv;
-                if (i == 4) { Pc0 = P0; Pc1 = P1; Pc2 = P2; Kuc = Ku; Kvc = Kv; }
-            }
-            if (Kuc >= 2.0 && Kvc >= 2.0 && Kuc < Wm2 && Kvc < Hm2) {   // setCenterProjectedTo (BA:131)
-                w.r_center[r * 3 + 0] = (float) Kuc; w.r_center[r * 3 + 1] = (float) Kvc; w.r_center[r * 3 + 2] = (float) ((double) (float) (1.0 / Pc2) * rho);
-            }
-            if (!inb) nst = RES_OOB;             // setNewState(OOB) (BA:116, 210); state_NewEnergy keeps its old value
-            else sample = true;
-        }
-    }
-    // ---- phase 2: cooperative tap fetch of the target image (image/Array2D.h:265-286 reads (ix,iy) (ix+1,iy) (ix,iy+1) (ix+1,iy+1))
-    int *woffs = s_offs;                         // [pixel i][residual j]: lane j writes a column, lane l reads row l>>2
-    if (sample) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) woffs[i * 32 + lane] = (int) qy[i] * w.W + (int) qx[i];
-    }
-    __syncwarp();
-    const unsigned smask = __ballot_sync(0xffffffffu, sample);
-    {
-        const float4 *__restrict__ img = w.img[t] + ((lane & 1) + ((lane & 2) ? w.W : 0));
-        const int4 *orow = reinterpret_cast<const int4 *>(woffs + (lane >> 2) * 32);
-        int4 o[8];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) o[j4] = orow[j4];
-        __syncwarp();                                // every lane holds its 32 offsets: the table may be overwritten by the taps
-        // tap l of residual j lives at s_taps[j][l ^ j]
-#pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) {
-            if ((smask >> (4 * j4 + 0)) & 1u) cp_async16(s_taps + (4 * j4 + 0) * TAP_ROW + (lane ^ (4 * j4 + 0)), img + o[j4].x);
-            if ((smask >> (4 * j4 + 1)) & 1u) cp_async16(s_taps + (4 * j4 + 1) * TAP_ROW + (lane ^ (4 * j4 + 1)), img + o[j4].y);
-            if ((smask >> (4 * j4 + 2)) & 1u) cp_async16(s_taps + (4 * j4 + 2) * TAP_ROW + (lane ^ (4 * j4 + 2)), img + o[j4].z);
-            if ((smask >> (4 * j4 + 3)) & 1u) cp_async16(s_taps + (4 * j4 + 3) * TAP_ROW + (lane ^ (4 * j4 + 3)), img + o[j4].w);
-        }
-        cp_async_wait_all();
-    }
-    __syncwarp();
-    // ---- phase 3: per-residual sampling + Jacobians
-    float rec[RJ_STRIDE];
-    float trow[T_STRIDE];
-#pragma unroll
-    for (int k = 0; k < RJ_STRIDE; k++) rec[k] = 0.f;
-#pragma unroll
-    for (int k = 0; k < T_STRIDE; k++) trow[k] = 0.f;
-    if (sample) {
-        const float4 *mytaps = s_taps + lane * TAP_ROW;
-        const float col[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        const float wts[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        const float b0 = pp.b0;
-        const float sqrt_cth = sqrtf(w.cth);
-        float J00 = 0, J11 = 0, J10 = 0, A00 = 0, A01 = 0, A10 = 0, A11 = 0, B00 = 0, B01 = 0, B11 = 0, wJI2 = 0, E = 0;
-        float JIr0 = 0, JIr1 = 0, Jabr0 = 0, Jabr1 = 0, rr = 0;
-        bool finite = true;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float4 t00 = mytaps[(i * 4 + 0) ^ lane], t10 = mytaps[(i * 4 + 1) ^ lane], t01 = mytaps[(i * 4 + 2) ^ lane], t11 = mytaps[(i * 4 + 3) ^ lane];
-            const int ix = (int) qx[i], iy = (int) qy[i];
-            const float dx = qx[i] - (float) ix, dy = qy[i] - (float) iy;
-            const float dxdy = dx * dy;
-            const float w00 = 1.f - dx - dy + dxdy, w10 = dx - dxdy, w01 = dy - dxdy, w11 = dxdy;
-            const float I = t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
-            const float gx = t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
-            const float gy = t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
-            finite = finite && isfinite(I) && isfinite(gx) && isfinite(gy);
-            const float refReal = (float) (pp.a * (double) col[i] + pp.b);     // exposureTransition (BA:229)
-            const float res = I - refReal;
-            const float ar = fabsf(res);
-            // MUFU-based division / rsqrt / sqrt (<= 2 ulp, ~2e-7 relative; the parity tolerance is 1e-4)
-            float hw = ar < w.huber ? 1.f : __fdividef(w.huber, ar);           // BA:233
-            float wg = sqrt_cth * rsqrtf(w.cth + (gx * gx + gy * gy));         // BA:234  sqrt(c / (c + |grad|^2))
-            wg = 0.5f * (wg + wts[i]);                                         // BA:235
-            E += wg * wg * hw * res * res * (2.f - hw);                        // BA:237
-            if (hw < 1.f) hw = __fsqrt_rn(hw);
-            hw = hw * wg;
-            const float h1 = gx * hw, h2 = gy * hw, drdA = I - b0;
-            const float rF = res * hw;
-            const float ja = (w.optA ? drdA * hw : 0.f), jb = (w.optB ? hw : 0.f);   // BA:273-278 (zeroed after the sums below)
-            J00 += h1 * h1; J11 += h2 * h2; J10 += h1 * h2;
-            A00 += drdA * hw * h1; A01 += drdA * hw * h2; A10 += hw * h1; A11 += hw * h2;
-            B00 += drdA * drdA * hw * hw; B01 += drdA * hw * hw; B11 += hw * hw;
-            wJI2 += hw * hw * (h1 * h1 + h2 * h2);
-            JIr0 += rF * h1; JIr1 += rF * h2; Jabr0 += rF * ja; Jabr1 += rF * jb; rr += rF * rF;   // BA:1722-1729
-            if (kDump) {
-                float *d = w.dbg + (size_t) r * DBG_STRIDE;
-                d[i] = rF; d[8 + i] = h1; d[16 + i] = h2; d[24 + i] = ja; d[32 + i] = jb;
-            }
-        }
-        if (!finite) {
-            // BA:220-223 sets the *committed* state to OOB.  (The reference leaves a stale isActiveAndIsGoodNEW
-            // behind in that case; only reachable with NaN/Inf texels, we clear it.)
-            st_out = RES_OOB;
-        } else if (!isfinite(E)) {
-            nst = RES_OOB;               // BA:297-300
-        } else {
-            neo = E;
-            const float th = fmaxf(w.frames[h].energy_th, w.frames[t].energy_th);
-            if (E > th || wJI2 < 2.f) { E = th; nst = RES_OUTLIER; } else nst = RES_IN;   // BA:303-311
-            ne = E;
-            ret = (double) E;
-            if (nst == RES_IN) {
-                // ---- geometric Jacobians at the FEJ point (BA:120-188); note u,v are the UN-normalised P.xy (BA:121-122)
-                const float drescale = (float) (1.0 / Pc2);
-                const float new_idepth = (float) ((double) drescale * rho);
-                const float u = (float) Pc0, v = (float) Pc1;
-                const float fxf = (float) w.fx, fyf = (float) w.fy;
-                const double ud = (double) u, vd = (double) v, dr = (double) drescale;
-                const double klx = (xc - w.cx) * w.fxi, kly = (yc - w.cy) * w.fyi;      // KliP
-                const float Jpdd0 = (float) (dr * (pp.t0[0] - pp.t0[2] * ud) * (double) fxf);
-                const float Jpdd1 = (float) (dr * (pp.t0[1] - pp.t0[2] * vd) * (double) fyf);
-                double dCx[4], dCy[4];
-                dCx[2] = dr * (pp.R0[6] * ud - pp.R0[0]);
-                dCx[3] = (double) (fxf * drescale) * (pp.R0[7] * ud - pp.R0[1]) / (double) fyf;
-                dCx[0] = klx * dCx[2]; dCx[1] = kly * dCx[3];
-                dCy[2] = (double) (fyf * drescale) * (pp.R0[6] * vd - pp.R0[3]) / (double) fxf;
-                dCy[3] = dr * (pp.R0[7] * vd - pp.R0[4]);
-                dCy[0] = klx * dCy[2]; dCy[1] = kly * dCy[3];
-                const double sF = (double) w.scaleF, sC = (double) w.scaleC;
-                dCx[0] = (dCx[0] + ud) * sF; dCx[1] *= sF; dCx[2] = (dCx[2] + 1.0) * sC; dCx[3] *= sC;
-                dCy[0] *= sF; dCy[1] = (dCy[1] + vd) * sF; dCy[2] *= sC; dCy[3] = (dCy[3] + 1.0) * sC;
-                // record: x = [Jpdc_x | Jpdxi_x], y = [Jpdc_y | Jpdxi_y]
-                rec[0] = (float) dCx[0]; rec[1] = (float) dCx[1]; rec[2] = (float) dCx[2]; rec[3] = (float) dCx[3];
-                rec[4] = new_idepth * fxf; rec[5] = 0.f; rec[6] = -new_idepth * u * fxf; rec[7] = -u * v * fxf; rec[8] = (1.f + u * u) * fxf; rec[9] = -v * fxf;
-                rec[10] = (float) dCy[0]; rec[11] = (float) dCy[1]; rec[12] = (float) dCy[2]; rec[13] = (float) dCy[3];
-                rec[14] = 0.f; rec[15] = new_idepth * fyf; rec[16] = -new_idepth * v * fyf; rec[17] = -(1.f + v * v) * fyf; rec[18] = u * v * fyf; rec[19] = u * fyf;
-                if (w.marg_mode) {
-                    // MARGINALIZED accumulation (BA:1686-1690): the residual vector is res_toZeroF = resF - [JI*Jp Jab]*delta
-                    // (fixLinearization, BA:2210-2238).  Its moments follow from the sums above; JabF is zeroed for a fixed a / b.
-                    const float *dp = w.pair_delta + (size_t) (h * w.N + t) * 8;
-                    const float dF = (float) (rho - (double) w.pt_idepth_zero[p]);
-                    float jx = Jpdd0 * dF, jy = Jpdd1 * dF;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) { jx += rec[4 + k] * dp[k]; jy += rec[14 + k] * dp[k]; }
-                    const float da = dp[6], db = dp[7];
-                    const float a00 = w.optA ? A00 : 0.f, a01 = w.optA ? A01 : 0.f, a10 = w.optB ? A10 : 0.f, a11 = w.optB ? A11 : 0.f;
-                    const float b00 = w.optA ? B00 : 0.f, b01 = (w.optA && w.optB) ? B01 : 0.f, b11 = w.optB ? B11 : 0.f;
-                    const float cross = JIr0 * jx + JIr1 * jy + Jabr0 * da + Jabr1 * db;
-                    const float gx_ = J00 * jx + J10 * jy + a00 * da + a10 * db, gy_ = J10 * jx + J11 * jy + a01 * da + a11 * db;
-                    const float ga = a00 * jx + a01 * jy + b00 * da + b01 * db, gb = a10 * jx + a11 * jy + b01 * da + b11 * db;
-                    rr = rr - 2.f * cross + (jx * gx_ + jy * gy_ + da * ga + db * gb);
-                    JIr0 -= gx_; JIr1 -= gy_; Jabr0 -= ga; Jabr1 -= gb;
-                }
-                rec[20] = J00; rec[21] = J10; rec[22] = J11;                    // JIdx2
-                rec[23] = A00; rec[24] = A10; rec[25] = JIr0;                   // x-multipliers of columns a, b, r (BA:1740-1745)
-                rec[26] = A01; rec[27] = A11; rec[28] = JIr1;                   // y-multipliers
-                rec[29] = B00; rec[30] = B01; rec[31] = Jabr0; rec[32] = B11; rec[33] = Jabr1; rec[34] = rr;   // BA:1736-1738
-                // applyRes (BA:2066-2080) and the per-point sums of addToHessianTop (BA:1747-1750)
-                const float v0 = J00 * Jpdd0 + J10 * Jpdd1, v1 = J10 * Jpdd0 + J11 * Jpdd1;
-#pragma unroll
-                for (int k = 0; k < 6; k++) trow[k] = rec[4 + k] * v0 + rec[14 + k] * v1;
-                trow[6] = A00 * Jpdd0 + A01 * Jpdd1;
-                trow[7] = A10 * Jpdd0 + A11 * Jpdd1;
-                trow[8] = JIr0 * Jpdd0 + JIr1 * Jpdd1;                          // bd
-                trow[9] = v0 * Jpdd0 + v1 * Jpdd1;                              // Hdd
-#pragma unroll
-                for (int k = 0; k < 4; k++) trow[10 + k] = rec[k] * v0 + rec[10 + k] * v1;   // Hcd
-                trow[14] = 1.f;
-                good = true;
-                if (kDump) {
-                    float *d = w.dbg + (size_t) r * DBG_STRIDE;
-                    d[40] = Jpdd0; d[41] = Jpdd1; d[42] = J00; d[43] = J10; d[44] = J11;
-                    d[45] = A00; d[46] = A01; d[47] = A10; d[48] = A11; d[49] = B00; d[50] = B01; d[51] = B11;
-                }
-                if (fix) {   // BA:1571-1592: relative baseline, numGoodResiduals
-                    const double Rk0 = pp.R[0] * klx + pp.R[1] * kly + pp.R[2], Rk1 = pp.R[3] * klx + pp.R[4] * kly + pp.R[5], Rk2 = pp.R[6] * klx + pp.R[7] * kly + pp.R[8];
-                    const double ix_ = (Rk0 / Rk2) * w.fx + w.cx, iy_ = (Rk1 / Rk2) * w.fy + w.cy;
-                    const double ddx = ix_ - Kuc, ddy = iy_ - Kvc;
-                    const float relBS = (float) (0.01 * sqrt(ddx * ddx + ddy * ddy));
-                    atomicMax(reinterpret_cast<int *>(w.pt_max_rel_bs + p), __float_as_int(relBS));
-                    atomicAdd(w.pt_num_good + p, 1);
-                }
-            }
-        }
-    }
-    if (valid) {
-        // applyRes (BA:2051-2093), as the candidate that becomes current when the step is accepted
-        if (st != RES_OOB && st_out != RES_OOB) { st_out = nst; e_out = ne; }
-        w.r_new_state[r] = nst; w.r_new_energy[r] = ne; w.r_new_energy_wo[r] = neo;
-        w.r_state[nxt][r] = st_out; w.r_energy[nxt][r] = e_out; w.r_good[nxt][r] = good ? 1 : 0;
-        if (kDump) {
-            float4 *rj4 = reinterpret_cast<float4 *>(w.rj + (size_t) r * RJ_STRIDE);
-#pragma unroll
-            for (int k = 0; k < RJ_STRIDE / 4; k++) rj4[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
-        }
-        float4 *t4 = reinterpret_cast<float4 *>(w.T[nxt] + ((size_t) p * w.N + t) * T_STRIDE);
-#pragma unroll
-        for (int k = 0; k < T_STRIDE / 4; k++) t4[k] = make_float4(trow[4 * k], trow[4 * k + 1], trow[4 * k + 2], trow[4 * k + 3]);
-        if (fix && !good) {                      // BA:1595-1598, 1623-1640: non-good residuals are deleted
-            w.r_alive[r] = 0;
-            atomicAdd(&ctrl->num_dropped, 1);
-        }
-    }
-    // ---- phase 4: 13x13 block of the bin (records of non-good residuals are all zero)
-    {
-        float Qx[10], Qy[10];
-        const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
-#pragma unroll
-        for (int k = 0; k < 10; k++) { Qx[k] = a00 * rec[k] + a01 * rec[10 + k]; Qy[k] = a01 * rec[k] + a11 * rec[10 + k]; }
-        float *out = w.acc_part[nxt] + (size_t) chunk * ACC_N;
-#pragma unroll
-        for (int g = 0; g < 3; g++) {
-            float v[32];
-#pragma unroll
-            for (int k = 0; k < 32; k++) v[k] = acc_entry(g * 32 + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
-            out[g * 32 + lane] = warp_transpose_sum(v, lane);
-        }
-    }
-    // chunk energy (fp64, fixed order)
-    const double es = warp_sum_d(ret);
-    if (lane == 0) w.energy_part[chunk] = es;
-}
+}  // namespace cmlba
+#include "linearize.cuh"
+namespace cmlba {
 
 // ------------------------------------------------------------------------------------------------
 // HOT LOOP 3: Schur complement of the inverse depths (addToHessianSC, BA:1880-1937).  One CTA per chunk of <=64
@@ -538,6 +265,7 @@ constexpr int ST_A_TT = 0, ST_A_IT = 64, ST_A_II = 128, ST_A_TC = 192, ST_A_IC =
               ST_S_JI = 296, ST_S_II = 360, ST_S_JC = 424, ST_S_IC = 456, ST_BS_J = 488, ST_BS_I = 496, ST_S_JK = 504;
 __host__ __device__ __forceinline__ int st_stride(int N) { return ST_S_JK + 64 * N; }
 constexpr int ST_THREADS = 512;
+constexpr int ST_LIST = 2048;    // partial-block indices compacted per batch (stitch_pair_kernel)
 
 __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
@@ -576,15 +304,44 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
         for (int c = cb; c < ce; c++, src += w.sc_stride) s += (double) __ldg(src);
         Dj[e] = s;                 // Dj, Ej, EBj are contiguous
     }
-    if (tid < 4 * ACC_N) {         // 13x13 block of bin (i -> j): four threads per entry over contiguous chunk ranges, fixed tree
-        const int bin = j * N + i, e = tid % ACC_N, q = tid / ACC_N;
-        const int b0 = w.bin_chunk_begin[bin], b1 = w.bin_chunk_begin[bin + 1], len = (b1 - b0 + 3) >> 2;
-        const int c0 = min(b0 + q * len, b1), c1 = min(c0 + len, b1);
-        const float *src = w.acc_part[cur] + (size_t) c0 * ACC_N + e;
-        double s = 0.0;
+    {   // 13x13 block of bin (i -> j): the partial blocks tagged (host i, target j) in seg_hdr.  The partials of one target are contiguous
+        // (seg_t_begin); the CTA compacts the matching indices batch-wise (ballot + warp counts), then four threads per entry sum
+        // contiguous parts of the list -- fixed order, no atomics.
+        __shared__ int s_list[ST_LIST];
+        __shared__ int s_wcnt[ST_THREADS / 32];
+        __shared__ int s_n;
+        const int sb = w.seg_t_begin[j], se = w.seg_t_begin[j + 1];
+        const uint8_t want = (uint8_t) (i | (j << 4));
+        const float *part = w.acc_part[cur];
+        const int e = tid % ACC_N, q = tid / ACC_N, lane = tid & 31, wid = tid >> 5;
+        double acc = 0.0;
+        int base = sb;
+        do {
+            if (tid == 0) s_n = 0;
+            __syncthreads();
+            while (base < se && s_n + ST_THREADS <= ST_LIST) {
+                const int k = base + tid;
+                const bool mt = k < se && w.seg_hdr[k] == want;
+                const unsigned bal = __ballot_sync(0xffffffffu, mt);
+                if (lane == 0) s_wcnt[wid] = __popc(bal);
+                __syncthreads();
+                int off = s_n;
+                for (int ww = 0; ww < wid; ww++) off += s_wcnt[ww];
+                if (mt) s_list[off + __popc(bal & ((1u << lane) - 1u))] = k;
+                __syncthreads();
+                if (tid == 0) { int t = 0; for (int ww = 0; ww < ST_THREADS / 32; ww++) t += s_wcnt[ww]; s_n += t; }
+                __syncthreads();
+                base += ST_THREADS;
+            }
+            const int n = s_n;
+            if (tid < 4 * ACC_N) {
+                const int len = (n + 3) >> 2, a = min(q * len, n), b = min(a + len, n);
 #pragma unroll 8
-        for (int c = c0; c < c1; c++, src += ACC_N) s += (double) __ldg(src);
-        Apart[tid] = s;
+                for (int k = a; k < b; k++) acc += (double) __ldg(part + (size_t) s_list[k] * ACC_N + e);
+            }
+            __syncthreads();
+        } while (base < se);
+        if (tid < 4 * ACC_N) Apart[tid] = acc;
     }
     for (int e = tid; e < N * 64; e += ST_THREADS) G[e] = w.AH[(size_t) (i * N) * 64 + e];
     for (int e = tid; e < NB; e += ST_THREADS) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
@@ -1130,7 +887,7 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
     }
     // energy: fixed-order sum of the block partials (multi-GPU: of the ranks' sums, all-gathered by pack_post_kernel)
     double e = 0.0;
-    if (!multi) for (int i = tid; i < w.n_lin_blocks; i += 1024) e += w.energy_part[i];
+    if (!multi) for (int i = tid; i < w.n_chunks; i += 1024) e += w.energy_part[i];
     else if (tid < w.world) e = w.post_recv[tid * rec_d];
     e = warp_sum_d(e);
     if ((tid & 31) == 0) s_red[tid >> 5] = e;
@@ -1271,7 +1028,7 @@ __global__ void __launch_bounds__(1024) pack_post_kernel(const DevWin w, const i
     const int tid = threadIdx.x;
     __shared__ double s_red[32];
     double e = 0.0;
-    for (int i = tid; i < w.n_lin_blocks; i += 1024) e += w.energy_part[i];
+    for (int i = tid; i < w.n_chunks; i += 1024) e += w.energy_part[i];
     e = warp_sum_d(e);
     if ((tid & 31) == 0) s_red[tid >> 5] = e;
     __syncthreads();

@@ -1,0 +1,637 @@
+// linearize.cuh -- the sampling kernel of the photometric-BA hot path and the device-side tile binning that feeds it.
+//
+// Reference behaviour restated on the device (file:line under /root/reference/src/cml):
+//   linearize_tile_kernel   optimization/dso/DSOBundleAdjustment.cpp:62-316 (linearize) + :2051-2093 (applyRes, as a double-buffered
+//                           candidate) + :1568-1599 (fixLinearization bookkeeping) + :1648-1779 (addToHessianTop ACTIVE / MARGINALIZED)
+//                           + MatrixAccumulators.h:776-937 (AccumulatorApprox); image/Array2D.h:265-286 (bilinear taps)
+//
+// Design (B200): the 8-pixel pattern of a residual reads a <= 6x6 texel footprint of the TARGET image.  Residuals are sorted on the
+// device, once per run(), by (target frame, 64x32 tile that holds the centre projection, host frame); a persistent CTA per SM then
+// walks a contiguous range of that order.  One producer warp streams the 72x40-texel boxes (tile + halo) of the tiles its CTA
+// needs through a 4-stage shared-memory ring with TMA (cp.async.bulk.tensor.2d + mbarrier complete_tx); eight consumer warps
+// (one residual per lane, 32 consecutive residuals per pass) take every bilinear tap from the staged tile.  A lane whose footprint
+// left its box (pose drift since the binning, strong warps) or whose tile is not in the ring reads its taps from global memory through
+// the same generic pointer, so correctness never depends on the binning.  HBM sees each image once per pass, in large boxes.
+//
+// Arithmetic: centre projection in fp64 (the reference's scalar_t); the 7 other pattern pixels as fp32 offsets from it,
+//   q_i - q_c = f (d_xy - (P_xy/P_z) d_z) / (P_z + d_z),  d = sx A + sy B,  A = R[:,0]/fx, B = R[:,1]/fy,
+// added to the centre kept as a float pair (hi, lo): |error| < 1.5e-6 px before the final rounding to float, i.e. the sample
+// position differs from the reference's by at most one float ulp in a few percent of the pixels (measured).  A residual with
+// a pixel closer than 1e-3 px to the in-bounds limits is re-projected exactly in fp64, so the OOB decision is the reference's.
+//
+// Accumulation: the 91 products of the 13x13 block are transposed through a per-warp scratch tile and summed per RUN of one
+// (host,target) pair inside the warp pass (the sort keeps such runs contiguous); one partial block per run goes to acc_part, with its
+// (h,t) tag in seg_hdr.  All orders are fixed: results are bitwise reproducible.
+#pragma once
+#include <cuda.h>
+
+#include "dev_types.h"
+
+namespace cmlba {
+
+struct alignas(64) TileMaps { CUtensorMap m[MAXF]; };   // one 2-D tensor map per window frame: rows of W float4 texels seen as 2W 8-byte elements
+
+// CW consumer warps (+1 producer warp), ST ring stages
+__host__ __device__ __forceinline__ size_t lt_smem_bytes(int N, int CW, int ST) {
+    return (size_t) ST * LT_TILE_BYTES + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long);
+}
+
+// ---- mbarrier / TMA (PTX ISA 8.x; SASS: SYNCS.*, UTMALDG)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded: a tile that never lands (bad tensor map) degrades the warp to global-memory taps instead of hanging the device
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, uint32_t parity) {
+#pragma unroll 1
+    for (int i = 0; i < (1 << 22); i++) if (mbar_try_wait(bar, parity)) return true;   // every failed try_wait has already slept for the hardware's time limit
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x),
+                 "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ float rcp_nr(float d) {      // MUFU.RCP + one Newton step: relative error ~1e-7 after rounding
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(d));
+    const float e = fmaf(-d, r, 1.f);
+    return fmaf(r, e, r);
+}
+
+// block-wide exclusive scan of one int per thread (256 threads); returns the exclusive prefix, *total = sum
+__device__ __forceinline__ int block_excl_scan_256(int v, int *total) {
+    __shared__ int s_w[8];
+    __shared__ int s_tot;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int k = 0; k < 8; k++) { const int t = s_w[k]; s_w[k] = run; run += t; } s_tot = run; }
+    __syncthreads();
+    const int res = inc - v + s_w[wid];
+    *total = s_tot;
+    __syncthreads();
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile binning, step 1: key of every residual (host order) = ((target * n_tiles + tile) * N + host), tile from the centre projection
+// at the current state; histogram with integer atomics (order-independent); the last CTA scans the histogram into bin_offs,
+// numbers the non-empty (target, tile) jobs and re-zeroes the histogram.
+__global__ void __launch_bounds__(256) bin_count_kernel(const DevWin w) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < w.R) {
+        const int p = w.r_point[i], h = w.r_host[i], t = w.r_target[i];
+        const PairPre &pp = w.pairs[h * w.N + t];
+        const double rho = w.pt_idepth[p];
+        const double kx = ((double) w.pt_x[p] - w.cx) * w.fxi, ky = ((double) w.pt_y[p] - w.cy) * w.fyi;
+        const double P0 = pp.R[0] * kx + pp.R[1] * ky + pp.R[2] + pp.t[0] * rho;
+        const double P1 = pp.R[3] * kx + pp.R[4] * ky + pp.R[5] + pp.t[1] * rho;
+        const double P2 = pp.R[6] * kx + pp.R[7] * ky + pp.R[8] + pp.t[2] * rho;
+        const double iz = 1.0 / P2;
+        double Ku = P0 * iz * w.fx + w.cx, Kv = P1 * iz * w.fy + w.cy;
+        int tx = 0, ty = 0;
+        if (Ku == Ku && Kv == Kv) {          // not NaN; infinities clamp
+            Ku = fmin(fmax(Ku, 0.0), (double) (w.W - 1)); Kv = fmin(fmax(Kv, 0.0), (double) (w.H - 1));
+            tx = (int) Ku / LT_TILE_W; ty = (int) Kv / LT_TILE_H;
+        }
+        const int key = ((t * w.n_tiles) + ty * w.tiles_x + tx) * w.N + h;
+        w.bin_key[i] = key;
+        atomicAdd(w.bin_hist + key, 1);
+    }
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(w.bin_ticket, 1) == (int) gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) w.bin_ticket[0] = 0;
+    // groups g = (target, tile) of N keys (one per host): exclusive scan of the counts (bin_offs) and numbering of the non-empty groups (tile jobs)
+    const int N = w.N, G = N * w.n_tiles;
+    int carry_c = 0, carry_j = 0;
+    for (int g0 = 0; g0 < G; g0 += 256) {
+        const int g = g0 + threadIdx.x;
+        int vals[MAXF];
+        int c = 0;
+#pragma unroll
+        for (int h = 0; h < MAXF; h++) { vals[h] = (g < G && h < N) ? __ldcg(w.bin_hist + (size_t) g * N + h) : 0; c += vals[h]; }
+        int tc, tj;
+        const int ec = block_excl_scan_256(c, &tc), ej = block_excl_scan_256(c > 0 ? 1 : 0, &tj);
+        if (g < G) {
+            int run = carry_c + ec;
+#pragma unroll
+            for (int h = 0; h < MAXF; h++) if (h < N) { w.bin_offs[(size_t) g * N + h] = run; run += vals[h]; }
+            if (c > 0) {
+                const int job = carry_j + ej, t = g / w.n_tiles, tile = g - t * w.n_tiles;
+                w.job_desc[job] = (uint32_t) t | ((uint32_t) (tile % w.tiles_x) << 4) | ((uint32_t) (tile / w.tiles_x) << 16);
+                w.job_of_tile[g] = job;
+            } else w.job_of_tile[g] = -1;
+        }
+        carry_c += tc; carry_j += tj;
+    }
+}
+
+// step 2: stable scatter into the sorted order.  One CTA per (target, host) bin: its residuals are contiguous in host order and it owns
+// every key of the bin.  Warp k takes the k-th eighth of the bin; per-warp tile counts (pass 1) are prefixed over the warps on top of
+// bin_offs, then every warp ranks its residuals inside their (target, tile, host) group by host order (pass 2) -- deterministic,
+// no atomics.
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const DevWin w) {
+    extern __shared__ int s_run[];           // [8 warps][n_tiles]
+    const int bin = blockIdx.x, N = w.N, t = bin / N, h = bin - t * N, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nt = w.n_tiles;
+    const int b0 = w.res_bin_begin[bin], b1 = w.res_bin_begin[bin + 1];
+    if (b0 >= b1) return;
+    const int per = (((b1 - b0 + 7) >> 3) + 31) & ~31;
+    const int a0 = min(b0 + wid * per, b1), a1 = min(a0 + per, b1);
+    for (int k = threadIdx.x; k < 8 * nt; k += 256) s_run[k] = 0;
+    __syncthreads();
+    int *mine = s_run + wid * nt;
+    for (int base = a0; base < a1; base += 32) {           // pass 1: how many residuals of my slice fall into every tile
+        const int i = base + lane;
+        const bool valid = i < a1;
+        const int tile = valid ? (w.bin_key[i] / N) % nt : -1 - lane;      // invalid lanes match nobody
+        const unsigned m = __match_any_sync(0xffffffffu, tile);
+        if (valid && (m & ((1u << lane) - 1u)) == 0) mine[tile] += __popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int tile = threadIdx.x; tile < nt; tile += 256) {
+        int run = w.bin_offs[((size_t) t * nt + tile) * N + h];
+        for (int k = 0; k < 8; k++) { const int c = s_run[k * nt + tile]; s_run[k * nt + tile] = run; run += c; }
+    }
+    __syncthreads();
+    for (int base = a0; base < a1; base += 32) {           // pass 2: scatter
+        const int i = base + lane;
+        const bool valid = i < a1;
+        const int tile = valid ? (w.bin_key[i] / N) % nt : -1 - lane;
+        const int rp = valid ? w.r_point[i] : 0;
+        const unsigned m = __match_any_sync(0xffffffffu, tile);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        int pos = 0;
+        if (valid) pos = mine[tile] + rank;
+        __syncwarp();
+        if (valid && rank == 0) mine[tile] += __popc(m);
+        __syncwarp();
+        if (valid) {
+            w.r_pht[pos] = (uint32_t) rp | ((uint32_t) h << 24) | ((uint32_t) t << 28);
+            w.r_job[pos] = w.job_of_tile[t * nt + tile];
+            w.r_src[pos] = i;
+        }
+    }
+}
+
+// step 3: runs of one (host, target) pair inside every warp pass (32 consecutive sorted residuals) -> seg_cnt; the last CTA scans
+// them into seg_base (seg_base[n_chunks] = number of partial blocks one linearization writes).
+__global__ void __launch_bounds__(256) bin_segments_kernel(const DevWin w) {
+    const int lane = threadIdx.x & 31, c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c < w.n_chunks) {
+        const int r = min(c * 32 + lane, w.R - 1);
+        const uint32_t key = w.r_pht[r] >> 24, prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const unsigned m = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+        if (lane == 0) w.seg_cnt[c] = __popc(m);
+    }
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(w.bin_ticket + 1, 1) == (int) gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) w.bin_ticket[1] = 0;
+    const int per = (w.n_chunks + 255) / 256;
+    const int a0 = min((int) threadIdx.x * per, w.n_chunks), a1 = min(a0 + per, w.n_chunks);
+    int cnt = 0;
+    for (int k = a0; k < a1; k++) cnt += __ldcg(w.seg_cnt + k);
+    int tot;
+    int run = block_excl_scan_256(cnt, &tot);
+    for (int k = a0; k < a1; k++) { w.seg_base[k] = run; run += __ldcg(w.seg_cnt + k); }
+    if (threadIdx.x == 0) w.seg_base[w.n_chunks] = tot;
+    __syncthreads();
+    // first partial of every target: the sort keeps the host's target-major order, so target t starts at sorted residual res_bin_begin[t*N]
+    __shared__ int s_tb[MAXF + 1];
+    if ((int) threadIdx.x <= w.N) {
+        const int t = threadIdx.x;
+        int val = -1;
+        if (t < w.N && w.res_bin_begin[t * w.N] < w.res_bin_begin[(t + 1) * w.N]) {
+            const int rt = w.res_bin_begin[t * w.N], ch = rt >> 5, l = rt & 31;
+            int starts = 0;
+            uint32_t prev = 0;
+            for (int k = 0; k < l; k++) { const uint32_t key = w.r_pht[ch * 32 + k] >> 24; starts += (k == 0 || key != prev) ? 1 : 0; prev = key; }
+            val = w.seg_base[ch] + starts;
+        }
+        s_tb[t] = val;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nextv = tot;
+        for (int t = w.N; t >= 0; t--) { if (t == w.N || s_tb[t] < 0) s_tb[t] = nextv; nextv = s_tb[t]; w.seg_t_begin[t] = s_tb[t]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool kDump, int LT_CWARPS, int LT_STAGES>
+__global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel(const DevWin w, const __grid_constant__ TileMaps tm, const int fix, const int respect_done) {
+    constexpr int LT_THREADS = (LT_CWARPS + 1) * 32;
+    Ctrl *ctrl = w.ctrl;
+    if (respect_done && ctrl->done) return;
+    extern __shared__ __align__(1024) unsigned char lt_smem[];
+    unsigned char *ring = lt_smem;                                                                  // [LT_STAGES][LT_BOX_H][LT_BOX_W] float4
+    float *scratch = reinterpret_cast<float *>(lt_smem + (size_t) LT_STAGES * LT_TILE_BYTES);       // [LT_CWARPS][32][LT_SCR_STRIDE]
+    PairPre *s_pairs = reinterpret_cast<PairPre *>(scratch + LT_CWARPS * 32 * LT_SCR_STRIDE);       // [2 targets][N hosts]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(s_pairs + 2 * w.N);
+    unsigned long long *empty = full + LT_STAGES;
+    const int N = w.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (w.n_chunks + (int) gridDim.x - 1) / (int) gridDim.x;
+    const int c0 = blockIdx.x * per, c1 = min(c0 + per, w.n_chunks);
+    if (c0 >= c1) return;
+    const int r_first = c0 * 32, r_last = min(c1 * 32, w.R) - 1;
+    const int q0 = __ldg(w.r_job + r_first), q1 = __ldg(w.r_job + r_last);       // tile jobs of this CTA: [q0, q1], all non-empty
+    const int t_first = (int) (__ldg(w.r_pht + r_first) >> 28);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_CWARPS); }
+        mbar_fence_init();
+    }
+    {   // pair constants of the (at most two, almost always) targets this CTA meets
+        constexpr int PW = sizeof(PairPre) / 8;
+        double *dst = reinterpret_cast<double *>(s_pairs);
+        for (int i = threadIdx.x; i < 2 * N * PW; i += LT_THREADS) {
+            const int rec = i / PW, k = i - rec * PW, tt = rec / N, h = rec - tt * N, t = min(t_first + tt, N - 1);
+            dst[i] = reinterpret_cast<const double *>(w.pairs + h * N + t)[k];
+        }
+    }
+    __syncthreads();
+    // ---- producer warp: streams the boxes of tiles q0..q1 through the ring
+    if (warp == LT_CWARPS) {
+        if (lane == 0 && w.tma_on) {
+            for (int i = 0; i <= q1 - q0; i++) {
+                const int s = i % LT_STAGES, u = i / LT_STAGES;
+                if (u > 0 && !mbar_wait(empty + s, (uint32_t) ((u - 1) & 1))) break;
+                const uint32_t jd = __ldg(w.job_desc + q0 + i);
+                const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
+                mbar_expect_tx(full + s, LT_TILE_BYTES);
+                tma_load_2d(ring + (size_t) s * LT_TILE_BYTES, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
+            }
+        }
+        return;
+    }
+    // ---- consumer warps
+    const int cur = ctrl->cur, nxt = cur ^ 1;
+    float *scr = scratch + warp * 32 * LT_SCR_STRIDE;
+    bool tma_ok = w.tma_on != 0;
+    int rel = q0;                                    // next tile this warp has to release (warp-uniform)
+    const double Wm2 = (double) ((float) w.W - 2.f), Hm2 = (double) ((float) w.H - 2.f);
+    for (int c = c0 + warp; c < c1; c += LT_CWARPS) {
+        const int r = c * 32 + lane;
+        const bool in_chunk = r < w.R;
+        const int r_ld = in_chunk ? r : w.R - 1;
+        // all per-residual scalars are requested together (one exposed latency), then the point record
+        const uint32_t pht = __ldg(w.r_pht + r_ld);
+        const int job = __ldg(w.r_job + r_ld);
+        const int q_next = (c + LT_CWARPS < c1) ? __ldg(w.r_job + (c + LT_CWARPS) * 32) : 0x7fffffff;   // first tile of this warp's next pass
+        const uint8_t alive_ld = w.r_alive[r_ld];
+        const uint8_t st = in_chunk ? w.r_state[cur][r_ld] : (uint8_t) RES_OOB;
+        const float e_old = w.r_energy[cur][r_ld];
+        uint8_t nst = w.r_new_state[r_ld];
+        float ne = w.r_new_energy[r_ld];
+        const int p = (int) (pht & 0xffffffu), h = (int) ((pht >> 24) & 15u), t = (int) (pht >> 28);
+        const bool valid = in_chunk && alive_ld;
+        const uint32_t jd = __ldg(w.job_desc + job);
+        const double rho = w.pt_idepth[p];
+        const double xc = (double) w.pt_x[p], yc = (double) w.pt_y[p];
+        const float4 *colp = reinterpret_cast<const float4 *>(w.pt_colors + (size_t) p * 8);
+        const float4 *wtp = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
+        const float4 c0v = __ldg(colp), c1v = __ldg(colp + 1), w0v = __ldg(wtp), w1v = __ldg(wtp + 1);
+        const PairPre *ppp = (t - t_first < 2) ? s_pairs + (t - t_first) * N + h : w.pairs + h * N + t;
+        const PairPre &pp = *ppp;
+        // ---- ring bookkeeping: every warp waits for and releases EVERY tile of the CTA, in order (a release is only legal once
+        // the tile has landed: the arrival then belongs to the right phase of the stage's barrier)
+        const int q_lo = __shfl_sync(0xffffffffu, job, 0);
+        const int q_hi = min(__shfl_sync(0xffffffffu, job, 31), q_lo + LT_STAGES - 1);
+        if (tma_ok) {
+            bool ok = true;
+            for (; rel < q_lo; rel++) {
+                const int k = rel - q0;
+                ok = ok && mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + k % LT_STAGES);
+            }
+            for (int q = q_lo; q <= q_hi; q++) { const int k = q - q0; ok = ok && mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1)); }
+            tma_ok = __all_sync(0xffffffffu, ok);
+        }
+        if (w.lt_mode == 1) continue;
+        // where this lane's taps come from: its staged tile, or the image itself
+        bool use_smem = tma_ok && job <= q_hi;
+        const int box_x = (int) ((jd >> 4) & 0xfffu) * LT_TILE_W - LT_HALO, box_y = (int) (jd >> 16) * LT_TILE_H - LT_HALO;
+
+        double ret = 0.0;
+        uint8_t st_out = st;
+        float e_out = e_old, neo = -1.f;             // state_NewEnergyWithOutlier = -1 (BA:66)
+        bool good = false, sample = false;
+        float qx[8], qy[8];
+        double Pc0 = 0, Pc1 = 0, Pc2 = 1, Kuc = 0, Kvc = 0;
+        if (valid) {
+            ret = (double) e_old;                    // every early exit returns state_energy
+            if (st != RES_OOB) {
+                const double R0 = pp.R[0], R1 = pp.R[1], R2 = pp.R[2], R3 = pp.R[3], R4 = pp.R[4], R5 = pp.R[5], R6 = pp.R[6], R7 = pp.R[7], R8 = pp.R[8];
+                const double tx = pp.t[0] * rho, ty = pp.t[1] * rho, tz = pp.t[2] * rho;
+                {   // centre in fp64 (BA:107-118)
+                    const double kx = (xc - w.cx) * w.fxi, ky = (yc - w.cy) * w.fyi;
+                    Pc0 = R0 * kx + R1 * ky + R2 + tx;
+                    Pc1 = R3 * kx + R4 * ky + R5 + ty;
+                    Pc2 = R6 * kx + R7 * ky + R8 + tz;
+                }
+                const double iP2 = 1.0 / Pc2;        // one reciprocal instead of two divisions (<= 1 ulp of fp64 before the cast to float)
+                const double un = Pc0 * iP2, vn = Pc1 * iP2;
+                Kuc = un * w.fx + w.cx; Kvc = vn * w.fy + w.cy;
+                const bool cin = Kuc >= 2.0 && Kvc >= 2.0 && Kuc < Wm2 && Kvc < Hm2;
+                if (cin) {                           // setCenterProjectedTo (BA:131)
+                    w.r_center[(size_t) r * 3 + 0] = (float) Kuc; w.r_center[(size_t) r * 3 + 1] = (float) Kvc; w.r_center[(size_t) r * 3 + 2] = (float) ((double) (float) iP2 * rho);
+                }
+                // pattern pixels as fp32 offsets from the centre
+                const float kh_x = (float) Kuc, kh_y = (float) Kvc;
+                const float kl_x = (float) (Kuc - (double) kh_x), kl_y = (float) (Kvc - (double) kh_y);
+                const float uf = (float) un, vf = (float) vn, pz = (float) Pc2, fxf = (float) w.fx, fyf = (float) w.fy;
+                const float a0 = pp.Af[0], a1 = pp.Af[1], a2 = pp.Af[2], b0_ = pp.Bf[0], b1_ = pp.Bf[1], b2_ = pp.Bf[2];
+                bool all_in = cin, any_out = !cin;
+                const float lo_in = 2.f + 1e-3f, hx_in = (float) Wm2 - 1e-3f, hy_in = (float) Hm2 - 1e-3f, lo_out = 2.f - 1e-3f, hx_out = (float) Wm2 + 1e-3f, hy_out = (float) Hm2 + 1e-3f;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float sx = (float) pat_sx(i), sy = (float) pat_sy(i);     // compile-time constants after unrolling
+                    const float d0 = sx * a0 + sy * b0_, d1 = sx * a1 + sy * b1_, d2 = sx * a2 + sy * b2_;
+                    const float rc = rcp_nr(pz + d2);
+                    const float dx = (fmaf(-uf, d2, d0) * rc) * fxf, dy = (fmaf(-vf, d2, d1) * rc) * fyf;
+                    const float x = i == 4 ? kh_x : kh_x + (kl_x + dx), y = i == 4 ? kh_y : kh_y + (kl_y + dy);
+                    qx[i] = x; qy[i] = y;
+                    all_in = all_in && (x >= lo_in && y >= lo_in && x < hx_in && y < hy_in);
+                    any_out = any_out || (x < lo_out || y < lo_out || x >= hx_out || y >= hy_out);
+                }
+                bool inb = all_in;
+                if ((!all_in && !any_out) || w.lt_exact) {
+                    // a pixel within 1e-3 px of the limits (or a non-finite offset): the reference's own fp64 projection decides (BA:197-212)
+                    inb = true;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const double kx = (xc + (double) c_sx[i] - w.cx) * w.fxi, ky = (yc + (double) c_sy[i] - w.cy) * w.fyi;
+                        const double P0 = R0 * kx + R1 * ky + R2 + tx, P1 = R3 * kx + R4 * ky + R5 + ty, P2 = R6 * kx + R7 * ky + R8 + tz;
+                        const double iz = 1.0 / P2;
+                        const double Ku = (P0 * iz) * w.fx + w.cx, Kv = (P1 * iz) * w.fy + w.cy;
+                        inb = inb && (Ku >= 2.0 && Kv >= 2.0 && Ku < Wm2 && Kv < Hm2);
+                        qx[i] = (float) Ku; qy[i] = (float) Kv;
+                    }
+                }
+                if (!inb) nst = RES_OOB;             // setNewState(OOB) (BA:116, 210); state_NewEnergy keeps its old value
+                else sample = true;
+            }
+        }
+        // ---- taps: from the staged tile when the whole footprint is inside its box, else from the image (image/Array2D.h:265-286)
+        int ox = 0, oy = 0, pitch = w.W;
+        const float4 *tbase = w.img[t];
+        if (sample && use_smem) {
+            int lx = (int) qx[0], hx = lx, ly = (int) qy[0], hy = ly;
+#pragma unroll
+            for (int i = 1; i < 8; i++) { const int ix = (int) qx[i], iy = (int) qy[i]; lx = min(lx, ix); hx = max(hx, ix); ly = min(ly, iy); hy = max(hy, iy); }
+            use_smem = lx >= box_x && ly >= box_y && hx + 1 < box_x + LT_BOX_W && hy + 1 < box_y + LT_BOX_H;
+            if (use_smem) { ox = box_x; oy = box_y; pitch = LT_BOX_W; tbase = reinterpret_cast<const float4 *>(ring + (size_t) ((job - q0) % LT_STAGES) * LT_TILE_BYTES); }
+        }
+        // ---- per-residual sampling + Jacobians
+        float rec[RJ_STRIDE];
+        float trow[T_STRIDE];
+#pragma unroll
+        for (int k = 0; k < RJ_STRIDE; k++) rec[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < T_STRIDE; k++) trow[k] = 0.f;
+        float sI[8], sgx[8], sgy[8];
+        if (sample) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {      // all 32 taps first (the tile can go back to the producer right after)
+                const int ix = (int) qx[i], iy = (int) qy[i];
+                const float4 *tp = tbase + ((iy - oy) * pitch + (ix - ox));
+                const float4 t00 = tp[0], t10 = tp[1], t01 = tp[pitch], t11 = tp[pitch + 1];
+                const float dx = qx[i] - (float) ix, dy = qy[i] - (float) iy;
+                const float dxdy = dx * dy;
+                const float w00 = 1.f - dx - dy + dxdy, w10 = dx - dxdy, w01 = dy - dxdy, w11 = dxdy;
+                sI[i] = t00.x * w00 + t10.x * w10 + t01.x * w01 + t11.x * w11;
+                sgx[i] = t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
+                sgy[i] = t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
+            }
+        }
+        // the taps are in registers: tiles the warp's next pass does not need go back to the producer now, not at the end of the pass
+        __syncwarp();
+        if (tma_ok) {
+            const int upto = min(q_next, q_hi + 1);
+            for (; rel < upto; rel++) { if (lane == 0) mbar_arrive(empty + (rel - q0) % LT_STAGES); }
+        }
+        if (sample) {
+            const float col[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+            const float wts[8] = {w0v.x, w0v.y, w0v.z, w0v.w, w1v.x, w1v.y, w1v.z, w1v.w};
+            const float b0 = pp.b0;
+            const float sqrt_cth = sqrtf(w.cth);
+            float J00 = 0, J11 = 0, J10 = 0, A00 = 0, A01 = 0, A10 = 0, A11 = 0, B00 = 0, B01 = 0, B11 = 0, wJI2 = 0, E = 0;
+            float JIr0 = 0, JIr1 = 0, Jabr0 = 0, Jabr1 = 0, rr = 0;
+            bool finite = true;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float I = sI[i], gx = sgx[i], gy = sgy[i];
+                finite = finite && isfinite(I) && isfinite(gx) && isfinite(gy);
+                const float refReal = (float) (pp.a * (double) col[i] + pp.b);     // exposureTransition (BA:229)
+                const float res = I - refReal;
+                const float ar = fabsf(res);
+                // MUFU-based division / rsqrt / sqrt (<= 2 ulp, ~2e-7 relative; the parity tolerance is 1e-4)
+                float hw = ar < w.huber ? 1.f : __fdividef(w.huber, ar);           // BA:233
+                float wg = sqrt_cth * rsqrtf(w.cth + (gx * gx + gy * gy));         // BA:234  sqrt(c / (c + |grad|^2))
+                wg = 0.5f * (wg + wts[i]);                                         // BA:235
+                E += wg * wg * hw * res * res * (2.f - hw);                        // BA:237
+                if (hw < 1.f) hw = __fsqrt_rn(hw);
+                hw = hw * wg;
+                const float h1 = gx * hw, h2 = gy * hw, drdA = I - b0;
+                const float rF = res * hw;
+                const float ja = (w.optA ? drdA * hw : 0.f), jb = (w.optB ? hw : 0.f);   // BA:273-278 (zeroed after the sums below)
+                J00 += h1 * h1; J11 += h2 * h2; J10 += h1 * h2;
+                A00 += drdA * hw * h1; A01 += drdA * hw * h2; A10 += hw * h1; A11 += hw * h2;
+                B00 += drdA * drdA * hw * hw; B01 += drdA * hw * hw; B11 += hw * hw;
+                wJI2 += hw * hw * (h1 * h1 + h2 * h2);
+                JIr0 += rF * h1; JIr1 += rF * h2; Jabr0 += rF * ja; Jabr1 += rF * jb; rr += rF * rF;   // BA:1722-1729
+                if (kDump) {
+                    float *d = w.dbg + (size_t) r * DBG_STRIDE;
+                    d[i] = rF; d[8 + i] = h1; d[16 + i] = h2; d[24 + i] = ja; d[32 + i] = jb;
+                }
+            }
+            if (!finite) {
+                // BA:220-223 sets the *committed* state to OOB.  (The reference leaves a stale isActiveAndIsGoodNEW
+                // behind in that case; only reachable with NaN/Inf texels, we clear it.)
+                st_out = RES_OOB;
+            } else if (!isfinite(E)) {
+                nst = RES_OOB;               // BA:297-300
+            } else {
+                neo = E;
+                const float th = fmaxf(w.frames[h].energy_th, w.frames[t].energy_th);
+                if (E > th || wJI2 < 2.f) { E = th; nst = RES_OUTLIER; } else nst = RES_IN;   // BA:303-311
+                ne = E;
+                ret = (double) E;
+                if (nst == RES_IN) {
+                    // ---- geometric Jacobians at the FEJ point (BA:120-188); note u,v are the UN-normalised P.xy (BA:121-122)
+                    const float drescale = (float) (1.0 / Pc2);
+                    const float new_idepth = (float) ((double) drescale * rho);
+                    const float u = (float) Pc0, v = (float) Pc1;
+                    const float fxf = (float) w.fx, fyf = (float) w.fy;
+                    const double ud = (double) u, vd = (double) v, dr = (double) drescale;
+                    const double klx = (xc - w.cx) * w.fxi, kly = (yc - w.cy) * w.fyi;      // KliP
+                    const float Jpdd0 = (float) (dr * (pp.t0[0] - pp.t0[2] * ud) * (double) fxf);
+                    const float Jpdd1 = (float) (dr * (pp.t0[1] - pp.t0[2] * vd) * (double) fyf);
+                    double dCx[4], dCy[4];
+                    dCx[2] = dr * (pp.R0[6] * ud - pp.R0[0]);
+                    dCx[3] = (double) (fxf * drescale) * (pp.R0[7] * ud - pp.R0[1]) / (double) fyf;
+                    dCx[0] = klx * dCx[2]; dCx[1] = kly * dCx[3];
+                    dCy[2] = (double) (fyf * drescale) * (pp.R0[6] * vd - pp.R0[3]) / (double) fxf;
+                    dCy[3] = dr * (pp.R0[7] * vd - pp.R0[4]);
+                    dCy[0] = klx * dCy[2]; dCy[1] = kly * dCy[3];
+                    const double sF = (double) w.scaleF, sC = (double) w.scaleC;
+                    dCx[0] = (dCx[0] + ud) * sF; dCx[1] *= sF; dCx[2] = (dCx[2] + 1.0) * sC; dCx[3] *= sC;
+                    dCy[0] *= sF; dCy[1] = (dCy[1] + vd) * sF; dCy[2] *= sC; dCy[3] = (dCy[3] + 1.0) * sC;
+                    // record: x = [Jpdc_x | Jpdxi_x], y = [Jpdc_y | Jpdxi_y]
+                    rec[0] = (float) dCx[0]; rec[1] = (float) dCx[1]; rec[2] = (float) dCx[2]; rec[3] = (float) dCx[3];
+                    rec[4] = new_idepth * fxf; rec[5] = 0.f; rec[6] = -new_idepth * u * fxf; rec[7] = -u * v * fxf; rec[8] = (1.f + u * u) * fxf; rec[9] = -v * fxf;
+                    rec[10] = (float) dCy[0]; rec[11] = (float) dCy[1]; rec[12] = (float) dCy[2]; rec[13] = (float) dCy[3];
+                    rec[14] = 0.f; rec[15] = new_idepth * fyf; rec[16] = -new_idepth * v * fyf; rec[17] = -(1.f + v * v) * fyf; rec[18] = u * v * fyf; rec[19] = u * fyf;
+                    if (w.marg_mode) {
+                        // MARGINALIZED accumulation (BA:1686-1690): the residual vector is res_toZeroF = resF - [JI*Jp Jab]*delta
+                        // (fixLinearization, BA:2210-2238).  Its moments follow from the sums above; JabF is zeroed for a fixed a / b.
+                        const float *dp = w.pair_delta + (size_t) (h * N + t) * 8;
+                        const float dF = (float) (rho - (double) w.pt_idepth_zero[p]);
+                        float jx = Jpdd0 * dF, jy = Jpdd1 * dF;
+#pragma unroll
+                        for (int k = 0; k < 6; k++) { jx += rec[4 + k] * dp[k]; jy += rec[14 + k] * dp[k]; }
+                        const float da = dp[6], db = dp[7];
+                        const float a00 = w.optA ? A00 : 0.f, a01 = w.optA ? A01 : 0.f, a10 = w.optB ? A10 : 0.f, a11 = w.optB ? A11 : 0.f;
+                        const float b00 = w.optA ? B00 : 0.f, b01 = (w.optA && w.optB) ? B01 : 0.f, b11 = w.optB ? B11 : 0.f;
+                        const float cross = JIr0 * jx + JIr1 * jy + Jabr0 * da + Jabr1 * db;
+                        const float gx_ = J00 * jx + J10 * jy + a00 * da + a10 * db, gy_ = J10 * jx + J11 * jy + a01 * da + a11 * db;
+                        const float ga = a00 * jx + a01 * jy + b00 * da + b01 * db, gb = a10 * jx + a11 * jy + b01 * da + b11 * db;
+                        rr = rr - 2.f * cross + (jx * gx_ + jy * gy_ + da * ga + db * gb);
+                        JIr0 -= gx_; JIr1 -= gy_; Jabr0 -= ga; Jabr1 -= gb;
+                    }
+                    rec[20] = J00; rec[21] = J10; rec[22] = J11;                    // JIdx2
+                    rec[23] = A00; rec[24] = A10; rec[25] = JIr0;                   // x-multipliers of columns a, b, r (BA:1740-1745)
+                    rec[26] = A01; rec[27] = A11; rec[28] = JIr1;                   // y-multipliers
+                    rec[29] = B00; rec[30] = B01; rec[31] = Jabr0; rec[32] = B11; rec[33] = Jabr1; rec[34] = rr;   // BA:1736-1738
+                    // applyRes (BA:2066-2080) and the per-point sums of addToHessianTop (BA:1747-1750)
+                    const float v0 = J00 * Jpdd0 + J10 * Jpdd1, v1 = J10 * Jpdd0 + J11 * Jpdd1;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) trow[k] = rec[4 + k] * v0 + rec[14 + k] * v1;
+                    trow[6] = A00 * Jpdd0 + A01 * Jpdd1;
+                    trow[7] = A10 * Jpdd0 + A11 * Jpdd1;
+                    trow[8] = JIr0 * Jpdd0 + JIr1 * Jpdd1;                          // bd
+                    trow[9] = v0 * Jpdd0 + v1 * Jpdd1;                              // Hdd
+#pragma unroll
+                    for (int k = 0; k < 4; k++) trow[10 + k] = rec[k] * v0 + rec[10 + k] * v1;   // Hcd
+                    trow[14] = 1.f;
+                    good = true;
+                    if (kDump) {
+                        float *d = w.dbg + (size_t) r * DBG_STRIDE;
+                        d[40] = Jpdd0; d[41] = Jpdd1; d[42] = J00; d[43] = J10; d[44] = J11;
+                        d[45] = A00; d[46] = A01; d[47] = A10; d[48] = A11; d[49] = B00; d[50] = B01; d[51] = B11;
+                    }
+                    if (fix) {   // BA:1571-1592: relative baseline, numGoodResiduals
+                        const double Rk0 = pp.R[0] * klx + pp.R[1] * kly + pp.R[2], Rk1 = pp.R[3] * klx + pp.R[4] * kly + pp.R[5], Rk2 = pp.R[6] * klx + pp.R[7] * kly + pp.R[8];
+                        const double ix_ = (Rk0 / Rk2) * w.fx + w.cx, iy_ = (Rk1 / Rk2) * w.fy + w.cy;
+                        const double ddx = ix_ - Kuc, ddy = iy_ - Kvc;
+                        const float relBS = (float) (0.01 * sqrt(ddx * ddx + ddy * ddy));
+                        atomicMax(reinterpret_cast<int *>(w.pt_max_rel_bs + p), __float_as_int(relBS));
+                        atomicAdd(w.pt_num_good + p, 1);
+                    }
+                }
+            }
+        }
+        if (valid) {
+            // applyRes (BA:2051-2093), as the candidate that becomes current when the step is accepted
+            if (st != RES_OOB && st_out != RES_OOB) { st_out = nst; e_out = ne; }
+            w.r_new_state[r] = nst; w.r_new_energy[r] = ne; w.r_new_energy_wo[r] = neo;
+            w.r_state[nxt][r] = st_out; w.r_energy[nxt][r] = e_out; w.r_good[nxt][r] = good ? 1 : 0;
+            if (kDump) {
+                float4 *rj4 = reinterpret_cast<float4 *>(w.rj + (size_t) r * RJ_STRIDE);
+#pragma unroll
+                for (int k = 0; k < RJ_STRIDE / 4; k++) rj4[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+            }
+            float4 *t4 = reinterpret_cast<float4 *>(w.T[nxt] + ((size_t) p * N + t) * T_STRIDE);
+#pragma unroll
+            for (int k = 0; k < T_STRIDE / 4; k++) t4[k] = make_float4(trow[4 * k], trow[4 * k + 1], trow[4 * k + 2], trow[4 * k + 3]);
+            if (fix && !good) {                      // BA:1595-1598, 1623-1640: non-good residuals are deleted
+                w.r_alive[r] = 0;
+                atomicAdd(&ctrl->num_dropped, 1);
+            }
+        }
+        if (fix && in_chunk) {                       // final states in the host's residual order (finish_run reads these)
+            const int src = __ldg(w.r_src + r);
+            w.fin_state[src] = st_out; w.fin_energy[src] = e_out; w.fin_alive[src] = (valid && good) ? 1 : 0;
+        }
+        // ---- 13x13 blocks: one partial per run of a (host,target) pair in this pass (records of non-good residuals are all zero)
+        {
+            const uint32_t key_ht = pht >> 24, kprev = __shfl_up_sync(0xffffffffu, key_ht, 1);
+            const unsigned segmask = __ballot_sync(0xffffffffu, lane == 0 || key_ht != kprev);
+            const int sbase = __ldg(w.seg_base + c);
+            if ((segmask >> lane) & 1u) w.seg_hdr[sbase + __popc(segmask & ((1u << lane) - 1u))] = (uint8_t) key_ht;
+            float Qx[10], Qy[10];
+            const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
+#pragma unroll
+            for (int k = 0; k < 10; k++) { Qx[k] = a00 * rec[k] + a01 * rec[10 + k]; Qy[k] = a01 * rec[k] + a11 * rec[10 + k]; }
+            float *outp = w.acc_part[nxt] + (size_t) sbase * ACC_N + lane;
+#pragma unroll 1
+            for (int g = 0; g < 3; g++) {
+                float v[32];
+                if (g == 0) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) v[k] = acc_entry(k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
+                } else if (g == 1) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) v[k] = acc_entry(32 + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) v[k] = acc_entry(64 + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
+                }
+                __syncwarp();                        // the previous group's column sums are done with the scratch tile
+                float4 *row = reinterpret_cast<float4 *>(scr + lane * LT_SCR_STRIDE);
+#pragma unroll
+                for (int k4 = 0; k4 < 8; k4++) row[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+                __syncwarp();
+                unsigned m = segmask;
+                float *o = outp + g * 32;
+                while (m) {                          // lane L sums entry (g, L) over the lanes [j0, j1) of one run: an unrolled chain entered at 32 - len
+                    const int j0 = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int len = (m ? __ffs(m) - 1 : 32) - j0;
+                    const float *pa = scr + lane + (j0 + len - 32) * LT_SCR_STRIDE;      // chain position k reads lane row j0 + k - (32 - len)
+                    float s0 = 0.f, s1 = 0.f;
+#define LT_ROW2(k) case 32 - (k): s0 += pa[(k) * LT_SCR_STRIDE]; case 31 - (k): s1 += pa[((k) + 1) * LT_SCR_STRIDE];
+                    switch (len) { LT_ROW2(0) LT_ROW2(2) LT_ROW2(4) LT_ROW2(6) LT_ROW2(8) LT_ROW2(10) LT_ROW2(12) LT_ROW2(14) LT_ROW2(16) LT_ROW2(18) LT_ROW2(20) LT_ROW2(22) LT_ROW2(24)
+                                   LT_ROW2(26) LT_ROW2(28) LT_ROW2(30) default: break; }
+#undef LT_ROW2
+                    *o = s0 + s1;
+                    o += ACC_N;
+                }
+            }
+        }
+        // chunk energy (fp64, fixed order)
+        const double es = warp_sum_d(ret);
+        if (lane == 0) w.energy_part[c] = es;
+    }
+    // release the tiles this warp did not reach (every warp releases every tile; see above)
+    if (tma_ok) {
+        for (; rel <= q1; rel++) {
+            const int k = rel - q0;
+            if (!mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1))) break;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + k % LT_STAGES);
+        }
+    }
+}
+
+}  // namespace cmlba
