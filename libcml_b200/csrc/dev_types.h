@@ -120,6 +120,7 @@ struct DevWin {
     int *bin_offs;                 // [N * n_tiles * N] exclusive scan of the histogram
     int *job_of_tile;              // [N * n_tiles] index of the (t, tile) job among the non-empty ones
     uint32_t *job_desc;            // [jobs] t | tile_x << 4 | tile_y << 16
+    int *job_begin;                // [jobs + 1] first sorted residual of every tile job
     uint32_t *r_pht;               // [R] device point | host << 24 | target << 28
     int *r_job;                    // [R] tile job of the residual
     int *r_src;                    // [R] host-order index of the residual

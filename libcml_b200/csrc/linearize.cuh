@@ -33,7 +33,7 @@ struct alignas(64) TileMaps { CUtensorMap m[MAXF]; };   // one 2-D tensor map pe
 
 // CW consumer warps (+1 producer warp), ST ring stages
 __host__ __device__ __forceinline__ size_t lt_smem_bytes(int N, int CW, int ST) {
-    return (size_t) ST * LT_TILE_BYTES + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long);
+    return (size_t) ST * LT_TILE_BYTES + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float);
 }
 
 // ---- mbarrier / TMA (PTX ISA 8.x; SASS: SYNCS.*, UTMALDG)
@@ -42,6 +42,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) { 
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_n(unsigned long long *bar, uint32_t n) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(n) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+constexpr int LT_EMPTY_COUNT = 1 << 12;   // arrival count of a stage's "empty" barrier: the producer tops the users of a tile up to this number
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
@@ -135,10 +138,12 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const DevWin w) {
                 const int job = carry_j + ej, t = g / w.n_tiles, tile = g - t * w.n_tiles;
                 w.job_desc[job] = (uint32_t) t | ((uint32_t) (tile % w.tiles_x) << 4) | ((uint32_t) (tile / w.tiles_x) << 16);
                 w.job_of_tile[g] = job;
+                w.job_begin[job] = carry_c + ec;             // first sorted residual of the job
             } else w.job_of_tile[g] = -1;
         }
         carry_c += tc; carry_j += tj;
     }
+    if (threadIdx.x == 0) w.job_begin[carry_j] = carry_c;    // = R
 }
 
 // step 2: stable scatter into the sorted order.  One CTA per (target, host) bin: its residuals are contiguous in host order and it owns
@@ -249,6 +254,7 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
     PairPre *s_pairs = reinterpret_cast<PairPre *>(scratch + LT_CWARPS * 32 * LT_SCR_STRIDE);       // [2 targets][N hosts]
     unsigned long long *full = reinterpret_cast<unsigned long long *>(s_pairs + 2 * w.N);
     unsigned long long *empty = full + LT_STAGES;
+    float *s_th = reinterpret_cast<float *>(empty + LT_STAGES);                                     // [N] frameEnergyTH
     const int N = w.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (w.n_chunks + (int) gridDim.x - 1) / (int) gridDim.x;
     const int c0 = blockIdx.x * per, c1 = min(c0 + per, w.n_chunks);
@@ -257,9 +263,10 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
     const int q0 = __ldg(w.r_job + r_first), q1 = __ldg(w.r_job + r_last);       // tile jobs of this CTA: [q0, q1], all non-empty
     const int t_first = (int) (__ldg(w.r_pht + r_first) >> 28);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_CWARPS); }
+        for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_EMPTY_COUNT); }
         mbar_fence_init();
     }
+    if ((int) threadIdx.x < N) s_th[threadIdx.x] = w.frames[threadIdx.x].energy_th;
     {   // pair constants of the (at most two, almost always) targets this CTA meets
         constexpr int PW = sizeof(PairPre) / 8;
         double *dst = reinterpret_cast<double *>(s_pairs);
@@ -269,25 +276,37 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
         }
     }
     __syncthreads();
-    // ---- producer warp: streams the boxes of tiles q0..q1 through the ring
+    // ---- producer warp: streams the boxes of tiles q0..q1 through the ring.  A stage goes back to the producer when every warp pass
+    // that overlaps its tile (the passes are consecutive, so their number follows from the tile's residual range) has arrived on the
+    // stage's "empty" barrier; the producer tops that number up to the barrier's fixed arrival count when it issues the load.
     if (warp == LT_CWARPS) {
         if (lane == 0 && w.tma_on) {
             for (int i = 0; i <= q1 - q0; i++) {
                 const int s = i % LT_STAGES, u = i / LT_STAGES;
                 if (u > 0 && !mbar_wait(empty + s, (uint32_t) ((u - 1) & 1))) break;
                 const uint32_t jd = __ldg(w.job_desc + q0 + i);
+                const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
+                const int users = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
                 const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
+                mbar_arrive_n(empty + s, (uint32_t) (LT_EMPTY_COUNT - users));
                 mbar_expect_tx(full + s, LT_TILE_BYTES);
                 tma_load_2d(ring + (size_t) s * LT_TILE_BYTES, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
             }
         }
         return;
     }
+    // ---- consumer warps.  First, while the first tiles are in flight: pull everything this CTA will read per residual into L2
+    // (the per-residual arrays are contiguous; the point records hang off r_pht), so that no pass waits on HBM for its inputs.
+    for (int r = r_first + (int) threadIdx.x; r <= r_last; r += LT_CWARPS * 32) {
+        const int p = (int) (__ldg(w.r_pht + r) & 0xffffffu);
+        prefetch_l2(w.pt_idepth + p); prefetch_l2(w.pt_x + p); prefetch_l2(w.pt_y + p); prefetch_l2(w.pt_colors + (size_t) p * 8); prefetch_l2(w.pt_weights + (size_t) p * 8);
+        if ((r & 31) == 0) { prefetch_l2(w.r_job + r); prefetch_l2(w.r_energy[ctrl->cur] + r); prefetch_l2(w.r_new_energy + r); prefetch_l2(w.r_src + r); }
+        if ((r & 127) == 0) { prefetch_l2(w.r_alive + r); prefetch_l2(w.r_state[ctrl->cur] + r); prefetch_l2(w.r_new_state + r); }
+    }
     // ---- consumer warps
     const int cur = ctrl->cur, nxt = cur ^ 1;
     float *scr = scratch + warp * 32 * LT_SCR_STRIDE;
     bool tma_ok = w.tma_on != 0;
-    int rel = q0;                                    // next tile this warp has to release (warp-uniform)
     const double Wm2 = (double) ((float) w.W - 2.f), Hm2 = (double) ((float) w.H - 2.f);
     for (int c = c0 + warp; c < c1; c += LT_CWARPS) {
         const int r = c * 32 + lane;
@@ -296,12 +315,13 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
         // all per-residual scalars are requested together (one exposed latency), then the point record
         const uint32_t pht = __ldg(w.r_pht + r_ld);
         const int job = __ldg(w.r_job + r_ld);
-        const int q_next = (c + LT_CWARPS < c1) ? __ldg(w.r_job + (c + LT_CWARPS) * 32) : 0x7fffffff;   // first tile of this warp's next pass
         const uint8_t alive_ld = w.r_alive[r_ld];
         const uint8_t st = in_chunk ? w.r_state[cur][r_ld] : (uint8_t) RES_OOB;
         const float e_old = w.r_energy[cur][r_ld];
         uint8_t nst = w.r_new_state[r_ld];
         float ne = w.r_new_energy[r_ld];
+        const int sbase = __ldg(w.seg_base + c);
+        const int src = __ldg(w.r_src + r_ld);
         const int p = (int) (pht & 0xffffffu), h = (int) ((pht >> 24) & 15u), t = (int) (pht >> 28);
         const bool valid = in_chunk && alive_ld;
         const uint32_t jd = __ldg(w.job_desc + job);
@@ -312,22 +332,20 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
         const float4 c0v = __ldg(colp), c1v = __ldg(colp + 1), w0v = __ldg(wtp), w1v = __ldg(wtp + 1);
         const PairPre *ppp = (t - t_first < 2) ? s_pairs + (t - t_first) * N + h : w.pairs + h * N + t;
         const PairPre &pp = *ppp;
-        // ---- ring bookkeeping: every warp waits for and releases EVERY tile of the CTA, in order (a release is only legal once
-        // the tile has landed: the arrival then belongs to the right phase of the stage's barrier)
-        const int q_lo = __shfl_sync(0xffffffffu, job, 0);
-        const int q_hi = min(__shfl_sync(0xffffffffu, job, 31), q_lo + LT_STAGES - 1);
+        // ---- the tiles of this pass: [q_lo, q_last]; the first LT_STAGES of them can be in the ring together
+        const int q_lo = __shfl_sync(0xffffffffu, job, 0), q_last = __shfl_sync(0xffffffffu, job, 31);
+        const int q_hi = min(q_last, q_lo + LT_STAGES - 1);
         if (tma_ok) {
             bool ok = true;
-            for (; rel < q_lo; rel++) {
-                const int k = rel - q0;
-                ok = ok && mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1));
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty + k % LT_STAGES);
-            }
             for (int q = q_lo; q <= q_hi; q++) { const int k = q - q0; ok = ok && mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1)); }
             tma_ok = __all_sync(0xffffffffu, ok);
         }
-        if (w.lt_mode == 1) continue;
+        if (w.lt_mode == 1) {      // development: ring protocol only
+            __syncwarp();
+            if (tma_ok && lane == 0) for (int q = q_lo; q <= q_hi; q++) mbar_arrive(empty + (q - q0) % LT_STAGES);
+            if (tma_ok) for (int q = q_hi + 1; q <= q_last; q++) { const int k = q - q0; if (!mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1))) break; __syncwarp(); if (lane == 0) mbar_arrive(empty + k % LT_STAGES); }
+            continue;
+        }
         // where this lane's taps come from: its staged tile, or the image itself
         bool use_smem = tma_ok && job <= q_hi;
         const int box_x = (int) ((jd >> 4) & 0xfffu) * LT_TILE_W - LT_HALO, box_y = (int) (jd >> 16) * LT_TILE_H - LT_HALO;
@@ -424,11 +442,17 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
                 sgy[i] = t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
             }
         }
-        // the taps are in registers: tiles the warp's next pass does not need go back to the producer now, not at the end of the pass
+        // the taps are in registers: this pass is done with its tiles.  Tiles beyond the ring window (very sparse windows only; their
+        // lanes read global memory) still count this pass as a user: wait for them and arrive, one by one.
         __syncwarp();
         if (tma_ok) {
-            const int upto = min(q_next, q_hi + 1);
-            for (; rel < upto; rel++) { if (lane == 0) mbar_arrive(empty + (rel - q0) % LT_STAGES); }
+            if (lane == 0) for (int q = q_lo; q <= q_hi; q++) mbar_arrive(empty + (q - q0) % LT_STAGES);
+            for (int q = q_hi + 1; q <= q_last; q++) {
+                const int k = q - q0;
+                if (!mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1))) { tma_ok = false; break; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + k % LT_STAGES);
+            }
         }
         if (sample) {
             const float col[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
@@ -473,7 +497,7 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
                 nst = RES_OOB;               // BA:297-300
             } else {
                 neo = E;
-                const float th = fmaxf(w.frames[h].energy_th, w.frames[t].energy_th);
+                const float th = fmaxf(s_th[h], s_th[t]);
                 if (E > th || wJI2 < 2.f) { E = th; nst = RES_OUTLIER; } else nst = RES_IN;   // BA:303-311
                 ne = E;
                 ret = (double) E;
@@ -570,14 +594,12 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
             }
         }
         if (fix && in_chunk) {                       // final states in the host's residual order (finish_run reads these)
-            const int src = __ldg(w.r_src + r);
             w.fin_state[src] = st_out; w.fin_energy[src] = e_out; w.fin_alive[src] = (valid && good) ? 1 : 0;
         }
         // ---- 13x13 blocks: one partial per run of a (host,target) pair in this pass (records of non-good residuals are all zero)
         {
             const uint32_t key_ht = pht >> 24, kprev = __shfl_up_sync(0xffffffffu, key_ht, 1);
             const unsigned segmask = __ballot_sync(0xffffffffu, lane == 0 || key_ht != kprev);
-            const int sbase = __ldg(w.seg_base + c);
             if ((segmask >> lane) & 1u) w.seg_hdr[sbase + __popc(segmask & ((1u << lane) - 1u))] = (uint8_t) key_ht;
             float Qx[10], Qy[10];
             const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
@@ -622,15 +644,6 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
         // chunk energy (fp64, fixed order)
         const double es = warp_sum_d(ret);
         if (lane == 0) w.energy_part[c] = es;
-    }
-    // release the tiles this warp did not reach (every warp releases every tile; see above)
-    if (tma_ok) {
-        for (; rel <= q1; rel++) {
-            const int k = rel - q0;
-            if (!mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1))) break;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + k % LT_STAGES);
-        }
     }
 }
 

@@ -13,14 +13,16 @@ echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -5 gpurun_out/${tag}_pytest.log
 if [ "$mode" == "variants" ]; then
   for v in 0 1 2 3; do
-    CMLBA_LT_VARIANT=$v timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/${tag}_bench_v$v.json 2> gpurun_out/${tag}_bench_v$v.err
-    python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_v$v.json'));print('variant $v', d['ms_per_step'], d['kernel_ms'], d['run'], d['e2e']['ms_per_step'])"
+    for nt in 0 1; do
+      if [ $nt == 1 ]; then export CMLBA_NO_TMA=1; else unset CMLBA_NO_TMA; fi
+      CMLBA_LT_VARIANT=$v timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/${tag}_bench_v${v}_$nt.json 2> gpurun_out/${tag}_bench_v${v}_$nt.err
+      python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_v${v}_$nt.json'));print('variant $v no_tma=$nt', round(d['ms_per_step']*1e3,1), 'lin', round(d['kernel_ms']['linearize_accumulate']*1e3,1), 'warm', round(d['kernel_ms']['linearize_accumulate_l2_warm']*1e3,1), d['run'], round(d['e2e']['ms_per_step'],3))"
+    done
   done
+  unset CMLBA_NO_TMA
   CMLBA_LT_MODE=1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/${tag}_bench_stream.json 2> gpurun_out/${tag}_bench_stream.err
   python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_stream.json'));print('stream-only', d['ms_per_step'], d['kernel_ms'])"
   CMLBA_LT_EXACT=1 timeout 300 python -m pytest tests/test_gpu_edge.py -m gpu -q --timeout 300 -p no:cacheprovider 2>&1 | tail -3
-  CMLBA_NO_TMA=1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/${tag}_bench_notma.json 2> gpurun_out/${tag}_bench_notma.err
-  python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_notma.json'));print('no-tma', d['ms_per_step'], d['kernel_ms'])"
 fi
 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 echo "bench rc=$?"
