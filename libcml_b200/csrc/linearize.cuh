@@ -33,7 +33,7 @@ struct alignas(64) TileMaps { CUtensorMap m[MAXF]; };   // one 2-D tensor map pe
 
 // CW consumer warps (+1 producer warp), ST ring stages
 __host__ __device__ __forceinline__ size_t lt_smem_bytes(int N, int CW, int ST) {
-    return (size_t) ST * LT_TILE_BYTES + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float);
+    return (size_t) ST * LT_TILE_BYTES + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float) + 8 * sizeof(int);
 }
 
 // ---- mbarrier / TMA (PTX ISA 8.x; SASS: SYNCS.*, UTMALDG)
@@ -55,6 +55,16 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long *bar, uint32_t pari
 #pragma unroll 1
     for (int i = 0; i < (1 << 22); i++) if (mbar_try_wait(bar, parity)) return true;   // every failed try_wait has already slept for the hardware's time limit
     return false;
+}
+// A consumer may run several tiles ahead of the producer, and a parity wait can only tell the current phase of a barrier from the
+// previous one.  So the producer tags every stage with the tile it is loading (plain shared-memory store before the TMA is issued); a
+// consumer first sees its tile's tag, then waits for the phase.  Its own pending arrival keeps the stage from moving on meanwhile.
+__device__ __forceinline__ bool lt_wait_tile(const volatile int *tag, unsigned long long *full, const int s, const int q, const uint32_t parity) {
+    if (tag[s] != q) {
+#pragma unroll 1
+        for (int i = 0; tag[s] != q; i++) { if (i > (1 << 22)) return false; __nanosleep(64); }
+    }
+    return mbar_wait(full + s, parity);
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, unsigned long long *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x),
@@ -255,6 +265,7 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
     unsigned long long *full = reinterpret_cast<unsigned long long *>(s_pairs + 2 * w.N);
     unsigned long long *empty = full + LT_STAGES;
     float *s_th = reinterpret_cast<float *>(empty + LT_STAGES);                                     // [N] frameEnergyTH
+    volatile int *s_tag = reinterpret_cast<volatile int *>(s_th + MAXF);                            // [LT_STAGES] tile in (or on its way into) every stage
     const int N = w.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (w.n_chunks + (int) gridDim.x - 1) / (int) gridDim.x;
     const int c0 = blockIdx.x * per, c1 = min(c0 + per, w.n_chunks);
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
     const int q0 = __ldg(w.r_job + r_first), q1 = __ldg(w.r_job + r_last);       // tile jobs of this CTA: [q0, q1], all non-empty
     const int t_first = (int) (__ldg(w.r_pht + r_first) >> 28);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_EMPTY_COUNT); }
+        for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_EMPTY_COUNT); s_tag[s] = -1; }
         mbar_fence_init();
     }
     if ((int) threadIdx.x < N) s_th[threadIdx.x] = w.frames[threadIdx.x].energy_th;
@@ -288,6 +299,7 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
                 const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
                 const int users = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
                 const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
+                s_tag[s] = q0 + i;
                 mbar_arrive_n(empty + s, (uint32_t) (LT_EMPTY_COUNT - users));
                 mbar_expect_tx(full + s, LT_TILE_BYTES);
                 tma_load_2d(ring + (size_t) s * LT_TILE_BYTES, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
@@ -337,13 +349,13 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
         const int q_hi = min(q_last, q_lo + LT_STAGES - 1);
         if (tma_ok) {
             bool ok = true;
-            for (int q = q_lo; q <= q_hi; q++) { const int k = q - q0; ok = ok && mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1)); }
+            for (int q = q_lo; q <= q_hi; q++) { const int k = q - q0; ok = ok && lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1)); }
             tma_ok = __all_sync(0xffffffffu, ok);
         }
         if (w.lt_mode == 1) {      // development: ring protocol only
             __syncwarp();
             if (tma_ok && lane == 0) for (int q = q_lo; q <= q_hi; q++) mbar_arrive(empty + (q - q0) % LT_STAGES);
-            if (tma_ok) for (int q = q_hi + 1; q <= q_last; q++) { const int k = q - q0; if (!mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1))) break; __syncwarp(); if (lane == 0) mbar_arrive(empty + k % LT_STAGES); }
+            if (tma_ok) for (int q = q_hi + 1; q <= q_last; q++) { const int k = q - q0; if (!lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1))) break; __syncwarp(); if (lane == 0) mbar_arrive(empty + k % LT_STAGES); }
             continue;
         }
         // where this lane's taps come from: its staged tile, or the image itself
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
             if (lane == 0) for (int q = q_lo; q <= q_hi; q++) mbar_arrive(empty + (q - q0) % LT_STAGES);
             for (int q = q_hi + 1; q <= q_last; q++) {
                 const int k = q - q0;
-                if (!mbar_wait(full + k % LT_STAGES, (uint32_t) ((k / LT_STAGES) & 1))) { tma_ok = false; break; }
+                if (!lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1))) { tma_ok = false; break; }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + k % LT_STAGES);
             }
