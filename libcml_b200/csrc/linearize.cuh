@@ -71,6 +71,9 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
                  "r"(y)
                  : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y) {     // the box goes to L2 only (SASS: UTMAPF)
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];\n" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ float rcp_nr(float d) {      // MUFU.RCP + one Newton step: relative error ~1e-7 after rounding
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(d));
@@ -273,9 +276,30 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
     const int r_first = c0 * 32, r_last = min(c1 * 32, w.R) - 1;
     const int q0 = __ldg(w.r_job + r_first), q1 = __ldg(w.r_job + r_last);       // tile jobs of this CTA: [q0, q1], all non-empty
     const int t_first = (int) (__ldg(w.r_pht + r_first) >> 28);
-    if (threadIdx.x == 0) {
+    // the producer lane sets the barriers up and gets the first LT_STAGES boxes (and an L2 prefetch of all the others: HBM streams from the
+    // first microsecond, independently of the ring) under way while the rest of the CTA stages its constants
+    int p_i = 0;                                     // next tile (relative to q0) the producer has to issue
+    auto issue_tile = [&](const int i) {
+        const int s = i % LT_STAGES;
+        const uint32_t jd = __ldg(w.job_desc + q0 + i);
+        const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
+        const int users = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
+        const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
+        s_tag[s] = q0 + i;
+        mbar_arrive_n(empty + s, (uint32_t) (LT_EMPTY_COUNT - users));
+        mbar_expect_tx(full + s, LT_TILE_BYTES);
+        tma_load_2d(ring + (size_t) s * LT_TILE_BYTES, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
+    };
+    if (threadIdx.x == LT_CWARPS * 32) {
         for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_EMPTY_COUNT); s_tag[s] = -1; }
         mbar_fence_init();
+        if (w.tma_on) {
+            for (; p_i < LT_STAGES && p_i <= q1 - q0; p_i++) issue_tile(p_i);
+            for (int i = p_i; i <= q1 - q0; i++) {
+                const uint32_t jd = __ldg(w.job_desc + q0 + i);
+                tma_prefetch_2d(&tm.m[jd & 15u], ((int) ((jd >> 4) & 0xfffu) * LT_TILE_W - LT_HALO) * 2, (int) (jd >> 16) * LT_TILE_H - LT_HALO);
+            }
+        }
     }
     if ((int) threadIdx.x < N) s_th[threadIdx.x] = w.frames[threadIdx.x].energy_th;
     {   // pair constants of the (at most two, almost always) targets this CTA meets
@@ -292,17 +316,9 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
     // stage's "empty" barrier; the producer tops that number up to the barrier's fixed arrival count when it issues the load.
     if (warp == LT_CWARPS) {
         if (lane == 0 && w.tma_on) {
-            for (int i = 0; i <= q1 - q0; i++) {
-                const int s = i % LT_STAGES, u = i / LT_STAGES;
-                if (u > 0 && !mbar_wait(empty + s, (uint32_t) ((u - 1) & 1))) break;
-                const uint32_t jd = __ldg(w.job_desc + q0 + i);
-                const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
-                const int users = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
-                const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
-                s_tag[s] = q0 + i;
-                mbar_arrive_n(empty + s, (uint32_t) (LT_EMPTY_COUNT - users));
-                mbar_expect_tx(full + s, LT_TILE_BYTES);
-                tma_load_2d(ring + (size_t) s * LT_TILE_BYTES, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
+            for (; p_i <= q1 - q0; p_i++) {
+                if (!mbar_wait(empty + p_i % LT_STAGES, (uint32_t) ((p_i / LT_STAGES - 1) & 1))) break;
+                issue_tile(p_i);
             }
         }
         return;
@@ -636,21 +652,19 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
 #pragma unroll
                 for (int k4 = 0; k4 < 8; k4++) row[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
                 __syncwarp();
-                unsigned m = segmask;
+                // lane L sums entry (g, L) over the lanes of every run: all 32 rows are requested up front (immediate offsets, nothing
+                // waits on a single LDS), then one chain of adds with a flush wherever a new run starts
+                float cv[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) cv[j] = scr[j * LT_SCR_STRIDE + lane];
                 float *o = outp + g * 32;
-                while (m) {                          // lane L sums entry (g, L) over the lanes [j0, j1) of one run: an unrolled chain entered at 32 - len
-                    const int j0 = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int len = (m ? __ffs(m) - 1 : 32) - j0;
-                    const float *pa = scr + lane + (j0 + len - 32) * LT_SCR_STRIDE;      // chain position k reads lane row j0 + k - (32 - len)
-                    float s0 = 0.f, s1 = 0.f;
-#define LT_ROW2(k) case 32 - (k): s0 += pa[(k) * LT_SCR_STRIDE]; case 31 - (k): s1 += pa[((k) + 1) * LT_SCR_STRIDE];
-                    switch (len) { LT_ROW2(0) LT_ROW2(2) LT_ROW2(4) LT_ROW2(6) LT_ROW2(8) LT_ROW2(10) LT_ROW2(12) LT_ROW2(14) LT_ROW2(16) LT_ROW2(18) LT_ROW2(20) LT_ROW2(22) LT_ROW2(24)
-                                   LT_ROW2(26) LT_ROW2(28) LT_ROW2(30) default: break; }
-#undef LT_ROW2
-                    *o = s0 + s1;
-                    o += ACC_N;
+                float acc = cv[0];
+#pragma unroll
+                for (int j = 1; j < 32; j++) {
+                    if ((segmask >> j) & 1u) { *o = acc; o += ACC_N; acc = 0.f; }
+                    acc += cv[j];
                 }
+                *o = acc;
             }
         }
         // chunk energy (fp64, fixed order)
