@@ -12,10 +12,11 @@ constexpr int ACC_N = 96;         // 91 unique entries of the 13x13 block, padde
 constexpr int ACC_CHUNK = 32;     // residuals per linearize warp pass (one thread per residual; consecutive residuals of the tile-sorted order)
 // linearize_tile_kernel: target-image tiles staged by TMA (cp.async.bulk.tensor.2d) into a shared-memory ring
 constexpr int LT_TILE_W = 64, LT_TILE_H = 32;         // core tile of the target image that owns a residual (by its centre projection at bin time)
-constexpr int LT_HALO = 4;                            // pattern reach (2) + bilinear tap (1) + drift allowance since the binning
-constexpr int LT_BOX_W = LT_TILE_W + 2 * LT_HALO;     // 72 texels
-constexpr int LT_BOX_H = LT_TILE_H + 2 * LT_HALO;     // 40 rows
-constexpr int LT_TILE_BYTES = LT_BOX_W * LT_BOX_H * 16;   // 46 080 B of float4 texels per staged tile
+constexpr int LT_HALO = 3;                            // pattern reach (2) + bilinear tap (1); footprints that drift out of the box since the binning read global memory
+constexpr int LT_BOX_W = LT_TILE_W + 2 * LT_HALO;     // 70 texels
+constexpr int LT_BOX_H = LT_TILE_H + 2 * LT_HALO;     // 38 rows
+constexpr int LT_TILE_BYTES = LT_BOX_W * LT_BOX_H * 16;   // 42 560 B of float4 texels per staged tile
+constexpr int LT_STAGE_STRIDE = (LT_TILE_BYTES + 127) & ~127;   // TMA destinations are 128-byte aligned
 // ring depth and consumer warps per CTA (+1 producer warp) are template parameters of the kernel (Engine::launch_linearize picks the variant)
 constexpr int LT_SCR_STRIDE = 36;                     // floats per lane row of the per-warp reduction scratch (32 + pad, keeps 16-byte alignment)
 constexpr int P2P_POST_CAND_MAX = 65536;      // candidates per rank record that fit the peer-memory exchange (else NCCL all-gather)
@@ -113,6 +114,8 @@ struct DevWin {
     int tiles_x, tiles_y, n_tiles; // LT_TILE_W x LT_TILE_H tiles per frame
     int n_chunks;                  // ceil(R / 32) warp passes of linearize_tile_kernel
     int tma_on;                    // tensor maps encoded: tiles are staged by TMA (else every tap is read from global memory)
+    int lt_grid;                   // CTAs of linearize_tile_kernel (cta_info is laid out for this grid)
+    int *cta_info;                 // [lt_grid][16] q0, q1, first target, -, descriptors[4], users[4] of the first tiles
     int lt_mode;                   // development: 1 = the consumers only run the ring protocol (TMA streaming floor of the pass)
     int lt_exact;                  // 1 = every pattern pixel is projected in fp64 like the reference (parity study; default: fp32 offsets from the fp64 centre)
     int *bin_key;                  // [R] host order: ((t * n_tiles + tile) * N + h)

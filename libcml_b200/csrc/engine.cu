@@ -242,7 +242,7 @@ public:
     DevBuf<int> d_pt_host, d_pt_num_good, d_pt_ngood_cur, d_r_point, d_res_bin_begin, d_sc_chunk_host,
         d_sc_chunk_begin, d_sc_chunk_count, d_host_chunk_begin;
     // tile binning (linearize.cuh): sorted residual order, tile jobs, partial-block bookkeeping, final states in host order
-    DevBuf<int> d_bin_key, d_bin_hist, d_bin_offs, d_job_of_tile, d_r_job, d_r_src, d_seg_cnt, d_seg_base, d_seg_t_begin, d_bin_ticket, d_job_begin;
+    DevBuf<int> d_bin_key, d_bin_hist, d_bin_offs, d_job_of_tile, d_r_job, d_r_src, d_seg_cnt, d_seg_base, d_seg_t_begin, d_bin_ticket, d_job_begin, d_cta_info;
     DevBuf<uint32_t> d_job_desc, d_r_pht;
     DevBuf<uint8_t> d_seg_hdr, d_fin_state, d_fin_alive;
     DevBuf<float> d_fin_energy;
@@ -282,7 +282,7 @@ public:
 #define LT_ATTR(CW, ST)                                                                                                                                  \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<false, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lt_smem_bytes(MAXF, CW, ST))); \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<true, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lt_smem_bytes(MAXF, CW, ST)));
-        LT_ATTR(11, 3) LT_ATTR(7, 4) LT_ATTR(15, 3) LT_ATTR(15, 2)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
+        LT_ATTR(11, 4) LT_ATTR(7, 4) LT_ATTR(15, 3) LT_ATTR(11, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
 #undef LT_ATTR
         if (const char *v = getenv("CMLBA_LT_VARIANT")) lt_variant = atoi(v);
         if (const char *v = getenv("CMLBA_LT_MODE")) lt_mode = atoi(v);
@@ -311,7 +311,7 @@ public:
         for (auto *b : dd) b->release();
         d_post_send.release(); d_post_recv.release(); d_cap.release();
         DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_res_bin_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin,
-                             &d_bin_key, &d_bin_hist, &d_bin_offs, &d_job_of_tile, &d_r_job, &d_r_src, &d_seg_cnt, &d_seg_base, &d_seg_t_begin, &d_bin_ticket, &d_job_begin};
+                             &d_bin_key, &d_bin_hist, &d_bin_offs, &d_job_of_tile, &d_r_job, &d_r_src, &d_seg_cnt, &d_seg_base, &d_seg_t_begin, &d_bin_ticket, &d_job_begin, &d_cta_info};
         for (auto *b : di) b->release();
         d_job_desc.release(); d_r_pht.release(); d_seg_hdr.release(); d_fin_state.release(); d_fin_alive.release(); d_fin_energy.release();
         DevBuf<float> *df[] = {&d_pt_x, &d_pt_y, &d_pt_idz, &d_pt_idb, &d_pt_colors, &d_pt_weights, &d_pt_priorF, &d_pt_Hdd, &d_pt_bd, &d_pt_Hcd, &d_pt_HdiF, &d_pt_bdSumF, &d_pt_idh, &d_pt_mrb,
@@ -821,7 +821,7 @@ public:
         if (want_dbg) CK(d_dbg.reserve(Rz * DBG_STRIDE));
         CK(d_energy_part.reserve(std::max(n_chunks, 1)));
         CK(d_acc0.reserve(seg_cap * ACC_N)); CK(d_acc1.reserve(seg_cap * ACC_N));
-        CK(d_bin_key.reserve(Rz)); CK(d_bin_hist.reserve(n_keys)); CK(d_bin_offs.reserve(n_keys)); CK(d_job_of_tile.reserve((size_t) N * n_tiles)); CK(d_job_desc.reserve((size_t) N * n_tiles)); CK(d_job_begin.reserve((size_t) N * n_tiles + 1));
+        CK(d_bin_key.reserve(Rz)); CK(d_bin_hist.reserve(n_keys)); CK(d_bin_offs.reserve(n_keys)); CK(d_job_of_tile.reserve((size_t) N * n_tiles)); CK(d_job_desc.reserve((size_t) N * n_tiles)); CK(d_job_begin.reserve((size_t) N * n_tiles + 1)); CK(d_cta_info.reserve((size_t) 16 * 1024));
         CK(d_r_pht.reserve(Rz)); CK(d_r_job.reserve(Rz)); CK(d_r_src.reserve(Rz)); CK(d_seg_cnt.reserve(std::max(n_chunks, 1))); CK(d_seg_base.reserve(n_chunks + 1));
         CK(d_seg_hdr.reserve(seg_cap)); CK(d_seg_t_begin.reserve(MAXF + 1));
         CK(d_fin_state.reserve(Rz)); CK(d_fin_alive.reserve(Rz)); CK(d_fin_energy.reserve(Rz));
@@ -858,7 +858,7 @@ public:
         w.pt_Hdd = d_pt_Hdd.p; w.pt_bd = d_pt_bd.p; w.pt_Hcd = d_pt_Hcd.p; w.pt_HdiF = d_pt_HdiF.p; w.pt_bdSumF = d_pt_bdSumF.p; w.pt_idepth_hessian = d_pt_idh.p; w.pt_max_rel_bs = d_pt_mrb.p;
         w.pt_num_good = d_pt_num_good.p; w.pt_ngood_cur = d_pt_ngood_cur.p; w.pt_step = d_pt_step.p;
         w.r_point = d_r_point.p; w.r_host = d_r_host.p; w.r_target = d_r_target.p; w.res_bin_begin = d_res_bin_begin.p;
-        w.bin_key = d_bin_key.p; w.bin_hist = d_bin_hist.p; w.bin_offs = d_bin_offs.p; w.job_of_tile = d_job_of_tile.p; w.job_desc = d_job_desc.p; w.job_begin = d_job_begin.p;
+        w.bin_key = d_bin_key.p; w.bin_hist = d_bin_hist.p; w.bin_offs = d_bin_offs.p; w.job_of_tile = d_job_of_tile.p; w.job_desc = d_job_desc.p; w.job_begin = d_job_begin.p; w.cta_info = d_cta_info.p; w.lt_grid = std::max(1, std::min(std::min(n_sm, 1024), n_chunks));
         w.r_pht = d_r_pht.p; w.r_job = d_r_job.p; w.r_src = d_r_src.p; w.seg_cnt = d_seg_cnt.p; w.seg_base = d_seg_base.p; w.seg_hdr = d_seg_hdr.p; w.seg_t_begin = d_seg_t_begin.p;
         w.bin_ticket = d_bin_ticket.p; w.fin_state = d_fin_state.p; w.fin_alive = d_fin_alive.p; w.fin_energy = d_fin_energy.p;
         w.tma_on = encode_tile_maps() ? 1 : 0;
@@ -1095,7 +1095,7 @@ public:
 
     void launch_linearize(int fix, int respect_done) {
         if (dw.R == 0) return;
-        const int grid = std::min(n_sm, dw.n_chunks);          // persistent CTAs: one per SM, a contiguous range of warp passes each
+        const int grid = dw.lt_grid;                           // persistent CTAs: one per SM, a contiguous range of warp passes each
         dw.lt_mode = lt_mode; dw.lt_exact = lt_exact;
 #define LT_LAUNCH(CW, ST)                                                                                                                                      \
     do {                                                                                                                                                       \
@@ -1105,8 +1105,8 @@ public:
         switch (lt_variant) {
             case 1: LT_LAUNCH(7, 4); break;
             case 2: LT_LAUNCH(15, 3); break;
-            case 3: LT_LAUNCH(15, 2); break;
-            default: LT_LAUNCH(11, 3); break;
+            case 3: LT_LAUNCH(11, 3); break;
+            default: LT_LAUNCH(11, 4); break;
         }
 #undef LT_LAUNCH
         launches++;

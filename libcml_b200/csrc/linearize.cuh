@@ -33,7 +33,7 @@ struct alignas(64) TileMaps { CUtensorMap m[MAXF]; };   // one 2-D tensor map pe
 
 // CW consumer warps (+1 producer warp), ST ring stages
 __host__ __device__ __forceinline__ size_t lt_smem_bytes(int N, int CW, int ST) {
-    return (size_t) ST * LT_TILE_BYTES + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float) + 8 * sizeof(int);
+    return (size_t) ST * LT_STAGE_STRIDE + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float) + 8 * sizeof(int);
 }
 
 // ---- mbarrier / TMA (PTX ISA 8.x; SASS: SYNCS.*, UTMALDG)
@@ -253,84 +253,112 @@ __global__ void __launch_bounds__(256) bin_segments_kernel(const DevWin w) {
         int nextv = tot;
         for (int t = w.N; t >= 0; t--) { if (t == w.N || s_tb[t] < 0) s_tb[t] = nextv; nextv = s_tb[t]; w.seg_t_begin[t] = s_tb[t]; }
     }
+    // per-CTA records of linearize_tile_kernel (grid = lt_grid persistent CTAs over contiguous ranges of warp passes)
+    const int per_cta = (w.n_chunks + w.lt_grid - 1) / w.lt_grid;
+    for (int b = threadIdx.x; b < w.lt_grid; b += 256) {
+        const int c0 = b * per_cta, c1 = min(c0 + per_cta, w.n_chunks);
+        int *info = w.cta_info + (size_t) b * 16;
+        for (int k = 0; k < 16; k++) info[k] = 0;
+        if (c0 >= c1) continue;
+        const int q0 = w.r_job[c0 * 32], q1 = w.r_job[min(c1 * 32, w.R) - 1];
+        info[0] = q0; info[1] = q1; info[2] = (int) (w.r_pht[c0 * 32] >> 28);
+        for (int i = 0; i < 4 && q0 + i <= q1; i++) {
+            const int jb = w.job_begin[q0 + i], je = w.job_begin[q0 + i + 1];
+            info[4 + i] = (int) w.job_desc[q0 + i];
+            info[8 + i] = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 template <bool kDump, int LT_CWARPS, int LT_STAGES>
 __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel(const DevWin w, const __grid_constant__ TileMaps tm, const int fix, const int respect_done) {
-    constexpr int LT_THREADS = (LT_CWARPS + 1) * 32;
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     extern __shared__ __align__(1024) unsigned char lt_smem[];
     unsigned char *ring = lt_smem;                                                                  // [LT_STAGES][LT_BOX_H][LT_BOX_W] float4
-    float *scratch = reinterpret_cast<float *>(lt_smem + (size_t) LT_STAGES * LT_TILE_BYTES);       // [LT_CWARPS][32][LT_SCR_STRIDE]
+    float *scratch = reinterpret_cast<float *>(lt_smem + (size_t) LT_STAGES * LT_STAGE_STRIDE);       // [LT_CWARPS][32][LT_SCR_STRIDE]
     PairPre *s_pairs = reinterpret_cast<PairPre *>(scratch + LT_CWARPS * 32 * LT_SCR_STRIDE);       // [2 targets][N hosts]
     unsigned long long *full = reinterpret_cast<unsigned long long *>(s_pairs + 2 * w.N);
     unsigned long long *empty = full + LT_STAGES;
     float *s_th = reinterpret_cast<float *>(empty + LT_STAGES);                                     // [N] frameEnergyTH
     volatile int *s_tag = reinterpret_cast<volatile int *>(s_th + MAXF);                            // [LT_STAGES] tile in (or on its way into) every stage
+    unsigned long long *pairs_bar = reinterpret_cast<unsigned long long *>(const_cast<int *>(s_tag) + 4);   // the staged constants are in place
     const int N = w.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (w.n_chunks + (int) gridDim.x - 1) / (int) gridDim.x;
     const int c0 = blockIdx.x * per, c1 = min(c0 + per, w.n_chunks);
     if (c0 >= c1) return;
     const int r_first = c0 * 32, r_last = min(c1 * 32, w.R) - 1;
-    const int q0 = __ldg(w.r_job + r_first), q1 = __ldg(w.r_job + r_last);       // tile jobs of this CTA: [q0, q1], all non-empty
-    const int t_first = (int) (__ldg(w.r_pht + r_first) >> 28);
-    // the producer lane sets the barriers up and gets the first LT_STAGES boxes (and an L2 prefetch of all the others: HBM streams from the
-    // first microsecond, independently of the ring) under way while the rest of the CTA stages its constants
-    int p_i = 0;                                     // next tile (relative to q0) the producer has to issue
-    auto issue_tile = [&](const int i) {
-        const int s = i % LT_STAGES;
-        const uint32_t jd = __ldg(w.job_desc + q0 + i);
-        const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
-        const int users = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
-        const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
-        s_tag[s] = q0 + i;
-        mbar_arrive_n(empty + s, (uint32_t) (LT_EMPTY_COUNT - users));
-        mbar_expect_tx(full + s, LT_TILE_BYTES);
-        tma_load_2d(ring + (size_t) s * LT_TILE_BYTES, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
-    };
+    // one record per CTA, prepared by bin_segments_kernel: tile jobs [q0, q1] of the CTA (all non-empty), first target, and the descriptors /
+    // user counts of its first four tiles -- a single load before the producer can issue its first boxes
+    const int4 *infop = reinterpret_cast<const int4 *>(w.cta_info + (size_t) blockIdx.x * 16);
+    const int4 info = __ldg(infop);
+    const int q0 = info.x, q1 = info.y, t_first = info.z;
     if (threadIdx.x == LT_CWARPS * 32) {
         for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_EMPTY_COUNT); s_tag[s] = -1; }
+        mbar_init(pairs_bar, 31);
         mbar_fence_init();
-        if (w.tma_on) {
-            for (; p_i < LT_STAGES && p_i <= q1 - q0; p_i++) issue_tile(p_i);
-            for (int i = p_i; i <= q1 - q0; i++) {
-                const uint32_t jd = __ldg(w.job_desc + q0 + i);
+    }
+    __syncthreads();                                 // cheap: nothing but the barrier set-up precedes it
+    // ---- producer warp.  Lane 0 streams the boxes of tiles q0..q1 through the ring: a stage goes back to the producer when every warp
+    // pass that overlaps its tile (the passes are consecutive, so their number follows from the tile's residual range) has arrived on the
+    // stage's "empty" barrier; the producer tops that number up to the barrier's fixed arrival count when it issues the load.  The
+    // tiles beyond the ring are prefetched into L2 right away, so HBM streams from the first microsecond, independently of the ring.
+    // Lanes 1..31 stage the pair constants of the (at most two, almost always) targets this CTA meets and the energy thresholds.
+    if (warp == LT_CWARPS) {
+        if (lane == 0) {
+            if (!w.tma_on) return;
+            auto issue = [&](const int i, const uint32_t jd, const int users) {
+                const int s = i % LT_STAGES;
+                const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
+                s_tag[s] = q0 + i;
+                mbar_arrive_n(empty + s, (uint32_t) (LT_EMPTY_COUNT - users));
+                mbar_expect_tx(full + s, LT_TILE_BYTES);
+                tma_load_2d(ring + (size_t) s * LT_STAGE_STRIDE, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
+            };
+            const int4 jd4 = __ldg(infop + 1), us4 = __ldg(infop + 2);
+            const int nt = q1 - q0 + 1;
+            int i = 0;
+            if (i < nt && i < LT_STAGES) { issue(0, (uint32_t) jd4.x, us4.x); i = 1; }
+            if (i < nt && i < LT_STAGES) { issue(1, (uint32_t) jd4.y, us4.y); i = 2; }
+            if (i < nt && i < LT_STAGES) { issue(2, (uint32_t) jd4.z, us4.z); i = 3; }
+            if (i < nt && i < LT_STAGES) { issue(3, (uint32_t) jd4.w, us4.w); i = 4; }
+            for (int k = i; k < nt; k++) {
+                const uint32_t jd = __ldg(w.job_desc + q0 + k);
                 tma_prefetch_2d(&tm.m[jd & 15u], ((int) ((jd >> 4) & 0xfffu) * LT_TILE_W - LT_HALO) * 2, (int) (jd >> 16) * LT_TILE_H - LT_HALO);
             }
-        }
-    }
-    if ((int) threadIdx.x < N) s_th[threadIdx.x] = w.frames[threadIdx.x].energy_th;
-    {   // pair constants of the (at most two, almost always) targets this CTA meets
-        constexpr int PW = sizeof(PairPre) / 8;
-        double *dst = reinterpret_cast<double *>(s_pairs);
-        for (int i = threadIdx.x; i < 2 * N * PW; i += LT_THREADS) {
-            const int rec = i / PW, k = i - rec * PW, tt = rec / N, h = rec - tt * N, t = min(t_first + tt, N - 1);
-            dst[i] = reinterpret_cast<const double *>(w.pairs + h * N + t)[k];
-        }
-    }
-    __syncthreads();
-    // ---- producer warp: streams the boxes of tiles q0..q1 through the ring.  A stage goes back to the producer when every warp pass
-    // that overlaps its tile (the passes are consecutive, so their number follows from the tile's residual range) has arrived on the
-    // stage's "empty" barrier; the producer tops that number up to the barrier's fixed arrival count when it issues the load.
-    if (warp == LT_CWARPS) {
-        if (lane == 0 && w.tma_on) {
-            for (; p_i <= q1 - q0; p_i++) {
-                if (!mbar_wait(empty + p_i % LT_STAGES, (uint32_t) ((p_i / LT_STAGES - 1) & 1))) break;
-                issue_tile(p_i);
+            for (; i < nt; i++) {
+                const uint32_t jd = __ldg(w.job_desc + q0 + i);
+                const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
+                const int users = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
+                if (!mbar_wait(empty + i % LT_STAGES, (uint32_t) ((i / LT_STAGES - 1) & 1))) break;
+                issue(i, jd, users);
             }
+        } else {
+            constexpr int PW = sizeof(PairPre) / 8;
+            double *dst = reinterpret_cast<double *>(s_pairs);
+            for (int i = lane - 1; i < 2 * N * PW; i += 31) {
+                const int rec = i / PW, k = i - rec * PW, tt = rec / N, h = rec - tt * N, t = min(t_first + tt, N - 1);
+                dst[i] = reinterpret_cast<const double *>(w.pairs + h * N + t)[k];
+            }
+            if (lane - 1 < N) s_th[lane - 1] = w.frames[lane - 1].energy_th;
+            mbar_arrive(pairs_bar);                  // release: the stores above are visible to whoever sees the phase complete
         }
         return;
     }
-    // ---- consumer warps.  First, while the first tiles are in flight: pull everything this CTA will read per residual into L2
-    // (the per-residual arrays are contiguous; the point records hang off r_pht), so that no pass waits on HBM for its inputs.
-    for (int r = r_first + (int) threadIdx.x; r <= r_last; r += LT_CWARPS * 32) {
-        const int p = (int) (__ldg(w.r_pht + r) & 0xffffffu);
-        prefetch_l2(w.pt_idepth + p); prefetch_l2(w.pt_x + p); prefetch_l2(w.pt_y + p); prefetch_l2(w.pt_colors + (size_t) p * 8); prefetch_l2(w.pt_weights + (size_t) p * 8);
-        if ((r & 31) == 0) { prefetch_l2(w.r_job + r); prefetch_l2(w.r_energy[ctrl->cur] + r); prefetch_l2(w.r_new_energy + r); prefetch_l2(w.r_src + r); }
-        if ((r & 127) == 0) { prefetch_l2(w.r_alive + r); prefetch_l2(w.r_state[ctrl->cur] + r); prefetch_l2(w.r_new_state + r); }
+    // ---- consumer warps.  The per-residual arrays of the CTA's range are contiguous: one L2 prefetch per 128-byte line up front (the point
+    // records of a pass are prefetched during the pass before it, below), so that only a warp's first pass waits on HBM for its inputs.
+    {
+        const int first_line = r_first >> 5, n_lines = (r_last >> 5) - first_line + 1;
+        for (int k = threadIdx.x; k < 7 * n_lines; k += LT_CWARPS * 32) {
+            const int arr = k / n_lines, r = (first_line + (k - arr * n_lines)) << 5;
+            const void *ptr = arr == 0 ? (const void *) (w.r_pht + r) : arr == 1 ? (const void *) (w.r_job + r) : arr == 2 ? (const void *) (w.r_energy[ctrl->cur] + r)
+                            : arr == 3 ? (const void *) (w.r_new_energy + r) : arr == 4 ? (const void *) (w.r_src + r)
+                            : arr == 5 ? (const void *) (w.r_state[ctrl->cur] + r) : (const void *) (w.r_new_state + r);
+            prefetch_l2(ptr);
+        }
     }
+    bool pairs_ready = false;
     // ---- consumer warps
     const int cur = ctrl->cur, nxt = cur ^ 1;
     float *scr = scratch + warp * 32 * LT_SCR_STRIDE;
@@ -358,6 +386,8 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
         const float4 *colp = reinterpret_cast<const float4 *>(w.pt_colors + (size_t) p * 8);
         const float4 *wtp = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
         const float4 c0v = __ldg(colp), c1v = __ldg(colp + 1), w0v = __ldg(wtp), w1v = __ldg(wtp + 1);
+        const uint32_t pht_next = (c + LT_CWARPS < c1) ? __ldg(w.r_pht + min((c + LT_CWARPS) * 32 + lane, w.R - 1)) : pht;     // for the L2 prefetch below
+        if (!pairs_ready) { mbar_wait(pairs_bar, 0); pairs_ready = true; }
         const PairPre *ppp = (t - t_first < 2) ? s_pairs + (t - t_first) * N + h : w.pairs + h * N + t;
         const PairPre &pp = *ppp;
         // ---- the tiles of this pass: [q_lo, q_last]; the first LT_STAGES of them can be in the ring together
@@ -446,7 +476,7 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
 #pragma unroll
             for (int i = 1; i < 8; i++) { const int ix = (int) qx[i], iy = (int) qy[i]; lx = min(lx, ix); hx = max(hx, ix); ly = min(ly, iy); hy = max(hy, iy); }
             use_smem = lx >= box_x && ly >= box_y && hx + 1 < box_x + LT_BOX_W && hy + 1 < box_y + LT_BOX_H;
-            if (use_smem) { ox = box_x; oy = box_y; pitch = LT_BOX_W; tbase = reinterpret_cast<const float4 *>(ring + (size_t) ((job - q0) % LT_STAGES) * LT_TILE_BYTES); }
+            if (use_smem) { ox = box_x; oy = box_y; pitch = LT_BOX_W; tbase = reinterpret_cast<const float4 *>(ring + (size_t) ((job - q0) % LT_STAGES) * LT_STAGE_STRIDE); }
         }
         // ---- per-residual sampling + Jacobians
         float rec[RJ_STRIDE];
@@ -469,6 +499,10 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
                 sgx[i] = t00.y * w00 + t10.y * w10 + t01.y * w01 + t11.y * w11;
                 sgy[i] = t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
             }
+        }
+        if (c + LT_CWARPS < c1) {                     // the point records of this warp's next pass: on their way to L2 while this one computes
+            const int pn = (int) (pht_next & 0xffffffu);
+            prefetch_l2(w.pt_idepth + pn); prefetch_l2(w.pt_x + pn); prefetch_l2(w.pt_y + pn); prefetch_l2(w.pt_colors + (size_t) pn * 8); prefetch_l2(w.pt_weights + (size_t) pn * 8);
         }
         // the taps are in registers: this pass is done with its tiles.  Tiles beyond the ring window (very sparse windows only; their
         // lanes read global memory) still count this pass as a user: wait for them and arrive, one by one.
@@ -652,19 +686,23 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
 #pragma unroll
                 for (int k4 = 0; k4 < 8; k4++) row[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
                 __syncwarp();
-                // lane L sums entry (g, L) over the lanes of every run: all 32 rows are requested up front (immediate offsets, nothing
-                // waits on a single LDS), then one chain of adds with a flush wherever a new run starts
-                float cv[32];
-#pragma unroll
-                for (int j = 0; j < 32; j++) cv[j] = scr[j * LT_SCR_STRIDE + lane];
+                // lane L sums entry (g, L) over the lanes [j0, j0 + len) of every run: the len % 4 first rows with guarded loads, then an
+                // unrolled chain of 4-row blocks entered at 8 - len / 4 (four loads in flight per block, four independent sums)
+                unsigned m = segmask;
                 float *o = outp + g * 32;
-                float acc = cv[0];
-#pragma unroll
-                for (int j = 1; j < 32; j++) {
-                    if ((segmask >> j) & 1u) { *o = acc; o += ACC_N; acc = 0.f; }
-                    acc += cv[j];
+                while (m) {
+                    const int j0 = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int len = (m ? __ffs(m) - 1 : 32) - j0, rem = len & 3;
+                    const float *pr = scr + lane + j0 * LT_SCR_STRIDE;
+                    float s0 = rem > 0 ? pr[0] : 0.f, s1 = rem > 1 ? pr[LT_SCR_STRIDE] : 0.f, s2 = rem > 2 ? pr[2 * LT_SCR_STRIDE] : 0.f, s3 = 0.f;
+                    const float *pa = pr + (rem + (len & ~3) - 32) * LT_SCR_STRIDE;      // block b of the chain reads rows j0 + rem + 4 (b - (8 - len / 4)) ...
+#define LT_BLK(b) case 8 - (b): { const float x0 = pa[(4 * (b)) * LT_SCR_STRIDE], x1 = pa[(4 * (b) + 1) * LT_SCR_STRIDE], x2 = pa[(4 * (b) + 2) * LT_SCR_STRIDE], x3 = pa[(4 * (b) + 3) * LT_SCR_STRIDE]; s0 += x0; s1 += x1; s2 += x2; s3 += x3; }
+                    switch (len >> 2) { LT_BLK(0) LT_BLK(1) LT_BLK(2) LT_BLK(3) LT_BLK(4) LT_BLK(5) LT_BLK(6) LT_BLK(7) default: break; }
+#undef LT_BLK
+                    *o = (s0 + s1) + (s2 + s3);
+                    o += ACC_N;
                 }
-                *o = acc;
             }
         }
         // chunk energy (fp64, fixed order)

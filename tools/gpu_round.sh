@@ -13,7 +13,7 @@ echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -5 gpurun_out/${tag}_pytest.log
 if [ "$mode" == "variants" ]; then
   for v in 0 1 2 3; do
-    for nt in 0 1; do
+    for nt in 0; do
       if [ $nt == 1 ]; then export CMLBA_NO_TMA=1; else unset CMLBA_NO_TMA; fi
       CMLBA_LT_VARIANT=$v timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/${tag}_bench_v${v}_$nt.json 2> gpurun_out/${tag}_bench_v${v}_$nt.err
       python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_v${v}_$nt.json'));print('variant $v no_tma=$nt', round(d['ms_per_step']*1e3,1), 'lin', round(d['kernel_ms']['linearize_accumulate']*1e3,1), 'warm', round(d['kernel_ms']['linearize_accumulate_l2_warm']*1e3,1), d['run'], round(d['e2e']['ms_per_step'],3))"
