@@ -246,6 +246,7 @@ public:
     DevBuf<uint32_t> d_job_desc, d_r_pht;
     DevBuf<uint8_t> d_seg_hdr, d_fin_state, d_fin_alive;
     DevBuf<float> d_fin_energy;
+    DevBuf<long long> d_lt_trace;
     TileMaps tile_maps;           // one tensor map per window frame (re-encoded by build_device_window)
     int n_sm = 148;
     int lt_variant = 0, lt_mode = 0, lt_exact = 0;   // development switches (CMLBA_LT_VARIANT, CMLBA_LT_MODE): kernel shape, streaming-only mode
@@ -282,7 +283,7 @@ public:
 #define LT_ATTR(CW, ST)                                                                                                                                  \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<false, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lt_smem_bytes(MAXF, CW, ST))); \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<true, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lt_smem_bytes(MAXF, CW, ST)));
-        LT_ATTR(11, 4) LT_ATTR(7, 4) LT_ATTR(15, 3) LT_ATTR(11, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
+        LT_ATTR(12, 4) LT_ATTR(8, 4) LT_ATTR(16, 3) LT_ATTR(12, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
 #undef LT_ATTR
         if (const char *v = getenv("CMLBA_LT_VARIANT")) lt_variant = atoi(v);
         if (const char *v = getenv("CMLBA_LT_MODE")) lt_mode = atoi(v);
@@ -1097,16 +1098,17 @@ public:
         if (dw.R == 0) return;
         const int grid = dw.lt_grid;                           // persistent CTAs: one per SM, a contiguous range of warp passes each
         dw.lt_mode = lt_mode; dw.lt_exact = lt_exact;
+        if (lt_mode & 2) { if (d_lt_trace.reserve((size_t) 1024 * 16 * 32) == cudaSuccess) { cudaMemsetAsync(d_lt_trace.p, 0, (size_t) grid * 16 * 32 * 8, stream); dw.lt_trace = d_lt_trace.p; } }
 #define LT_LAUNCH(CW, ST)                                                                                                                                      \
     do {                                                                                                                                                       \
-        if (want_dbg) linearize_tile_kernel<true, CW, ST><<<grid, (CW + 1) * 32, lt_smem_bytes(dw.N, CW, ST), stream>>>(dw, tile_maps, fix, respect_done);    \
-        else linearize_tile_kernel<false, CW, ST><<<grid, (CW + 1) * 32, lt_smem_bytes(dw.N, CW, ST), stream>>>(dw, tile_maps, fix, respect_done);            \
+        if (want_dbg) linearize_tile_kernel<true, CW, ST><<<grid, CW * 32, lt_smem_bytes(dw.N, CW, ST), stream>>>(dw, tile_maps, fix, respect_done);    \
+        else linearize_tile_kernel<false, CW, ST><<<grid, CW * 32, lt_smem_bytes(dw.N, CW, ST), stream>>>(dw, tile_maps, fix, respect_done);            \
     } while (0)
         switch (lt_variant) {
-            case 1: LT_LAUNCH(7, 4); break;
-            case 2: LT_LAUNCH(15, 3); break;
-            case 3: LT_LAUNCH(11, 3); break;
-            default: LT_LAUNCH(11, 4); break;
+            case 1: LT_LAUNCH(8, 4); break;
+            case 2: LT_LAUNCH(16, 3); break;
+            case 3: LT_LAUNCH(12, 3); break;
+            default: if (lt_smem_bytes(dw.N, 12, 4) <= (size_t) 227 * 1024) LT_LAUNCH(12, 4); else LT_LAUNCH(12, 3); break;
         }
 #undef LT_LAUNCH
         launches++;
@@ -1420,6 +1422,7 @@ public:
             for (int i = 0; i < R; i++) v[i] = (uint8_t) (name == "res_host" ? ((pht[i] >> 24) & 15u) : (pht[i] >> 28));
             return host_out(v.data(), R, dst, cap, bytes);
         }
+        if (name == "lt_trace") return copy_out(d_lt_trace.p, (size_t) dw.lt_grid * 16 * 32, dst, cap, bytes);
         if (name == "res_src") return copy_out(d_r_src.p, R, dst, cap, bytes);
         if (name == "res_job") return copy_out(d_r_job.p, R, dst, cap, bytes);
         if (name == "res_state") return copy_out(cur ? d_r_state1.p : d_r_state0.p, R, dst, cap, bytes);

@@ -29,11 +29,12 @@
 
 namespace cmlba {
 
+constexpr int LT_TILE_TABLE = 64;     // tile descriptors / user counts of a CTA kept in shared memory (more tiles: read from global memory)
 struct alignas(64) TileMaps { CUtensorMap m[MAXF]; };   // one 2-D tensor map per window frame: rows of W float4 texels seen as 2W 8-byte elements
 
-// CW consumer warps (+1 producer warp), ST ring stages
+// CW warps, ST ring stages
 __host__ __device__ __forceinline__ size_t lt_smem_bytes(int N, int CW, int ST) {
-    return (size_t) ST * LT_STAGE_STRIDE + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float) + 8 * sizeof(int);
+    return (size_t) ST * LT_STAGE_STRIDE + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float) + 8 * sizeof(int) + LT_TILE_TABLE * 2 * sizeof(int);
 }
 
 // ---- mbarrier / TMA (PTX ISA 8.x; SASS: SYNCS.*, UTMALDG)
@@ -50,6 +51,11 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t 
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t parity) {      // non-blocking
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 // bounded: a tile that never lands (bad tensor map) degrades the warp to global-memory taps instead of hanging the device
 __device__ __forceinline__ bool mbar_wait(unsigned long long *bar, uint32_t parity) {
 #pragma unroll 1
@@ -59,7 +65,8 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long *bar, uint32_t pari
 // A consumer may run several tiles ahead of the producer, and a parity wait can only tell the current phase of a barrier from the
 // previous one.  So the producer tags every stage with the tile it is loading (plain shared-memory store before the TMA is issued); a
 // consumer first sees its tile's tag, then waits for the phase.  Its own pending arrival keeps the stage from moving on meanwhile.
-__device__ __forceinline__ bool lt_wait_tile(const volatile int *tag, unsigned long long *full, const int s, const int q, const uint32_t parity) {
+__device__ __forceinline__ bool lt_wait_tile(const int *tag_, unsigned long long *full, const int s, const int q, const uint32_t parity) {
+    const volatile int *tag = tag_;
     if (tag[s] != q) {
 #pragma unroll 1
         for (int i = 0; tag[s] != q; i++) { if (i > (1 << 22)) return false; __nanosleep(64); }
@@ -272,79 +279,88 @@ __global__ void __launch_bounds__(256) bin_segments_kernel(const DevWin w) {
 
 // ------------------------------------------------------------------------------------------------
 template <bool kDump, int LT_CWARPS, int LT_STAGES>
-__global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel(const DevWin w, const __grid_constant__ TileMaps tm, const int fix, const int respect_done) {
+__global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const DevWin w, const __grid_constant__ TileMaps tm, const int fix, const int respect_done) {
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     extern __shared__ __align__(1024) unsigned char lt_smem[];
     unsigned char *ring = lt_smem;                                                                  // [LT_STAGES][LT_BOX_H][LT_BOX_W] float4
-    float *scratch = reinterpret_cast<float *>(lt_smem + (size_t) LT_STAGES * LT_STAGE_STRIDE);       // [LT_CWARPS][32][LT_SCR_STRIDE]
+    float *scratch = reinterpret_cast<float *>(lt_smem + (size_t) LT_STAGES * LT_STAGE_STRIDE);     // [LT_CWARPS][32][LT_SCR_STRIDE]
     PairPre *s_pairs = reinterpret_cast<PairPre *>(scratch + LT_CWARPS * 32 * LT_SCR_STRIDE);       // [2 targets][N hosts]
     unsigned long long *full = reinterpret_cast<unsigned long long *>(s_pairs + 2 * w.N);
     unsigned long long *empty = full + LT_STAGES;
     float *s_th = reinterpret_cast<float *>(empty + LT_STAGES);                                     // [N] frameEnergyTH
-    volatile int *s_tag = reinterpret_cast<volatile int *>(s_th + MAXF);                            // [LT_STAGES] tile in (or on its way into) every stage
-    unsigned long long *pairs_bar = reinterpret_cast<unsigned long long *>(const_cast<int *>(s_tag) + 4);   // the staged constants are in place
+    int *s_tag = reinterpret_cast<int *>(s_th + MAXF);                                              // [LT_STAGES] tile in (or on its way into) every stage
+    unsigned long long *pairs_bar = reinterpret_cast<unsigned long long *>(s_tag + 4);              // the staged constants are in place
+    int *s_jd = s_tag + 8, *s_users = s_jd + LT_TILE_TABLE;                                         // descriptors / user counts of the CTA's first LT_TILE_TABLE tiles
     const int N = w.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (w.n_chunks + (int) gridDim.x - 1) / (int) gridDim.x;
     const int c0 = blockIdx.x * per, c1 = min(c0 + per, w.n_chunks);
     if (c0 >= c1) return;
+    // development trace: stamp k of this warp (SM clock); compiled to a predicated-off store in normal runs
+    long long *trace = (w.lt_mode & 2) ? w.lt_trace + ((size_t) blockIdx.x * 16 + warp) * 32 : nullptr;
+    int tr_k = 0;
+#define LT_STAMP() do { if (trace && lane == 0 && tr_k < 32) trace[tr_k++] = clock64(); } while (0)
+    LT_STAMP();
     const int r_first = c0 * 32, r_last = min(c1 * 32, w.R) - 1;
     // one record per CTA, prepared by bin_segments_kernel: tile jobs [q0, q1] of the CTA (all non-empty), first target, and the descriptors /
-    // user counts of its first four tiles -- a single load before the producer can issue its first boxes
+    // user counts of its first four tiles -- a single load before the first boxes can be issued
     const int4 *infop = reinterpret_cast<const int4 *>(w.cta_info + (size_t) blockIdx.x * 16);
     const int4 info = __ldg(infop);
-    const int q0 = info.x, q1 = info.y, t_first = info.z;
-    if (threadIdx.x == LT_CWARPS * 32) {
-        for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_EMPTY_COUNT); s_tag[s] = -1; }
-        mbar_init(pairs_bar, 31);
-        mbar_fence_init();
-    }
-    __syncthreads();                                 // cheap: nothing but the barrier set-up precedes it
-    // ---- producer warp.  Lane 0 streams the boxes of tiles q0..q1 through the ring: a stage goes back to the producer when every warp
-    // pass that overlaps its tile (the passes are consecutive, so their number follows from the tile's residual range) has arrived on the
-    // stage's "empty" barrier; the producer tops that number up to the barrier's fixed arrival count when it issues the load.  The
-    // tiles beyond the ring are prefetched into L2 right away, so HBM streams from the first microsecond, independently of the ring.
-    // Lanes 1..31 stage the pair constants of the (at most two, almost always) targets this CTA meets and the energy thresholds.
-    if (warp == LT_CWARPS) {
-        if (lane == 0) {
-            if (!w.tma_on) return;
-            auto issue = [&](const int i, const uint32_t jd, const int users) {
-                const int s = i % LT_STAGES;
-                const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
-                s_tag[s] = q0 + i;
-                mbar_arrive_n(empty + s, (uint32_t) (LT_EMPTY_COUNT - users));
-                mbar_expect_tx(full + s, LT_TILE_BYTES);
-                tma_load_2d(ring + (size_t) s * LT_STAGE_STRIDE, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
-            };
-            const int4 jd4 = __ldg(infop + 1), us4 = __ldg(infop + 2);
-            const int nt = q1 - q0 + 1;
-            int i = 0;
-            if (i < nt && i < LT_STAGES) { issue(0, (uint32_t) jd4.x, us4.x); i = 1; }
-            if (i < nt && i < LT_STAGES) { issue(1, (uint32_t) jd4.y, us4.y); i = 2; }
-            if (i < nt && i < LT_STAGES) { issue(2, (uint32_t) jd4.z, us4.z); i = 3; }
-            if (i < nt && i < LT_STAGES) { issue(3, (uint32_t) jd4.w, us4.w); i = 4; }
-            for (int k = i; k < nt; k++) {
-                const uint32_t jd = __ldg(w.job_desc + q0 + k);
-                tma_prefetch_2d(&tm.m[jd & 15u], ((int) ((jd >> 4) & 0xfffu) * LT_TILE_W - LT_HALO) * 2, (int) (jd >> 16) * LT_TILE_H - LT_HALO);
-            }
-            for (; i < nt; i++) {
-                const uint32_t jd = __ldg(w.job_desc + q0 + i);
-                const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
-                const int users = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
-                if (!mbar_wait(empty + i % LT_STAGES, (uint32_t) ((i / LT_STAGES - 1) & 1))) break;
-                issue(i, jd, users);
-            }
-        } else {
-            constexpr int PW = sizeof(PairPre) / 8;
-            double *dst = reinterpret_cast<double *>(s_pairs);
-            for (int i = lane - 1; i < 2 * N * PW; i += 31) {
-                const int rec = i / PW, k = i - rec * PW, tt = rec / N, h = rec - tt * N, t = min(t_first + tt, N - 1);
-                dst[i] = reinterpret_cast<const double *>(w.pairs + h * N + t)[k];
-            }
-            if (lane - 1 < N) s_th[lane - 1] = w.frames[lane - 1].energy_th;
-            mbar_arrive(pairs_bar);                  // release: the stores above are visible to whoever sees the phase complete
+    const int q0 = info.x, q1 = info.y, t_first = info.z, n_tiles_cta = q1 - q0 + 1;
+    // There is no producer warp.  A stage goes back to "empty" when every warp pass that overlaps its tile (the passes are consecutive, so
+    // their number follows from the tile's residual range) has arrived on the stage's barrier; the warp whose arrival completes that
+    // phase issues the box of the tile that comes LT_STAGES later into the same stage (one winner: compare-and-swap on the stage tag),
+    // topping the new tile's user count up to the barrier's fixed arrival count.
+    auto issue = [&](const int i, const uint32_t jd, const int users) {        // tile q0 + i, by one thread; the stage tag is already set
+        const int s = i % LT_STAGES;
+        const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
+        mbar_arrive_n(empty + s, (uint32_t) (LT_EMPTY_COUNT - users));
+        mbar_expect_tx(full + s, LT_TILE_BYTES);
+        tma_load_2d(ring + (size_t) s * LT_STAGE_STRIDE, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
+    };
+    auto tile_meta = [&](const int i, uint32_t &jd, int &users) {
+        if (i < LT_TILE_TABLE) { jd = (uint32_t) ((volatile int *) s_jd)[i]; users = ((volatile int *) s_users)[i]; return; }
+        jd = __ldg(w.job_desc + q0 + i);
+        const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
+        users = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
+    };
+    // lane 0 of a warp, after its pass is done with tile q0 + k: arrive; if that completed the stage's phase, bring in tile q0 + k + LT_STAGES
+    auto release = [&](const int k) {
+        const int s = k % LT_STAGES;
+        mbar_arrive(empty + s);
+        if (k + LT_STAGES < n_tiles_cta && mbar_test(empty + s, (uint32_t) ((k / LT_STAGES) & 1)) && atomicCAS(s_tag + s, q0 + k, q0 + k + LT_STAGES) == q0 + k) {
+            uint32_t jd; int users;
+            tile_meta(k + LT_STAGES, jd, users);
+            issue(k + LT_STAGES, jd, users);
         }
-        return;
+    };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_EMPTY_COUNT); s_tag[s] = q0 + s; }
+        mbar_init(pairs_bar, LT_CWARPS * 32);
+        mbar_fence_init();
+        if (w.tma_on) {
+            const int4 jd4 = __ldg(infop + 1), us4 = __ldg(infop + 2);
+            if (0 < n_tiles_cta && 0 < LT_STAGES) issue(0, (uint32_t) jd4.x, us4.x);
+            if (1 < n_tiles_cta && 1 < LT_STAGES) issue(1, (uint32_t) jd4.y, us4.y);
+            if (2 < n_tiles_cta && 2 < LT_STAGES) issue(2, (uint32_t) jd4.z, us4.z);
+            if (3 < n_tiles_cta && 3 < LT_STAGES) issue(3, (uint32_t) jd4.w, us4.w);
+        }
+    }
+    __syncthreads();                                 // cheap: nothing but the barrier set-up (and the first boxes' issue) precedes it
+    {   // every thread stages its share of the constants, then arrives on pairs_bar; nobody waits here
+        for (int i = threadIdx.x; i < min(n_tiles_cta, LT_TILE_TABLE); i += LT_CWARPS * 32) {
+            const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
+            s_jd[i] = (int) __ldg(w.job_desc + q0 + i);
+            s_users[i] = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
+        }
+        constexpr int PW = sizeof(PairPre) / 8;
+        double *dst = reinterpret_cast<double *>(s_pairs);
+        for (int i = threadIdx.x; i < 2 * N * PW; i += LT_CWARPS * 32) {
+            const int rec = i / PW, k = i - rec * PW, tt = rec / N, h = rec - tt * N, t = min(t_first + tt, N - 1);
+            dst[i] = reinterpret_cast<const double *>(w.pairs + h * N + t)[k];
+        }
+        if ((int) threadIdx.x < N) s_th[threadIdx.x] = w.frames[threadIdx.x].energy_th;
+        mbar_arrive(pairs_bar);                      // release: the stores above are visible to whoever sees the phase complete
     }
     // ---- consumer warps.  The per-residual arrays of the CTA's range are contiguous: one L2 prefetch per 128-byte line up front (the point
     // records of a pass are prefetched during the pass before it, below), so that only a warp's first pass waits on HBM for its inputs.
@@ -387,6 +403,7 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
         const float4 *wtp = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
         const float4 c0v = __ldg(colp), c1v = __ldg(colp + 1), w0v = __ldg(wtp), w1v = __ldg(wtp + 1);
         const uint32_t pht_next = (c + LT_CWARPS < c1) ? __ldg(w.r_pht + min((c + LT_CWARPS) * 32 + lane, w.R - 1)) : pht;     // for the L2 prefetch below
+        LT_STAMP();                                  // pass start
         if (!pairs_ready) { mbar_wait(pairs_bar, 0); pairs_ready = true; }
         const PairPre *ppp = (t - t_first < 2) ? s_pairs + (t - t_first) * N + h : w.pairs + h * N + t;
         const PairPre &pp = *ppp;
@@ -398,10 +415,11 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
             for (int q = q_lo; q <= q_hi; q++) { const int k = q - q0; ok = ok && lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1)); }
             tma_ok = __all_sync(0xffffffffu, ok);
         }
-        if (w.lt_mode == 1) {      // development: ring protocol only
+        LT_STAMP();                                  // tiles landed (header loads arrived)
+        if ((w.lt_mode & 1) == 1) {      // development: ring protocol only
             __syncwarp();
-            if (tma_ok && lane == 0) for (int q = q_lo; q <= q_hi; q++) mbar_arrive(empty + (q - q0) % LT_STAGES);
-            if (tma_ok) for (int q = q_hi + 1; q <= q_last; q++) { const int k = q - q0; if (!lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1))) break; __syncwarp(); if (lane == 0) mbar_arrive(empty + k % LT_STAGES); }
+            if (tma_ok && lane == 0) for (int q = q_lo; q <= q_hi; q++) release(q - q0);
+            if (tma_ok) for (int q = q_hi + 1; q <= q_last; q++) { const int k = q - q0; if (!lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1))) break; __syncwarp(); if (lane == 0) release(k); }
             continue;
         }
         // where this lane's taps come from: its staged tile, or the image itself
@@ -500,6 +518,7 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
                 sgy[i] = t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
             }
         }
+        LT_STAMP();                                  // taps done
         if (c + LT_CWARPS < c1) {                     // the point records of this warp's next pass: on their way to L2 while this one computes
             const int pn = (int) (pht_next & 0xffffffu);
             prefetch_l2(w.pt_idepth + pn); prefetch_l2(w.pt_x + pn); prefetch_l2(w.pt_y + pn); prefetch_l2(w.pt_colors + (size_t) pn * 8); prefetch_l2(w.pt_weights + (size_t) pn * 8);
@@ -508,12 +527,12 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
         // lanes read global memory) still count this pass as a user: wait for them and arrive, one by one.
         __syncwarp();
         if (tma_ok) {
-            if (lane == 0) for (int q = q_lo; q <= q_hi; q++) mbar_arrive(empty + (q - q0) % LT_STAGES);
+            if (lane == 0) for (int q = q_lo; q <= q_hi; q++) release(q - q0);
             for (int q = q_hi + 1; q <= q_last; q++) {
                 const int k = q - q0;
                 if (!lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1))) { tma_ok = false; break; }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty + k % LT_STAGES);
+                if (lane == 0) release(k);
             }
         }
         if (sample) {
@@ -705,10 +724,12 @@ __global__ void __launch_bounds__((LT_CWARPS + 1) * 32, 1) linearize_tile_kernel
                 }
             }
         }
+        LT_STAMP();                                  // pass done
         // chunk energy (fp64, fixed order)
         const double es = warp_sum_d(ret);
         if (lane == 0) w.energy_part[c] = es;
     }
+#undef LT_STAMP
 }
 
 }  // namespace cmlba

@@ -20,6 +20,8 @@ if [ "$mode" == "variants" ]; then
     done
   done
   unset CMLBA_NO_TMA
+  LT_COLD=0 CMLBA_LT_MODE=2 timeout 120 python tools/lt_trace.py > gpurun_out/${tag}_trace_warm.txt 2>&1
+  LT_COLD=1 CMLBA_LT_MODE=2 timeout 120 python tools/lt_trace.py > gpurun_out/${tag}_trace_cold.txt 2>&1
   CMLBA_LT_MODE=1 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/${tag}_bench_stream.json 2> gpurun_out/${tag}_bench_stream.err
   python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_stream.json'));print('stream-only', d['ms_per_step'], d['kernel_ms'])"
   CMLBA_LT_EXACT=1 timeout 300 python -m pytest tests/test_gpu_edge.py -m gpu -q --timeout 300 -p no:cacheprovider 2>&1 | tail -3
