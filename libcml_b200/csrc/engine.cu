@@ -281,8 +281,8 @@ public:
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
         CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
 #define LT_ATTR(CW, ST)                                                                                                                                  \
-    CK(cudaFuncSetAttribute(linearize_tile_kernel<false, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lt_smem_bytes(MAXF, CW, ST))); \
-    CK(cudaFuncSetAttribute(linearize_tile_kernel<true, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lt_smem_bytes(MAXF, CW, ST)));
+    CK(cudaFuncSetAttribute(linearize_tile_kernel<false, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min<size_t>(lt_smem_bytes(MAXF, CW, ST), 227 * 1024))); \
+    CK(cudaFuncSetAttribute(linearize_tile_kernel<true, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min<size_t>(lt_smem_bytes(MAXF, CW, ST), 227 * 1024)));
         LT_ATTR(12, 4) LT_ATTR(8, 4) LT_ATTR(16, 3) LT_ATTR(12, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
 #undef LT_ATTR
         if (const char *v = getenv("CMLBA_LT_VARIANT")) lt_variant = atoi(v);
