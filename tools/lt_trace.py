@@ -9,14 +9,20 @@ win = synth.make_config(wl)
 ba = DSOBundleAdjustment(device=0)
 cams = ba.loadWindow(win)
 ba.prepare(cams)
-ba.benchPass(3, 2, os.environ.get("LT_COLD", "1") == "1")
+br = ba.benchPass(3, 2, os.environ.get("LT_COLD", "1") == "1")
+print("bench: pass", br.ms_pass * 1e3, "us, linearize", br.ms_linearize * 1e3, "us")
 tr = ba.read("lt_trace", np.int64).reshape(-1, 16, 32)
-for cta in (0, 1, 73, 147):
-    if cta >= tr.shape[0]:
-        continue
-    t0 = tr[cta][tr[cta] > 0].min()
+g0 = tr[:, :, 30]; g1 = tr[:, :, 31]
+ok = g0 > 0
+gmin = g0[ok].min()
+print(f"globaltimer (ns): first warp start 0, last warp start {g0[ok].max() - gmin}, first end {g1[ok].min() - gmin}, last end {g1[ok].max() - gmin}")
+ends = np.array([g1[c][ok[c]].max() - gmin for c in range(tr.shape[0]) if ok[c].any()]); starts = np.array([g0[c][ok[c]].min() - gmin for c in range(tr.shape[0]) if ok[c].any()])
+print("CTA start ns: min/median/max", starts.min(), np.median(starts), starts.max(), " CTA end ns: min/median/max", ends.min(), np.median(ends), ends.max())
+print("slowest CTAs:", np.argsort(-ends)[:6], np.sort(-ends)[:6] * -1)
+for cta in (0, 73, int(np.argmax(ends))):
+    t0 = tr[cta, :, :30][tr[cta, :, :30] > 0].min()
     print(f"== CTA {cta}")
     for wv in range(16):
-        v = tr[cta, wv]; v = v[v > 0]
+        v = tr[cta, wv, :30]; v = v[v > 0]
         if v.size:
             print(f"  warp {wv:2d}: " + " ".join(f"{(x - t0) / 1965.0:6.2f}" for x in v))
