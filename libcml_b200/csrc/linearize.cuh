@@ -299,21 +299,9 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
     // development trace: stamp k of this warp (SM clock); compiled to a predicated-off store in normal runs
     long long *trace = (w.lt_mode & 2) ? w.lt_trace + ((size_t) blockIdx.x * 16 + warp) * 32 : nullptr;
     int tr_k = 0;
-#define LT_STAMP() do { if (trace && lane == 0 && tr_k < 30) trace[tr_k++] = clock64(); } while (0)
+#define LT_STAMP() do { if (trace && lane == 0 && tr_k < 32) trace[tr_k++] = clock64(); } while (0)
     LT_STAMP();
-    if (trace && lane == 0) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); trace[30] = gt; }
     const int r_first = c0 * 32, r_last = min(c1 * 32, w.R) - 1;
-    // the per-residual scalars of this warp's first pass are requested before anything else (they only depend on the block index): they
-    // travel together with the CTA record below instead of one memory round trip later.  Both state buffers: ctrl->cur is itself a load.
-    uint32_t pht = 0; int job = 0, sbase = 0, src = 0; uint8_t alive_ld = 0, st_a = 0, st_b = 0, nst = 0; float e_a = 0.f, e_b = 0.f, ne = 0.f;
-    auto load_hdr = [&](const int cc) {
-        const int rl = min(cc * 32 + lane, w.R - 1);
-        pht = __ldg(w.r_pht + rl); job = __ldg(w.r_job + rl);
-        alive_ld = w.r_alive[rl]; st_a = w.r_state[0][rl]; st_b = w.r_state[1][rl]; e_a = w.r_energy[0][rl]; e_b = w.r_energy[1][rl];
-        nst = w.r_new_state[rl]; ne = w.r_new_energy[rl];
-        sbase = __ldg(w.seg_base + cc); src = __ldg(w.r_src + rl);
-    };
-    if (c0 + warp < c1) load_hdr(c0 + warp);
     // one record per CTA, prepared by bin_segments_kernel: tile jobs [q0, q1] of the CTA (all non-empty), first target, and the descriptors /
     // user counts of its first four tiles -- a single load before the first boxes can be issued
     const int4 *infop = reinterpret_cast<const int4 *>(w.cta_info + (size_t) blockIdx.x * 16);
@@ -395,10 +383,17 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
     for (int c = c0 + warp; c < c1; c += LT_CWARPS) {
         const int r = c * 32 + lane;
         const bool in_chunk = r < w.R;
+        const int r_ld = in_chunk ? r : w.R - 1;
         // all per-residual scalars are requested together (one exposed latency), then the point record
-        if (c != c0 + warp) load_hdr(c);
-        const uint8_t st = in_chunk ? (cur ? st_b : st_a) : (uint8_t) RES_OOB;
-        const float e_old = cur ? e_b : e_a;
+        const uint32_t pht = __ldg(w.r_pht + r_ld);
+        const int job = __ldg(w.r_job + r_ld);
+        const uint8_t alive_ld = w.r_alive[r_ld];
+        const uint8_t st = in_chunk ? w.r_state[cur][r_ld] : (uint8_t) RES_OOB;
+        const float e_old = w.r_energy[cur][r_ld];
+        uint8_t nst = w.r_new_state[r_ld];
+        float ne = w.r_new_energy[r_ld];
+        const int sbase = __ldg(w.seg_base + c);
+        const int src = __ldg(w.r_src + r_ld);
         const int p = (int) (pht & 0xffffffu), h = (int) ((pht >> 24) & 15u), t = (int) (pht >> 28);
         const bool valid = in_chunk && alive_ld;
         const uint32_t jd = __ldg(w.job_desc + job);
@@ -545,9 +540,6 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
             const float wts[8] = {w0v.x, w0v.y, w0v.z, w0v.w, w1v.x, w1v.y, w1v.z, w1v.w};
             const float b0 = pp.b0;
             const float sqrt_cth = sqrtf(w.cth);
-            // exposure transition a * colour + b (BA:229, fp64 in the reference, result cast to float): a and b as float pairs, so the eight
-            // evaluations are three fp32 FMAs each instead of two conversions and a DFMA; same value up to the final float rounding
-            const float ea_h = (float) pp.a, ea_l = (float) (pp.a - (double) ea_h), eb_h = (float) pp.b, eb_l = (float) (pp.b - (double) eb_h);
             float J00 = 0, J11 = 0, J10 = 0, A00 = 0, A01 = 0, A10 = 0, A11 = 0, B00 = 0, B01 = 0, B11 = 0, wJI2 = 0, E = 0;
             float JIr0 = 0, JIr1 = 0, Jabr0 = 0, Jabr1 = 0, rr = 0;
             bool finite = true;
@@ -555,7 +547,7 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
             for (int i = 0; i < 8; i++) {
                 const float I = sI[i], gx = sgx[i], gy = sgy[i];
                 finite = finite && isfinite(I) && isfinite(gx) && isfinite(gy);
-                const float refReal = fmaf(ea_h, col[i], eb_h) + fmaf(ea_l, col[i], eb_l);     // exposureTransition (BA:229)
+                const float refReal = (float) (pp.a * (double) col[i] + pp.b);     // exposureTransition (BA:229)
                 const float res = I - refReal;
                 const float ar = fabsf(res);
                 // MUFU-based division / rsqrt / sqrt (<= 2 ulp, ~2e-7 relative; the parity tolerance is 1e-4)
@@ -602,10 +594,9 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
                     const float Jpdd1 = (float) (dr * (pp.t0[1] - pp.t0[2] * vd) * (double) fyf);
                     double dCx[4], dCy[4];
                     dCx[2] = dr * (pp.R0[6] * ud - pp.R0[0]);
-                    const double ifx = 1.0 / (double) fxf, ify = 1.0 / (double) fyf;        // warp-uniform: hoisted by the compiler
-                    dCx[3] = (double) (fxf * drescale) * (pp.R0[7] * ud - pp.R0[1]) * ify;
+                    dCx[3] = (double) (fxf * drescale) * (pp.R0[7] * ud - pp.R0[1]) / (double) fyf;
                     dCx[0] = klx * dCx[2]; dCx[1] = kly * dCx[3];
-                    dCy[2] = (double) (fyf * drescale) * (pp.R0[6] * vd - pp.R0[3]) * ifx;
+                    dCy[2] = (double) (fyf * drescale) * (pp.R0[6] * vd - pp.R0[3]) / (double) fxf;
                     dCy[3] = dr * (pp.R0[7] * vd - pp.R0[4]);
                     dCy[0] = klx * dCy[2]; dCy[1] = kly * dCy[3];
                     const double sF = (double) w.scaleF, sC = (double) w.scaleC;
@@ -738,7 +729,6 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
         const double es = warp_sum_d(ret);
         if (lane == 0) w.energy_part[c] = es;
     }
-    if (trace && lane == 0) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); trace[31] = gt; }
 #undef LT_STAMP
 }
 
