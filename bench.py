@@ -300,7 +300,7 @@ def main():
                       "l2": "flushed between timed passes (384 MB write outside the timed region)", "parallelism": f"points sharded x{world}, frames replicated" + ("" if world == 1 else (", reduced system + post-linearize records over NVLink peer memory (cudaIpc)" if getattr(ba, "peer_memory", False) else ", reduced system by ncclAllReduce, post-linearize records by ncclAllGather")),
                       "pass": "linearize+accumulate+schur+stitch"},
            "ms_per_step_l2_warm": ms_pass_warm, "value_l2_warm": world * R / (ms_pass_warm * 1e-3),
-           "kernel_ms": {"linearize_accumulate": br.ms_linearize, "schur": br.ms_schur, "stitch_assemble": br.ms_stitch,
+           "kernel_ms": {"linearize_accumulate": br.ms_linearize, "schur_stitch_assemble" if br.ms_stitch < 0.004 else "schur": br.ms_schur, "stitch_assemble": br.ms_stitch,
                          "linearize_accumulate_l2_warm": brw.ms_linearize, "event_overhead_per_interval": br.ms_accumulate,
                          "note": "event-to-event intervals of a separate loop; each includes one event-record overhead"},
            "run": {"gpu_ms": run_gpu_ms, "kernel_launches": run_launches, "iterations": e2e_iters},

@@ -249,7 +249,8 @@ public:
     DevBuf<long long> d_lt_trace;
     TileMaps tile_maps;           // one tensor map per window frame (re-encoded by build_device_window)
     int n_sm = 148;
-    int lt_variant = 0, lt_mode = 0, lt_exact = 0;   // development switches (CMLBA_LT_VARIANT, CMLBA_LT_MODE): kernel shape, streaming-only mode
+    int lt_variant = 0, lt_mode = 0, lt_exact = 0;
+    int tail_cluster_max = 0;     // largest cluster tail_kernel can be scheduled with (0: fused tail unavailable -> schur / stitch_pair / assemble)   // development switches (CMLBA_LT_VARIANT, CMLBA_LT_MODE): kernel shape, streaming-only mode
     size_t seg_cap = 0;
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
         d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj, d_T0, d_T1, d_dbg, d_acc0, d_acc1, d_sc_part, d_stage[MAXF];
@@ -285,6 +286,19 @@ public:
     CK(cudaFuncSetAttribute(linearize_tile_kernel<true, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min<size_t>(lt_smem_bytes(MAXF, CW, ST), 227 * 1024)));
         LT_ATTR(12, 4) LT_ATTR(8, 4) LT_ATTR(16, 3) LT_ATTR(12, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
 #undef LT_ATTR
+        // fused tail (tail.cuh): one cluster per host frame, one CTA per frame -> clusters of 8 (portable) or 16 (opt-in) CTAs
+        if (!getenv("CMLBA_NO_TAIL_FUSION") && cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tail_smem_bytes(MAXF)) == cudaSuccess) {
+            tail_cluster_max = 8;
+            if (cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                cudaLaunchConfig_t lc = {}; cudaLaunchAttribute at[1];
+                lc.gridDim = dim3(16); lc.blockDim = dim3(TAIL_THREADS); lc.dynamicSmemBytes = tail_smem_bytes(MAXF);
+                at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.attrs = at; lc.numAttrs = 1;
+                int nc = 0;
+                if (cudaOccupancyMaxActiveClusters(&nc, tail_kernel, &lc) == cudaSuccess && nc >= 1) tail_cluster_max = 16;
+            }
+        }
+        cudaGetLastError();
         if (const char *v = getenv("CMLBA_LT_VARIANT")) lt_variant = atoi(v);
         if (const char *v = getenv("CMLBA_LT_MODE")) lt_mode = atoi(v);
         if (const char *v = getenv("CMLBA_LT_EXACT")) lt_exact = atoi(v);
@@ -685,7 +699,7 @@ public:
                 dw.marg_mode = 1;
                 launch_linearize(0, 0);                                  // tryMarginalize's resetOOB + linearize + applyRes + fixLinearization (BA:2289-2300)
                 commit_candidate_kernel<<<1, 32, 0, stream>>>(dw); launches++;
-                launch_schur(0); launch_stitch(0);
+                launch_tail(0);
                 const int nn_ = dw.n * dw.n, n_ = dw.n;
                 std::vector<double> sys((size_t) 2 * nn_ + 2 * n_);
                 if (cudaMemcpyAsync(sys.data(), d_sys.p, sys.size() * 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { set_error("marginalize_points: device error"); rc = CMLBA_ERR_CUDA; }
@@ -1130,6 +1144,19 @@ public:
     void launch_schur(int respect_done) {
         if (dw.n_sc_chunks > 0) { schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, respect_done); launches++; }
     }
+    // Schur complement + stitching + assembly of sys = [HA | bA | H_sc | b_sc]: one cluster kernel when a cluster of >= N CTAs is available
+    bool tail_fused() const { return dw.N <= tail_cluster_max && dw.n_sc_chunks > 0; }
+    void launch_tail(int respect_done) {
+        if (!tail_fused()) { launch_schur(respect_done); launch_stitch(respect_done); return; }
+        const int cs = dw.N <= 8 ? 8 : 16;
+        if (dw.p2p_on) dw.p2p_epoch = ++p2p_epoch;       // the same count on every rank: one exchange per stitched system
+        cudaLaunchConfig_t lc = {}; cudaLaunchAttribute at[1];
+        lc.gridDim = dim3(dw.N * cs); lc.blockDim = dim3(TAIL_THREADS); lc.dynamicSmemBytes = tail_smem_bytes(dw.N); lc.stream = stream;
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        if (cudaLaunchKernelEx(&lc, tail_kernel, dw, respect_done) != cudaSuccess) { set_error(std::string("tail_kernel launch: ") + cudaGetErrorString(cudaGetLastError())); }
+        launches++;
+    }
     // one CTA per ordered frame pair, then the gather into sys = [HA | bA | H_sc | b_sc]
     void launch_stitch(int respect_done) {
         const int N = dw.N, n = dw.n;
@@ -1138,8 +1165,7 @@ public:
         assemble_kernel<<<(2 * n * n + 2 * n + 255) / 256 + 3, 256, 0, stream>>>(dw, respect_done); launches++;   // +3 CTAs: 20 warps for HA[C,C], bA[C]
     }
     int launch_solve_sequence(int respect_done) {
-        launch_schur(respect_done);
-        launch_stitch(respect_done);
+        launch_tail(respect_done);
         if (world > 1 && !dw.p2p_on) { int rc = allreduce_system(); if (rc) return rc; }      // with peer memory solve_kernel sums the ranks itself
         solve_kernel<<<1, 256, solve_smem(), stream>>>(dw, respect_done); launches++;
         if (dw.P > 0) { point_step_kernel<<<dw.n_pt_blocks, 256, 0, stream>>>(dw, respect_done); launches++; }
@@ -1315,7 +1341,7 @@ public:
         };
         // the committed buffers must hold a linearization for schur/stitch to chew on
         launch_linearize(0, 0); launch_post(0, 0);
-        for (int i = 0; i < warmup; i++) { flush(); launch_linearize(0, 0); launch_schur(0); launch_stitch(0); }
+        for (int i = 0; i < warmup; i++) { flush(); launch_linearize(0, 0); launch_tail(0); }
         CK(cudaStreamSynchronize(stream));
         double tot = 0, tk[4] = {0, 0, 0, 0};
         const int l0 = launches;
@@ -1323,7 +1349,7 @@ public:
             flush();
             CK(cudaEventRecord(ev[0], stream));
             launch_linearize(0, 0);
-            launch_schur(0); launch_stitch(0);
+            launch_tail(0);
             if (world > 1) { int rc = allreduce_system(); if (rc) return rc; }
             CK(cudaEventRecord(ev[1], stream));
             CK(cudaStreamSynchronize(stream));
@@ -1334,8 +1360,8 @@ public:
             flush();
             CK(cudaEventRecord(ev[0], stream)); launch_linearize(0, 0);
             CK(cudaEventRecord(ev[1], stream));
-            CK(cudaEventRecord(ev[2], stream)); launch_schur(0);
-            CK(cudaEventRecord(ev[3], stream)); launch_stitch(0);
+            CK(cudaEventRecord(ev[2], stream)); if (tail_fused()) launch_tail(0); else launch_schur(0);      // fused: the whole tail is reported as ms_schur
+            CK(cudaEventRecord(ev[3], stream)); if (!tail_fused()) launch_stitch(0);
             CK(cudaEventRecord(ev[4], stream));
             CK(cudaStreamSynchronize(stream));
             for (int k = 0; k < 4; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); tk[k] += ms; }

@@ -457,9 +457,9 @@ __global__ void __launch_bounds__(32) p2p_barrier_kernel(const DevWin w) {
 __device__ __forceinline__ double sum_slots(const double *st, const int N, const int S, const int a, const int o_row, const int o_col) {
     double v = 0.0;
 #pragma unroll 8
-    for (int k = 0; k < N; k++) { const double x = st[(size_t) (a * N + (k != a ? k : (a + 1) % N)) * S + o_row]; v += (k != a) ? x : 0.0; }
+    for (int k = 0; k < N; k++) { const double x = __ldcg(st + (size_t) (a * N + (k != a ? k : (a + 1) % N)) * S + o_row); v += (k != a) ? x : 0.0; }
 #pragma unroll 8
-    for (int k = 0; k < N; k++) { const double x = st[(size_t) ((k != a ? k : (a + 1) % N) * N + a) * S + o_col]; v += (k != a) ? x : 0.0; }
+    for (int k = 0; k < N; k++) { const double x = __ldcg(st + (size_t) ((k != a ? k : (a + 1) % N) * N + a) * S + o_col); v += (k != a) ? x : 0.0; }
     return v;
 }
 
@@ -545,6 +545,10 @@ __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int
         }
     }
 }
+
+}  // namespace cmlba
+#include "tail.cuh"
+namespace cmlba {
 
 // ------------------------------------------------------------------------------------------------
 // Reduced camera system: assemble, damp, Jacobi-scale, LDL^T (lower triangle, like Eigen's default), solve,
