@@ -1104,7 +1104,7 @@ public:
     }
 
     // ------------------------------------------------------------------ kernel sequences
-    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128 + 4 * ACC_N); }
+    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128 + ST_SLICES * ACC_N); }
     size_t solve_smem() const { const int n = dw.n; return sizeof(double) * ((size_t) n * n + 4 * n + 256); }
     size_t schur_smem() const { return schur_smem_bytes(dw.N); }
 
@@ -1148,7 +1148,7 @@ public:
     bool tail_fused() const { return dw.N <= tail_cluster_max && dw.n_sc_chunks > 0; }
     void launch_tail(int respect_done) {
         if (!tail_fused()) { launch_schur(respect_done); launch_stitch(respect_done); return; }
-        const int cs = dw.N <= 8 ? 8 : 16;
+        const int cs = tail_cluster_max;                 // 16 CTAs per host frame when the device can co-schedule them (twice the Schur parallelism), else 8
         if (dw.p2p_on) dw.p2p_epoch = ++p2p_epoch;       // the same count on every rank: one exchange per stitched system
         cudaLaunchConfig_t lc = {}; cudaLaunchAttribute at[1];
         lc.gridDim = dim3(dw.N * cs); lc.blockDim = dim3(TAIL_THREADS); lc.dynamicSmemBytes = tail_smem_bytes(dw.N); lc.stream = stream;

@@ -265,7 +265,57 @@ constexpr int ST_A_TT = 0, ST_A_IT = 64, ST_A_II = 128, ST_A_TC = 192, ST_A_IC =
               ST_S_JI = 296, ST_S_II = 360, ST_S_JC = 424, ST_S_IC = 456, ST_BS_J = 488, ST_BS_I = 496, ST_S_JK = 504;
 __host__ __device__ __forceinline__ int st_stride(int N) { return ST_S_JK + 64 * N; }
 constexpr int ST_THREADS = 512;
-constexpr int ST_LIST = 2048;    // partial-block indices compacted per batch (stitch_pair_kernel)
+constexpr int ST_LIST = 4096;    // partial-block indices compacted per batch
+constexpr int ST_SLICES = ST_THREADS / ACC_N;    // threads per entry of the 13x13 block (5)
+
+// 13x13 block of bin (host i -> target j) from the sampling kernel's partial blocks: those tagged (i, j) in seg_hdr.  The partials of one
+// target are contiguous (seg_t_begin); the CTA (ST_THREADS threads) compacts the matching indices batch-wise -- four tags per thread,
+// block scan of the match counts -- then ST_SLICES threads per entry sum contiguous parts of the list with 16 loads in flight.  Fixed
+// order, no atomics.  Apart: [ST_SLICES][ACC_N] doubles of shared memory; the caller adds the slices after a __syncthreads().
+__device__ __forceinline__ void sum_bin_partials(const DevWin &w, const int cur, const int i, const int j, double *Apart) {
+    __shared__ int s_list[ST_LIST];
+    __shared__ int s_wtot[ST_THREADS / 32];
+    __shared__ int s_n;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int sb = w.seg_t_begin[j], se = w.seg_t_begin[j + 1];
+    const uint8_t want = (uint8_t) (i | (j << 4));
+    const float *part = w.acc_part[cur];
+    const int e = tid % ACC_N, q = tid / ACC_N;
+    double acc = 0.0;
+    int base = sb;
+    do {
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        while (base < se && s_n + 4 * ST_THREADS <= ST_LIST) {
+            const int k0 = base + 4 * tid;
+            unsigned m = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) if (k0 + b < se && __ldg(w.seg_hdr + k0 + b) == want) m |= 1u << b;
+            const int c = __popc(m);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            if (lane == 31) s_wtot[wid] = incl;
+            __syncthreads();
+            int off = s_n + incl - c;
+            for (int ww = 0; ww < wid; ww++) off += s_wtot[ww];
+#pragma unroll
+            for (int b = 0; b < 4; b++) if ((m >> b) & 1u) s_list[off++] = k0 + b;
+            __syncthreads();
+            if (tid == 0) { int t = 0; for (int ww = 0; ww < ST_THREADS / 32; ww++) t += s_wtot[ww]; s_n += t; }
+            __syncthreads();
+            base += 4 * ST_THREADS;
+        }
+        const int n = s_n;
+        if (tid < ST_SLICES * ACC_N) {
+            const int len = (n + ST_SLICES - 1) / ST_SLICES, a = min(q * len, n), b = min(a + len, n);
+#pragma unroll 16
+            for (int k = a; k < b; k++) acc += (double) __ldg(part + (size_t) s_list[k] * ACC_N + e);
+        }
+        __syncthreads();
+    } while (base < se);
+    if (tid < ST_SLICES * ACC_N) Apart[tid] = acc;
+}
 
 __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
@@ -292,7 +342,7 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
     double *A = atd + NB;          // [ACC_N]  packed 13x13 block of bin (i -> j)
     double *Y = A + ACC_N;         // [8][8]   sum_k D_jk AH_ik^T
     double *M = Y + 64;            // [8][8]   AH_ij A8
-    double *Apart = M + 64;        // [4][ACC_N] partial sums of A
+    double *Apart = M + 64;        // [ST_SLICES][ACC_N] partial sums of A
     for (int e = tid; e < 8 * NB + 40; e += ST_THREADS) {
         int off;
         if (e < 8 * NB) off = j * 8 * NB + e;
@@ -304,49 +354,11 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
         for (int c = cb; c < ce; c++, src += w.sc_stride) s += (double) __ldg(src);
         Dj[e] = s;                 // Dj, Ej, EBj are contiguous
     }
-    {   // 13x13 block of bin (i -> j): the partial blocks tagged (host i, target j) in seg_hdr.  The partials of one target are contiguous
-        // (seg_t_begin); the CTA compacts the matching indices batch-wise (ballot + warp counts), then four threads per entry sum
-        // contiguous parts of the list -- fixed order, no atomics.
-        __shared__ int s_list[ST_LIST];
-        __shared__ int s_wcnt[ST_THREADS / 32];
-        __shared__ int s_n;
-        const int sb = w.seg_t_begin[j], se = w.seg_t_begin[j + 1];
-        const uint8_t want = (uint8_t) (i | (j << 4));
-        const float *part = w.acc_part[cur];
-        const int e = tid % ACC_N, q = tid / ACC_N, lane = tid & 31, wid = tid >> 5;
-        double acc = 0.0;
-        int base = sb;
-        do {
-            if (tid == 0) s_n = 0;
-            __syncthreads();
-            while (base < se && s_n + ST_THREADS <= ST_LIST) {
-                const int k = base + tid;
-                const bool mt = k < se && w.seg_hdr[k] == want;
-                const unsigned bal = __ballot_sync(0xffffffffu, mt);
-                if (lane == 0) s_wcnt[wid] = __popc(bal);
-                __syncthreads();
-                int off = s_n;
-                for (int ww = 0; ww < wid; ww++) off += s_wcnt[ww];
-                if (mt) s_list[off + __popc(bal & ((1u << lane) - 1u))] = k;
-                __syncthreads();
-                if (tid == 0) { int t = 0; for (int ww = 0; ww < ST_THREADS / 32; ww++) t += s_wcnt[ww]; s_n += t; }
-                __syncthreads();
-                base += ST_THREADS;
-            }
-            const int n = s_n;
-            if (tid < 4 * ACC_N) {
-                const int len = (n + 3) >> 2, a = min(q * len, n), b = min(a + len, n);
-#pragma unroll 8
-                for (int k = a; k < b; k++) acc += (double) __ldg(part + (size_t) s_list[k] * ACC_N + e);
-            }
-            __syncthreads();
-        } while (base < se);
-        if (tid < 4 * ACC_N) Apart[tid] = acc;
-    }
+    sum_bin_partials(w, cur, i, j, Apart);
     for (int e = tid; e < N * 64; e += ST_THREADS) G[e] = w.AH[(size_t) (i * N) * 64 + e];
     for (int e = tid; e < NB; e += ST_THREADS) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
     __syncthreads();
-    if (tid < ACC_N) A[tid] = (Apart[tid] + Apart[ACC_N + tid]) + (Apart[2 * ACC_N + tid] + Apart[3 * ACC_N + tid]);
+    if (tid < ACC_N) A[tid] = ((Apart[tid] + Apart[ACC_N + tid]) + (Apart[2 * ACC_N + tid] + Apart[3 * ACC_N + tid])) + Apart[4 * ACC_N + tid];
     __syncthreads();
     const double *AHj = G + j * 64, *atj = atd + j * 8;
     {

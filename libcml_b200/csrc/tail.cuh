@@ -25,7 +25,7 @@ constexpr int TAIL_TPT = 2;          // 4x4 tiles of the rank update per thread 
 __host__ __device__ __forceinline__ size_t tail_smem_bytes(int N) {
     const size_t NB = 8 * (size_t) N;
     const size_t phase1 = sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * (NB + SCZ_PAD));
-    const size_t phase2 = sizeof(double) * (8 * NB + 40 + (size_t) N * 64 + NB + ACC_N + 128 + 4 * ACC_N);
+    const size_t phase2 = sizeof(double) * (8 * NB + 40 + (size_t) N * 64 + NB + ACC_N + 128 + ST_SLICES * ACC_N);
     const size_t part = sizeof(float) * (((NB * NB + NB * 5 + 20) + 3) & ~(size_t) 3);
     return (phase1 > phase2 ? phase1 : phase2) + part;
 }
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const DevWin w, c
     const int N = w.N, NB = 8 * N, ZS = NB + SCZ_PAD, tid = threadIdx.x, i = blockIdx.x / CS;
     const int cur = w.ctrl->cur;
     const size_t phase1 = sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * ZS);
-    const size_t phase2 = sizeof(double) * ((size_t) 8 * NB + 40 + (size_t) N * 64 + NB + ACC_N + 128 + 4 * ACC_N);
+    const size_t phase2 = sizeof(double) * ((size_t) 8 * NB + 40 + (size_t) N * 64 + NB + ACC_N + 128 + ST_SLICES * ACC_N);
     float *part = reinterpret_cast<float *>(tail_smem + (phase1 > phase2 ? phase1 : phase2));      // this CTA's Schur partial, layout of sc_part
     float *sT = reinterpret_cast<float *>(tail_smem);                  // [SC_CHUNK][N][T_STRIDE] raw Schur rows
     float *sZ = sT + SC_CHUNK * N * T_STRIDE;                          // [SC_CHUNK][ZS]          augmented, scaled
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const DevWin w, c
             double *A = atd + NB;          // [ACC_N]  packed 13x13 block of bin (i -> j)
             double *Y = A + ACC_N;         // [8][8]   sum_k D_jk AH_ik^T
             double *M = Y + 64;            // [8][8]   AH_ij A8
-            double *Apart = M + 64;        // [4][ACC_N] partial sums of A
+            double *Apart = M + 64;        // [ST_SLICES][ACC_N] partial sums of A
             for (int e = tid; e < 8 * NB + 40; e += TAIL_THREADS) {
                 int off;
                 if (e < 8 * NB) off = j * 8 * NB + e;
@@ -242,47 +242,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const DevWin w, c
                 for (int k = 0; k < CS; k++) s += (double) cluster.map_shared_rank(part, k)[off];
                 Dj[e] = s;                 // Dj, Ej, EBj are contiguous
             }
-            {   // 13x13 block of bin (i -> j): the sampling kernel's partial blocks tagged (host i, target j), see stitch_pair_kernel
-                __shared__ int s_list[ST_LIST];
-                __shared__ int s_wcnt[TAIL_THREADS / 32];
-                __shared__ int s_n;
-                const int sb = w.seg_t_begin[j], se = w.seg_t_begin[j + 1];
-                const uint8_t want = (uint8_t) (i | (j << 4));
-                const float *pblk = w.acc_part[cur];
-                const int e = tid % ACC_N, q = tid / ACC_N, lane = tid & 31, wid = tid >> 5;
-                double accA = 0.0;
-                int base = sb;
-                do {
-                    if (tid == 0) s_n = 0;
-                    __syncthreads();
-                    while (base < se && s_n + TAIL_THREADS <= ST_LIST) {
-                        const int k = base + tid;
-                        const bool mt = k < se && w.seg_hdr[k] == want;
-                        const unsigned bal = __ballot_sync(0xffffffffu, mt);
-                        if (lane == 0) s_wcnt[wid] = __popc(bal);
-                        __syncthreads();
-                        int off = s_n;
-                        for (int ww = 0; ww < wid; ww++) off += s_wcnt[ww];
-                        if (mt) s_list[off + __popc(bal & ((1u << lane) - 1u))] = k;
-                        __syncthreads();
-                        if (tid == 0) { int t = 0; for (int ww = 0; ww < TAIL_THREADS / 32; ww++) t += s_wcnt[ww]; s_n += t; }
-                        __syncthreads();
-                        base += TAIL_THREADS;
-                    }
-                    const int n = s_n;
-                    if (tid < 4 * ACC_N) {
-                        const int len = (n + 3) >> 2, a = min(q * len, n), b = min(a + len, n);
-#pragma unroll 8
-                        for (int k = a; k < b; k++) accA += (double) __ldg(pblk + (size_t) s_list[k] * ACC_N + e);
-                    }
-                    __syncthreads();
-                } while (base < se);
-                if (tid < 4 * ACC_N) Apart[tid] = accA;
-            }
+            sum_bin_partials(w, cur, i, j, Apart);        // 13x13 block of bin (i -> j) from the sampling kernel's partial blocks
             for (int e = tid; e < N * 64; e += TAIL_THREADS) G[e] = w.AH[(size_t) (i * N) * 64 + e];
             for (int e = tid; e < NB; e += TAIL_THREADS) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
             __syncthreads();
-            if (tid < ACC_N) A[tid] = (Apart[tid] + Apart[ACC_N + tid]) + (Apart[2 * ACC_N + tid] + Apart[3 * ACC_N + tid]);
+            if (tid < ACC_N) A[tid] = ((Apart[tid] + Apart[ACC_N + tid]) + (Apart[2 * ACC_N + tid] + Apart[3 * ACC_N + tid])) + Apart[4 * ACC_N + tid];
             __syncthreads();
             const double *AHj = G + j * 64, *atj = atd + j * 8;
             {
