@@ -31,6 +31,6 @@ echo "bench rc=$?"
 cat gpurun_out/${tag}_bench.json | head -c 3000
 if [ "$mode" != "quick" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${tag}_ncu_l.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'linearize_tile|schur|stitch|assemble|solve|post_lin|point_step|bin_' -s 20 -c 14 -o gpurun_out/${tag}_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${tag}_ncu_f.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'linearize_tile|tail_kernel|schur|stitch|assemble|solve|post_lin|point_step|bin_' -s 20 -c 14 -o gpurun_out/${tag}_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${tag}_ncu_f.log 2>&1
   ls -la gpurun_out/${tag}_* | tail -20
 fi
