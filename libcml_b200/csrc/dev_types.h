@@ -18,7 +18,7 @@ constexpr int LT_BOX_H = LT_TILE_H + 2 * LT_HALO;     // 38 rows
 constexpr int LT_TILE_BYTES = LT_BOX_W * LT_BOX_H * 16;   // 42 560 B of float4 texels per staged tile
 constexpr int LT_STAGE_STRIDE = (LT_TILE_BYTES + 127) & ~127;   // TMA destinations are 128-byte aligned
 // ring depth and consumer warps per CTA (+1 producer warp) are template parameters of the kernel (Engine::launch_linearize picks the variant)
-constexpr int LT_SCR_STRIDE = 36;                     // floats per lane row of the per-warp reduction scratch (32 + pad, keeps 16-byte alignment)
+constexpr int ACC_SLICES = 3;                         // CTAs per (host,target) bin that evaluate addToHessianTop from the Jacobian records
 constexpr int P2P_POST_CAND_MAX = 65536;      // candidates per rank record that fit the peer-memory exchange (else NCCL all-gather)
 constexpr size_t P2P_POST_DOUBLES = 8 + P2P_POST_CAND_MAX / 2;
 constexpr size_t P2P_SLOT_DOUBLES = 2 * (size_t) (8 * MAXF + 4) * (8 * MAXF + 4) + 2 * (8 * MAXF + 4);   // sys at the largest window
@@ -128,9 +128,6 @@ struct DevWin {
     uint32_t *r_pht;               // [R] device point | host << 24 | target << 28
     int *r_job;                    // [R] tile job of the residual
     int *r_src;                    // [R] host-order index of the residual
-    int *seg_cnt, *seg_base;       // [n_chunks] (+1) segments (runs of one (h,t) pair) per warp pass and their exclusive scan; seg_base[n_chunks] = total
-    uint8_t *seg_hdr;              // [segments] h | t << 4 of every partial sum in acc_part
-    int *seg_t_begin;              // [N+1] first partial of every target frame (partials are sorted by target)
     int *bin_ticket;               // last-block counters of the binning kernels
     // final states in HOST order, written by the fixLinearization pass (what finish_run reads back)
     uint8_t *fin_state, *fin_alive;
@@ -142,12 +139,12 @@ struct DevWin {
     float *r_new_energy, *r_new_energy_wo;
     uint8_t *r_alive;
     float *r_center;               // [R][3] centerProjectedTo
-    float *rj;                     // [R][RJ_STRIDE] candidate Jacobian records
+    float *rj[2];                  // [R][RJ_STRIDE] Jacobian records (committed / candidate) in the HOST's residual order; rec[35] = 1 marks a good residual
     float *T[2];                   // [P][N][T_STRIDE]
     float *dbg;                    // optional [R][40]: resF[8] JIdx[16] JabF[16]
     // partial sums
     double *energy_part;           // [n_chunks]
-    float *acc_part[2];            // [segments][ACC_N] partial 13x13 blocks, one per (warp pass, (h,t) run)
+    float *acc_bin;                // [N*N (bin = t*N+h)][ACC_SLICES][ACC_N] 13x13 blocks of the committed linearization (accumulate role of schur_acc_kernel)
     float *sc_part;                // [n_sc_chunks][sc_stride]
     int sc_stride;                 // (8N)^2 + 32N + 8N + 16 + 4 (padded to 4)
     const int *sc_chunk_host, *sc_chunk_begin, *sc_chunk_count;

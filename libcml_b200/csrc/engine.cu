@@ -242,18 +242,17 @@ public:
     DevBuf<int> d_pt_host, d_pt_num_good, d_pt_ngood_cur, d_r_point, d_res_bin_begin, d_sc_chunk_host,
         d_sc_chunk_begin, d_sc_chunk_count, d_host_chunk_begin;
     // tile binning (linearize.cuh): sorted residual order, tile jobs, partial-block bookkeeping, final states in host order
-    DevBuf<int> d_bin_key, d_bin_hist, d_bin_offs, d_job_of_tile, d_r_job, d_r_src, d_seg_cnt, d_seg_base, d_seg_t_begin, d_bin_ticket, d_job_begin, d_cta_info;
+    DevBuf<int> d_bin_key, d_bin_hist, d_bin_offs, d_job_of_tile, d_r_job, d_r_src, d_bin_ticket, d_job_begin, d_cta_info;
     DevBuf<uint32_t> d_job_desc, d_r_pht;
-    DevBuf<uint8_t> d_seg_hdr, d_fin_state, d_fin_alive;
+    DevBuf<uint8_t> d_fin_state, d_fin_alive;
     DevBuf<float> d_fin_energy;
     DevBuf<long long> d_lt_trace;
     TileMaps tile_maps;           // one tensor map per window frame (re-encoded by build_device_window)
     int n_sm = 148;
     int lt_variant = 0, lt_mode = 0, lt_exact = 0;
     int tail_cluster_max = 0;     // largest cluster tail_kernel can be scheduled with (0: fused tail unavailable -> schur / stitch_pair / assemble)   // development switches (CMLBA_LT_VARIANT, CMLBA_LT_MODE): kernel shape, streaming-only mode
-    size_t seg_cap = 0;
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
-        d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj, d_T0, d_T1, d_dbg, d_acc0, d_acc1, d_sc_part, d_stage[MAXF];
+        d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj0, d_rj1, d_T0, d_T1, d_dbg, d_acc_bin, d_sc_part, d_stage[MAXF];
     int stage_flip = 0;
     cudaEvent_t ev_copy = nullptr;
     UploadArena up;                               // every array build_device_window uploads
@@ -284,10 +283,10 @@ public:
 #define LT_ATTR(CW, ST)                                                                                                                                  \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<false, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min<size_t>(lt_smem_bytes(MAXF, CW, ST), 227 * 1024))); \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<true, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min<size_t>(lt_smem_bytes(MAXF, CW, ST), 227 * 1024)));
-        LT_ATTR(12, 4) LT_ATTR(8, 4) LT_ATTR(16, 3) LT_ATTR(12, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
+        LT_ATTR(12, 4) LT_ATTR(8, 4) LT_ATTR(16, 4) LT_ATTR(12, 5) LT_ATTR(12, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
 #undef LT_ATTR
         // fused tail (tail.cuh): one cluster per host frame, one CTA per frame -> clusters of 8 (portable) or 16 (opt-in) CTAs
-        if (!getenv("CMLBA_NO_TAIL_FUSION") && cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tail_smem_bytes(MAXF)) == cudaSuccess) {
+        if (getenv("CMLBA_TAIL_FUSION") && cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tail_smem_bytes(MAXF)) == cudaSuccess) {
             tail_cluster_max = 8;
             if (cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
                 cudaLaunchConfig_t lc = {}; cudaLaunchAttribute at[1];
@@ -304,7 +303,7 @@ public:
         if (const char *v = getenv("CMLBA_LT_EXACT")) lt_exact = atoi(v);
         CK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CK(cudaFuncSetAttribute(schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(schur_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         return CMLBA_OK;
     }
 
@@ -326,11 +325,11 @@ public:
         for (auto *b : dd) b->release();
         d_post_send.release(); d_post_recv.release(); d_cap.release();
         DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_res_bin_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin,
-                             &d_bin_key, &d_bin_hist, &d_bin_offs, &d_job_of_tile, &d_r_job, &d_r_src, &d_seg_cnt, &d_seg_base, &d_seg_t_begin, &d_bin_ticket, &d_job_begin, &d_cta_info};
+                             &d_bin_key, &d_bin_hist, &d_bin_offs, &d_job_of_tile, &d_r_job, &d_r_src, &d_bin_ticket, &d_job_begin, &d_cta_info};
         for (auto *b : di) b->release();
-        d_job_desc.release(); d_r_pht.release(); d_seg_hdr.release(); d_fin_state.release(); d_fin_alive.release(); d_fin_energy.release();
+        d_job_desc.release(); d_r_pht.release(); d_fin_state.release(); d_fin_alive.release(); d_fin_energy.release();
         DevBuf<float> *df[] = {&d_pt_x, &d_pt_y, &d_pt_idz, &d_pt_idb, &d_pt_colors, &d_pt_weights, &d_pt_priorF, &d_pt_Hdd, &d_pt_bd, &d_pt_Hcd, &d_pt_HdiF, &d_pt_bdSumF, &d_pt_idh, &d_pt_mrb,
-                               &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj, &d_T0, &d_T1, &d_dbg, &d_acc0, &d_acc1, &d_sc_part};
+                               &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj0, &d_rj1, &d_T0, &d_T1, &d_dbg, &d_acc_bin, &d_sc_part};
         for (auto *b : df) b->release();
         for (auto &b : d_stage) b.release();
         DevBuf<uint8_t> *du[] = {&d_r_host, &d_r_target, &d_r_state0, &d_r_state1, &d_r_good0, &d_r_good1, &d_r_new_state, &d_r_alive};
@@ -779,7 +778,6 @@ public:
         n_chunks = (R + ACC_CHUNK - 1) / ACC_CHUNK;
         const int tiles_x = (W + LT_TILE_W - 1) / LT_TILE_W, tiles_y = (H + LT_TILE_H - 1) / LT_TILE_H, n_tiles = tiles_x * tiles_y;
         const size_t n_keys = (size_t) N * n_tiles * N;
-        seg_cap = std::min<size_t>((size_t) R, n_keys) + (size_t) n_chunks + 1;     // runs of one (h,t) pair: one per non-empty (t,tile,h) group, plus the cuts at pass boundaries
         h_host_chunk_begin.assign(N + 1, 0);
         for (int h = 0; h < N; h++) h_host_chunk_begin[h + 1] = h_host_chunk_begin[h] + (hcnt[h + 1] - hcnt[h] + SC_CHUNK - 1) / SC_CHUNK;
         n_sc_chunks = h_host_chunk_begin[N];
@@ -832,13 +830,12 @@ public:
         CK(d_pt_ngood_cur.reserve(Pz)); CK(d_pt_step.reserve(Pz));
         CK(d_r_state0.reserve(Rz)); CK(d_r_state1.reserve(Rz)); CK(d_r_energy0.reserve(Rz)); CK(d_r_energy1.reserve(Rz)); CK(d_r_good0.reserve(Rz)); CK(d_r_good1.reserve(Rz));
         CK(d_r_new_state.reserve(Rz)); CK(d_r_new_energy.reserve(Rz)); CK(d_r_new_energy_wo.reserve(Rz)); CK(d_r_alive.reserve(Rz)); CK(d_r_center.reserve(Rz * 3));
-        CK(d_rj.reserve(Rz * RJ_STRIDE)); CK(d_T0.reserve(Pz * N * T_STRIDE)); CK(d_T1.reserve(Pz * N * T_STRIDE));
+        CK(d_rj0.reserve(Rz * RJ_STRIDE)); CK(d_rj1.reserve(Rz * RJ_STRIDE)); CK(d_T0.reserve(Pz * N * T_STRIDE)); CK(d_T1.reserve(Pz * N * T_STRIDE));
         if (want_dbg) CK(d_dbg.reserve(Rz * DBG_STRIDE));
         CK(d_energy_part.reserve(std::max(n_chunks, 1)));
-        CK(d_acc0.reserve(seg_cap * ACC_N)); CK(d_acc1.reserve(seg_cap * ACC_N));
+        CK(d_acc_bin.reserve((size_t) N * N * ACC_SLICES * ACC_N));
         CK(d_bin_key.reserve(Rz)); CK(d_bin_hist.reserve(n_keys)); CK(d_bin_offs.reserve(n_keys)); CK(d_job_of_tile.reserve((size_t) N * n_tiles)); CK(d_job_desc.reserve((size_t) N * n_tiles)); CK(d_job_begin.reserve((size_t) N * n_tiles + 1)); CK(d_cta_info.reserve((size_t) 16 * 1024));
-        CK(d_r_pht.reserve(Rz)); CK(d_r_job.reserve(Rz)); CK(d_r_src.reserve(Rz)); CK(d_seg_cnt.reserve(std::max(n_chunks, 1))); CK(d_seg_base.reserve(n_chunks + 1));
-        CK(d_seg_hdr.reserve(seg_cap)); CK(d_seg_t_begin.reserve(MAXF + 1));
+        CK(d_r_pht.reserve(Rz)); CK(d_r_job.reserve(Rz)); CK(d_r_src.reserve(Rz));
         CK(d_fin_state.reserve(Rz)); CK(d_fin_alive.reserve(Rz)); CK(d_fin_energy.reserve(Rz));
         if (!d_bin_ticket.p) { CK(d_bin_ticket.reserve(2)); CK(cudaMemsetAsync(d_bin_ticket.p, 0, 2 * sizeof(int), stream)); }
         CK(d_sc_part.reserve((size_t) std::max(n_sc_chunks, 1) * sc_stride));
@@ -874,13 +871,13 @@ public:
         w.pt_num_good = d_pt_num_good.p; w.pt_ngood_cur = d_pt_ngood_cur.p; w.pt_step = d_pt_step.p;
         w.r_point = d_r_point.p; w.r_host = d_r_host.p; w.r_target = d_r_target.p; w.res_bin_begin = d_res_bin_begin.p;
         w.bin_key = d_bin_key.p; w.bin_hist = d_bin_hist.p; w.bin_offs = d_bin_offs.p; w.job_of_tile = d_job_of_tile.p; w.job_desc = d_job_desc.p; w.job_begin = d_job_begin.p; w.cta_info = d_cta_info.p; w.lt_grid = std::max(1, std::min(std::min(n_sm, 1024), n_chunks));
-        w.r_pht = d_r_pht.p; w.r_job = d_r_job.p; w.r_src = d_r_src.p; w.seg_cnt = d_seg_cnt.p; w.seg_base = d_seg_base.p; w.seg_hdr = d_seg_hdr.p; w.seg_t_begin = d_seg_t_begin.p;
+        w.r_pht = d_r_pht.p; w.r_job = d_r_job.p; w.r_src = d_r_src.p;
         w.bin_ticket = d_bin_ticket.p; w.fin_state = d_fin_state.p; w.fin_alive = d_fin_alive.p; w.fin_energy = d_fin_energy.p;
         w.tma_on = encode_tile_maps() ? 1 : 0;
         w.r_state[0] = d_r_state0.p; w.r_state[1] = d_r_state1.p; w.r_energy[0] = d_r_energy0.p; w.r_energy[1] = d_r_energy1.p; w.r_good[0] = d_r_good0.p; w.r_good[1] = d_r_good1.p;
         w.r_new_state = d_r_new_state.p; w.r_new_energy = d_r_new_energy.p; w.r_new_energy_wo = d_r_new_energy_wo.p; w.r_alive = d_r_alive.p; w.r_center = d_r_center.p;
-        w.rj = d_rj.p; w.T[0] = d_T0.p; w.T[1] = d_T1.p; w.dbg = want_dbg ? d_dbg.p : nullptr;
-        w.energy_part = d_energy_part.p; w.acc_part[0] = d_acc0.p; w.acc_part[1] = d_acc1.p;
+        w.rj[0] = d_rj0.p; w.rj[1] = d_rj1.p; w.T[0] = d_T0.p; w.T[1] = d_T1.p; w.dbg = want_dbg ? d_dbg.p : nullptr;
+        w.energy_part = d_energy_part.p; w.acc_bin = d_acc_bin.p;
         w.sc_part = d_sc_part.p; w.sc_stride = sc_stride; w.sc_chunk_host = d_sc_chunk_host.p; w.sc_chunk_begin = d_sc_chunk_begin.p; w.sc_chunk_count = d_sc_chunk_count.p;
         w.host_chunk_begin = d_host_chunk_begin.p;
         w.st_out = d_st_out.p; w.sys = d_sys.p; w.x = d_x.p; w.xAd = d_xAd.p;
@@ -1095,7 +1092,7 @@ public:
             CK(cudaMemsetAsync(d_bin_hist.p, 0, (size_t) N * dw.n_tiles * N * sizeof(int), stream));
             bin_count_kernel<<<(dw.R + 255) / 256, 256, 0, stream>>>(dw); launches++;
             bin_scatter_kernel<<<N * N, 256, (size_t) 8 * dw.n_tiles * sizeof(int), stream>>>(dw); launches++;
-            bin_segments_kernel<<<(dw.n_chunks + 7) / 8, 256, 0, stream>>>(dw); launches++;
+            bin_finish_kernel<<<1, 256, 0, stream>>>(dw); launches++;
         }
         CK(cudaGetLastError());
         lap("prep.upload_reset");
@@ -1104,7 +1101,7 @@ public:
     }
 
     // ------------------------------------------------------------------ kernel sequences
-    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128 + ST_SLICES * ACC_N); }
+    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128); }
     size_t solve_smem() const { const int n = dw.n; return sizeof(double) * ((size_t) n * n + 4 * n + 256); }
     size_t schur_smem() const { return schur_smem_bytes(dw.N); }
 
@@ -1120,8 +1117,8 @@ public:
     } while (0)
         switch (lt_variant) {
             case 1: LT_LAUNCH(8, 4); break;
-            case 2: LT_LAUNCH(16, 3); break;
-            case 3: LT_LAUNCH(12, 3); break;
+            case 2: LT_LAUNCH(16, 4); break;
+            case 3: LT_LAUNCH(12, 5); break;
             default: if (lt_smem_bytes(dw.N, 12, 4) <= (size_t) 227 * 1024) LT_LAUNCH(12, 4); else LT_LAUNCH(12, 3); break;
         }
 #undef LT_LAUNCH
@@ -1142,12 +1139,14 @@ public:
         post_linearize_kernel<<<1, 1024, 0, stream>>>(dw, mode, respect_done); launches++;
     }
     void launch_schur(int respect_done) {
-        if (dw.n_sc_chunks > 0) { schur_kernel<<<dw.n_sc_chunks, 256, schur_smem(), stream>>>(dw, respect_done); launches++; }
+        // Schur chunks and, in the same launch, the (bin, slice) jobs that evaluate addToHessianTop from the Jacobian records
+        if (dw.n_sc_chunks > 0) { schur_acc_kernel<<<dw.n_sc_chunks + dw.N * dw.N * ACC_SLICES, 256, schur_smem(), stream>>>(dw, respect_done, 0); launches++; }
     }
     // Schur complement + stitching + assembly of sys = [HA | bA | H_sc | b_sc]: one cluster kernel when a cluster of >= N CTAs is available
     bool tail_fused() const { return dw.N <= tail_cluster_max && dw.n_sc_chunks > 0; }
     void launch_tail(int respect_done) {
         if (!tail_fused()) { launch_schur(respect_done); launch_stitch(respect_done); return; }
+        schur_acc_kernel<<<dw.N * dw.N * ACC_SLICES, 256, schur_smem(), stream>>>(dw, respect_done, dw.n_sc_chunks); launches++;     // accumulate jobs only
         const int cs = tail_cluster_max;                 // 16 CTAs per host frame when the device can co-schedule them (twice the Schur parallelism), else 8
         if (dw.p2p_on) dw.p2p_epoch = ++p2p_epoch;       // the same count on every rank: one exchange per stitched system
         cudaLaunchConfig_t lc = {}; cudaLaunchAttribute at[1];
@@ -1461,7 +1460,13 @@ public:
         if (name == "res_new_energy_wo") return copy_out(d_r_new_energy_wo.p, R, dst, cap, bytes);
         if (name == "res_alive") return copy_out(d_r_alive.p, R, dst, cap, bytes);
         if (name == "res_center") return copy_out(d_r_center.p, (size_t) R * 3, dst, cap, bytes);
-        if (name == "rj") return copy_out(d_rj.p, (size_t) R * RJ_STRIDE, dst, cap, bytes);
+        if (name == "rj") {   // candidate records (the last linearization), re-ordered from the host's residual order to the device's tile-sorted one
+            std::vector<float> rec((size_t) R * RJ_STRIDE), out((size_t) R * RJ_STRIDE, 0.f);
+            std::vector<int> srcv(R);
+            if (R) { CK(cudaMemcpy(rec.data(), cur ? d_rj0.p : d_rj1.p, rec.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(srcv.data(), d_r_src.p, (size_t) R * 4, cudaMemcpyDeviceToHost)); }
+            for (int i = 0; i < R; i++) if (rec[(size_t) srcv[i] * RJ_STRIDE + 35] != 0.f) memcpy(&out[(size_t) i * RJ_STRIDE], &rec[(size_t) srcv[i] * RJ_STRIDE], 35 * sizeof(float));
+            return host_out(out.data(), out.size() * 4, dst, cap, bytes);
+        }
         if (name == "dbg") { if (!want_dbg) { set_error("debug dump not enabled (cmlba_read(\"enable_dbg\") first)"); return CMLBA_ERR_STATE; } return copy_out(d_dbg.p, (size_t) R * DBG_STRIDE, dst, cap, bytes); }
         if (name == "T") return copy_out(cur ? d_T1.p : d_T0.p, (size_t) P * N * T_STRIDE, dst, cap, bytes);
         if (name == "T_cand") return copy_out(cur ? d_T0.p : d_T1.p, (size_t) P * N * T_STRIDE, dst, cap, bytes);
@@ -1485,16 +1490,18 @@ public:
         if (name == "sys") return copy_out(d_sys.p, (size_t) 2 * n * n + 2 * n, dst, cap, bytes);
         if (name == "x") return copy_out(d_x.p, n, dst, cap, bytes);
         if (name == "xAd") return copy_out(d_xAd.p, (size_t) N * N * 8, dst, cap, bytes);
-        if (name == "acc" || name == "acc_cand") {   // per bin (t*N+h) packed 96 doubles, chunk partials summed in order
+        if (name == "acc" || name == "acc_cand") {   // per bin (t*N+h) packed 96 doubles: addToHessianTop evaluated from the Jacobian records (host order = bin-major)
             const bool cand = name == "acc_cand";
-            const float *src = (cur ^ (cand ? 1 : 0)) ? d_acc1.p : d_acc0.p;
-            int n_seg = 0;
-            if (n_chunks) CK(cudaMemcpy(&n_seg, d_seg_base.p + n_chunks, sizeof(int), cudaMemcpyDeviceToHost));
-            std::vector<float> part((size_t) n_seg * ACC_N);
-            std::vector<uint8_t> hdr(n_seg);
-            if (n_seg) { CK(cudaMemcpy(part.data(), src, part.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hdr.data(), d_seg_hdr.p, n_seg, cudaMemcpyDeviceToHost)); }
+            std::vector<float> rec((size_t) R * RJ_STRIDE);
+            if (R) CK(cudaMemcpy(rec.data(), (cur ^ (cand ? 1 : 0)) ? d_rj1.p : d_rj0.p, rec.size() * 4, cudaMemcpyDeviceToHost));
             std::vector<double> acc((size_t) N * N * ACC_N, 0.0);
-            for (int sg = 0; sg < n_seg; sg++) { const int b = (hdr[sg] >> 4) * N + (hdr[sg] & 15); for (int k = 0; k < ACC_N; k++) acc[(size_t) b * ACC_N + k] += part[(size_t) sg * ACC_N + k]; }
+            for (int b = 0; b < N * N; b++) for (int r = res_bin_begin[b]; r < res_bin_begin[b + 1]; r++) {
+                const float *q = &rec[(size_t) r * RJ_STRIDE];
+                if (q[35] == 0.f) continue;
+                float Qx[10], Qy[10];
+                for (int k = 0; k < 10; k++) { Qx[k] = q[20] * q[k] + q[21] * q[10 + k]; Qy[k] = q[21] * q[k] + q[22] * q[10 + k]; }
+                for (int e = 0; e < 91; e++) acc[(size_t) b * ACC_N + e] += (double) acc_entry(e, q, q + 10, Qx, Qy, q + 23, q + 26, q + 29);
+            }
             return host_out(acc.data(), acc.size() * 8, dst, cap, bytes);
         }
         if (name == "sc") {   // per host: D[(8N)^2] E[32N] EB[8N] Hcc[16] bc[4] doubles

@@ -92,7 +92,7 @@ __global__ void set_evalpt_newest_kernel(const DevWin w) {
 // linearize.cuh (linearize_tile_kernel: TMA-staged target tiles, one residual per lane, per-(host,target)-run partial blocks).
 // entry e (0..95) of the packed 13x13 block as a product of record fields; x = Jp_x[10], y = Jp_y[10], Q = JIdx2 * Jp,
 // B = the 2x3 top-right multipliers, BR = the 6 bottom-right sums.  e is a compile-time constant after unrolling.
-__device__ __forceinline__ float acc_entry(const int e, const float *x, const float *y, const float *Qx, const float *Qy, const float *Bx, const float *By, const float *BR) {
+__host__ __device__ __forceinline__ float acc_entry(const int e, const float *x, const float *y, const float *Qx, const float *Qy, const float *Bx, const float *By, const float *BR) {
     if (e < 55) {
         int r = 0, base = 0;
         while (e >= base + (10 - r)) { base += 10 - r; r++; }
@@ -131,16 +131,65 @@ namespace cmlba {
 // (the N^3 8x8 accumulators of BA:1040 per host are the (8N)^2 matrix D).  4x4 register tiles, 2 LDS.128 per 16 FMA;
 // only tiles on or below the diagonal of D are computed; each is stored together with its mirror image.
 constexpr int SCZ_PAD = 8;     // z_c (4) z_b (1) pad (3)
-__host__ __device__ __forceinline__ size_t schur_smem_bytes(int N) { return sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * (8 * N + SCZ_PAD)); }
+__host__ __device__ __forceinline__ size_t schur_smem_bytes(int N) { const size_t a = sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * (8 * N + SCZ_PAD)), b = sizeof(float) * 64 * ACC_N; return a > b ? a : b; }
 
-__global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int respect_done) {
+// addToHessianTop (BA:1648-1779, MatrixAccumulators.h:776-937) from the Jacobian records of the sampling kernel: one CTA per (bin, slice).
+// Warp k of the CTA owns entries [24 (k & 3), 24 (k & 3) + 24) of the packed 13x13 block for residual slots 32 (k >> 2) + lane; every
+// thread keeps its 24 sums in registers over its residuals (slot, slot + 64, ...), then the 64 slots are summed in order.
+template <int Q>
+__device__ __forceinline__ void acc_quarter(float (&acc)[24], const float *rec, const float *Qx, const float *Qy) {
+#pragma unroll
+    for (int k = 0; k < 24; k++) acc[k] += acc_entry(24 * Q + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
+}
+__device__ __forceinline__ void accumulate_role(const DevWin &w, const int cur, const int job, float *sm) {
+    const int N = w.N, bin = job / ACC_SLICES, sl = job - bin * ACC_SLICES, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int b0 = w.res_bin_begin[bin], b1 = w.res_bin_begin[bin + 1];
+    const int len = (b1 - b0 + ACC_SLICES - 1) / ACC_SLICES, a0 = min(b0 + sl * len, b1), a1 = min(a0 + len, b1);
+    const int q = wid & 3, slot = (wid >> 2) * 32 + lane;
+    float acc[24];
+#pragma unroll
+    for (int k = 0; k < 24; k++) acc[k] = 0.f;
+    const float *rj = w.rj[cur];
+    for (int r = a0 + slot; r < a1; r += 64) {
+        const float4 *p4 = reinterpret_cast<const float4 *>(rj + (size_t) r * RJ_STRIDE);
+        const float4 last = __ldcg(p4 + 8);
+        if (last.w == 0.f) continue;                 // not a good residual: no record
+        float rec[RJ_STRIDE];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const float4 v = __ldcg(p4 + k); rec[4 * k] = v.x; rec[4 * k + 1] = v.y; rec[4 * k + 2] = v.z; rec[4 * k + 3] = v.w; }
+        rec[32] = last.x; rec[33] = last.y; rec[34] = last.z; rec[35] = 0.f;
+        float Qx[10], Qy[10];
+        const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
+#pragma unroll
+        for (int k = 0; k < 10; k++) { Qx[k] = a00 * rec[k] + a01 * rec[10 + k]; Qy[k] = a01 * rec[k] + a11 * rec[10 + k]; }
+        if (q == 0) acc_quarter<0>(acc, rec, Qx, Qy);
+        else if (q == 1) acc_quarter<1>(acc, rec, Qx, Qy);
+        else if (q == 2) acc_quarter<2>(acc, rec, Qx, Qy);
+        else acc_quarter<3>(acc, rec, Qx, Qy);
+    }
+    float *s_red = sm;                               // [64 slots][ACC_N]
+#pragma unroll
+    for (int k = 0; k < 24; k++) s_red[slot * ACC_N + 24 * q + k] = acc[k];
+    __syncthreads();
+    if (tid < ACC_N) {
+        float t = 0.f;
+        for (int sl2 = 0; sl2 < 64; sl2++) t += s_red[sl2 * ACC_N + tid];
+        w.acc_bin[(size_t) job * ACC_N + tid] = t;
+    }
+    (void) N;
+}
+
+// CTA role by job = blockIdx.x + job_offset: the first n_sc_chunks jobs are Schur chunks, the others (bin, slice) accumulate jobs
+__global__ void __launch_bounds__(256) schur_acc_kernel(const DevWin w, const int respect_done, const int job_offset) {
     if (respect_done && w.ctrl->done) return;
     extern __shared__ __align__(16) float sm[];
+    const int job_id = (int) blockIdx.x + job_offset;
+    if (job_id >= w.n_sc_chunks) { accumulate_role(w, w.ctrl->cur, job_id - w.n_sc_chunks, sm); return; }
     const int N = w.N, NB = 8 * N, ZS = NB + SCZ_PAD;
     const int cur = w.ctrl->cur;
     float *sT = sm;                                  // [SC_CHUNK][N][T_STRIDE] raw Schur rows
     float *sZ = sT + SC_CHUNK * N * T_STRIDE;        // [SC_CHUNK][ZS]         augmented, scaled
-    const int c = blockIdx.x, tid = threadIdx.x;
+    const int c = job_id, tid = threadIdx.x;
     const int begin = w.sc_chunk_begin[c], cnt = w.sc_chunk_count[c];
     {   // stage the rows of the chunk's points (contiguous in T)
         const float4 *src = reinterpret_cast<const float4 *>(w.T[cur] + (size_t) begin * N * T_STRIDE);
@@ -265,57 +314,6 @@ constexpr int ST_A_TT = 0, ST_A_IT = 64, ST_A_II = 128, ST_A_TC = 192, ST_A_IC =
               ST_S_JI = 296, ST_S_II = 360, ST_S_JC = 424, ST_S_IC = 456, ST_BS_J = 488, ST_BS_I = 496, ST_S_JK = 504;
 __host__ __device__ __forceinline__ int st_stride(int N) { return ST_S_JK + 64 * N; }
 constexpr int ST_THREADS = 512;
-constexpr int ST_LIST = 4096;    // partial-block indices compacted per batch
-constexpr int ST_SLICES = ST_THREADS / ACC_N;    // threads per entry of the 13x13 block (5)
-
-// 13x13 block of bin (host i -> target j) from the sampling kernel's partial blocks: those tagged (i, j) in seg_hdr.  The partials of one
-// target are contiguous (seg_t_begin); the CTA (ST_THREADS threads) compacts the matching indices batch-wise -- four tags per thread,
-// block scan of the match counts -- then ST_SLICES threads per entry sum contiguous parts of the list with 16 loads in flight.  Fixed
-// order, no atomics.  Apart: [ST_SLICES][ACC_N] doubles of shared memory; the caller adds the slices after a __syncthreads().
-__device__ __forceinline__ void sum_bin_partials(const DevWin &w, const int cur, const int i, const int j, double *Apart) {
-    __shared__ int s_list[ST_LIST];
-    __shared__ int s_wtot[ST_THREADS / 32];
-    __shared__ int s_n;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int sb = w.seg_t_begin[j], se = w.seg_t_begin[j + 1];
-    const uint8_t want = (uint8_t) (i | (j << 4));
-    const float *part = w.acc_part[cur];
-    const int e = tid % ACC_N, q = tid / ACC_N;
-    double acc = 0.0;
-    int base = sb;
-    do {
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-        while (base < se && s_n + 4 * ST_THREADS <= ST_LIST) {
-            const int k0 = base + 4 * tid;
-            unsigned m = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) if (k0 + b < se && __ldg(w.seg_hdr + k0 + b) == want) m |= 1u << b;
-            const int c = __popc(m);
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-            if (lane == 31) s_wtot[wid] = incl;
-            __syncthreads();
-            int off = s_n + incl - c;
-            for (int ww = 0; ww < wid; ww++) off += s_wtot[ww];
-#pragma unroll
-            for (int b = 0; b < 4; b++) if ((m >> b) & 1u) s_list[off++] = k0 + b;
-            __syncthreads();
-            if (tid == 0) { int t = 0; for (int ww = 0; ww < ST_THREADS / 32; ww++) t += s_wtot[ww]; s_n += t; }
-            __syncthreads();
-            base += 4 * ST_THREADS;
-        }
-        const int n = s_n;
-        if (tid < ST_SLICES * ACC_N) {
-            const int len = (n + ST_SLICES - 1) / ST_SLICES, a = min(q * len, n), b = min(a + len, n);
-#pragma unroll 16
-            for (int k = a; k < b; k++) acc += (double) __ldg(part + (size_t) s_list[k] * ACC_N + e);
-        }
-        __syncthreads();
-    } while (base < se);
-    if (tid < ST_SLICES * ACC_N) Apart[tid] = acc;
-}
 
 __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
@@ -342,7 +340,6 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
     double *A = atd + NB;          // [ACC_N]  packed 13x13 block of bin (i -> j)
     double *Y = A + ACC_N;         // [8][8]   sum_k D_jk AH_ik^T
     double *M = Y + 64;            // [8][8]   AH_ij A8
-    double *Apart = M + 64;        // [ST_SLICES][ACC_N] partial sums of A
     for (int e = tid; e < 8 * NB + 40; e += ST_THREADS) {
         int off;
         if (e < 8 * NB) off = j * 8 * NB + e;
@@ -354,11 +351,14 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
         for (int c = cb; c < ce; c++, src += w.sc_stride) s += (double) __ldg(src);
         Dj[e] = s;                 // Dj, Ej, EBj are contiguous
     }
-    sum_bin_partials(w, cur, i, j, Apart);
+    if (tid < ACC_N) {   // 13x13 block of bin (i -> j): the slices of the accumulate role of schur_acc_kernel, fixed order
+        const float *src = w.acc_bin + (size_t) (j * N + i) * ACC_SLICES * ACC_N + tid;
+        double a = 0.0;
+        for (int sl = 0; sl < ACC_SLICES; sl++) a += (double) __ldcg(src + sl * ACC_N);
+        A[tid] = a;
+    }
     for (int e = tid; e < N * 64; e += ST_THREADS) G[e] = w.AH[(size_t) (i * N) * 64 + e];
     for (int e = tid; e < NB; e += ST_THREADS) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
-    __syncthreads();
-    if (tid < ACC_N) A[tid] = ((Apart[tid] + Apart[ACC_N + tid]) + (Apart[2 * ACC_N + tid] + Apart[3 * ACC_N + tid])) + Apart[4 * ACC_N + tid];
     __syncthreads();
     const double *AHj = G + j * 64, *atj = atd + j * 8;
     {

@@ -19,9 +19,9 @@
 // position differs from the reference's by at most one float ulp in a few percent of the pixels (measured).  A residual with
 // a pixel closer than 1e-3 px to the in-bounds limits is re-projected exactly in fp64, so the OOB decision is the reference's.
 //
-// Accumulation: the 91 products of the 13x13 block are transposed through a per-warp scratch tile and summed per RUN of one
-// (host,target) pair inside the warp pass (the sort keeps such runs contiguous); one partial block per run goes to acc_part, with its
-// (h,t) tag in seg_hdr.  All orders are fixed: results are bitwise reproducible.
+// Output: the Jacobian record of every good residual (x[10] y[10] JIdx2[3] ...; the reference's efsJ, DSOResidual.h:22-69) goes to
+// rj[candidate] in the HOST's bin-major residual order; addToHessianTop (the 13x13 blocks) is evaluated from these records by
+// accumulate_role of schur_acc_kernel (kernels.cuh), bin by bin, in a fixed order: results are bitwise reproducible.
 #pragma once
 #include <cuda.h>
 
@@ -34,7 +34,7 @@ struct alignas(64) TileMaps { CUtensorMap m[MAXF]; };   // one 2-D tensor map pe
 
 // CW warps, ST ring stages
 __host__ __device__ __forceinline__ size_t lt_smem_bytes(int N, int CW, int ST) {
-    return (size_t) ST * LT_STAGE_STRIDE + (size_t) CW * 32 * LT_SCR_STRIDE * sizeof(float) + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float) + 8 * sizeof(int) + LT_TILE_TABLE * 2 * sizeof(int);
+    return (size_t) ST * LT_STAGE_STRIDE + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float) + 8 * sizeof(int) + LT_TILE_TABLE * 2 * sizeof(int);
 }
 
 // ---- mbarrier / TMA (PTX ISA 8.x; SASS: SYNCS.*, UTMALDG)
@@ -214,53 +214,8 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const DevWin w) {
     }
 }
 
-// step 3: runs of one (host, target) pair inside every warp pass (32 consecutive sorted residuals) -> seg_cnt; the last CTA scans
-// them into seg_base (seg_base[n_chunks] = number of partial blocks one linearization writes).
-__global__ void __launch_bounds__(256) bin_segments_kernel(const DevWin w) {
-    const int lane = threadIdx.x & 31, c = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (c < w.n_chunks) {
-        const int r = min(c * 32 + lane, w.R - 1);
-        const uint32_t key = w.r_pht[r] >> 24, prev = __shfl_up_sync(0xffffffffu, key, 1);
-        const unsigned m = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
-        if (lane == 0) w.seg_cnt[c] = __popc(m);
-    }
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(w.bin_ticket + 1, 1) == (int) gridDim.x - 1) ? 1 : 0;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) w.bin_ticket[1] = 0;
-    const int per = (w.n_chunks + 255) / 256;
-    const int a0 = min((int) threadIdx.x * per, w.n_chunks), a1 = min(a0 + per, w.n_chunks);
-    int cnt = 0;
-    for (int k = a0; k < a1; k++) cnt += __ldcg(w.seg_cnt + k);
-    int tot;
-    int run = block_excl_scan_256(cnt, &tot);
-    for (int k = a0; k < a1; k++) { w.seg_base[k] = run; run += __ldcg(w.seg_cnt + k); }
-    if (threadIdx.x == 0) w.seg_base[w.n_chunks] = tot;
-    __syncthreads();
-    // first partial of every target: the sort keeps the host's target-major order, so target t starts at sorted residual res_bin_begin[t*N]
-    __shared__ int s_tb[MAXF + 1];
-    if ((int) threadIdx.x <= w.N) {
-        const int t = threadIdx.x;
-        int val = -1;
-        if (t < w.N && w.res_bin_begin[t * w.N] < w.res_bin_begin[(t + 1) * w.N]) {
-            const int rt = w.res_bin_begin[t * w.N], ch = rt >> 5, l = rt & 31;
-            int starts = 0;
-            uint32_t prev = 0;
-            for (int k = 0; k < l; k++) { const uint32_t key = w.r_pht[ch * 32 + k] >> 24; starts += (k == 0 || key != prev) ? 1 : 0; prev = key; }
-            val = w.seg_base[ch] + starts;
-        }
-        s_tb[t] = val;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int nextv = tot;
-        for (int t = w.N; t >= 0; t--) { if (t == w.N || s_tb[t] < 0) s_tb[t] = nextv; nextv = s_tb[t]; w.seg_t_begin[t] = s_tb[t]; }
-    }
-    // per-CTA records of linearize_tile_kernel (grid = lt_grid persistent CTAs over contiguous ranges of warp passes)
+// step 3: per-CTA records of linearize_tile_kernel (grid = lt_grid persistent CTAs over contiguous ranges of warp passes)
+__global__ void __launch_bounds__(256) bin_finish_kernel(const DevWin w) {
     const int per_cta = (w.n_chunks + w.lt_grid - 1) / w.lt_grid;
     for (int b = threadIdx.x; b < w.lt_grid; b += 256) {
         const int c0 = b * per_cta, c1 = min(c0 + per_cta, w.n_chunks);
@@ -284,8 +239,7 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
     if (respect_done && ctrl->done) return;
     extern __shared__ __align__(1024) unsigned char lt_smem[];
     unsigned char *ring = lt_smem;                                                                  // [LT_STAGES][LT_BOX_H][LT_BOX_W] float4
-    float *scratch = reinterpret_cast<float *>(lt_smem + (size_t) LT_STAGES * LT_STAGE_STRIDE);     // [LT_CWARPS][32][LT_SCR_STRIDE]
-    PairPre *s_pairs = reinterpret_cast<PairPre *>(scratch + LT_CWARPS * 32 * LT_SCR_STRIDE);       // [2 targets][N hosts]
+    PairPre *s_pairs = reinterpret_cast<PairPre *>(lt_smem + (size_t) LT_STAGES * LT_STAGE_STRIDE); // [2 targets][N hosts]
     unsigned long long *full = reinterpret_cast<unsigned long long *>(s_pairs + 2 * w.N);
     unsigned long long *empty = full + LT_STAGES;
     float *s_th = reinterpret_cast<float *>(empty + LT_STAGES);                                     // [N] frameEnergyTH
@@ -377,7 +331,6 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
     bool pairs_ready = false;
     // ---- consumer warps
     const int cur = ctrl->cur, nxt = cur ^ 1;
-    float *scr = scratch + warp * 32 * LT_SCR_STRIDE;
     bool tma_ok = w.tma_on != 0;
     const double Wm2 = (double) ((float) w.W - 2.f), Hm2 = (double) ((float) w.H - 2.f);
     for (int c = c0 + warp; c < c1; c += LT_CWARPS) {
@@ -392,7 +345,6 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
         const float e_old = w.r_energy[cur][r_ld];
         uint8_t nst = w.r_new_state[r_ld];
         float ne = w.r_new_energy[r_ld];
-        const int sbase = __ldg(w.seg_base + c);
         const int src = __ldg(w.r_src + r_ld);
         const int p = (int) (pht & 0xffffffu), h = (int) ((pht >> 24) & 15u), t = (int) (pht >> 28);
         const bool valid = in_chunk && alive_ld;
@@ -661,11 +613,6 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
             if (st != RES_OOB && st_out != RES_OOB) { st_out = nst; e_out = ne; }
             w.r_new_state[r] = nst; w.r_new_energy[r] = ne; w.r_new_energy_wo[r] = neo;
             w.r_state[nxt][r] = st_out; w.r_energy[nxt][r] = e_out; w.r_good[nxt][r] = good ? 1 : 0;
-            if (kDump) {
-                float4 *rj4 = reinterpret_cast<float4 *>(w.rj + (size_t) r * RJ_STRIDE);
-#pragma unroll
-                for (int k = 0; k < RJ_STRIDE / 4; k++) rj4[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
-            }
             float4 *t4 = reinterpret_cast<float4 *>(w.T[nxt] + ((size_t) p * N + t) * T_STRIDE);
 #pragma unroll
             for (int k = 0; k < T_STRIDE / 4; k++) t4[k] = make_float4(trow[4 * k], trow[4 * k + 1], trow[4 * k + 2], trow[4 * k + 3]);
@@ -677,52 +624,15 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
         if (fix && in_chunk) {                       // final states in the host's residual order (finish_run reads these)
             w.fin_state[src] = st_out; w.fin_energy[src] = e_out; w.fin_alive[src] = (valid && good) ? 1 : 0;
         }
-        // ---- 13x13 blocks: one partial per run of a (host,target) pair in this pass (records of non-good residuals are all zero)
-        {
-            const uint32_t key_ht = pht >> 24, kprev = __shfl_up_sync(0xffffffffu, key_ht, 1);
-            const unsigned segmask = __ballot_sync(0xffffffffu, lane == 0 || key_ht != kprev);
-            if ((segmask >> lane) & 1u) w.seg_hdr[sbase + __popc(segmask & ((1u << lane) - 1u))] = (uint8_t) key_ht;
-            float Qx[10], Qy[10];
-            const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
+        // ---- the Jacobian record (the reference's efsJ) in the host's residual order: what addToHessianTop is evaluated from
+        // (accumulate role of schur_acc_kernel).  rec[35] = 1 marks a good residual; the others only clear that mark.
+        if (in_chunk) {
+            float4 *rj4 = reinterpret_cast<float4 *>(w.rj[nxt] + (size_t) src * RJ_STRIDE);
+            if (good) {
 #pragma unroll
-            for (int k = 0; k < 10; k++) { Qx[k] = a00 * rec[k] + a01 * rec[10 + k]; Qy[k] = a01 * rec[k] + a11 * rec[10 + k]; }
-            float *outp = w.acc_part[nxt] + (size_t) sbase * ACC_N + lane;
-#pragma unroll 1
-            for (int g = 0; g < 3; g++) {
-                float v[32];
-                if (g == 0) {
-#pragma unroll
-                    for (int k = 0; k < 32; k++) v[k] = acc_entry(k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
-                } else if (g == 1) {
-#pragma unroll
-                    for (int k = 0; k < 32; k++) v[k] = acc_entry(32 + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 32; k++) v[k] = acc_entry(64 + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
-                }
-                __syncwarp();                        // the previous group's column sums are done with the scratch tile
-                float4 *row = reinterpret_cast<float4 *>(scr + lane * LT_SCR_STRIDE);
-#pragma unroll
-                for (int k4 = 0; k4 < 8; k4++) row[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-                __syncwarp();
-                // lane L sums entry (g, L) over the lanes [j0, j0 + len) of every run: the len % 4 first rows with guarded loads, then an
-                // unrolled chain of 4-row blocks entered at 8 - len / 4 (four loads in flight per block, four independent sums)
-                unsigned m = segmask;
-                float *o = outp + g * 32;
-                while (m) {
-                    const int j0 = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int len = (m ? __ffs(m) - 1 : 32) - j0, rem = len & 3;
-                    const float *pr = scr + lane + j0 * LT_SCR_STRIDE;
-                    float s0 = rem > 0 ? pr[0] : 0.f, s1 = rem > 1 ? pr[LT_SCR_STRIDE] : 0.f, s2 = rem > 2 ? pr[2 * LT_SCR_STRIDE] : 0.f, s3 = 0.f;
-                    const float *pa = pr + (rem + (len & ~3) - 32) * LT_SCR_STRIDE;      // block b of the chain reads rows j0 + rem + 4 (b - (8 - len / 4)) ...
-#define LT_BLK(b) case 8 - (b): { const float x0 = pa[(4 * (b)) * LT_SCR_STRIDE], x1 = pa[(4 * (b) + 1) * LT_SCR_STRIDE], x2 = pa[(4 * (b) + 2) * LT_SCR_STRIDE], x3 = pa[(4 * (b) + 3) * LT_SCR_STRIDE]; s0 += x0; s1 += x1; s2 += x2; s3 += x3; }
-                    switch (len >> 2) { LT_BLK(0) LT_BLK(1) LT_BLK(2) LT_BLK(3) LT_BLK(4) LT_BLK(5) LT_BLK(6) LT_BLK(7) default: break; }
-#undef LT_BLK
-                    *o = (s0 + s1) + (s2 + s3);
-                    o += ACC_N;
-                }
-            }
+                for (int k = 0; k < RJ_STRIDE / 4 - 1; k++) rj4[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+                rj4[RJ_STRIDE / 4 - 1] = make_float4(rec[32], rec[33], rec[34], 1.f);
+            } else rj4[RJ_STRIDE / 4 - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         LT_STAMP();                                  // pass done
         // chunk energy (fp64, fixed order)

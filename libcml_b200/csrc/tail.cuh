@@ -25,7 +25,7 @@ constexpr int TAIL_TPT = 2;          // 4x4 tiles of the rank update per thread 
 __host__ __device__ __forceinline__ size_t tail_smem_bytes(int N) {
     const size_t NB = 8 * (size_t) N;
     const size_t phase1 = sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * (NB + SCZ_PAD));
-    const size_t phase2 = sizeof(double) * (8 * NB + 40 + (size_t) N * 64 + NB + ACC_N + 128 + ST_SLICES * ACC_N);
+    const size_t phase2 = sizeof(double) * (8 * NB + 40 + (size_t) N * 64 + NB + ACC_N + 128);
     const size_t part = sizeof(float) * (((NB * NB + NB * 5 + 20) + 3) & ~(size_t) 3);
     return (phase1 > phase2 ? phase1 : phase2) + part;
 }
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const DevWin w, c
     const int N = w.N, NB = 8 * N, ZS = NB + SCZ_PAD, tid = threadIdx.x, i = blockIdx.x / CS;
     const int cur = w.ctrl->cur;
     const size_t phase1 = sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * ZS);
-    const size_t phase2 = sizeof(double) * ((size_t) 8 * NB + 40 + (size_t) N * 64 + NB + ACC_N + 128 + ST_SLICES * ACC_N);
+    const size_t phase2 = sizeof(double) * ((size_t) 8 * NB + 40 + (size_t) N * 64 + NB + ACC_N + 128);
     float *part = reinterpret_cast<float *>(tail_smem + (phase1 > phase2 ? phase1 : phase2));      // this CTA's Schur partial, layout of sc_part
     float *sT = reinterpret_cast<float *>(tail_smem);                  // [SC_CHUNK][N][T_STRIDE] raw Schur rows
     float *sZ = sT + SC_CHUNK * N * T_STRIDE;                          // [SC_CHUNK][ZS]          augmented, scaled
@@ -232,7 +232,6 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const DevWin w, c
             double *A = atd + NB;          // [ACC_N]  packed 13x13 block of bin (i -> j)
             double *Y = A + ACC_N;         // [8][8]   sum_k D_jk AH_ik^T
             double *M = Y + 64;            // [8][8]   AH_ij A8
-            double *Apart = M + 64;        // [ST_SLICES][ACC_N] partial sums of A
             for (int e = tid; e < 8 * NB + 40; e += TAIL_THREADS) {
                 int off;
                 if (e < 8 * NB) off = j * 8 * NB + e;
@@ -242,11 +241,14 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const DevWin w, c
                 for (int k = 0; k < CS; k++) s += (double) cluster.map_shared_rank(part, k)[off];
                 Dj[e] = s;                 // Dj, Ej, EBj are contiguous
             }
-            sum_bin_partials(w, cur, i, j, Apart);        // 13x13 block of bin (i -> j) from the sampling kernel's partial blocks
+            if (tid < ACC_N) {   // 13x13 block of bin (i -> j): the slices of the accumulate role of schur_acc_kernel
+                const float *src = w.acc_bin + (size_t) (j * N + i) * ACC_SLICES * ACC_N + tid;
+                double a = 0.0;
+                for (int sl = 0; sl < ACC_SLICES; sl++) a += (double) __ldcg(src + sl * ACC_N);
+                A[tid] = a;
+            }
             for (int e = tid; e < N * 64; e += TAIL_THREADS) G[e] = w.AH[(size_t) (i * N) * 64 + e];
             for (int e = tid; e < NB; e += TAIL_THREADS) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
-            __syncthreads();
-            if (tid < ACC_N) A[tid] = ((Apart[tid] + Apart[ACC_N + tid]) + (Apart[2 * ACC_N + tid] + Apart[3 * ACC_N + tid])) + Apart[4 * ACC_N + tid];
             __syncthreads();
             const double *AHj = G + j * 64, *atj = atd + j * 8;
             {
