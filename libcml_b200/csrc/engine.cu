@@ -283,7 +283,7 @@ public:
 #define LT_ATTR(CW, ST)                                                                                                                                  \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<false, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min<size_t>(lt_smem_bytes(MAXF, CW, ST), 227 * 1024))); \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<true, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min<size_t>(lt_smem_bytes(MAXF, CW, ST), 227 * 1024)));
-        LT_ATTR(12, 4) LT_ATTR(8, 4) LT_ATTR(16, 4) LT_ATTR(12, 5) LT_ATTR(12, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
+        LT_ATTR(12, 4) LT_ATTR(8, 4) LT_ATTR(16, 4) LT_ATTR(12, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
 #undef LT_ATTR
         // fused tail (tail.cuh): one cluster per host frame, one CTA per frame -> clusters of 8 (portable) or 16 (opt-in) CTAs
         if (getenv("CMLBA_TAIL_FUSION") && cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tail_smem_bytes(MAXF)) == cudaSuccess) {
@@ -1118,7 +1118,7 @@ public:
         switch (lt_variant) {
             case 1: LT_LAUNCH(8, 4); break;
             case 2: LT_LAUNCH(16, 4); break;
-            case 3: LT_LAUNCH(12, 5); break;
+            case 3: LT_LAUNCH(12, 3); break;
             default: if (lt_smem_bytes(dw.N, 12, 4) <= (size_t) 227 * 1024) LT_LAUNCH(12, 4); else LT_LAUNCH(12, 3); break;
         }
 #undef LT_LAUNCH

@@ -152,11 +152,11 @@ __device__ __forceinline__ void accumulate_role(const DevWin &w, const int cur, 
     const float *rj = w.rj[cur];
     for (int r = a0 + slot; r < a1; r += 64) {
         const float4 *p4 = reinterpret_cast<const float4 *>(rj + (size_t) r * RJ_STRIDE);
-        const float4 last = __ldcg(p4 + 8);
+        const float4 last = __ldg(p4 + 8);
         if (last.w == 0.f) continue;                 // not a good residual: no record
         float rec[RJ_STRIDE];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const float4 v = __ldcg(p4 + k); rec[4 * k] = v.x; rec[4 * k + 1] = v.y; rec[4 * k + 2] = v.z; rec[4 * k + 3] = v.w; }
+        for (int k = 0; k < 8; k++) { const float4 v = __ldg(p4 + k); rec[4 * k] = v.x; rec[4 * k + 1] = v.y; rec[4 * k + 2] = v.z; rec[4 * k + 3] = v.w; }
         rec[32] = last.x; rec[33] = last.y; rec[34] = last.z; rec[35] = 0.f;
         float Qx[10], Qy[10];
         const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
@@ -172,9 +172,10 @@ __device__ __forceinline__ void accumulate_role(const DevWin &w, const int cur, 
     for (int k = 0; k < 24; k++) s_red[slot * ACC_N + 24 * q + k] = acc[k];
     __syncthreads();
     if (tid < ACC_N) {
-        float t = 0.f;
-        for (int sl2 = 0; sl2 < 64; sl2++) t += s_red[sl2 * ACC_N + tid];
-        w.acc_bin[(size_t) job * ACC_N + tid] = t;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll 4
+        for (int sl2 = 0; sl2 < 64; sl2 += 4) { t0 += s_red[sl2 * ACC_N + tid]; t1 += s_red[(sl2 + 1) * ACC_N + tid]; t2 += s_red[(sl2 + 2) * ACC_N + tid]; t3 += s_red[(sl2 + 3) * ACC_N + tid]; }
+        w.acc_bin[(size_t) job * ACC_N + tid] = (t0 + t1) + (t2 + t3);
     }
     (void) N;
 }
@@ -320,7 +321,6 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
     extern __shared__ __align__(16) double smd[];
     const int N = w.N, NB = 8 * N, tid = threadIdx.x;
     const int i = blockIdx.x / N, j = blockIdx.x % N;
-    const int cur = w.ctrl->cur;
     double *out = w.st_out + (size_t) blockIdx.x * st_stride(N);
     const int cb = w.host_chunk_begin[i], ce = w.host_chunk_begin[i + 1];
     if (i == j) {   // calibration block of host i's Schur complement (BA:1908-1909, 2026-2027)

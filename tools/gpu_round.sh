@@ -12,7 +12,7 @@ timeout 900 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider >
 echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -5 gpurun_out/${tag}_pytest.log
 if [ "$mode" == "variants" ]; then
-  for v in 0 1 2 3; do
+  for v in 0 2; do
     for nt in 0; do
       if [ $nt == 1 ]; then export CMLBA_NO_TMA=1; else unset CMLBA_NO_TMA; fi
       CMLBA_LT_VARIANT=$v timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/${tag}_bench_v${v}_$nt.json 2> gpurun_out/${tag}_bench_v${v}_$nt.err
