@@ -38,6 +38,14 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
+// Programmatic dependent launch (Engine::launch_pdl): a kernel of the chain lets its successor be scheduled as soon as all of its own
+// CTAs are running (the successor's CTAs then sit in pdl_wait until this grid has completed and its writes are visible), so the
+// launch latency of kernel k+1 overlaps the execution of kernel k.  No-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+
 // Frame state -> PRE_worldToCam (DSOFrame::setState, DSOFrame.h:110-124)
 __device__ inline void frame_set_state(FrameDev &f, const double *state, const DevWin &w) {
     const double sc[10] = {w.scaleT, w.scaleT, w.scaleT, w.scaleR, w.scaleR, w.scaleR, w.scaleA, w.scaleB, w.scaleA, w.scaleB};
@@ -131,7 +139,7 @@ namespace cmlba {
 // (the N^3 8x8 accumulators of BA:1040 per host are the (8N)^2 matrix D).  4x4 register tiles, 2 LDS.128 per 16 FMA;
 // only tiles on or below the diagonal of D are computed; each is stored together with its mirror image.
 constexpr int SCZ_PAD = 8;     // z_c (4) z_b (1) pad (3)
-__host__ __device__ __forceinline__ size_t schur_smem_bytes(int N) { const size_t a = sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * (8 * N + SCZ_PAD)), b = sizeof(float) * 64 * ACC_N; return a > b ? a : b; }
+__host__ __device__ __forceinline__ size_t schur_smem_bytes(int N) { return sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * (8 * N + SCZ_PAD)); }
 
 // addToHessianTop (BA:1648-1779, MatrixAccumulators.h:776-937) from the Jacobian records of the sampling kernel: one CTA per (bin, slice).
 // Warp k of the CTA owns entries [24 (k & 3), 24 (k & 3) + 24) of the packed 13x13 block for residual slots 32 (k >> 2) + lane; every
@@ -141,16 +149,18 @@ __device__ __forceinline__ void acc_quarter(float (&acc)[24], const float *rec, 
 #pragma unroll
     for (int k = 0; k < 24; k++) acc[k] += acc_entry(24 * Q + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
 }
-__device__ __forceinline__ void accumulate_role(const DevWin &w, const int cur, const int job, float *sm) {
-    const int N = w.N, bin = job / ACC_SLICES, sl = job - bin * ACC_SLICES, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+__global__ void __launch_bounds__(128, 6) accumulate_kernel(const DevWin w, const int respect_done) {
+    pdl_enter();
+    if (respect_done && w.ctrl->done) return;
+    const int job = blockIdx.x, bin = job / ACC_SLICES, sl = job - bin * ACC_SLICES, tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+    const int cur = w.ctrl->cur;
     const int b0 = w.res_bin_begin[bin], b1 = w.res_bin_begin[bin + 1];
     const int len = (b1 - b0 + ACC_SLICES - 1) / ACC_SLICES, a0 = min(b0 + sl * len, b1), a1 = min(a0 + len, b1);
-    const int q = wid & 3, slot = (wid >> 2) * 32 + lane;
     float acc[24];
 #pragma unroll
     for (int k = 0; k < 24; k++) acc[k] = 0.f;
     const float *rj = w.rj[cur];
-    for (int r = a0 + slot; r < a1; r += 64) {
+    for (int r = a0 + lane; r < a1; r += 32) {
         const float4 *p4 = reinterpret_cast<const float4 *>(rj + (size_t) r * RJ_STRIDE);
         const float4 last = __ldg(p4 + 8);
         if (last.w == 0.f) continue;                 // not a good residual: no record
@@ -167,30 +177,23 @@ __device__ __forceinline__ void accumulate_role(const DevWin &w, const int cur, 
         else if (q == 2) acc_quarter<2>(acc, rec, Qx, Qy);
         else acc_quarter<3>(acc, rec, Qx, Qy);
     }
-    float *s_red = sm;                               // [64 slots][ACC_N]
+    // the 24 sums over the warp's 32 slots: transposing butterfly on 32 values (8 padding zeros), lane L ends up with entry L
+    float v[32];
 #pragma unroll
-    for (int k = 0; k < 24; k++) s_red[slot * ACC_N + 24 * q + k] = acc[k];
-    __syncthreads();
-    if (tid < ACC_N) {
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-#pragma unroll 4
-        for (int sl2 = 0; sl2 < 64; sl2 += 4) { t0 += s_red[sl2 * ACC_N + tid]; t1 += s_red[(sl2 + 1) * ACC_N + tid]; t2 += s_red[(sl2 + 2) * ACC_N + tid]; t3 += s_red[(sl2 + 3) * ACC_N + tid]; }
-        w.acc_bin[(size_t) job * ACC_N + tid] = (t0 + t1) + (t2 + t3);
-    }
-    (void) N;
+    for (int k = 0; k < 32; k++) v[k] = k < 24 ? acc[k] : 0.f;
+    const float tot = warp_transpose_sum(v, lane);
+    if (lane < 24) w.acc_bin[(size_t) job * ACC_N + 24 * q + lane] = tot;
 }
 
-// CTA role by job = blockIdx.x + job_offset: the first n_sc_chunks jobs are Schur chunks, the others (bin, slice) accumulate jobs
-__global__ void __launch_bounds__(256) schur_acc_kernel(const DevWin w, const int respect_done, const int job_offset) {
+__global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int respect_done) {
+    pdl_enter();
     if (respect_done && w.ctrl->done) return;
     extern __shared__ __align__(16) float sm[];
-    const int job_id = (int) blockIdx.x + job_offset;
-    if (job_id >= w.n_sc_chunks) { accumulate_role(w, w.ctrl->cur, job_id - w.n_sc_chunks, sm); return; }
     const int N = w.N, NB = 8 * N, ZS = NB + SCZ_PAD;
     const int cur = w.ctrl->cur;
     float *sT = sm;                                  // [SC_CHUNK][N][T_STRIDE] raw Schur rows
     float *sZ = sT + SC_CHUNK * N * T_STRIDE;        // [SC_CHUNK][ZS]         augmented, scaled
-    const int c = job_id, tid = threadIdx.x;
+    const int c = blockIdx.x, tid = threadIdx.x;
     const int begin = w.sc_chunk_begin[c], cnt = w.sc_chunk_count[c];
     {   // stage the rows of the chunk's points (contiguous in T)
         const float4 *src = reinterpret_cast<const float4 *>(w.T[cur] + (size_t) begin * N * T_STRIDE);
@@ -317,6 +320,7 @@ __host__ __device__ __forceinline__ int st_stride(int N) { return ST_S_JK + 64 *
 constexpr int ST_THREADS = 512;
 
 __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w, const int respect_done) {
+    pdl_enter();
     if (respect_done && w.ctrl->done) return;
     extern __shared__ __align__(16) double smd[];
     const int N = w.N, NB = 8 * N, tid = threadIdx.x;
@@ -545,6 +549,7 @@ __device__ __forceinline__ void assemble_body(const DevWin &w, const bool p2p) {
 }
 
 __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int respect_done) {
+    pdl_enter();
     if (respect_done && w.ctrl->done) return;
     const bool p2p = w.p2p_on && w.world > 1;
     assemble_body(w, p2p);
@@ -566,6 +571,7 @@ namespace cmlba {
 // Reduced camera system: assemble, damp, Jacobi-scale, LDL^T (lower triangle, like Eigen's default), solve,
 // orthogonalise against the gauge nullspaces, frame steps + new frame states + pair constants, xAd.
 __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int respect_done) {
+    pdl_enter();
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     extern __shared__ __align__(16) double smd[];
@@ -798,6 +804,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
 // ------------------------------------------------------------------------------------------------
 // Per-point back-substitution and step (BA:1455-1487, 976-994) + convergence test (BA:1013-1026)
 __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const int respect_done) {
+    pdl_enter();
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     const int N = w.N, cur = ctrl->cur;
@@ -876,6 +883,7 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
 // std::nth_element leaves at index floor(0.7 n)), accept bookkeeping of run() (forceAccept path).
 // mode 0: first linearization of run() (+applyActiveRes)  1: GN iteration  2: final linearizeAll(true)  3: stage call (no flip)
 __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, const int mode, const int respect_done) {
+    pdl_enter();
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     const int tid = threadIdx.x;
@@ -1039,6 +1047,7 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
 
 // multi-GPU: this rank's record for the all-gather that precedes post_linearize_kernel (see DevWin::post_send)
 __global__ void __launch_bounds__(1024) pack_post_kernel(const DevWin w, const int respect_done) {
+    pdl_enter();
     Ctrl *ctrl = w.ctrl;
     (void) respect_done;   // always packs: every rank must feed the collective, even after its own early exit
     const int tid = threadIdx.x;
@@ -1090,6 +1099,7 @@ __global__ void commit_candidate_kernel(const DevWin w) { if (threadIdx.x == 0 &
 
 // forceAccept = false: undo a rejected step (loadSateBackup, BA:928-946).  `it1` = the iteration counter value the step belongs to.
 __global__ void __launch_bounds__(256) restore_state_kernel(const DevWin w, const int it1) {
+    pdl_enter();
     Ctrl *ctrl = w.ctrl;
     if (ctrl->rejected_at != it1) return;
     const int p = blockIdx.x * 256 + threadIdx.x;

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(256) bin_finish_kernel(const DevWin w) {
 // ------------------------------------------------------------------------------------------------
 template <bool kDump, int LT_CWARPS, int LT_STAGES>
 __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const DevWin w, const __grid_constant__ TileMaps tm, const int fix, const int respect_done) {
+    pdl_enter();
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     extern __shared__ __align__(1024) unsigned char lt_smem[];
@@ -252,9 +253,9 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
     if (c0 >= c1) return;
     // development trace: stamp k of this warp (SM clock); compiled to a predicated-off store in normal runs
     long long *trace = (w.lt_mode & 2) ? w.lt_trace + ((size_t) blockIdx.x * 16 + warp) * 32 : nullptr;
-    int tr_k = 0;
-#define LT_STAMP() do { if (trace && lane == 0 && tr_k < 32) trace[tr_k++] = clock64(); } while (0)
-    LT_STAMP();
+#define LT_STAMPK(k) do { if (trace && (k) < 30 && lane == (__ffs(__activemask()) - 1)) trace[(k)] = clock64(); } while (0)
+    LT_STAMPK(0);
+    if (trace && lane == 0) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); trace[30] = gt; }
     const int r_first = c0 * 32, r_last = min(c1 * 32, w.R) - 1;
     // one record per CTA, prepared by bin_segments_kernel: tile jobs [q0, q1] of the CTA (all non-empty), first target, and the descriptors /
     // user counts of its first four tiles -- a single load before the first boxes can be issued
@@ -355,7 +356,8 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
         const float4 *wtp = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
         const float4 c0v = __ldg(colp), c1v = __ldg(colp + 1), w0v = __ldg(wtp), w1v = __ldg(wtp + 1);
         const uint32_t pht_next = (c + LT_CWARPS < c1) ? __ldg(w.r_pht + min((c + LT_CWARPS) * 32 + lane, w.R - 1)) : pht;     // for the L2 prefetch below
-        LT_STAMP();                                  // pass start
+        const int tr_b = 1 + 7 * ((c - c0 - warp) / LT_CWARPS);
+        LT_STAMPK(tr_b);                             // pass start
         if (!pairs_ready) { mbar_wait(pairs_bar, 0); pairs_ready = true; }
         const PairPre *ppp = (t - t_first < 2) ? s_pairs + (t - t_first) * N + h : w.pairs + h * N + t;
         const PairPre &pp = *ppp;
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
             for (int q = q_lo; q <= q_hi; q++) { const int k = q - q0; ok = ok && lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1)); }
             tma_ok = __all_sync(0xffffffffu, ok);
         }
-        LT_STAMP();                                  // tiles landed (header loads arrived)
+        LT_STAMPK(tr_b + 1);                         // tiles landed (header loads arrived)
         if ((w.lt_mode & 1) == 1) {      // development: ring protocol only
             __syncwarp();
             if (tma_ok && lane == 0) for (int q = q_lo; q <= q_hi; q++) release(q - q0);
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
                 else sample = true;
             }
         }
+        LT_STAMPK(tr_b + 2);                         // projection done
         // ---- taps: from the staged tile when the whole footprint is inside its box, else from the image (image/Array2D.h:265-286)
         int ox = 0, oy = 0, pitch = w.W;
         const float4 *tbase = w.img[t];
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
                 sgy[i] = t00.z * w00 + t10.z * w10 + t01.z * w01 + t11.z * w11;
             }
         }
-        LT_STAMP();                                  // taps done
+        LT_STAMPK(tr_b + 3);                         // taps done
         if (c + LT_CWARPS < c1) {                     // the point records of this warp's next pass: on their way to L2 while this one computes
             const int pn = (int) (pht_next & 0xffffffu);
             prefetch_l2(w.pt_idepth + pn); prefetch_l2(w.pt_x + pn); prefetch_l2(w.pt_y + pn); prefetch_l2(w.pt_colors + (size_t) pn * 8); prefetch_l2(w.pt_weights + (size_t) pn * 8);
@@ -522,6 +525,7 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
                     d[i] = rF; d[8 + i] = h1; d[16 + i] = h2; d[24 + i] = ja; d[32 + i] = jb;
                 }
             }
+            LT_STAMPK(tr_b + 4);                         // photometric sums done
             if (!finite) {
                 // BA:220-223 sets the *committed* state to OOB.  (The reference leaves a stale isActiveAndIsGoodNEW
                 // behind in that case; only reachable with NaN/Inf texels, we clear it.)
@@ -608,6 +612,7 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
                 }
             }
         }
+        LT_STAMPK(tr_b + 5);                         // classification, Jacobians done
         if (valid) {
             // applyRes (BA:2051-2093), as the candidate that becomes current when the step is accepted
             if (st != RES_OOB && st_out != RES_OOB) { st_out = nst; e_out = ne; }
@@ -634,12 +639,13 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
                 rj4[RJ_STRIDE / 4 - 1] = make_float4(rec[32], rec[33], rec[34], 1.f);
             } else rj4[RJ_STRIDE / 4 - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        LT_STAMP();                                  // pass done
+        LT_STAMPK(tr_b + 6);                         // pass done
         // chunk energy (fp64, fixed order)
         const double es = warp_sum_d(ret);
         if (lane == 0) w.energy_part[c] = es;
     }
-#undef LT_STAMP
+    if (trace && lane == 0) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); trace[31] = gt; }
+#undef LT_STAMPK
 }
 
 }  // namespace cmlba

@@ -81,6 +81,7 @@ __device__ __forceinline__ void assemble_element(const DevWin &w, const bool p2p
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const DevWin w, const int respect_done) {
+    pdl_enter();
     if (respect_done && w.ctrl->done) return;          // uniform over the grid
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int) cluster.num_blocks(), rank = (int) cluster.block_rank();

@@ -23,6 +23,6 @@ for cta in (0, 73, int(np.argmax(ends))):
     t0 = tr[cta, :, :30][tr[cta, :, :30] > 0].min()
     print(f"== CTA {cta}")
     for wv in range(16):
-        v = tr[cta, wv, :30]; v = v[v > 0]
-        if v.size:
-            print(f"  warp {wv:2d}: " + " ".join(f"{(x - t0) / 1965.0:6.2f}" for x in v))
+        v = tr[cta, wv, :30]
+        if (v > 0).any():
+            print(f"  warp {wv:2d}: " + " ".join((f"{(x - t0) / 1965.0:6.2f}" if x > 0 else "     -") + (" |" if k % 7 == 0 else "") for k, x in enumerate(v[:22])))
