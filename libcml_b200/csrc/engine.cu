@@ -251,6 +251,7 @@ public:
     int n_sm = 148;
     int lt_variant = 0, lt_mode = 0, lt_exact = 0;
     bool use_pdl = true;
+    int pdl_mask = 48;            // development (CMLBA_PDL_MASK): 1 linearize 2 post 4 accumulate 8 schur 16 stitch 32 assemble 64 solve 128 point step
     int tail_cluster_max = 0;     // largest cluster tail_kernel can be scheduled with (0: fused tail unavailable -> schur / stitch_pair / assemble)   // development switches (CMLBA_LT_VARIANT, CMLBA_LT_MODE): kernel shape, streaming-only mode
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
         d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj0, d_rj1, d_T0, d_T1, d_dbg, d_acc_bin, d_sc_part, d_stage[MAXF];
@@ -302,6 +303,7 @@ public:
         if (const char *v = getenv("CMLBA_LT_VARIANT")) lt_variant = atoi(v);
         if (const char *v = getenv("CMLBA_LT_MODE")) lt_mode = atoi(v);
         if (getenv("CMLBA_NO_PDL")) use_pdl = false;
+        if (const char *v = getenv("CMLBA_PDL_MASK")) pdl_mask = atoi(v);
         if (const char *v = getenv("CMLBA_LT_EXACT")) lt_exact = atoi(v);
         CK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         CK(cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1110,11 +1112,11 @@ public:
     // Kernels of the pass / Gauss-Newton chain are launched with programmatic stream serialization: kernel k+1 may be scheduled while
     // kernel k still runs; its CTAs block in pdl_enter() (griddepcontrol.wait) until kernel k has completed.  CMLBA_NO_PDL=1 turns it off.
     template <typename... KArgs, typename... Args>
-    void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    void launch_pdl(int site, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
         cudaLaunchConfig_t lc = {};
         lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = stream;
         cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = (use_pdl && (pdl_mask & site)) ? 1 : 0;
         lc.attrs = at; lc.numAttrs = 1;
         if (cudaLaunchKernelEx(&lc, kernel, KArgs(args)...) != cudaSuccess) set_error(std::string("kernel launch: ") + cudaGetErrorString(cudaGetLastError()));
         launches++;
@@ -1127,8 +1129,8 @@ public:
         if (lt_mode & 2) { if (d_lt_trace.reserve((size_t) 1024 * 16 * 32) == cudaSuccess) { cudaMemsetAsync(d_lt_trace.p, 0, (size_t) grid * 16 * 32 * 8, stream); dw.lt_trace = d_lt_trace.p; } }
 #define LT_LAUNCH(CW, ST)                                                                                                                                      \
     do {                                                                                                                                                       \
-        if (want_dbg) launch_pdl(linearize_tile_kernel<true, CW, ST>, dim3(grid), dim3(CW * 32), lt_smem_bytes(dw.N, CW, ST), dw, tile_maps, fix, respect_done);    \
-        else launch_pdl(linearize_tile_kernel<false, CW, ST>, dim3(grid), dim3(CW * 32), lt_smem_bytes(dw.N, CW, ST), dw, tile_maps, fix, respect_done);            \
+        if (want_dbg) launch_pdl(1, linearize_tile_kernel<true, CW, ST>, dim3(grid), dim3(CW * 32), lt_smem_bytes(dw.N, CW, ST), dw, tile_maps, fix, respect_done);    \
+        else launch_pdl(1, linearize_tile_kernel<false, CW, ST>, dim3(grid), dim3(CW * 32), lt_smem_bytes(dw.N, CW, ST), dw, tile_maps, fix, respect_done);            \
     } while (0)
         switch (lt_variant) {
             case 1: LT_LAUNCH(8, 4); break;
@@ -1143,25 +1145,25 @@ public:
             if (dw.p2p_post_on) {   // pushed through peer memory by pack_post_kernel itself
                 dw.p2p_post_epoch = ++p2p_post_epoch;
                 dw.post_recv = reinterpret_cast<const double *>(p2p_local + 256) + (size_t) 2 * world * P2P_SLOT_DOUBLES + (size_t) (dw.p2p_post_epoch & 1ull) * world * P2P_POST_DOUBLES;
-                launch_pdl(pack_post_kernel, dim3(1), dim3(1024), 0, dw, respect_done);
+                launch_pdl(2, pack_post_kernel, dim3(1), dim3(1024), 0, dw, respect_done);
             } else {
-                launch_pdl(pack_post_kernel, dim3(1), dim3(1024), 0, dw, respect_done);
+                launch_pdl(2, pack_post_kernel, dim3(1), dim3(1024), 0, dw, respect_done);
                 const size_t rec_d = 8 + (size_t) (dw.cand_cap + 1) / 2;
                 if (g_nccl.AllGather(d_post_send.p, d_post_recv.p, rec_d, /*ncclDouble*/ 8, comm, stream) != 0) set_error("ncclAllGather failed");
             }
         }
-        launch_pdl(post_linearize_kernel, dim3(1), dim3(1024), 0, dw, mode, respect_done);
+        launch_pdl(2, post_linearize_kernel, dim3(1), dim3(1024), 0, dw, mode, respect_done);
     }
     void launch_schur(int respect_done) {
         // addToHessianTop from the Jacobian records ((bin, slice) jobs), then the Schur chunks
-        if (dw.R > 0) launch_pdl(accumulate_kernel, dim3(dw.N * dw.N * ACC_SLICES), dim3(128), 0, dw, respect_done);
-        if (dw.n_sc_chunks > 0) launch_pdl(schur_kernel, dim3(dw.n_sc_chunks), dim3(256), schur_smem(), dw, respect_done);
+        if (dw.R > 0) launch_pdl(4, accumulate_kernel, dim3(dw.N * dw.N * ACC_SLICES), dim3(32), 0, dw, respect_done);
+        if (dw.n_sc_chunks > 0) launch_pdl(8, schur_kernel, dim3(dw.n_sc_chunks), dim3(256), schur_smem(), dw, respect_done);
     }
     // Schur complement + stitching + assembly of sys = [HA | bA | H_sc | b_sc]: one cluster kernel when a cluster of >= N CTAs is available
     bool tail_fused() const { return dw.N <= tail_cluster_max && dw.n_sc_chunks > 0; }
     void launch_tail(int respect_done) {
         if (!tail_fused()) { launch_schur(respect_done); launch_stitch(respect_done); return; }
-        launch_pdl(accumulate_kernel, dim3(dw.N * dw.N * ACC_SLICES), dim3(128), 0, dw, respect_done);
+        launch_pdl(4, accumulate_kernel, dim3(dw.N * dw.N * ACC_SLICES), dim3(32), 0, dw, respect_done);
         const int cs = tail_cluster_max;                 // 16 CTAs per host frame when the device can co-schedule them (twice the Schur parallelism), else 8
         if (dw.p2p_on) dw.p2p_epoch = ++p2p_epoch;       // the same count on every rank: one exchange per stitched system
         cudaLaunchConfig_t lc = {}; cudaLaunchAttribute at[1];
@@ -1174,15 +1176,15 @@ public:
     // one CTA per ordered frame pair, then the gather into sys = [HA | bA | H_sc | b_sc]
     void launch_stitch(int respect_done) {
         const int N = dw.N, n = dw.n;
-        launch_pdl(stitch_pair_kernel, dim3(N * N), dim3(ST_THREADS), stitch_smem(), dw, respect_done);
+        launch_pdl(16, stitch_pair_kernel, dim3(N * N), dim3(ST_THREADS), stitch_smem(), dw, respect_done);
         if (dw.p2p_on) dw.p2p_epoch = ++p2p_epoch;       // the same count on every rank: one exchange per stitched system
-        launch_pdl(assemble_kernel, dim3((2 * n * n + 2 * n + 255) / 256 + 3), dim3(256), 0, dw, respect_done);   // +3 CTAs: 20 warps for HA[C,C], bA[C]
+        launch_pdl(32, assemble_kernel, dim3((2 * n * n + 2 * n + 255) / 256 + 3), dim3(256), 0, dw, respect_done);   // +3 CTAs: 20 warps for HA[C,C], bA[C]
     }
     int launch_solve_sequence(int respect_done) {
         launch_tail(respect_done);
         if (world > 1 && !dw.p2p_on) { int rc = allreduce_system(); if (rc) return rc; }      // with peer memory solve_kernel sums the ranks itself
-        launch_pdl(solve_kernel, dim3(1), dim3(256), solve_smem(), dw, respect_done);
-        if (dw.P > 0) launch_pdl(point_step_kernel, dim3(dw.n_pt_blocks), dim3(256), 0, dw, respect_done);
+        launch_pdl(64, solve_kernel, dim3(1), dim3(256), solve_smem(), dw, respect_done);
+        if (dw.P > 0) launch_pdl(128, point_step_kernel, dim3(dw.n_pt_blocks), dim3(256), 0, dw, respect_done);
         return CMLBA_OK;
     }
 
@@ -1213,7 +1215,7 @@ public:
             for (; it < batch_end; it++) {
                 rc = launch_solve_sequence(1); if (rc) return rc;
                 launch_linearize(0, 1); launch_post(1, 1);
-                if (!cfg.force_accept) launch_pdl(restore_state_kernel, dim3(std::max(dw.n_pt_blocks, 1)), dim3(256), 0, dw, it + 1);   // no-op unless the step was rejected
+                if (!cfg.force_accept) launch_pdl(128, restore_state_kernel, dim3(std::max(dw.n_pt_blocks, 1)), dim3(256), 0, dw, it + 1);   // no-op unless the step was rejected
             }
             if (it < iterations) {
                 CK(cudaMemcpyAsync(peek_h.p, reinterpret_cast<const char *>(d_ctrl.p) + offsetof(Ctrl, done), sizeof(int), cudaMemcpyDeviceToHost, stream));

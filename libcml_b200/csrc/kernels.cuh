@@ -141,48 +141,52 @@ namespace cmlba {
 constexpr int SCZ_PAD = 8;     // z_c (4) z_b (1) pad (3)
 __host__ __device__ __forceinline__ size_t schur_smem_bytes(int N) { return sizeof(float) * ((size_t) SC_CHUNK * N * T_STRIDE + (size_t) SC_CHUNK * (8 * N + SCZ_PAD)); }
 
-// addToHessianTop (BA:1648-1779, MatrixAccumulators.h:776-937) from the Jacobian records of the sampling kernel: one CTA per (bin, slice).
-// Warp k of the CTA owns entries [24 (k & 3), 24 (k & 3) + 24) of the packed 13x13 block for residual slots 32 (k >> 2) + lane; every
-// thread keeps its 24 sums in registers over its residuals (slot, slot + 64, ...), then the 64 slots are summed in order.
-template <int Q>
-__device__ __forceinline__ void acc_quarter(float (&acc)[24], const float *rec, const float *Qx, const float *Qy) {
-#pragma unroll
-    for (int k = 0; k < 24; k++) acc[k] += acc_entry(24 * Q + k, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
-}
-__global__ void __launch_bounds__(128, 6) accumulate_kernel(const DevWin w, const int respect_done) {
+// addToHessianTop (BA:1648-1779, MatrixAccumulators.h:776-937) from the Jacobian records of the sampling kernel: one warp per (bin,
+// slice).  Every lane keeps the 91 sums of the packed 13x13 block in registers over its residuals (lane, lane + 32, ...: the next
+// record is in flight while the current one is evaluated), then one transposing butterfly per 32 entries sums the lanes.
+__global__ void __launch_bounds__(32) accumulate_kernel(const DevWin w, const int respect_done) {
     pdl_enter();
     if (respect_done && w.ctrl->done) return;
-    const int job = blockIdx.x, bin = job / ACC_SLICES, sl = job - bin * ACC_SLICES, tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+    const int job = blockIdx.x, bin = job / ACC_SLICES, sl = job - bin * ACC_SLICES, lane = threadIdx.x;
     const int cur = w.ctrl->cur;
     const int b0 = w.res_bin_begin[bin], b1 = w.res_bin_begin[bin + 1];
     const int len = (b1 - b0 + ACC_SLICES - 1) / ACC_SLICES, a0 = min(b0 + sl * len, b1), a1 = min(a0 + len, b1);
-    float acc[24];
+    float acc[ACC_N];
 #pragma unroll
-    for (int k = 0; k < 24; k++) acc[k] = 0.f;
-    const float *rj = w.rj[cur];
-    for (int r = a0 + lane; r < a1; r += 32) {
-        const float4 *p4 = reinterpret_cast<const float4 *>(rj + (size_t) r * RJ_STRIDE);
-        const float4 last = __ldg(p4 + 8);
-        if (last.w == 0.f) continue;                 // not a good residual: no record
+    for (int k = 0; k < ACC_N; k++) acc[k] = 0.f;
+    const float4 *rj4 = reinterpret_cast<const float4 *>(w.rj[cur]);
+    float4 nx[9];                                    // the next record of this lane: in flight while the current one is evaluated
+    int r = a0 + lane;
+    if (r < a1) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) nx[k] = __ldg(rj4 + (size_t) r * 9 + k);
+    }
+    while (r < a1) {
         float rec[RJ_STRIDE];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const float4 v = __ldg(p4 + k); rec[4 * k] = v.x; rec[4 * k + 1] = v.y; rec[4 * k + 2] = v.z; rec[4 * k + 3] = v.w; }
-        rec[32] = last.x; rec[33] = last.y; rec[34] = last.z; rec[35] = 0.f;
-        float Qx[10], Qy[10];
-        const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
+        for (int k = 0; k < 9; k++) { rec[4 * k] = nx[k].x; rec[4 * k + 1] = nx[k].y; rec[4 * k + 2] = nx[k].z; rec[4 * k + 3] = nx[k].w; }
+        r += 32;
+        if (r < a1) {
 #pragma unroll
-        for (int k = 0; k < 10; k++) { Qx[k] = a00 * rec[k] + a01 * rec[10 + k]; Qy[k] = a01 * rec[k] + a11 * rec[10 + k]; }
-        if (q == 0) acc_quarter<0>(acc, rec, Qx, Qy);
-        else if (q == 1) acc_quarter<1>(acc, rec, Qx, Qy);
-        else if (q == 2) acc_quarter<2>(acc, rec, Qx, Qy);
-        else acc_quarter<3>(acc, rec, Qx, Qy);
+            for (int k = 0; k < 9; k++) nx[k] = __ldg(rj4 + (size_t) r * 9 + k);
+        }
+        if (rec[35] != 0.f) {                        // a good residual (the others carry no record)
+            float Qx[10], Qy[10];
+            const float a00 = rec[20], a01 = rec[21], a11 = rec[22];
+#pragma unroll
+            for (int k = 0; k < 10; k++) { Qx[k] = a00 * rec[k] + a01 * rec[10 + k]; Qy[k] = a01 * rec[k] + a11 * rec[10 + k]; }
+#pragma unroll
+            for (int e = 0; e < 91; e++) acc[e] += acc_entry(e, rec, rec + 10, Qx, Qy, rec + 23, rec + 26, rec + 29);
+        }
     }
-    // the 24 sums over the warp's 32 slots: transposing butterfly on 32 values (8 padding zeros), lane L ends up with entry L
-    float v[32];
+    // sum over the 32 lanes: transposing butterfly, lane L ends up with entry (g, L)
 #pragma unroll
-    for (int k = 0; k < 32; k++) v[k] = k < 24 ? acc[k] : 0.f;
-    const float tot = warp_transpose_sum(v, lane);
-    if (lane < 24) w.acc_bin[(size_t) job * ACC_N + 24 * q + lane] = tot;
+    for (int g = 0; g < 3; g++) {
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = acc[g * 32 + k];
+        w.acc_bin[(size_t) job * ACC_N + g * 32 + lane] = warp_transpose_sum(v, lane);
+    }
 }
 
 __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int respect_done) {
