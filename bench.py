@@ -55,9 +55,9 @@ def ncu_traffic(workload):
         return None, None
     import glob
     import re
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernels_*.txt")), reverse=True):
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_kernels*.txt")), reverse=True):
         txt = open(path).read()
-        m = re.search(r"== void linearize_kernel.*?dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+).*?dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", txt, re.S)
+        m = re.search(r"== void linearize_tile_kernel.*?dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+).*?dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", txt, re.S)
         if m:
             unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             return float(m.group(1)) * unit.get(m.group(2), 1.0) + float(m.group(3)) * unit.get(m.group(4), 1.0), os.path.relpath(path, ROOT)
@@ -95,9 +95,30 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def config_dict(workload, scaling):
+    """The `config` object of the JSON line: identical in both arms (ours / --impl reference) for the same command line."""
+    from libcml_b200 import synth
+    W, H, N, ppk, iters, affine = synth.CONFIGS[workload]
+    return {"workload": f"{workload}: {N} KF x {ppk} pts/KF, {W}x{H} level 0, {iters} GN iterations" + (", affine brightness" if affine else ""),
+            "residuals_per_window": N * (N - 1) * ppk, "pass": "linearize + accumulate + Schur + stitch (one pass of the Jacobian + Schur accumulation over the window)",
+            "sharding": "weak: every GPU owns a full window-sized shard of points" if scaling == "weak" else "strong: the points of ONE window are split over the GPUs"}
+
+
+def pin_prefix():
+    """taskset prefix that pins the single-threaded reference to one core; empty if taskset is missing."""
+    import shutil
+    if not shutil.which("taskset"):
+        return [], None
+    try:
+        core = sorted(os.sched_getaffinity(0))[-1]
+    except Exception:
+        core = 0
+    return ["taskset", "-c", str(core)], core
+
+
 def run_reference_bench(win_path, repeat):
     """Times the reference's own CPU implementation (oracle/_ref/cmlba_ref, 1 thread = upstream behaviour)."""
-    r = subprocess.run([REF_BIN, "--window", win_path, "--mode", "bench", "--repeat", str(repeat)], capture_output=True, text=True, timeout=1500)
+    r = subprocess.run(pin_prefix()[0] + [REF_BIN, "--window", win_path, "--mode", "bench", "--repeat", str(repeat)], capture_output=True, text=True, timeout=1500)
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if r.returncode != 0 or not line:
         raise RuntimeError("cmlba_ref bench failed: " + r.stderr[-500:])
@@ -152,8 +173,8 @@ def reference_arm(args):
     path = window_file(win, "ref")
     t0 = time.time()
     best = None
-    steps = max(1, min(args.steps, 5))
-    for _ in range(max(0, min(args.warmup, 1)) + 1):   # one untimed warm pass at most: a pass costs seconds on one core
+    steps = max(1, args.steps)                          # every step = one full pass over the window (0.17 s on one core at c2) + one run()
+    for _ in range(max(0, min(args.warmup, 1)) + 1):   # one untimed warm invocation at most: a run() costs ~0.7 s on one core
         res = run_reference_bench(path, steps)
         best = res
     os.remove(path)
@@ -163,9 +184,10 @@ def reference_arm(args):
     e2e = R * best["iterations"] / best["t_run"]
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": t_pass * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (projection f64)", "data": "synthetic", "impl": "reference",
-           "config": {"workload": f"{args.workload}: {N} KF x {ppk} pts/KF, {W}x{H} level 0, {iters} GN iterations", "residuals": R,
-                      "note": "unmodified reference DSOBundleAdjustment compiled from /root/reference (oracle/_ref), min over repeats"},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "cpu": cpu_model(), "nproc": os.cpu_count(),
+           "config": config_dict(args.workload, args.scaling),
+           "notes": {"impl": "unmodified reference DSOBundleAdjustment compiled from /root/reference (oracle/_ref: g++ -O2 -march=x86-64-v3 -fno-math-errno -DNDEBUG, the reference's Release flags except -march=native so that the binary runs on any GPU host), min over the steps",
+                     "pinned_core": pin_prefix()[1]},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "cpu": cpu_model(), "nproc": os.cpu_count(), "pinned_core": pin_prefix()[1],
                             "sample": f"full {args.workload} window, min of {steps} repeats; t_linearize={best['t_linearize']:.4f}s t_top={best['t_top']:.4f}s t_sc={best['t_sc']:.4f}s t_run={best['t_run']:.3f}s"},
            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -180,6 +202,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: weak = a window-sized shard per GPU (default), strong = ONE window split over the GPUs (BASELINE.json configs[3] with --workload c4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--nccl-only", action="store_true", help="N>1: all-reduce the reduced system with NCCL instead of the peer-memory exchange")
@@ -212,9 +235,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     W, H, N, ppk, iters, affine = synth.CONFIGS[args.workload]
-    # weak scaling: every rank owns a full c2-sized shard of points (different seed), frames/images replicated
+    # weak scaling: every rank owns a full window-sized shard of points (different seed), frames/images replicated;
+    # strong scaling: the points of the ONE seed-1234 window are dealt round-robin to the ranks
     win = synth.make_config(args.workload, seed=1234)
-    if world > 1:
+    if world > 1 and args.scaling == "strong":
+        sel = np.arange(win["pt_host"].size)[rank::world]
+        for k in ("pt_host", "pt_xy", "pt_idepth"):
+            win[k] = win[k][sel]
+    elif world > 1:
         shard = synth.make_config(args.workload, seed=1234 + 1000 * rank, with_gradients=False)
         for k in ("pt_host", "pt_xy"):
             win[k] = shard[k]
@@ -248,10 +276,13 @@ def main():
     clocks["note"] = "sampled from the start of the timed passes to the end of 2000 further identical (untimed) passes"
     R = br.residuals
     ms = torch.tensor([br.ms_pass, br.ms_linearize, brw.ms_pass], dtype=torch.float64, device="cuda")
+    Rtot = torch.tensor([float(R)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(Rtot, op=dist.ReduceOp.SUM)
     ms_pass, ms_lin, ms_pass_warm = [float(v) for v in ms.cpu()]
-    value = world * R / (ms_pass * 1e-3)
+    R_all = float(Rtot.cpu()[0])                         # residuals all ranks processed per pass
+    value = R_all / (ms_pass * 1e-3)
 
     # ---------------- end to end through the C ABI from pinned host buffers
     # the rectified level-0 gray images (what CaptureImage::getGrayImage(0) holds); the derivative images are built on the device
@@ -284,7 +315,36 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_ms.cpu()[0])
-    e2e_value = world * R * e2e_iters / e2e_s
+    e2e_value = R_all * e2e_iters / e2e_s
+
+    # ---------------- N > 1: self-check.  (1) every rank finished the same run(): iterations and poses identical;  (2) the reduced system
+    # exchanged over peer memory equals the one exchanged by ncclAllReduce on a second handle with the same shard (same partials).
+    multi = None
+    if world > 1:
+        fr = ba.getFrames()
+        mine = torch.from_numpy(np.concatenate([fr["world_to_cam"].ravel(), fr["affine"].ravel(), [float(ba.last_result.iterations_done), ba.last_result.energy_last]])).cuda()
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()
+        pose_spread = float(np.abs(allr[:, :-2] - allr[0, :-2]).max())
+        iters_same = bool((allr[:, -2] == allr[0, -2]).all())
+
+        def stage_sys(peer):
+            b2 = DSOBundleAdjustment(device=local_rank, iterations=iters)
+            b2.initCommunicator(rank, world, peer_memory=peer)
+            c2 = b2.loadWindow(win)
+            b2.prepare(c2); b2.linearizeAll(False); b2.applyActiveRes(); b2.solveSystem(0)
+            sy = b2.read("sys", np.float64).copy(); x = b2.read("x", np.float64).copy()
+            b2.close()
+            return sy, x
+        sys_p, x_p = stage_sys(not args.nccl_only)
+        sys_n, x_n = stage_sys(False)
+        d_sys = float(np.abs(sys_p - sys_n).max() / max(np.abs(sys_n).max(), 1e-300)); d_x = float(np.abs(x_p - x_n).max() / max(np.abs(x_n).max(), 1e-300))
+        chk = torch.tensor([d_sys, d_x], dtype=torch.float64, device="cuda"); dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+        d_sys, d_x = [float(v) for v in chk.cpu()]
+        multi = {"ranks": world, "iterations_identical": iters_same, "iterations": int(allr[0, -2]), "pose_affine_max_abs_spread_over_ranks": pose_spread,
+                 "reduced_system_peer_vs_nccl_rel": d_sys, "x_peer_vs_nccl_rel": d_x,
+                 "ok": bool(iters_same and pose_spread == 0.0 and d_sys < 1e-12 and d_x < 1e-9)}
 
     if rank != 0:
         if world > 1:
@@ -295,21 +355,23 @@ def main():
     achieved = R * b_alg(N) / (ms_lin * 1e-3) / 1e9
     traffic, traffic_src = ncu_traffic(args.workload)
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_pass,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (projection f64)", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {N} KF x {ppk} pts/KF per GPU, {W}x{H} level 0, {iters} GN iterations", "residuals_per_gpu": R,
-                      "l2": "flushed between timed passes (384 MB write outside the timed region)", "parallelism": f"points sharded x{world}, frames replicated" + ("" if world == 1 else (", reduced system + post-linearize records over NVLink peer memory (cudaIpc)" if getattr(ba, "peer_memory", False) else ", reduced system by ncclAllReduce, post-linearize records by ncclAllGather")),
-                      "pass": "linearize+accumulate+schur+stitch"},
+           "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 (projection f64)", "data": "synthetic",
+           "config": config_dict(args.workload, args.scaling),
+           "notes": {"residuals_per_gpu": R, "residuals_all_gpus": R_all, "l2": "flushed between timed passes (384 MB write outside the timed region)",
+                     "parallelism": f"points sharded x{world}, frames replicated" + ("" if world == 1 else (", reduced system + post-linearize records over NVLink peer memory (cudaIpc)" if getattr(ba, "peer_memory", False) else ", reduced system by ncclAllReduce, post-linearize records by ncclAllGather"))},
            "ms_per_step_l2_warm": ms_pass_warm, "value_l2_warm": world * R / (ms_pass_warm * 1e-3),
-           "kernel_ms": {"linearize_accumulate": br.ms_linearize, "schur_stitch_assemble" if br.ms_stitch < 0.004 else "schur": br.ms_schur, "stitch_assemble": br.ms_stitch,
-                         "linearize_accumulate_l2_warm": brw.ms_linearize, "event_overhead_per_interval": br.ms_accumulate,
+           "kernel_ms": {"linearize": br.ms_linearize, "accumulate_schur": br.ms_schur, "stitch_assemble": br.ms_stitch,
+                         "linearize_l2_warm": brw.ms_linearize, "event_overhead_per_interval": br.ms_accumulate,
                          "note": "event-to-event intervals of a separate loop; each includes one event-record overhead"},
            "run": {"gpu_ms": run_gpu_ms, "kernel_launches": run_launches, "iterations": e2e_iters},
-           "roofline": {"bound": "hbm", "kernel": "linearize_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "roofline": {"bound": "hbm", "kernel": "linearize_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_unit": b_alg(N), "units_per_launch": R},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                    "what": f"reset + set_calib + {N} x add_frame_gray (pinned host gray images, asynchronous upload, derivative images built on the device) + add_points + run(up to {iters} GN iterations, {e2e_iters} executed) + get_frames/get_points"},
            "gpu_launches": int(br.launches_per_pass * args.steps),
            "clocks": clocks}
+    if multi is not None:
+        out["multi_gpu_check"] = multi
     # ---------------- CPU baseline: the reference itself on this box's host cores (rank 0, N=1 only)
     if world == 1 and not args.no_cpu_baseline:
         try:

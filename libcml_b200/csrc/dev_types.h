@@ -55,7 +55,7 @@ struct Ctrl {
     int iteration;      // GN iterations completed
     int accepted;
     int num_dropped;
-    int pad0;
+    int pad0;           // set when a peer-memory exchange timed out (reported as CMLBA_ERR_STATE, not as a numeric failure)
     double lambda;
     double energy_last;     // energy of the committed linearization
     double energy_new;      // energy of the candidate linearization

@@ -251,6 +251,7 @@ public:
     int n_sm = 148;
     int lt_variant = 0, lt_mode = 0, lt_exact = 0;
     bool use_pdl = true;
+    int launch_rc = CMLBA_OK;     // sticky status of the enqueue helpers (kernel launch / NCCL call failed); run() and the stage calls report it
     int pdl_mask = 48;            // development (CMLBA_PDL_MASK): 1 linearize 2 post 4 accumulate 8 schur 16 stitch 32 assemble 64 solve 128 point step
     int tail_cluster_max = 0;     // largest cluster tail_kernel can be scheduled with (0: fused tail unavailable -> schur / stitch_pair / assemble)   // development switches (CMLBA_LT_VARIANT, CMLBA_LT_MODE): kernel shape, streaming-only mode
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
@@ -1118,7 +1119,7 @@ public:
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = (use_pdl && (pdl_mask & site)) ? 1 : 0;
         lc.attrs = at; lc.numAttrs = 1;
-        if (cudaLaunchKernelEx(&lc, kernel, KArgs(args)...) != cudaSuccess) set_error(std::string("kernel launch: ") + cudaGetErrorString(cudaGetLastError()));
+        if (cudaLaunchKernelEx(&lc, kernel, KArgs(args)...) != cudaSuccess) { set_error(std::string("kernel launch: ") + cudaGetErrorString(cudaGetLastError())); launch_rc = CMLBA_ERR_CUDA; }
         launches++;
     }
 
@@ -1149,7 +1150,7 @@ public:
             } else {
                 launch_pdl(2, pack_post_kernel, dim3(1), dim3(1024), 0, dw, respect_done);
                 const size_t rec_d = 8 + (size_t) (dw.cand_cap + 1) / 2;
-                if (g_nccl.AllGather(d_post_send.p, d_post_recv.p, rec_d, /*ncclDouble*/ 8, comm, stream) != 0) set_error("ncclAllGather failed");
+                if (g_nccl.AllGather(d_post_send.p, d_post_recv.p, rec_d, /*ncclDouble*/ 8, comm, stream) != 0) { set_error("ncclAllGather failed"); launch_rc = CMLBA_ERR_CUDA; }
             }
         }
         launch_pdl(2, post_linearize_kernel, dim3(1), dim3(1024), 0, dw, mode, respect_done);
@@ -1188,6 +1189,14 @@ public:
         return CMLBA_OK;
     }
 
+    // status of a finished run / stage from the device control block: a peer exchange that timed out (a rank never reached it) is a
+    // protocol / state error, not the reference's "run() returned false"
+    int exchange_status(const Ctrl &c) {
+        if (c.pad0) { set_error("peer-memory exchange timed out: a rank did not reach the exchange (every rank must call the same sequence)"); return CMLBA_ERR_STATE; }
+        if (c.failed) { set_error("non-finite energy or step (reference run() returns false)"); return CMLBA_ERR_NUMERIC; }
+        return CMLBA_OK;
+    }
+
     int allreduce_system() {
         if (dw.p2p_on) { p2p_allreduce_kernel<<<(2 * dw.n * dw.n + 2 * dw.n + 255) / 256, 256, 0, stream>>>(dw, 0); launches++; return CMLBA_OK; }
         const size_t cnt = (size_t) 2 * dw.n * dw.n + 2 * dw.n;
@@ -1204,6 +1213,11 @@ public:
         if (iterations <= 0) iterations = cfg.iterations;
         dw.update_points_only = update_points_only ? 1 : 0;
         const int l0 = launches;
+        launch_rc = CMLBA_OK;
+        if (world > 1 && comm) {   // align the ranks on the device before the first peer exchange of this run (NCCL has no timeout; the exchanges then only bridge in-run skew)
+            CK(d_cap.reserve(1));
+            if (g_nccl.AllReduce(d_cap.p, d_cap.p, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, comm, stream) != 0) { set_error("ncclAllReduce (rank alignment) failed"); return CMLBA_ERR_CUDA; }
+        }
         CK(cudaEventRecord(ev0, stream));
         if (!cfg.force_accept) { point_prior_energy_kernel<<<1, 256, 0, stream>>>(dw); launches++; }
         launch_linearize(0, 0); launch_post(0, 0);
@@ -1228,6 +1242,7 @@ public:
         launch_linearize(1, 0); launch_post(2, 0);
         CK(cudaEventRecord(ev1, stream));
         CK(cudaGetLastError());
+        if (launch_rc) return launch_rc;
         lap("run.launch");
         rc = finish_run(out);
         if (out) {
@@ -1326,8 +1341,7 @@ public:
         if (n_dead * 4 > points_.size()) compact();
         flap("finish.compact");
         prepared = false;
-        if (c.failed) { set_error("non-finite energy or step (reference run() returns false)"); return CMLBA_ERR_NUMERIC; }
-        return CMLBA_OK;
+        return exchange_status(c);
     }
 
     // drop the whole window but keep the allocations (used by streaming callers and the end-to-end benchmark)
@@ -1685,7 +1699,8 @@ int cmlba_linearize(cmlba_handle *h, int fix, double *energy) {
         e.set_error(std::string("linearize: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA;
     }
     if (energy) *energy = c.energy_new;
-    return c.failed ? CMLBA_ERR_NUMERIC : CMLBA_OK;
+    if (e.launch_rc) { const int rc = e.launch_rc; e.launch_rc = CMLBA_OK; return rc; }
+    return e.exchange_status(c);
 }
 
 int cmlba_apply(cmlba_handle *h) {
@@ -1693,9 +1708,9 @@ int cmlba_apply(cmlba_handle *h) {
     if (!e.prepared) { e.set_error("cmlba_prepare first"); return CMLBA_ERR_STATE; }
     cudaSetDevice(e.device);
     cmlba::Ctrl c;
-    cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost);
+    if (cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) { e.set_error(std::string("apply: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA; }
     c.cur ^= 1; c.energy_last = c.energy_new;
-    cudaMemcpy(e.d_ctrl.p, &c, sizeof(c), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(e.d_ctrl.p, &c, sizeof(c), cudaMemcpyHostToDevice) != cudaSuccess) { e.set_error(std::string("apply: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA; }
     return CMLBA_OK;
 }
 
@@ -1704,22 +1719,25 @@ int cmlba_solve(cmlba_handle *h, int iteration) {
     if (!e.prepared) { e.set_error("cmlba_prepare first"); return CMLBA_ERR_STATE; }
     cudaSetDevice(e.device);
     cmlba::Ctrl c;
-    cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost);
+    if (cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) { e.set_error(std::string("solve: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA; }
     c.iteration = iteration;
-    cudaMemcpy(e.d_ctrl.p, &c, sizeof(c), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(e.d_ctrl.p, &c, sizeof(c), cudaMemcpyHostToDevice) != cudaSuccess) { e.set_error(std::string("solve: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA; }
     int rc = e.launch_solve_sequence(0);
     if (rc) return rc;
-    if (cudaStreamSynchronize(e.stream) != cudaSuccess) { e.set_error(std::string("solve: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA; }
-    cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost);
-    return c.failed ? CMLBA_ERR_NUMERIC : CMLBA_OK;
+    if (cudaStreamSynchronize(e.stream) != cudaSuccess || cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        e.set_error(std::string("solve: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA;
+    }
+    return e.exchange_status(c);
 }
 
 int cmlba_step(cmlba_handle *h, int update_points_only, int *can_break) {
     HCHK; Engine &e = h->eng;
     (void) update_points_only;   // the step is applied on the device inside cmlba_solve (solve_kernel / point_step_kernel)
+    if (!e.prepared) { e.set_error("cmlba_prepare first"); return CMLBA_ERR_STATE; }
     cmlba::Ctrl c;
-    cudaSetDevice(e.device);
-    cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost);
+    if (cudaSetDevice(e.device) != cudaSuccess || cudaMemcpy(&c, e.d_ctrl.p, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        e.set_error(std::string("step: ") + cudaGetErrorString(cudaGetLastError())); return CMLBA_ERR_CUDA;
+    }
     if (can_break) *can_break = c.canbreak;
     return CMLBA_OK;
 }
@@ -1746,6 +1764,7 @@ int cmlba_comm_ipc_open(cmlba_handle *h, const void *handles) {
 int cmlba_comm_init(cmlba_handle *h, const void *uid, int rank, int world) {
     HCHK; Engine &e = h->eng;
     if (!uid || world < 1 || rank < 0 || rank >= world) { e.set_error("bad communicator arguments"); return CMLBA_ERR_ARG; }
+    if (world > cmlba::MAXF) { e.set_error("at most 16 ranks: the peer-exchange header and the flag arrays hold 16 entries"); return CMLBA_ERR_ARG; }
     if (world == 1) { e.rank = 0; e.world = 1; return CMLBA_OK; }
     if (!cmlba::g_nccl.load(e.err)) return CMLBA_ERR_UNSUPPORTED;
     cudaSetDevice(e.device);

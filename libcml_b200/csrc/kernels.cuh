@@ -438,7 +438,7 @@ __device__ __forceinline__ bool p2p_reduce(const DevWin &w, double *dst, const i
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(f) : "memory");
             if (v >= w.p2p_epoch) break;
-            if (++spins > (1l << 23)) { s_ok = 0; break; }     // ~1 s: never hang the device on a protocol error
+            if (++spins > (1l << 26)) { s_ok = 0; break; }     // ~10 s (the ranks are aligned by NCCL at the start of run()): never hang the device on a protocol error
             __nanosleep(100);
         }
     }
@@ -455,7 +455,7 @@ __device__ __forceinline__ bool p2p_reduce(const DevWin &w, double *dst, const i
 }
 __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const DevWin w, const int respect_done) {
     if (respect_done && w.ctrl->done) return;
-    if (!p2p_reduce(w, w.sys, 2 * w.n * w.n + 2 * w.n) && threadIdx.x == 0) { w.ctrl->failed = 1; w.ctrl->done = 1; }
+    if (!p2p_reduce(w, w.sys, 2 * w.n * w.n + 2 * w.n) && threadIdx.x == 0) { w.ctrl->failed = 1; w.ctrl->pad0 = 1; w.ctrl->done = 1; }
 }
 
 // cross-rank barrier on the same epoch flags (an exchange without payload): aligns the ranks before a timed pass so that a rank
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(32) p2p_barrier_kernel(const DevWin w) {
         unsigned long long v = 0; long spins = 0;
         for (;;) {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(f) : "memory");
-            if (v >= w.p2p_epoch || ++spins > (1l << 23)) break;
+            if (v >= w.p2p_epoch || ++spins > (1l << 26)) break;
             __nanosleep(100);
         }
     }
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
     double *invd = red + 256;   // [m] reciprocals of the LDL^T pivots
     double *sysHA = w.sys, *sysbA = w.sys + nn, *sysHS = w.sys + nn + n, *sysbS = w.sys + 2 * nn + n;
     if (w.p2p_on && w.world > 1) {   // sum of the ranks' partial systems over NVLink (replaces ncclAllReduce + its launch)
-        if (!p2p_reduce(w, w.sys, 2 * nn + 2 * n)) { if (tid == 0) { ctrl->failed = 1; ctrl->done = 1; } return; }
+        if (!p2p_reduce(w, w.sys, 2 * nn + 2 * n)) { if (tid == 0) { ctrl->failed = 1; ctrl->pad0 = 1; ctrl->done = 1; } return; }
     }
     // H <- HA (already completed by assemble_kernel)
     for (int e = tid; e < nn; e += 256) H[e] = sysHA[e];
@@ -906,12 +906,12 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
             for (;;) {
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(f) : "memory");
                 if (v >= w.p2p_post_epoch) break;
-                if (++spins > (1l << 23)) { s_ok = 0; break; }
+                if (++spins > (1l << 26)) { s_ok = 0; break; }
                 __nanosleep(100);
             }
         }
         __syncthreads();
-        if (!s_ok) { if (tid == 0) { ctrl->failed = 1; ctrl->done = 1; } return; }
+        if (!s_ok) { if (tid == 0) { ctrl->failed = 1; ctrl->pad0 = 1; ctrl->done = 1; } return; }
     }
     // energy: fixed-order sum of the block partials (multi-GPU: of the ranks' sums, all-gathered by pack_post_kernel)
     double e = 0.0;

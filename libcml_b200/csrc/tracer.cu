@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <climits>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,6 +31,39 @@ using cmlba::Pose;
         }                                                                                          \
     } while (0)
 
+// Point ids are handed out once and never reused; the device arrays are indexed by SLOT.  Removed points leave dead slots behind, which
+// compact_kernel squeezes out when more than a quarter of the slots are dead (Tracer::maybe_compact), so device memory and the cost of a
+// trace pass follow the LIVE points, not every point ever created.
+__global__ void compact_kernel(const PointsDev src, const PointsDev dst, const int n_live, const int *__restrict__ perm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_live) return;
+    const int o = perm[i];
+    dst.host[i] = src.host[o]; dst.xy[i] = src.xy[o]; dst.status[i] = src.status[o];
+    dst.idmin[i] = src.idmin[o]; dst.idmax[i] = src.idmax[o]; dst.u[i] = src.u[o]; dst.v[i] = src.v[o];
+    dst.interval[i] = src.interval[o]; dst.quality[i] = src.quality[o]; dst.energyTH[i] = src.energyTH[o];
+    for (int k = 0; k < 4; k++) dst.gradH[(size_t) i * 4 + k] = src.gradH[(size_t) o * 4 + k];
+    for (int k = 0; k < 8; k++) dst.weights[(size_t) i * 8 + k] = src.weights[(size_t) o * 8 + k];
+}
+// read-back of an arbitrary list of slots (-1 = removed point) as packed cmltrc_point records + pixel: one copy instead of ten
+__global__ void gather_points_kernel(const PointsDev pts, const int n, const int *__restrict__ slot, cmltrc_point *__restrict__ out, float2 *__restrict__ xy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = slot[i];
+    cmltrc_point o;
+    memset(&o, 0, sizeof o);
+    o.host_frame_slot = -1;
+    float2 q = make_float2(0.f, 0.f);
+    if (s >= 0) {
+        o.status = pts.status[s]; o.host_frame_slot = pts.host[s]; o.idepth_min = pts.idmin[s]; o.idepth_max = pts.idmax[s];
+        o.last_trace_uv[0] = pts.u[s]; o.last_trace_uv[1] = pts.v[s]; o.last_trace_pixel_interval = pts.interval[s]; o.quality = pts.quality[s];
+        for (int k = 0; k < 4; k++) o.grad_h[k] = pts.gradH[(size_t) s * 4 + k];
+        o.energy_th = pts.energyTH[s];
+        q = pts.xy[s];
+    }
+    out[i] = o;
+    if (xy) xy[i] = q;
+}
+
 struct Tracer {
     TrcParams P{};
     int device = 0;
@@ -44,8 +79,12 @@ struct Tracer {
     char *h_pin = nullptr; size_t pin_bytes = 0;
     // points
     PointsDev pts{};
-    size_t cap = 0; int64_t num = 0;
-    std::vector<int> host_slot;        // host mirror of pts.host
+    size_t cap = 0; int64_t num = 0;   // slots in use (live + dead until the next compaction)
+    std::vector<int> host_slot;        // [num] per SLOT: host mirror of pts.host (-1 = dead)
+    int64_t next_id = 0, n_dead = 0;   // ids handed out so far (never reused); dead slots
+    std::vector<int> id2slot;          // [next_id] slot of a live point, -1 once removed
+    std::vector<int64_t> slot2id;      // [num]
+    int *d_gidx = nullptr; cmltrc_point *d_gpt = nullptr; float2 *d_gxy = nullptr; size_t g_cap = 0;   // gather scratch
     int *d_ids = nullptr; ActivateOut *d_out = nullptr; size_t act_cap = 0;
 
     ~Tracer() {
@@ -53,6 +92,7 @@ struct Tracer {
         free_points();
         if (d_frames) cudaFree(d_frames); if (d_pairs) cudaFree(d_pairs); if (d_slots) cudaFree(d_slots); if (d_counts) cudaFree(d_counts);
         if (d_ids) cudaFree(d_ids); if (d_out) cudaFree(d_out);
+        if (d_gidx) cudaFree(d_gidx); if (d_gpt) cudaFree(d_gpt); if (d_gxy) cudaFree(d_gxy);
         if (h_pin) cudaFreeHost(h_pin);
         if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -129,8 +169,67 @@ struct Tracer {
         if (s < 0) { error = "unknown frame id"; return CMLTRC_ERR_ARG; }
         slots[s].used = false;
         std::vector<int64_t> dead;
-        for (int64_t p = 0; p < num; p++) if (host_slot[p] == s) dead.push_back(p);
+        for (int64_t p = 0; p < num; p++) if (host_slot[p] == s) dead.push_back(slot2id[p]);
         return dead.empty() ? CMLTRC_OK : remove_points((int) dead.size(), dead.data());
+    }
+
+    int alloc_points(PointsDev &n, size_t ncap) {
+        RCK(cudaMalloc((void **) &n.host, ncap * 4)); RCK(cudaMalloc((void **) &n.xy, ncap * 8)); RCK(cudaMalloc((void **) &n.status, ncap * 4));
+        RCK(cudaMalloc((void **) &n.idmin, ncap * 8)); RCK(cudaMalloc((void **) &n.idmax, ncap * 8)); RCK(cudaMalloc((void **) &n.u, ncap * 8)); RCK(cudaMalloc((void **) &n.v, ncap * 8));
+        RCK(cudaMalloc((void **) &n.interval, ncap * 8)); RCK(cudaMalloc((void **) &n.quality, ncap * 8)); RCK(cudaMalloc((void **) &n.gradH, ncap * 32));
+        RCK(cudaMalloc((void **) &n.energyTH, ncap * 8)); RCK(cudaMalloc((void **) &n.weights, ncap * 32));
+        return CMLTRC_OK;
+    }
+    // squeeze the dead slots out once they are more than a quarter of the slots in use
+    int maybe_compact() {
+        if (n_dead < 1024 || n_dead * 4 <= num) return CMLTRC_OK;
+        std::vector<int> perm;
+        perm.reserve((size_t) (num - n_dead));
+        for (int64_t p = 0; p < num; p++) if (host_slot[p] >= 0) perm.push_back((int) p);
+        const int live = (int) perm.size();
+        PointsDev n{};
+        int rc = alloc_points(n, cap);
+        if (rc) return rc;
+        rc = gather_reserve((size_t) std::max(live, 1));
+        if (rc) return rc;
+        if (live) {
+            RCK(cudaMemcpyAsync(d_gidx, perm.data(), (size_t) live * 4, cudaMemcpyHostToDevice, stream));
+            compact_kernel<<<(live + 255) / 256, 256, 0, stream>>>(pts, n, live, d_gidx);
+            RCK(cudaGetLastError());
+        }
+        RCK(cudaStreamSynchronize(stream));
+        free_points();
+        pts = n;
+        std::vector<int> hs(live); std::vector<int64_t> s2i(live);
+        for (int i = 0; i < live; i++) { hs[i] = host_slot[perm[i]]; s2i[i] = slot2id[perm[i]]; id2slot[(size_t) s2i[i]] = i; }
+        host_slot.swap(hs); slot2id.swap(s2i);
+        num = live; n_dead = 0;
+        return CMLTRC_OK;
+    }
+    int gather_reserve(size_t n) {
+        if (n <= g_cap) return CMLTRC_OK;
+        if (d_gidx) cudaFree(d_gidx); if (d_gpt) cudaFree(d_gpt); if (d_gxy) cudaFree(d_gxy);
+        d_gidx = nullptr; d_gpt = nullptr; d_gxy = nullptr; g_cap = 0;
+        const size_t want = n + n / 2 + 256;
+        RCK(cudaMalloc(&d_gidx, want * 4)); RCK(cudaMalloc(&d_gpt, want * sizeof(cmltrc_point))); RCK(cudaMalloc(&d_gxy, want * sizeof(float2)));
+        g_cap = want;
+        return CMLTRC_OK;
+    }
+    // packed records (+ pixels) of the given point ids; a removed id yields host_frame_slot = -1
+    int gather(int count, const int64_t *ids, int64_t first, cmltrc_point *out, float2 *xy) {
+        if (count == 0) return CMLTRC_OK;
+        RCK(cudaSetDevice(device));
+        int rc = gather_reserve((size_t) count);
+        if (rc) return rc;
+        std::vector<int> sl(count);
+        for (int i = 0; i < count; i++) sl[i] = id2slot[(size_t) (ids ? ids[i] : first + i)];
+        RCK(cudaMemcpyAsync(d_gidx, sl.data(), (size_t) count * 4, cudaMemcpyHostToDevice, stream));
+        gather_points_kernel<<<(count + 255) / 256, 256, 0, stream>>>(pts, count, d_gidx, d_gpt, xy ? d_gxy : nullptr);
+        RCK(cudaGetLastError());
+        RCK(cudaMemcpyAsync(out, d_gpt, (size_t) count * sizeof(cmltrc_point), cudaMemcpyDeviceToHost, stream));
+        if (xy) RCK(cudaMemcpyAsync(xy, d_gxy, (size_t) count * sizeof(float2), cudaMemcpyDeviceToHost, stream));
+        RCK(cudaStreamSynchronize(stream));
+        return CMLTRC_OK;
     }
 
     int grow(size_t want) {
@@ -161,9 +260,11 @@ struct Tracer {
             if (!(x >= 3 && y >= 3 && x < P.W - 4 && y < P.H - 4)) { error = "corner too close to the image border"; return CMLTRC_ERR_ARG; }
         }
         RCK(cudaSetDevice(device));
-        int rc = grow((size_t) num + count);
+        int rc = maybe_compact();
         if (rc) return rc;
-        if (first) *first = num;
+        rc = grow((size_t) num + count);
+        if (rc) return rc;
+        if (first) *first = next_id;
         if (count == 0) return CMLTRC_OK;
         RCK(cudaMemcpyAsync(pts.xy + num, xy, (size_t) count * 8, cudaMemcpyHostToDevice, stream));
         const FrameImg img{slots[s].gray, slots[s].grad};
@@ -171,20 +272,23 @@ struct Tracer {
         RCK(cudaGetLastError());
         RCK(cudaStreamSynchronize(stream));
         host_slot.resize((size_t) num + count, s);
-        num += count;
+        for (int i = 0; i < count; i++) { id2slot.push_back((int) num + i); slot2id.push_back(next_id + i); }
+        num += count; next_id += count;
         return CMLTRC_OK;
     }
 
     int remove_points(int count, const int64_t *ids) {
         if (count < 0 || (count > 0 && !ids)) { error = "bad arguments"; return CMLTRC_ERR_ARG; }
+        for (int i = 0; i < count; i++) if (ids[i] < 0 || ids[i] >= next_id) { error = "unknown point id"; return CMLTRC_ERR_ARG; }     // validate everything before anything changes
         RCK(cudaSetDevice(device));
-        bool any = false;
+        int lo = INT32_MAX, hi = -1;
         for (int i = 0; i < count; i++) {
-            if (ids[i] < 0 || ids[i] >= num) { error = "unknown point id"; return CMLTRC_ERR_ARG; }
-            if (host_slot[ids[i]] < 0) continue;
-            host_slot[ids[i]] = -1; any = true;
+            const int sl = id2slot[(size_t) ids[i]];
+            if (sl < 0) continue;                      // already removed
+            host_slot[sl] = -1; id2slot[(size_t) ids[i]] = -1; n_dead++;
+            lo = std::min(lo, sl); hi = std::max(hi, sl);
         }
-        if (any) RCK(cudaMemcpyAsync(pts.host, host_slot.data(), (size_t) num * sizeof(int), cudaMemcpyHostToDevice, stream));     // one copy of the mirror, not one per point
+        if (hi >= 0) RCK(cudaMemcpyAsync(pts.host + lo, host_slot.data() + lo, (size_t) (hi - lo + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));     // the changed range of the mirror
         RCK(cudaStreamSynchronize(stream));
         return CMLTRC_OK;
     }
@@ -231,8 +335,8 @@ struct Tracer {
         RCK(cudaSetDevice(device));
         std::vector<int> id32(count);
         for (int i = 0; i < count; i++) {
-            if (ids[i] < 0 || ids[i] >= num || host_slot[ids[i]] < 0) { error = "unknown or removed point id"; return CMLTRC_ERR_ARG; }
-            id32[i] = (int) ids[i];
+            if (ids[i] < 0 || ids[i] >= next_id || id2slot[(size_t) ids[i]] < 0) { error = "unknown or removed point id"; return CMLTRC_ERR_ARG; }
+            id32[i] = id2slot[(size_t) ids[i]];
         }
         // window order: newest frame first (OrderedSet<PFrame, Comparator> orders by descending id)
         std::vector<int> order;
@@ -292,7 +396,7 @@ struct Tracer {
         if (last < 0 || nact < 0 || nim < 0 || (nact > 0 && !axy) || (nim > 0 && !ids) || !n_act || !n_rem || capacity < 0 || (capacity > 0 && (!act_ids || !act || !rem_ids))) {
             error = "unknown frame id or bad arguments"; return CMLTRC_ERR_ARG;
         }
-        for (int i = 0; i < nim; i++) if (ids[i] < 0 || ids[i] >= num || host_slot[ids[i]] < 0) { error = "unknown or removed point id"; return CMLTRC_ERR_ARG; }
+        for (int i = 0; i < nim; i++) if (ids[i] < 0 || ids[i] >= next_id || id2slot[(size_t) ids[i]] < 0) { error = "unknown or removed point id"; return CMLTRC_ERR_ARG; }
         cmltrc_activate_stats s{};
         // minimum-distance adaptation (DSOTracer.cpp:62-85)
         double md = min_distance;
@@ -310,15 +414,15 @@ struct Tracer {
         const float maxType = 10;
         ChebGrid dmap(P.W, P.H, (int) (md * maxType));
         for (int i = 0; i < nact; i++) dmap.add(axy[2 * i], axy[2 * i + 1]);
-        // point states (one read-back), then the sequential gating in the caller's order
-        std::vector<cmltrc_point> pt((size_t) num);
-        if (num) { int rc = get_points(0, (int) num, pt.data()); if (rc) return rc; }
-        std::vector<float2> pxy((size_t) num);
-        if (num && cudaMemcpy(pxy.data(), pts.xy, (size_t) num * sizeof(float2), cudaMemcpyDeviceToHost) != cudaSuccess) { error = "device read failed"; return CMLTRC_ERR_CUDA; }
+        // states of the candidates only (one gathered read-back), then the sequential gating in the caller's order
+        std::vector<cmltrc_point> pt((size_t) nim);
+        std::vector<float2> pxy((size_t) nim);
+        if (nim) { int rc = gather(nim, ids, 0, pt.data(), pxy.data()); if (rc) return rc; }
         std::vector<int64_t> to_opt, removed;
+        std::vector<int> to_opt_k;
         for (int i = 0; i < nim; i++) {
             const int64_t id = ids[i];
-            const cmltrc_point &p = pt[id];
+            const cmltrc_point &p = pt[i];
             if (p.host_frame_slot == last) continue;
             if (!std::isfinite(p.idepth_max) || p.status == IPS_OUTLIER) { removed.push_back(id); s.num_deleted_outlier++; continue; }
             const bool okStatus = p.status == IPS_GOOD || p.status == IPS_SKIPPED || p.status == IPS_BADCONDITION || p.status == IPS_OOB;
@@ -335,7 +439,7 @@ struct Tracer {
             const double idepth = (p.idepth_min + p.idepth_max) / 2.0;
             const Slot &hs = slots[p.host_frame_slot];
             const Pose rel = cmlba::pose_mul(slots[last].cam, cmlba::pose_inv(hs.cam));
-            const float2 xy = pxy[id];
+            const float2 xy = pxy[i];
             const double ray[3] = {((double) xy.x - P.cx) / P.fx / idepth, ((double) xy.y - P.cy) / P.fy / idepth, 1.0 / idepth};
             double X[3];
             cmlba::mat3_vec(rel.R, ray, X);
@@ -343,7 +447,7 @@ struct Tracer {
             const double px = P.fx * (X[0] / X[2]) + P.cx, py = P.fy * (X[1] / X[2]) + P.cy;
             if (px >= 0 && py >= 0 && px < P.W && py < P.H) {
                 const double dist = dmap.get(px, py) + (px - std::floor(px));
-                if (dist >= md * (double) (types ? types[i] : 1.f)) { dmap.add(px, py); to_opt.push_back(id); }
+                if (dist >= md * (double) (types ? types[i] : 1.f)) { dmap.add(px, py); to_opt.push_back(id); to_opt_k.push_back(i); }
             } else removed.push_back(id);
         }
         s.num_to_optimize = (int) to_opt.size();
@@ -355,7 +459,7 @@ struct Tracer {
             if (res[k].rc == 1) {
                 if (na < capacity) { act_ids[na] = to_opt[k]; act[na] = res[k]; }
                 na++; s.num_mapped++; gone.push_back(to_opt[k]);
-            } else if (res[k].rc == -1 || pt[to_opt[k]].status == IPS_OOB) { removed.push_back(to_opt[k]); s.num_dropped++; }
+            } else if (res[k].rc == -1 || pt[to_opt_k[k]].status == IPS_OOB) { removed.push_back(to_opt[k]); s.num_dropped++; }
             else s.num_non_mapped++;
         }
         for (size_t k = 0; k < removed.size() && (int) k < capacity; k++) rem_ids[k] = removed[k];
@@ -367,28 +471,8 @@ struct Tracer {
     }
 
     int get_points(int64_t first, int count, cmltrc_point *out) {
-        if (first < 0 || count < 0 || first + count > num || (count > 0 && !out)) { error = "bad range"; return CMLTRC_ERR_ARG; }
-        if (count == 0) return CMLTRC_OK;
-        RCK(cudaSetDevice(device));
-        RCK(cudaStreamSynchronize(stream));
-        std::vector<int> st(count), hs(count);
-        std::vector<double> a(count), b(count), u(count), v(count), iv(count), q(count), g((size_t) count * 4), e(count);
-        RCK(cudaMemcpy(st.data(), pts.status + first, (size_t) count * 4, cudaMemcpyDeviceToHost));
-        RCK(cudaMemcpy(hs.data(), pts.host + first, (size_t) count * 4, cudaMemcpyDeviceToHost));
-        RCK(cudaMemcpy(a.data(), pts.idmin + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
-        RCK(cudaMemcpy(b.data(), pts.idmax + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
-        RCK(cudaMemcpy(u.data(), pts.u + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
-        RCK(cudaMemcpy(v.data(), pts.v + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
-        RCK(cudaMemcpy(iv.data(), pts.interval + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
-        RCK(cudaMemcpy(q.data(), pts.quality + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
-        RCK(cudaMemcpy(g.data(), pts.gradH + first * 4, (size_t) count * 32, cudaMemcpyDeviceToHost));
-        RCK(cudaMemcpy(e.data(), pts.energyTH + first, (size_t) count * 8, cudaMemcpyDeviceToHost));
-        for (int i = 0; i < count; i++) {
-            cmltrc_point &o = out[i];
-            o.status = st[i]; o.host_frame_slot = hs[i]; o.idepth_min = a[i]; o.idepth_max = b[i]; o.last_trace_uv[0] = u[i]; o.last_trace_uv[1] = v[i];
-            o.last_trace_pixel_interval = iv[i]; o.quality = q[i]; memcpy(o.grad_h, &g[(size_t) i * 4], 32); o.energy_th = e[i];
-        }
-        return CMLTRC_OK;
+        if (first < 0 || count < 0 || first + count > next_id || (count > 0 && !out)) { error = "bad range"; return CMLTRC_ERR_ARG; }
+        return gather(count, nullptr, first, out, nullptr);
     }
 };
 
@@ -428,7 +512,7 @@ int cmltrc_set_frame_pose(cmltrc_handle h, int64_t id, const double cam[12], con
 int cmltrc_remove_frame(cmltrc_handle h, int64_t id) { return h ? TH(h)->remove_frame(id) : CMLTRC_ERR_ARG; }
 int cmltrc_make_new_traces(cmltrc_handle h, int64_t id, int count, const float *xy, int64_t *first_id) { return h ? TH(h)->make_new_traces(id, count, xy, first_id) : CMLTRC_ERR_ARG; }
 int cmltrc_remove_points(cmltrc_handle h, int count, const int64_t *ids) { return h ? TH(h)->remove_points(count, ids) : CMLTRC_ERR_ARG; }
-int64_t cmltrc_num_points(cmltrc_handle h) { return h ? TH(h)->num : CMLTRC_ERR_ARG; }
+int64_t cmltrc_num_points(cmltrc_handle h) { return h ? TH(h)->next_id : CMLTRC_ERR_ARG; }
 int cmltrc_trace_new_coarse(cmltrc_handle h, int64_t id, int32_t *hist, float *gpu_ms) { return h ? TH(h)->trace(id, hist, gpu_ms) : CMLTRC_ERR_ARG; }
 int cmltrc_optimize_immature(cmltrc_handle h, int count, const int64_t *ids, int min_obs, cmltrc_activation *results, float *gpu_ms) {
     return h ? TH(h)->activate(count, ids, min_obs, results, gpu_ms) : CMLTRC_ERR_ARG;

@@ -208,3 +208,42 @@ def test_non_default_parameters_against_oracle():
                 r = trc.optimizeImmaturePoint([ids[h][k]])[0]
                 assert r["rc"] == rc and (rc != 1 or abs(r["idepth"] - idp) <= 1e-4 * idp)
     assert len(seen) >= 3
+
+
+def test_dead_slots_are_compacted_and_ids_stay_stable():
+    """Removed points leave dead device slots; once more than a quarter of the slots is dead the next makeNewTracesFrom squeezes them out.
+    Ids are never reused and keep addressing the same points: the records of the survivors are bit-identical before and after the
+    compaction, removed ids read back as host_frame_slot = -1, and a trace pass after the compaction equals the one of an un-compacted handle."""
+    from libcml_b200 import DSOTracer
+    win, _ = load()
+    H, W = win["gray"].shape[1:]
+    rng = np.random.default_rng(7)
+    xy = np.stack([rng.uniform(8, W - 9, 6000), rng.uniform(8, H - 9, 6000)], axis=1).astype(np.float32)
+
+    def make():
+        t = DSOTracer(W, H, win["calib"])
+        t.addFrame(0, win["gray"][0], win["frame_cam"][0], exposure(win, 0))
+        i = t.makeNewTracesFrom(0, xy)
+        t.addFrame(1, win["gray"][1], win["frame_cam"][1], exposure(win, 1))
+        t.traceNewCoarse(1)
+        return t, i
+    trc, ids = make()
+    ref, ids_ref = make()
+    before = trc.getPoints()
+    gone = ids[::2]                                             # half of the points: far above the 25 % threshold
+    trc.removePoints(gone); ref.removePoints(gone[:100])        # the reference handle stays below the threshold (no compaction)
+    ref.removePoints(gone[100:1000])
+    extra = trc.makeNewTracesFrom(1, xy[:10])                   # triggers the compaction
+    assert extra[0] == 6000 and trc.numPoints() == 6010         # ids are not reused
+    after = trc.getPoints()
+    keep = ids[1::2]
+    for k in before.dtype.names:
+        assert np.array_equal(before[k][keep], after[k][keep], equal_nan=True), k
+    assert (after["host_frame_slot"][gone] == -1).all()
+    trc.addFrame(2, win["gray"][2], win["frame_cam"][2], exposure(win, 2)); ref.addFrame(2, win["gray"][2], win["frame_cam"][2], exposure(win, 2))
+    trc.traceNewCoarse(2); ref.traceNewCoarse(2)
+    a, b = trc.getPoints(), ref.getPoints()
+    for k in a.dtype.names:
+        assert np.array_equal(a[k][keep], b[k][keep], equal_nan=True), k
+    with pytest.raises(Exception):
+        trc.optimizeImmaturePoint(gone[:1])                      # a removed id stays removed
