@@ -262,8 +262,42 @@ def select():
     print("select window", os.path.getsize(os.path.join(OUT, "select_window.cmlw")) // 1024, "KB  golden", os.path.getsize(os.path.join(OUT, "select_golden.cmlw")) // 1024, "KB", pots)
 
 
+def full_size_summaries():
+    """Compact summaries of the reference's run() at BASELINE.json's full sizes (c1..c4): final poses, affine, summed residual energy, accepted-step count,
+    every 16th inverse depth and a digest of the surviving (point, target) residual set.  The windows are regenerated from libcml_b200.synth
+    (seeded), so only the summary travels; tests/test_gpu_parity.py::test_against_reference_summary_full_size reads it on the GPU box.
+        python oracle/make_golden.py summaries"""
+    import hashlib
+    tmp = "/tmp/cmlba_golden"
+    os.makedirs(tmp, exist_ok=True)
+    out = {}
+    for cfg in ("c1", "c2", "c3", "c4"):
+        win = synth.make_config(cfg, with_gradients=False)
+        wp = os.path.join(tmp, f"{cfg}.cmlw"); op = os.path.join(tmp, f"{cfg}_run.cmlw")
+        cmlw.save(wp, {k: v for k, v in win.items() if k != "grad"})
+        run_ref(wp, "run", op)
+        g = cmlw.load(op)
+        key = np.sort(g["fin_alive_res_point"].astype(np.int64) * 64 + g["fin_alive_res_target"].astype(np.int64))
+        out[f"{cfg}_ok"] = g["fin_ok"]
+        out[f"{cfg}_w2c"] = g["fin_frame_pre_w2c"]
+        out[f"{cfg}_affine"] = g["fin_frame_affine"]
+        out[f"{cfg}_energy"] = np.array([g["fin_alive_res_energy"].sum()])
+        out[f"{cfg}_accepted"] = g["accepted_count"]
+        out[f"{cfg}_idepth16"] = g["fin_pt_idepth"][::16].copy()
+        out[f"{cfg}_alive16"] = g["fin_pt_alive"][::16].astype(np.uint8)
+        out[f"{cfg}_n_alive_res"] = np.array([key.size], np.int64)
+        out[f"{cfg}_n_alive_pts"] = np.array([int(g["fin_pt_alive"].sum())], np.int64)
+        out[f"{cfg}_res_digest"] = np.frombuffer(hashlib.sha1(key.tobytes()).digest(), dtype=np.uint8).copy()
+        out[f"{cfg}_res_per_target"] = np.bincount(g["fin_alive_res_target"].astype(np.int64), minlength=win["frame_cam"].shape[0]).astype(np.int64)
+        print(cfg, "accepted", int(g["accepted_count"][0]), "alive residuals", key.size, "energy", out[f"{cfg}_energy"])
+    cmlw.save(os.path.join(OUT, "fullsize_summary.cmlw"), out)
+    print("fullsize_summary.cmlw", os.path.getsize(os.path.join(OUT, "fullsize_summary.cmlw")) // 1024, "KB")
+
+
 if __name__ == "__main__":
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    if len(sys.argv) > 1 and sys.argv[1] == "summaries":
+        full_size_summaries(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "select":
         select(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fast":

@@ -30,6 +30,42 @@ def rel(a, b, floor=1e-30):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), floor))
 
 
+def record(test, **vals):
+    """Append the MEASURED errors of a parity check to gpurun_out/parity_report.jsonl (copied to profiles/ per round),
+    so the asserted gates can be read next to what the kernels actually achieve."""
+    import json
+    try:
+        d = os.path.join(ROOT, "gpurun_out"); os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps({"test": test, **{k: (float(v) if np.ndim(v) == 0 else np.asarray(v).tolist()) for k, v in vals.items()}}) + "\n")
+    except OSError:
+        pass
+
+
+def pose_errors(w2c, w2c_ref):
+    """(rotation error [absolute, max entry of R - R_ref], translation error RELATIVE to the largest ||t_ref|| of the window).
+    A pose row is 9 rotation entries (row major) followed by the translation."""
+    a = np.asarray(w2c, np.float64).reshape(-1, 12); b = np.asarray(w2c_ref, np.float64).reshape(-1, 12)
+    tn = max(float(np.linalg.norm(b[:, 9:], axis=1).max()), 1e-30)
+    return float(np.abs(a[:, :9] - b[:, :9]).max()), float(np.linalg.norm(a[:, 9:] - b[:, 9:], axis=1).max() / tn)
+
+
+def x_noise_floor(gold, pre, N, eps=float(np.finfo(np.float32).eps), trials=16, seed=0):
+    """Forward-error floor of the reference's own Gauss-Newton step: its H is accumulated in fp32 (AccumulatorApprox), so
+    every entry carries >= 1 ulp of noise.  Returns (rel. change of x when the reference solves the upper instead of the lower
+    triangle of ITS matrix, median rel. change of x under an fp32-ulp relative perturbation of H, cond(H))."""
+    H, b = solve_reference_system(gold, pre, N)
+    Hs = H[4:, 4:]; bs = b[4:]
+    lo = np.tril(Hs) + np.tril(Hs, -1).T; up = np.triu(Hs) + np.triu(Hs, 1).T
+    xl = np.linalg.solve(lo, bs)
+    rng = np.random.default_rng(seed)
+    fl = []
+    for _ in range(trials):
+        P = np.tril(lo * (1 + eps * rng.standard_normal(lo.shape)))
+        fl.append(rel(np.linalg.solve(P + np.tril(P, -1).T, bs), xl))
+    return rel(np.linalg.solve(up, bs), xl), float(np.median(fl)), float(np.linalg.cond(lo))
+
+
 def res_key(point, target):
     return np.asarray(point, np.int64) * 64 + np.asarray(target, np.int64)
 

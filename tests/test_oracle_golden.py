@@ -153,3 +153,15 @@ def test_marginalisation_prior_restatement_matches_reference():
     assert np.linalg.norm(dH - g["m2_HM"]) / np.linalg.norm(g["m2_HM"]) < 1e-5
     # b_M cancels heavily near convergence (J^T resF against J^T J delta): 1e-6 state differences after three runs show up at ~1e-3
     assert np.linalg.norm(db.ravel() - g["m2_bM"][:, 0]) / np.linalg.norm(g["m2_bM"]) < 3e-3
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_affine"])
+def test_forward_error_floor_of_the_reference_system(name):
+    """The experiment behind the x gate of tests/test_gpu_parity.py: the reference's own Gauss-Newton system is conditioned at ~1e11, so
+    solving the UPPER instead of the lower triangle of ITS H (they differ by 1e-13 relative), or one fp32 ulp of noise on the entries (the
+    reference accumulates H in fp32), moves x by ~1e-3.  A forward gate on x below that floor would test the noise, not the kernels."""
+    from parity_util import load_golden, x_noise_floor
+    win, g = load_golden(name)
+    tri, ulp, cond = x_noise_floor(g, "sol0_", win["frame_evalpt"].shape[0])
+    assert cond > 1e10
+    assert 2e-4 < tri < 5e-3 and 2e-4 < ulp < 1e-2
