@@ -360,9 +360,10 @@ def main():
            "notes": {"residuals_per_gpu": R, "residuals_all_gpus": R_all, "l2": "flushed between timed passes (384 MB write outside the timed region)",
                      "parallelism": f"points sharded x{world}, frames replicated" + ("" if world == 1 else (", reduced system + post-linearize records over NVLink peer memory (cudaIpc)" if getattr(ba, "peer_memory", False) else ", reduced system by ncclAllReduce, post-linearize records by ncclAllGather"))},
            "ms_per_step_l2_warm": ms_pass_warm, "value_l2_warm": world * R / (ms_pass_warm * 1e-3),
-           "kernel_ms": {"linearize": br.ms_linearize, "accumulate_schur": br.ms_schur, "stitch_assemble": br.ms_stitch,
-                         "linearize_l2_warm": brw.ms_linearize, "event_overhead_per_interval": br.ms_accumulate,
-                         "note": "event-to-event intervals of a separate loop; each includes one event-record overhead"},
+           "kernel_ms": {"linearize": br.ms_linearize, "accumulate": br.ms_accumulate, "schur": br.ms_schur, "stitch": br.ms_stitch, "assemble": br.ms_assemble,
+                         "linearize_l2_warm": brw.ms_linearize, "event_overhead_per_interval": br.ms_event_overhead,
+                         "note": "event-to-event intervals of a separate loop with the kernels serialised on one stream; each includes one event-record overhead. "
+                                 "In the timed pass accumulate runs on a side stream concurrently with schur"},
            "run": {"gpu_ms": run_gpu_ms, "kernel_launches": run_launches, "iterations": e2e_iters},
            "roofline": {"bound": "hbm", "kernel": "linearize_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_unit": b_alg(N), "units_per_launch": R},

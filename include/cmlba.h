@@ -193,8 +193,11 @@ int cmlba_reset(cmlba_handle *h);
 typedef struct cmlba_bench_result {
     int steps, residuals, points, frames, launches_per_pass;
     double ms_pass;         /* mean duration of one whole pass */
-    double ms_linearize, ms_accumulate, ms_schur, ms_stitch;   /* mean event-to-event intervals of a separate loop: linearize+accumulate (fused),
-                                                                * an EMPTY interval (= the event overhead every interval carries), Schur, stitch+assemble */
+    double ms_linearize, ms_accumulate, ms_schur, ms_stitch;   /* mean event-to-event intervals of a separate loop in which the kernels of the pass
+                                                                * run serialised on one stream: linearize_tile_kernel, accumulate_kernel, schur_kernel,
+                                                                * stitch_pair_kernel */
+    double ms_assemble;        /* ... assemble_kernel */
+    double ms_event_overhead;  /* ... an EMPTY interval: the event-record overhead every interval above carries */
 } cmlba_bench_result;
 int cmlba_bench_pass(cmlba_handle *h, int steps, int warmup, int flush_l2, cmlba_bench_result *out);
 

@@ -39,7 +39,8 @@ class RunResult(C.Structure):
 
 class BenchResult(C.Structure):
     _fields_ = [("steps", C.c_int), ("residuals", C.c_int), ("points", C.c_int), ("frames", C.c_int), ("launches_per_pass", C.c_int),
-                ("ms_pass", C.c_double), ("ms_linearize", C.c_double), ("ms_accumulate", C.c_double), ("ms_schur", C.c_double), ("ms_stitch", C.c_double)]
+                ("ms_pass", C.c_double), ("ms_linearize", C.c_double), ("ms_accumulate", C.c_double), ("ms_schur", C.c_double), ("ms_stitch", C.c_double),
+                ("ms_assemble", C.c_double), ("ms_event_overhead", C.c_double)]
 
 
 # every symbol include/cmlba.h declares (tests/test_abi.py checks the .so exports all of them)

@@ -115,8 +115,10 @@ struct DevWin {
     int n_chunks;                  // ceil(R / 32) warp passes of linearize_tile_kernel
     int tma_on;                    // tensor maps encoded: tiles are staged by TMA (else every tap is read from global memory)
     int lt_grid;                   // CTAs of linearize_tile_kernel (cta_info is laid out for this grid)
-    int *cta_info;                 // [lt_grid][16] q0, q1, first target, -, descriptors[4], users[4] of the first tiles
+    float4 *r_pt4;                 // [5][R] per-residual copies of the point constants in the sorted order: (x, y, -, -), colours[0..3], [4..7], weights[0..3], [4..7]
+    int *cta_info;                 // [lt_grid][LT_INFO_INTS] q0, q1, first target, -, descriptors[4], users[4] of the first tiles, tile table (linearize.cuh)
     long long *lt_trace;           // development (lt_mode & 2): [lt_grid][16 warps][32] SM clock stamps of the first passes
+    unsigned long long *ktrace;    // development (CMLBA_KTRACE): [kernel][3] globaltimer of first CTA scheduled / first CTA past its dependency wait / last warp done
     int lt_mode;                   // development: 1 = the consumers only run the ring protocol (TMA streaming floor of the pass)
     int lt_exact;                  // 1 = every pattern pixel is projected in fp64 like the reference (parity study; default: fp32 offsets from the fp64 centre)
     int *bin_key;                  // [R] host order: ((t * n_tiles + tile) * N + h)

@@ -226,7 +226,7 @@ public:
     bool subset_to_marginalize = false;   // build_device_window keeps only the points marked DSOTOMARGINALIZE (marginalize_points)
     // device-window layout (host mirrors)
     std::vector<int> pt_order;    // device point i -> points_ index
-    DevWin dw;
+    DevWin dw = {};
     int launches = 0;
     // multi-GPU
     void *comm = nullptr; int rank = 0, world = 1;
@@ -246,7 +246,10 @@ public:
     DevBuf<uint32_t> d_job_desc, d_r_pht;
     DevBuf<uint8_t> d_fin_state, d_fin_alive;
     DevBuf<float> d_fin_energy;
+    DevBuf<float4> d_r_pt4;
     DevBuf<long long> d_lt_trace;
+    DevBuf<unsigned long long> d_ktrace;   // development timeline (CMLBA_KTRACE=1)
+    bool want_ktrace = false;
     TileMaps tile_maps;           // one tensor map per window frame (re-encoded by build_device_window)
     int n_sm = 148;
     int lt_variant = 0, lt_mode = 0, lt_exact = 0;
@@ -258,6 +261,11 @@ public:
         d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj0, d_rj1, d_T0, d_T1, d_dbg, d_acc_bin, d_sc_part, d_stage[MAXF];
     int stage_flip = 0;
     cudaEvent_t ev_copy = nullptr;
+    // accumulate_kernel (Jacobian records -> 13x13 blocks) and schur_kernel (Schur rows -> per-chunk blocks) are independent consumers of one
+    // linearization: the first runs on a side stream forked off / joined back into the main one (CMLBA_NO_FORK=1 serialises them)
+    cudaStream_t side_stream = nullptr, launch_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool use_fork = true;
     UploadArena up;                               // every array build_device_window uploads
     UploadArena prep;                             // per-run constants uploaded by prepare()
     std::vector<int> res_bin_begin;               // [N*N+1] first device residual of every bin (t*N+h)
@@ -282,11 +290,16 @@ public:
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        launch_stream = stream;
+        if (getenv("CMLBA_NO_FORK")) use_fork = false;
+        if (getenv("CMLBA_KTRACE")) want_ktrace = true;
         CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
 #define LT_ATTR(CW, ST)                                                                                                                                  \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<false, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min<size_t>(lt_smem_bytes(MAXF, CW, ST), 227 * 1024))); \
     CK(cudaFuncSetAttribute(linearize_tile_kernel<true, CW, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::min<size_t>(lt_smem_bytes(MAXF, CW, ST), 227 * 1024)));
-        LT_ATTR(12, 4) LT_ATTR(8, 4) LT_ATTR(16, 4) LT_ATTR(12, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
+        LT_ATTR(12, 4) LT_ATTR(8, 4) LT_ATTR(16, 3) LT_ATTR(12, 3)   // warps are allocated in groups of four: 8 / 12 / 16 warps per CTA incl. the producer
 #undef LT_ATTR
         // fused tail (tail.cuh): one cluster per host frame, one CTA per frame -> clusters of 8 (portable) or 16 (opt-in) CTAs
         if (getenv("CMLBA_TAIL_FUSION") && cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tail_smem_bytes(MAXF)) == cudaSuccess) {
@@ -321,6 +334,9 @@ public:
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_copy) cudaEventDestroy(ev_copy);
+        if (side_stream) cudaStreamDestroy(side_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         up.h.release(); up.d.release(); prep.h.release(); prep.d.release(); fin_h.release(); peek_h.release();
         for (int q = 0; q < MAXF; q++) if (p2p_peer[q] && p2p_peer[q] != p2p_local) cudaIpcCloseMemHandle(p2p_peer[q]);
         if (p2p_local) cudaFree(p2p_local);
@@ -332,7 +348,7 @@ public:
         DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_res_bin_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin,
                              &d_bin_key, &d_bin_hist, &d_bin_offs, &d_job_of_tile, &d_r_job, &d_r_src, &d_bin_ticket, &d_job_begin, &d_cta_info};
         for (auto *b : di) b->release();
-        d_job_desc.release(); d_r_pht.release(); d_fin_state.release(); d_fin_alive.release(); d_fin_energy.release();
+        d_job_desc.release(); d_r_pht.release(); d_r_pt4.release(); d_ktrace.release(); d_fin_state.release(); d_fin_alive.release(); d_fin_energy.release();
         DevBuf<float> *df[] = {&d_pt_x, &d_pt_y, &d_pt_idz, &d_pt_idb, &d_pt_colors, &d_pt_weights, &d_pt_priorF, &d_pt_Hdd, &d_pt_bd, &d_pt_Hcd, &d_pt_HdiF, &d_pt_bdSumF, &d_pt_idh, &d_pt_mrb,
                                &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj0, &d_rj1, &d_T0, &d_T1, &d_dbg, &d_acc_bin, &d_sc_part};
         for (auto *b : df) b->release();
@@ -839,8 +855,8 @@ public:
         if (want_dbg) CK(d_dbg.reserve(Rz * DBG_STRIDE));
         CK(d_energy_part.reserve(std::max(n_chunks, 1)));
         CK(d_acc_bin.reserve((size_t) N * N * ACC_SLICES * ACC_N));
-        CK(d_bin_key.reserve(Rz)); CK(d_bin_hist.reserve(n_keys)); CK(d_bin_offs.reserve(n_keys)); CK(d_job_of_tile.reserve((size_t) N * n_tiles)); CK(d_job_desc.reserve((size_t) N * n_tiles)); CK(d_job_begin.reserve((size_t) N * n_tiles + 1)); CK(d_cta_info.reserve((size_t) 16 * 1024));
-        CK(d_r_pht.reserve(Rz)); CK(d_r_job.reserve(Rz)); CK(d_r_src.reserve(Rz));
+        CK(d_bin_key.reserve(Rz)); CK(d_bin_hist.reserve(n_keys)); CK(d_bin_offs.reserve(n_keys)); CK(d_job_of_tile.reserve((size_t) N * n_tiles)); CK(d_job_desc.reserve((size_t) N * n_tiles)); CK(d_job_begin.reserve((size_t) N * n_tiles + 1)); CK(d_cta_info.reserve((size_t) LT_INFO_INTS * 1024));
+        CK(d_r_pht.reserve(Rz)); CK(d_r_job.reserve(Rz)); CK(d_r_src.reserve(Rz)); CK(d_r_pt4.reserve(Rz * 5));
         CK(d_fin_state.reserve(Rz)); CK(d_fin_alive.reserve(Rz)); CK(d_fin_energy.reserve(Rz));
         if (!d_bin_ticket.p) { CK(d_bin_ticket.reserve(2)); CK(cudaMemsetAsync(d_bin_ticket.p, 0, 2 * sizeof(int), stream)); }
         CK(d_sc_part.reserve((size_t) std::max(n_sc_chunks, 1) * sc_stride));
@@ -875,7 +891,7 @@ public:
         w.pt_Hdd = d_pt_Hdd.p; w.pt_bd = d_pt_bd.p; w.pt_Hcd = d_pt_Hcd.p; w.pt_HdiF = d_pt_HdiF.p; w.pt_bdSumF = d_pt_bdSumF.p; w.pt_idepth_hessian = d_pt_idh.p; w.pt_max_rel_bs = d_pt_mrb.p;
         w.pt_num_good = d_pt_num_good.p; w.pt_ngood_cur = d_pt_ngood_cur.p; w.pt_step = d_pt_step.p;
         w.r_point = d_r_point.p; w.r_host = d_r_host.p; w.r_target = d_r_target.p; w.res_bin_begin = d_res_bin_begin.p;
-        w.bin_key = d_bin_key.p; w.bin_hist = d_bin_hist.p; w.bin_offs = d_bin_offs.p; w.job_of_tile = d_job_of_tile.p; w.job_desc = d_job_desc.p; w.job_begin = d_job_begin.p; w.cta_info = d_cta_info.p; w.lt_grid = std::max(1, std::min(std::min(n_sm, 1024), n_chunks));
+        w.bin_key = d_bin_key.p; w.bin_hist = d_bin_hist.p; w.bin_offs = d_bin_offs.p; w.job_of_tile = d_job_of_tile.p; w.job_desc = d_job_desc.p; w.job_begin = d_job_begin.p; w.cta_info = d_cta_info.p; w.r_pt4 = d_r_pt4.p; w.lt_grid = std::max(1, std::min(std::min(n_sm, 1024), n_chunks));
         w.r_pht = d_r_pht.p; w.r_job = d_r_job.p; w.r_src = d_r_src.p;
         w.bin_ticket = d_bin_ticket.p; w.fin_state = d_fin_state.p; w.fin_alive = d_fin_alive.p; w.fin_energy = d_fin_energy.p;
         w.tma_on = encode_tile_maps() ? 1 : 0;
@@ -1097,6 +1113,7 @@ public:
             CK(cudaMemsetAsync(d_bin_hist.p, 0, (size_t) N * dw.n_tiles * N * sizeof(int), stream));
             bin_count_kernel<<<(dw.R + 255) / 256, 256, 0, stream>>>(dw); launches++;
             bin_scatter_kernel<<<N * N, 256, (size_t) 8 * dw.n_tiles * sizeof(int), stream>>>(dw); launches++;
+            bin_pack_kernel<<<(dw.R + 255) / 256, 256, 0, stream>>>(dw); launches++;
             bin_finish_kernel<<<1, 256, 0, stream>>>(dw); launches++;
         }
         CK(cudaGetLastError());
@@ -1106,7 +1123,7 @@ public:
     }
 
     // ------------------------------------------------------------------ kernel sequences
-    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128); }
+    size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128 + N * 64); }
     size_t solve_smem() const { const int n = dw.n; return sizeof(double) * ((size_t) n * n + 4 * n + 256); }
     size_t schur_smem() const { return schur_smem_bytes(dw.N); }
 
@@ -1115,7 +1132,7 @@ public:
     template <typename... KArgs, typename... Args>
     void launch_pdl(int site, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = stream;
+        lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = launch_stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = (use_pdl && (pdl_mask & site)) ? 1 : 0;
         lc.attrs = at; lc.numAttrs = 1;
@@ -1135,7 +1152,7 @@ public:
     } while (0)
         switch (lt_variant) {
             case 1: LT_LAUNCH(8, 4); break;
-            case 2: LT_LAUNCH(16, 4); break;
+            case 2: LT_LAUNCH(16, 3); break;
             case 3: LT_LAUNCH(12, 3); break;
             default: if (lt_smem_bytes(dw.N, 12, 4) <= (size_t) 227 * 1024) LT_LAUNCH(12, 4); else LT_LAUNCH(12, 3); break;
         }
@@ -1155,10 +1172,22 @@ public:
         }
         launch_pdl(2, post_linearize_kernel, dim3(1), dim3(1024), 0, dw, mode, respect_done);
     }
-    void launch_schur(int respect_done) {
-        // addToHessianTop from the Jacobian records ((bin, slice) jobs), then the Schur chunks
+    void launch_accumulate(int respect_done) {
         if (dw.R > 0) launch_pdl(4, accumulate_kernel, dim3(dw.N * dw.N * ACC_SLICES), dim3(32), 0, dw, respect_done);
+    }
+    void launch_schur_only(int respect_done) {
         if (dw.n_sc_chunks > 0) launch_pdl(8, schur_kernel, dim3(dw.n_sc_chunks), dim3(256), schur_smem(), dw, respect_done);
+    }
+    void launch_schur(int respect_done) {
+        // addToHessianTop from the Jacobian records ((bin, slice) jobs) on the side stream, the Schur chunks on the main one
+        const bool fork = use_fork && dw.R > 0 && dw.n_sc_chunks > 0;
+        if (fork) {
+            if (cudaEventRecord(ev_fork, stream) != cudaSuccess || cudaStreamWaitEvent(side_stream, ev_fork, 0) != cudaSuccess) { set_error("fork failed"); launch_rc = CMLBA_ERR_CUDA; }
+            launch_stream = side_stream; launch_accumulate(respect_done); launch_stream = stream;
+            if (cudaEventRecord(ev_join, side_stream) != cudaSuccess) { set_error("fork failed"); launch_rc = CMLBA_ERR_CUDA; }
+            launch_schur_only(respect_done);
+            if (cudaStreamWaitEvent(stream, ev_join, 0) != cudaSuccess) { set_error("join failed"); launch_rc = CMLBA_ERR_CUDA; }
+        } else { launch_accumulate(respect_done); launch_schur_only(respect_done); }
     }
     // Schur complement + stitching + assembly of sys = [HA | bA | H_sc | b_sc]: one cluster kernel when a cluster of >= N CTAs is available
     bool tail_fused() const { return dw.N <= tail_cluster_max && dw.n_sc_chunks > 0; }
@@ -1175,12 +1204,13 @@ public:
         launches++;
     }
     // one CTA per ordered frame pair, then the gather into sys = [HA | bA | H_sc | b_sc]
-    void launch_stitch(int respect_done) {
-        const int N = dw.N, n = dw.n;
-        launch_pdl(16, stitch_pair_kernel, dim3(N * N), dim3(ST_THREADS), stitch_smem(), dw, respect_done);
+    void launch_stitch_only(int respect_done) { launch_pdl(16, stitch_pair_kernel, dim3(dw.N * dw.N), dim3(ST_THREADS), stitch_smem(), dw, respect_done); }
+    void launch_assemble(int respect_done) {
+        const int n = dw.n;
         if (dw.p2p_on) dw.p2p_epoch = ++p2p_epoch;       // the same count on every rank: one exchange per stitched system
         launch_pdl(32, assemble_kernel, dim3((2 * n * n + 2 * n + 255) / 256 + 3), dim3(256), 0, dw, respect_done);   // +3 CTAs: 20 warps for HA[C,C], bA[C]
     }
+    void launch_stitch(int respect_done) { launch_stitch_only(respect_done); launch_assemble(respect_done); }
     int launch_solve_sequence(int respect_done) {
         launch_tail(respect_done);
         if (world > 1 && !dw.p2p_on) { int rc = allreduce_system(); if (rc) return rc; }      // with peer memory solve_kernel sums the ranks itself
@@ -1218,6 +1248,7 @@ public:
             CK(d_cap.reserve(1));
             if (g_nccl.AllReduce(d_cap.p, d_cap.p, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, comm, stream) != 0) { set_error("ncclAllReduce (rank alignment) failed"); return CMLBA_ERR_CUDA; }
         }
+        if (want_ktrace) { CK(d_ktrace.reserve(96)); dw.ktrace = d_ktrace.p; ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
         CK(cudaEventRecord(ev0, stream));
         if (!cfg.force_accept) { point_prior_energy_kernel<<<1, 256, 0, stream>>>(dw); launches++; }
         launch_linearize(0, 0); launch_post(0, 0);
@@ -1362,7 +1393,7 @@ public:
         CK(cudaSetDevice(device));
         const size_t flush_bytes = (size_t) 384 << 20;
         if (flush_l2) CK(d_flush.reserve(flush_bytes / sizeof(float4)));
-        cudaEvent_t ev[6];
+        cudaEvent_t ev[7];
         for (auto &e : ev) CK(cudaEventCreate(&e));
         // after the flush the ranks are re-aligned on the device (peer-memory barrier, outside the timed region): the flush lengths differ per rank
         auto flush = [&]() {
@@ -1373,10 +1404,11 @@ public:
         launch_linearize(0, 0); launch_post(0, 0);
         for (int i = 0; i < warmup; i++) { flush(); launch_linearize(0, 0); launch_tail(0); }
         CK(cudaStreamSynchronize(stream));
-        double tot = 0, tk[4] = {0, 0, 0, 0};
+        double tot = 0, tk[6] = {0, 0, 0, 0, 0, 0};
         const int l0 = launches;
         for (int i = 0; i < steps; i++) {          // whole pass, two events only
             flush();
+            if (want_ktrace) { CK(d_ktrace.reserve(96)); dw.ktrace = d_ktrace.p; ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
             CK(cudaEventRecord(ev[0], stream));
             launch_linearize(0, 0);
             launch_tail(0);
@@ -1386,20 +1418,31 @@ public:
             float ms = 0; CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); tot += ms;
         }
         const int per_pass = (launches - l0) / steps;
-        for (int i = 0; i < steps; i++) {          // per-kernel breakdown (every interval carries one event-record overhead, reported as ms_accumulate)
+        // per-kernel breakdown: the same kernels SERIALISED on the main stream (no fork), one event-to-event interval each; every interval
+        // carries one event-record overhead, measured by the empty interval ev[1]..ev[2]
+        const bool fork_saved = use_fork; use_fork = false;
+        unsigned long long *kt_saved = dw.ktrace; dw.ktrace = nullptr;       // the timeline keeps the last whole pass
+        for (int i = 0; i < steps; i++) {
             flush();
             CK(cudaEventRecord(ev[0], stream)); launch_linearize(0, 0);
             CK(cudaEventRecord(ev[1], stream));
-            CK(cudaEventRecord(ev[2], stream)); if (tail_fused()) launch_tail(0); else launch_schur(0);      // fused: the whole tail is reported as ms_schur
-            CK(cudaEventRecord(ev[3], stream)); if (!tail_fused()) launch_stitch(0);
-            CK(cudaEventRecord(ev[4], stream));
+            CK(cudaEventRecord(ev[2], stream));
+            if (tail_fused()) { launch_tail(0); for (int k = 3; k < 7; k++) CK(cudaEventRecord(ev[k], stream)); }      // fused: the whole tail is reported as ms_accumulate
+            else {
+                launch_accumulate(0); CK(cudaEventRecord(ev[3], stream));
+                launch_schur_only(0); CK(cudaEventRecord(ev[4], stream));
+                launch_stitch_only(0); CK(cudaEventRecord(ev[5], stream));
+                launch_assemble(0); CK(cudaEventRecord(ev[6], stream));
+            }
             CK(cudaStreamSynchronize(stream));
-            for (int k = 0; k < 4; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); tk[k] += ms; }
+            for (int k = 0; k < 6; k++) { float ms = 0; CK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1])); tk[k] += ms; }
         }
+        use_fork = fork_saved; dw.ktrace = kt_saved;
         CK(cudaGetLastError());
         for (auto &e : ev) cudaEventDestroy(e);
         out->steps = steps; out->residuals = dw.R; out->points = dw.P; out->frames = dw.N;
-        out->ms_pass = tot / steps; out->ms_linearize = tk[0] / steps; out->ms_accumulate = tk[1] / steps; out->ms_schur = tk[2] / steps; out->ms_stitch = tk[3] / steps;
+        out->ms_pass = tot / steps; out->ms_linearize = tk[0] / steps; out->ms_event_overhead = tk[1] / steps; out->ms_accumulate = tk[2] / steps; out->ms_schur = tk[3] / steps;
+        out->ms_stitch = tk[4] / steps; out->ms_assemble = tk[5] / steps;
         out->launches_per_pass = per_pass;
         return CMLBA_OK;
     }
@@ -1478,6 +1521,7 @@ public:
             for (int i = 0; i < R; i++) v[i] = (uint8_t) (name == "res_host" ? ((pht[i] >> 24) & 15u) : (pht[i] >> 28));
             return host_out(v.data(), R, dst, cap, bytes);
         }
+        if (name == "ktrace") { if (!d_ktrace.p) { set_error("CMLBA_KTRACE=1 first"); return CMLBA_ERR_STATE; } return copy_out(d_ktrace.p, 96, dst, cap, bytes); }
         if (name == "lt_trace") return copy_out(d_lt_trace.p, (size_t) dw.lt_grid * 16 * 32, dst, cap, bytes);
         if (name == "res_src") return copy_out(d_r_src.p, R, dst, cap, bytes);
         if (name == "res_job") return copy_out(d_r_job.p, R, dst, cap, bytes);

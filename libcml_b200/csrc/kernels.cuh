@@ -46,6 +46,18 @@ __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
 }
 
+// development timeline (CMLBA_KTRACE=1, tools/ktrace.py): one object at the top of every kernel of the chain
+struct KTrace {
+    unsigned long long *p;
+    static __device__ __forceinline__ unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+    __device__ __forceinline__ KTrace(const DevWin &w, const int k) : p(w.ktrace ? w.ktrace + 3 * k : nullptr) { if (p && (threadIdx.x & 31) == 0) atomicMin(p, now()); }
+    __device__ __forceinline__ void begin() const { if (p && (threadIdx.x & 31) == 0) atomicMin(p + 1, now()); }
+    __device__ __forceinline__ ~KTrace() { if (p && (threadIdx.x & 31) == 0) atomicMax(p + 2, now()); }
+};
+#define KTRACE_ENTER(k) KTrace kt_(w, (k)); pdl_enter(); kt_.begin()
+// slot 0 (the sampling kernel, which carries no stamps of its own: register budget) gets the time of this reset = the start of the timed region
+__global__ void ktrace_reset_kernel(unsigned long long *kt) { const int i = threadIdx.x; if (i < 96) kt[i] = i < 3 ? KTrace::now() : (i % 3 == 2) ? 0ull : ~0ull; }
+
 // Frame state -> PRE_worldToCam (DSOFrame::setState, DSOFrame.h:110-124)
 __device__ inline void frame_set_state(FrameDev &f, const double *state, const DevWin &w) {
     const double sc[10] = {w.scaleT, w.scaleT, w.scaleT, w.scaleR, w.scaleR, w.scaleR, w.scaleA, w.scaleB, w.scaleA, w.scaleB};
@@ -145,11 +157,12 @@ __host__ __device__ __forceinline__ size_t schur_smem_bytes(int N) { return size
 // slice).  Every lane keeps the 91 sums of the packed 13x13 block in registers over its residuals (lane, lane + 32, ...: the next
 // record is in flight while the current one is evaluated), then one transposing butterfly per 32 entries sums the lanes.
 __global__ void __launch_bounds__(32) accumulate_kernel(const DevWin w, const int respect_done) {
-    pdl_enter();
-    if (respect_done && w.ctrl->done) return;
+    KTRACE_ENTER(1);
     const int job = blockIdx.x, bin = job / ACC_SLICES, sl = job - bin * ACC_SLICES, lane = threadIdx.x;
-    const int cur = w.ctrl->cur;
+    // everything the first record load needs is requested together (one latency): control block, bin bounds
+    const int done_ld = w.ctrl->done, cur = w.ctrl->cur;
     const int b0 = w.res_bin_begin[bin], b1 = w.res_bin_begin[bin + 1];
+    if (respect_done && done_ld) return;
     const int len = (b1 - b0 + ACC_SLICES - 1) / ACC_SLICES, a0 = min(b0 + sl * len, b1), a1 = min(a0 + len, b1);
     float acc[ACC_N];
 #pragma unroll
@@ -190,15 +203,16 @@ __global__ void __launch_bounds__(32) accumulate_kernel(const DevWin w, const in
 }
 
 __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int respect_done) {
-    pdl_enter();
-    if (respect_done && w.ctrl->done) return;
+    KTRACE_ENTER(2);
     extern __shared__ __align__(16) float sm[];
     const int N = w.N, NB = 8 * N, ZS = NB + SCZ_PAD;
-    const int cur = w.ctrl->cur;
+    const int done_ld = w.ctrl->done, cur = w.ctrl->cur;                 // requested together with the chunk bounds below (one latency)
+    const int begin_ld = w.sc_chunk_begin[blockIdx.x], cnt_ld = w.sc_chunk_count[blockIdx.x];
+    if (respect_done && done_ld) return;
     float *sT = sm;                                  // [SC_CHUNK][N][T_STRIDE] raw Schur rows
     float *sZ = sT + SC_CHUNK * N * T_STRIDE;        // [SC_CHUNK][ZS]         augmented, scaled
     const int c = blockIdx.x, tid = threadIdx.x;
-    const int begin = w.sc_chunk_begin[c], cnt = w.sc_chunk_count[c];
+    const int begin = begin_ld, cnt = cnt_ld;
     {   // stage the rows of the chunk's points (contiguous in T)
         const float4 *src = reinterpret_cast<const float4 *>(w.T[cur] + (size_t) begin * N * T_STRIDE);
         float4 *dst = reinterpret_cast<float4 *>(sT);
@@ -321,16 +335,17 @@ __device__ __forceinline__ int acc_index(int r, int c) {
 constexpr int ST_A_TT = 0, ST_A_IT = 64, ST_A_II = 128, ST_A_TC = 192, ST_A_IC = 224, ST_A_CC = 256, ST_BA_T = 272, ST_BA_I = 280, ST_BA_C = 288,
               ST_S_JI = 296, ST_S_II = 360, ST_S_JC = 424, ST_S_IC = 456, ST_BS_J = 488, ST_BS_I = 496, ST_S_JK = 504;
 __host__ __device__ __forceinline__ int st_stride(int N) { return ST_S_JK + 64 * N; }
-constexpr int ST_THREADS = 512;
+constexpr int ST_THREADS = 576;     // 8 * 64 + 40 partial sums + ... : one round of the chunk sums for N = 8
 
 __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w, const int respect_done) {
-    pdl_enter();
-    if (respect_done && w.ctrl->done) return;
+    KTRACE_ENTER(3);
     extern __shared__ __align__(16) double smd[];
     const int N = w.N, NB = 8 * N, tid = threadIdx.x;
     const int i = blockIdx.x / N, j = blockIdx.x % N;
     double *out = w.st_out + (size_t) blockIdx.x * st_stride(N);
-    const int cb = w.host_chunk_begin[i], ce = w.host_chunk_begin[i + 1];
+    const int done_ld = respect_done ? w.ctrl->done : 0;
+    const int cb = w.host_chunk_begin[i], ce = w.host_chunk_begin[i + 1];       // requested together with the control block (one latency)
+    if (done_ld) return;
     if (i == j) {   // calibration block of host i's Schur complement (BA:1908-1909, 2026-2027)
         if (tid < 20) {
             const float *src = w.sc_part + (size_t) cb * w.sc_stride + NB * NB + NB * 5 + tid;
@@ -348,6 +363,7 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
     double *A = atd + NB;          // [ACC_N]  packed 13x13 block of bin (i -> j)
     double *Y = A + ACC_N;         // [8][8]   sum_k D_jk AH_ik^T
     double *M = Y + 64;            // [8][8]   AH_ij A8
+    double *Yp = M + 64;           // [N][8][8] D_jk AH_ik^T per k (summed into Y in fixed order)
     for (int e = tid; e < 8 * NB + 40; e += ST_THREADS) {
         int off;
         if (e < 8 * NB) off = j * 8 * NB + e;
@@ -362,19 +378,25 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
     if (tid < ACC_N) {   // 13x13 block of bin (i -> j): the slices of the accumulate role of schur_acc_kernel, fixed order
         const float *src = w.acc_bin + (size_t) (j * N + i) * ACC_SLICES * ACC_N + tid;
         double a = 0.0;
-        for (int sl = 0; sl < ACC_SLICES; sl++) a += (double) __ldcg(src + sl * ACC_N);
+        float part[ACC_SLICES];
+#pragma unroll
+        for (int sl = 0; sl < ACC_SLICES; sl++) part[sl] = src[sl * ACC_N];     // plain loads: all in flight together (ld.global.cg is a strong access the compiler keeps in order: 16 serial L2 round trips)
+#pragma unroll
+        for (int sl = 0; sl < ACC_SLICES; sl++) a += (double) part[sl];
         A[tid] = a;
     }
     for (int e = tid; e < N * 64; e += ST_THREADS) G[e] = w.AH[(size_t) (i * N) * 64 + e];
     for (int e = tid; e < NB; e += ST_THREADS) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
     __syncthreads();
     const double *AHj = G + j * 64, *atj = atd + j * 8;
-    {
-        const int r = (tid >> 3) & 7, c = tid & 7;
+    for (int e = tid; e < N * 64 + 64; e += ST_THREADS) {       // short dependent chains: 8 products per thread
+        const int r = (e >> 3) & 7, c = e & 7;
         double s = 0.0;
-        if (tid < 64) { for (int k = 0; k < N; k++) for (int m = 0; m < 8; m++) s += Dj[r * NB + k * 8 + m] * G[k * 64 + c * 8 + m]; Y[tid] = s; }
-        else if (tid < 128) { for (int m = 0; m < 8; m++) s += AHj[r * 8 + m] * A[acc_index(4 + m, 4 + c)]; M[tid - 64] = s; }
+        if (e < N * 64) { const int k = e >> 6; for (int m = 0; m < 8; m++) s += Dj[r * NB + k * 8 + m] * G[k * 64 + c * 8 + m]; Yp[e] = s; }
+        else { for (int m = 0; m < 8; m++) s += AHj[r * 8 + m] * A[acc_index(4 + m, 4 + c)]; M[e - N * 64] = s; }
     }
+    __syncthreads();
+    if (tid < 64) { double s = 0.0; for (int k = 0; k < N; k++) s += Yp[k * 64 + tid]; Y[tid] = s; }
     __syncthreads();
     const int tot = st_stride(N);
     for (int e = tid; e < tot; e += ST_THREADS) {
@@ -473,25 +495,31 @@ __global__ void __launch_bounds__(32) p2p_barrier_kernel(const DevWin w) {
     }
 }
 
-// sum_k!=a slot(a,k)[o_row] + sum_k!=a slot(k,a)[o_col], all loads issued before the (fixed-order) adds
-__device__ __forceinline__ double sum_slots(const double *st, const int N, const int S, const int a, const int o_row, const int o_col) {
-    double v = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < N; k++) { const double x = __ldcg(st + (size_t) (a * N + (k != a ? k : (a + 1) % N)) * S + o_row); v += (k != a) ? x : 0.0; }
-#pragma unroll 8
-    for (int k = 0; k < N; k++) { const double x = __ldcg(st + (size_t) ((k != a ? k : (a + 1) % N) * N + a) * S + o_col); v += (k != a) ? x : 0.0; }
-    return v;
-}
-
 // element e of this rank's sys: local buffer, or (peer exchange) the rank's slot in every rank's buffer
 __device__ __forceinline__ void sys_emit(const DevWin &w, const bool p2p, const int e, const double v) {
     if (!p2p) { w.sys[e] = v; return; }
     for (int q = 0; q < w.world; q++) p2p_slot(w, q, w.rank)[e] = v;
 }
+// Every element of sys is a fixed-order sum of pair-slot entries of one of three shapes: a strided sequence over the frames k that skips
+// up to two of them (sequence A), a second such sequence (B), and up to two single entries.  The element only selects the shapes (integer
+// work); ONE copy of the gather loops then does the loads, so the kernel stays a few hundred instructions (the per-case unrolled
+// version was 127 KB of SASS and spent its time fetching instructions).
+__device__ __forceinline__ double gather_seq(const double *st, const int N, const int off, const int stride, const int skip1, const int skip2) {
+    double v = 0.0;
+    for (int k0 = 0; k0 < N; k0 += 8) {
+        // eight unconditional loads into eight registers (a skipped k reads entry 0 of the sequence, which exists, and is discarded): they are
+        // all in flight before the first add.  Written as "load if used" the compiler chained load -> add -> load through one register.
+        double x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { const int k = k0 + j; const bool use = k < N && k != skip1 && k != skip2; x[j] = st[off + (use ? k : 0) * stride]; if (!use) x[j] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < 8; j++) v += x[j];
+    }
+    return v;
+}
 __device__ __forceinline__ void assemble_body(const DevWin &w, const bool p2p) {
     const int N = w.N, n = w.n, nn = n * n, S = st_stride(N);
     const double *st = w.st_out;
-#define SLOT(i, j) (st + (size_t) ((i) * N + (j)) * S)
     const int nelem = 2 * nn + 2 * n;
     if ((int) blockIdx.x * 256 >= nelem) {
         // calibration block of the active part: HA[C,C] (16) and bA[C] (4) sum over all N(N-1) pairs -> one warp per entry
@@ -499,7 +527,7 @@ __device__ __forceinline__ void assemble_body(const DevWin &w, const bool p2p) {
         if (k >= 20) return;
         const int off = k < 16 ? ST_A_CC + k : ST_BA_C + (k - 16);
         double v = 0.0;
-        for (int q = lane; q < N * N; q += 32) { const int i = q / N, j = q - i * N; const double x = SLOT(i, i != j ? j : (i + 1) % N)[off]; v += (i != j) ? x : 0.0; }
+        for (int q = lane; q < N * N; q += 32) { const int i = q / N, j = q - i * N; double x = 0.0; if (i != j) x = st[(size_t) q * S + off]; v += x; }
         v = warp_sum_d(v);
         if (lane == 0) sys_emit(w, p2p, k < 16 ? (k >> 2) * n + (k & 3) : nn + (k - 16), v);
         return;
@@ -508,32 +536,33 @@ __device__ __forceinline__ void assemble_body(const DevWin &w, const bool p2p) {
     if (e >= nelem) return;
     const bool schur = e >= nn + n;
     const int q = schur ? e - nn - n : e;
-    double v = 0.0;
+    // shapes: sequence A (offA + k * strA, k != skA1, skA2), sequence B, singles one1 / one2 (added in this order)
+    int offA = -1, strA = 0, skA1 = -1, skA2 = -1, offB = -1, strB = 0, skB = -1, one1 = -1, one2 = -1;
+    auto row_col = [&](const int a, const int o_row, const int o_col) {       // sum_k!=a slot(a,k)[o_row] + sum_k!=a slot(k,a)[o_col]
+        offA = a * N * S + o_row; strA = S; skA1 = a;
+        offB = a * S + o_col; strB = N * S; skB = a;
+    };
     if (q < nn) {
         int r = q / n, c = q - r * n;
         if (r < 4 && c >= 4) { const int t = r; r = c; c = t; }          // calibration rows mirror the columns
         if (r < 4) {                                                      // (C,C)
             if (!schur) return;                                           // written by the warp-per-entry blocks above
-            for (int i = 0; i < N; i++) v += SLOT(i, i)[r * 4 + c];
+            offA = r * 4 + c; strA = (N + 1) * S;                         // sum_i slot(i,i)
         } else if (c < 4) {                                               // (frame a, C)
             const int a = (r - 4) >> 3, rr = (r - 4) & 7;
-            const int o_i = (schur ? ST_S_IC : ST_A_IC) + rr * 4 + c, o_t = (schur ? ST_S_JC : ST_A_TC) + rr * 4 + c;
-            v = sum_slots(st, N, S, a, o_i, o_t);
+            row_col(a, (schur ? ST_S_IC : ST_A_IC) + rr * 4 + c, (schur ? ST_S_JC : ST_A_TC) + rr * 4 + c);
         } else {
             const int a = (r - 4) >> 3, rr = (r - 4) & 7, b = (c - 4) >> 3, cc = (c - 4) & 7;
             if (a == b) {
-                if (!schur) v = sum_slots(st, N, S, a, ST_A_II + rr * 8 + cc, ST_A_TT + rr * 8 + cc);
-                else v = sum_slots(st, N, S, a, ST_S_II + rr * 8 + cc, ST_S_JK + a * 64 + rr * 8 + cc);
+                if (!schur) row_col(a, ST_A_II + rr * 8 + cc, ST_A_TT + rr * 8 + cc);
+                else row_col(a, ST_S_II + rr * 8 + cc, ST_S_JK + a * 64 + rr * 8 + cc);
             } else {
                 // the (lo,hi) orientation is summed the same way from both sides: the result is bitwise symmetric
                 const int lo = a < b ? a : b, hi = a < b ? b : a, rl = a < b ? rr : cc, rh = a < b ? cc : rr;   // element (lo rl, hi rh)
-                if (!schur) v = SLOT(lo, hi)[ST_A_IT + rl * 8 + rh] + SLOT(hi, lo)[ST_A_IT + rh * 8 + rl];
+                if (!schur) { one1 = (lo * N + hi) * S + ST_A_IT + rl * 8 + rh; one2 = (hi * N + lo) * S + ST_A_IT + rh * 8 + rl; }
                 else {
-                    const double x1 = SLOT(hi, lo)[ST_S_JI + rl * 8 + rh], x2 = SLOT(lo, hi)[ST_S_JI + rh * 8 + rl];
-#pragma unroll 8
-                    for (int k = 0; k < N; k++) { const bool use = k != lo && k != hi; const double x = SLOT(use ? k : hi, lo)[ST_S_JK + hi * 64 + rl * 8 + rh]; v += use ? x : 0.0; }
-                    v += x1;
-                    v += x2;
+                    offA = lo * S + ST_S_JK + hi * 64 + rl * 8 + rh; strA = N * S; skA1 = lo; skA2 = hi;      // sum_k!=lo,hi slot(k,lo)
+                    one1 = (hi * N + lo) * S + ST_S_JI + rl * 8 + rh; one2 = (lo * N + hi) * S + ST_S_JI + rh * 8 + rl;
                 }
             }
         }
@@ -541,19 +570,21 @@ __device__ __forceinline__ void assemble_body(const DevWin &w, const bool p2p) {
         const int r = q - nn;
         if (r < 4) {
             if (!schur) return;
-            for (int i = 0; i < N; i++) v += SLOT(i, i)[16 + r];
+            offA = 16 + r; strA = (N + 1) * S;
         } else {
             const int a = (r - 4) >> 3, rr = (r - 4) & 7;
-            const int o_i = (schur ? ST_BS_I : ST_BA_I) + rr, o_t = (schur ? ST_BS_J : ST_BA_T) + rr;
-            v = sum_slots(st, N, S, a, o_i, o_t);
+            row_col(a, (schur ? ST_BS_I : ST_BA_I) + rr, (schur ? ST_BS_J : ST_BA_T) + rr);
         }
     }
-#undef SLOT
+    double v = 0.0;
+    if (offA >= 0) v = gather_seq(st, N, offA, strA, skA1, skA2);
+    if (offB >= 0) v += gather_seq(st, N, offB, strB, skB, -1);
+    if (one1 >= 0) { const double x1 = st[one1], x2 = st[one2]; v += x1; v += x2; }
     sys_emit(w, p2p, e, v);
 }
 
 __global__ void __launch_bounds__(256) assemble_kernel(const DevWin w, const int respect_done) {
-    pdl_enter();
+    KTRACE_ENTER(4);
     if (respect_done && w.ctrl->done) return;
     const bool p2p = w.p2p_on && w.world > 1;
     assemble_body(w, p2p);
@@ -575,7 +606,7 @@ namespace cmlba {
 // Reduced camera system: assemble, damp, Jacobi-scale, LDL^T (lower triangle, like Eigen's default), solve,
 // orthogonalise against the gauge nullspaces, frame steps + new frame states + pair constants, xAd.
 __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int respect_done) {
-    pdl_enter();
+    KTRACE_ENTER(5);
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     extern __shared__ __align__(16) double smd[];
@@ -808,7 +839,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
 // ------------------------------------------------------------------------------------------------
 // Per-point back-substitution and step (BA:1455-1487, 976-994) + convergence test (BA:1013-1026)
 __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const int respect_done) {
-    pdl_enter();
+    KTRACE_ENTER(6);
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     const int N = w.N, cur = ctrl->cur;
@@ -887,7 +918,7 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
 // std::nth_element leaves at index floor(0.7 n)), accept bookkeeping of run() (forceAccept path).
 // mode 0: first linearization of run() (+applyActiveRes)  1: GN iteration  2: final linearizeAll(true)  3: stage call (no flip)
 __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, const int mode, const int respect_done) {
-    pdl_enter();
+    KTRACE_ENTER(7);
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     const int tid = threadIdx.x;
@@ -1051,7 +1082,7 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
 
 // multi-GPU: this rank's record for the all-gather that precedes post_linearize_kernel (see DevWin::post_send)
 __global__ void __launch_bounds__(1024) pack_post_kernel(const DevWin w, const int respect_done) {
-    pdl_enter();
+    KTRACE_ENTER(8);
     Ctrl *ctrl = w.ctrl;
     (void) respect_done;   // always packs: every rank must feed the collective, even after its own early exit
     const int tid = threadIdx.x;
@@ -1103,7 +1134,7 @@ __global__ void commit_candidate_kernel(const DevWin w) { if (threadIdx.x == 0 &
 
 // forceAccept = false: undo a rejected step (loadSateBackup, BA:928-946).  `it1` = the iteration counter value the step belongs to.
 __global__ void __launch_bounds__(256) restore_state_kernel(const DevWin w, const int it1) {
-    pdl_enter();
+    KTRACE_ENTER(9);
     Ctrl *ctrl = w.ctrl;
     if (ctrl->rejected_at != it1) return;
     const int p = blockIdx.x * 256 + threadIdx.x;

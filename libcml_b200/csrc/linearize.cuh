@@ -29,12 +29,15 @@
 
 namespace cmlba {
 
-constexpr int LT_TILE_TABLE = 64;     // tile descriptors / user counts of a CTA kept in shared memory (more tiles: read from global memory)
+constexpr int LT_TILE_TABLE = 24;     // tile descriptors / user counts of a CTA that travel in its cta_info record and are kept in shared memory (more tiles: read from global memory)
+constexpr int LT_INIT_BOXES = 2;      // boxes a CTA issues up front; the rest of the ring is filled as those land (bulk traffic in flight delays every other request of the SM)
+constexpr int LT_INFO_INTS = 64;      // ints per cta_info record: q0 q1 t_first - | jd[4] | users[4] | - [4] | jd table [LT_TILE_TABLE] | users table [LT_TILE_TABLE]
 struct alignas(64) TileMaps { CUtensorMap m[MAXF]; };   // one 2-D tensor map per window frame: rows of W float4 texels seen as 2W 8-byte elements
 
+constexpr int LT_STAGE_REC = 32;       // Jacobian records a warp stages in shared memory at a time (two rounds per pass) for its line-coalesced stores
 // CW warps, ST ring stages
 __host__ __device__ __forceinline__ size_t lt_smem_bytes(int N, int CW, int ST) {
-    return (size_t) ST * LT_STAGE_STRIDE + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float) + 8 * sizeof(int) + LT_TILE_TABLE * 2 * sizeof(int);
+    return (size_t) ST * LT_STAGE_STRIDE + (size_t) 2 * N * sizeof(PairPre) + 2 * ST * sizeof(unsigned long long) + MAXF * sizeof(float) + 8 * sizeof(int) + LT_TILE_TABLE * 2 * sizeof(int) + (size_t) CW * LT_STAGE_REC * RJ_STRIDE * sizeof(float);
 }
 
 // ---- mbarrier / TMA (PTX ISA 8.x; SASS: SYNCS.*, UTMALDG)
@@ -45,6 +48,7 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_n(unsigned long long *bar, uint32_t n) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(n) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 constexpr int LT_EMPTY_COUNT = 1 << 12;   // arrival count of a stage's "empty" barrier: the producer tops the users of a tile up to this number
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity) {
     uint32_t ok;
@@ -214,20 +218,42 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const DevWin w) {
     }
 }
 
+// one box into a ring stage, as a real call: the call sites sit in register-critical code and run once per tile
+__device__ __noinline__ void lt_issue_box(unsigned char *stage, const CUtensorMap *maps, const uint32_t jd, const int users, unsigned long long *full_s, unsigned long long *empty_s) {
+    const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
+    mbar_arrive_n(empty_s, (uint32_t) (LT_EMPTY_COUNT - users));
+    mbar_expect_tx(full_s, LT_TILE_BYTES);
+    tma_load_2d(stage, maps + t, (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full_s);
+}
+
+// step 2b: the per-point constants of every residual (pixel, reference colours, gradient weights), copied into the sorted residual order as
+// five float4 columns r_pt4[k][R]: the sampling kernel reads them with fully coalesced 16-byte loads (20 LSU wavefronts per warp pass)
+// instead of gathering seven arrays by point index (~250 wavefronts: the load/store unit, not HBM, was what its first phase waited on)
+__global__ void __launch_bounds__(256) bin_pack_kernel(const DevWin w) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= w.R) return;
+    const int p = (int) (w.r_pht[r] & 0xffffffu);
+    const float4 *col = reinterpret_cast<const float4 *>(w.pt_colors + (size_t) p * 8), *wt = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
+    w.r_pt4[r] = make_float4(w.pt_x[p], w.pt_y[p], 0.f, 0.f);
+    w.r_pt4[(size_t) w.R + r] = col[0]; w.r_pt4[(size_t) 2 * w.R + r] = col[1];
+    w.r_pt4[(size_t) 3 * w.R + r] = wt[0]; w.r_pt4[(size_t) 4 * w.R + r] = wt[1];
+}
+
 // step 3: per-CTA records of linearize_tile_kernel (grid = lt_grid persistent CTAs over contiguous ranges of warp passes)
 __global__ void __launch_bounds__(256) bin_finish_kernel(const DevWin w) {
     const int per_cta = (w.n_chunks + w.lt_grid - 1) / w.lt_grid;
     for (int b = threadIdx.x; b < w.lt_grid; b += 256) {
         const int c0 = b * per_cta, c1 = min(c0 + per_cta, w.n_chunks);
-        int *info = w.cta_info + (size_t) b * 16;
-        for (int k = 0; k < 16; k++) info[k] = 0;
+        int *info = w.cta_info + (size_t) b * LT_INFO_INTS;
+        for (int k = 0; k < LT_INFO_INTS; k++) info[k] = 0;
         if (c0 >= c1) continue;
         const int q0 = w.r_job[c0 * 32], q1 = w.r_job[min(c1 * 32, w.R) - 1];
         info[0] = q0; info[1] = q1; info[2] = (int) (w.r_pht[c0 * 32] >> 28);
-        for (int i = 0; i < 4 && q0 + i <= q1; i++) {
+        for (int i = 0; i < LT_TILE_TABLE && q0 + i <= q1; i++) {
             const int jb = w.job_begin[q0 + i], je = w.job_begin[q0 + i + 1];
-            info[4 + i] = (int) w.job_desc[q0 + i];
-            info[8 + i] = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
+            const int jd = (int) w.job_desc[q0 + i], users = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
+            if (i < 4) { info[4 + i] = jd; info[8 + i] = users; }
+            info[16 + i] = jd; info[16 + LT_TILE_TABLE + i] = users;
         }
     }
 }
@@ -237,7 +263,6 @@ template <bool kDump, int LT_CWARPS, int LT_STAGES>
 __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const DevWin w, const __grid_constant__ TileMaps tm, const int fix, const int respect_done) {
     pdl_enter();
     Ctrl *ctrl = w.ctrl;
-    if (respect_done && ctrl->done) return;
     extern __shared__ __align__(1024) unsigned char lt_smem[];
     unsigned char *ring = lt_smem;                                                                  // [LT_STAGES][LT_BOX_H][LT_BOX_W] float4
     PairPre *s_pairs = reinterpret_cast<PairPre *>(lt_smem + (size_t) LT_STAGES * LT_STAGE_STRIDE); // [2 targets][N hosts]
@@ -247,28 +272,53 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
     int *s_tag = reinterpret_cast<int *>(s_th + MAXF);                                              // [LT_STAGES] tile in (or on its way into) every stage
     unsigned long long *pairs_bar = reinterpret_cast<unsigned long long *>(s_tag + 4);              // the staged constants are in place
     int *s_jd = s_tag + 8, *s_users = s_jd + LT_TILE_TABLE;                                         // descriptors / user counts of the CTA's first LT_TILE_TABLE tiles
+    float4 *s_stage = reinterpret_cast<float4 *>(s_users + LT_TILE_TABLE) + (size_t) (threadIdx.x >> 5) * (LT_STAGE_REC * RJ_STRIDE / 4);   // [LT_CWARPS][LT_STAGE_REC][9] float4
     const int N = w.N, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (w.n_chunks + (int) gridDim.x - 1) / (int) gridDim.x;
     const int c0 = blockIdx.x * per, c1 = min(c0 + per, w.n_chunks);
     if (c0 >= c1) return;
+    // ---- ONE exposed memory latency before the first boxes can be issued and the first point records requested: everything below depends
+    // on the launch geometry only -- the control block, the CTA's record (tile range, descriptors and user counts of its first
+    // LT_TILE_TABLE tiles; written by bin_finish_kernel) and the per-residual scalars of every warp's first pass (both copies of the
+    // double-buffered state / energy: which one is current is part of the same round trip).
+    const int4 *infop = reinterpret_cast<const int4 *>(w.cta_info + (size_t) blockIdx.x * LT_INFO_INTS);
+    const int done_ld = ctrl->done, cur = ctrl->cur;
+    const int4 info = __ldg(infop);
+    int tab_jd = 0, tab_users = 0;
+    if ((int) threadIdx.x < LT_TILE_TABLE) { tab_jd = __ldg(w.cta_info + (size_t) blockIdx.x * LT_INFO_INTS + 16 + threadIdx.x); tab_users = __ldg(w.cta_info + (size_t) blockIdx.x * LT_INFO_INTS + 16 + LT_TILE_TABLE + threadIdx.x); }
+    uint32_t pht = 0; int job = 0, src = 0; uint8_t alive_ld = 0, st = RES_OOB, nst = 0; float e_old = 0.f, ne = 0.f;
+    {
+        const int rr = (c0 + warp < c1 ? c0 + warp : c0) * 32 + lane, rl = rr < w.R ? rr : w.R - 1;
+        pht = __ldg(w.r_pht + rl); job = __ldg(w.r_job + rl); src = __ldg(w.r_src + rl);
+        alive_ld = w.r_alive[rl]; nst = w.r_new_state[rl]; ne = w.r_new_energy[rl];
+        const uint8_t st0 = w.r_state[0][rl], st1 = w.r_state[1][rl];
+        const float e0 = w.r_energy[0][rl], e1 = w.r_energy[1][rl];
+        st = rr < w.R ? (cur ? st1 : st0) : (uint8_t) RES_OOB; e_old = cur ? e1 : e0;
+    }
+    const int nxt = cur ^ 1;
+    if (respect_done && done_ld) return;
+    // the per-residual scalars of every later pass are requested at the bottom of the pass before it
+    auto load_headers = [&](const int cc) {
+        const int rr = cc * 32 + lane, rl = rr < w.R ? rr : w.R - 1;
+        pht = __ldg(w.r_pht + rl); job = __ldg(w.r_job + rl); src = __ldg(w.r_src + rl);
+        alive_ld = w.r_alive[rl]; st = rr < w.R ? w.r_state[cur][rl] : (uint8_t) RES_OOB; e_old = w.r_energy[cur][rl];
+        nst = w.r_new_state[rl]; ne = w.r_new_energy[rl];
+    };
     // development trace: stamp k of this warp (SM clock); compiled to a predicated-off store in normal runs
     long long *trace = (w.lt_mode & 2) ? w.lt_trace + ((size_t) blockIdx.x * 16 + warp) * 32 : nullptr;
-#define LT_STAMPK(k) do { if (trace && (k) < 30 && lane == (__ffs(__activemask()) - 1)) trace[(k)] = clock64(); } while (0)
+#define LT_STAMPK(k) do { if (trace && (k) < 28 && lane == (__ffs(__activemask()) - 1)) trace[(k)] = clock64(); } while (0)
     LT_STAMPK(0);
     if (trace && lane == 0) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); trace[30] = gt; }
     const int r_first = c0 * 32, r_last = min(c1 * 32, w.R) - 1;
-    // one record per CTA, prepared by bin_segments_kernel: tile jobs [q0, q1] of the CTA (all non-empty), first target, and the descriptors /
-    // user counts of its first four tiles -- a single load before the first boxes can be issued
-    const int4 *infop = reinterpret_cast<const int4 *>(w.cta_info + (size_t) blockIdx.x * 16);
-    const int4 info = __ldg(infop);
     const int q0 = info.x, q1 = info.y, t_first = info.z, n_tiles_cta = q1 - q0 + 1;
+    if (trace && q0 >= 0) LT_STAMPK(22);             // the CTA record has arrived
     // There is no producer warp.  A stage goes back to "empty" when every warp pass that overlaps its tile (the passes are consecutive, so
     // their number follows from the tile's residual range) has arrived on the stage's barrier; the warp whose arrival completes that
     // phase issues the box of the tile that comes LT_STAGES later into the same stage (one winner: compare-and-swap on the stage tag),
     // topping the new tile's user count up to the barrier's fixed arrival count.
-    auto issue = [&](const int i, const uint32_t jd, const int users) {        // tile q0 + i, by one thread; the stage tag is already set
+    auto issue = [&](const int i, const uint32_t jd_, const int users) {      // tile q0 + i, by one thread; the stage tag is already set
         const int s = i % LT_STAGES;
-        const int t = (int) (jd & 15u), tx = (int) ((jd >> 4) & 0xfffu), ty = (int) (jd >> 16);
+        const int t = (int) (jd_ & 15u), tx = (int) ((jd_ >> 4) & 0xfffu), ty = (int) (jd_ >> 16);
         mbar_arrive_n(empty + s, (uint32_t) (LT_EMPTY_COUNT - users));
         mbar_expect_tx(full + s, LT_TILE_BYTES);
         tma_load_2d(ring + (size_t) s * LT_STAGE_STRIDE, &tm.m[t], (tx * LT_TILE_W - LT_HALO) * 2, ty * LT_TILE_H - LT_HALO, full + s);
@@ -289,97 +339,105 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
             issue(k + LT_STAGES, jd, users);
         }
     };
+    // Only LT_INIT_BOXES boxes are issued up front: a box in flight sits in front of every other request of the SM (measured: with four
+    // 42 KB boxes outstanding the first per-residual loads of the kernel took 3 us longer).  Tile k + LT_INIT_BOXES of the initial ring
+    // window is issued by whoever first sees tile k landed (one winner per tile: compare-and-swap on s_pump).
+    int *s_pump = s_tag + 6;                         // [2]
+    auto pump = [&](const int k) {
+        const int i = k + LT_INIT_BOXES;
+        if (i < LT_STAGES && i < n_tiles_cta && atomicCAS(s_pump + (i - LT_INIT_BOXES), 0, 1) == 0)
+            lt_issue_box(ring + (size_t) i * LT_STAGE_STRIDE, tm.m, (uint32_t) ((volatile int *) s_jd)[i], ((volatile int *) s_users)[i], full + i, empty + i);
+    };
     if (threadIdx.x == 0) {
         for (int s = 0; s < LT_STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, LT_EMPTY_COUNT); s_tag[s] = q0 + s; }
+        s_pump[0] = 0; s_pump[1] = 0;
         mbar_init(pairs_bar, LT_CWARPS * 32);
         mbar_fence_init();
         if (w.tma_on) {
             const int4 jd4 = __ldg(infop + 1), us4 = __ldg(infop + 2);
-            if (0 < n_tiles_cta && 0 < LT_STAGES) issue(0, (uint32_t) jd4.x, us4.x);
-            if (1 < n_tiles_cta && 1 < LT_STAGES) issue(1, (uint32_t) jd4.y, us4.y);
-            if (2 < n_tiles_cta && 2 < LT_STAGES) issue(2, (uint32_t) jd4.z, us4.z);
-            if (3 < n_tiles_cta && 3 < LT_STAGES) issue(3, (uint32_t) jd4.w, us4.w);
+            const int init = (w.lt_mode & 16) ? LT_STAGES : LT_INIT_BOXES;     // development: 16 = the whole ring up front
+            if (0 < n_tiles_cta && 0 < init) issue(0, (uint32_t) jd4.x, us4.x);
+            if (1 < n_tiles_cta && 1 < init) issue(1, (uint32_t) jd4.y, us4.y);
+            if (2 < n_tiles_cta && 2 < init) { s_pump[0] = 1; issue(2, (uint32_t) jd4.z, us4.z); }
+            if (3 < n_tiles_cta && 3 < init) { s_pump[1] = 1; issue(3, (uint32_t) jd4.w, us4.w); }
         }
     }
-    __syncthreads();                                 // cheap: nothing but the barrier set-up (and the first boxes' issue) precedes it
-    {   // every thread stages its share of the constants, then arrives on pairs_bar; nobody waits here
-        for (int i = threadIdx.x; i < min(n_tiles_cta, LT_TILE_TABLE); i += LT_CWARPS * 32) {
-            const int jb = __ldg(w.job_begin + q0 + i), je = __ldg(w.job_begin + q0 + i + 1);
-            s_jd[i] = (int) __ldg(w.job_desc + q0 + i);
-            s_users[i] = min((je - 1) >> 5, c1 - 1) - max(jb >> 5, c0) + 1;
-        }
-        constexpr int PW = sizeof(PairPre) / 8;
+    if ((int) threadIdx.x < LT_TILE_TABLE) { s_jd[threadIdx.x] = tab_jd; s_users[threadIdx.x] = tab_users; }
+    LT_STAMPK(23);                                   // (warp 0: barriers initialised, first boxes issued)
+    __syncthreads();                                 // the barriers and the tile table are set up (the first boxes are on their way)
+    // ---- second round trip: the pair constants (staged in shared memory by all threads) and, issued before the staging stores can
+    // stall on them, the point records of every warp's first pass
+    LT_STAMPK(24);
+    constexpr int PW = sizeof(PairPre) / 8, PAIR_IT = (2 * MAXF * PW + LT_CWARPS * 32 - 1) / (LT_CWARPS * 32);
+    double pair_v[PAIR_IT];
+#pragma unroll
+    for (int it = 0; it < PAIR_IT; it++) {
+        const int i = threadIdx.x + it * LT_CWARPS * 32;
+        const int rec = i / PW, k = i - rec * PW, tt = rec / N, h = rec - tt * N, t = min(t_first + tt, N - 1);
+        pair_v[it] = i < 2 * N * PW ? reinterpret_cast<const double *>(w.pairs + h * N + t)[k] : 0.0;
+    }
+    const float th_v = (int) threadIdx.x < N ? w.frames[threadIdx.x].energy_th : 0.f;
+    // the point record of a pass (requested right after its per-residual scalars have arrived)
+    uint32_t jd = 0, pht_next = 0; double rho = 0.0; float xcf = 0.f, ycf = 0.f; float4 c0v, c1v, w0v, w1v;
+    auto load_point = [&](const int cc) {
+        const int pp_ = (int) (pht & 0xffffffu), rl = min(cc * 32 + lane, w.R - 1);
+        jd = __ldg(w.job_desc + job);
+        rho = w.pt_idepth[pp_];                      // the only per-point value that changes between passes: gathered
+        const float4 xy = __ldg(w.r_pt4 + rl);
+        xcf = xy.x; ycf = xy.y;
+        c0v = __ldg(w.r_pt4 + (size_t) w.R + rl); c1v = __ldg(w.r_pt4 + (size_t) 2 * w.R + rl);
+        w0v = __ldg(w.r_pt4 + (size_t) 3 * w.R + rl); w1v = __ldg(w.r_pt4 + (size_t) 4 * w.R + rl);
+        pht_next = (cc + LT_CWARPS < c1) ? __ldg(w.r_pht + min((cc + LT_CWARPS) * 32 + lane, w.R - 1)) : pht;     // for the L2 prefetch of the pass after
+    };
+    if (c0 + warp < c1) {     // first pass: the point record is on its way to L2 while the pair constants are staged (no registers held across the prologue)
+        const int pn = (int) (pht & 0xffffffu);
+        prefetch_l2(w.pt_idepth + pn); prefetch_l2(w.job_desc + job);
+        if (lane < 20) prefetch_l2(w.r_pt4 + (size_t) (lane >> 2) * w.R + (c0 + warp) * 32 + (lane & 3) * 8);      // 5 columns x 4 lines
+    }
+    {
         double *dst = reinterpret_cast<double *>(s_pairs);
-        for (int i = threadIdx.x; i < 2 * N * PW; i += LT_CWARPS * 32) {
-            const int rec = i / PW, k = i - rec * PW, tt = rec / N, h = rec - tt * N, t = min(t_first + tt, N - 1);
-            dst[i] = reinterpret_cast<const double *>(w.pairs + h * N + t)[k];
-        }
-        if ((int) threadIdx.x < N) s_th[threadIdx.x] = w.frames[threadIdx.x].energy_th;
+#pragma unroll
+        for (int it = 0; it < PAIR_IT; it++) { const int i = threadIdx.x + it * LT_CWARPS * 32; if (i < 2 * N * PW) dst[i] = pair_v[it]; }
+        if ((int) threadIdx.x < N) s_th[threadIdx.x] = th_v;
         mbar_arrive(pairs_bar);                      // release: the stores above are visible to whoever sees the phase complete
     }
+    LT_STAMPK(25);                                   // pair constants staged
     // ---- consumer warps.  The per-residual arrays of the CTA's range are contiguous: one L2 prefetch per 128-byte line up front (the point
     // records of a pass are prefetched during the pass before it, below), so that only a warp's first pass waits on HBM for its inputs.
     {
-        const int first_line = r_first >> 5, n_lines = (r_last >> 5) - first_line + 1;
+        const int first_line = (r_first >> 5) + LT_CWARPS, n_lines = (r_last >> 5) - first_line + 1;      // the first pass of every warp has its own loads in flight
         for (int k = threadIdx.x; k < 7 * n_lines; k += LT_CWARPS * 32) {
             const int arr = k / n_lines, r = (first_line + (k - arr * n_lines)) << 5;
-            const void *ptr = arr == 0 ? (const void *) (w.r_pht + r) : arr == 1 ? (const void *) (w.r_job + r) : arr == 2 ? (const void *) (w.r_energy[ctrl->cur] + r)
+            const void *ptr = arr == 0 ? (const void *) (w.r_pht + r) : arr == 1 ? (const void *) (w.r_job + r) : arr == 2 ? (const void *) (w.r_energy[cur] + r)
                             : arr == 3 ? (const void *) (w.r_new_energy + r) : arr == 4 ? (const void *) (w.r_src + r)
-                            : arr == 5 ? (const void *) (w.r_state[ctrl->cur] + r) : (const void *) (w.r_new_state + r);
+                            : arr == 5 ? (const void *) (w.r_state[cur] + r) : (const void *) (w.r_new_state + r);
             prefetch_l2(ptr);
         }
     }
+    LT_STAMPK(26);                                   // prefetches issued
     bool pairs_ready = false;
     // ---- consumer warps
-    const int cur = ctrl->cur, nxt = cur ^ 1;
     bool tma_ok = w.tma_on != 0;
     const double Wm2 = (double) ((float) w.W - 2.f), Hm2 = (double) ((float) w.H - 2.f);
-    for (int c = c0 + warp; c < c1; c += LT_CWARPS) {
+    for (int c = c0 + warp; c < c1; c += LT_CWARPS, c < c1 ? load_headers(c) : (void) 0) {
         const int r = c * 32 + lane;
         const bool in_chunk = r < w.R;
-        const int r_ld = in_chunk ? r : w.R - 1;
-        // all per-residual scalars are requested together (one exposed latency), then the point record
-        const uint32_t pht = __ldg(w.r_pht + r_ld);
-        const int job = __ldg(w.r_job + r_ld);
-        const uint8_t alive_ld = w.r_alive[r_ld];
-        const uint8_t st = in_chunk ? w.r_state[cur][r_ld] : (uint8_t) RES_OOB;
-        const float e_old = w.r_energy[cur][r_ld];
-        uint8_t nst = w.r_new_state[r_ld];
-        float ne = w.r_new_energy[r_ld];
-        const int src = __ldg(w.r_src + r_ld);
+        load_point(c);
+        if (c + LT_CWARPS < c1 && lane < 8) {        // the per-residual scalars of this warp's NEXT pass (one line per array): into L1 now, loaded at the bottom of this pass
+            const int rn = (c + LT_CWARPS) * 32;
+            const void *ptr = lane == 0 ? (const void *) (w.r_pht + rn) : lane == 1 ? (const void *) (w.r_job + rn) : lane == 2 ? (const void *) (w.r_src + rn)
+                            : lane == 3 ? (const void *) (w.r_alive + rn) : lane == 4 ? (const void *) (w.r_state[cur] + rn) : lane == 5 ? (const void *) (w.r_energy[cur] + rn)
+                            : lane == 6 ? (const void *) (w.r_new_state + rn) : (const void *) (w.r_new_energy + rn);
+            prefetch_l1(ptr);
+        }
         const int p = (int) (pht & 0xffffffu), h = (int) ((pht >> 24) & 15u), t = (int) (pht >> 28);
         const bool valid = in_chunk && alive_ld;
-        const uint32_t jd = __ldg(w.job_desc + job);
-        const double rho = w.pt_idepth[p];
-        const double xc = (double) w.pt_x[p], yc = (double) w.pt_y[p];
-        const float4 *colp = reinterpret_cast<const float4 *>(w.pt_colors + (size_t) p * 8);
-        const float4 *wtp = reinterpret_cast<const float4 *>(w.pt_weights + (size_t) p * 8);
-        const float4 c0v = __ldg(colp), c1v = __ldg(colp + 1), w0v = __ldg(wtp), w1v = __ldg(wtp + 1);
-        const uint32_t pht_next = (c + LT_CWARPS < c1) ? __ldg(w.r_pht + min((c + LT_CWARPS) * 32 + lane, w.R - 1)) : pht;     // for the L2 prefetch below
+        const double xc = (double) xcf, yc = (double) ycf;
         const int tr_b = 1 + 7 * ((c - c0 - warp) / LT_CWARPS);
         LT_STAMPK(tr_b);                             // pass start
         if (!pairs_ready) { mbar_wait(pairs_bar, 0); pairs_ready = true; }
         const PairPre *ppp = (t - t_first < 2) ? s_pairs + (t - t_first) * N + h : w.pairs + h * N + t;
         const PairPre &pp = *ppp;
-        // ---- the tiles of this pass: [q_lo, q_last]; the first LT_STAGES of them can be in the ring together
-        const int q_lo = __shfl_sync(0xffffffffu, job, 0), q_last = __shfl_sync(0xffffffffu, job, 31);
-        const int q_hi = min(q_last, q_lo + LT_STAGES - 1);
-        if (tma_ok) {
-            bool ok = true;
-            for (int q = q_lo; q <= q_hi; q++) { const int k = q - q0; ok = ok && lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1)); }
-            tma_ok = __all_sync(0xffffffffu, ok);
-        }
-        LT_STAMPK(tr_b + 1);                         // tiles landed (header loads arrived)
-        if ((w.lt_mode & 1) == 1) {      // development: ring protocol only
-            __syncwarp();
-            if (tma_ok && lane == 0) for (int q = q_lo; q <= q_hi; q++) release(q - q0);
-            if (tma_ok) for (int q = q_hi + 1; q <= q_last; q++) { const int k = q - q0; if (!lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1))) break; __syncwarp(); if (lane == 0) release(k); }
-            continue;
-        }
-        // where this lane's taps come from: its staged tile, or the image itself
-        bool use_smem = tma_ok && job <= q_hi;
-        const int box_x = (int) ((jd >> 4) & 0xfffu) * LT_TILE_W - LT_HALO, box_y = (int) (jd >> 16) * LT_TILE_H - LT_HALO;
-
         double ret = 0.0;
         uint8_t st_out = st;
         float e_out = e_old, neo = -1.f;             // state_NewEnergyWithOutlier = -1 (BA:66)
@@ -440,7 +498,29 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
                 else sample = true;
             }
         }
-        LT_STAMPK(tr_b + 2);                         // projection done
+        LT_STAMPK(tr_b + 1);                         // projection done
+        // ---- the tiles of this pass: [q_lo, q_last]; the first LT_STAGES of them can be in the ring together
+        const int q_lo = __shfl_sync(0xffffffffu, job, 0), q_last = __shfl_sync(0xffffffffu, job, 31);
+        const int q_hi = min(q_last, q_lo + LT_STAGES - 1);
+        if (tma_ok) {
+            bool ok = true;
+            for (int q = q_lo; q <= q_hi; q++) {
+                const int k = q - q0;
+                ok = ok && lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1));
+                if (ok && k < LT_INIT_BOXES && lane == 0) pump(k);
+            }
+            tma_ok = __all_sync(0xffffffffu, ok);
+        }
+        LT_STAMPK(tr_b + 2);                         // tiles landed
+        if ((w.lt_mode & 1) == 1) {      // development: ring protocol only
+            __syncwarp();
+            if (tma_ok && lane == 0) for (int q = q_lo; q <= q_hi; q++) release(q - q0);
+            if (tma_ok) for (int q = q_hi + 1; q <= q_last; q++) { const int k = q - q0; if (!lt_wait_tile(s_tag, full, k % LT_STAGES, q, (uint32_t) ((k / LT_STAGES) & 1))) break; __syncwarp(); if (lane == 0) release(k); }
+            continue;
+        }
+        // where this lane's taps come from: its staged tile, or the image itself
+        bool use_smem = tma_ok && job <= q_hi;
+        const int box_x = (int) ((jd >> 4) & 0xfffu) * LT_TILE_W - LT_HALO, box_y = (int) (jd >> 16) * LT_TILE_H - LT_HALO;
         // ---- taps: from the staged tile when the whole footprint is inside its box, else from the image (image/Array2D.h:265-286)
         int ox = 0, oy = 0, pitch = w.W;
         const float4 *tbase = w.img[t];
@@ -451,6 +531,11 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
             use_smem = lx >= box_x && ly >= box_y && hx + 1 < box_x + LT_BOX_W && hy + 1 < box_y + LT_BOX_H;
             if (use_smem) { ox = box_x; oy = box_y; pitch = LT_BOX_W; tbase = reinterpret_cast<const float4 *>(ring + (size_t) ((job - q0) % LT_STAGES) * LT_STAGE_STRIDE); }
         }
+        if (trace) {     // development: lanes that sample / lanes that fall back to the image (slots 28, 29 of the warp's trace row)
+            const unsigned ms = __ballot_sync(0xffffffffu, sample), mf = __ballot_sync(0xffffffffu, sample && !use_smem);
+            if (lane == 0) { trace[28] += __popc(ms); trace[29] += __popc(mf); }
+        }
+        if ((w.lt_mode & 4) && !use_smem) sample = false;     // development: what the image fallback costs (results are wrong in this mode)
         // ---- per-residual sampling + Jacobians
         float rec[RJ_STRIDE];
         float trow[T_STRIDE];
@@ -476,7 +561,8 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
         LT_STAMPK(tr_b + 3);                         // taps done
         if (c + LT_CWARPS < c1) {                     // the point records of this warp's next pass: on their way to L2 while this one computes
             const int pn = (int) (pht_next & 0xffffffu);
-            prefetch_l2(w.pt_idepth + pn); prefetch_l2(w.pt_x + pn); prefetch_l2(w.pt_y + pn); prefetch_l2(w.pt_colors + (size_t) pn * 8); prefetch_l2(w.pt_weights + (size_t) pn * 8);
+            prefetch_l2(w.pt_idepth + pn);
+            if (lane < 20) prefetch_l2(w.r_pt4 + (size_t) (lane >> 2) * w.R + min((c + LT_CWARPS) * 32 + (lane & 3) * 8, w.R - 1));
         }
         // the taps are in registers: this pass is done with its tiles.  Tiles beyond the ring window (very sparse windows only; their
         // lanes read global memory) still count this pass as a user: wait for them and arrive, one by one.
@@ -613,14 +699,12 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
             }
         }
         LT_STAMPK(tr_b + 5);                         // classification, Jacobians done
+        if (w.lt_mode & 8) { const double es = warp_sum_d(ret); if (lane == 0) w.energy_part[c] = es; continue; }     // development: no per-residual stores
         if (valid) {
             // applyRes (BA:2051-2093), as the candidate that becomes current when the step is accepted
             if (st != RES_OOB && st_out != RES_OOB) { st_out = nst; e_out = ne; }
             w.r_new_state[r] = nst; w.r_new_energy[r] = ne; w.r_new_energy_wo[r] = neo;
             w.r_state[nxt][r] = st_out; w.r_energy[nxt][r] = e_out; w.r_good[nxt][r] = good ? 1 : 0;
-            float4 *t4 = reinterpret_cast<float4 *>(w.T[nxt] + ((size_t) p * N + t) * T_STRIDE);
-#pragma unroll
-            for (int k = 0; k < T_STRIDE / 4; k++) t4[k] = make_float4(trow[4 * k], trow[4 * k + 1], trow[4 * k + 2], trow[4 * k + 3]);
             if (fix && !good) {                      // BA:1595-1598, 1623-1640: non-good residuals are deleted
                 w.r_alive[r] = 0;
                 atomicAdd(&ctrl->num_dropped, 1);
@@ -630,15 +714,47 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
             w.fin_state[src] = st_out; w.fin_energy[src] = e_out; w.fin_alive[src] = (valid && good) ? 1 : 0;
         }
         // ---- the Jacobian record (the reference's efsJ) in the host's residual order: what addToHessianTop is evaluated from
-        // (accumulate role of schur_acc_kernel).  rec[35] = 1 marks a good residual; the others only clear that mark.
+        // (accumulate_kernel).  rec[35] = 1 marks a good residual; the record of any other residual is all zeros.  A record is 144
+        // contiguous bytes but the records of a warp are scattered: the warp stages 16 records at a time in shared memory and writes
+        // them out with 9 consecutive lanes per record (4-5 lines per store instruction instead of 32).
+        {   // the Schur row of (point, target): 64 contiguous bytes per lane, staged and written out by four consecutive lanes per row
+            const int row_or_none = valid ? p * N + t : -1;
+            float4 *mine = s_stage + lane * (T_STRIDE / 4 + 1);       // +1: rows 80 bytes apart, conflict-free for the quarter-warp phases of a 16-byte store
+#pragma unroll
+            for (int k = 0; k < T_STRIDE / 4; k++) mine[k] = make_float4(trow[4 * k], trow[4 * k + 1], trow[4 * k + 2], trow[4 * k + 3]);
+            __syncwarp();
+#pragma unroll 2
+            for (int j = 0; j < T_STRIDE / 4; j++) {
+                const int f = lane + 32 * j, m = f >> 2, k = f & 3;
+                const int rowm = __shfl_sync(0xffffffffu, row_or_none, m);
+                if (rowm >= 0) reinterpret_cast<float4 *>(w.T[nxt] + (size_t) rowm * T_STRIDE)[k] = s_stage[m * (T_STRIDE / 4 + 1) + k];
+            }
+            __syncwarp();
+        }
+#ifndef LT_NO_COOP
+        {
+            const int src_or_none = in_chunk ? src : -1;
+            float4 *mine = s_stage + lane * (RJ_STRIDE / 4);
+#pragma unroll
+            for (int k = 0; k < RJ_STRIDE / 4 - 1; k++) mine[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+            mine[RJ_STRIDE / 4 - 1] = make_float4(rec[32], rec[33], rec[34], good ? 1.f : 0.f);
+            __syncwarp();
+#pragma unroll 3
+            for (int j = 0; j < RJ_STRIDE / 4; j++) {
+                const int f = lane + 32 * j, m = f / (RJ_STRIDE / 4), k = f - m * (RJ_STRIDE / 4);
+                const int srcm = __shfl_sync(0xffffffffu, src_or_none, m);
+                if (srcm >= 0) reinterpret_cast<float4 *>(w.rj[nxt] + (size_t) srcm * RJ_STRIDE)[k] = s_stage[f];
+            }
+            __syncwarp();
+        }
+#else
         if (in_chunk) {
             float4 *rj4 = reinterpret_cast<float4 *>(w.rj[nxt] + (size_t) src * RJ_STRIDE);
-            if (good) {
 #pragma unroll
-                for (int k = 0; k < RJ_STRIDE / 4 - 1; k++) rj4[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
-                rj4[RJ_STRIDE / 4 - 1] = make_float4(rec[32], rec[33], rec[34], 1.f);
-            } else rj4[RJ_STRIDE / 4 - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < RJ_STRIDE / 4 - 1; k++) rj4[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+            rj4[RJ_STRIDE / 4 - 1] = make_float4(rec[32], rec[33], rec[34], good ? 1.f : 0.f);
         }
+#endif
         LT_STAMPK(tr_b + 6);                         // pass done
         // chunk energy (fp64, fixed order)
         const double es = warp_sum_d(ret);

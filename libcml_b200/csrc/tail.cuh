@@ -31,6 +31,10 @@ __host__ __device__ __forceinline__ size_t tail_smem_bytes(int N) {
 }
 
 // element e of sys from the st_out slots (the body of assemble_kernel, one element per call)
+// sum_k!=a slot(a,k)[o_row] + sum_k!=a slot(k,a)[o_col], all loads issued before the (fixed-order) adds
+__device__ __forceinline__ double sum_slots(const double *st, const int N, const int S, const int a, const int o_row, const int o_col) {
+    return gather_seq(st, N, a * N * S + o_row, S, a, -1) + gather_seq(st, N, a * S + o_col, N * S, a, -1);
+}
 __device__ __forceinline__ void assemble_element(const DevWin &w, const bool p2p, const int e) {
     const int N = w.N, n = w.n, nn = n * n, S = st_stride(N);
     const double *st = w.st_out;

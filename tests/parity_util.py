@@ -43,11 +43,16 @@ def record(test, **vals):
 
 
 def pose_errors(w2c, w2c_ref):
-    """(rotation error [absolute, max entry of R - R_ref], translation error RELATIVE to the largest ||t_ref|| of the window).
-    A pose row is 9 rotation entries (row major) followed by the translation."""
+    """(rotation error [absolute, max entry of R - R_ref], translation error RELATIVE to the largest ||t_ref|| of the window, the same after
+    removing the common scale factor of the translations).  A pose row is 9 rotation entries (row major) followed by the translation.
+    Monocular BA cannot observe the scale of the window (DSO only damps it through the nullspace projection, BA:1348-1420), so the part of
+    the solver's conditioning noise that falls into that direction shows up as ONE factor on all translations and inverse depths."""
     a = np.asarray(w2c, np.float64).reshape(-1, 12); b = np.asarray(w2c_ref, np.float64).reshape(-1, 12)
-    tn = max(float(np.linalg.norm(b[:, 9:], axis=1).max()), 1e-30)
-    return float(np.abs(a[:, :9] - b[:, :9]).max()), float(np.linalg.norm(a[:, 9:] - b[:, 9:], axis=1).max() / tn)
+    ta, tb = a[:, 9:], b[:, 9:]
+    tn = max(float(np.linalg.norm(tb, axis=1).max()), 1e-30)
+    scale = float((ta * tb).sum() / max((tb * tb).sum(), 1e-300))
+    return (float(np.abs(a[:, :9] - b[:, :9]).max()), float(np.linalg.norm(ta - tb, axis=1).max() / tn),
+            float(np.linalg.norm(ta - scale * tb, axis=1).max() / tn))
 
 
 def x_noise_floor(gold, pre, N, eps=float(np.finfo(np.float32).eps), trials=16, seed=0):
