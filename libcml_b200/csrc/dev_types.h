@@ -122,6 +122,7 @@ struct DevWin {
     int lt_mode;                   // development: 1 = the consumers only run the ring protocol (TMA streaming floor of the pass)
     int lt_exact;                  // 1 = every pattern pixel is projected in fp64 like the reference (parity study; default: fp32 offsets from the fp64 centre)
     int *bin_key;                  // [R] host order: ((t * n_tiles + tile) * N + h)
+    uint8_t *bin_g;                // [R] host order: shared-memory bank group of the centre texel inside its tile box (bin_interleave_kernel)
     int *bin_hist;                 // [N * n_tiles * N] zero between uses
     int *bin_offs;                 // [N * n_tiles * N] exclusive scan of the histogram
     int *job_of_tile;              // [N * n_tiles] index of the (t, tile) job among the non-empty ones

@@ -247,15 +247,17 @@ public:
     DevBuf<uint8_t> d_fin_state, d_fin_alive;
     DevBuf<float> d_fin_energy;
     DevBuf<float4> d_r_pt4;
+    DevBuf<uint8_t> d_bin_g;
     DevBuf<long long> d_lt_trace;
     DevBuf<unsigned long long> d_ktrace;   // development timeline (CMLBA_KTRACE=1)
     bool want_ktrace = false;
+    int kt_seq = 0; std::vector<int> kt_sites;   // launch slots of the timeline (slot 0: the reset)
     TileMaps tile_maps;           // one tensor map per window frame (re-encoded by build_device_window)
     int n_sm = 148;
     int lt_variant = 0, lt_mode = 0, lt_exact = 0;
     bool use_pdl = true;
     int launch_rc = CMLBA_OK;     // sticky status of the enqueue helpers (kernel launch / NCCL call failed); run() and the stage calls report it
-    int pdl_mask = 48;            // development (CMLBA_PDL_MASK): 1 linearize 2 post 4 accumulate 8 schur 16 stitch 32 assemble 64 solve 128 point step
+    int pdl_mask = 60;            // development (CMLBA_PDL_MASK): 1 linearize 2 post 4 accumulate 8 schur 16 stitch 32 assemble 64 solve 128 point step
     int tail_cluster_max = 0;     // largest cluster tail_kernel can be scheduled with (0: fused tail unavailable -> schur / stitch_pair / assemble)   // development switches (CMLBA_LT_VARIANT, CMLBA_LT_MODE): kernel shape, streaming-only mode
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
         d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj0, d_rj1, d_T0, d_T1, d_dbg, d_acc_bin, d_sc_part, d_stage[MAXF];
@@ -348,7 +350,7 @@ public:
         DevBuf<int> *di[] = {&d_pt_host, &d_pt_num_good, &d_pt_ngood_cur, &d_r_point, &d_res_bin_begin, &d_sc_chunk_host, &d_sc_chunk_begin, &d_sc_chunk_count, &d_host_chunk_begin,
                              &d_bin_key, &d_bin_hist, &d_bin_offs, &d_job_of_tile, &d_r_job, &d_r_src, &d_bin_ticket, &d_job_begin, &d_cta_info};
         for (auto *b : di) b->release();
-        d_job_desc.release(); d_r_pht.release(); d_r_pt4.release(); d_ktrace.release(); d_fin_state.release(); d_fin_alive.release(); d_fin_energy.release();
+        d_job_desc.release(); d_r_pht.release(); d_r_pt4.release(); d_bin_g.release(); d_ktrace.release(); d_fin_state.release(); d_fin_alive.release(); d_fin_energy.release();
         DevBuf<float> *df[] = {&d_pt_x, &d_pt_y, &d_pt_idz, &d_pt_idb, &d_pt_colors, &d_pt_weights, &d_pt_priorF, &d_pt_Hdd, &d_pt_bd, &d_pt_Hcd, &d_pt_HdiF, &d_pt_bdSumF, &d_pt_idh, &d_pt_mrb,
                                &d_r_energy0, &d_r_energy1, &d_r_new_energy, &d_r_new_energy_wo, &d_r_center, &d_rj0, &d_rj1, &d_T0, &d_T1, &d_dbg, &d_acc_bin, &d_sc_part};
         for (auto *b : df) b->release();
@@ -856,7 +858,7 @@ public:
         CK(d_energy_part.reserve(std::max(n_chunks, 1)));
         CK(d_acc_bin.reserve((size_t) N * N * ACC_SLICES * ACC_N));
         CK(d_bin_key.reserve(Rz)); CK(d_bin_hist.reserve(n_keys)); CK(d_bin_offs.reserve(n_keys)); CK(d_job_of_tile.reserve((size_t) N * n_tiles)); CK(d_job_desc.reserve((size_t) N * n_tiles)); CK(d_job_begin.reserve((size_t) N * n_tiles + 1)); CK(d_cta_info.reserve((size_t) LT_INFO_INTS * 1024));
-        CK(d_r_pht.reserve(Rz)); CK(d_r_job.reserve(Rz)); CK(d_r_src.reserve(Rz)); CK(d_r_pt4.reserve(Rz * 5));
+        CK(d_r_pht.reserve(Rz)); CK(d_r_job.reserve(Rz)); CK(d_r_src.reserve(Rz)); CK(d_r_pt4.reserve(Rz * 5)); CK(d_bin_g.reserve(Rz));
         CK(d_fin_state.reserve(Rz)); CK(d_fin_alive.reserve(Rz)); CK(d_fin_energy.reserve(Rz));
         if (!d_bin_ticket.p) { CK(d_bin_ticket.reserve(2)); CK(cudaMemsetAsync(d_bin_ticket.p, 0, 2 * sizeof(int), stream)); }
         CK(d_sc_part.reserve((size_t) std::max(n_sc_chunks, 1) * sc_stride));
@@ -891,7 +893,7 @@ public:
         w.pt_Hdd = d_pt_Hdd.p; w.pt_bd = d_pt_bd.p; w.pt_Hcd = d_pt_Hcd.p; w.pt_HdiF = d_pt_HdiF.p; w.pt_bdSumF = d_pt_bdSumF.p; w.pt_idepth_hessian = d_pt_idh.p; w.pt_max_rel_bs = d_pt_mrb.p;
         w.pt_num_good = d_pt_num_good.p; w.pt_ngood_cur = d_pt_ngood_cur.p; w.pt_step = d_pt_step.p;
         w.r_point = d_r_point.p; w.r_host = d_r_host.p; w.r_target = d_r_target.p; w.res_bin_begin = d_res_bin_begin.p;
-        w.bin_key = d_bin_key.p; w.bin_hist = d_bin_hist.p; w.bin_offs = d_bin_offs.p; w.job_of_tile = d_job_of_tile.p; w.job_desc = d_job_desc.p; w.job_begin = d_job_begin.p; w.cta_info = d_cta_info.p; w.r_pt4 = d_r_pt4.p; w.lt_grid = std::max(1, std::min(std::min(n_sm, 1024), n_chunks));
+        w.bin_key = d_bin_key.p; w.bin_hist = d_bin_hist.p; w.bin_offs = d_bin_offs.p; w.job_of_tile = d_job_of_tile.p; w.job_desc = d_job_desc.p; w.job_begin = d_job_begin.p; w.cta_info = d_cta_info.p; w.r_pt4 = d_r_pt4.p; w.bin_g = d_bin_g.p; w.lt_grid = std::max(1, std::min(std::min(n_sm, 1024), n_chunks));
         w.r_pht = d_r_pht.p; w.r_job = d_r_job.p; w.r_src = d_r_src.p;
         w.bin_ticket = d_bin_ticket.p; w.fin_state = d_fin_state.p; w.fin_alive = d_fin_alive.p; w.fin_energy = d_fin_energy.p;
         w.tma_on = encode_tile_maps() ? 1 : 0;
@@ -1113,6 +1115,7 @@ public:
             CK(cudaMemsetAsync(d_bin_hist.p, 0, (size_t) N * dw.n_tiles * N * sizeof(int), stream));
             bin_count_kernel<<<(dw.R + 255) / 256, 256, 0, stream>>>(dw); launches++;
             bin_scatter_kernel<<<N * N, 256, (size_t) 8 * dw.n_tiles * sizeof(int), stream>>>(dw); launches++;
+            if (!getenv("CMLBA_NO_INTERLEAVE")) { bin_interleave_kernel<<<N * dw.n_tiles, 256, 0, stream>>>(dw); launches++; }
             bin_pack_kernel<<<(dw.R + 255) / 256, 256, 0, stream>>>(dw); launches++;
             bin_finish_kernel<<<1, 256, 0, stream>>>(dw); launches++;
         }
@@ -1129,8 +1132,11 @@ public:
 
     // Kernels of the pass / Gauss-Newton chain are launched with programmatic stream serialization: kernel k+1 may be scheduled while
     // kernel k still runs; its CTAs block in pdl_enter() (griddepcontrol.wait) until kernel k has completed.  CMLBA_NO_PDL=1 turns it off.
+    void kt_patch(DevWin &w) { w.ktrace = d_ktrace.p + 3 * kt_seq; }
+    template <typename T> void kt_patch(T &) {}
     template <typename... KArgs, typename... Args>
     void launch_pdl(int site, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+        if (want_ktrace && d_ktrace.p && dw.ktrace && kt_seq < 127) { kt_seq++; kt_sites.push_back(site); (kt_patch(args), ...); }
         cudaLaunchConfig_t lc = {};
         lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = launch_stream;
         cudaLaunchAttribute at[1];
@@ -1248,7 +1254,7 @@ public:
             CK(d_cap.reserve(1));
             if (g_nccl.AllReduce(d_cap.p, d_cap.p, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, comm, stream) != 0) { set_error("ncclAllReduce (rank alignment) failed"); return CMLBA_ERR_CUDA; }
         }
-        if (want_ktrace) { CK(d_ktrace.reserve(96)); dw.ktrace = d_ktrace.p; ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
+        if (want_ktrace) { CK(d_ktrace.reserve(3 * 128)); dw.ktrace = d_ktrace.p; kt_seq = 0; kt_sites.clear(); ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
         CK(cudaEventRecord(ev0, stream));
         if (!cfg.force_accept) { point_prior_energy_kernel<<<1, 256, 0, stream>>>(dw); launches++; }
         launch_linearize(0, 0); launch_post(0, 0);
@@ -1408,7 +1414,7 @@ public:
         const int l0 = launches;
         for (int i = 0; i < steps; i++) {          // whole pass, two events only
             flush();
-            if (want_ktrace) { CK(d_ktrace.reserve(96)); dw.ktrace = d_ktrace.p; ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
+            if (want_ktrace) { CK(d_ktrace.reserve(3 * 128)); dw.ktrace = d_ktrace.p; kt_seq = 0; kt_sites.clear(); ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
             CK(cudaEventRecord(ev[0], stream));
             launch_linearize(0, 0);
             launch_tail(0);
@@ -1500,6 +1506,12 @@ public:
             for (size_t i = 0; i < frames_.size(); i++) { v.push_back(frames_[i].flagged); v.push_back(frames_[i].num_marginalized); v.push_back(frames_[i].num_residuals_out); v.push_back(frame_residual_count((int) i)); }
             return host_out(v.data(), v.size() * 4, dst, cap, bytes);
         }
+        if (name == "ktrace") { if (!d_ktrace.p) { set_error("CMLBA_KTRACE=1 first"); return CMLBA_ERR_STATE; } CK(cudaSetDevice(device)); CK(cudaStreamSynchronize(stream)); 
+            std::vector<unsigned long long> v(4 * 128, 0);      // [slot][sched, past wait, done, site]
+            std::vector<unsigned long long> raw(3 * 128);
+            CK(cudaMemcpy(raw.data(), d_ktrace.p, raw.size() * 8, cudaMemcpyDeviceToHost));
+            for (int i = 0; i <= kt_seq && i < 128; i++) { for (int k = 0; k < 3; k++) v[4 * i + k] = raw[3 * i + k]; v[4 * i + 3] = i == 0 ? 0 : (unsigned long long) kt_sites[i - 1]; }
+            return host_out(v.data(), (size_t) (kt_seq + 1) * 32, dst, cap, bytes); }
         if (name == "enable_dbg") { want_dbg = true; dirty = true; prepared = false; if (bytes) *bytes = 0; return CMLBA_OK; }
         if (dirty || !d_ctrl.p) { set_error("window not built yet (cmlba_prepare / cmlba_run first)"); return CMLBA_ERR_STATE; }
         CK(cudaSetDevice(device));
@@ -1521,7 +1533,6 @@ public:
             for (int i = 0; i < R; i++) v[i] = (uint8_t) (name == "res_host" ? ((pht[i] >> 24) & 15u) : (pht[i] >> 28));
             return host_out(v.data(), R, dst, cap, bytes);
         }
-        if (name == "ktrace") { if (!d_ktrace.p) { set_error("CMLBA_KTRACE=1 first"); return CMLBA_ERR_STATE; } return copy_out(d_ktrace.p, 96, dst, cap, bytes); }
         if (name == "lt_trace") return copy_out(d_lt_trace.p, (size_t) dw.lt_grid * 16 * 32, dst, cap, bytes);
         if (name == "res_src") return copy_out(d_r_src.p, R, dst, cap, bytes);
         if (name == "res_job") return copy_out(d_r_job.p, R, dst, cap, bytes);

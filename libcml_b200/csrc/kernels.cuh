@@ -46,17 +46,18 @@ __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
 }
 
-// development timeline (CMLBA_KTRACE=1, tools/ktrace.py): one object at the top of every kernel of the chain
+// development timeline (CMLBA_KTRACE=1, tools/ktrace.py): one object at the top of every kernel of the chain; the host points w.ktrace at
+// the slot of the launch (Engine::launch_pdl), slot 0 holds the time of the reset
 struct KTrace {
     unsigned long long *p;
     static __device__ __forceinline__ unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-    __device__ __forceinline__ KTrace(const DevWin &w, const int k) : p(w.ktrace ? w.ktrace + 3 * k : nullptr) { if (p && (threadIdx.x & 31) == 0) atomicMin(p, now()); }
+    __device__ __forceinline__ KTrace(const DevWin &w, const int) : p(w.ktrace) { if (p && (threadIdx.x & 31) == 0) atomicMin(p, now()); }
     __device__ __forceinline__ void begin() const { if (p && (threadIdx.x & 31) == 0) atomicMin(p + 1, now()); }
     __device__ __forceinline__ ~KTrace() { if (p && (threadIdx.x & 31) == 0) atomicMax(p + 2, now()); }
 };
 #define KTRACE_ENTER(k) KTrace kt_(w, (k)); pdl_enter(); kt_.begin()
 // slot 0 (the sampling kernel, which carries no stamps of its own: register budget) gets the time of this reset = the start of the timed region
-__global__ void ktrace_reset_kernel(unsigned long long *kt) { const int i = threadIdx.x; if (i < 96) kt[i] = i < 3 ? KTrace::now() : (i % 3 == 2) ? 0ull : ~0ull; }
+__global__ void ktrace_reset_kernel(unsigned long long *kt) { const int i = threadIdx.x; if (i < 3) kt[i] = KTrace::now(); for (int j = 3 + i; j < 3 * 128; j += 96) kt[j] = (j % 3 == 2) ? 0ull : ~0ull; }
 
 // Frame state -> PRE_worldToCam (DSOFrame::setState, DSOFrame.h:110-124)
 __device__ inline void frame_set_state(FrameDev &f, const double *state, const DevWin &w) {

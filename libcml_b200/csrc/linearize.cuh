@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const DevWin w) {
         }
         const int key = ((t * w.n_tiles) + ty * w.tiles_x + tx) * w.N + h;
         w.bin_key[i] = key;
+        // shared-memory bank group (16-byte units, 8 per 128-byte row of banks) of the centre texel inside the tile's staged box
+        w.bin_g[i] = (uint8_t) ((((int) Kv - (ty * LT_TILE_H - LT_HALO)) * LT_BOX_W + ((int) Ku - (tx * LT_TILE_W - LT_HALO))) & 7);
         atomicAdd(w.bin_hist + key, 1);
     }
     __shared__ int s_last;
@@ -215,6 +217,45 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const DevWin w) {
             w.r_job[pos] = w.job_of_tile[t * nt + tile];
             w.r_src[pos] = i;
         }
+    }
+}
+
+// step 2a: inside every tile job the residuals are re-ordered so that consecutive lanes cycle through the eight bank groups of their centre
+// texel.  All lanes of a warp apply (nearly) the same pattern offsets, so the 32 taps of eight consecutive lanes then fall into eight
+// different 16-byte bank groups: the LDS.128 of a quarter warp is conflict-free instead of ~2.6-way conflicted (random positions).
+// Order inside a group = sorted order (deterministic).  One CTA per (target, tile); jobs larger than LT_IL_MAX keep their order.
+constexpr int LT_IL_MAX = 1024;
+__global__ void __launch_bounds__(256) bin_interleave_kernel(const DevWin w) {
+    const int job = w.job_of_tile[blockIdx.x];
+    if (job < 0) return;
+    const int jb = w.job_begin[job], n = w.job_begin[job + 1] - jb;
+    if (n < 16 || n > LT_IL_MAX) return;
+    __shared__ uint32_t s_pht[LT_IL_MAX];
+    __shared__ int s_src[LT_IL_MAX];
+    __shared__ short s_rank[LT_IL_MAX];
+    __shared__ uint8_t s_g[LT_IL_MAX];
+    __shared__ int s_cnt[8];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += 256) { const int src = w.r_src[jb + i]; s_pht[i] = w.r_pht[jb + i]; s_src[i] = src; s_g[i] = w.bin_g[src]; }
+    __syncthreads();
+    const int i0 = tid * 4;                          // blocked assignment keeps the sorted order inside a group
+    for (int g = 0; g < 8; g++) {
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) c += (i0 + k < n && s_g[i0 + k] == g) ? 1 : 0;
+        int tot;
+        int run = block_excl_scan_256(c, &tot);
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + k < n && s_g[i0 + k] == g) s_rank[i0 + k] = (short) run++;
+        if (tid == 0) s_cnt[g] = tot;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        const int g = s_g[i], j = s_rank[i];
+        int pos = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) { const int cq = s_cnt[q]; pos += min(cq, j) + ((q < g && cq > j) ? 1 : 0); }
+        w.r_pht[jb + pos] = s_pht[i]; w.r_src[jb + pos] = s_src[i];
     }
 }
 

@@ -8,7 +8,9 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
 timeout 120 python tools/gpu_check.py tiny > gpurun_out/${tag}_check_tiny.log 2>&1
 echo "gpu_check rc=$?" >> gpurun_out/${tag}_check_tiny.log
+rm -f gpurun_out/parity_report.jsonl
 timeout 900 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/${tag}_pytest.log 2>&1
+cp gpurun_out/parity_report.jsonl gpurun_out/${tag}_parity_report.jsonl 2>/dev/null
 echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -5 gpurun_out/${tag}_pytest.log
 if [ "$mode" == "variants" ]; then
@@ -16,7 +18,7 @@ if [ "$mode" == "variants" ]; then
     for nt in 0; do
       if [ $nt == 1 ]; then export CMLBA_NO_TMA=1; else unset CMLBA_NO_TMA; fi
       CMLBA_LT_VARIANT=$v timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/${tag}_bench_v${v}_$nt.json 2> gpurun_out/${tag}_bench_v${v}_$nt.err
-      python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_v${v}_$nt.json'));print('variant $v no_tma=$nt', round(d['ms_per_step']*1e3,1), 'lin', round(d['kernel_ms']['linearize_accumulate']*1e3,1), 'warm', round(d['kernel_ms']['linearize_accumulate_l2_warm']*1e3,1), d['run'], round(d['e2e']['ms_per_step'],3))"
+      python -c "import json;d=json.load(open('gpurun_out/${tag}_bench_v${v}_$nt.json'));print('variant $v no_tma=$nt', round(d['ms_per_step']*1e3,1), 'lin', round(d['kernel_ms']['linearize']*1e3,1), 'warm', round(d['kernel_ms']['linearize_l2_warm']*1e3,1), d['run'], round(d['e2e']['ms_per_step'],3))"
     done
   done
   unset CMLBA_NO_TMA
@@ -31,6 +33,6 @@ echo "bench rc=$?"
 cat gpurun_out/${tag}_bench.json | head -c 3000
 if [ "$mode" != "quick" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${tag}_ncu_l.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'linearize_tile|tail_kernel|schur|stitch|assemble|solve|post_lin|point_step|bin_' -s 20 -c 14 -o gpurun_out/${tag}_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${tag}_ncu_f.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'linearize_tile|accumulate|schur|stitch|assemble|solve|post_lin|point_step|bin_' -s 24 -c 16 -o gpurun_out/${tag}_prof python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/${tag}_ncu_f.log 2>&1
   ls -la gpurun_out/${tag}_* | tail -20
 fi

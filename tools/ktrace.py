@@ -1,5 +1,7 @@
-"""Development aid: device timeline of one timed pass (CMLBA_KTRACE=1): when the first CTA of every kernel was scheduled, when it got past its
-dependency wait, when its last warp finished (globaltimer, ns relative to the first stamp).   CMLBA_KTRACE=1 python tools/ktrace.py [workload] [run]"""
+"""Development aid: device timeline (CMLBA_KTRACE=1) of the last timed pass of cmlba_bench_pass, or of a whole run(): per launch, when its first
+CTA was scheduled, when the first CTA got past its dependency wait, when its last warp finished (globaltimer, ns after the reset kernel that opens
+the region).  The sampling kernel carries no stamps (register budget): it ends where the next kernel gets past its wait.
+    CMLBA_KTRACE=1 python tools/ktrace.py [workload] [pass|run]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,7 +10,24 @@ os.environ.setdefault("CMLBA_KTRACE", "1")
 from libcml_b200 import DSOBundleAdjustment, synth
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 mode = sys.argv[2] if len(sys.argv) > 2 else "pass"
-names = ["(timed region starts)", "accumulate", "schur", "stitch", "assemble", "solve", "point_step", "post_linearize", "pack_post", "restore_state"]
+SITES = {0: "(region starts)", 1: "linearize_tile", 2: "post_linearize/pack_post", 4: "accumulate", 8: "schur", 16: "stitch_pair", 32: "assemble", 64: "solve", 128: "point_step/restore_state"}
+
+
+def show(ba, title):
+    kt = ba.read("ktrace", np.uint64).reshape(-1, 4).astype(np.int64)
+    t0 = kt[0, 0]
+    print(title)
+    prev_done = 0
+    for i in range(kt.shape[0]):
+        sched, wait, done, site = kt[i]
+        name = SITES.get(int(site), str(site))
+        if done <= 0:
+            print(f"  {i:3d} {name:26s} (no stamps)")
+            continue
+        print(f"  {i:3d} {name:26s} scheduled {sched - t0:8d}  past wait {wait - t0:8d}  done {done - t0:8d}   busy {done - wait:6d}   idle before {wait - t0 - prev_done:6d} ns")
+        prev_done = max(prev_done, done - t0)
+
+
 win = synth.make_config(wl)
 ba = DSOBundleAdjustment(device=0)
 cams = ba.loadWindow(win)
@@ -16,18 +35,8 @@ if mode == "pass":
     ba.prepare(cams)
     for cold in (True, False):
         br = ba.benchPass(5, 3, cold)
-        kt = ba.read("ktrace", np.uint64).reshape(-1, 3).astype(np.int64)
-        live = [k for k in range(len(names)) if kt[k, 2] > 0]
-        t0 = min(kt[k, 0] for k in live)
-        print(f"{'cold' if cold else 'warm'} pass: {br.ms_pass * 1e3:.1f} us by events (timeline of the last timed pass below)")
-        for k in sorted(live, key=lambda k: kt[k, 0]):
-            print(f"  {names[k]:15s} scheduled {kt[k, 0] - t0:7d}  past wait {kt[k, 1] - t0:7d}  done {kt[k, 2] - t0:7d}   busy {kt[k, 2] - kt[k, 1]:6d} ns")
+        show(ba, f"{'cold' if cold else 'warm'} pass: {br.ms_pass * 1e3:.1f} us by events; timeline of the last timed pass:")
 else:
     ba.run(cams, iterations=int(win["iterations"][0]))
     r = ba.last_result
-    kt = ba.read("ktrace", np.uint64).reshape(-1, 3).astype(np.int64)
-    live = [k for k in range(len(names)) if kt[k, 2] > 0]
-    t0 = min(kt[k, 0] for k in live)
-    print(f"run: gpu_ms {r.gpu_ms:.3f}, {r.kernel_launches} launches, {r.iterations_done} iterations; first schedule / last completion per kernel type")
-    for k in sorted(live, key=lambda k: kt[k, 0]):
-        print(f"  {names[k]:15s} first scheduled {kt[k, 0] - t0:7d}  last done {kt[k, 2] - t0:7d}")
+    show(ba, f"run: gpu_ms {r.gpu_ms:.3f}, {r.kernel_launches} launches, {r.iterations_done} iterations")
