@@ -118,6 +118,7 @@ struct DevWin {
     float4 *r_pt4;                 // [5][R] per-residual copies of the point constants in the sorted order: (x, y, -, -), colours[0..3], [4..7], weights[0..3], [4..7]
     int *cta_info;                 // [lt_grid][LT_INFO_INTS] q0, q1, first target, -, descriptors[4], users[4] of the first tiles, tile table (linearize.cuh)
     long long *lt_trace;           // development (lt_mode & 2): [lt_grid][16 warps][32] SM clock stamps of the first passes
+    unsigned long long *ktrace_base;   // first slot of the timeline buffer (phase stamps of solve_kernel live behind the launch slots)
     unsigned long long *ktrace;    // development (CMLBA_KTRACE): [kernel][3] globaltimer of first CTA scheduled / first CTA past its dependency wait / last warp done
     int lt_mode;                   // development: 1 = the consumers only run the ring protocol (TMA streaming floor of the pass)
     int lt_exact;                  // 1 = every pattern pixel is projected in fp64 like the reference (parity study; default: fp32 offsets from the fp64 centre)

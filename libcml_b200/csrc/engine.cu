@@ -1127,7 +1127,7 @@ public:
 
     // ------------------------------------------------------------------ kernel sequences
     size_t stitch_smem() const { const int N = dw.N, NB = 8 * N; return sizeof(double) * ((size_t) 8 * NB + N * 64 + NB + 40 + ACC_N + 128 + N * 64); }
-    size_t solve_smem() const { const int n = dw.n; return sizeof(double) * ((size_t) n * n + 4 * n + 256); }
+    size_t solve_smem() const { return sizeof(double) * solve_smem_doubles(dw.n); }
     size_t schur_smem() const { return schur_smem_bytes(dw.N); }
 
     // Kernels of the pass / Gauss-Newton chain are launched with programmatic stream serialization: kernel k+1 may be scheduled while
@@ -1254,7 +1254,7 @@ public:
             CK(d_cap.reserve(1));
             if (g_nccl.AllReduce(d_cap.p, d_cap.p, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, comm, stream) != 0) { set_error("ncclAllReduce (rank alignment) failed"); return CMLBA_ERR_CUDA; }
         }
-        if (want_ktrace) { CK(d_ktrace.reserve(3 * 128)); dw.ktrace = d_ktrace.p; kt_seq = 0; kt_sites.clear(); ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
+        if (want_ktrace) { CK(d_ktrace.reserve(3 * 128 + 32)); dw.ktrace = d_ktrace.p; dw.ktrace_base = d_ktrace.p; kt_seq = 0; kt_sites.clear(); ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
         CK(cudaEventRecord(ev0, stream));
         if (!cfg.force_accept) { point_prior_energy_kernel<<<1, 256, 0, stream>>>(dw); launches++; }
         launch_linearize(0, 0); launch_post(0, 0);
@@ -1414,7 +1414,7 @@ public:
         const int l0 = launches;
         for (int i = 0; i < steps; i++) {          // whole pass, two events only
             flush();
-            if (want_ktrace) { CK(d_ktrace.reserve(3 * 128)); dw.ktrace = d_ktrace.p; kt_seq = 0; kt_sites.clear(); ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
+            if (want_ktrace) { CK(d_ktrace.reserve(3 * 128 + 32)); dw.ktrace = d_ktrace.p; dw.ktrace_base = d_ktrace.p; kt_seq = 0; kt_sites.clear(); ktrace_reset_kernel<<<1, 96, 0, stream>>>(d_ktrace.p); }
             CK(cudaEventRecord(ev[0], stream));
             launch_linearize(0, 0);
             launch_tail(0);
@@ -1506,11 +1506,12 @@ public:
             for (size_t i = 0; i < frames_.size(); i++) { v.push_back(frames_[i].flagged); v.push_back(frames_[i].num_marginalized); v.push_back(frames_[i].num_residuals_out); v.push_back(frame_residual_count((int) i)); }
             return host_out(v.data(), v.size() * 4, dst, cap, bytes);
         }
-        if (name == "ktrace") { if (!d_ktrace.p) { set_error("CMLBA_KTRACE=1 first"); return CMLBA_ERR_STATE; } CK(cudaSetDevice(device)); CK(cudaStreamSynchronize(stream)); 
+        if (name == "ktrace" || name == "ktrace_solve") { if (!d_ktrace.p) { set_error("CMLBA_KTRACE=1 first"); return CMLBA_ERR_STATE; } CK(cudaSetDevice(device)); CK(cudaStreamSynchronize(stream)); 
             std::vector<unsigned long long> v(4 * 128, 0);      // [slot][sched, past wait, done, site]
-            std::vector<unsigned long long> raw(3 * 128);
+            std::vector<unsigned long long> raw(3 * 128 + 32);
             CK(cudaMemcpy(raw.data(), d_ktrace.p, raw.size() * 8, cudaMemcpyDeviceToHost));
             for (int i = 0; i <= kt_seq && i < 128; i++) { for (int k = 0; k < 3; k++) v[4 * i + k] = raw[3 * i + k]; v[4 * i + 3] = i == 0 ? 0 : (unsigned long long) kt_sites[i - 1]; }
+            if (name == "ktrace_solve") return host_out(raw.data() + 3 * 128, 32 * 8, dst, cap, bytes);
             return host_out(v.data(), (size_t) (kt_seq + 1) * 32, dst, cap, bytes); }
         if (name == "enable_dbg") { want_dbg = true; dirty = true; prepared = false; if (bytes) *bytes = 0; return CMLBA_OK; }
         if (dirty || !d_ctrl.p) { set_error("window not built yet (cmlba_prepare / cmlba_run first)"); return CMLBA_ERR_STATE; }

@@ -606,8 +606,25 @@ namespace cmlba {
 // ------------------------------------------------------------------------------------------------
 // Reduced camera system: assemble, damp, Jacobi-scale, LDL^T (lower triangle, like Eigen's default), solve,
 // orthogonalise against the gauge nullspaces, frame steps + new frame states + pair constants, xAd.
+__host__ __device__ __forceinline__ bool solve_stages_hs(const int n) { return ((size_t) 2 * n * n + 5 * n + 256 + 8 * MAXF) * sizeof(double) <= (size_t) 200 * 1024; }
+__host__ __device__ __forceinline__ size_t solve_smem_doubles(const int n) { return (size_t) (solve_stages_hs(n) ? 2 : 1) * n * n + 5 * n + 256 + 8 * MAXF; }
+
+// 1 / x for a normal, finite x: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps (quadratic: >= 52 bits up to rounding, <= 2 ulp).
+// The IEEE division is a ~30-instruction dependent chain and the LDL^T pivots are strictly sequential.
+__device__ __forceinline__ double rcp_f64(const double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
 __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int respect_done) {
     KTRACE_ENTER(5);
+    // development: phase stamps of the LAST solve of a traced run (tools/ktrace.py), 32 slots behind the launch slots
+#define SOLVE_STAMP(k) do { if (kt_.p && tid_ == 0) w.ktrace_base[3 * 128 + (k)] = KTrace::now(); } while (0)
+    const int tid_ = threadIdx.x;
+    SOLVE_STAMP(0);
     Ctrl *ctrl = w.ctrl;
     if (respect_done && ctrl->done) return;
     extern __shared__ __align__(16) double smd[];
@@ -622,9 +639,18 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
     if (w.p2p_on && w.world > 1) {   // sum of the ranks' partial systems over NVLink (replaces ncclAllReduce + its launch)
         if (!p2p_reduce(w, w.sys, 2 * nn + 2 * n)) { if (tid == 0) { ctrl->failed = 1; ctrl->pad0 = 1; ctrl->done = 1; } return; }
     }
-    // H <- HA (already completed by assemble_kernel)
-    for (int e = tid; e < nn; e += 256) H[e] = sysHA[e];
+    // H <- HA, scratch <- H_sc (already completed by assemble_kernel): both matrices are requested together, eight elements per thread in flight
+    const bool stage_hs = solve_stages_hs(n);   // large windows (N > 11): the Schur part is read from global memory where it is used
+    const double *Hs = stage_hs ? H + nn + 4 * n + 256 + m : sysHS;      // [n][n] Schur part, staged next to the system (solve_smem_doubles() reserves it)
+    for (int e0 = 0; e0 < nn; e0 += 256 * 4) {
+        double va[4], vs[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int e = e0 + k * 256 + tid; va[k] = e < nn ? sysHA[e] : 0.0; vs[k] = (stage_hs && e < nn) ? sysHS[e] : 0.0; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int e = e0 + k * 256 + tid; if (e < nn) { H[e] = va[k]; if (stage_hs) (H + nn + 4 * n + 256 + m)[e] = vs[k]; } }
+    }
     __syncthreads();
+    SOLVE_STAMP(1);   // system loaded
     const double lambda = w.fix_lambda ? w.fixed_lambda : ctrl->lambda;
     const int wid = tid >> 5, lane = tid & 31;
     // b = bL + bM + bA - b_sc ; H = HL + HM + HA (BA:1299-1300); HL = diag(prior), bL = prior*delta_prior (BA:1857-1865)
@@ -653,17 +679,19 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
         if (w.has_HM) v += w.HM[e];
         if (r == c && r >= 4) v += w.frames[(r - 4) >> 3].prior[(r - 4) & 7];
         if (r == c) v *= (1.0 + lambda);                        // BA:1306-1308
-        v -= sysHS[e] * (1.0 / (1.0 + lambda));                 // BA:1309
+        v -= Hs[e] * (1.0 / (1.0 + lambda));                    // BA:1309
         H[e] = v;
     }
     __syncthreads();
     for (int e = tid; e < n; e += 256) s[e] = 1.0 / sqrt(H[e * n + e] + 10.0);   // BA:1312
     __syncthreads();
+    SOLVE_STAMP(2);   // damped, scale factors
     // scaled system on the trailing m x m block (calibration fixed, BA:1319); only the lower triangle is read
 #define AA(r, c) H[(size_t) (4 + (r)) * n + 4 + (c)]
     for (int e = tid; e < m * m; e += 256) { const int r = e / m, c = e % m; if (r >= c) AA(r, c) = AA(r, c) * s[4 + r] * s[4 + c]; }
     for (int e = tid; e < m; e += 256) x[e] = s[4 + e] * b[4 + e];
     __syncthreads();
+    SOLVE_STAMP(3);   // scaled
     // LDL^T without pivoting (SPD after damping + priors), right-looking in panels of 8 columns (= one frame).  The right-hand
     // side rides along as an extra row, so the forward substitution L y = rhs costs no pass of its own:
     //   (1) warp 0 factors the 8x8 diagonal block in registers (shuffles) and forward-substitutes the panel's 8 rhs entries,
@@ -679,7 +707,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const double dk = __shfl_sync(0xffffffffu, a[k], k);
-                const double idk = 1.0 / dk;                       // one reciprocal per pivot; rows are scaled by multiplication
+                const double idk = rcp_f64(dk);                    // one reciprocal per pivot (on the critical path of all 8N pivots); rows are scaled by multiplication
                 if (lane == k) invd[k0 + k] = idk;
                 const double lrk = a[k] * idk;
                 if (lane > k) a[k] = lrk;
@@ -751,6 +779,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
         }
         __syncthreads();
     }
+    SOLVE_STAMP(4);   // factorised + forward
     // z = y / d, then backward L^T x = z: column dots over the rows below (one warp per column), 8x8 block by shuffles
     for (int e = tid; e < m; e += 256) x[e] = x[e] * invd[e];
     __syncthreads();
@@ -777,20 +806,27 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
         __syncthreads();
     }
 #undef AA
+    SOLVE_STAMP(5);   // backward
     // x = SVecI * y, calibration entries 0 (BA:1314-1319)
     for (int e = tid; e < n; e += 256) b[e] = (e >= 4) ? s[e] * x[e - 4] : 0.0;   // b now holds x
     __syncthreads();
     if (ctrl->iteration >= 2) {                                  // orthogonalize(x) (BA:1332-1334), projector precomputed on the host
-        for (int e = wid; e < n; e += 8) {
+        // P is symmetric: thread (g, r) sums P[c][r] * x[c] over the g-th slice of c (coalesced over r, eight loads in flight), then the slices are added
+        const int groups = max(1, min(256 / n, 8)), chunk = (n + groups - 1) / groups, g = tid / n, r = tid - g * n;
+        if (g < groups) {
             double v = 0.0;
-            for (int c = lane; c < n; c += 32) v += w.Pns[(size_t) e * n + c] * b[c];
-            v = warp_sum_d(v);
-            if (lane == 0) s[e] = b[e] - v;
+            const int c_lo = g * chunk, c_hi = min(n, c_lo + chunk);
+#pragma unroll 8
+            for (int c = c_lo; c < c_hi; c++) v += w.Pns[(size_t) c * n + r] * b[c];
+            red[g * n + r] = v;
         }
+        __syncthreads();
+        if (tid < n) { double v = 0.0; for (int q = 0; q < groups; q++) v += red[q * n + tid]; s[tid] = b[tid] - v; }
         __syncthreads();
         for (int e = tid; e < n; e += 256) b[e] = s[e];
         __syncthreads();
     }
+    SOLVE_STAMP(6);   // orthogonalised
     for (int e = tid; e < n; e += 256) w.x[e] = b[e];
     // statistics (BA:1415-1425)
     if (tid < 32) {
@@ -799,6 +835,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
         v = warp_sum_d(v);
         if (tid == 0) ctrl->stats[4] = sqrt(v);
     }
+    SOLVE_STAMP(7);
     // frame steps + states (BA:1433-1441, 957-973; DSOFrame::doStepFromBackup) and convergence sums
     if (tid < N) {
         FrameDev &f = w.frames[tid];
@@ -823,6 +860,7 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
         }
         ctrl->sumA = sumA / N; ctrl->sumB = sumB / N; ctrl->sumT = sumT / N; ctrl->sumR = sumR / N;
     }
+    SOLVE_STAMP(8);   // frame states
     // xAd[h*N+t] = x_h^T AH + x_t^T AT (BA:1447)
     for (int e = tid; e < N * N * 8; e += 256) {
         const int ht = e >> 3, c = e & 7, h = ht / N, t = ht % N;
@@ -834,7 +872,10 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
         for (int r = 0; r < 8; r++) v += b[4 + 8 * h + r] * pa[r] + b[4 + 8 * t + r] * pt[r];
         w.xAd[e] = v;
     }
+    SOLVE_STAMP(9);   // xAd
     for (int e = tid; e < N * N; e += 256) pair_precompute(w, e / N, e % N);
+    SOLVE_STAMP(10);
+#undef SOLVE_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -40,3 +40,6 @@ else:
     ba.run(cams, iterations=int(win["iterations"][0]))
     r = ba.last_result
     show(ba, f"run: gpu_ms {r.gpu_ms:.3f}, {r.kernel_launches} launches, {r.iterations_done} iterations")
+    st = ba.read("ktrace_solve", np.uint64).astype(np.int64)[:11]
+    names = ["enter", "system loaded", "damped", "scaled", "factorised+forward", "backward", "orthogonalised", "x stored", "frame states", "xAd", "pair constants"]
+    print("last solve_kernel, ns since its entry: " + ", ".join(f"{n} {st[k] - st[0]}" for k, n in enumerate(names) if st[k] > 0))
