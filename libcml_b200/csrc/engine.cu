@@ -257,7 +257,7 @@ public:
     int lt_variant = 0, lt_mode = 0, lt_exact = 0;
     bool use_pdl = true;
     int launch_rc = CMLBA_OK;     // sticky status of the enqueue helpers (kernel launch / NCCL call failed); run() and the stage calls report it
-    int pdl_mask = 60;            // development (CMLBA_PDL_MASK): 1 linearize 2 post 4 accumulate 8 schur 16 stitch 32 assemble 64 solve 128 point step
+    int pdl_mask = 316;            // development (CMLBA_PDL_MASK): 1 linearize 2 post 4 accumulate 8 schur 16 stitch 32 assemble 64 solve 128 point step 256 peer all-reduce
     int tail_cluster_max = 0;     // largest cluster tail_kernel can be scheduled with (0: fused tail unavailable -> schur / stitch_pair / assemble)   // development switches (CMLBA_LT_VARIANT, CMLBA_LT_MODE): kernel shape, streaming-only mode
     DevBuf<float> d_pt_x, d_pt_y, d_pt_idz, d_pt_idb, d_pt_colors, d_pt_weights, d_pt_priorF, d_pt_Hdd, d_pt_bd, d_pt_Hcd, d_pt_HdiF, d_pt_bdSumF, d_pt_idh, d_pt_mrb,
         d_r_energy0, d_r_energy1, d_r_new_energy, d_r_new_energy_wo, d_r_center, d_rj0, d_rj1, d_T0, d_T1, d_dbg, d_acc_bin, d_sc_part, d_stage[MAXF];
@@ -1234,7 +1234,7 @@ public:
     }
 
     int allreduce_system() {
-        if (dw.p2p_on) { p2p_allreduce_kernel<<<(2 * dw.n * dw.n + 2 * dw.n + 255) / 256, 256, 0, stream>>>(dw, 0); launches++; return CMLBA_OK; }
+        if (dw.p2p_on) { launch_pdl(256, p2p_allreduce_kernel, dim3((2 * dw.n * dw.n + 2 * dw.n + 255) / 256), dim3(256), 0, dw, 0); return CMLBA_OK; }
         const size_t cnt = (size_t) 2 * dw.n * dw.n + 2 * dw.n;
         const int rc = g_nccl.AllReduce(d_sys.p, d_sys.p, cnt, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, stream);
         if (rc != 0) { set_error("ncclAllReduce failed"); return CMLBA_ERR_CUDA; }

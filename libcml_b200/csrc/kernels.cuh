@@ -477,6 +477,7 @@ __device__ __forceinline__ bool p2p_reduce(const DevWin &w, double *dst, const i
     return true;
 }
 __global__ void __launch_bounds__(256) p2p_allreduce_kernel(const DevWin w, const int respect_done) {
+    pdl_enter();                                     // launched while assemble_kernel still runs; its own pushes must be complete before the sums are stored
     if (respect_done && w.ctrl->done) return;
     if (!p2p_reduce(w, w.sys, 2 * w.n * w.n + 2 * w.n) && threadIdx.x == 0) { w.ctrl->failed = 1; w.ctrl->pad0 = 1; w.ctrl->done = 1; }
 }

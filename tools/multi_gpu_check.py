@@ -52,26 +52,29 @@ def main():
     r1 = ref.last_result
     fr1 = ref.getFrames(); pts1 = ref.getPoints(); rs1 = ref.getResiduals()
     rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-30))
+    # tolerances: the shards sum their fp32 accumulators in a different order than the single-GPU run (1 ulp on the entries of H); the reduced
+    # system's conditioning (~1e11, tests/test_oracle_golden.py::test_forward_error_floor_of_the_reference_system) turns that into ~1e-6 on the
+    # poses and ~1e-5 on inverse depths with 8 shards (measured: profiles/r02_multi_gpu.md).  Gates: 10x below the 1e-4 of the parity tests.
     errs = []
     if ok != ok1: errs.append("ok flag")
     if r.iterations_done != r1.iterations_done: errs.append(f"iterations {r.iterations_done} vs {r1.iterations_done}")
     e_pose = rel(fr["world_to_cam"], fr1["world_to_cam"]); e_aff = float(np.abs(fr["affine"] - fr1["affine"]).max()); e_th = rel(fr["energy_th"], fr1["energy_th"])
-    if e_pose > 1e-6: errs.append(f"poses {e_pose:.2e}")
-    if e_aff > 1e-6: errs.append(f"affine {e_aff:.2e}")
-    if e_th > 1e-6: errs.append(f"frameEnergyTH {e_th:.2e}")
+    if e_pose > 1e-5: errs.append(f"poses {e_pose:.2e}")
+    if e_aff > 1e-5: errs.append(f"affine {e_aff:.2e}")
+    if e_th > 1e-5: errs.append(f"frameEnergyTH {e_th:.2e}")
     idx1 = {int(i): k for k, i in enumerate(pts1["id"])}
     mine_ids = [int(i) for i in pts["id"]]
     missing = [i for i in mine_ids if i not in idx1]
     if missing: errs.append(f"{len(missing)} points alive here but not in the single-GPU run")
     sel1 = np.array([idx1[i] for i in mine_ids if i in idx1], dtype=np.int64)
     e_id = rel(pts["idepth"][[k for k, i in enumerate(mine_ids) if i in idx1]], pts1["idepth"][sel1]) if sel1.size else 0.0
-    if e_id > 1e-5: errs.append(f"idepth {e_id:.2e}")
+    if e_id > 1e-4: errs.append(f"idepth {e_id:.2e}")
     own = set(int(i) for i in sel)
     mine_res = set(zip(rs["point_id"].tolist(), rs["target_frame_id"].tolist()))
     their_res = set((p, t) for p, t in zip(rs1["point_id"].tolist(), rs1["target_frame_id"].tolist()) if p in own)
     if len(mine_res ^ their_res) > 0: errs.append(f"{len(mine_res ^ their_res)} residuals differ")
     e_en = abs(r.energy_last - r1.energy_last) / r1.energy_last
-    if e_en > 1e-6: errs.append(f"energy {e_en:.2e}")
+    if e_en > 1e-5: errs.append(f"energy {e_en:.2e}")
     print(f"rank {rank}/{world}: iterations {r.iterations_done}, poses {e_pose:.2e}, affine {e_aff:.2e}, th {e_th:.2e}, idepth {e_id:.2e}, energy {e_en:.2e}, "
           f"residuals {len(mine_res)} (diff {len(mine_res ^ their_res)}), launches {r.kernel_launches}: {'OK' if not errs else 'FAIL ' + '; '.join(errs)}", flush=True)
     flag = torch.tensor([len(errs)], device="cuda"); dist.all_reduce(flag)
