@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "cmlba_ref")
 
 
-X_FLOOR_FACTOR = 8      # x is gated at this multiple of the reference system's own measured noise floor (parity_util.x_noise_floor)
+X_FLOOR_FACTOR = 4      # x is gated at this multiple of the reference system's own measured noise floor (parity_util.x_noise_floor)
 
 
 def _ba(**kw):
@@ -234,13 +234,15 @@ def test_against_reference_summary_full_size(cfg):
            per_target_count_diff=flips_lb, identical_residual_set=float(same_set), alive16_mismatch=int((alive16 != mine_alive16).sum()),
            iterations_done=ba.last_result.iterations_done, accepted_ref=int(S[f"{cfg}_accepted"][0]),
            energy_sum_rel_err=abs(energy - float(S[f"{cfg}_energy"][0])) / float(S[f"{cfg}_energy"][0]))
-    assert er < 1e-4 and ets < 1e-4 and et < 3e-4
-    assert ea < 1e-4 * max(1.0, np.abs(S[f"{cfg}_affine"]).max())
-    assert ed < 1e-3
-    assert abs(key.size - n_ref) <= max(1, n_ref // 1000) and flips_lb <= max(1, n_ref // 1000)
-    assert (alive16 != mine_alive16).sum() <= max(1, alive16.size // 1000)
-    assert abs(len(pts["id"]) - int(S[f"{cfg}_n_alive_pts"][0])) <= max(1, P // 1000)
-    assert abs(energy - float(S[f"{cfg}_energy"][0])) / float(S[f"{cfg}_energy"][0]) < 1e-3
+    # gates ~4x above the measured errors (profiles/r02_parity_report.txt: rotations <= 7.5e-8, translations <= 2.5e-5 raw / 8e-7 without the
+    # common scale, inverse depths <= 2.5e-5, energies <= 8e-6, surviving sets identical on all four configurations)
+    assert er < 1e-6 and ets < 1e-5 and et < 1e-4
+    assert ea < 1e-5 * max(1.0, np.abs(S[f"{cfg}_affine"]).max())
+    assert ed < 1e-4
+    assert abs(key.size - n_ref) <= n_ref // 10000 and flips_lb <= n_ref // 10000          # >= 99.99 % of the surviving set (measured: identical, sha1 equal)
+    assert (alive16 != mine_alive16).sum() == 0
+    assert len(pts["id"]) == int(S[f"{cfg}_n_alive_pts"][0])
+    assert abs(energy - float(S[f"{cfg}_energy"][0])) / float(S[f"{cfg}_energy"][0]) < 1e-4
     ba.close()
 
 
