@@ -171,6 +171,14 @@ int cmlba_get_outliers(const cmlba_handle *h, int64_t *point_id, int *n);
 /* surviving residuals: (point_id, target frame_id, state, energy) */
 int cmlba_get_residuals(const cmlba_handle *h, int64_t *point_id, int64_t *target_frame_id, int32_t *state, double *energy);
 
+/* The 19 Statistic series the class declares (BA.h:215-233), latest value of each, in declaration order; cmlba_statistic_name(i) returns
+ * the reference's own name of series i ("P Energy ( All residuals )", ..., "Num Linearized").  Energies and norms come from device
+ * scalars of the last GN iteration (BA:798-802, 847-851, 1415-1425), OOB / In / InIn / Nores from the last cmlba_try_marginalize
+ * (BA:2356-2359).  The four "B Norm" series are declared but never fed by the reference; here they hold |bA|, |bL|, |bM|, |b_sc|. */
+#define CMLBA_NUM_STATISTICS 19
+int cmlba_get_statistics(const cmlba_handle *h, double *values /* [CMLBA_NUM_STATISTICS] */);
+const char *cmlba_statistic_name(int i);
+
 /* ---- stage entry points (protected members of the class; used by parity tests and profiling) ----
  * cmlba_prepare      run() prologue BA:753-782: updateCamera, collect active residuals, computeAdjoints, computeDelta
  * cmlba_linearize    linearizeAll(fixLinearization) BA:1497-1646 (+ setNewFrameEnergyTH); *energy = returned [0]

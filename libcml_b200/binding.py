@@ -47,7 +47,7 @@ class BenchResult(C.Structure):
 SYMBOLS = ["cmlba_default_config", "cmlba_create", "cmlba_destroy", "cmlba_last_error", "cmlba_set_calib", "cmlba_add_frame", "cmlba_add_frame_gray", "cmlba_add_frame_device", "cmlba_add_points",
            "cmlba_remove_point", "cmlba_remove_frame", "cmlba_flag_frames_for_marginalization", "cmlba_try_marginalize", "cmlba_marginalize_points",
            "cmlba_marginalize_frames", "cmlba_run", "cmlba_num_frames", "cmlba_num_points", "cmlba_num_residuals", "cmlba_get_frames",
-           "cmlba_get_points", "cmlba_get_outliers", "cmlba_get_residuals", "cmlba_prepare", "cmlba_linearize", "cmlba_apply", "cmlba_solve", "cmlba_step",
+           "cmlba_get_points", "cmlba_get_outliers", "cmlba_get_residuals", "cmlba_get_statistics", "cmlba_statistic_name", "cmlba_prepare", "cmlba_linearize", "cmlba_apply", "cmlba_solve", "cmlba_step",
            "cmlba_read", "cmlba_reset", "cmlba_bench_pass", "cmlba_nccl_unique_id", "cmlba_comm_init", "cmlba_comm_ipc_handle", "cmlba_comm_ipc_open", "cmlba_version"]
 
 _lib = None
@@ -233,6 +233,13 @@ class DSOBundleAdjustment:
             return False
         self._ck(rc)
         return True
+
+    def getStatistics(self):
+        """{name: latest value} of the 19 Statistic series of DSOBundleAdjustment.h:215-233 (the reference's own names)."""
+        v = np.zeros(19)
+        self._ck(self.lib.cmlba_get_statistics(self.h, _ptr(v, C.c_double)))
+        self.lib.cmlba_statistic_name.restype = C.c_char_p
+        return {self.lib.cmlba_statistic_name(i).decode(): float(v[i]) for i in range(19)}
 
     def getOutliers(self):
         n = C.c_int(0)

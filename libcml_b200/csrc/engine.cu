@@ -250,6 +250,7 @@ public:
     DevBuf<uint8_t> d_bin_g;
     DevBuf<long long> d_lt_trace;
     DevBuf<unsigned long long> d_ktrace;   // development timeline (CMLBA_KTRACE=1)
+    double stats_[19] = {0};      // latest value of every Statistic series of BA.h:215-233 (cmlba_get_statistics)
     bool want_ktrace = false;
     int kt_seq = 0; std::vector<int> kt_sites;   // launch slots of the timeline (slot 0: the reset)
     TileMaps tile_maps;           // one tensor map per window frame (re-encoded by build_device_window)
@@ -680,7 +681,7 @@ public:
                 if (snap.state[i] == RES_IN) { num_in[q]++; if (frames_[t].flagged) vis[q]++; }
             }
         }
-        int dropped = 0, tomarg = 0;
+        int dropped = 0, tomarg = 0, st_oob = 0, st_in = 0, st_inin = 0;     // flag_oob / flag_in / flag_inin of BA:2268 (flag_nores is never incremented there)
         std::vector<size_t> to_drop;
         for (size_t q = 0; q < PA; q++) {
             PointHost &p = points_[q];
@@ -688,21 +689,23 @@ public:
             // residuals created since the last run() are in state IN (DSOResidual.h:81-86)
             for (unsigned m = p.res_mask & ~seen[q]; m; m &= m - 1) { num_in[q]++; if (frames_[__builtin_ctz(m)].flagged) vis[q]++; }
             const int nres = __builtin_popcount(p.res_mask);
-            if (p.idepth < 0 || nres == 0) { to_drop.push_back(q); continue; }
+            if (p.idepth < 0 || nres == 0) { to_drop.push_back(q); st_oob++; continue; }
             bool oob;
             if (num_in[q] >= 3 && p.num_good > 4 + 10 && num_in[q] - vis[q] < 3) oob = true;
             else if (p.last_state[0] == CMLBA_RES_OOB) oob = true;
             else if (num_in[q] < 2) oob = false;
             else oob = p.last_state[0] == CMLBA_RES_OUTLIER && p.last_state[1] == CMLBA_RES_OUTLIER;
             if (oob || frames_[p.host].flagged) {
-                if (nres >= 3 && p.num_good >= 4 && p.idepth_hessian > cfg.min_idepth_h_marg) { p.to_marginalize = true; tomarg++; }
-                else to_drop.push_back(q);
+                if (nres >= 3 && p.num_good >= 4) st_in++;
+                if (nres >= 3 && p.num_good >= 4 && p.idepth_hessian > cfg.min_idepth_h_marg) { p.to_marginalize = true; tomarg++; st_inin++; }
+                else { to_drop.push_back(q); st_oob++; }
             }
         }
         for (size_t q : to_drop) { outliers_.push_back(points_[q].id); drop_point(q, false); dropped++; }
         (void) N;
         if (n_dropped) *n_dropped = dropped;
         if (n_to_marg) *n_to_marg = tomarg;
+        stats_[14] = st_oob; stats_[15] = st_in; stats_[16] = st_inin; stats_[17] = 0.0;      // BA:2356-2359
         if (dropped) maybe_compact();
         return CMLBA_OK;
     }
@@ -1369,6 +1372,16 @@ public:
             snap.point_id[i] = p.id;
             if (p.res_mask == 0) { kill_point(q); outliers_.push_back(p.id); nout++; }
         }
+        {   // Statistic series (BA:798-802, 847-851, 1415-1425, 2204): the values of the last iteration
+            const double nres = std::max(R, 1);
+            const double eM = 0.0;                                      // calcMEnergy is folded into the linearised energy here (post_linearize_kernel)
+            stats_[0] = c.energy_last / nres; stats_[1] = 0.0; stats_[2] = c.energyL_last; stats_[3] = eM;
+            stats_[4] = (c.energy_last + c.energyL_last + eM) / nres;
+            stats_[5] = c.stats[4];                                     // X Norm
+            stats_[6] = c.stats[5]; stats_[7] = c.stats[6]; stats_[8] = c.stats[7]; stats_[9] = c.stats[8];          // Hessian P / L / M / SC norms
+            stats_[10] = c.stats[9]; stats_[11] = c.stats[10]; stats_[12] = c.stats[11]; stats_[13] = c.stats[12];   // B norms (declared, never fed by the reference)
+            stats_[18] = 0.0;                                           // Num Linearized: run() never holds a linearised residual
+        }
         if (out) {
             out->iterations_done = c.iteration; out->num_residuals = R; out->num_dropped = dropped; out->num_outliers = nout;
             out->energy_first = c.energy_first; out->energy_last = c.energy_last; out->num_rejected = c.rejected;
@@ -1799,6 +1812,15 @@ int cmlba_step(cmlba_handle *h, int update_points_only, int *can_break) {
 }
 
 int cmlba_reset(cmlba_handle *h) { HCHK; return h->eng.reset(); }
+static const char *const kStatNames[19] = {"P Energy ( All residuals )", "R Energy", "L Energy ( Linearized )", "M Energy ( Marginalized )", "Total Energy", "X Norm",
+                                           " Hessian P Norm", " Hessian L Norm", " Hessian M Norm", " Hessian SC Norm", "P B Norm", "L B Norm", "M B Norm", "SC B Norm",
+                                           "OOB", "In", "InIn", "Nores", "Num Linearized"};
+int cmlba_get_statistics(const cmlba_handle *h, double *values) {
+    if (!h || !values) return CMLBA_ERR_ARG;
+    for (int i = 0; i < 19; i++) values[i] = h->eng.stats_[i];
+    return CMLBA_OK;
+}
+const char *cmlba_statistic_name(int i) { return (i >= 0 && i < 19) ? kStatNames[i] : nullptr; }
 int cmlba_bench_pass(cmlba_handle *h, int steps, int warmup, int flush_l2, cmlba_bench_result *out) { HCHK; return h->eng.bench_pass(steps, warmup, flush_l2, out); }
 
 int cmlba_read(cmlba_handle *h, const char *name, void *dst, size_t cap, size_t *bytes) { HCHK; if (!name) return CMLBA_ERR_ARG; return h->eng.read(name, dst, cap, bytes); }

@@ -674,15 +674,30 @@ __global__ void __launch_bounds__(256) solve_kernel(const DevWin w, const int re
             if (lane == 0) b[e] += w.bM[e] + hm;
         }
     }
+    double nrm[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // squared Frobenius norms of HA HL HM Hsc | bA bL bM bsc (the Statistic series of BA.h:221-228, BA:1415-1418)
     for (int e = tid; e < nn; e += 256) {
         const int r = e / n, c = e % n;
         double v = H[e];
-        if (w.has_HM) v += w.HM[e];
-        if (r == c && r >= 4) v += w.frames[(r - 4) >> 3].prior[(r - 4) & 7];
+        nrm[0] += v * v;
+        if (w.has_HM) { const double hm = w.HM[e]; v += hm; nrm[2] += hm * hm; }
+        if (r == c && r >= 4) { const double pr = w.frames[(r - 4) >> 3].prior[(r - 4) & 7]; v += pr; nrm[1] += pr * pr; }
         if (r == c) v *= (1.0 + lambda);                        // BA:1306-1308
-        v -= Hs[e] * (1.0 / (1.0 + lambda));                    // BA:1309
+        const double hs = Hs[e];
+        nrm[3] += hs * hs;
+        v -= hs * (1.0 / (1.0 + lambda));                       // BA:1309
         H[e] = v;
     }
+    for (int e = tid; e < n; e += 256) {
+        const double ba = sysbA[e], bs = sysbS[e];
+        nrm[4] += ba * ba; nrm[7] += bs * bs;
+        if (e >= 4) { const FrameDev &f = w.frames[(e - 4) >> 3]; const double bl = f.prior[(e - 4) & 7] * f.state[(e - 4) & 7]; nrm[5] += bl * bl; }
+        if (w.has_HM) { const double bm = w.bM[e]; nrm[6] += bm * bm; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) nrm[k] = warp_sum_d(nrm[k]);
+    if (lane == 0) for (int k = 0; k < 8; k++) red[wid * 8 + k] = nrm[k];
+    __syncthreads();
+    if (tid < 8) { double t = 0.0; for (int q = 0; q < 8; q++) t += red[q * 8 + tid]; ctrl->stats[5 + tid] = sqrt(t); }
     __syncthreads();
     for (int e = tid; e < n; e += 256) s[e] = 1.0 / sqrt(H[e * n + e] + 10.0);   // BA:1312
     __syncthreads();

@@ -53,7 +53,7 @@ def main():
     fr1 = ref.getFrames(); pts1 = ref.getPoints(); rs1 = ref.getResiduals()
     rel = lambda a, b: float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-30))
     # tolerances: the shards sum their fp32 accumulators in a different order than the single-GPU run (1 ulp on the entries of H); the reduced
-    # system's conditioning (~1e11, tests/test_oracle_golden.py::test_forward_error_floor_of_the_reference_system) turns that into ~1e-6 on the
+    # system's conditioning (~1e11, DESIGN.md section 4 "Conditioning") turns that into ~1e-6 on the
     # poses and ~1e-5 on inverse depths with 8 shards (measured: profiles/r02_multi_gpu.md).  Gates: 10x below the 1e-4 of the parity tests.
     errs = []
     if ok != ok1: errs.append("ok flag")
