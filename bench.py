@@ -317,6 +317,69 @@ def main():
     e2e_s = float(e2e_ms.cpu()[0])
     e2e_value = R_all * e2e_iters / e2e_s
 
+    # ---------------- the caller's steady-state cycle (Hybrid::directMap, slam/modslam/direct/Mapping.cpp:61-100): ONE new keyframe per cycle.
+    # A 16-frame sequence of the same scene: frames 0..N-1 form the first window; every cycle flags frames, adds the next keyframe (one pinned
+    # gray image crosses PCIe) and its points, runs the BA, reads the results back and does the window maintenance (tryMarginalize, outlier
+    # removal, marginalizePointsF, marginalizeFrames) so that the window is back to N keyframes.  Single GPU only; N=1 line.
+    cycle = None
+    noisy = None
+    if world == 1 and args.workload == "c2":
+        seq = synth.make_window(W, H, 2 * N, ppk, iters, affine, seed=1234, with_gradients=False)
+        sg = torch.from_numpy(np.ascontiguousarray(seq["gray"], dtype=np.float32)).pin_memory().numpy()
+        sb = DSOBundleAdjustment(device=local_rank, iterations=iters, async_image_upload=1, max_frames=N)
+        sb.setCalibration(*[float(v) for v in seq["calib"]], W, H)
+        per = ppk
+        def add_kf(f):
+            sb.addNewFrameGray(f, seq["frame_evalpt"][f], seq["frame_affine"][f, 0], seq["frame_affine"][f, 1], seq["frame_exposure"][f], sg[f], False)
+            sel = slice(f * per, (f + 1) * per)
+            sb.addPoints(np.arange(f * per, (f + 1) * per), seq["pt_host"][sel], seq["pt_xy"][sel], seq["pt_idepth"][sel])
+        for f in range(N):
+            add_kf(f)
+        cams_of = lambda: np.stack([seq["frame_cam"][int(i)] for i in sb.getFrames()["id"]])
+        sb.run(cams_of(), iterations=iters)
+        ct, cres, cit, cframes = [], [], [], []
+        for f in range(N, 2 * N):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sb.flagFramesForMarginalization(cams_of())
+            add_kf(f)
+            ok = sb.run(cams_of(), iterations=iters)
+            frs = sb.getFrames(); ptsr = sb.getPoints()
+            sb.tryMarginalize()
+            for o in sb.getOutliers():
+                pass                                   # libcmlba has already dropped them; the caller only forgets them
+            sb.marginalizePointsF()
+            sb.marginalizeFrames()
+            torch.cuda.synchronize()
+            ct.append(time.perf_counter() - t0)
+            cres.append(sb.last_result.num_residuals); cit.append(sb.last_result.iterations_done); cframes.append(int(frs["id"].size))
+            if not ok:
+                raise SystemExit("run() failed in the sliding-window cycle")
+        ct, cres, cit = np.array(ct[1:]), np.array(cres[1:]), np.array(cit[1:])     # first cycle warms the allocations up
+        cycle = {"value": float((cres * cit).sum() / ct.sum()), "unit": UNIT, "ms_per_cycle": float(ct.mean() * 1e3), "cycles": int(ct.size),
+                 "residuals_per_run": float(cres.mean()), "iterations_per_run": float(cit.mean()), "frames_in_run": cframes[1:],
+                 "h2d_bytes_per_cycle": int(sg[0].nbytes + per * (8 + 8 + 8 + 8) + 12 * 8 * (N + 1)),
+                 "what": "flagFramesForMarginalization + addNewFrame (one pinned gray image) + addPoints(%d) + run + get_frames/get_points + tryMarginalize + marginalizePointsF + marginalizeFrames, window of %d keyframes" % (per, N)}
+        sb.close()
+        # the same window with 4x the pose / 8x the inverse-depth noise and the convergence test off: all GN iterations run
+        nz = synth.make_config(args.workload, seed=1234, idepth_noise=0.04, pose_noise=2e-3, with_gradients=False)
+        nb = DSOBundleAdjustment(device=local_rank, iterations=iters, async_image_upload=1, th_opt_iterations=0.0)    # "ThOptIterations" 0: the convergence test never ends the loop early
+        nt = []
+        for i in range(4):
+            nb.reset(); nb.setCalibration(*[float(v) for v in nz["calib"]], W, H)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for f in range(N):
+                nb.addNewFrameGray(f, nz["frame_evalpt"][f], nz["frame_affine"][f, 0], nz["frame_affine"][f, 1], nz["frame_exposure"][f], gnp[f], False)
+            nb.addPoints(np.arange(P), nz["pt_host"], nz["pt_xy"], nz["pt_idepth"])
+            nb.run(nz["frame_cam"], iterations=iters)
+            nb.getFrames(); nb.getPoints()
+            torch.cuda.synchronize(); nt.append(time.perf_counter() - t0)
+        r_ = nb.last_result
+        noisy = {"iterations": int(r_.iterations_done), "rejected_steps": int(r_.num_rejected), "run_gpu_ms": float(r_.gpu_ms), "kernel_launches": int(r_.kernel_launches),
+                 "e2e_ms": float(np.mean(nt[1:]) * 1e3), "e2e_value": float(r_.num_residuals * r_.iterations_done / np.mean(nt[1:])), "energy_first": float(r_.energy_first),
+                 "energy_last": float(r_.energy_last), "what": "c2 with inverse-depth noise 4 % (default 0.5 %), pose noise 2e-3 (default 5e-4) and ThOptIterations = 0 (no early exit): all %d GN iterations run" % iters}
+        nb.close()
+
     # ---------------- N > 1: self-check.  (1) every rank finished the same run(): iterations and poses identical;  (2) the reduced system
     # exchanged over peer memory equals the one exchanged by ncclAllReduce on a second handle with the same shard (same partials).
     multi = None
@@ -369,6 +432,7 @@ def main():
                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_unit": b_alg(N), "units_per_launch": R},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                    "what": f"reset + set_calib + {N} x add_frame_gray (pinned host gray images, asynchronous upload, derivative images built on the device) + add_points + run(up to {iters} GN iterations, {e2e_iters} executed) + get_frames/get_points"},
+           "e2e_sliding_window": cycle, "run_noisy": noisy,
            "gpu_launches": int(br.launches_per_pass * args.steps),
            "clocks": clocks}
     if multi is not None:
