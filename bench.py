@@ -195,6 +195,43 @@ def reference_arm(args):
     return 0
 
 
+def c5_reference_cpu(W, H, NW, density):
+    """Reference CPU time of ONE frame of the C5 cycle (every frame a keyframe), assembled from the unmodified reference's own stages timed by
+    oracle/_ref/cmlba_ref at the stream's resolution: prepare (CaptureImageGenerator::generate) + pixel selection + tracing one frame against
+    the window's immature points + activation + coarse tracking (optimize) + one BA run() on a window of NW keyframes.  The stages are timed one
+    by one (each through the component tool that also checks parity), not chained; the reference is single-threaded."""
+    if not os.path.exists(REF_BIN):
+        return None
+    import contextlib
+    import importlib
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    size = ["--width", str(W), "--height", str(H)]
+    def tool(name, extra):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            importlib.import_module(name).main(size + extra, reference=reference_cpu)
+        line = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
+        return json.loads(line[-1]) if line else {}
+    st = {}
+    p = tool("prep_bench", ["--repeats", "5"]); st["prepare"] = p.get("reference_cpu_generate_ms")
+    q = tool("select_bench", ["--repeats", "3"]); st["select"] = q.get("reference_cpu_compute_ms_best")
+    t = tool("trace_bench", ["--frames", str(NW), "--points", str(density), "--repeats", "3"])
+    st["trace"] = t["reference_cpu_trace_ms_total"] / max(NW - 1, 1) if "reference_cpu_trace_ms_total" in t else None
+    st["activate"] = t.get("reference_cpu_activation_ms")
+    k = tool("track_bench", ["--frames", str(NW), "--points", str(density), "--repeats", "5"]); st["track"] = k.get("reference_cpu_optimize_ms")
+    from libcml_b200 import synth
+    win = synth.make_window(W, H, NW, density, 6, False, seed=1234, with_gradients=False)
+    path = window_file(win, "c5ref")
+    res = run_reference_bench(path, 1)
+    os.remove(path)
+    st["ba_run"] = res["t_run"] * 1e3
+    if any(v is None for v in st.values()):
+        return {"stages_ms": st, "ms_per_frame": None}
+    return {"stages_ms": {k_: round(float(v), 3) for k_, v in st.items()}, "ms_per_frame": round(float(sum(st.values())), 3), "cores": 1, "cpu": cpu_model(),
+            "how": "sum of the reference's own stages, each timed by oracle/_ref/cmlba_ref at this resolution (not chained)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,6 +251,29 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         name = {"tracker": "track_bench", "tracer": "trace_bench", "prepare": "prep_bench", "select": "select_bench"}[args.component]
         return importlib.import_module(name).main(rest, reference=reference_cpu)
+    if args.workload == "c5":      # BASELINE.json configs[4]: the whole direct-odometry cycle as a stream (tools/stream_bench.py)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import stream_bench
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) != 0:
+                return 0
+            import argparse as _ap
+            q = _ap.ArgumentParser(); q.add_argument("--width", type=int, default=1920); q.add_argument("--height", type=int, default=1080)
+            q.add_argument("--window", type=int, default=8); q.add_argument("--density", type=int, default=2000)
+            a2, _ = q.parse_known_args(rest)
+            ref = c5_reference_cpu(a2.width, a2.height, a2.window, a2.density)
+            if not ref or not ref.get("ms_per_frame"):
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/cmlba_ref not built or a stage failed", "detail": ref}))
+                return 0
+            print(json.dumps({"metric": "frames/s of the direct-odometry cycle (every frame a keyframe) at %dx%d, %d-keyframe window" % (a2.width, a2.height, a2.window),
+                              "value": 1e3 / ref["ms_per_frame"], "unit": "frames/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": ref["ms_per_frame"],
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (projection f64)", "data": "synthetic", "impl": "reference",
+                              "config": {"workload": "c5: %dx%d stream, sliding window of %d keyframes, %d points per keyframe desired" % (a2.width, a2.height, a2.window, a2.density)},
+                              "cpu_baseline": {"value": 1e3 / ref["ms_per_frame"], "unit": "frames/s", "cores": 1, "kind": "reference", "sample": ref["how"], "stages_ms": ref["stages_ms"]},
+                              "e2e": {"value": 1e3 / ref["ms_per_frame"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return 0
+        stream_bench.main(rest + ["--gpus", str(args.gpus)], reference=None if args.no_cpu_baseline else c5_reference_cpu)
+        return 0
     if rest:
         ap.error("unrecognised arguments: " + " ".join(rest))
     if args.warmup < 3 and args.impl == "ours":

@@ -234,6 +234,9 @@ class DSOBundleAdjustment:
         self._ck(rc)
         return True
 
+    def numPoints(self):
+        return int(self.lib.cmlba_num_points(self.h))
+
     def getStatistics(self):
         """{name: latest value} of the 19 Statistic series of DSOBundleAdjustment.h:215-233 (the reference's own names)."""
         v = np.zeros(19)

@@ -128,3 +128,16 @@ def test_degenerate_inputs_fail_cleanly():
     hist = trc.traceNewCoarse(1)                              # identical pose: zero baseline, the search direction is undefined -> OOB like the reference
     assert hist.sum() == 2
     assert set(trc.getPoints()["status"][ids]) <= {1, 2, 3, 4}
+
+
+def test_stream_cycle_small():
+    """The chained per-frame cycle of BASELINE.json configs[4] (tools/stream_bench.py = `bench.py --workload c5`) on a small sequence: every frame is
+    prepared, tracked, traced, selected, activated and bundle-adjusted on the device; the sliding window stays at its size, the tracker stays on
+    the truth and the BA keeps running."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import stream_bench
+    out = stream_bench.main(["--width", "320", "--height", "240", "--frames", "13", "--window", "6", "--density", "400"])
+    assert out["steps"] == 5 and out["value"] > 0
+    assert all(f["window"] == 6 and f["ba_iterations"] >= 1 and f["ba_residuals"] > 1000 and f["activated"] > 50 for f in out["frames"])
+    assert out["track_translation_error_rel_to_motion"]["max"] < 0.05
