@@ -108,6 +108,19 @@ int cmltrk_optimize(cmltrk_handle h, int num_candidates, const double *start_cam
 int cmltrk_track(cmltrk_handle h, const float *gray, double exposure_time, int num_candidates, const double *start_cams, const double *start_affine,
                  const double *last_rmse, cmltrk_result *results);
 
+/* DSOTracker::trackWithMotionModel (DSOTracker.h:240-360): the candidate loop over the poses of Map::multiConstantVelocityMotionModel on the
+ * frame given to cmltrk_set_frame / cmltrk_set_frame_device.  The poses are optimised one after the other because every run is gated by the best
+ * residual so far (mLastResidual = trackingResult, DSOTracker.cpp:190-196) and the loop stops at the first candidate that is good enough
+ * (achievedRes < 1.5 * mLastCoarseRMSE; at most 51 candidates once one succeeded).  failure_mode 1 = when every candidate failed, optimise the
+ * first pose again and return that (the reference's "return the best effort" branch).
+ * *ok = 1: `best` holds the residual / pose / brightness the reference would leave in the frame (frame->setCamera, setExposureParameters);
+ * *ok = 0: tracking failed, `best` is the last kept residual (is_correct = 0 when there was none).  *tried = candidates optimised.
+ * The handle keeps mLastCoarseRMSE / mFirstRMSE between calls like the class does (cmltrk_reset_motion_model clears them). */
+int cmltrk_track_with_motion_model(cmltrk_handle h, int num_cameras, const double *cameras /* [K][12] */, const double initial_affine[2], int failure_mode,
+                                   int *ok, cmltrk_result *best, int *tried);
+int cmltrk_reset_motion_model(cmltrk_handle h);
+int cmltrk_motion_model_state(cmltrk_handle h, double *last_coarse_rmse, double *first_rmse);
+
 /* Debug / test reads: "pc_n" (int32[levels]), "pc<l>" (float [n][4]), "grad<l>" (float [h][w][4] = I, dx, dy, 0 of the frame to track),
  * "levels_wh" (int32 [levels][2]), "K" (double [levels][4]), "cycles" (int64 [4]: evaluations and SM cycles spent advancing the optimiser,
  * evaluating points and reducing/exchanging sums in the last optimize, start pose 0).  Returns bytes written or a negative error. */

@@ -31,6 +31,7 @@ static thread_local std::string g_create_error;
     } while (0)
 
 struct Tracker {
+    double last_coarse_rmse = INFINITY, first_rmse = -1.0;     // mLastCoarseRMSE / mFirstRMSE of the class (trackWithMotionModel)
     cmltrk_config cfg{};
     int device = 0, W = 0, H = 0, L = 0;
     int w[MAXL]{}, h[MAXL]{};
@@ -440,6 +441,66 @@ int cmltrk_track(cmltrk_handle h, const float *gray, double exposure_time, int n
     const int rc = t->set_frame(gray, exposure_time);
     if (rc) return rc;
     return t->optimize(num_candidates, start_cams, start_affine, last_rmse, results, before);
+}
+
+// DSOTracker::trackWithMotionModel (DSOTracker.h:240-360); mirrors libcml_b200/tracker.py::trackWithMotionModelPy step by step
+static double trk_rmse(const cmltrk_result &r, int l) { return r.num_terms_in_E[l] > 0 ? r.E[l] / r.num_terms_in_E[l] : 0.0; }
+int cmltrk_track_with_motion_model(cmltrk_handle h, int num_cameras, const double *cameras, const double initial_affine[2], int failure_mode, int *ok, cmltrk_result *best_out,
+                                   int *tried) {
+    if (!h || !cameras || !initial_affine || !ok || !best_out || num_cameras < 1) return CMLTRK_ERR_ARG;
+    Tracker *t = reinterpret_cast<Tracker *>(h);
+    bool have = false, have_best = false;
+    cmltrk_result best; memset(&best, 0, sizeof(best));
+    double achieved = INFINITY;
+    int n_tried = 0;
+    auto last_of = [&](double *last) -> const double * {                    // mLastResidual = trackingResult: the rmse gate of the next optimize
+        if (!have_best || !best.is_correct) return nullptr;
+        for (int l = 0; l < CMLTRK_OPT_LEVELS; l++) last[l] = l < best.levels_used ? trk_rmse(best, l) : 0.0;
+        return last;
+    };
+    for (int i = 0; i < num_cameras; i++) {
+        n_tried = i + 1;
+        double last[CMLTRK_OPT_LEVELS];
+        cmltrk_result test;
+        const int rc = t->optimize(1, cameras + 12 * i, initial_affine, last_of(last), &test, t->launches);
+        if (rc) return rc;
+        const double test_rmse = test.num_terms_in_E[0] > 0 ? test.E[0] / test.num_terms_in_E[0] : INFINITY;
+        const bool test_ok = test.is_correct && test.num_terms_in_E[0] > 0 && std::isfinite(test_rmse);
+        const bool best_sat = have_best ? best.too_many_saturated != 0 : true;                     // Residual(): tooManySaturated = true
+        if (best_sat && !test.too_many_saturated && test_ok) { have = true; best = test; have_best = true; }
+        if (test_ok && !(test_rmse >= achieved)) {
+            if ((have_best ? best.too_many_saturated != 0 : true) || !test.too_many_saturated) { have = true; best = test; have_best = true; }
+        }
+        if (have && test.num_terms_in_E[0] > 0 && test_rmse < achieved) achieved = test_rmse;
+        if (have && achieved < t->last_coarse_rmse * 1.5) break;
+        if (have && i >= 50) break;
+    }
+    if (tried) *tried = n_tried;
+    if (!have) {
+        if (failure_mode != 1) { *ok = 0; *best_out = best; return CMLTRK_OK; }
+        double last[CMLTRK_OPT_LEVELS];
+        const int rc = t->optimize(1, cameras, initial_affine, last_of(last), &best, t->launches);
+        if (rc) return rc;
+        *ok = 1; *best_out = best;
+        return CMLTRK_OK;
+    }
+    t->last_coarse_rmse = achieved;
+    if (t->first_rmse < 0) t->first_rmse = achieved;
+    *ok = 1; *best_out = best;
+    return CMLTRK_OK;
+}
+int cmltrk_reset_motion_model(cmltrk_handle h) {
+    if (!h) return CMLTRK_ERR_ARG;
+    Tracker *t = reinterpret_cast<Tracker *>(h);
+    t->last_coarse_rmse = INFINITY; t->first_rmse = -1.0;
+    return CMLTRK_OK;
+}
+int cmltrk_motion_model_state(cmltrk_handle h, double *last_coarse_rmse, double *first_rmse) {
+    if (!h) return CMLTRK_ERR_ARG;
+    Tracker *t = reinterpret_cast<Tracker *>(h);
+    if (last_coarse_rmse) *last_coarse_rmse = t->last_coarse_rmse;
+    if (first_rmse) *first_rmse = t->first_rmse;
+    return CMLTRK_OK;
 }
 
 float *cmltrk_frame_buffer(cmltrk_handle h) {

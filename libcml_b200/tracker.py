@@ -30,7 +30,8 @@ class TrackerResult(C.Structure):
 
 
 TRACKER_SYMBOLS = ["cmltrk_default_config", "cmltrk_create", "cmltrk_destroy", "cmltrk_last_error", "cmltrk_make_coarse_depth", "cmltrk_set_frame", "cmltrk_optimize",
-                   "cmltrk_track", "cmltrk_read", "cmltrk_bench_optimize", "cmltrk_frame_buffer", "cmltrk_make_coarse_depth_device", "cmltrk_set_frame_device"]
+                   "cmltrk_track", "cmltrk_read", "cmltrk_bench_optimize", "cmltrk_frame_buffer", "cmltrk_make_coarse_depth_device", "cmltrk_set_frame_device",
+                   "cmltrk_track_with_motion_model", "cmltrk_reset_motion_model", "cmltrk_motion_model_state"]
 
 _bound = False
 
@@ -54,6 +55,9 @@ def _bind(lib):
     lib.cmltrk_read.restype = C.c_int64
     lib.cmltrk_read.argtypes = [vp, C.c_char_p, vp, C.c_int64]
     lib.cmltrk_bench_optimize.argtypes = [vp, C.c_int, fp]
+    lib.cmltrk_track_with_motion_model.argtypes = [vp, C.c_int, dp, dp, C.c_int, C.POINTER(C.c_int), C.POINTER(TrackerResult), C.POINTER(C.c_int)]
+    lib.cmltrk_reset_motion_model.argtypes = [vp]
+    lib.cmltrk_motion_model_state.argtypes = [vp, dp, dp]
     lib.cmltrk_frame_buffer.restype = fp
     lib.cmltrk_frame_buffer.argtypes = [vp]
     _bound = True
@@ -212,8 +216,25 @@ class DSOTracker:
         out = [Residual(r) for r in res]
         return out[0] if single else out
 
-    # ---- DSOTracker::trackWithMotionModel (DSOTracker.h:240-360): the candidate loop over motion-model poses
+    # ---- DSOTracker::trackWithMotionModel (DSOTracker.h:240-360) through the C ABI (cmltrk_track_with_motion_model)
     def trackWithMotionModel(self, cameras, initial_exposure=(0.0, 0.0), failure_mode=0):
+        """cameras [K][12] = the poses of Map::multiConstantVelocityMotionModel, tried in order on the frame given to setFrame / setFrameDevice.
+        Returns (ok, camera, exposure, residual) like the reference (frame->setCamera / setExposureParameters / residual)."""
+        cams = np.ascontiguousarray(cameras, dtype=np.float64).reshape(-1, 12)
+        init = np.ascontiguousarray(initial_exposure, dtype=np.float64).reshape(2)
+        ok, tried, res = C.c_int(0), C.c_int(0), TrackerResult()
+        self._ck(self.lib.cmltrk_track_with_motion_model(self.h, cams.shape[0], _dp(cams), _dp(init), int(failure_mode), C.byref(ok), C.byref(res), C.byref(tried)))
+        self.lastTriedCameras = tried.value
+        a, b = C.c_double(), C.c_double()
+        self.lib.cmltrk_motion_model_state(self.h, C.byref(a), C.byref(b))
+        self.mLastCoarseRMSE, self.mFirstRMSE = a.value, b.value
+        r = Residual(res)
+        if not ok.value:
+            return False, None, None, (r if r.isCorrect else None)
+        return True, r.camera, r.exposure, r
+
+    # the same loop in Python on top of cmltrk_optimize (kept as the executable specification the C entry point is tested against)
+    def trackWithMotionModelPy(self, cameras, initial_exposure=(0.0, 0.0), failure_mode=0):
         """cameras [K][12] = the poses of Map::multiConstantVelocityMotionModel, tried in order on the frame given to setFrame / setFrameDevice.
         Returns (ok, camera, exposure, residual) like the reference (frame->setCamera / setExposureParameters / residual); the candidates are
         optimised one after the other because each run is gated by the best residual so far (mLastResidual = trackingResult) and the loop

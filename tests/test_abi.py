@@ -32,7 +32,7 @@ def test_tracker_header_symbols_exported(lib):
     src = open(os.path.join(ROOT, "include", "cmltrk.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     syms = sorted(set(re.findall(r"\b(cmltrk_[a-z_0-9]+)\s*\(", src)))
-    assert sorted(tracker.TRACKER_SYMBOLS) == syms and len(syms) == 13
+    assert sorted(tracker.TRACKER_SYMBOLS) == syms and len(syms) == 16
     for s in syms:
         assert hasattr(lib, s), f"libcmlba.so does not export {s}"
     cfg = tracker.TrackerConfig()

@@ -176,6 +176,15 @@ def test_track_with_motion_model_candidate_loop():
     trk2.setFrame(win["gray"][new], win["frame_exposure"][new])
     ok, cam, ex, res = trk2.trackWithMotionModel([far, far])
     assert not ok and cam is None and trk2.lastTriedCameras == 2
+    # the C entry point (cmltrk_track_with_motion_model) against the Python loop over cmltrk_optimize it was written from: same decisions, same bits
+    for poses, mode in (([far, good, good], 0), ([good, far], 0), ([far, far], 1)):
+        ta, _, _ = make_tracker(win); tb, _, _ = make_tracker(win)
+        ta.setFrame(win["gray"][new], win["frame_exposure"][new]); tb.setFrame(win["gray"][new], win["frame_exposure"][new])
+        oa, ca, ea, ra = ta.trackWithMotionModel(poses, failure_mode=mode)
+        ob, cb, eb, rb = tb.trackWithMotionModelPy(poses, failure_mode=mode)
+        assert oa == ob and ta.lastTriedCameras == tb.lastTriedCameras
+        if oa:
+            assert np.array_equal(ca, cb) and np.array_equal(ea, eb) and ra.isCorrect == rb.isCorrect
 
 
 def test_error_paths():
