@@ -72,6 +72,8 @@ struct Ctrl {
     int rejected;               // number of rejected steps
     int pt_bad;                 // non-finite point steps of this rank (point_step_kernel)
     int asm_done_count;         // last-block counter of assemble_kernel (peer signalling)
+    int acc_done_count;         // jobs of accumulate_kernel finished since prepare(): stitch_pair_kernel waits on it (the kernels run on two streams, no stream-level join)
+    int pad1;
 };
 
 struct DevWin {
@@ -148,6 +150,7 @@ struct DevWin {
     float *dbg;                    // optional [R][40]: resF[8] JIdx[16] JabF[16]
     // partial sums
     double *energy_part;           // [n_chunks]
+    int acc_target;                // value acc_done_count reaches when the accumulation this stitch depends on has finished (0: no device-side wait)
     float *acc_bin;                // [N*N (bin = t*N+h)][ACC_SLICES][ACC_N] 13x13 blocks of the committed linearization (accumulate role of schur_acc_kernel)
     float *sc_part;                // [n_sc_chunks][sc_stride]
     int sc_stride;                 // (8N)^2 + 32N + 8N + 16 + 4 (padded to 4)

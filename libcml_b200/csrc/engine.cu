@@ -269,6 +269,8 @@ public:
     cudaStream_t side_stream = nullptr, launch_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool use_fork = true;
+    int acc_jobs_launched = 0;     // accumulate jobs launched since prepare() (= the value Ctrl.acc_done_count reaches), see launch_schur
+    bool side_pending = false;     // work on the side stream that the main stream has not joined yet
     UploadArena up;                               // every array build_device_window uploads
     UploadArena prep;                             // per-run constants uploaded by prepare()
     std::vector<int> res_bin_begin;               // [N*N+1] first device residual of every bin (t*N+h)
@@ -992,6 +994,8 @@ public:
         if (N < 1) { set_error("no frames"); return CMLBA_ERR_STATE; }
         if (points_.size() == n_dead) { set_error("No points..."); return CMLBA_ERR_STATE; }   // BA:759-762
         CK(cudaSetDevice(device));
+        join_side();                                  // nothing of the previous run may still count into the control block that is rebuilt below
+        acc_jobs_launched = 0;
         if (dirty) { int rc = build_device_window(); if (rc) return rc; }
         const int n = 8 * N + 4;
         double sc[10]; scales(sc);
@@ -1185,21 +1189,29 @@ public:
         launch_pdl(2, post_linearize_kernel, dim3(1), dim3(1024), 0, dw, mode, respect_done);
     }
     void launch_accumulate(int respect_done) {
-        if (dw.R > 0) launch_pdl(4, accumulate_kernel, dim3(dw.N * dw.N * ACC_SLICES), dim3(32), 0, dw, respect_done);
+        if (dw.R > 0) { launch_pdl(4, accumulate_kernel, dim3(dw.N * dw.N * ACC_SLICES), dim3(32), 0, dw, respect_done); acc_jobs_launched += dw.N * dw.N * ACC_SLICES; }
     }
     void launch_schur_only(int respect_done) {
         if (dw.n_sc_chunks > 0) launch_pdl(8, schur_kernel, dim3(dw.n_sc_chunks), dim3(256), schur_smem(), dw, respect_done);
     }
+    // addToHessianTop from the Jacobian records ((bin, slice) jobs) on the side stream, the Schur chunks on the main one.  The side stream is
+    // forked off with an event; it is NOT joined back per pass: stitch_pair_kernel waits on the device for Ctrl.acc_done_count to reach
+    // dw.acc_target (a stream-level join costs ~3 us of idle time before the stitch), and the host joins once before it reads results
+    // (join_side()).  A job that is skipped because the run is done counts as well, so the target stays in step.
     void launch_schur(int respect_done) {
-        // addToHessianTop from the Jacobian records ((bin, slice) jobs) on the side stream, the Schur chunks on the main one
         const bool fork = use_fork && dw.R > 0 && dw.n_sc_chunks > 0;
         if (fork) {
             if (cudaEventRecord(ev_fork, stream) != cudaSuccess || cudaStreamWaitEvent(side_stream, ev_fork, 0) != cudaSuccess) { set_error("fork failed"); launch_rc = CMLBA_ERR_CUDA; }
             launch_stream = side_stream; launch_accumulate(respect_done); launch_stream = stream;
-            if (cudaEventRecord(ev_join, side_stream) != cudaSuccess) { set_error("fork failed"); launch_rc = CMLBA_ERR_CUDA; }
+            side_pending = true;
+            dw.acc_target = acc_jobs_launched;
             launch_schur_only(respect_done);
-            if (cudaStreamWaitEvent(stream, ev_join, 0) != cudaSuccess) { set_error("join failed"); launch_rc = CMLBA_ERR_CUDA; }
-        } else { launch_accumulate(respect_done); launch_schur_only(respect_done); }
+        } else { dw.acc_target = 0; launch_accumulate(respect_done); launch_schur_only(respect_done); }
+    }
+    void join_side() {
+        if (!side_pending) return;
+        if (cudaEventRecord(ev_join, side_stream) != cudaSuccess || cudaStreamWaitEvent(stream, ev_join, 0) != cudaSuccess) { set_error("join failed"); launch_rc = CMLBA_ERR_CUDA; }
+        side_pending = false;
     }
     // Schur complement + stitching + assembly of sys = [HA | bA | H_sc | b_sc]: one cluster kernel when a cluster of >= N CTAs is available
     bool tail_fused() const { return dw.N <= tail_cluster_max && dw.n_sc_chunks > 0; }
@@ -1306,6 +1318,7 @@ public:
         const size_t o_fd = take(N * sizeof(FrameDev)), o_c = take(sizeof(Ctrl)), o_id = take((size_t) P * 8), o_idz = take((size_t) P * 4), o_idh = take((size_t) P * 4),
                      o_mrb = take((size_t) P * 4), o_ng = take((size_t) P * 4), o_al = take(R), o_s0 = take(R), o_e0 = take((size_t) R * 4);
         CK(fin_h.reserve(off));
+        join_side();
         char *hb = fin_h.p;
         CK(cudaMemcpyAsync(hb + o_fd, d_frames.p, N * sizeof(FrameDev), cudaMemcpyDeviceToHost, stream));
         CK(cudaMemcpyAsync(hb + o_c, d_ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
@@ -1437,6 +1450,7 @@ public:
             if (world > 1) { int rc = allreduce_system(); if (rc) return rc; }
             CK(cudaEventRecord(ev[1], stream));
             CK(cudaStreamSynchronize(stream));
+            CK(cudaStreamSynchronize(side_stream));
             float ms = 0; CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); tot += ms;
         }
         const int per_pass = (launches - l0) / steps;

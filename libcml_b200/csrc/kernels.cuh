@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(32) accumulate_kernel(const DevWin w, const in
     // everything the first record load needs is requested together (one latency): control block, bin bounds
     const int done_ld = w.ctrl->done, cur = w.ctrl->cur;
     const int b0 = w.res_bin_begin[bin], b1 = w.res_bin_begin[bin + 1];
-    if (respect_done && done_ld) return;
+    if (respect_done && done_ld) { if (lane == 0) atomicAdd(&w.ctrl->acc_done_count, 1); return; }      // skipped jobs count too: the host's target stays in step
     const int len = (b1 - b0 + ACC_SLICES - 1) / ACC_SLICES, a0 = min(b0 + sl * len, b1), a1 = min(a0 + len, b1);
     float acc[ACC_N];
 #pragma unroll
@@ -201,6 +201,10 @@ __global__ void __launch_bounds__(32) accumulate_kernel(const DevWin w, const in
         for (int k = 0; k < 32; k++) v[k] = acc[g * 32 + k];
         w.acc_bin[(size_t) job * ACC_N + g * 32 + lane] = warp_transpose_sum(v, lane);
     }
+    // this job's slices are in place: publish (stitch_pair_kernel, on the main stream, waits until every job of this launch has counted)
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&w.ctrl->acc_done_count, 1);
 }
 
 __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int respect_done) {
@@ -376,7 +380,19 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
         for (int c = cb; c < ce; c++, src += w.sc_stride) s += (double) __ldg(src);
         Dj[e] = s;                 // Dj, Ej, EBj are contiguous
     }
-    if (tid < ACC_N) {   // 13x13 block of bin (i -> j): the slices of the accumulate role of schur_acc_kernel, fixed order
+    if (w.acc_target > 0) {   // accumulate_kernel runs on the side stream: wait (bounded) until all of its jobs have published their slices
+        if (tid == 0) {
+            int v = 0; long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(&w.ctrl->acc_done_count) : "memory");
+                if (v >= w.acc_target || ++spins > (1l << 24)) break;
+                __nanosleep(40);
+            }
+            if (v < w.acc_target) { w.ctrl->failed = 1; w.ctrl->done = 1; }      // never seen with a correct launch sequence; fail the run instead of reading stale blocks
+        }
+        __syncthreads();
+    }
+    if (tid < ACC_N) {   // 13x13 block of bin (i -> j): the slices of accumulate_kernel, fixed order
         const float *src = w.acc_bin + (size_t) (j * N + i) * ACC_SLICES * ACC_N + tid;
         double a = 0.0;
         float part[ACC_SLICES];
