@@ -73,7 +73,7 @@ struct Ctrl {
     int pt_bad;                 // non-finite point steps of this rank (point_step_kernel)
     int asm_done_count;         // last-block counter of assemble_kernel (peer signalling)
     int acc_done_count;         // jobs of accumulate_kernel finished since prepare(): stitch_pair_kernel waits on it (the kernels run on two streams, no stream-level join)
-    int pad1;
+    int pad1;                   // set when stitch_pair_kernel's bounded wait for acc_done_count expired (reported as CMLBA_ERR_STATE)
 };
 
 struct DevWin {

@@ -1247,6 +1247,7 @@ public:
     // protocol / state error, not the reference's "run() returned false"
     int exchange_status(const Ctrl &c) {
         if (c.pad0) { set_error("peer-memory exchange timed out: a rank did not reach the exchange (every rank must call the same sequence)"); return CMLBA_ERR_STATE; }
+        if (c.pad1) { set_error("internal: the side-stream accumulation did not finish before the stitch gave up waiting for it"); return CMLBA_ERR_STATE; }
         if (c.failed) { set_error("non-finite energy or step (reference run() returns false)"); return CMLBA_ERR_NUMERIC; }
         return CMLBA_OK;
     }

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
                 if (v >= w.acc_target || ++spins > (1l << 24)) break;
                 __nanosleep(40);
             }
-            if (v < w.acc_target) { w.ctrl->failed = 1; w.ctrl->done = 1; }      // never seen with a correct launch sequence; fail the run instead of reading stale blocks
+            if (v < w.acc_target) { w.ctrl->failed = 1; w.ctrl->pad1 = 1; w.ctrl->done = 1; }      // never seen with a correct launch sequence; fail the run (own status) instead of reading stale blocks
         }
         __syncthreads();
     }
