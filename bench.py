@@ -49,7 +49,7 @@ def measured_peaks():
 
 
 def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of linearize_kernel per launch, from the committed ncu --set full summary
+    """dram__bytes_read.sum + dram__bytes_write.sum of linearize_tile_kernel per launch, from the committed ncu --set full summary
     (profiles/, captured on the c2 workload); None for other workloads or when the summary is absent."""
     if workload != "c2":
         return None, None

@@ -151,7 +151,7 @@ struct DevWin {
     // partial sums
     double *energy_part;           // [n_chunks]
     int acc_target;                // value acc_done_count reaches when the accumulation this stitch depends on has finished (0: no device-side wait)
-    float *acc_bin;                // [N*N (bin = t*N+h)][ACC_SLICES][ACC_N] 13x13 blocks of the committed linearization (accumulate role of schur_acc_kernel)
+    float *acc_bin;                // [N*N (bin = t*N+h)][ACC_SLICES][ACC_N] 13x13 blocks of the committed linearization (accumulate_kernel)
     float *sc_part;                // [n_sc_chunks][sc_stride]
     int sc_stride;                 // (8N)^2 + 32N + 8N + 16 + 4 (padded to 4)
     const int *sc_chunk_host, *sc_chunk_begin, *sc_chunk_count;

@@ -2,16 +2,18 @@
 //
 // Reference behaviour restated on the device (file:line under /root/reference/src/cml):
 //   linearize_tile_kernel   optimization/dso/DSOBundleAdjustment.cpp:62-316 (linearize) + :2051-2093 (applyRes, as a double-buffered
-//                           candidate) + :1568-1599 (fixLinearization bookkeeping) + :1648-1779 (addToHessianTop ACTIVE / MARGINALIZED)
-//                           + MatrixAccumulators.h:776-937 (AccumulatorApprox); image/Array2D.h:265-286 (bilinear taps)
+//                           candidate) + :1568-1599 (fixLinearization bookkeeping); image/Array2D.h:265-286 (bilinear taps).  The sums of
+//                           addToHessianTop (:1648-1779, MatrixAccumulators.h:776-937) are taken from its Jacobian records by accumulate_kernel.
 //
 // Design (B200): the 8-pixel pattern of a residual reads a <= 6x6 texel footprint of the TARGET image.  Residuals are sorted on the
-// device, once per run(), by (target frame, 64x32 tile that holds the centre projection, host frame); a persistent CTA per SM then
-// walks a contiguous range of that order.  One producer warp streams the 72x40-texel boxes (tile + halo) of the tiles its CTA
-// needs through a 4-stage shared-memory ring with TMA (cp.async.bulk.tensor.2d + mbarrier complete_tx); eight consumer warps
-// (one residual per lane, 32 consecutive residuals per pass) take every bilinear tap from the staged tile.  A lane whose footprint
-// left its box (pose drift since the binning, strong warps) or whose tile is not in the ring reads its taps from global memory through
-// the same generic pointer, so correctness never depends on the binning.  HBM sees each image once per pass, in large boxes.
+// device, once per run(), by (target frame, 64x32 tile that holds the centre projection); inside a tile they are interleaved by the
+// shared-memory bank group of their centre texel.  A persistent CTA per SM (12 warps, no producer warp) walks a contiguous range of that
+// order.  The 70x38-texel boxes (tile + halo 3) of the tiles the CTA needs are streamed through a 4-stage shared-memory ring with TMA
+// (cp.async.bulk.tensor.2d + mbarrier complete_tx): two boxes up front, the next ones issued by the warp that first sees a box landed /
+// whose arrival frees a stage.  One residual per lane, 32 consecutive residuals per pass; every bilinear tap comes from the staged tile.  A
+// lane whose footprint left its box (pose drift since the binning, strong warps) or whose tile is not in the ring reads its taps from
+// global memory through the same generic pointer, so correctness never depends on the binning; sparse windows (few residuals per tile)
+// run without staging altogether (DevWin::tma_on = 0).
 //
 // Arithmetic: centre projection in fp64 (the reference's scalar_t); the 7 other pattern pixels as fp32 offsets from it,
 //   q_i - q_c = f (d_xy - (P_xy/P_z) d_z) / (P_z + d_z),  d = sx A + sy B,  A = R[:,0]/fx, B = R[:,1]/fy,
@@ -21,7 +23,7 @@
 //
 // Output: the Jacobian record of every good residual (x[10] y[10] JIdx2[3] ...; the reference's efsJ, DSOResidual.h:22-69) goes to
 // rj[candidate] in the HOST's bin-major residual order; addToHessianTop (the 13x13 blocks) is evaluated from these records by
-// accumulate_role of schur_acc_kernel (kernels.cuh), bin by bin, in a fixed order: results are bitwise reproducible.
+// accumulate_kernel (kernels.cuh), bin by bin, in a fixed order: results are bitwise reproducible.
 #pragma once
 #include <cuda.h>
 

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const DevWin w, c
                 for (int k = 0; k < CS; k++) s += (double) cluster.map_shared_rank(part, k)[off];
                 Dj[e] = s;                 // Dj, Ej, EBj are contiguous
             }
-            if (tid < ACC_N) {   // 13x13 block of bin (i -> j): the slices of the accumulate role of schur_acc_kernel
+            if (tid < ACC_N) {   // 13x13 block of bin (i -> j): the slices of accumulate_kernel
                 const float *src = w.acc_bin + (size_t) (j * N + i) * ACC_SLICES * ACC_N + tid;
                 double a = 0.0;
                 for (int sl = 0; sl < ACC_SLICES; sl++) a += (double) __ldcg(src + sl * ACC_N);
