@@ -165,3 +165,20 @@ def test_forward_error_floor_of_the_reference_system(name):
     tri, ulp, cond = x_noise_floor(g, "sol0_", win["frame_evalpt"].shape[0])
     assert cond > 1e10
     assert 2e-4 < tri < 5e-3 and 2e-4 < ulp < 1e-2
+
+
+def test_oracle_against_reference_summary_c1():
+    """The numpy restatement at BASELINE.json's configs[0] (the reference's own CPU-runnable case: 2 KF, 200 points, 1 GN iteration at 640x480) against
+    the compact summary of the UNMODIFIED reference's run() on the same seeded window (tests/golden/fullsize_summary.cmlw)."""
+    import os
+    from libcml_b200 import cmlw, synth
+    from parity_util import GOLDEN, pose_errors
+    S = cmlw.load(os.path.join(GOLDEN, "fullsize_summary.cmlw"))
+    ow = O.Window(synth.make_config("c1"))
+    assert O.run(ow) == bool(S["c1_ok"][0])
+    w2c = np.stack([np.concatenate([R.ravel(), t]) for R, t in ow.pre_w2c])
+    er, et, ets = pose_errors(w2c, S["c1_w2c"])
+    assert er < 1e-6 and et < 1e-4 and ets < 1e-5
+    alive = S["c1_alive16"].astype(bool)
+    assert rel(ow.idepth[::16][alive], S["c1_idepth16"][alive]) < 1e-4
+    assert int(ow.res_alive.sum()) == int(S["c1_n_alive_res"][0])
