@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    return os.path.join(_HERE, "libcmlba.so")
+    # CMLBA_LIB: development aid (tuning builds of the same sources with other compile-time constants)
+    return os.environ.get("CMLBA_LIB") or os.path.join(_HERE, "libcmlba.so")
 
 
 class CmlbaError(RuntimeError):

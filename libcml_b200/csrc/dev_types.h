@@ -18,11 +18,17 @@ constexpr int LT_BOX_H = LT_TILE_H + 2 * LT_HALO;     // 38 rows
 constexpr int LT_TILE_BYTES = LT_BOX_W * LT_BOX_H * 16;   // 42 560 B of float4 texels per staged tile
 constexpr int LT_STAGE_STRIDE = (LT_TILE_BYTES + 127) & ~127;   // TMA destinations are 128-byte aligned
 // ring depth and consumer warps per CTA (+1 producer warp) are template parameters of the kernel (Engine::launch_linearize picks the variant)
-constexpr int ACC_SLICES = 16;                        // CTAs per (host,target) bin that evaluate addToHessianTop from the Jacobian records
+#ifndef CMLBA_ACC_SLICES
+#define CMLBA_ACC_SLICES 16
+#endif
+constexpr int ACC_SLICES = CMLBA_ACC_SLICES;                        // CTAs per (host,target) bin that evaluate addToHessianTop from the Jacobian records
 constexpr int P2P_POST_CAND_MAX = 65536;      // candidates per rank record that fit the peer-memory exchange (else NCCL all-gather)
 constexpr size_t P2P_POST_DOUBLES = 8 + P2P_POST_CAND_MAX / 2;
 constexpr size_t P2P_SLOT_DOUBLES = 2 * (size_t) (8 * MAXF + 4) * (8 * MAXF + 4) + 2 * (8 * MAXF + 4);   // sys at the largest window
-constexpr int SC_CHUNK = 64;      // points per Schur CTA (all hosted in one frame)
+#ifndef CMLBA_SC_CHUNK
+#define CMLBA_SC_CHUNK 64
+#endif
+constexpr int SC_CHUNK = CMLBA_SC_CHUNK;      // points per Schur CTA (all hosted in one frame)
 
 enum : uint8_t { RES_IN = 0, RES_OOB = 1, RES_OUTLIER = 2 };
 
