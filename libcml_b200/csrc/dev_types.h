@@ -80,6 +80,8 @@ struct Ctrl {
     int asm_done_count;         // last-block counter of assemble_kernel (peer signalling)
     int acc_done_count;         // jobs of accumulate_kernel finished since prepare(): stitch_pair_kernel waits on it (the kernels run on two streams, no stream-level join)
     int pad1;                   // set when stitch_pair_kernel's bounded wait for acc_done_count expired (reported as CMLBA_ERR_STATE)
+    int final_done;             // the closing linearizeAll(true) of run() has been executed (guard 2 of the pre-launched closing sequence)
+    int pad2;
 };
 
 struct DevWin {

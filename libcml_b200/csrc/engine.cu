@@ -1120,7 +1120,7 @@ public:
         dw.pair_delta = prep.dev<float>(o_pdel); dw.marg_mode = 0;
         // resetOOB on every active residual (BA:766-779, DSOResidual.h:81-86), empty Schur tables
         reset_window_kernel<<<148 * 4, 256, 0, stream>>>(dw); launches++;
-        pairs_kernel<<<(N * N + 63) / 64, 64, 0, stream>>>(dw); launches++;
+        pairs_kernel<<<(N * N + 63) / 64, 64, 0, stream>>>(dw, 0); launches++;
         if (dw.R > 0) {   // tile binning at the poses this run() starts from: residuals sorted by (target, tile, host)
             CK(cudaMemsetAsync(d_bin_hist.p, 0, (size_t) N * dw.n_tiles * N * sizeof(int), stream));
             bin_count_kernel<<<(dw.R + 255) / 256, 256, 0, stream>>>(dw); launches++;
@@ -1278,8 +1278,19 @@ public:
         if (!cfg.force_accept) { point_prior_energy_kernel<<<1, 256, 0, stream>>>(dw); launches++; }
         launch_linearize(0, 0); launch_post(0, 0);
         // GN iterations are enqueued two at a time (run() cannot stop before it = 1, BA:879); between batches the host peeks at
-        // Ctrl.done instead of enqueueing up to 7 no-op launches per iteration that the window no longer needs.
+        // Ctrl.done instead of enqueueing up to 7 no-op launches per iteration that the window no longer needs.  On one GPU the closing
+        // sequence (new FEJ point of the newest frame, pair constants, linearizeAll(true), BA:885-905) is launched AHEAD of every peek with
+        // guard 2 (it runs only if the loop is done): when the host then sees Ctrl.done the device has already finished the run, instead of
+        // idling through the host round trip and four launches (~40 us of a 0.37 ms run at C2).  With several ranks the closing sequence
+        // contains a peer exchange whose epochs must not be skipped, so it is enqueued after the loop as before.
+        auto launch_closing = [&](int guard) {
+            set_evalpt_newest_kernel<<<1, 32, 0, stream>>>(dw, guard); launches++;
+            pairs_kernel<<<(dw.N * dw.N + 63) / 64, 64, 0, stream>>>(dw, guard); launches++;
+            launch_linearize(1, guard); launch_post(2, guard);
+            cudaEventRecord(ev1, stream);             // end of the device work of this run (the last record wins)
+        };
         CK(peek_h.reserve(1));
+        bool closed = false;
         for (int it = 0; it < iterations;) {
             const int batch_end = std::min(iterations, it + 2);
             for (; it < batch_end; it++) {
@@ -1288,15 +1299,13 @@ public:
                 if (!cfg.force_accept) launch_pdl(128, restore_state_kernel, dim3(std::max(dw.n_pt_blocks, 1)), dim3(256), 0, dw, it + 1);   // no-op unless the step was rejected
             }
             if (it < iterations) {
+                if (world == 1) launch_closing(2);
                 CK(cudaMemcpyAsync(peek_h.p, reinterpret_cast<const char *>(d_ctrl.p) + offsetof(Ctrl, done), sizeof(int), cudaMemcpyDeviceToHost, stream));
                 CK(cudaStreamSynchronize(stream));
-                if (*peek_h.p) break;
+                if (*peek_h.p) { closed = world == 1; break; }
             }
         }
-        set_evalpt_newest_kernel<<<1, 32, 0, stream>>>(dw); launches++;
-        pairs_kernel<<<(dw.N * dw.N + 63) / 64, 64, 0, stream>>>(dw); launches++;
-        launch_linearize(1, 0); launch_post(2, 0);
-        CK(cudaEventRecord(ev1, stream));
+        if (!closed) launch_closing(0);
         CK(cudaGetLastError());
         if (launch_rc) return launch_rc;
         lap("run.launch");
@@ -1775,8 +1784,8 @@ int cmlba_linearize(cmlba_handle *h, int fix, double *energy) {
     if (!e.prepared) { e.set_error("cmlba_prepare first"); return CMLBA_ERR_STATE; }
     cudaSetDevice(e.device);
     if (fix) {
-        cmlba::set_evalpt_newest_kernel<<<1, 32, 0, e.stream>>>(e.dw);
-        cmlba::pairs_kernel<<<(e.dw.N * e.dw.N + 63) / 64, 64, 0, e.stream>>>(e.dw);
+        cmlba::set_evalpt_newest_kernel<<<1, 32, 0, e.stream>>>(e.dw, 0);
+        cmlba::pairs_kernel<<<(e.dw.N * e.dw.N + 63) / 64, 64, 0, e.stream>>>(e.dw, 0);
         e.launch_linearize(1, 0); e.launch_post(2, 0);
     } else {
         e.launch_linearize(0, 0); e.launch_post(3, 0);

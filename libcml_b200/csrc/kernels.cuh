@@ -59,6 +59,13 @@ struct KTrace {
 // slot 0 (the sampling kernel, which carries no stamps of its own: register budget) gets the time of this reset = the start of the timed region
 __global__ void ktrace_reset_kernel(unsigned long long *kt) { const int i = threadIdx.x; if (i < 3) kt[i] = KTrace::now(); for (int j = 3 + i; j < 3 * 128; j += 96) kt[j] = (j % 3 == 2) ? 0ull : ~0ull; }
 
+// Guard of a pre-launched kernel (`respect_done` argument): 0 = always run; 1 = skip once the Gauss-Newton loop is done (Ctrl.done); 2 = the
+// closing sequence of run() launched AHEAD of the host's look at Ctrl.done: run only when the loop is done and the closing linearization
+// has not been executed yet.
+__device__ __forceinline__ bool launch_skipped(const int guard, const int done, const int final_done) {
+    return guard == 1 ? done != 0 : guard == 2 ? !(done != 0 && final_done == 0) : false;
+}
+
 // Frame state -> PRE_worldToCam (DSOFrame::setState, DSOFrame.h:110-124)
 __device__ inline void frame_set_state(FrameDev &f, const double *state, const DevWin &w) {
     const double sc[10] = {w.scaleT, w.scaleT, w.scaleT, w.scaleR, w.scaleR, w.scaleR, w.scaleA, w.scaleB, w.scaleA, w.scaleB};
@@ -89,13 +96,15 @@ __device__ inline void pair_precompute(const DevWin &w, int h, int t) {
     for (int k = 0; k < 3; k++) { pp.Af[k] = (float) (T.R[3 * k] * w.fxi); pp.Bf[k] = (float) (T.R[3 * k + 1] * w.fyi); }
 }
 
-__global__ void pairs_kernel(const DevWin w) {
+__global__ void pairs_kernel(const DevWin w, const int guard) {
+    if (guard && launch_skipped(guard, w.ctrl->done, w.ctrl->final_done)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < w.N * w.N) pair_precompute(w, i / w.N, i % w.N);
 }
 
 // run() epilogue BA:885-889: newest frame gets a new FEJ evaluation point, then pairs are refreshed
-__global__ void set_evalpt_newest_kernel(const DevWin w) {
+__global__ void set_evalpt_newest_kernel(const DevWin w, const int guard) {
+    if (guard && launch_skipped(guard, w.ctrl->done, w.ctrl->final_done)) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         FrameDev &f = w.frames[w.N - 1];
         for (int k = 0; k < 9; k++) f.evalR[k] = f.preR[k];
@@ -994,7 +1003,7 @@ __global__ void __launch_bounds__(256) point_step_kernel(const DevWin w, const i
 __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, const int mode, const int respect_done) {
     KTRACE_ENTER(7);
     Ctrl *ctrl = w.ctrl;
-    if (respect_done && ctrl->done) return;
+    if (respect_done && launch_skipped(respect_done, ctrl->done, ctrl->final_done)) return;
     const int tid = threadIdx.x;
     __shared__ double s_red[32];
     __shared__ unsigned int hist[256];
@@ -1149,7 +1158,7 @@ __global__ void __launch_bounds__(1024) post_linearize_kernel(const DevWin w, co
             }
             ctrl->iteration = it + 1;
             if (ctrl->canbreak && it >= 1) ctrl->done = 1;             // BA:879
-        } else if (mode == 2) { ctrl->cur ^= 1; ctrl->energy_last = energy; }
+        } else if (mode == 2) { ctrl->cur ^= 1; ctrl->energy_last = energy; ctrl->final_done = 1; }
         if (!keep_th) w.frames[w.N - 1].energy_th = th_new;            // a rejected linearization leaves frameEnergyTH as the re-linearization would
     }
 }

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
     // LT_TILE_TABLE tiles; written by bin_finish_kernel) and the per-residual scalars of every warp's first pass (both copies of the
     // double-buffered state / energy: which one is current is part of the same round trip).
     const int4 *infop = reinterpret_cast<const int4 *>(w.cta_info + (size_t) blockIdx.x * LT_INFO_INTS);
-    const int done_ld = ctrl->done, cur = ctrl->cur;
+    const int done_ld = ctrl->done, cur = ctrl->cur, fin_ld = respect_done == 2 ? ctrl->final_done : 0;
     const int4 info = __ldg(infop);
     int tab_jd = 0, tab_users = 0;
     if ((int) threadIdx.x < LT_TILE_TABLE) { tab_jd = __ldg(w.cta_info + (size_t) blockIdx.x * LT_INFO_INTS + 16 + threadIdx.x); tab_users = __ldg(w.cta_info + (size_t) blockIdx.x * LT_INFO_INTS + 16 + LT_TILE_TABLE + threadIdx.x); }
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(LT_CWARPS * 32, 1) linearize_tile_kernel(const
         st = rr < w.R ? (cur ? st1 : st0) : (uint8_t) RES_OOB; e_old = cur ? e1 : e0;
     }
     const int nxt = cur ^ 1;
-    if (respect_done && done_ld) return;
+    if (respect_done && launch_skipped(respect_done, done_ld, fin_ld)) return;
     // the per-residual scalars of every later pass are requested at the bottom of the pass before it
     auto load_headers = [&](const int cc) {
         const int rr = cc * 32 + lane, rl = rr < w.R ? rr : w.R - 1;

@@ -12,7 +12,7 @@ FRAME_DEV = np.dtype([("evalR", "<f8", 9), ("evalt", "<f8", 3), ("preR", "<f8", 
 CTRL = np.dtype([("cur", "<i4"), ("done", "<i4"), ("canbreak", "<i4"), ("failed", "<i4"), ("iteration", "<i4"), ("accepted", "<i4"), ("num_dropped", "<i4"), ("pad0", "<i4"),
                  ("lambda", "<f8"), ("energy_last", "<f8"), ("energy_new", "<f8"), ("energy_first", "<f8"), ("sumA", "<f4"), ("sumB", "<f4"), ("sumT", "<f4"), ("sumR", "<f4"),
                  ("sumNID", "<f8"), ("numID", "<i4"), ("sc_done_count", "<i4"), ("stats", "<f8", 16),
-                 ("energyL_last", "<f8"), ("energyL_new", "<f8"), ("prior_energy_pts", "<f8"), ("rejected_at", "<i4"), ("rejected", "<i4"), ("pt_bad", "<i4"), ("asm_done_count", "<i4"), ("acc_done_count", "<i4"), ("pad1", "<i4")])
+                 ("energyL_last", "<f8"), ("energyL_new", "<f8"), ("prior_energy_pts", "<f8"), ("rejected_at", "<i4"), ("rejected", "<i4"), ("pt_bad", "<i4"), ("asm_done_count", "<i4"), ("acc_done_count", "<i4"), ("pad1", "<i4"), ("final_done", "<i4"), ("pad2", "<i4")])
 
 
 def load_golden(name):
