@@ -241,7 +241,7 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1: weak = a window-sized shard per GPU (default), strong = ONE window split over the GPUs (BASELINE.json configs[3] with --workload c4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=9)
     ap.add_argument("--nccl-only", action="store_true", help="N>1: all-reduce the reduced system with NCCL instead of the peer-memory exchange")
     ap.add_argument("--component", default="ba", choices=["ba", "tracker", "tracer", "prepare", "select"],
                     help="ba = the contract's headline line; the others = the measurement of a widened SURVEY 8f row (tools/<name>_bench.py), one JSON line each")
@@ -371,7 +371,7 @@ def main():
         run_gpu_ms = ba.last_result.gpu_ms; run_launches = ba.last_result.kernel_launches
         if not ok:
             raise SystemExit("run() failed in the end-to-end loop")
-    e2e_ms = torch.tensor([float(np.mean(e2e_t))], dtype=torch.float64, device="cuda")
+    e2e_ms = torch.tensor([float(np.median(e2e_t))], dtype=torch.float64, device="cuda")       # median of the cycles: the host side of the cycle is sensitive to scheduling noise
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_ms.cpu()[0])
@@ -500,7 +500,7 @@ def main():
            "roofline": {"bound": "hbm", "kernel": "linearize_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_unit": b_alg(N), "units_per_launch": R},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
-                   "what": f"reset + set_calib + {N} x add_frame_gray (pinned host gray images, asynchronous upload, derivative images built on the device) + add_points + run(up to {iters} GN iterations, {e2e_iters} executed) + get_frames/get_points"},
+                   "cycles": len(e2e_t), "ms_per_step_min_max": [float(np.min(e2e_t) * 1e3), float(np.max(e2e_t) * 1e3)], "what": f"median over the cycles of: reset + set_calib + {N} x add_frame_gray (pinned host gray images, asynchronous upload, derivative images built on the device) + add_points + run(up to {iters} GN iterations, {e2e_iters} executed) + get_frames/get_points"},
            "e2e_sliding_window": cycle, "run_noisy": noisy,
            "gpu_launches": int(br.launches_per_pass * args.steps),
            "clocks": clocks}
