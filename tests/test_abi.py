@@ -167,3 +167,18 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "ba_oracle" not in txt and "oracle/" not in txt.replace("oracle/cmlw_io.h", "").replace("oracle/ref_driver.cpp", ""), f
+
+
+def test_statistic_names_are_the_reference_ones(lib):
+    """cmlba_statistic_name(i) = the 19 createStatistic("...") names of DSOBundleAdjustment.h:215-233, in declaration order (the committed list below is
+    what the reference header holds; when /root/reference is mounted the header itself is parsed as well)."""
+    import ctypes as C
+    expected = ["P Energy ( All residuals )", "R Energy", "L Energy ( Linearized )", "M Energy ( Marginalized )", "Total Energy", "X Norm", " Hessian P Norm",
+                " Hessian L Norm", " Hessian M Norm", " Hessian SC Norm", "P B Norm", "L B Norm", "M B Norm", "SC B Norm", "OOB", "In", "InIn", "Nores", "Num Linearized"]
+    lib.cmlba_statistic_name.restype = C.c_char_p
+    lib.cmlba_statistic_name.argtypes = [C.c_int]
+    names = [lib.cmlba_statistic_name(i).decode() for i in range(19)]
+    assert names == expected and lib.cmlba_statistic_name(19) is None
+    hdr = "/root/reference/src/cml/optimization/dso/DSOBundleAdjustment.h"
+    if os.path.exists(hdr):
+        assert re.findall(r'createStatistic\("([^"]*)"\)', open(hdr).read()) == expected
