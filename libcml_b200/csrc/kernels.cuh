@@ -227,6 +227,9 @@ __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int re
     float *sZ = sT + SC_CHUNK * N * T_STRIDE;        // [SC_CHUNK][ZS]         augmented, scaled
     const int c = blockIdx.x, tid = threadIdx.x;
     const int begin = begin_ld, cnt = cnt_ld;
+    // the per-point scalars of the second phase are requested together with the rows (same round trip)
+    float priorF_ld = 0.f, idz_ld = 0.f; double id_ld = 0.0;
+    if (tid < cnt) { priorF_ld = w.pt_priorF[begin + tid]; id_ld = w.pt_idepth[begin + tid]; idz_ld = w.pt_idepth_zero[begin + tid]; }
     {   // stage the rows of the chunk's points (contiguous in T)
         const float4 *src = reinterpret_cast<const float4 *>(w.T[cur] + (size_t) begin * N * T_STRIDE);
         float4 *dst = reinterpret_cast<float4 *>(sT);
@@ -245,14 +248,14 @@ __global__ void __launch_bounds__(256) schur_kernel(const DevWin w, const int re
                 const float4 b = *reinterpret_cast<const float4 *>(sT + (tid * N + t) * T_STRIDE + 12);   // Hcd2 Hcd3 good pad
                 bd += a.x; Hdd += a.y; h0 += a.z; h1 += a.w; h2 += b.x; h3 += b.y; ng += (b.z != 0.f);
             }
-            const float priorF = w.pt_priorF[p];
+            const float priorF = priorF_ld;
             float idh = 0.f, bdSum = 0.f, hd = 0.f;
             if (ng > 0) {
                 float Hs = Hdd + priorF;
                 if (Hs < 1e-10f) Hs = 1e-10f;
                 idh = Hs;
                 hd = (float) (1.0 / (double) Hs);
-                const float deltaF = (float) (w.pt_idepth[p] - (double) w.pt_idepth_zero[p]);
+                const float deltaF = (float) (id_ld - (double) idz_ld);
                 bdSum = w.marg_mode ? bd : bd + priorF * deltaF;       // addToHessianSC(shiftPriorToZero) (BA:1902)
                 sh = sqrtf(hd);
             } else {
@@ -378,6 +381,12 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
     double *Y = A + ACC_N;         // [8][8]   sum_k D_jk AH_ik^T
     double *M = Y + 64;            // [8][8]   AH_ij A8
     double *Yp = M + 64;           // [N][8][8] D_jk AH_ik^T per k (summed into Y in fixed order)
+    // the adjoints of host i are requested before the chunk sums below start to wait on their own loads (one round trip instead of two)
+    constexpr int G_IT = (MAXF * 64 + ST_THREADS - 1) / ST_THREADS;
+    double g_ld[G_IT];
+#pragma unroll
+    for (int it = 0; it < G_IT; it++) { const int e = tid + it * ST_THREADS; g_ld[it] = e < N * 64 ? w.AH[(size_t) (i * N) * 64 + e] : 0.0; }
+    const double atd_ld = tid < NB ? w.AT[((size_t) (i * N + (tid >> 3))) * 64 + (tid & 7) * 9] : 0.0;
     for (int e = tid; e < 8 * NB + 40; e += ST_THREADS) {
         int off;
         if (e < 8 * NB) off = j * 8 * NB + e;
@@ -411,8 +420,9 @@ __global__ void __launch_bounds__(ST_THREADS) stitch_pair_kernel(const DevWin w,
         for (int sl = 0; sl < ACC_SLICES; sl++) a += (double) part[sl];
         A[tid] = a;
     }
-    for (int e = tid; e < N * 64; e += ST_THREADS) G[e] = w.AH[(size_t) (i * N) * 64 + e];
-    for (int e = tid; e < NB; e += ST_THREADS) atd[e] = w.AT[((size_t) (i * N + (e >> 3))) * 64 + (e & 7) * 9];
+#pragma unroll
+    for (int it = 0; it < G_IT; it++) { const int e = tid + it * ST_THREADS; if (e < N * 64) G[e] = g_ld[it]; }
+    if (tid < NB) atd[tid] = atd_ld;
     __syncthreads();
     const double *AHj = G + j * 64, *atj = atd + j * 8;
     for (int e = tid; e < N * 64 + 64; e += ST_THREADS) {       // short dependent chains: 8 products per thread
