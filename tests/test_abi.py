@@ -182,3 +182,16 @@ def test_statistic_names_are_the_reference_ones(lib):
     hdr = "/root/reference/src/cml/optimization/dso/DSOBundleAdjustment.h"
     if os.path.exists(hdr):
         assert re.findall(r'createStatistic\("([^"]*)"\)', open(hdr).read()) == expected
+
+
+def test_bench_arms_share_one_config_object():
+    """bench.py: the `config` of our arm and of `--impl reference` comes from the same function (the driver compares them), per workload and scaling."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    for wl in ("c2", "c4"):
+        for sc in ("weak", "strong"):
+            c = b.config_dict(wl, sc)
+            assert c == b.config_dict(wl, sc) and "workload" in c and not any(k in c for k in ("model", "seq_len", "global_batch"))
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": config_dict(args.workload, args.scaling)') == 2        # once per arm
